@@ -1,0 +1,261 @@
+// api.cu -- C-ABI glue: error plumbing, convolution descriptors and engine/algo dispatch.
+//
+// The dispatch mirrors GetConvolutionLayer (reference src/caffe/layer_factory.cpp:53-88):
+//   engine CAFFE          -> explicit per-image im2col + GEMM + bias, the literal structure of
+//                            ConvolutionLayer::Forward_gpu/Backward_gpu (conv_layer.cu:7-57).
+//   engine DEFAULT/CUDNN  -> whole-batch implicit GEMM (the cuDNN role): tcgen05 kernels
+//                            (conv_tc.cu) when the shape qualifies, else the SIMT direct kernels.
+#include <stdarg.h>
+#include <string.h>
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+std::string& last_error() {
+  thread_local std::string e;
+  return e;
+}
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+static std::atomic<int> g_default_math{B2C_MATH_FP32};
+static std::atomic<int> g_default_algo{B2C_ALGO_AUTO};
+
+// kernels in the other translation units
+int launch_im2col2d(const float*, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
+int launch_col2im2d(const float*, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
+int launch_sgemm_simt(bool, bool, int, int, int, float, const float*, int, const float*, int, float, float*, int,
+                      cudaStream_t);
+int launch_conv_fwd_simt(const ConvShape&, const float*, const float*, const float*, float*, cudaStream_t);
+int launch_conv_dgrad_simt(const ConvShape&, const float*, const float*, float*, cudaStream_t);
+int launch_conv_wgrad_simt(const ConvShape&, const float*, const float*, float*, cudaStream_t);
+int launch_bias_add(int, int, int, const float*, float*, cudaStream_t);
+int launch_bias_grad(int, int, int, const float*, float*, cudaStream_t);
+// tcgen05 family (conv_tc.cu / gemm_tc.cu)
+bool tc_conv_supported(const ConvShape&, int op);
+size_t tc_conv_workspace(const ConvShape&, int op, int math);
+int launch_conv_tc(const ConvShape&, int op, int math, const float* a, const float* b, const float* bias, float* out,
+                   void* ws, size_t ws_bytes, cudaStream_t);
+bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K);
+int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta,
+                    float* C, int math, cudaStream_t);
+
+static bool have_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int n = 0;
+    ok = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+  }
+  return ok == 1;
+}
+
+static int resolve_algo(const b2c_conv_desc* d, int op) {
+  if (d->engine == B2C_ENGINE_CAFFE) return B2C_ALGO_SIMT;  // reported family of the explicit path's GEMM
+  if (d->algo == B2C_ALGO_SIMT) return B2C_ALGO_SIMT;
+  return tc_conv_supported(d->s, op) ? B2C_ALGO_TCGEN05 : B2C_ALGO_SIMT;
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" const char* b2c_last_error(void) { return last_error().c_str(); }
+extern "C" const char* b2c_version(void) { return "b2c 0.1 (sm_100a)"; }
+extern "C" uint64_t b2c_launch_count(void) { return g_launches.load(); }
+extern "C" int b2c_set_default_math(int m) {
+  if (m != B2C_MATH_FP32 && m != B2C_MATH_TF32) return fail(B2C_ERR_INVALID, "bad math mode %d", m);
+  g_default_math = m;
+  return B2C_OK;
+}
+extern "C" int b2c_set_default_algo(int a) {
+  if (a < B2C_ALGO_AUTO || a > B2C_ALGO_TCGEN05) return fail(B2C_ERR_INVALID, "bad algo %d", a);
+  g_default_algo = a;
+  return B2C_OK;
+}
+
+extern "C" int b2c_conv_desc_create(const b2c_conv_params* p, int engine, b2c_conv_desc** out) {
+  if (!p || !out) return fail(B2C_ERR_INVALID, "b2c_conv_desc_create: null");
+  if (engine < B2C_ENGINE_DEFAULT || engine > B2C_ENGINE_CUDNN) return fail(B2C_ERR_INVALID, "bad engine %d", engine);
+  // the CHECKs of BaseConvolutionLayer::LayerSetUp (base_conv_layer.cpp:44-118)
+  if (p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0 || p->O <= 0)
+    return fail(B2C_ERR_INVALID, "conv: non-positive blob dimension");
+  if (p->kh <= 0 || p->kw <= 0) return fail(B2C_ERR_INVALID, "conv: Filter dimensions must be nonzero");
+  if (p->sh <= 0 || p->sw <= 0) return fail(B2C_ERR_INVALID, "conv: Stride dimensions must be nonzero");
+  if (p->dh <= 0 || p->dw <= 0) return fail(B2C_ERR_INVALID, "conv: dilation must be positive");
+  if (p->ph < 0 || p->pw < 0) return fail(B2C_ERR_INVALID, "conv: negative pad");
+  if (p->G <= 0 || p->C % p->G) return fail(B2C_ERR_INVALID, "conv: channels %d not divisible by group %d", p->C, p->G);
+  if (p->O % p->G) return fail(B2C_ERR_INVALID, "conv: Number of output should be multiples of group");
+  b2c_conv_desc* d = new b2c_conv_desc;
+  ConvShape& s = d->s;
+  s.N = p->N; s.C = p->C; s.H = p->H; s.W = p->W; s.O = p->O; s.G = p->G;
+  s.kh = p->kh; s.kw = p->kw; s.sh = p->sh; s.sw = p->sw; s.ph = p->ph; s.pw = p->pw; s.dh = p->dh; s.dw = p->dw;
+  s.has_bias = p->has_bias;
+  s.Ho = (s.H + 2 * s.ph - (s.dh * (s.kh - 1) + 1)) / s.sh + 1;   // conv_layer.cpp:14-21
+  s.Wo = (s.W + 2 * s.pw - (s.dw * (s.kw - 1) + 1)) / s.sw + 1;
+  if (s.Ho <= 0 || s.Wo <= 0) { delete d; return fail(B2C_ERR_INVALID, "conv: kernel larger than padded input"); }
+  s.Cg = s.C / s.G; s.Og = s.O / s.G; s.Kd = s.Cg * s.kh * s.kw;
+  s.is_1x1 = s.kh == 1 && s.kw == 1 && s.sh == 1 && s.sw == 1 && s.ph == 0 && s.pw == 0;
+  d->engine = engine;
+  d->math = g_default_math;
+  d->algo = g_default_algo;
+  *out = d;
+  return B2C_OK;
+}
+extern "C" int b2c_conv_desc_destroy(b2c_conv_desc* d) { delete d; return B2C_OK; }
+extern "C" int b2c_conv_desc_set_math(b2c_conv_desc* d, int m) {
+  if (!d || (m != B2C_MATH_FP32 && m != B2C_MATH_TF32)) return fail(B2C_ERR_INVALID, "set_math: bad argument");
+  d->math = m;
+  return B2C_OK;
+}
+extern "C" int b2c_conv_desc_set_algo(b2c_conv_desc* d, int a) {
+  if (!d || a < B2C_ALGO_AUTO || a > B2C_ALGO_TCGEN05) return fail(B2C_ERR_INVALID, "set_algo: bad argument");
+  d->algo = a;
+  return B2C_OK;
+}
+extern "C" int b2c_conv_out_shape(const b2c_conv_desc* d, int* Ho, int* Wo) {
+  if (!d) return fail(B2C_ERR_INVALID, "null desc");
+  if (Ho) *Ho = d->s.Ho;
+  if (Wo) *Wo = d->s.Wo;
+  return B2C_OK;
+}
+extern "C" int b2c_conv_algo_used(const b2c_conv_desc* d, int op) {
+  if (!d) return B2C_ERR_INVALID;
+  return resolve_algo(d, op);
+}
+
+extern "C" size_t b2c_conv_workspace_bytes(const b2c_conv_desc* d, int op) {
+  if (!d) return 0;
+  const ConvShape& s = d->s;
+  if (d->engine == B2C_ENGINE_CAFFE)   // one image's col buffer [Kd*G, Ho, Wo] (base_conv_layer.cpp:225-233)
+    return s.is_1x1 ? 0 : sizeof(float) * (size_t)s.Kd * s.G * s.Ho * s.Wo;
+  if (resolve_algo(d, op) == B2C_ALGO_TCGEN05) return tc_conv_workspace(s, op, d->math);
+  return 0;
+}
+
+#define REQUIRE_DEVICE() \
+  if (!have_device()) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback")
+
+extern "C" int b2c_conv_forward(const b2c_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                                void* ws, size_t ws_bytes, void* stream) {
+  if (!d || !x || !w || !y) return fail(B2C_ERR_INVALID, "b2c_conv_forward: null pointer");
+  REQUIRE_DEVICE();
+  const ConvShape& s = d->s;
+  if (s.has_bias && !bias) return fail(B2C_ERR_INVALID, "b2c_conv_forward: bias_term set but bias is null");
+  if (!s.has_bias) bias = nullptr;
+  cudaStream_t st = as_stream(stream);
+  if (ws_bytes < b2c_conv_workspace_bytes(d, B2C_OP_FORWARD) || (b2c_conv_workspace_bytes(d, B2C_OP_FORWARD) && !ws))
+    return fail(B2C_ERR_WORKSPACE, "forward workspace too small");
+  if (d->engine == B2C_ENGINE_CAFFE) {
+    const int P = s.Ho * s.Wo;
+    const size_t bdim = (size_t)s.C * s.H * s.W, tdim = (size_t)s.O * P;
+    float* col = static_cast<float*>(ws);
+    for (int n = 0; n < s.N; ++n) {
+      const float* cb = x + n * bdim;
+      if (!s.is_1x1) {
+        if (int rc = launch_im2col2d(x + n * bdim, s.C, s.H, s.W, s.kh, s.kw, s.ph, s.pw, s.sh, s.sw, s.dh, s.dw, col, st)) return rc;
+        cb = col;
+      }
+      for (int g = 0; g < s.G; ++g)
+        if (int rc = b2c_sgemm(0, 0, s.Og, P, s.Kd, 1.0f, w + (size_t)g * s.Og * s.Kd, cb + (size_t)g * s.Kd * P, 0.0f,
+                               y + n * tdim + (size_t)g * s.Og * P, stream)) return rc;
+    }
+    if (bias) return launch_bias_add(s.N, s.O, P, bias, y, st);
+    return B2C_OK;
+  }
+  if (resolve_algo(d, B2C_OP_FORWARD) == B2C_ALGO_TCGEN05)
+    return launch_conv_tc(s, B2C_OP_FORWARD, d->math, x, w, bias, y, ws, ws_bytes, st);
+  return launch_conv_fwd_simt(s, x, w, bias, y, st);
+}
+
+extern "C" int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
+                                      size_t ws_bytes, void* stream) {
+  if (!d || !dy || !w || !dx) return fail(B2C_ERR_INVALID, "b2c_conv_backward_data: null pointer");
+  REQUIRE_DEVICE();
+  const ConvShape& s = d->s;
+  cudaStream_t st = as_stream(stream);
+  const size_t need = b2c_conv_workspace_bytes(d, B2C_OP_BACKWARD_DATA);
+  if (ws_bytes < need || (need && !ws)) return fail(B2C_ERR_WORKSPACE, "backward_data workspace too small");
+  if (d->engine == B2C_ENGINE_CAFFE) {
+    const int P = s.Ho * s.Wo;
+    const size_t bdim = (size_t)s.C * s.H * s.W, tdim = (size_t)s.O * P;
+    float* col = static_cast<float*>(ws);
+    for (int n = 0; n < s.N; ++n) {
+      float* cb = s.is_1x1 ? dx + n * bdim : col;
+      for (int g = 0; g < s.G; ++g)
+        if (int rc = b2c_sgemm(1, 0, s.Kd, P, s.Og, 1.0f, w + (size_t)g * s.Og * s.Kd, dy + n * tdim + (size_t)g * s.Og * P,
+                               0.0f, cb + (size_t)g * s.Kd * P, stream)) return rc;
+      if (!s.is_1x1)
+        if (int rc = launch_col2im2d(col, s.C, s.H, s.W, s.kh, s.kw, s.ph, s.pw, s.sh, s.sw, s.dh, s.dw, dx + n * bdim, st)) return rc;
+    }
+    return B2C_OK;
+  }
+  if (resolve_algo(d, B2C_OP_BACKWARD_DATA) == B2C_ALGO_TCGEN05)
+    return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, d->math, dy, w, nullptr, dx, ws, ws_bytes, st);
+  return launch_conv_dgrad_simt(s, dy, w, dx, st);
+}
+
+extern "C" int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, const float* dy, float* dw, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  if (!d || !x || !dy || !dw) return fail(B2C_ERR_INVALID, "b2c_conv_backward_filter: null pointer");
+  REQUIRE_DEVICE();
+  const ConvShape& s = d->s;
+  cudaStream_t st = as_stream(stream);
+  const size_t need = b2c_conv_workspace_bytes(d, B2C_OP_BACKWARD_FILTER);
+  if (ws_bytes < need || (need && !ws)) return fail(B2C_ERR_WORKSPACE, "backward_filter workspace too small");
+  if (d->engine == B2C_ENGINE_CAFFE) {
+    const int P = s.Ho * s.Wo;
+    const size_t bdim = (size_t)s.C * s.H * s.W, tdim = (size_t)s.O * P;
+    float* col = static_cast<float*>(ws);
+    for (int n = 0; n < s.N; ++n) {
+      const float* cb = x + n * bdim;
+      if (!s.is_1x1) {
+        if (int rc = launch_im2col2d(x + n * bdim, s.C, s.H, s.W, s.kh, s.kw, s.ph, s.pw, s.sh, s.sw, s.dh, s.dw, col, st)) return rc;
+        cb = col;
+      }
+      for (int g = 0; g < s.G; ++g)
+        if (int rc = b2c_sgemm(0, 1, s.Og, s.Kd, P, 1.0f, dy + n * tdim + (size_t)g * s.Og * P, cb + (size_t)g * s.Kd * P,
+                               1.0f, dw + (size_t)g * s.Og * s.Kd, stream)) return rc;
+    }
+    return B2C_OK;
+  }
+  if (resolve_algo(d, B2C_OP_BACKWARD_FILTER) == B2C_ALGO_TCGEN05)
+    return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, d->math, x, dy, nullptr, dw, ws, ws_bytes, st);
+  return launch_conv_wgrad_simt(s, x, dy, dw, st);
+}
+
+extern "C" int b2c_conv_backward_bias(const b2c_conv_desc* d, const float* dy, float* db, void* stream) {
+  if (!d || !dy || !db) return fail(B2C_ERR_INVALID, "b2c_conv_backward_bias: null pointer");
+  REQUIRE_DEVICE();
+  return launch_bias_grad(d->s.N, d->s.O, d->s.Ho * d->s.Wo, dy, db, as_stream(stream));
+}
+
+extern "C" int b2c_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* B,
+                         float beta, float* C, void* stream) {
+  if (!A || !B || !C || M < 0 || N < 0 || K < 0) return fail(B2C_ERR_INVALID, "b2c_sgemm: bad argument");
+  REQUIRE_DEVICE();
+  if (M == 0 || N == 0) return B2C_OK;
+  const bool tA = transA != 0, tB = transB != 0;
+  if (g_default_algo != B2C_ALGO_SIMT && tc_gemm_supported(tA, tB, M, N, K))
+    return launch_sgemm_tc(tA, tB, M, N, K, alpha, A, B, beta, C, g_default_math, as_stream(stream));
+  return launch_sgemm_simt(tA, tB, M, N, K, alpha, A, tA ? M : K, B, tB ? K : N, beta, C, N, as_stream(stream));
+}

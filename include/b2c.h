@@ -1,0 +1,182 @@
+/*
+ * b2c.h -- C ABI of the B200-native Caffe-MPI data-parallel hot path
+ *          (ConvolutionLayer forward/backward, im2col/col2im, SGEMM/SGEMV, fused
+ *          SGD-momentum update, NCCL gradient exchange).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch or
+ * C++ types.  Every entry point names the reference interface it replaces (paths
+ * relative to the Caffe-MPI tree).  All tensor pointers are DEVICE pointers, fp32,
+ * dense row-major; activations NCHW, weights [O, C/g, kh, kw], bias [O].  `stream`
+ * is the caller's cudaStream_t passed as void* (NULL = legacy default stream).
+ * Calls are asynchronous on `stream`; nothing host-synchronises (the reference syncs
+ * after every BLAS call, math_functions.cu:25 -- callers that need that behaviour
+ * synchronise the stream themselves).
+ *
+ * Error model: the reference aborts through glog CHECK / CUDA_CHECK
+ * (include/caffe/util/nccl.hpp:10-15).  Here every function returns 0 on success or
+ * a negative b2c_status and leaves a thread-local message readable with
+ * b2c_last_error(); the C++ layer shim turns non-zero into a fatal check.
+ * There is NO CPU fallback: on a machine without a CUDA device every compute entry
+ * point returns B2C_ERR_CUDA.
+ */
+#ifndef B2C_H_
+#define B2C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2C_OK = 0,
+  B2C_ERR_INVALID = -1,     /* bad argument / unsupported shape            */
+  B2C_ERR_CUDA = -2,        /* CUDA runtime / launch error                 */
+  B2C_ERR_NCCL = -3,        /* NCCL error                                  */
+  B2C_ERR_WORKSPACE = -4    /* workspace too small                         */
+} b2c_status;
+
+/* ConvolutionParameter.engine, src/caffe/proto/caffe.proto:745-750 (same values).
+ * CAFFE  -> explicit per-image im2col + GEMM (base_conv_layer.hpp:105-168).
+ * CUDNN / DEFAULT -> implicit-GEMM kernels (replaces cudnn_conv_layer.cu:13-132). */
+typedef enum { B2C_ENGINE_DEFAULT = 0, B2C_ENGINE_CAFFE = 1, B2C_ENGINE_CUDNN = 2 } b2c_engine;
+
+/* Math mode of the tensor-core kernels (NetParameter default_forward_math /
+ * default_backward_math, caffe.proto:124-127, is the reference's analogous knob).
+ * FP32  : 3xTF32 split-precision tcgen05 MMA, fp32-equivalent results (default).
+ * TF32  : single-pass TF32 (round-to-nearest operands), ~1e-3 relative.          */
+typedef enum { B2C_MATH_FP32 = 0, B2C_MATH_TF32 = 1 } b2c_math;
+
+/* Kernel family used by the implicit-GEMM engine (diagnostics / tests). */
+typedef enum { B2C_ALGO_AUTO = 0, B2C_ALGO_SIMT = 1, B2C_ALGO_TCGEN05 = 2 } b2c_algo;
+
+typedef enum { B2C_OP_FORWARD = 0, B2C_OP_BACKWARD_DATA = 1, B2C_OP_BACKWARD_FILTER = 2 } b2c_conv_op;
+
+/* Shape of one ConvolutionLayer call: ConvolutionParameter (caffe.proto:718-786) plus
+ * the bottom shape BaseConvolutionLayer::Reshape reads (base_conv_layer.cpp:172-239). */
+typedef struct {
+  int N, C, H, W;     /* bottom blob                                              */
+  int O, G;           /* num_output, group                                        */
+  int kh, kw;         /* kernel_size / kernel_h,kernel_w                          */
+  int sh, sw;         /* stride                                                   */
+  int ph, pw;         /* pad                                                      */
+  int dh, dw;         /* dilation                                                 */
+  int has_bias;       /* bias_term                                                */
+} b2c_conv_params;
+
+typedef struct b2c_conv_desc b2c_conv_desc;
+typedef struct b2c_comm b2c_comm;
+
+/* ---- library ------------------------------------------------------------------- */
+const char* b2c_last_error(void);
+const char* b2c_version(void);
+/* number of kernels THIS library has launched in this process (all threads).      */
+uint64_t b2c_launch_count(void);
+/* process-wide defaults used by descriptors created afterwards                    */
+int b2c_set_default_math(int math /* b2c_math */);
+int b2c_set_default_algo(int algo /* b2c_algo */);
+
+/* ---- convolution descriptor -------------------------------------------------------
+ * Replaces BaseConvolutionLayer::LayerSetUp/Reshape bookkeeping (base_conv_layer.cpp:12-239)
+ * and CuDNNConvolutionLayer's descriptor set-up (cudnn_conv_layer.cpp:78-210).        */
+int b2c_conv_desc_create(const b2c_conv_params* p, int engine, b2c_conv_desc** out);
+int b2c_conv_desc_destroy(b2c_conv_desc* d);
+int b2c_conv_desc_set_math(b2c_conv_desc* d, int math);
+int b2c_conv_desc_set_algo(b2c_conv_desc* d, int algo);
+/* output extent, conv_layer.cpp:7-22 (truncating division)                          */
+int b2c_conv_out_shape(const b2c_conv_desc* d, int* Ho, int* Wo);
+/* scratch bytes the given op needs (col buffer for CAFFE engine: base_conv_layer.cpp:225-233;
+ * split-K partials / transformed weights for the implicit engine).                   */
+size_t b2c_conv_workspace_bytes(const b2c_conv_desc* d, int op);
+/* which kernel family the op will run (b2c_algo) -- lets tests assert "tcgen05 ran". */
+int b2c_conv_algo_used(const b2c_conv_desc* d, int op);
+
+/* Y = conv(X, W) (+ bias).  y OVERWRITTEN.
+ * Replaces ConvolutionLayer::Forward_gpu (conv_layer.cu:7-23) = forward_gpu_gemm +
+ * forward_gpu_bias (base_conv_layer.hpp:105-128) and CuDNNConvolutionLayer::Forward_gpu
+ * (cudnn_conv_layer.cu:13-58: cudnnConvolutionForward beta=0 + cudnnAddTensor).      */
+int b2c_conv_forward(const b2c_conv_desc* d, const float* x, const float* w, const float* bias,
+                     float* y, void* ws, size_t ws_bytes, void* stream);
+/* dX = conv_bwd_data(dY, W).  dx OVERWRITTEN.
+ * Replaces backward_gpu_gemm + col2im (base_conv_layer.hpp:130-146) /
+ * cudnnConvolutionBackwardData beta=0 (cudnn_conv_layer.cu:118-123).                 */
+int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, const float* w, float* dx,
+                           void* ws, size_t ws_bytes, void* stream);
+/* dW += conv_bwd_filter(X, dY).  dw ACCUMULATED (beta = 1).
+ * Replaces weight_gpu_gemm (base_conv_layer.hpp:148-162) /
+ * cudnnConvolutionBackwardFilter beta=1 (cudnn_conv_layer.cu:95-99).                 */
+int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, const float* dy, float* dw,
+                             void* ws, size_t ws_bytes, void* stream);
+/* db[o] += sum_{n,h,w} dY.  db ACCUMULATED (beta = 1).
+ * Replaces backward_gpu_bias (base_conv_layer.hpp:164-168, gemv per image) /
+ * cudnnConvolutionBackwardBias beta=1 (cudnn_conv_layer.cu:73-75).                   */
+int b2c_conv_backward_bias(const b2c_conv_desc* d, const float* dy, float* db, void* stream);
+
+/* ---- im2col / col2im ----------------------------------------------------------------
+ * One image [C,H,W] <-> [C*kh*kw, Ho, Wo].  Replace im2col_gpu / col2im_gpu
+ * (src/caffe/util/im2col.cu:42-62, 298-317).  col2im OVERWRITES im and adds the
+ * contributions of each pixel in ascending (kh,kw) order (bit-identical to the
+ * reference's col2im_cpu, im2col.cpp:176-211).                                         */
+int b2c_im2col(const float* im, int C, int H, int W, int kh, int kw, int ph, int pw,
+               int sh, int sw, int dh, int dw, float* col, void* stream);
+int b2c_col2im(const float* col, int C, int H, int W, int kh, int kw, int ph, int pw,
+               int sh, int sw, int dh, int dw, float* im, void* stream);
+/* N-D (1..10 spatial axes): im2col_nd_gpu / col2im_nd_gpu (im2col.cu:165-253, 443-530).
+ * Shape arrays are HOST int arrays: im_shape [C, d0..], col_shape [C*prod(k), o0..].   */
+int b2c_im2col_nd(const float* im, int num_axes, const int* im_shape, const int* col_shape,
+                  const int* kernel, const int* pad, const int* stride, const int* dilation,
+                  float* col, void* stream);
+int b2c_col2im_nd(const float* col, int num_axes, const int* im_shape, const int* col_shape,
+                  const int* kernel, const int* pad, const int* stride, const int* dilation,
+                  float* im, void* stream);
+
+/* ---- BLAS-shaped entry points -----------------------------------------------------------
+ * Row-major C[MxN] = alpha*op(A)*op(B) + beta*C with the reference's leading
+ * dimensions (lda = transA ? M : K, ldb = transB ? K : N, ldc = N).
+ * Replaces caffe_gpu_gemm<float> -> cublasSgemm (src/caffe/util/math_functions.cu:11-26). */
+int b2c_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A,
+              const float* B, float beta, float* C, void* stream);
+/* y = alpha*op(A)*x + beta*y, A row-major MxN.
+ * Replaces caffe_gpu_gemv<float> -> cublasSgemv (math_functions.cu:73-82).               */
+int b2c_sgemv(int transA, int M, int N, float alpha, const float* A, const float* x,
+              float beta, float* y, void* stream);
+
+/* ---- fused SGD-momentum update -----------------------------------------------------------
+ * h = momentum*h + local_rate*(grad_scale*g + local_decay*reg(w)); w -= h;
+ * g = clear_grads ? 0 : h.   reg(w) = w (l2 != 0) or sign(w).
+ * Replaces SGDRegUpdateAllAndClear + its launcher (src/caffe/solvers/sgd_solver.cu:9-72),
+ * with Net::ReduceBucket's 1/solver_count scal (net.cpp:910), the 1/global_grad_scale
+ * scal (net.cpp:815-817) and SGDSolver::Normalize's 1/iter_size (sgd_solver.cpp:152-158)
+ * folded into grad_scale.                                                                 */
+int b2c_sgd_update(size_t n, float* g, float* w, float* h, float momentum, float local_rate,
+                   float local_decay, int l2, float grad_scale, int clear_grads, void* stream);
+/* Multi-tensor form over a contiguous arena (Net::InitializeLearnableDiffSpace,
+ * net.cpp:1350-1373): nseg segments, segment s covers elements [offset[s], offset[s]+count[s])
+ * of g, w and h (same offsets in all three arenas) with its own local_rate / local_decay
+ * (lr_mult / decay_mult, sgd_solver.cpp:208-210,254-259).  The four arrays are HOST arrays.
+ * One launch replaces one SGDRegUpdateAllAndClear launch per learnable blob.               */
+int b2c_sgd_update_arena(int nseg, const size_t* offset, const size_t* count,
+                         const float* local_rate, const float* local_decay,
+                         float* g, float* w, float* h, float momentum, int l2,
+                         float grad_scale, int clear_grads, void* stream);
+
+/* ---- gradient exchange ---------------------------------------------------------------------
+ * Replaces P2PManager/P2PSync's NCCL use (src/caffe/parallel.cpp:36-87,145-253) and the MPI
+ * bootstrap (src/caffe/clusters.cpp:8-16; parallel.cpp:42-45,163-172).  One communicator per
+ * process (one process per GPU).  The 128-byte id is produced on rank 0 and carried to the
+ * other ranks by the caller (MPI_Bcast in the reference; any byte transport here).           */
+#define B2C_UNIQUE_ID_BYTES 128
+int b2c_comm_get_unique_id(void* id_out /* B2C_UNIQUE_ID_BYTES */);
+int b2c_comm_init(int nranks, int rank, const void* id, b2c_comm** out);
+int b2c_comm_destroy(b2c_comm* c);
+int b2c_comm_nranks(const b2c_comm* c);
+/* ncclBcast of parameter data from `root` (P2PSync::on_start, parallel.cpp:208-227).        */
+int b2c_comm_bcast(b2c_comm* c, float* buf, size_t count, int root, void* stream);
+/* in-place ncclSum allreduce of a diff bucket (P2PSync::allreduce_bucket, parallel.cpp:245-253) */
+int b2c_comm_allreduce_sum(b2c_comm* c, float* buf, size_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* B2C_H_ */
