@@ -1,0 +1,340 @@
+// conv_tc_wgrad.cu -- tcgen05 implicit-GEMM weight-gradient kernel (sm_100a).
+//
+// Replaces cudnnConvolutionBackwardFilter beta=1 (reference src/caffe/layers/cudnn_conv_layer.cu:95-99)
+// and, semantically, the per-image weight_gpu_gemm loop (base_conv_layer.hpp:148-162):
+//     dW[o][k'=(c,i,j)] += sum_{q=(n,ho,wo)} dY[n,o,ho,wo] * X[n,c,ho*s-p+i*d,wo*s-p+j*d]
+// GEMM view: M = output channels of one group (tile 128), N = K_dim = (C/g)*kh*kw (tile N_TILE), the
+// reduction runs over q = N*Ho*Wo, which is the CONTIGUOUS axis of both operands in NCHW memory, so both
+// smem tiles are filled "lanes along K": dY with 128-bit loads, X through the im2col gather.  The
+// reduction is split across CTAs (grid.x); partial tiles go to a workspace and a second, deterministic
+// kernel adds them to dW in split order (the reference accumulates image by image, also a fixed order).
+#include "b2c_common.cuh"
+#include "tc_common.cuh"
+
+namespace b2c {
+using namespace tc;
+
+constexpr int WG_THREADS = 288;
+
+struct WgradParams {
+  const float* dy;   // [N, O, Ho, Wo]
+  const float* x;    // [N, C, H, W]
+  int N, C, H, W, O, Cg, Og, Kd;
+  int kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo;
+  long long Q;       // N*Ho*Wo
+  int kb_per_split;  // k-blocks (of 32 q) per split
+  int splits;
+  float* out;        // splits == 1: dW (accumulated);  else partials [splits][O*Kd] (overwritten)
+};
+
+template <int N_TILE, bool SPLIT>
+struct WgradSmem {
+  static constexpr uint32_t A_BYTES = tile_bytes(128);
+  static constexpr uint32_t B_BYTES = tile_bytes(N_TILE);
+  static constexpr uint32_t STAGE = (SPLIT ? 2u : 1u) * (A_BYTES + B_BYTES);
+  static constexpr uint32_t TABLE = N_TILE * 8u;
+  static constexpr int STAGES = (int)((216u * 1024u) / STAGE) > 6 ? 6 : (int)((216u * 1024u) / STAGE);
+  static constexpr uint32_t BAR_OFF = STAGES * STAGE;
+  static constexpr uint32_t TAB_OFF = BAR_OFF + 256;
+  static constexpr uint32_t TOTAL = TAB_OFF + TABLE;
+};
+
+template <int N_TILE, bool SPLIT, bool X1X1>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using S = WgradSmem<N_TILE, SPLIT>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + S::BAR_OFF;
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_tmem = bar_empty + 8 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  int2* rowtab = reinterpret_cast<int2*>(smem + S::TAB_OFF);   // per B row: {channel offset, hoff | woff<<16}
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int n0 = blockIdx.y * N_TILE;                 // k' tile
+  const int mtiles = (p.Og + 127) / 128;
+  const int g = blockIdx.z / mtiles, m0 = (blockIdx.z % mtiles) * 128;
+  const int P = p.Ho * p.Wo;
+  const long long HW = (long long)p.H * p.W;
+  const long long nkb_total = (p.Q + BK - 1) / BK;
+  const long long kb_begin = (long long)split * p.kb_per_split;
+  long long kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > nkb_total) kb_end = nkb_total;
+  const int nkb = (int)(kb_end - kb_begin);           // >= 1 by construction
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), N_TILE);
+  // row table for the X gather: k' = (c,i,j)
+  for (int r = tid; r < N_TILE; r += WG_THREADS) {
+    const int kp = n0 + r;
+    int2 e = make_int2(-1, 0);
+    if (kp < p.Kd) {
+      const int j = kp % p.kw, i = (kp / p.kw) % p.kh, c = kp / (p.kw * p.kh);
+      e.x = (int)(((long long)g * p.Cg + c) * HW);      // channel offset inside one image (C*H*W < 2^31)
+      e.y = (i * p.dh) | ((j * p.dw) << 16);
+    }
+    rowtab[r] = e;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr uint32_t LBO_A = tile_lbo(128), LBO_B = tile_lbo(N_TILE);
+  auto stage_a_hi = [&](int s) { return sbase + s * S::STAGE; };
+  auto stage_a_lo = [&](int s) { return sbase + s * S::STAGE + S::A_BYTES; };
+  auto stage_b_hi = [&](int s) { return sbase + s * S::STAGE + (SPLIT ? 2u : 1u) * S::A_BYTES; };
+  auto stage_b_lo = [&](int s) { return stage_b_hi(s) + S::B_BYTES; };
+
+  if (warp < 4) {
+    // ================= A producer: dY rows (output channels), lanes along q ==========================
+    const int kc = tid & 7, rb = tid >> 3;
+    const bool vec_ok = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dy) & 15u) == 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      const long long q = (kb_begin + kb) * BK + kc * 4;
+      const uint32_t a_hi = stage_a_hi(s) + kc * LBO_A, a_lo = stage_a_lo(s) + kc * LBO_A;
+      // decompose the 4 consecutive q's of this thread
+      int nn[4], pp[4];
+      bool qv[4];
+      {
+        long long n_ = q / P;
+        int p_ = (int)(q - n_ * P);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          qv[e] = (q + e) < p.Q;
+          nn[e] = (int)n_; pp[e] = p_;
+          if (++p_ == P) { p_ = 0; ++n_; }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = r * 16 + rb;
+        const int o = m0 + row;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (o < p.Og) {
+          const long long ch = (long long)g * p.Og + o;
+          if (vec_ok && qv[3]) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.dy + ((long long)nn[0] * p.O + ch) * P + pp[0]));
+            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (qv[e]) v[e] = __ldg(p.dy + ((long long)nn[e] * p.O + ch) * P + pp[e]);
+          }
+        }
+        store_chunk<SPLIT>(a_hi + row * 16, a_lo + row * 16, v[0], v[1], v[2], v[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+    // ================= epilogue ========================================================================
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+    const int o = m0 + tid;
+    const bool ovalid = o < p.Og;
+    float* orow = p.out + (p.splits > 1 ? (long long)split * p.O * p.Kd : 0LL) +
+                  ((long long)g * p.Og + (ovalid ? o : 0)) * p.Kd + n0;
+    const bool accumulate = p.splits == 1;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      if (n0 + c0 >= p.Kd) break;
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (ovalid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.Kd) orow[c0 + j] = accumulate ? orow[c0 + j] + v[j] : v[j];
+      }
+    }
+    tc_fence_before();
+  } else if (warp < 8) {
+    // ================= B producer: im2col gather of X, rows k'=(c,i,j), lanes along q ==================
+    const int t = tid - 128;
+    const int kc = t & 7, rb = t >> 3;
+    const bool vec_ok = X1X1 && (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      const long long q = (kb_begin + kb) * BK + kc * 4;
+      const uint32_t b_hi = stage_b_hi(s) + kc * LBO_B, b_lo = stage_b_lo(s) + kc * LBO_B;
+      long long base[4];
+      int ihb[4], iwb[4];
+      bool qv[4];
+      {
+        long long n_ = q / P;
+        int p_ = (int)(q - n_ * P);
+        int ho = p_ / p.Wo, wo = p_ - ho * p.Wo;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          qv[e] = (q + e) < p.Q;
+          base[e] = n_ * (long long)p.C * HW;
+          ihb[e] = ho * p.sh - p.ph; iwb[e] = wo * p.sw - p.pw;
+          if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++n_; } }
+        }
+      }
+#pragma unroll 4
+      for (int r = 0; r < N_TILE / 16; ++r) {
+        const int row = r * 16 + rb;
+        const int2 rt = rowtab[row];
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (rt.x >= 0) {
+          if (X1X1) {
+            // k=1, s=1, p=0: X rows are contiguous in q exactly like dY
+            if (vec_ok && qv[3]) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.x + base[0] + rt.x + (long long)ihb[0] * p.W + iwb[0]));
+              v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (qv[e]) v[e] = __ldg(p.x + base[e] + rt.x + (long long)ihb[e] * p.W + iwb[e]);
+            }
+          } else {
+            const int hoff = rt.y & 0xffff, woff = rt.y >> 16;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ih = ihb[e] + hoff, iw = iwb[e] + woff;
+              if (qv[e] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W)
+                v[e] = __ldg(p.x + base[e] + rt.x + (long long)ih * p.W + iw);
+            }
+          }
+        }
+        store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v[0], v[1], v[2], v[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+  } else {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        mbar_wait(bar_full + 8 * s, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t ah = smem_desc(stage_a_hi(s) + 2 * kk * LBO_A, LBO_A, 128);
+          const uint64_t bh = smem_desc(stage_b_hi(s) + 2 * kk * LBO_B, LBO_B, 128);
+          if (SPLIT) {
+            const uint64_t al = smem_desc(stage_a_lo(s) + 2 * kk * LBO_A, LBO_A, 128);
+            const uint64_t bl = smem_desc(stage_b_lo(s) + 2 * kk * LBO_B, LBO_B, 128);
+            umma_tf32(tmem_base, al, bh, IDESC, acc); acc = 1;
+            umma_tf32(tmem_base, ah, bl, IDESC, 1);
+          }
+          umma_tf32(tmem_base, ah, bh, IDESC, acc); acc = 1;
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_tmem);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, N_TILE);
+  }
+}
+
+// dw[i] += sum_s part[s][i], s ascending (deterministic)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ dw) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.0f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(part + (long long)s * n + i);
+    dw[i] += acc;
+  }
+}
+
+struct WgradPlan { int n_tile, splits, kb_per_split; };
+
+static WgradPlan wgrad_plan(const ConvShape& s) {
+  WgradPlan pl;
+  pl.n_tile = s.Kd > 128 ? 256 : s.Kd > 64 ? 128 : s.Kd > 32 ? 64 : 32;
+  const long long Q = (long long)s.N * s.Ho * s.Wo;
+  const long long nkb = (Q + BK - 1) / BK;
+  const long long mn = (long long)((s.Og + 127) / 128) * ((s.Kd + pl.n_tile - 1) / pl.n_tile) * s.G;
+  long long splits = (2LL * sm_count() + mn - 1) / mn;
+  const long long max_splits = nkb / 8 > 0 ? nkb / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long per = (nkb + splits - 1) / splits;
+  splits = (nkb + per - 1) / per;
+  pl.splits = (int)splits;
+  pl.kb_per_split = (int)per;
+  return pl;
+}
+
+bool tc_wgrad_supported(const ConvShape& s) {
+  if ((long long)s.C * s.H * s.W >= 0x7fffffffLL) return false;
+  if ((s.kh - 1) * s.dh > 0xffff || (s.kw - 1) * s.dw > 0x7fff) return false;
+  const long long nkb = ((long long)s.N * s.Ho * s.Wo + BK - 1) / BK;
+  return nkb < 0x7fffffffLL;
+}
+
+size_t tc_wgrad_workspace(const ConvShape& s) {
+  const WgradPlan pl = wgrad_plan(s);
+  return pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+}
+
+template <int N_TILE, bool SPLIT, bool X1X1>
+static int launch_wgrad_inst(const WgradParams& p, int G, cudaStream_t st) {
+  using S = WgradSmem<N_TILE, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CUDA_OK(cudaFuncSetAttribute(igemm_wgrad_kernel<N_TILE, SPLIT, X1X1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(p.splits, (p.Kd + N_TILE - 1) / N_TILE, G * ((p.Og + 127) / 128));
+  igemm_wgrad_kernel<N_TILE, SPLIT, X1X1><<<grid, WG_THREADS, S::TOTAL, st>>>(p);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+template <int N_TILE>
+static int launch_wgrad_n(const WgradParams& p, int G, int math, bool x1, cudaStream_t st) {
+  if (math == B2C_MATH_FP32)
+    return x1 ? launch_wgrad_inst<N_TILE, true, true>(p, G, st) : launch_wgrad_inst<N_TILE, true, false>(p, G, st);
+  return x1 ? launch_wgrad_inst<N_TILE, false, true>(p, G, st) : launch_wgrad_inst<N_TILE, false, false>(p, G, st);
+}
+
+int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const float* dy, float* dw, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  const WgradPlan pl = wgrad_plan(s);
+  WgradParams p;
+  p.dy = dy; p.x = x;
+  p.N = s.N; p.C = s.C; p.H = s.H; p.W = s.W; p.O = s.O; p.Cg = s.Cg; p.Og = s.Og; p.Kd = s.Kd;
+  p.kh = s.kh; p.kw = s.kw; p.sh = s.sh; p.sw = s.sw; p.ph = s.ph; p.pw = s.pw; p.dh = s.dh; p.dw = s.dw;
+  p.Ho = s.Ho; p.Wo = s.Wo;
+  p.Q = (long long)s.N * s.Ho * s.Wo;
+  p.kb_per_split = pl.kb_per_split; p.splits = pl.splits;
+  const size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+  if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "wgrad: workspace too small");
+  p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
+  int rc;
+  switch (pl.n_tile) {
+    case 256: rc = launch_wgrad_n<256>(p, s.G, math, s.is_1x1, st); break;
+    case 128: rc = launch_wgrad_n<128>(p, s.G, math, s.is_1x1, st); break;
+    case 64: rc = launch_wgrad_n<64>(p, s.G, math, s.is_1x1, st); break;
+    default: rc = launch_wgrad_n<32>(p, s.G, math, s.is_1x1, st); break;
+  }
+  if (rc) return rc;
+  if (pl.splits > 1) {
+    const long long n = (long long)s.O * s.Kd;
+    wgrad_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(static_cast<const float*>(ws), pl.splits, n, dw);
+    B2C_POST_LAUNCH();
+  }
+  return B2C_OK;
+}
+
+}  // namespace b2c

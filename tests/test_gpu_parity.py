@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 import caffe_mpi_b200 as m  # noqa: E402
 from caffe_mpi_b200 import capi  # noqa: E402
 
-TOL_FP32 = 2e-5
+TOL_FP32 = 1e-4   # 3xTF32: tensor-core accumulator rounding grows with K (3e-5 at K=4608), DESIGN.md
+TOL_SIMT = 2e-5
 TOL_TF32 = 1e-3
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -119,7 +120,7 @@ def test_sgemm_random_vs_oracle(rng, M, N, K, tA, tB):
         want = o.gemm(tA, tB, M, N, K, alpha, A, B, beta, C0, acc64=True)
         Cm = dev(C0.copy())
         capi.sgemm(tA, tB, M, N, K, alpha, dev(A), dev(B), beta, Cm)
-        assert rel_err(host(Cm), want) < TOL_FP32
+        assert rel_err(host(Cm), want) < TOL_SIMT
 
 
 # ---------------------------------------------------------------------------------------------- conv
