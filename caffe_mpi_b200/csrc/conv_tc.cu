@@ -1,133 +1,180 @@
-// conv_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM convolution kernels for sm_100a.
+// conv_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM convolution, forward and data-gradient (sm_100a).
 //
-// Replaces cudnnConvolutionForward / BackwardData / BackwardFilter as called by the reference's
-// CuDNNConvolutionLayer (src/caffe/layers/cudnn_conv_layer.cu:25-29,118-123,95-99): whole batch per
-// launch, NCHW fp32 in and out, y / dx overwritten, dw accumulated, no col buffer in HBM.
+// Replaces cudnnConvolutionForward / cudnnConvolutionBackwardData as called by the reference's
+// CuDNNConvolutionLayer (src/caffe/layers/cudnn_conv_layer.cu:25-29,118-123) and, semantically, the
+// per-image forward_gpu_gemm / backward_gpu_gemm loops (base_conv_layer.hpp:105-146): whole batch per
+// launch, NCHW fp32 in and out, y / dx overwritten, bias fused, no col buffer in HBM.
 //
-// GEMM view (SURVEY.md 8a rows a4/a7/a8 with the batch folded into the pixel dimension):
-//   forward : D[q=(n,ho,wo)][o]      = sum_{k=(c,i,j)} X[n,c,ho*s-p+i*d,wo*s-p+j*d] * W[o][k]
-//   dgrad   : the same kernel run on dY with the transposed / flipped filter (stride 1), or on the
-//             output grid with a strided scatter epilogue (1x1, stride > 1)
-//   wgrad   : D[o][k'=(c,i,j)]      += sum_{q=(n,ho,wo)} dY[n,o,q] * X[n,c,...]      (split over q)
+// GEMM view (batch folded into the pixel dimension):
+//   forward : D[q=(n,ho,wo)][o] = sum_k A[q][k] * B[o][k],  A = im2col gather of X, B = filter
+//   dgrad   : the same kernel run on dY with the transposed (+ flipped) filter for stride-1 layers, or
+//             on the top grid with a strided scatter epilogue for 1x1 / stride>1 / pad 0 layers.
 //
-// Kernel anatomy (one 128 x N_TILE output tile per CTA, 288 threads):
-//   warps 0-3  A producers: gather 128 rows x 32 K of the activation operand straight from NCHW global
-//              memory (coalesced along W), convert to TF32 (hi [+ lo]) in registers, 128-bit st.shared
-//              into the canonical K-major UMMA layout; afterwards they are the epilogue warps
-//              (tcgen05.ld TMEM -> registers -> coalesced NCHW stores, bias fused).
-//   warps 4-7  B producers: weight / K-contiguous operand, 128-bit global loads, same conversion.
-//   warp  8    allocates TMEM, one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=N_TILE, K=8)
-//              against smem descriptors, tcgen05.commit releases pipeline stages through mbarriers.
-// The activation operand cannot be staged by TMA from NCHW: the implicit-GEMM K index (c,i,j) is not
-// a unit-stride axis of the tensor and the 7x7 maps have 196-byte channel strides (TMA needs 16-byte
-// multiples), see DESIGN.md.  fp32 mode issues 3 TF32 MMAs per K step (lo*hi, hi*lo, hi*hi).
+// Kernel anatomy -- persistent, one CTA per SM, 128 x N_TILE output tiles, 320 threads:
+//   warps 0-3  A producers.  One GEMM row (pixel) per thread; the im2col gather reads NCHW global
+//              memory directly (coalesced along W), prefetches one K block (32 values) ahead in
+//              registers, converts to TF32 hi (+ lo) and writes the canonical K-major UMMA layout with
+//              128-bit st.shared.  K is ordered (tap, channel) when C/g % 4 == 0 so one bounds check
+//              covers a 4-channel chunk.
+//   warp  4    TMA producer for the filter operand: a prepass kernel writes the filter in GEMM-K order,
+//              already split into TF32 hi / lo and zero padded to a multiple of 32; cp.async.bulk.tensor
+//              (SWIZZLE_128B) drops [N_TILE x 32] boxes into smem, completion on the stage mbarrier.
+//   warp  5    allocates TMEM (2 x N_TILE columns) and issues tcgen05.mma.kind::tf32 (M=128, N=N_TILE,
+//              K=8); tcgen05.commit releases smem stages and publishes finished accumulators.
+//   warps 6-9  epilogue: tcgen05.ld TMEM -> registers -> bias -> coalesced NCHW stores, overlapped with
+//              the next tile's main loop through the double-buffered accumulator.
+// The activation operand is not TMA-staged: with NCHW the GEMM-K axis (c,i,j) is not unit-stride and
+// 7x7 maps have 196-byte channel pitches (TMA needs 16-byte multiples); see DESIGN.md.
+// fp32 math mode = 3 TF32 MMAs per K step (lo*hi, hi*lo, hi*hi); TF32 mode = 1.
+#include <cuda.h>
 #include "b2c_common.cuh"
 #include "tc_common.cuh"
 
 namespace b2c {
 using namespace tc;
 
-constexpr int TC_THREADS = 288;
+constexpr int FW_THREADS = 320;
 
-struct FwdLikeParams {
+struct FwdParams {
   // A: activations [Nimg, Cin_tot, H, W]; group g reads channels [g*Cg, (g+1)*Cg)
   const float* x;
   int Cin_tot, H, W, Cg;
   int kh, kw, sh, sw, ph, pw, dh, dw;
   int Ho, Wo;        // pixel grid of the GEMM rows: m = (n*Ho + ho)*Wo + wo
   int Mtot;          // Nimg*Ho*Wo
-  // B: [G][Ntot][K] row-major, K contiguous (K = Cg*kh*kw)
-  const float* w;
-  int Ntot, K;
+  int Ntot;          // GEMM columns per group
+  int K, Kp;         // true / padded (multiple of 32) reduction length
   // out[(n*Cout_tot + g*Ntot + col)*out_plane + ho*out_hs + wo*out_ws]
   float* out;
   int Cout_tot, out_hs, out_ws;
   long long out_plane;
   const float* bias;  // [G*Ntot] or null
+  int m_tiles, n_tiles, G, total_tiles;
 };
 
 template <int N_TILE, bool SPLIT>
-struct FwdLikeSmem {
+struct FwdSmem {
   static constexpr uint32_t A_BYTES = tile_bytes(128);
-  static constexpr uint32_t B_BYTES = tile_bytes(N_TILE);
-  static constexpr uint32_t STAGE = (SPLIT ? 2u : 1u) * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (int)((220u * 1024u) / STAGE) > 6 ? 6 : (int)((220u * 1024u) / STAGE);
+  static constexpr uint32_t B_BYTES = N_TILE * 128u;                       // [N_TILE rows][32 fp32], SW128
+  static constexpr uint32_t NP = SPLIT ? 2u : 1u;
+  static constexpr uint32_t STAGE = ((NP * (A_BYTES + B_BYTES) + 1023u) / 1024u) * 1024u;
+  static constexpr int STAGES = (int)((222u * 1024u) / STAGE) > 6 ? 6 : (int)((222u * 1024u) / STAGE);
   static constexpr uint32_t BAR_OFF = STAGES * STAGE;
-  static constexpr uint32_t TOTAL = BAR_OFF + 256;
+  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;                  // + alignment slack
+  static constexpr uint32_t TX_BYTES = NP * B_BYTES;
 };
 
-template <int N_TILE, bool SPLIT, bool K1X1>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-igemm_fwdlike_kernel(const __grid_constant__ FwdLikeParams p) {
-  using S = FwdLikeSmem<N_TILE, SPLIT>;
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;         // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// KMODE 0: natural K order (c,i,j), per-element decode (any C/g).  KMODE 1: K order (i,j,c), C/g % 4 == 0.
+template <int N_TILE, bool SPLIT, int KMODE>
+__global__ void __launch_bounds__(FW_THREADS, 1)
+igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap map_hi,
+                 const __grid_constant__ CUtensorMap map_lo) {
+  using S = FwdSmem<N_TILE, SPLIT>;
   constexpr int STAGES = S::STAGES;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + S::BAR_OFF;            // STAGES x 8 B
-  const uint32_t bar_empty = bar_full + 8 * STAGES;        // STAGES x 8 B
-  const uint32_t bar_tmem = bar_empty + 8 * STAGES;        // 8 B
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SW128 tiles need 1024-byte alignment
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_full = sbase + S::BAR_OFF;
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;     // 2 x 8 B
+  const uint32_t bar_tempty = bar_tfull + 16;            // 2 x 8 B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 8 * (2 * STAGES + 4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * N_TILE, g = blockIdx.z;
-  const int nkb = (p.K + BK - 1) / BK;
+  const int nkb = p.Kp / BK;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 256);   // every producer thread arrives
-      mbar_init(bar_empty + 8 * s, 1);    // one tcgen05.commit
+      mbar_init(bar_full + 8 * s, 128 + 1);   // 128 A-producer threads + the TMA thread's expect_tx arrive
+      mbar_init(bar_empty + 8 * s, 1);        // one tcgen05.commit
     }
-    mbar_init(bar_tmem, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), N_TILE);
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 2 * N_TILE);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr uint32_t LBO_A = tile_lbo(128), LBO_B = tile_lbo(N_TILE);
-  auto stage_a_hi = [&](int s) { return sbase + s * S::STAGE; };
-  auto stage_a_lo = [&](int s) { return sbase + s * S::STAGE + S::A_BYTES; };
-  auto stage_b_hi = [&](int s) { return sbase + s * S::STAGE + (SPLIT ? 2u : 1u) * S::A_BYTES; };
-  auto stage_b_lo = [&](int s) { return stage_b_hi(s) + S::B_BYTES; };
+  constexpr uint32_t LBO_A = tile_lbo(128);
+  // stage layout: [B_hi | B_lo | A_hi | A_lo]  (B first: 1024-aligned)
+  auto stage_b_hi = [&](int s) { return sbase + s * S::STAGE; };
+  auto stage_b_lo = [&](int s) { return sbase + s * S::STAGE + S::B_BYTES; };
+  auto stage_a_hi = [&](int s) { return sbase + s * S::STAGE + S::NP * S::B_BYTES; };
+  auto stage_a_lo = [&](int s) { return stage_a_hi(s) + S::A_BYTES; };
+
+  auto tile_coords = [&](int tile, int& m0, int& n0, int& g) {
+    const int nt = tile % p.n_tiles;
+    const int r = tile / p.n_tiles;
+    const int mt = r % p.m_tiles;
+    g = r / p.m_tiles;
+    m0 = mt * 128; n0 = nt * N_TILE;
+  };
 
   if (warp < 4) {
-    // ================= A producer: one GEMM row (output pixel) per thread =========================
-    const int m = m0 + tid;
-    const bool mvalid = m < p.Mtot;
-    const int P = p.Ho * p.Wo;
-    const int mm = mvalid ? m : 0;
-    const int n = mm / P, pix = mm - n * P;
-    const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
-    const int ih0 = ho * p.sh - p.ph, iw0 = wo * p.sw - p.pw;
+    // ================= A producers =====================================================================
     const long long HW = (long long)p.H * p.W;
-    const float* xrow = p.x + ((long long)n * p.Cin_tot + (long long)g * p.Cg) * HW + (long long)ih0 * p.W + iw0;
-    const bool row_inb = mvalid && (unsigned)ih0 < (unsigned)p.H && (unsigned)iw0 < (unsigned)p.W;  // used when K1X1
-    // incremental decode of k -> (c,i,j): koff = c*HW + i*dh*W + j*dw, hoff = i*dh, woff = j*dw
-    int ki = 0, kj = 0, hoff = 0, woff = 0, k = 0;
-    long long koff = 0;
+    const int P = p.Ho * p.Wo;
     const uint32_t row_off = (uint32_t)tid * 16u;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
-      const uint32_t a_hi = stage_a_hi(s) + row_off, a_lo = stage_a_lo(s) + row_off;
+    int kbg = 0;   // running k-block counter across tiles (pipeline position)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int m0, n0, g;
+      tile_coords(tile, m0, n0, g);
+      const int m = m0 + tid;
+      const bool mvalid = m < p.Mtot;
+      const int mm = mvalid ? m : 0;
+      const int n = mm / P, pix = mm - n * P;
+      const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
+      const int ih0 = ho * p.sh - p.ph, iw0 = wo * p.sw - p.pw;
+      const float* xrow = p.x + ((long long)n * p.Cin_tot + (long long)g * p.Cg) * HW + (long long)ih0 * p.W + iw0;
+      // decode cursor (advances with the loads)
+      int ki = 0, kj = 0, hoff = 0, woff = 0, kc_ = 0;   // kc_: channel (KMODE 1) / flat k (KMODE 0)
+      long long koff = 0;
+
+      auto load_block = [&](float (&v)[32]) {
+        if (KMODE == 1) {
 #pragma unroll
-      for (int kc = 0; kc < KCHUNKS; ++kc) {
-        float v[4];
+          for (int ch = 0; ch < KCHUNKS; ++ch) {
+            const bool ok = mvalid && ki < p.kh && (unsigned)(ih0 + hoff) < (unsigned)p.H &&
+                            (unsigned)(iw0 + woff) < (unsigned)p.W;
+            const float* src = xrow + koff;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          bool ok;
-          if (K1X1) {
-            ok = row_inb && k < p.K;
-          } else {
-            ok = mvalid && k < p.K && (unsigned)(ih0 + hoff) < (unsigned)p.H && (unsigned)(iw0 + woff) < (unsigned)p.W;
+            for (int e = 0; e < 4; ++e) v[ch * 4 + e] = ok ? __ldg(src + e * HW) : 0.0f;
+            kc_ += 4; koff += 4 * HW;
+            if (kc_ >= p.Cg) {              // next tap
+              kc_ = 0; koff -= (long long)p.Cg * HW;
+              ++kj; woff += p.dw; koff += p.dw;
+              if (kj == p.kw) { kj = 0; koff -= woff; woff = 0; ++ki; hoff += p.dh; koff += (long long)p.dh * p.W; }
+            }
           }
-          v[e] = ok ? __ldg(xrow + koff) : 0.0f;
-          ++k;
-          if (K1X1) {
-            koff += HW;
-          } else {
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const bool ok = mvalid && kc_ < p.K && (unsigned)(ih0 + hoff) < (unsigned)p.H &&
+                            (unsigned)(iw0 + woff) < (unsigned)p.W;
+            v[e] = ok ? __ldg(xrow + koff) : 0.0f;
+            ++kc_;
             ++kj; woff += p.dw; koff += p.dw;
             if (kj == p.kw) {
               kj = 0; koff -= woff; woff = 0;
@@ -136,147 +183,238 @@ igemm_fwdlike_kernel(const __grid_constant__ FwdLikeParams p) {
             }
           }
         }
-        store_chunk<SPLIT>(a_hi + kc * LBO_A, a_lo + kc * LBO_A, v[0], v[1], v[2], v[3]);
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
-    }
-    // ================= epilogue: TMEM -> registers -> NCHW global ==================================
-    mbar_wait(bar_tmem, 0);
-    tc_fence_after();
-    float* orow = p.out + ((long long)n * p.Cout_tot + (long long)g * p.Ntot + n0) * p.out_plane +
-                  (long long)ho * p.out_hs + (long long)wo * p.out_ws;
-    const float* brow = p.bias ? p.bias + (long long)g * p.Ntot + n0 : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-      if (n0 + c0 >= p.Ntot) break;   // warp-uniform
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (mvalid) {
+      };
+      auto store_block = [&](const float (&v)[32]) {
+        const int s = kbg % STAGES, it = kbg / STAGES;
+        mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+        const uint32_t a_hi = stage_a_hi(s) + row_off, a_lo = stage_a_lo(s) + row_off;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (n0 + c0 + j < p.Ntot) {
-            float r = v[j];
-            if (brow) r += __ldg(brow + c0 + j);
-            orow[(long long)(c0 + j) * p.out_plane] = r;
-          }
-        }
+        for (int ch = 0; ch < KCHUNKS; ++ch)
+          store_chunk<SPLIT>(a_hi + ch * LBO_A, a_lo + ch * LBO_A, v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
+        ++kbg;
+      };
+
+      float va[32], vb[32];
+      load_block(va);
+      int kb = 0;
+      for (; kb + 2 <= nkb; kb += 2) {
+        load_block(vb);
+        store_block(va);
+        if (kb + 2 < nkb) load_block(va);
+        store_block(vb);
       }
+      if (kb < nkb) store_block(va);
     }
-    tc_fence_before();
-  } else if (warp < 8) {
-    // ================= B producer: lanes along K, 4 rows x 8 chunks per warp pass ==================
-    const int t = tid - 128;
-    const float* wg = p.w + (long long)g * p.Ntot * p.K;
-    const bool vec_ok = (p.K % 4 == 0) && ((reinterpret_cast<uintptr_t>(wg) & 15u) == 0);
-    const int kc = t & 7;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
-      const uint32_t b_hi = stage_b_hi(s) + kc * LBO_B, b_lo = stage_b_lo(s) + kc * LBO_B;
-      const int k = kb * BK + kc * 4;
-#pragma unroll
-      for (int r = 0; r < N_TILE / 16; ++r) {
-        const int row = r * 16 + (t >> 3);
-        const int col = n0 + row;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-        if (col < p.Ntot) {
-          const float* src = wg + (long long)col * p.K + k;
-          if (vec_ok && k + 3 < p.K) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(src));
-            v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
-          } else {
-            if (k < p.K) v0 = __ldg(src);
-            if (k + 1 < p.K) v1 = __ldg(src + 1);
-            if (k + 2 < p.K) v2 = __ldg(src + 2);
-            if (k + 3 < p.K) v3 = __ldg(src + 3);
-          }
-        }
-        store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v0, v1, v2, v3);
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
-    }
-  } else {
-    // ================= MMA issuer ====================================================================
+  } else if (warp == 4) {
+    // ================= TMA producer (filter operand) ===================================================
     if (lane == 0) {
-      constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
-      uint32_t acc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
-        mbar_wait(bar_full + 8 * s, it & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t ah = smem_desc(stage_a_hi(s) + 2 * kk * LBO_A, LBO_A, 128);
-          const uint64_t bh = smem_desc(stage_b_hi(s) + 2 * kk * LBO_B, LBO_B, 128);
-          if (SPLIT) {
-            const uint64_t al = smem_desc(stage_a_lo(s) + 2 * kk * LBO_A, LBO_A, 128);
-            const uint64_t bl = smem_desc(stage_b_lo(s) + 2 * kk * LBO_B, LBO_B, 128);
-            umma_tf32(tmem_base, al, bh, IDESC, acc); acc = 1;
-            umma_tf32(tmem_base, ah, bl, IDESC, 1);
-          }
-          umma_tf32(tmem_base, ah, bh, IDESC, acc); acc = 1;
+      int kbg = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int m0, n0, g;
+        tile_coords(tile, m0, n0, g);
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % STAGES, it = kbg / STAGES;
+          mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, S::TX_BYTES);
+          tma_load_3d(stage_b_hi(s), &map_hi, bar_full + 8 * s, kb * BK, n0, g);
+          if (SPLIT) tma_load_3d(stage_b_lo(s), &map_lo, bar_full + 8 * s, kb * BK, n0, g);
         }
-        umma_commit(bar_empty + 8 * s);     // stage reusable once these MMAs have read it
       }
-      umma_commit(bar_tmem);                // accumulator complete
     }
     __syncwarp();
+  } else if (warp == 5) {
+    // ================= MMA issuer ========================================================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
+      int kbg = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % STAGES, it = kbg / STAGES;
+          mbar_wait(bar_full + 8 * s, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t ah = smem_desc(stage_a_hi(s) + 2 * kk * LBO_A, LBO_A, 128);
+            const uint64_t bh = smem_desc_sw128(stage_b_hi(s) + kk * 32);
+            if (SPLIT) {
+              const uint64_t al = smem_desc(stage_a_lo(s) + 2 * kk * LBO_A, LBO_A, 128);
+              const uint64_t bl = smem_desc_sw128(stage_b_lo(s) + kk * 32);
+              umma_tf32(d_tmem, al, bh, IDESC, acc); acc = 1;
+              umma_tf32(d_tmem, ah, bl, IDESC, 1);
+            }
+            umma_tf32(d_tmem, ah, bh, IDESC, acc); acc = 1;
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps 6..9 ================================================================
+    const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int r = lg * 32 + lane;            // GEMM row inside the tile
+    const int P = p.Ho * p.Wo;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      int m0, n0, g;
+      tile_coords(tile, m0, n0, g);
+      const int buf = ti & 1;
+      const int m = m0 + r;
+      const bool mvalid = m < p.Mtot;
+      const int mm = mvalid ? m : 0;
+      const int n = mm / P, pix = mm - n * P;
+      const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
+      float* orow = p.out + ((long long)n * p.Cout_tot + (long long)g * p.Ntot + n0) * p.out_plane +
+                    (long long)ho * p.out_hs + (long long)wo * p.out_ws;
+      const float* brow = p.bias ? p.bias + (long long)g * p.Ntot + n0 : nullptr;
+      mbar_wait(bar_tfull + 8 * buf, (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        if (n0 + c0 >= p.Ntot) break;   // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N_TILE + c0), v);
+        if (mvalid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + c0 + j < p.Ntot) {
+              float t = v[j];
+              if (brow) t += __ldg(brow + c0 + j);
+              orow[(long long)(c0 + j) * p.out_plane] = t;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+    }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, N_TILE);
+    tmem_dealloc(tmem_base, 2 * N_TILE);
   }
 }
 
-// ---- weight transform for dgrad-as-forward --------------------------------------------------------
-// wt[g][c][o][i'][j'] = w[g*Og+o][c][kh-1-i'][kw-1-j']   (flip == 0 keeps (i,j))
+// ---- filter prepass: GEMM-K ordering, TF32 split, zero padding -------------------------------------------
+// out_hi/out_lo [G][rows][Kp].  mode 0 (forward): row = o, K = (c,i,j) natural or (i,j,c) tap-major.
+// mode 1 (dgrad): row = c, K = (o,i',j') natural or (i',j',o) tap-major, filter flipped when flip != 0.
+struct PrepParams {
+  const float* w;
+  float* hi;
+  float* lo;       // null in TF32 mode
+  int G, Og, Cg, kh, kw, rows, K, Kp, mode, tap_major, flip;
+};
+
 __global__ void __launch_bounds__(256)
-weight_transpose_flip_kernel(const float* __restrict__ w, float* __restrict__ wt, int G, int Og, int Cg, int kh, int kw) {
-  const long long total = (long long)G * Og * Cg * kh * kw;
+filter_prep_kernel(const PrepParams q) {
+  const long long total = (long long)q.G * q.rows * q.Kp;
+  const int taps = q.kh * q.kw;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx % kw), i = (int)((idx / kw) % kh);
-    const int o = (int)((idx / ((long long)kw * kh)) % Og), c = (int)((idx / ((long long)kw * kh * Og)) % Cg);
-    const int g = (int)(idx / ((long long)kw * kh * Og * Cg));
-    wt[idx] = __ldg(w + ((((long long)g * Og + o) * Cg + c) * kh + (kh - 1 - i)) * kw + (kw - 1 - j));
+    const int kp = (int)(idx % q.Kp);
+    const int row = (int)((idx / q.Kp) % q.rows);
+    const int g = (int)(idx / ((long long)q.Kp * q.rows));
+    float v = 0.0f;
+    if (kp < q.K) {
+      const int inner = q.mode == 0 ? q.Cg : q.Og;    // the channel-like axis of K
+      int ch, tap;
+      if (q.tap_major) { tap = kp / inner; ch = kp - tap * inner; } else { ch = kp / taps; tap = kp - ch * taps; }
+      if (q.flip) tap = taps - 1 - tap;
+      const int o = q.mode == 0 ? row : ch, c = q.mode == 0 ? ch : row;
+      v = __ldg(q.w + (((long long)g * q.Og + o) * q.Cg + c) * taps + tap);
+    }
+    if (q.lo) {
+      float h, l;
+      split_tf32(v, h, l);
+      q.hi[idx] = h; q.lo[idx] = l;
+    } else {
+      q.hi[idx] = to_tf32(v);
+    }
   }
 }
 
-template <int N_TILE, bool SPLIT, bool K1X1>
-static int launch_fwdlike_inst(const FwdLikeParams& p, int G, cudaStream_t st) {
-  using S = FwdLikeSmem<N_TILE, SPLIT>;
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+static int make_filter_map(CUtensorMap* map, const float* base, int Kp, int rows, int G, int n_tile) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)G};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)Kp * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {32, (cuuint32_t)n_tile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B2C_OK;
+}
+
+template <int N_TILE, bool SPLIT, int KMODE>
+static int launch_fwd_inst(const FwdParams& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+  using S = FwdSmem<N_TILE, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2C_CUDA_OK(cudaFuncSetAttribute(igemm_fwdlike_kernel<N_TILE, SPLIT, K1X1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    B2C_CUDA_OK(cudaFuncSetAttribute(igemm_fwd_kernel<N_TILE, SPLIT, KMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)S::TOTAL));
     attr_set = true;
   }
-  dim3 grid((p.Mtot + 127) / 128, (p.Ntot + N_TILE - 1) / N_TILE, G);
-  igemm_fwdlike_kernel<N_TILE, SPLIT, K1X1><<<grid, TC_THREADS, S::TOTAL, st>>>(p);
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  igemm_fwd_kernel<N_TILE, SPLIT, KMODE><<<grid, FW_THREADS, S::TOTAL, st>>>(p, mh, ml);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
 
 template <int N_TILE>
-static int launch_fwdlike_n(const FwdLikeParams& p, int G, int math, bool k1, cudaStream_t st) {
-  if (math == B2C_MATH_FP32) {
-    return k1 ? launch_fwdlike_inst<N_TILE, true, true>(p, G, st) : launch_fwdlike_inst<N_TILE, true, false>(p, G, st);
+static int launch_fwd_n(const FwdParams& p, const CUtensorMap& mh, const CUtensorMap& ml, int math, int kmode,
+                        cudaStream_t st) {
+  if (math == B2C_MATH_FP32)
+    return kmode ? launch_fwd_inst<N_TILE, true, 1>(p, mh, ml, st) : launch_fwd_inst<N_TILE, true, 0>(p, mh, ml, st);
+  return kmode ? launch_fwd_inst<N_TILE, false, 1>(p, mh, ml, st) : launch_fwd_inst<N_TILE, false, 0>(p, mh, ml, st);
+}
+
+// pick the N tile: per-tile cost ~ nkb * max(mma, producer) + epilogue, tiles spread over the SMs in rounds
+static int pick_n_tile(int Mtot, int Ntot, int G, int Kp, int math) {
+  const int cands[4] = {256, 128, 64, 32};
+  int best = 32;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int nt = cands[i];
+    if (nt > 32 && nt / 2 >= Ntot) continue;   // a smaller tile already covers all columns
+    const long long tiles = (long long)((Mtot + 127) / 128) * ((Ntot + nt - 1) / nt) * G;
+    const double mma = (math == B2C_MATH_FP32 ? 1.5 : 0.5) * nt;      // cycles per 32-deep K block
+    const double prod = 420.0;
+    const double per_tile = (Kp / 32) * (mma > prod ? mma : prod) + 10.0 * nt + 1500.0;
+    const double rounds = (double)((tiles + sm_count() - 1) / sm_count());
+    const double cost = rounds * per_tile;
+    if (cost < best_cost * 0.97) { best_cost = cost; best = nt; }
   }
-  return k1 ? launch_fwdlike_inst<N_TILE, false, true>(p, G, st) : launch_fwdlike_inst<N_TILE, false, false>(p, G, st);
+  return best;
 }
 
-static int launch_fwdlike(const FwdLikeParams& p, int G, int math, cudaStream_t st) {
-  const bool k1 = p.kh == 1 && p.kw == 1;
-  if (p.Ntot > 128) return launch_fwdlike_n<256>(p, G, math, k1, st);
-  if (p.Ntot > 64) return launch_fwdlike_n<128>(p, G, math, k1, st);
-  if (p.Ntot > 32) return launch_fwdlike_n<64>(p, G, math, k1, st);
-  return launch_fwdlike_n<32>(p, G, math, k1, st);
-}
-
-// ---- public entry points of this translation unit ---------------------------------------------------
 bool tc_wgrad_supported(const ConvShape& s);
 size_t tc_wgrad_workspace(const ConvShape& s);
 int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const float* dy, float* dw, void* ws,
@@ -284,6 +422,8 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
 
 static bool dgrad_as_fwd(const ConvShape& s) { return s.sh == 1 && s.sw == 1; }
 static bool dgrad_scatter(const ConvShape& s) { return s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1); }
+
+static int padded_k(int K) { return (K + BK - 1) / BK * BK; }
 
 bool tc_conv_supported(const ConvShape& s, int op) {
   const long long Mtot = (long long)s.N * s.Ho * s.Wo;
@@ -294,54 +434,73 @@ bool tc_conv_supported(const ConvShape& s, int op) {
 }
 
 size_t tc_conv_workspace(const ConvShape& s, int op, int math) {
-  (void)math;
-  if (op == B2C_OP_BACKWARD_DATA) return sizeof(float) * (size_t)s.O * s.Cg * s.kh * s.kw;  // transposed filter
-  if (op == B2C_OP_BACKWARD_FILTER) return tc_wgrad_workspace(s);                          // split-K partials
-  return 0;
+  const size_t np = math == B2C_MATH_FP32 ? 2 : 1;
+  if (op == B2C_OP_FORWARD) return sizeof(float) * np * (size_t)s.O * padded_k(s.Kd) + 256;
+  if (op == B2C_OP_BACKWARD_DATA) return sizeof(float) * np * (size_t)s.C * padded_k(s.Og * s.kh * s.kw) + 256;
+  return tc_wgrad_workspace(s);
 }
 
 int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const float* b, const float* bias, float* out,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
-  FwdLikeParams p;
+  if (op == B2C_OP_BACKWARD_FILTER) return launch_conv_tc_wgrad(s, math, a, b, out, ws, ws_bytes, st);
+  if (ws_bytes < tc_conv_workspace(s, op, math) || !ws) return fail(B2C_ERR_WORKSPACE, "tcgen05 conv: workspace too small");
+  FwdParams p;
+  PrepParams q;
+  q.w = b; q.G = s.G; q.Og = s.Og; q.Cg = s.Cg; q.kh = s.kh; q.kw = s.kw;
+  float* wbase = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   if (op == B2C_OP_FORWARD) {
     p.x = a; p.Cin_tot = s.C; p.H = s.H; p.W = s.W; p.Cg = s.Cg;
     p.kh = s.kh; p.kw = s.kw; p.sh = s.sh; p.sw = s.sw; p.ph = s.ph; p.pw = s.pw; p.dh = s.dh; p.dw = s.dw;
     p.Ho = s.Ho; p.Wo = s.Wo; p.Mtot = s.N * s.Ho * s.Wo;
-    p.w = b; p.Ntot = s.Og; p.K = s.Kd;
+    p.Ntot = s.Og; p.K = s.Kd;
     p.out = out; p.Cout_tot = s.O; p.out_plane = (long long)s.Ho * s.Wo; p.out_hs = s.Wo; p.out_ws = 1;
     p.bias = bias;
-    return launch_fwdlike(p, s.G, math, st);
-  }
-  if (op == B2C_OP_BACKWARD_DATA) {
-    // a = dy [N,O,Ho,Wo], b = w [O,Cg,kh,kw], out = dx [N,C,H,W]
-    const size_t need = sizeof(float) * (size_t)s.O * s.Cg * s.kh * s.kw;
-    if (!ws || ws_bytes < need) return fail(B2C_ERR_WORKSPACE, "dgrad: workspace too small");
-    float* wt = static_cast<float*>(ws);
-    const long long total = (long long)s.O * s.Cg * s.kh * s.kw;
-    weight_transpose_flip_kernel<<<grid_for((size_t)total, 256), 256, 0, st>>>(b, wt, s.G, s.Og, s.Cg, s.kh, s.kw);
-    B2C_POST_LAUNCH();
+    q.mode = 0; q.rows = s.Og; q.flip = 0;
+  } else {
+    // a = dy [N,O,Ho,Wo], b = w, out = dx [N,C,H,W]
     p.x = a; p.Cin_tot = s.O; p.Cg = s.Og;
-    p.w = wt; p.Ntot = s.Cg; p.K = s.Og * s.kh * s.kw;
+    p.Ntot = s.Cg; p.K = s.Og * s.kh * s.kw;
     p.out = out; p.Cout_tot = s.C; p.out_plane = (long long)s.H * s.W; p.bias = nullptr;
+    q.mode = 1; q.rows = s.Cg;
     if (dgrad_as_fwd(s)) {
-      // stride-1 conv of dY with the flipped filter, pad' = (k-1)*d - p, output grid = bottom grid
+      // stride-1 conv of dY with the flipped filter, pad' = (k-1)*d - p, rows = bottom pixels
       p.H = s.Ho; p.W = s.Wo;
       p.kh = s.kh; p.kw = s.kw; p.sh = 1; p.sw = 1; p.dh = s.dh; p.dw = s.dw;
       p.ph = (s.kh - 1) * s.dh - s.ph; p.pw = (s.kw - 1) * s.dw - s.pw;
       p.Ho = s.H; p.Wo = s.W; p.Mtot = s.N * s.H * s.W;
       p.out_hs = s.W; p.out_ws = 1;
-      return launch_fwdlike(p, s.G, math, st);
+      q.flip = 1;
+    } else {
+      // 1x1, stride > 1, pad 0: rows = top pixels, scatter to bottom[ho*sh][wo*sw]; the rest of dx is 0
+      B2C_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)s.N * s.C * s.H * s.W, st));
+      p.H = s.Ho; p.W = s.Wo;
+      p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1; p.dh = 1; p.dw = 1; p.ph = 0; p.pw = 0;
+      p.Ho = s.Ho; p.Wo = s.Wo; p.Mtot = s.N * s.Ho * s.Wo;
+      p.out_hs = s.sh * s.W; p.out_ws = s.sw;
+      q.flip = 0;
     }
-    // 1x1, stride > 1, pad 0: GEMM over the top grid, scatter to bottom[ho*sh][wo*sw]; everything else is 0
-    B2C_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)s.N * s.C * s.H * s.W, st));
-    p.H = s.Ho; p.W = s.Wo;
-    p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1; p.dh = 1; p.dw = 1; p.ph = 0; p.pw = 0;
-    p.Ho = s.Ho; p.Wo = s.Wo; p.Mtot = s.N * s.Ho * s.Wo;
-    p.out_hs = s.sh * s.W; p.out_ws = s.sw;
-    return launch_fwdlike(p, s.G, math, st);
   }
-  if (op == B2C_OP_BACKWARD_FILTER) return launch_conv_tc_wgrad(s, math, a, b, out, ws, ws_bytes, st);
-  return fail(B2C_ERR_INVALID, "tcgen05 path: unsupported op %d", op);
+  p.Kp = padded_k(p.K);
+  const int kmode = (p.Cg % 4 == 0) ? 1 : 0;
+  q.tap_major = kmode; q.K = p.K; q.Kp = p.Kp;
+  const size_t plane = (size_t)s.G * q.rows * p.Kp;
+  q.hi = wbase;
+  q.lo = math == B2C_MATH_FP32 ? wbase + plane : nullptr;
+  filter_prep_kernel<<<grid_for(plane, 256), 256, 0, st>>>(q);
+  B2C_POST_LAUNCH();
+
+  const int n_tile = pick_n_tile(p.Mtot, p.Ntot, s.G, p.Kp, math);
+  p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (p.Ntot + n_tile - 1) / n_tile; p.G = s.G;
+  p.total_tiles = p.m_tiles * p.n_tiles * p.G;
+  alignas(64) CUtensorMap mh, ml;
+  if (int rc = make_filter_map(&mh, q.hi, p.Kp, q.rows, s.G, n_tile)) return rc;
+  if (int rc = make_filter_map(&ml, q.lo ? q.lo : q.hi, p.Kp, q.rows, s.G, n_tile)) return rc;
+  switch (n_tile) {
+    case 256: return launch_fwd_n<256>(p, mh, ml, math, kmode, st);
+    case 128: return launch_fwd_n<128>(p, mh, ml, math, kmode, st);
+    case 64: return launch_fwd_n<64>(p, mh, ml, math, kmode, st);
+    default: return launch_fwd_n<32>(p, mh, ml, math, kmode, st);
+  }
 }
 
 bool tc_gemm_supported(bool, bool, int, int, int) { return false; }

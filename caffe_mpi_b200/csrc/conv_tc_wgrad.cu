@@ -14,7 +14,7 @@
 namespace b2c {
 using namespace tc;
 
-constexpr int WG_THREADS = 288;
+constexpr int WG_THREADS = 416;   // warps 0-3: dY producers + epilogue, 4-11: X gather producers, 12: MMA
 
 struct WgradParams {
   const float* dy;   // [N, O, Ho, Wo]
@@ -66,11 +66,11 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int nkb = (int)(kb_end - kb_begin);           // >= 1 by construction
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 256); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 128 + 256); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tmem, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), N_TILE);
+  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), N_TILE);
   // row table for the X gather: k' = (c,i,j)
   for (int r = tid; r < N_TILE; r += WG_THREADS) {
     const int kp = n0 + r;
@@ -97,12 +97,9 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     // ================= A producer: dY rows (output channels), lanes along q ==========================
     const int kc = tid & 7, rb = tid >> 3;
     const bool vec_ok = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dy) & 15u) == 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+    // loads of k-block kb+1 are issued before the stores of k-block kb (register double buffer)
+    auto load_block = [&](int kb, float (&v)[32]) {
       const long long q = (kb_begin + kb) * BK + kc * 4;
-      const uint32_t a_hi = stage_a_hi(s) + kc * LBO_A, a_lo = stage_a_lo(s) + kc * LBO_A;
-      // decompose the 4 consecutive q's of this thread
       int nn[4], pp[4];
       bool qv[4];
       {
@@ -117,24 +114,45 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const int row = r * 16 + rb;
-        const int o = m0 + row;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const int o = m0 + r * 16 + rb;
+        float* vv = v + r * 4;
+        vv[0] = vv[1] = vv[2] = vv[3] = 0.f;
         if (o < p.Og) {
           const long long ch = (long long)g * p.Og + o;
           if (vec_ok && qv[3]) {
             const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.dy + ((long long)nn[0] * p.O + ch) * P + pp[0]));
-            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+            vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (qv[e]) v[e] = __ldg(p.dy + ((long long)nn[e] * p.O + ch) * P + pp[e]);
+              if (qv[e]) vv[e] = __ldg(p.dy + ((long long)nn[e] * p.O + ch) * P + pp[e]);
           }
         }
-        store_chunk<SPLIT>(a_hi + row * 16, a_lo + row * 16, v[0], v[1], v[2], v[3]);
+      }
+    };
+    auto store_block = [&](int kb, const float (&v)[32]) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      const uint32_t a_hi = stage_a_hi(s) + kc * LBO_A, a_lo = stage_a_lo(s) + kc * LBO_A;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = r * 16 + rb;
+        store_chunk<SPLIT>(a_hi + row * 16, a_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+    };
+    {
+      float va[32], vb[32];
+      load_block(0, va);
+      int kb = 0;
+      for (; kb + 2 <= nkb; kb += 2) {
+        load_block(kb + 1, vb);
+        store_block(kb, va);
+        if (kb + 2 < nkb) load_block(kb + 2, va);
+        store_block(kb + 1, vb);
+      }
+      if (kb < nkb) store_block(kb, va);
     }
     // ================= epilogue ========================================================================
     mbar_wait(bar_tmem, 0);
@@ -156,16 +174,14 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
     }
     tc_fence_before();
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ================= B producer: im2col gather of X, rows k'=(c,i,j), lanes along q ==================
     const int t = tid - 128;
     const int kc = t & 7, rb = t >> 3;
     const bool vec_ok = X1X1 && (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+    constexpr int RB = N_TILE / 32;
+    auto load_block = [&](int kb, float (&v)[RB * 4]) {
       const long long q = (kb_begin + kb) * BK + kc * 4;
-      const uint32_t b_hi = stage_b_hi(s) + kc * LBO_B, b_lo = stage_b_lo(s) + kc * LBO_B;
       long long base[4];
       int ihb[4], iwb[4];
       bool qv[4];
@@ -181,21 +197,21 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
           if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++n_; } }
         }
       }
-#pragma unroll 4
-      for (int r = 0; r < N_TILE / 16; ++r) {
-        const int row = r * 16 + rb;
-        const int2 rt = rowtab[row];
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int2 rt = rowtab[r * 32 + rb];
+        float* vv = v + r * 4;
+        vv[0] = vv[1] = vv[2] = vv[3] = 0.f;
         if (rt.x >= 0) {
           if (X1X1) {
             // k=1, s=1, p=0: X rows are contiguous in q exactly like dY
             if (vec_ok && qv[3]) {
               const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.x + base[0] + rt.x + (long long)ihb[0] * p.W + iwb[0]));
-              v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+              vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (qv[e]) v[e] = __ldg(p.x + base[e] + rt.x + (long long)ihb[e] * p.W + iwb[e]);
+                if (qv[e]) vv[e] = __ldg(p.x + base[e] + rt.x + (long long)ihb[e] * p.W + iwb[e]);
             }
           } else {
             const int hoff = rt.y & 0xffff, woff = rt.y >> 16;
@@ -203,14 +219,35 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
             for (int e = 0; e < 4; ++e) {
               const int ih = ihb[e] + hoff, iw = iwb[e] + woff;
               if (qv[e] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W)
-                v[e] = __ldg(p.x + base[e] + rt.x + (long long)ih * p.W + iw);
+                vv[e] = __ldg(p.x + base[e] + rt.x + (long long)ih * p.W + iw);
             }
           }
         }
-        store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v[0], v[1], v[2], v[3]);
+      }
+    };
+    auto store_block = [&](int kb, const float (&v)[RB * 4]) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      const uint32_t b_hi = stage_b_hi(s) + kc * LBO_B, b_lo = stage_b_lo(s) + kc * LBO_B;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = r * 32 + rb;
+        store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
       }
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
+    };
+    {
+      float va[RB * 4], vb[RB * 4];
+      load_block(0, va);
+      int kb = 0;
+      for (; kb + 2 <= nkb; kb += 2) {
+        load_block(kb + 1, vb);
+        store_block(kb, va);
+        if (kb + 2 < nkb) load_block(kb + 2, va);
+        store_block(kb + 1, vb);
+      }
+      if (kb < nkb) store_block(kb, va);
     }
   } else {
     if (lane == 0) {
@@ -239,7 +276,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, N_TILE);
   }
