@@ -10,30 +10,35 @@
 //   dgrad   : the same kernel run on dY with the transposed (+ flipped) filter for stride-1 layers, or
 //             on the top grid with a strided scatter epilogue for 1x1 / stride>1 / pad 0 layers.
 //
-// Kernel anatomy -- persistent, one CTA per SM, 128 x N_TILE output tiles, 320 threads:
-//   warps 0-3  A producers.  One GEMM row (pixel) per thread; the im2col gather reads NCHW global
-//              memory directly (coalesced along W), prefetches one K block (32 values) ahead in
-//              registers, converts to TF32 hi (+ lo) and writes the canonical K-major UMMA layout with
-//              128-bit st.shared.  K is ordered (tap, channel) when C/g % 4 == 0 so one bounds check
-//              covers a 4-channel chunk.
-//   warp  4    TMA producer for the filter operand: a prepass kernel writes the filter in GEMM-K order,
+// Kernel anatomy -- persistent, one CTA per SM, 128 x N_TILE output tiles, 448 threads:
+//   warps 0-7  A producers.  Two threads per GEMM row (pixel), each owning four of the eight 16-byte K
+//              chunks of a K block; the im2col gather reads NCHW global memory directly (coalesced along
+//              W) from a per-kernel smem table of chunk offsets (the (c,i,j) decode is the same for every
+//              tile), keeps two K blocks of loads in flight in registers across tile boundaries, splits
+//              to TF32 hi (+ lo) on the ALU pipe and writes its row of the A tile straight into tensor
+//              memory (tcgen05.st, lane = GEMM row).  K is ordered (channel/4, tap, channel%4) when C/g % 4 == 0.
+//   warp  8    TMA producer for the filter operand: a prepass kernel writes the filter in GEMM-K order,
 //              already split into TF32 hi / lo and zero padded to a multiple of 32; cp.async.bulk.tensor
 //              (SWIZZLE_128B) drops [N_TILE x 32] boxes into smem, completion on the stage mbarrier.
-//   warp  5    allocates TMEM (2 x N_TILE columns) and issues tcgen05.mma.kind::tf32 (M=128, N=N_TILE,
-//              K=8); tcgen05.commit releases smem stages and publishes finished accumulators.
-//   warps 6-9  epilogue: tcgen05.ld TMEM -> registers -> bias -> coalesced NCHW stores, overlapped with
+//   warp  9    allocates TMEM and issues tcgen05.mma.kind::tf32 (M=128, N=N_TILE, K=8) with the A operand in
+//              TENSOR MEMORY (written there by the producers with tcgen05.st) and B from smem: the 3xTF32 mode
+//              is otherwise shared-memory-bandwidth bound (each K step reads A and B three times); tcgen05.commit releases smem stages and publishes finished accumulators.
+//   warps 10-13 epilogue: tcgen05.ld TMEM -> registers -> bias -> coalesced NCHW stores, overlapped with
 //              the next tile's main loop through the double-buffered accumulator.
 // The activation operand is not TMA-staged: with NCHW the GEMM-K axis (c,i,j) is not unit-stride and
 // 7x7 maps have 196-byte channel pitches (TMA needs 16-byte multiples); see DESIGN.md.
 // fp32 math mode = 3 TF32 MMAs per K step (lo*hi, hi*lo, hi*hi); TF32 mode = 1.
 #include <cuda.h>
+#include <limits.h>
+#include <stdlib.h>
 #include "b2c_common.cuh"
 #include "tc_common.cuh"
 
 namespace b2c {
 using namespace tc;
 
-constexpr int FW_THREADS = 320;
+constexpr int FW_THREADS = 448;
+constexpr int TAB_ENTRIES = 1152;   // gather table: one entry per K chunk (KMODE 1) or per K element (KMODE 0)
 
 struct FwdParams {
   // A: activations [Nimg, Cin_tot, H, W]; group g reads channels [g*Cg, (g+1)*Cg)
@@ -50,17 +55,28 @@ struct FwdParams {
   long long out_plane;
   const float* bias;  // [G*Ntot] or null
   int m_tiles, n_tiles, G, total_tiles;
+  int dbg;            // B2C_DBG experiments: 1 = skip the global gather (producer-side ceiling), 2 = skip the MMAs
 };
 
+// Resources of one CTA.  Shared memory holds only the filter (B) stages; the activation (A) operand
+// lives in tensor memory next to the accumulators:
+//   TMEM columns [0, ACC_BUFS*N_TILE)            fp32 accumulators (double buffered unless N_TILE = 256)
+//                [A_COL0 + s*A_COLS, +A_COLS)     A stage s: 32 columns TF32 hi (+ 32 columns lo)
 template <int N_TILE, bool SPLIT>
 struct FwdSmem {
-  static constexpr uint32_t A_BYTES = tile_bytes(128);
   static constexpr uint32_t B_BYTES = N_TILE * 128u;                       // [N_TILE rows][32 fp32], SW128
   static constexpr uint32_t NP = SPLIT ? 2u : 1u;
-  static constexpr uint32_t STAGE = ((NP * (A_BYTES + B_BYTES) + 1023u) / 1024u) * 1024u;
-  static constexpr int STAGES = (int)((222u * 1024u) / STAGE) > 6 ? 6 : (int)((222u * 1024u) / STAGE);
+  static constexpr uint32_t STAGE = NP * B_BYTES;                          // multiple of 1024
+  static constexpr int ACC_BUFS = N_TILE == 256 ? 1 : 2;
+  static constexpr uint32_t A_COL0 = ACC_BUFS * N_TILE;
+  static constexpr uint32_t A_COLS = SPLIT ? 64u : 32u;
+  static constexpr int TMEM_STAGES = (int)((512u - A_COL0) / A_COLS);
+  static constexpr int SMEM_STAGES = (int)((196u * 1024u) / STAGE);
+  static constexpr int STAGES_ = TMEM_STAGES < SMEM_STAGES ? TMEM_STAGES : SMEM_STAGES;
+  static constexpr int STAGES = STAGES_ > 6 ? 6 : STAGES_;
   static constexpr uint32_t BAR_OFF = STAGES * STAGE;
-  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;                  // + alignment slack
+  static constexpr uint32_t TAB_OFF = BAR_OFF + 256;
+  static constexpr uint32_t TOTAL = TAB_OFF + TAB_ENTRIES * 8 + 1024;      // + alignment slack
   static constexpr uint32_t TX_BYTES = NP * B_BYTES;
 };
 
@@ -84,7 +100,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-// KMODE 0: natural K order (c,i,j), per-element decode (any C/g).  KMODE 1: K order (i,j,c), C/g % 4 == 0.
+// KMODE 0: natural K order (c,i,j), per-element decode (any C/g).
+// KMODE 1 (C/g % 4 == 0): K order (c/4, i, j, c%4): a 16-byte chunk = 4 channels of one tap (one bounds check),
+// and the kh*kw taps of a channel block are consecutive chunks, so their overlapping pixel windows hit in L1
+// instead of re-reading L2 kh*kw times.
 template <int N_TILE, bool SPLIT, int KMODE>
 __global__ void __launch_bounds__(FW_THREADS, 1)
 igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap map_hi,
@@ -105,24 +124,41 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 128 + 1);   // 128 A-producer threads + the TMA thread's expect_tx arrive
+      mbar_init(bar_full + 8 * s, 256 + 1);   // 256 A-producer threads + the TMA thread's expect_tx arrive
       mbar_init(bar_empty + 8 * s, 1);        // one tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 2 * N_TILE);
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+  // gather table (identical for every tile): element offset inside one image's group slab + tap offsets
+  {
+    int2* tab = reinterpret_cast<int2*>(sptr + S::TAB_OFF);
+    const int HWi = p.H * p.W;
+    const int entries = KMODE == 1 ? p.Kp / 4 : p.Kp;
+    for (int e = tid; e < entries; e += FW_THREADS) {
+      int2 t = make_int2(INT_MIN, 0);
+      const int k = KMODE == 1 ? e * 4 : e;
+      if (k < p.K) {
+        int c, i, j;
+        if (KMODE == 1) { const int taps = p.kh * p.kw; const int cb = k / (4 * taps); const int tap = (k - cb * 4 * taps) >> 2;
+                          c = cb * 4; i = tap / p.kw; j = tap - i * p.kw; }
+        else { c = k / (p.kh * p.kw); const int tap = k - c * p.kh * p.kw; i = tap / p.kw; j = tap - i * p.kw; }
+        t.x = c * HWi + i * p.dh * p.W + j * p.dw;
+        t.y = (i * p.dh) | ((j * p.dw) << 16);
+      }
+      tab[e] = t;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr uint32_t LBO_A = tile_lbo(128);
-  // stage layout: [B_hi | B_lo | A_hi | A_lo]  (B first: 1024-aligned)
+  // smem stage layout: [B_hi | B_lo], 1024-aligned; A stages are TMEM columns
   auto stage_b_hi = [&](int s) { return sbase + s * S::STAGE; };
   auto stage_b_lo = [&](int s) { return sbase + s * S::STAGE + S::B_BYTES; };
-  auto stage_a_hi = [&](int s) { return sbase + s * S::STAGE + S::NP * S::B_BYTES; };
-  auto stage_a_lo = [&](int s) { return stage_a_hi(s) + S::A_BYTES; };
+  auto stage_a_col = [&](int s) { return S::A_COL0 + (uint32_t)s * S::A_COLS; };
 
   auto tile_coords = [&](int tile, int& m0, int& n0, int& g) {
     const int nt = tile % p.n_tiles;
@@ -132,82 +168,99 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     m0 = mt * 128; n0 = nt * N_TILE;
   };
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ================= A producers =====================================================================
+    const int2* tab = reinterpret_cast<const int2*>(sptr + S::TAB_OFF);
     const long long HW = (long long)p.H * p.W;
     const int P = p.Ho * p.Wo;
-    const uint32_t row_off = (uint32_t)tid * 16u;
-    int kbg = 0;   // running k-block counter across tiles (pipeline position)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int m0, n0, g;
-      tile_coords(tile, m0, n0, g);
-      const int m = m0 + tid;
-      const bool mvalid = m < p.Mtot;
-      const int mm = mvalid ? m : 0;
-      const int n = mm / P, pix = mm - n * P;
-      const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
-      const int ih0 = ho * p.sh - p.ph, iw0 = wo * p.sw - p.pw;
-      const float* xrow = p.x + ((long long)n * p.Cin_tot + (long long)g * p.Cg) * HW + (long long)ih0 * p.W + iw0;
-      // decode cursor (advances with the loads)
-      int ki = 0, kj = 0, hoff = 0, woff = 0, kc_ = 0;   // kc_: channel (KMODE 1) / flat k (KMODE 0)
-      long long koff = 0;
+    const int row = tid & 127, half = tid >> 7;            // this thread owns chunks half*4 .. half*4+3
+    const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;   // TMEM lane quarter of this warp; row == (warp&3)*32 + lane
+    const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_blocks = my_tiles * nkb;
+    // load cursor state (row context of the tile the cursor is in)
+    const float* xrow = p.x;
+    int ih0 = 0, iw0 = 0;
+    bool mvalid = false;
+    int lt = 0, lkb = 0;       // cursor: local tile index, k-block inside it
 
-      auto load_block = [&](float (&v)[32]) {
-        if (KMODE == 1) {
-#pragma unroll
-          for (int ch = 0; ch < KCHUNKS; ++ch) {
-            const bool ok = mvalid && ki < p.kh && (unsigned)(ih0 + hoff) < (unsigned)p.H &&
-                            (unsigned)(iw0 + woff) < (unsigned)p.W;
-            const float* src = xrow + koff;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[ch * 4 + e] = ok ? __ldg(src + e * HW) : 0.0f;
-            kc_ += 4; koff += 4 * HW;
-            if (kc_ >= p.Cg) {              // next tap
-              kc_ = 0; koff -= (long long)p.Cg * HW;
-              ++kj; woff += p.dw; koff += p.dw;
-              if (kj == p.kw) { kj = 0; koff -= woff; woff = 0; ++ki; hoff += p.dh; koff += (long long)p.dh * p.W; }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const bool ok = mvalid && kc_ < p.K && (unsigned)(ih0 + hoff) < (unsigned)p.H &&
-                            (unsigned)(iw0 + woff) < (unsigned)p.W;
-            v[e] = ok ? __ldg(xrow + koff) : 0.0f;
-            ++kc_;
-            ++kj; woff += p.dw; koff += p.dw;
-            if (kj == p.kw) {
-              kj = 0; koff -= woff; woff = 0;
-              ++ki; hoff += p.dh; koff += (long long)p.dh * p.W;
-              if (ki == p.kh) { ki = 0; koff -= (long long)hoff * p.W; hoff = 0; koff += HW; }
-            }
-          }
-        }
-      };
-      auto store_block = [&](const float (&v)[32]) {
-        const int s = kbg % STAGES, it = kbg / STAGES;
-        mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
-        const uint32_t a_hi = stage_a_hi(s) + row_off, a_lo = stage_a_lo(s) + row_off;
-#pragma unroll
-        for (int ch = 0; ch < KCHUNKS; ++ch)
-          store_chunk<SPLIT>(a_hi + ch * LBO_A, a_lo + ch * LBO_A, v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * s);
-        ++kbg;
-      };
-
-      float va[32], vb[32];
-      load_block(va);
-      int kb = 0;
-      for (; kb + 2 <= nkb; kb += 2) {
-        load_block(vb);
-        store_block(va);
-        if (kb + 2 < nkb) load_block(va);
-        store_block(vb);
+    auto load_block = [&](float (&v)[16]) {
+      if (lkb == 0) {
+        int m0, n0, g;
+        tile_coords((int)blockIdx.x + lt * (int)gridDim.x, m0, n0, g);
+        const int m = m0 + row;
+        mvalid = m < p.Mtot;
+        const int mm = mvalid ? m : 0;
+        const int n = mm / P, pix = mm - n * P;
+        const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
+        ih0 = ho * p.sh - p.ph; iw0 = wo * p.sw - p.pw;
+        xrow = p.x + ((long long)n * p.Cin_tot + (long long)g * p.Cg) * HW + (long long)ih0 * p.W + iw0;
       }
-      if (kb < nkb) store_block(va);
+      if (p.dbg & 1) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 1.0f;
+      } else if (KMODE == 1) {
+        const int2* te = tab + lkb * KCHUNKS + half * 4;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int2 t = te[ch];
+          const bool ok = mvalid && t.x != INT_MIN && (unsigned)(ih0 + (t.y & 0xffff)) < (unsigned)p.H &&
+                          (unsigned)(iw0 + (t.y >> 16)) < (unsigned)p.W;
+          const float* src = xrow + t.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[ch * 4 + e] = ok ? __ldg(src + e * HW) : 0.0f;
+        }
+      } else {
+        const int2* te = tab + lkb * BK + half * 16;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int2 t = te[e];
+          const bool ok = mvalid && t.x != INT_MIN && (unsigned)(ih0 + (t.y & 0xffff)) < (unsigned)p.H &&
+                          (unsigned)(iw0 + (t.y >> 16)) < (unsigned)p.W;
+          v[e] = ok ? __ldg(xrow + t.x) : 0.0f;
+        }
+      }
+      if (++lkb == nkb) { lkb = 0; ++lt; }
+    };
+    int kbg = 0;   // pipeline position of the store cursor
+    auto store_block = [&](const float (&v)[16]) {
+      const int s = kbg % STAGES, it = kbg / STAGES;
+      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + a_lane + stage_a_col(s) + (uint32_t)(half * 16);
+      if (SPLIT) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) split_tf32(v[e], hi[e], lo[e]);
+        tmem_st16(a_hi, hi);
+        tmem_st16(a_hi + 32, lo);
+      } else {
+        float hi[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) hi[e] = to_tf32(v[e]);
+        tmem_st16(a_hi, hi);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_full + 8 * s);
+      ++kbg;
+    };
+
+    // two K blocks of loads in flight ahead of the block being stored, across tile boundaries
+    float v0[16], v1[16], v2[16];
+    int issued = 0;
+    if (issued < total_blocks) { load_block(v0); ++issued; }
+    if (issued < total_blocks) { load_block(v1); ++issued; }
+    for (int j = 0; j < total_blocks; j += 3) {
+      if (issued < total_blocks) { load_block(v2); ++issued; }
+      store_block(v0);
+      if (j + 1 >= total_blocks) break;
+      if (issued < total_blocks) { load_block(v0); ++issued; }
+      store_block(v1);
+      if (j + 2 >= total_blocks) break;
+      if (issued < total_blocks) { load_block(v1); ++issued; }
+      store_block(v2);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ================= TMA producer (filter operand) ===================================================
     if (lane == 0) {
       int kbg = 0;
@@ -224,14 +277,14 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================= MMA issuer ========================================================================
     if (lane == 0) {
       constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
       int kbg = 0, ti = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-        const int buf = ti & 1;
-        mbar_wait(bar_tempty + 8 * buf, ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        const int buf = ti % S::ACC_BUFS, use = ti / S::ACC_BUFS;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);         // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
         uint32_t acc = 0;
@@ -241,15 +294,15 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t ah = smem_desc(stage_a_hi(s) + 2 * kk * LBO_A, LBO_A, 128);
+            if (p.dbg & 2) break;
+            const uint32_t ah = tmem_base + stage_a_col(s) + (uint32_t)(kk * 8);
             const uint64_t bh = smem_desc_sw128(stage_b_hi(s) + kk * 32);
             if (SPLIT) {
-              const uint64_t al = smem_desc(stage_a_lo(s) + 2 * kk * LBO_A, LBO_A, 128);
               const uint64_t bl = smem_desc_sw128(stage_b_lo(s) + kk * 32);
-              umma_tf32(d_tmem, al, bh, IDESC, acc); acc = 1;
-              umma_tf32(d_tmem, ah, bl, IDESC, 1);
+              umma_tf32_ts(d_tmem, ah + 32, bh, IDESC, acc); acc = 1;   // lo * hi
+              umma_tf32_ts(d_tmem, ah, bl, IDESC, 1);                   // hi * lo
             }
-            umma_tf32(d_tmem, ah, bh, IDESC, acc); acc = 1;
+            umma_tf32_ts(d_tmem, ah, bh, IDESC, acc); acc = 1;          // hi * hi
           }
           umma_commit(bar_empty + 8 * s);
         }
@@ -258,7 +311,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps 6..9 ================================================================
+    // ================= epilogue warps 10..13 ==============================================================
     const int lg = warp & 3;                 // TMEM lane group this warp may access
     const int r = lg * 32 + lane;            // GEMM row inside the tile
     const int P = p.Ho * p.Wo;
@@ -266,7 +319,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       int m0, n0, g;
       tile_coords(tile, m0, n0, g);
-      const int buf = ti & 1;
+      const int buf = ti % S::ACC_BUFS, use = ti / S::ACC_BUFS;
       const int m = m0 + r;
       const bool mvalid = m < p.Mtot;
       const int mm = mvalid ? m : 0;
@@ -275,7 +328,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       float* orow = p.out + ((long long)n * p.Cout_tot + (long long)g * p.Ntot + n0) * p.out_plane +
                     (long long)ho * p.out_hs + (long long)wo * p.out_ws;
       const float* brow = p.bias ? p.bias + (long long)g * p.Ntot + n0 : nullptr;
-      mbar_wait(bar_tfull + 8 * buf, (ti >> 1) & 1);
+      mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
@@ -298,9 +351,9 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * N_TILE);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -327,7 +380,8 @@ filter_prep_kernel(const PrepParams q) {
     if (kp < q.K) {
       const int inner = q.mode == 0 ? q.Cg : q.Og;    // the channel-like axis of K
       int ch, tap;
-      if (q.tap_major) { tap = kp / inner; ch = kp - tap * inner; } else { ch = kp / taps; tap = kp - ch * taps; }
+      if (q.tap_major) { const int cb = kp / (4 * taps); const int r = kp - cb * 4 * taps; tap = r >> 2; ch = cb * 4 + (r & 3); }
+      else { ch = kp / taps; tap = kp - ch * taps; }
       if (q.flip) tap = taps - 1 - tap;
       const int o = q.mode == 0 ? row : ch, c = q.mode == 0 ? ch : row;
       v = __ldg(q.w + (((long long)g * q.Og + o) * q.Cg + c) * taps + tap);
@@ -405,9 +459,10 @@ static int pick_n_tile(int Mtot, int Ntot, int G, int Kp, int math) {
     const int nt = cands[i];
     if (nt > 32 && nt / 2 >= Ntot) continue;   // a smaller tile already covers all columns
     const long long tiles = (long long)((Mtot + 127) / 128) * ((Ntot + nt - 1) / nt) * G;
-    const double mma = (math == B2C_MATH_FP32 ? 1.5 : 0.5) * nt;      // cycles per 32-deep K block
-    const double prod = 420.0;
-    const double per_tile = (Kp / 32) * (mma > prod ? mma : prod) + 10.0 * nt + 1500.0;
+    const double mma = (math == B2C_MATH_FP32 ? 6.0 : 2.0) * nt;      // tensor-pipe cycles per 32-deep K block
+    const double prod = 300.0;                                        // A-producer cycles per K block
+    const double epi = nt == 256 ? 14.0 * nt : 2.0 * nt;              // 256: single accumulator, epilogue exposed
+    const double per_tile = (Kp / 32) * (mma > prod ? mma : prod) + epi + 1000.0;
     const double rounds = (double)((tiles + sm_count() - 1) / sm_count());
     const double cost = rounds * per_tile;
     if (cost < best_cost * 0.97) { best_cost = cost; best = nt; }
@@ -428,8 +483,11 @@ static int padded_k(int K) { return (K + BK - 1) / BK * BK; }
 bool tc_conv_supported(const ConvShape& s, int op) {
   const long long Mtot = (long long)s.N * s.Ho * s.Wo;
   if (Mtot > 0x7fffffffLL || (long long)s.N * s.H * s.W > 0x7fffffffLL) return false;
-  if (op == B2C_OP_FORWARD) return true;
-  if (op == B2C_OP_BACKWARD_DATA) return dgrad_as_fwd(s) || dgrad_scatter(s);
+  if ((long long)s.C * s.H * s.W >= 0x7fffffffLL || (long long)s.O * s.Ho * s.Wo >= 0x7fffffffLL) return false;
+  if ((s.kh - 1) * s.dh > 0x7fff || (s.kw - 1) * s.dw > 0x7fff) return false;
+  auto table_fits = [](int K, int chan) { const int Kp = (K + 31) / 32 * 32; return (chan % 4 == 0 ? Kp / 4 : Kp) <= TAB_ENTRIES; };
+  if (op == B2C_OP_FORWARD) return table_fits(s.Kd, s.Cg);
+  if (op == B2C_OP_BACKWARD_DATA) return (dgrad_as_fwd(s) || dgrad_scatter(s)) && table_fits(s.Og * s.kh * s.kw, s.Og);
   return tc_wgrad_supported(s);
 }
 
@@ -481,6 +539,7 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
     }
   }
   p.Kp = padded_k(p.K);
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2C_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   const int kmode = (p.Cg % 4 == 0) ? 1 : 0;
   q.tap_major = kmode; q.K = p.K; q.Kp = p.Kp;
   const size_t plane = (size_t)s.G * q.rows * p.Kp;
@@ -489,7 +548,9 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
   filter_prep_kernel<<<grid_for(plane, 256), 256, 0, st>>>(q);
   B2C_POST_LAUNCH();
 
-  const int n_tile = pick_n_tile(p.Mtot, p.Ntot, s.G, p.Kp, math);
+  int n_tile = pick_n_tile(p.Mtot, p.Ntot, s.G, p.Kp, math);
+  { static int force = -1; if (force < 0) { const char* e = getenv("B2C_NTILE"); force = e ? atoi(e) : 0; }
+    if (force && force / 2 < p.Ntot) n_tile = force; }
   p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (p.Ntot + n_tile - 1) / n_tile; p.G = s.G;
   p.total_tiles = p.m_tiles * p.n_tiles * p.G;
   alignas(64) CUtensorMap mh, ml;

@@ -154,24 +154,32 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
       if (kb < nkb) store_block(kb, va);
     }
-    // ================= epilogue ========================================================================
+    // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced row stores ===========
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
-    const int o = m0 + tid;
-    const bool ovalid = o < p.Og;
-    float* orow = p.out + (p.splits > 1 ? (long long)split * p.O * p.Kd : 0LL) +
-                  ((long long)g * p.Og + (ovalid ? o : 0)) * p.Kd + n0;
+    // all MMAs have completed, so the pipeline stages are free: each warp uses a private 32 x 33 fp32 pad
+    float* tpad = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    float* obase = p.out + (p.splits > 1 ? (long long)split * p.O * p.Kd : 0LL) + ((long long)g * p.Og + m0 + warp * 32) * p.Kd + n0;
+    const int rows_valid = p.Og - (m0 + warp * 32);       // rows of this warp's 32 that exist
     const bool accumulate = p.splits == 1;
 #pragma unroll 1
     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
       if (n0 + c0 >= p.Kd) break;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (ovalid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < p.Kd) orow[c0 + j] = accumulate ? orow[c0 + j] + v[j] : v[j];
+      for (int j = 0; j < 32; ++j) tpad[lane * 33 + j] = v[j];     // row = lane, conflict-free (stride 33)
+      __syncwarp();
+      const bool colok = n0 + c0 + lane < p.Kd;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        if (r < rows_valid && colok) {
+          float* dst = obase + (long long)r * p.Kd + c0 + lane;     // 32 lanes -> 128 contiguous bytes
+          const float t = tpad[r * 33 + lane];
+          *dst = accumulate ? *dst + t : t;
+        }
       }
+      __syncwarp();
     }
     tc_fence_before();
   } else if (warp < 12) {
@@ -300,7 +308,9 @@ static WgradPlan wgrad_plan(const ConvShape& s) {
   const long long Q = (long long)s.N * s.Ho * s.Wo;
   const long long nkb = (Q + BK - 1) / BK;
   const long long mn = (long long)((s.Og + 127) / 128) * ((s.Kd + pl.n_tile - 1) / pl.n_tile) * s.G;
-  long long splits = (2LL * sm_count() + mn - 1) / mn;
+  // one wave: every CTA pays a fixed prologue + epilogue (partial tile write), so fewer, longer CTAs win;
+  // never exceed the SM count (a partial second wave costs a full CTA time)
+  long long splits = sm_count() / mn;
   const long long max_splits = nkb / 8 > 0 ? nkb / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -103,17 +103,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns (thread t writes lane base+t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: A operand read from tensor memory (rows = lanes, K along columns)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // ---- TF32 split ------------------------------------------------------------------------------------
-// hi = rn_tf32(a); lo = rn_tf32(a - hi).  a - hi is exact in fp32; hi*hi' + hi*lo' + lo*hi' carries
-// ~2^-21 relative error per product, i.e. fp32-class accuracy on the TF32 tensor pipe.
+// fp32-equivalent mode: hi = a with the 13 low mantissa bits cleared (exactly a TF32 value), lo = a - hi
+// (exact in fp32, |lo| < 2^-10 |a|; the tensor core reads its top 19 bits).  hi*hi' + hi*lo' + lo*hi'
+// then carries ~2^-20 relative error per product -- fp32-class accuracy on the TF32 pipe for two ALU
+// ops per element (cvt.rna.tf32 runs at 1/4 rate and made the producers conversion-bound).
+// TF32 mode: round-to-nearest (ties away) on the integer pipe: (bits + 0x1000) & ~0x1fff.
 __device__ __forceinline__ float to_tf32(float a) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
-  hi = to_tf32(a);
-  lo = to_tf32(a - hi);
+  hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+  lo = a - hi;
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
