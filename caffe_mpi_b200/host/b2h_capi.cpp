@@ -1,0 +1,193 @@
+// b2h_capi.cpp -- flat C entry points over the C++ host layer, used by tests/ and bench.py through ctypes.
+// (The C++ classes in b2caffe.hpp are the interface a Caffe maintainer codes against; this file only
+// marshals arrays so Python can drive them.)  Every function returns 0 / a handle, or -1 / NULL with the
+// message available from b2h_last_error().
+#include <cstring>
+#include <memory>
+#include "b2caffe.hpp"
+
+using namespace caffe;
+
+static thread_local std::string g_err;
+#define B2H_TRY(body)                          \
+  try { body; return 0; }                      \
+  catch (const std::exception& e) { g_err = e.what(); return -1; }
+
+struct ConvHandle {
+  shared_ptr<LayerBase> layer;
+  Blob bottom, top;
+  bool set_up = false;
+};
+struct SolverHandle {
+  std::unique_ptr<SGDSolver> solver;
+  vector<shared_ptr<Blob>> params;
+  std::unique_ptr<P2PSync> sync;
+  std::unique_ptr<ReduceScheduler> sched;
+};
+
+extern "C" {
+
+const char* b2h_last_error() { return g_err.c_str(); }
+
+int b2h_registry_has(const char* type) {
+  for (auto& t : LayerRegistry::LayerTypeList()) if (t == type) return 1;
+  return 0;
+}
+
+// ---- ConvolutionLayer through LayerRegistry::CreateLayer --------------------------------------------------
+void* b2h_conv_create(int num_output, int bias_term, int nk, const int* kernel, int ns, const int* stride, int np, const int* pad,
+                      int nd, const int* dilation, int group, int engine, int math, int force_nd) {
+  try {
+    LayerParameter lp;
+    lp.name = "conv"; lp.type = "Convolution";
+    ConvolutionParameter& c = lp.convolution_param;
+    c.num_output = num_output; c.bias_term = bias_term != 0; c.group = group; c.engine = engine; c.math = math;
+    c.force_nd_im2col = force_nd != 0;
+    c.kernel_size.assign(kernel, kernel + nk);
+    c.stride.assign(stride, stride + ns);
+    c.pad.assign(pad, pad + np);
+    c.dilation.assign(dilation, dilation + nd);
+    c.weight_filler.type = "gaussian"; c.weight_filler.std = 0.01f;
+    c.bias_filler.type = "constant"; c.bias_filler.value = 0.1f;
+    auto* h = new ConvHandle;
+    h->layer = LayerRegistry::CreateLayer(lp);
+    return h;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+int b2h_conv_setup(void* hv, int naxes, const int* bottom_shape) {
+  auto* h = static_cast<ConvHandle*>(hv);
+  B2H_TRY({
+    h->bottom.Reshape(vector<int>(bottom_shape, bottom_shape + naxes));
+    h->layer->SetUp({&h->bottom}, {&h->top});
+    h->set_up = true;
+  });
+}
+int b2h_conv_top_shape(void* hv, int* naxes, int* shape) {
+  auto* h = static_cast<ConvHandle*>(hv);
+  *naxes = h->top.num_axes();
+  for (int i = 0; i < h->top.num_axes(); ++i) shape[i] = h->top.shape(i);
+  return 0;
+}
+int b2h_conv_num_blobs(void* hv) { return (int)static_cast<ConvHandle*>(hv)->layer->blobs().size(); }
+long long b2h_conv_blob_count(void* hv, int i) { return (long long)static_cast<ConvHandle*>(hv)->layer->blobs()[i]->count(); }
+int b2h_conv_set_blob(void* hv, int i, int diff, const float* src) {
+  auto* h = static_cast<ConvHandle*>(hv);
+  B2H_TRY({
+    Blob& b = *h->layer->blobs()[i];
+    memcpy(diff ? b.mutable_cpu_diff() : b.mutable_cpu_data(), src, sizeof(float) * b.count());
+  });
+}
+int b2h_conv_get_blob(void* hv, int i, int diff, float* dst) {
+  auto* h = static_cast<ConvHandle*>(hv);
+  B2H_TRY({
+    Blob& b = *h->layer->blobs()[i];
+    memcpy(dst, diff ? b.cpu_diff() : b.cpu_data(), sizeof(float) * b.count());
+  });
+}
+int b2h_conv_forward(void* hv, const float* x, float* y) {
+  auto* h = static_cast<ConvHandle*>(hv);
+  B2H_TRY({
+    memcpy(h->bottom.mutable_cpu_data(), x, sizeof(float) * h->bottom.count());
+    h->layer->Forward({&h->bottom}, {&h->top});
+    memcpy(y, h->top.cpu_data(), sizeof(float) * h->top.count());
+  });
+}
+int b2h_conv_backward(void* hv, const float* dy, float* dx, int propagate_down) {
+  auto* h = static_cast<ConvHandle*>(hv);
+  B2H_TRY({
+    memcpy(h->top.mutable_cpu_diff(), dy, sizeof(float) * h->top.count());
+    h->layer->Backward({&h->top}, {propagate_down != 0}, {&h->bottom});
+    if (dx && propagate_down) memcpy(dx, h->bottom.cpu_diff(), sizeof(float) * h->bottom.count());
+    else CUDA_CHECK(cudaStreamSynchronize(Caffe::thread_stream()));
+  });
+}
+int b2h_conv_algo_used(void* hv, int op) {
+  auto* c = dynamic_cast<ConvolutionLayer*>(static_cast<ConvHandle*>(hv)->layer.get());
+  return c ? c->algo_used(op) : -1;
+}
+void b2h_conv_destroy(void* hv) { delete static_cast<ConvHandle*>(hv); }
+
+// ---- solver / scheduler ---------------------------------------------------------------------------------------
+void* b2h_solver_create(float base_lr, const char* lr_policy, float gamma, float power, int stepsize, int max_iter,
+                        float momentum, float weight_decay, const char* reg_type, int iter_size, int reduce_buckets,
+                        int nstep, const int* stepvalue, int rampup_interval, float rampup_lr, float min_lr) {
+  SolverParameter p;
+  p.base_lr = base_lr; p.lr_policy = lr_policy; p.gamma = gamma; p.power = power; p.stepsize = stepsize; p.max_iter = max_iter;
+  p.momentum = momentum; p.weight_decay = weight_decay; p.regularization_type = reg_type; p.iter_size = iter_size;
+  p.reduce_buckets = reduce_buckets; p.rampup_interval = rampup_interval; p.rampup_lr = rampup_lr; p.min_lr = min_lr;
+  if (nstep) p.stepvalue.assign(stepvalue, stepvalue + nstep);
+  auto* h = new SolverHandle;
+  h->solver.reset(new SGDSolver(p));
+  return h;
+}
+void b2h_solver_destroy(void* hv) { delete static_cast<SolverHandle*>(hv); }
+float b2h_solver_lr_at(void* hv, int iter) {
+  auto* h = static_cast<SolverHandle*>(hv);
+  try { h->solver->set_iter(iter); return h->solver->GetLearningRate(); } catch (const std::exception& e) { g_err = e.what(); return -1.f; }
+}
+// bucket plan over a layout of `n` params with the given element counts (no device memory needed)
+int b2h_plan_buckets(int n, const size_t* counts, int reduce_buckets, int max_out, int* id_from, int* id_to, size_t* offset, size_t* count) {
+  try {
+    ParamArena a;
+    a.InitLayout(vector<size_t>(counts, counts + n));
+    vector<Bucket> b = PlanBuckets(a, reduce_buckets);
+    for (int i = 0; i < (int)b.size() && i < max_out; ++i) { id_from[i] = b[i].id_from; id_to[i] = b[i].id_to; offset[i] = b[i].offset; count[i] = b[i].count; }
+    return (int)b.size();
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int b2h_divide_batch_size(int total, int solver_count) { return P2PSync::divide_batch_size(total, solver_count); }
+
+int b2h_solver_set_params(void* hv, int n, const size_t* counts, const float* lr_mult, const float* decay_mult) {
+  auto* h = static_cast<SolverHandle*>(hv);
+  B2H_TRY({
+    vector<ParamSpec> specs(n);
+    h->params.clear();
+    for (int i = 0; i < n; ++i) {
+      h->params.emplace_back(new Blob(vector<int>{(int)counts[i]}));
+      specs[i].lr_mult = lr_mult[i]; specs[i].decay_mult = decay_mult[i];
+    }
+    h->solver->SetParams(h->params, specs);
+  });
+}
+int b2h_solver_set(void* hv, int i, int diff, const float* src) {
+  auto* h = static_cast<SolverHandle*>(hv);
+  B2H_TRY({
+    Blob& b = *h->params[i];
+    CUDA_CHECK(cudaMemcpy(diff ? b.mutable_gpu_diff() : b.mutable_gpu_data(), src, sizeof(float) * b.count(), cudaMemcpyHostToDevice));
+  });
+}
+int b2h_solver_get(void* hv, int i, int what, float* dst) {   // what: 0 data, 1 diff, 2 history
+  auto* h = static_cast<SolverHandle*>(hv);
+  B2H_TRY({
+    Blob& b = *h->params[i];
+    CUDA_CHECK(cudaDeviceSynchronize());
+    const float* src = what == 0 ? b.gpu_data() : what == 1 ? b.gpu_diff() : h->solver->arena().history() + h->solver->arena().offset(i);
+    CUDA_CHECK(cudaMemcpy(dst, src, sizeof(float) * b.count(), cudaMemcpyDeviceToHost));
+  });
+}
+// multi-GPU: rank 0 fills `id` (128 B) when create_id != 0; every rank then passes the same bytes
+int b2h_solver_attach_sync(void* hv, int nranks, int rank, unsigned char* id, int create_id) {
+  auto* h = static_cast<SolverHandle*>(hv);
+  B2H_TRY({
+    if (create_id) { B2C_CHECK(b2c_comm_get_unique_id(id)); return 0; }
+    // the launcher has already carried rank 0's id to every rank: the bcast hook only hands it over
+    unsigned char* idp = id;
+    // P2PSync asks rank 0 for a fresh id and then "broadcasts"; here the broadcast overwrites with the carried id
+    h->sync.reset(new P2PSync(nranks, rank, [idp](void* buf, size_t bytes, int) { memcpy(buf, idp, bytes); }));
+    h->sync->on_start(h->solver->arena());
+  });
+}
+// one iteration of the reduce-and-update schedule: params become ready last-to-first on the thread stream
+int b2h_solver_step(void* hv) {
+  auto* h = static_cast<SolverHandle*>(hv);
+  B2H_TRY({
+    if (!h->sched) h->sched.reset(new ReduceScheduler(h->solver.get(), h->sync.get()));
+    cudaStream_t st = Caffe::thread_stream();
+    for (int i = (int)h->params.size() - 1; i >= 0; --i) h->sched->on_param_ready(i, st);
+    h->sched->end_of_iteration(st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+int b2h_solver_iter(void* hv) { return static_cast<SolverHandle*>(hv)->solver->iter(); }
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""ctypes binding of the flat C test/driver API (host/b2h_capi.cpp) over the C++ host layer libb2caffe.so."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libb2caffe.so")
+_lib = None
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        capi.lib()   # libb2c.so first (RTLD_GLOBAL)
+        if not os.path.exists(_SO):
+            raise HostError(f"{_SO} missing: run __graft_entry__.build()")
+        L = C.CDLL(_SO)
+        i, vp, f, ip = C.c_int, C.c_void_p, C.c_float, C.POINTER(C.c_int)
+        szp = C.POINTER(C.c_size_t)
+        L.b2h_last_error.restype = C.c_char_p
+        L.b2h_registry_has.argtypes = [C.c_char_p]
+        L.b2h_conv_create.restype = vp
+        L.b2h_conv_create.argtypes = [i, i, i, ip, i, ip, i, ip, i, ip, i, i, i, i]
+        L.b2h_conv_setup.argtypes = [vp, i, ip]
+        L.b2h_conv_top_shape.argtypes = [vp, ip, ip]
+        L.b2h_conv_num_blobs.argtypes = [vp]
+        L.b2h_conv_blob_count.argtypes = [vp, i]
+        L.b2h_conv_blob_count.restype = C.c_longlong
+        L.b2h_conv_set_blob.argtypes = [vp, i, i, _f32]
+        L.b2h_conv_get_blob.argtypes = [vp, i, i, _f32]
+        L.b2h_conv_forward.argtypes = [vp, _f32, _f32]
+        L.b2h_conv_backward.argtypes = [vp, _f32, vp, i]
+        L.b2h_conv_algo_used.argtypes = [vp, i]
+        L.b2h_conv_destroy.argtypes = [vp]
+        L.b2h_solver_create.restype = vp
+        L.b2h_solver_create.argtypes = [f, C.c_char_p, f, f, i, i, f, f, C.c_char_p, i, i, i, ip, i, f, f]
+        L.b2h_solver_destroy.argtypes = [vp]
+        L.b2h_solver_lr_at.argtypes = [vp, i]
+        L.b2h_solver_lr_at.restype = f
+        L.b2h_plan_buckets.argtypes = [i, szp, i, i, ip, ip, szp, szp]
+        L.b2h_divide_batch_size.argtypes = [i, i]
+        L.b2h_solver_set_params.argtypes = [vp, i, szp, C.POINTER(f), C.POINTER(f)]
+        L.b2h_solver_set.argtypes = [vp, i, i, _f32]
+        L.b2h_solver_get.argtypes = [vp, i, i, _f32]
+        L.b2h_solver_attach_sync.argtypes = [vp, i, i, C.c_char_p, i]
+        L.b2h_solver_step.argtypes = [vp]
+        L.b2h_solver_iter.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise HostError(lib().b2h_last_error().decode())
+
+
+def _ia(v):
+    return (C.c_int * len(v))(*[int(a) for a in v])
+
+
+class ConvolutionLayer:
+    """caffe::ConvolutionLayer created through LayerRegistry::CreateLayer({type: "Convolution"})."""
+
+    def __init__(self, num_output, kernel, stride=(), pad=(), dilation=(), group=1, bias_term=True,
+                 engine=capi.ENGINE_DEFAULT, math=capi.MATH_FP32, force_nd=False):
+        as_list = lambda v: [v] if isinstance(v, int) else list(v)
+        k, s, p, d = as_list(kernel), as_list(stride), as_list(pad), as_list(dilation)
+        self._h = lib().b2h_conv_create(num_output, int(bias_term), len(k), _ia(k), len(s), _ia(s), len(p), _ia(p), len(d), _ia(d),
+                                        group, engine, math, int(force_nd))
+        if not self._h:
+            raise HostError(lib().b2h_last_error().decode())
+
+    def setup(self, bottom_shape):
+        _ck(lib().b2h_conv_setup(self._h, len(bottom_shape), _ia(bottom_shape)))
+        self.bottom_shape = tuple(bottom_shape)
+        n, shp = C.c_int(), (C.c_int * 16)()
+        lib().b2h_conv_top_shape(self._h, C.byref(n), shp)
+        self.top_shape = tuple(shp[i] for i in range(n.value))
+        return self.top_shape
+
+    def num_blobs(self):
+        return lib().b2h_conv_num_blobs(self._h)
+
+    def set_blob(self, i, arr, diff=False):
+        _ck(lib().b2h_conv_set_blob(self._h, i, int(diff), np.ascontiguousarray(arr, np.float32).reshape(-1)))
+
+    def get_blob(self, i, diff=False):
+        out = np.empty(lib().b2h_conv_blob_count(self._h, i), np.float32)
+        _ck(lib().b2h_conv_get_blob(self._h, i, int(diff), out))
+        return out
+
+    def forward(self, x):
+        y = np.empty(self.top_shape, np.float32)
+        _ck(lib().b2h_conv_forward(self._h, np.ascontiguousarray(x, np.float32).reshape(-1), y.reshape(-1)))
+        return y
+
+    def backward(self, dy, propagate_down=True):
+        dx = np.empty(self.bottom_shape, np.float32) if propagate_down else None
+        _ck(lib().b2h_conv_backward(self._h, np.ascontiguousarray(dy, np.float32).reshape(-1),
+                                    dx.ctypes.data_as(C.c_void_p) if dx is not None else None, int(propagate_down)))
+        return dx
+
+    def algo_used(self, op):
+        return lib().b2h_conv_algo_used(self._h, op)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.b2h_conv_destroy(self._h)
+            self._h = None
+
+
+class SGDSolver:
+    def __init__(self, base_lr=0.01, lr_policy="fixed", gamma=0.1, power=1.0, stepsize=1, max_iter=1, momentum=0.0,
+                 weight_decay=0.0, regularization_type="L2", iter_size=1, reduce_buckets=6, stepvalue=(), rampup_interval=0,
+                 rampup_lr=0.0, min_lr=0.0):
+        sv = list(stepvalue)
+        self._h = lib().b2h_solver_create(base_lr, lr_policy.encode(), gamma, power, stepsize, max_iter, momentum, weight_decay,
+                                          regularization_type.encode(), iter_size, reduce_buckets, len(sv), _ia(sv) if sv else None,
+                                          rampup_interval, rampup_lr, min_lr)
+
+    def lr_at(self, it):
+        v = lib().b2h_solver_lr_at(self._h, it)
+        if v < 0:
+            raise HostError(lib().b2h_last_error().decode())
+        return float(v)
+
+    def set_params(self, counts, lr_mult=None, decay_mult=None):
+        n = len(counts)
+        lr = lr_mult or [1.0] * n
+        dc = decay_mult or [1.0] * n
+        _ck(lib().b2h_solver_set_params(self._h, n, (C.c_size_t * n)(*counts), (C.c_float * n)(*lr), (C.c_float * n)(*dc)))
+        self.counts = list(counts)
+
+    def set(self, i, arr, diff=False):
+        _ck(lib().b2h_solver_set(self._h, i, int(diff), np.ascontiguousarray(arr, np.float32).reshape(-1)))
+
+    def get(self, i, what=0):
+        out = np.empty(self.counts[i], np.float32)
+        _ck(lib().b2h_solver_get(self._h, i, what, out))
+        return out
+
+    def new_unique_id(self):
+        buf = C.create_string_buffer(128)
+        _ck(lib().b2h_solver_attach_sync(self._h, 1, 0, buf, 1))
+        return buf.raw
+
+    def attach_sync(self, nranks, rank, id_bytes):
+        buf = C.create_string_buffer(bytes(id_bytes), 128)
+        _ck(lib().b2h_solver_attach_sync(self._h, nranks, rank, buf, 0))
+
+    def step(self):
+        _ck(lib().b2h_solver_step(self._h))
+
+    def iter(self):
+        return lib().b2h_solver_iter(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.b2h_solver_destroy(self._h)
+            self._h = None
+
+
+def plan_buckets(counts, reduce_buckets=6):
+    n = len(counts)
+    mx = n + 1
+    f, t = (C.c_int * mx)(), (C.c_int * mx)()
+    off, cnt = (C.c_size_t * mx)(), (C.c_size_t * mx)()
+    nb = lib().b2h_plan_buckets(n, (C.c_size_t * n)(*counts), reduce_buckets, mx, f, t, off, cnt)
+    if nb < 0:
+        raise HostError(lib().b2h_last_error().decode())
+    return [(f[i], t[i], off[i], cnt[i]) for i in range(nb)]
+
+
+def divide_batch_size(total, solver_count):
+    return lib().b2h_divide_batch_size(total, solver_count)
