@@ -220,9 +220,28 @@ def run_ours(args):
     offs = [s_[0] for s_ in segs]; cnts = [s_[1] for s_ in segs]
     rates = [lr] * len(segs); decays = [wd] * len(segs)
     comm_stream = torch.cuda.Stream(device=dev, priority=-1)
-    ev_bwd_done = torch.cuda.Event()
     ev_upd_done = torch.cuda.Event()
     timers = {"fwd": [], "wgrad": [], "dgrad": [], "sgd": []}
+    # Net::ReduceAndUpdate's bucketing (net.cpp:824-862) over the arena, planned by the C++ host layer: params
+    # become ready last-to-first during backward; a bucket is exchanged + updated as soon as its lowest id is done
+    from caffe_mpi_b200 import host_api
+    buckets = host_api.plan_buckets(cnts, 6) if world > 1 else [(0, len(segs) - 1, 0, arena_n)]
+    seg_of_conv = {}            # conv index -> lowest segment id it owns
+    si = 0
+    for ci, c in enumerate(convs):
+        seg_of_conv[ci] = si
+        si += 2 if c["b_off"] is not None else 1
+    bucket_events = [torch.cuda.Event() for _ in buckets]
+
+    def flush_bucket(bi, cur):
+        f, t, off_, cnt_ = buckets[bi]
+        bucket_events[bi].record(cur)
+        side = comm_stream if comm is not None else cur
+        if comm is not None:
+            comm_stream.wait_event(bucket_events[bi])
+            comm.allreduce_sum(Gd[off_:off_ + cnt_], stream=comm_stream)
+        capi.sgd_update_arena(offs[f:t + 1], cnts[f:t + 1], rates[f:t + 1], decays[f:t + 1], Gd, Wd, Hd, momentum, l2=True,
+                              grad_scale=1.0 / world, clear_grads=True, stream=side)
 
     def step(e2e=False, timed=False):
         cur = torch.cuda.current_stream()
@@ -239,6 +258,10 @@ def run_ours(args):
             b = torch.cuda.Event(enable_timing=True); b.record(cur); timers[tok[0]].append((tok[1], b))
         for c in convs:
             t = rec("fwd"); c["desc"].forward(c["x"], c["w"], c["b"], Y); end(t)
+        nb = 0
+        # the fc / BN parameters (last segment) have no conv math here: their (zero) diffs are ready at once
+        while nb < len(buckets) and buckets[nb][0] >= len(segs) - 1 and world > 1:
+            flush_bucket(nb, cur); nb += 1
         for i in range(len(convs) - 1, -1, -1):
             c = convs[i]
             t = rec("wgrad"); c["desc"].backward_filter(c["x"], DY, c["dw"]); end(t)
@@ -246,19 +269,16 @@ def run_ours(args):
                 c["desc"].backward_bias(DY, c["db"])
             if i > 0:                           # conv1's bottom is data: propagate_down = false (net.cpp:183-191)
                 t = rec("dgrad"); c["desc"].backward_data(DY, c["w"], DX); end(t)
-        ev_bwd_done.record(cur)
-        upd_stream = comm_stream if comm is not None else cur
-        if comm is not None:
-            comm_stream.wait_event(ev_bwd_done)
-            comm.allreduce_sum(Gd, stream=comm_stream)
-        with torch.cuda.stream(upd_stream):
-            t = None
-            if timed and comm is None:
-                t = rec("sgd")
-            capi.sgd_update_arena(offs, cnts, rates, decays, Gd, Wd, Hd, momentum, l2=True,
-                                  grad_scale=1.0 / world, clear_grads=True, stream=upd_stream)
-            end(t)
-        ev_upd_done.record(upd_stream)
+            if world > 1:
+                while nb < len(buckets) and seg_of_conv[i] <= buckets[nb][0]:
+                    flush_bucket(nb, cur); nb += 1
+        if world > 1:
+            while nb < len(buckets):
+                flush_bucket(nb, cur); nb += 1
+            ev_upd_done.record(comm_stream)
+        else:
+            t = rec("sgd"); flush_bucket(0, cur); end(t)
+            ev_upd_done.record(cur)
         if e2e:
             cur.wait_event(ev_upd_done)
             host_out.copy_(Wd[:1], non_blocking=True)   # device->host read of a step result
@@ -312,7 +332,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{MODEL}: 53 conv layers fwd+bwd (N={N}/GPU, 224x224) + "
-                                   f"{'NCCL allreduce of the %.1f MB diff arena + ' % (arena_n * 4 / 1e6) if world > 1 else ''}"
+                                   f"{'bucketed NCCL allreduce of the %.1f MB diff arena overlapped with backward + ' % (arena_n * 4 / 1e6) if world > 1 else ''}"
                                    "fused SGD update of 25.56M params; non-conv layers not in the timed region",
                        "per_gpu_batch": N, "global_batch": N * world, "parallelism": f"dp{world}",
                        "math": "fp32 (3xTF32 tcgen05) / fp32 SIMT", "algos_used": algo,

@@ -124,10 +124,11 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 256 + 1);   // 256 A-producer threads + the TMA thread's expect_tx arrive
+      mbar_init(bar_full + 8 * s, 8 + 1);     // one elected arrive per A-producer warp + the TMA thread's expect_tx arrive
+                                              // (256 same-address arrivals per stage serialised the pipeline)
       mbar_init(bar_empty + 8 * s, 1);        // one tcgen05.commit
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -241,7 +242,8 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_full + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
       ++kbg;
     };
 
@@ -270,6 +272,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES, it = kbg / STAGES;
           mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+          if (p.dbg & 8) { mbar_arrive(bar_full + 8 * s); continue; }
           mbar_arrive_expect_tx(bar_full + 8 * s, S::TX_BYTES);
           tma_load_3d(stage_b_hi(s), &map_hi, bar_full + 8 * s, kb * BK, n0, g);
           if (SPLIT) tma_load_3d(stage_b_lo(s), &map_lo, bar_full + 8 * s, kb * BK, n0, g);
@@ -335,7 +338,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         if (n0 + c0 >= p.Ntot) break;   // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N_TILE + c0), v);
-        if (mvalid) {
+        if (mvalid && !(p.dbg & 4)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (n0 + c0 + j < p.Ntot) {
@@ -347,7 +350,8 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
   }
   __syncthreads();

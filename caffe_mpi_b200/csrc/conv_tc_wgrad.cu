@@ -66,7 +66,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int nkb = (int)(kb_end - kb_begin);           // >= 1 by construction
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 128 + 256); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 4 + 8); mbar_init(bar_empty + 8 * s, 1); }   // one elected arrive per producer warp
     mbar_init(bar_tmem, 1);
     fence_barrier_init();
   }
@@ -140,7 +140,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
         store_chunk<SPLIT>(a_hi + row * 16, a_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
       }
       fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
     };
     {
       float va[32], vb[32];
@@ -243,7 +244,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
         store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
       }
       fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
     };
     {
       float va[RB * 4], vb[RB * 4];

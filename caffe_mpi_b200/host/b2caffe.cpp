@@ -315,8 +315,8 @@ void ConvolutionLayer::Forward_gpu(const vector<Blob*>& bottom, const vector<Blo
   for (size_t i = 0; i < bottom.size(); ++i) {       // several bottom/top pairs share one weight set
     if (desc_) {
       const size_t need = b2c_conv_workspace_bytes(desc_, B2C_OP_FORWARD);
-      B2C_CHECK(b2c_conv_forward(desc_, bottom[i]->gpu_data(), w, b, top[i]->mutable_gpu_data(), need ? workspace(need) : nullptr,
-                                 ws_bytes_, st));
+      void* ws = need ? workspace(need) : nullptr;     // (sequenced before ws_bytes_ is read)
+      B2C_CHECK(b2c_conv_forward(desc_, bottom[i]->gpu_data(), w, b, top[i]->mutable_gpu_data(), ws, ws_bytes_, st));
       continue;
     }
     // N-D path: the literal per-image im2col_nd + GEMM of base_conv_layer.hpp:105-128
@@ -360,12 +360,13 @@ void ConvolutionLayer::Backward_gpu(const vector<Blob*>& top, const vector<bool>
       if (bias_term_ && param_propagate_down_[1]) B2C_CHECK(b2c_conv_backward_bias(desc_, dy, blobs_[1]->mutable_gpu_diff(), st));
       if (param_propagate_down_[0]) {
         const size_t need = b2c_conv_workspace_bytes(desc_, B2C_OP_BACKWARD_FILTER);
-        B2C_CHECK(b2c_conv_backward_filter(desc_, bottom[i]->gpu_data(), dy, blobs_[0]->mutable_gpu_diff(),
-                                           need ? workspace(need) : nullptr, ws_bytes_, st));
+        void* ws = need ? workspace(need) : nullptr;
+        B2C_CHECK(b2c_conv_backward_filter(desc_, bottom[i]->gpu_data(), dy, blobs_[0]->mutable_gpu_diff(), ws, ws_bytes_, st));
       }
       if (propagate_down[i]) {
         const size_t need = b2c_conv_workspace_bytes(desc_, B2C_OP_BACKWARD_DATA);
-        B2C_CHECK(b2c_conv_backward_data(desc_, dy, w, bottom[i]->mutable_gpu_diff(), need ? workspace(need) : nullptr, ws_bytes_, st));
+        void* ws = need ? workspace(need) : nullptr;
+        B2C_CHECK(b2c_conv_backward_data(desc_, dy, w, bottom[i]->mutable_gpu_diff(), ws, ws_bytes_, st));
       }
       continue;
     }
