@@ -10,20 +10,20 @@
 //   dgrad   : the same kernel run on dY with the transposed (+ flipped) filter for stride-1 layers, or
 //             on the top grid with a strided scatter epilogue for 1x1 / stride>1 / pad 0 layers.
 //
-// Kernel anatomy -- persistent, one CTA per SM, 128 x N_TILE output tiles, 448 threads:
-//   warps 0-7  A producers.  Two threads per GEMM row (pixel), each owning four of the eight 16-byte K
+// Kernel anatomy -- persistent, one CTA per SM, 128 x N_TILE output tiles, 704 threads:
+//   warps 0-15 A producers.  Four threads per GEMM row (pixel), each owning two of the eight 16-byte K
 //              chunks of a K block; the im2col gather reads NCHW global memory directly (coalesced along
 //              W) from a per-kernel smem table of chunk offsets (the (c,i,j) decode is the same for every
 //              tile), keeps two K blocks of loads in flight in registers across tile boundaries, splits
 //              to TF32 hi (+ lo) on the ALU pipe and writes its row of the A tile straight into tensor
 //              memory (tcgen05.st, lane = GEMM row).  K is ordered (channel/4, tap, channel%4) when C/g % 4 == 0.
-//   warp  8    TMA producer for the filter operand: a prepass kernel writes the filter in GEMM-K order,
+//   warp  16   TMA producer for the filter operand: a prepass kernel writes the filter in GEMM-K order,
 //              already split into TF32 hi / lo and zero padded to a multiple of 32; cp.async.bulk.tensor
 //              (SWIZZLE_128B) drops [N_TILE x 32] boxes into smem, completion on the stage mbarrier.
-//   warp  9    allocates TMEM and issues tcgen05.mma.kind::tf32 (M=128, N=N_TILE, K=8) with the A operand in
+//   warp  17   allocates TMEM and issues tcgen05.mma.kind::tf32 (M=128, N=N_TILE, K=8) with the A operand in
 //              TENSOR MEMORY (written there by the producers with tcgen05.st) and B from smem: the 3xTF32 mode
 //              is otherwise shared-memory-bandwidth bound (each K step reads A and B three times); tcgen05.commit releases smem stages and publishes finished accumulators.
-//   warps 10-13 epilogue: tcgen05.ld TMEM -> registers -> bias -> coalesced NCHW stores, overlapped with
+//   warps 18-21 epilogue: tcgen05.ld TMEM -> registers -> bias -> coalesced NCHW stores, overlapped with
 //              the next tile's main loop through the double-buffered accumulator.
 // The activation operand is not TMA-staged: with NCHW the GEMM-K axis (c,i,j) is not unit-stride and
 // 7x7 maps have 196-byte channel pitches (TMA needs 16-byte multiples); see DESIGN.md.
@@ -31,13 +31,15 @@
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include "b2c_common.cuh"
 #include "tc_common.cuh"
 
 namespace b2c {
 using namespace tc;
 
-constexpr int FW_THREADS = 448;
+constexpr int NPW = 16;                     // A-producer warps
+constexpr int FW_THREADS = (NPW + 6) * 32;  // + TMA warp, MMA warp, 4 epilogue warps = 704
 constexpr int TAB_ENTRIES = 1152;   // gather table: one entry per K chunk (KMODE 1) or per K element (KMODE 0)
 
 struct FwdParams {
@@ -55,6 +57,7 @@ struct FwdParams {
   long long out_plane;
   const float* bias;  // [G*Ntot] or null
   int m_tiles, n_tiles, G, total_tiles;
+  long long* prof;    // optional cycle counters written by CTA 0 (B2C_PROF=1), else null
   int dbg;            // B2C_DBG experiments: 1 = skip the global gather (producer-side ceiling), 2 = skip the MMAs
 };
 
@@ -124,14 +127,13 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 8 + 1);     // one elected arrive per A-producer warp + the TMA thread's expect_tx arrive
-                                              // (256 same-address arrivals per stage serialised the pipeline)
+      mbar_init(bar_full + 8 * s, NPW + 1);   // one elected arrive per producer warp + the TMA thread's expect_tx
       mbar_init(bar_empty + 8 * s, 1);        // one tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == NPW + 1) tmem_alloc(smem_u32(tmem_slot), 512);
   // gather table (identical for every tile): element offset inside one image's group slab + tap offsets
   {
     int2* tab = reinterpret_cast<int2*>(sptr + S::TAB_OFF);
@@ -169,22 +171,26 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     m0 = mt * 128; n0 = nt * N_TILE;
   };
 
-  if (warp < 8) {
+  if (warp < NPW) {
     // ================= A producers =====================================================================
+    // 16 warps: four threads per GEMM row, each owning two of the eight 16-byte K chunks of every K block.
+    // (A warp is one sequential instruction stream: with 4-8 producer warps the ~170 dependent instructions
+    // per K block and warp, not bandwidth, set the K-block period -- measured ~1450 cycles regardless of
+    // MMA count, tile width or staging path.  More, lighter warps cut that chain to ~60 instructions.)
     const int2* tab = reinterpret_cast<const int2*>(sptr + S::TAB_OFF);
     const long long HW = (long long)p.H * p.W;
     const int P = p.Ho * p.Wo;
-    const int row = tid & 127, half = tid >> 7;            // this thread owns chunks half*4 .. half*4+3
+    const int row = tid & 127, cp = tid >> 7;              // chunk pair 0..3 -> chunks 2cp, 2cp+1 (8 K columns)
     const uint32_t a_lane = (uint32_t)((warp & 3) * 32) << 16;   // TMEM lane quarter of this warp; row == (warp&3)*32 + lane
     const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_blocks = my_tiles * nkb;
-    // load cursor state (row context of the tile the cursor is in)
     const float* xrow = p.x;
     int ih0 = 0, iw0 = 0;
     bool mvalid = false;
-    int lt = 0, lkb = 0;       // cursor: local tile index, k-block inside it
+    int lt = 0, lkb = 0;       // load cursor: local tile index, K block inside it
 
-    auto load_block = [&](float (&v)[16]) {
+    long long pw_load = 0;
+    auto load_block_ = [&](float (&v)[8]) {
       if (lkb == 0) {
         int m0, n0, g;
         tile_coords((int)blockIdx.x + lt * (int)gridDim.x, m0, n0, g);
@@ -198,57 +204,63 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       }
       if (p.dbg & 1) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 1.0f;
+        for (int e = 0; e < 8; ++e) v[e] = 1.0f;
       } else if (KMODE == 1) {
-        const int2* te = tab + lkb * KCHUNKS + half * 4;
+        const int2* te = tab + lkb * KCHUNKS + cp * 2;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int2 t = te[ch];
-          const bool ok = mvalid && t.x != INT_MIN && (unsigned)(ih0 + (t.y & 0xffff)) < (unsigned)p.H &&
-                          (unsigned)(iw0 + (t.y >> 16)) < (unsigned)p.W;
-          const float* src = xrow + t.x;
+        for (int ch = 0; ch < 2; ++ch) {
+          const int2 tt = te[ch];
+          const bool ok = mvalid && tt.x != INT_MIN && (unsigned)(ih0 + (tt.y & 0xffff)) < (unsigned)p.H &&
+                          (unsigned)(iw0 + (tt.y >> 16)) < (unsigned)p.W;
+          const float* src = xrow + tt.x;
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[ch * 4 + e] = ok ? __ldg(src + e * HW) : 0.0f;
         }
       } else {
-        const int2* te = tab + lkb * BK + half * 16;
+        const int2* te = tab + lkb * BK + cp * 8;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int2 t = te[e];
-          const bool ok = mvalid && t.x != INT_MIN && (unsigned)(ih0 + (t.y & 0xffff)) < (unsigned)p.H &&
-                          (unsigned)(iw0 + (t.y >> 16)) < (unsigned)p.W;
-          v[e] = ok ? __ldg(xrow + t.x) : 0.0f;
+        for (int e = 0; e < 8; ++e) {
+          const int2 tt = te[e];
+          const bool ok = mvalid && tt.x != INT_MIN && (unsigned)(ih0 + (tt.y & 0xffff)) < (unsigned)p.H &&
+                          (unsigned)(iw0 + (tt.y >> 16)) < (unsigned)p.W;
+          v[e] = ok ? __ldg(xrow + tt.x) : 0.0f;
         }
       }
       if (++lkb == nkb) { lkb = 0; ++lt; }
     };
+    auto load_block = [&](float (&v)[8]) { const long long a0 = clock64(); load_block_(v); pw_load += clock64() - a0; };
     int kbg = 0;   // pipeline position of the store cursor
-    auto store_block = [&](const float (&v)[16]) {
+    long long pw_empty = 0, pw_store = 0;
+    const long long pt0 = clock64();
+    auto store_block = [&](const float (&v)[8]) {
       const int s = kbg % STAGES, it = kbg / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      const long long t0 = clock64();
+      mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 40);
+      const long long t1 = clock64();
       tc_fence_after();
-      const uint32_t a_hi = tmem_base + a_lane + stage_a_col(s) + (uint32_t)(half * 16);
+      const uint32_t a_hi = tmem_base + a_lane + stage_a_col(s) + (uint32_t)(cp * 8);
       if (SPLIT) {
-        float hi[16], lo[16];
+        float hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) split_tf32(v[e], hi[e], lo[e]);
-        tmem_st16(a_hi, hi);
-        tmem_st16(a_hi + 32, lo);
+        for (int e = 0; e < 8; ++e) split_tf32(v[e], hi[e], lo[e]);
+        tmem_st8(a_hi, hi);
+        tmem_st8(a_hi + 32, lo);
       } else {
-        float hi[16];
+        float hi[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) hi[e] = to_tf32(v[e]);
-        tmem_st16(a_hi, hi);
+        for (int e = 0; e < 8; ++e) hi[e] = to_tf32(v[e]);
+        tmem_st8(a_hi, hi);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
       ++kbg;
+      pw_empty += t1 - t0; pw_store += clock64() - t1;
     };
 
     // two K blocks of loads in flight ahead of the block being stored, across tile boundaries
-    float v0[16], v1[16], v2[16];
+    float v0[8], v1[8], v2[8];
     int issued = 0;
     if (issued < total_blocks) { load_block(v0); ++issued; }
     if (issued < total_blocks) { load_block(v1); ++issued; }
@@ -262,63 +274,88 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       if (issued < total_blocks) { load_block(v1); ++issued; }
       store_block(v2);
     }
-  } else if (warp == 8) {
+    if (p.prof && blockIdx.x == 0 && tid == 0) {
+      p.prof[0] = clock64() - pt0; p.prof[1] = pw_empty; p.prof[2] = pw_store; p.prof[3] = pw_load; p.prof[4] = total_blocks;
+    }
+  } else if (warp == NPW) {
     // ================= TMA producer (filter operand) ===================================================
-    if (lane == 0) {
+    // (whole warp runs the loop converged; one elected lane issues)
+    {
       int kbg = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int m0, n0, g;
         tile_coords(tile, m0, n0, g);
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES, it = kbg / STAGES;
-          mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
-          if (p.dbg & 8) { mbar_arrive(bar_full + 8 * s); continue; }
-          mbar_arrive_expect_tx(bar_full + 8 * s, S::TX_BYTES);
-          tma_load_3d(stage_b_hi(s), &map_hi, bar_full + 8 * s, kb * BK, n0, g);
-          if (SPLIT) tma_load_3d(stage_b_lo(s), &map_lo, bar_full + 8 * s, kb * BK, n0, g);
+          mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 40);
+          if (elect_one()) {
+            if (p.dbg & 8) {
+              mbar_arrive(bar_full + 8 * s);
+            } else {
+              mbar_arrive_expect_tx(bar_full + 8 * s, S::TX_BYTES);
+              tma_load_3d(stage_b_hi(s), &map_hi, bar_full + 8 * s, kb * BK, n0, g);
+              if (SPLIT) tma_load_3d(stage_b_lo(s), &map_lo, bar_full + 8 * s, kb * BK, n0, g);
+            }
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == NPW + 1) {
     // ================= MMA issuer ========================================================================
-    if (lane == 0) {
+    // whole warp converged; the elected lane issues tcgen05.mma / tcgen05.commit
+    {
       constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
       int kbg = 0, ti = 0;
+      long long mw_full = 0, mw_issue = 0, mw_tempty = 0;
+      const long long mt0 = clock64();
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
         const int buf = ti % S::ACC_BUFS, use = ti / S::ACC_BUFS;
+        const long long q0 = clock64();
         mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);         // epilogue has drained this accumulator
+        mw_tempty += clock64() - q0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
         uint32_t acc = 0;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES, it = kbg / STAGES;
+          const long long f0 = clock64();
           mbar_wait(bar_full + 8 * s, it & 1);
+          const long long f1 = clock64();
+          mw_full += f1 - f0;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {
-            if (p.dbg & 2) break;
-            const uint32_t ah = tmem_base + stage_a_col(s) + (uint32_t)(kk * 8);
-            const uint64_t bh = smem_desc_sw128(stage_b_hi(s) + kk * 32);
-            if (SPLIT) {
-              const uint64_t bl = smem_desc_sw128(stage_b_lo(s) + kk * 32);
-              umma_tf32_ts(d_tmem, ah + 32, bh, IDESC, acc); acc = 1;   // lo * hi
-              umma_tf32_ts(d_tmem, ah, bl, IDESC, 1);                   // hi * lo
+            for (int kk = 0; kk < BK / 8; ++kk) {
+              if (p.dbg & 2) break;
+              const uint32_t ah = tmem_base + stage_a_col(s) + (uint32_t)(kk * 8);
+              const uint64_t bh = smem_desc_sw128(stage_b_hi(s) + kk * 32);
+              if (SPLIT) {
+                const uint64_t bl = smem_desc_sw128(stage_b_lo(s) + kk * 32);
+                umma_tf32_ts(d_tmem, ah + 32, bh, IDESC, (kb | kk) != 0);   // lo * hi
+                umma_tf32_ts(d_tmem, ah, bl, IDESC, 1);                      // hi * lo
+                umma_tf32_ts(d_tmem, ah, bh, IDESC, 1);                      // hi * hi
+              } else {
+                umma_tf32_ts(d_tmem, ah, bh, IDESC, (kb | kk) != 0);
+              }
             }
-            umma_tf32_ts(d_tmem, ah, bh, IDESC, acc); acc = 1;          // hi * hi
+            umma_commit(bar_empty + 8 * s);
+            if (kb == nkb - 1) umma_commit(bar_tfull + 8 * buf);
           }
-          umma_commit(bar_empty + 8 * s);
+          __syncwarp();
+          mw_issue += clock64() - f1;
         }
-        umma_commit(bar_tfull + 8 * buf);
+        (void)acc;
       }
+      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[8] = clock64() - mt0; p.prof[9] = mw_full; p.prof[10] = mw_issue; p.prof[11] = mw_tempty; }
     }
-    __syncwarp();
   } else {
-    // ================= epilogue warps 10..13 ==============================================================
+    // ================= epilogue warps NPW+2 .. NPW+5 ============================================================
     const int lg = warp & 3;                 // TMEM lane group this warp may access
     const int r = lg * 32 + lane;            // GEMM row inside the tile
     const int P = p.Ho * p.Wo;
     int ti = 0;
+    long long ep_wait = 0, ep_work = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       int m0, n0, g;
       tile_coords(tile, m0, n0, g);
@@ -331,7 +368,10 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       float* orow = p.out + ((long long)n * p.Cout_tot + (long long)g * p.Ntot + n0) * p.out_plane +
                     (long long)ho * p.out_hs + (long long)wo * p.out_ws;
       const float* brow = p.bias ? p.bias + (long long)g * p.Ntot + n0 : nullptr;
-      mbar_wait(bar_tfull + 8 * buf, use & 1);
+      const long long e0 = clock64();
+      mbar_wait_backoff(bar_tfull + 8 * buf, use & 1, 200);
+      const long long e1 = clock64();
+      ep_wait += e1 - e0;
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
@@ -352,10 +392,12 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      ep_work += clock64() - e1;
     }
+    if (p.prof && blockIdx.x == 0 && r == 0) { p.prof[16] = ep_wait; p.prof[17] = ep_work; p.prof[18] = ti; }
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == NPW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -454,24 +496,15 @@ static int launch_fwd_n(const FwdParams& p, const CUtensorMap& mh, const CUtenso
   return kmode ? launch_fwd_inst<N_TILE, false, 1>(p, mh, ml, st) : launch_fwd_inst<N_TILE, false, 0>(p, mh, ml, st);
 }
 
-// pick the N tile: per-tile cost ~ nkb * max(mma, producer) + epilogue, tiles spread over the SMs in rounds
+// N tile choice, from the per-layer sweeps in profiles/: the producers stage 32 KB of TF32 hi/lo per K block
+// into tensor memory regardless of N, so narrow tiles are staging-bound (N = 64: ~2x slower per FLOP than
+// N = 128) and N = 256 loses the second accumulator buffer (exposed epilogue).  128 whenever the layer has
+// more than 64 output columns, else the smallest tile that covers them.
 static int pick_n_tile(int Mtot, int Ntot, int G, int Kp, int math) {
-  const int cands[4] = {256, 128, 64, 32};
-  int best = 32;
-  double best_cost = 1e30;
-  for (int i = 0; i < 4; ++i) {
-    const int nt = cands[i];
-    if (nt > 32 && nt / 2 >= Ntot) continue;   // a smaller tile already covers all columns
-    const long long tiles = (long long)((Mtot + 127) / 128) * ((Ntot + nt - 1) / nt) * G;
-    const double mma = (math == B2C_MATH_FP32 ? 6.0 : 2.0) * nt;      // tensor-pipe cycles per 32-deep K block
-    const double prod = 300.0;                                        // A-producer cycles per K block
-    const double epi = nt == 256 ? 14.0 * nt : 2.0 * nt;              // 256: single accumulator, epilogue exposed
-    const double per_tile = (Kp / 32) * (mma > prod ? mma : prod) + epi + 1000.0;
-    const double rounds = (double)((tiles + sm_count() - 1) / sm_count());
-    const double cost = rounds * per_tile;
-    if (cost < best_cost * 0.97) { best_cost = cost; best = nt; }
-  }
-  return best;
+  (void)Mtot; (void)G; (void)Kp; (void)math;
+  if (Ntot > 64) return 128;
+  if (Ntot > 32) return 64;
+  return 32;
 }
 
 bool tc_wgrad_supported(const ConvShape& s);
@@ -543,6 +576,10 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
     }
   }
   p.Kp = padded_k(p.K);
+  static long long* prof_buf = nullptr;
+  static int prof_on = -1;
+  if (prof_on < 0) { const char* e = getenv("B2C_PROF"); prof_on = e ? atoi(e) : 0; if (prof_on) cudaMalloc(&prof_buf, 32 * sizeof(long long)); }
+  p.prof = prof_on ? prof_buf : nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2C_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   const int kmode = (p.Cg % 4 == 0) ? 1 : 0;
   q.tap_major = kmode; q.K = p.K; q.Kp = p.Kp;
@@ -560,6 +597,15 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
   alignas(64) CUtensorMap mh, ml;
   if (int rc = make_filter_map(&mh, q.hi, p.Kp, q.rows, s.G, n_tile)) return rc;
   if (int rc = make_filter_map(&ml, q.lo ? q.lo : q.hi, p.Kp, q.rows, s.G, n_tile)) return rc;
+  if (prof_on) {
+    cudaMemsetAsync(prof_buf, 0, 32 * sizeof(long long), st);
+    int rc = n_tile == 128 ? launch_fwd_n<128>(p, mh, ml, math, kmode, st) : n_tile == 64 ? launch_fwd_n<64>(p, mh, ml, math, kmode, st) : launch_fwd_n<32>(p, mh, ml, math, kmode, st);
+    long long h[32];
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[prof] N_TILE=%d nkb=%d tiles=%d | producer(t0): total=%lld wait_empty=%lld store=%lld load=%lld blocks=%lld | mma: total=%lld wait_full=%lld issue=%lld wait_tempty=%lld | epi: wait=%lld work=%lld tiles=%lld\n",
+            n_tile, p.Kp / 32, p.total_tiles, h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[16], h[17], h[18]);
+    return rc;
+  }
   switch (n_tile) {
     case 256: return launch_fwd_n<256>(p, mh, ml, math, kmode, st);
     case 128: return launch_fwd_n<128>(p, mh, ml, math, kmode, st);

@@ -132,7 +132,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     };
     auto store_block = [&](int kb, const float (&v)[32]) {
       const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 40);
       const uint32_t a_hi = stage_a_hi(s) + kc * LBO_A, a_lo = stage_a_lo(s) + kc * LBO_A;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -156,7 +156,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       if (kb < nkb) store_block(kb, va);
     }
     // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced row stores ===========
-    mbar_wait(bar_tmem, 0);
+    mbar_wait_backoff(bar_tmem, 0, 100);
     tc_fence_after();
     // all MMAs have completed, so the pipeline stages are free: each warp uses a private 32 x 33 fp32 pad
     float* tpad = reinterpret_cast<float*>(smem) + warp * (32 * 33);
@@ -236,7 +236,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     };
     auto store_block = [&](int kb, const float (&v)[RB * 4]) {
       const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+      mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 40);
       const uint32_t b_hi = stage_b_hi(s) + kc * LBO_B, b_lo = stage_b_lo(s) + kc * LBO_B;
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
@@ -260,13 +260,13 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       if (kb < nkb) store_block(kb, va);
     }
   } else {
-    if (lane == 0) {
-      constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
-      uint32_t acc = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, it = kb / STAGES;
-        mbar_wait(bar_full + 8 * s, it & 1);
-        tc_fence_after();
+    // MMA issuer: whole warp converged, the elected lane issues (see elect_one() in tc_common.cuh)
+    constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_full + 8 * s, it & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
           const uint64_t ah = smem_desc(stage_a_hi(s) + 2 * kk * LBO_A, LBO_A, 128);
@@ -274,16 +274,18 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
           if (SPLIT) {
             const uint64_t al = smem_desc(stage_a_lo(s) + 2 * kk * LBO_A, LBO_A, 128);
             const uint64_t bl = smem_desc(stage_b_lo(s) + 2 * kk * LBO_B, LBO_B, 128);
-            umma_tf32(tmem_base, al, bh, IDESC, acc); acc = 1;
+            umma_tf32(tmem_base, al, bh, IDESC, (kb | kk) != 0);
             umma_tf32(tmem_base, ah, bl, IDESC, 1);
+            umma_tf32(tmem_base, ah, bh, IDESC, 1);
+          } else {
+            umma_tf32(tmem_base, ah, bh, IDESC, (kb | kk) != 0);
           }
-          umma_tf32(tmem_base, ah, bh, IDESC, acc); acc = 1;
         }
         umma_commit(bar_empty + 8 * s);
+        if (kb == nkb - 1) umma_commit(bar_tmem);
       }
-      umma_commit(bar_tmem);
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == 12) {
