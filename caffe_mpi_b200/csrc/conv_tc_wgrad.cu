@@ -8,13 +8,16 @@
 // smem tiles are filled "lanes along K": dY with 128-bit loads, X through the im2col gather.  The
 // reduction is split across CTAs (grid.x); partial tiles go to a workspace and a second, deterministic
 // kernel adds them to dW in split order (the reference accumulates image by image, also a fixed order).
+#include <stdlib.h>
 #include "b2c_common.cuh"
 #include "tc_common.cuh"
 
 namespace b2c {
 using namespace tc;
 
-constexpr int WG_THREADS = 416;   // warps 0-3: dY producers + epilogue, 4-11: X gather producers, 12: MMA
+constexpr int WG_YW = 8;                        // dY producer warps (warps 0-3 of them run the epilogue afterwards)
+constexpr int WG_GW = 16;                       // X-gather producer warps
+constexpr int WG_THREADS = (WG_YW + WG_GW + 1) * 32;   // + the MMA warp
 
 struct WgradParams {
   const float* dy;   // [N, O, Ho, Wo]
@@ -25,6 +28,7 @@ struct WgradParams {
   int kb_per_split;  // k-blocks (of 32 q) per split
   int splits;
   float* out;        // splits == 1: dW (accumulated);  else partials [splits][O*Kd] (overwritten)
+  long long* prof;   // optional cycle counters from CTA (0,0,0) (B2C_PROF=1)
 };
 
 template <int N_TILE, bool SPLIT>
@@ -66,11 +70,11 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int nkb = (int)(kb_end - kb_begin);           // >= 1 by construction
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 4 + 8); mbar_init(bar_empty + 8 * s, 1); }   // one elected arrive per producer warp
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, WG_YW + WG_GW); mbar_init(bar_empty + 8 * s, 1); }   // one elected arrive per producer warp
     mbar_init(bar_tmem, 1);
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(smem_u32(tmem_slot), N_TILE);
+  if (warp == WG_YW + WG_GW) tmem_alloc(smem_u32(tmem_slot), N_TILE);
   // row table for the X gather: k' = (c,i,j)
   for (int r = tid; r < N_TILE; r += WG_THREADS) {
     const int kp = n0 + r;
@@ -93,33 +97,40 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
   auto stage_b_hi = [&](int s) { return sbase + s * S::STAGE + (SPLIT ? 2u : 1u) * S::A_BYTES; };
   auto stage_b_lo = [&](int s) { return stage_b_hi(s) + S::B_BYTES; };
 
-  if (warp < 4) {
+  if (warp < WG_YW) {
     // ================= A producer: dY rows (output channels), lanes along q ==========================
-    const int kc = tid & 7, rb = tid >> 3;
+    const int kc = tid & 7, rb = tid >> 3;              // rb in [0, 32): rows r*32 + rb, r < 4
     const bool vec_ok = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dy) & 15u) == 0);
     // loads of k-block kb+1 are issued before the stores of k-block kb (register double buffer)
-    auto load_block = [&](int kb, float (&v)[32]) {
-      const long long q = (kb_begin + kb) * BK + kc * 4;
+    // q = n*P + p of this thread's first element; advanced by BK per K block with 32-bit arithmetic only
+    // (the 64-bit q / P per block made the load phase ~2000 cycles)
+    int cur_n, cur_p;
+    {
+      const long long q0 = kb_begin * BK + kc * 4;
+      cur_n = (int)(q0 / P); cur_p = (int)(q0 - (long long)cur_n * P);
+    }
+    auto load_block = [&](int /*kb*/, float (&v)[16]) {
       int nn[4], pp[4];
       bool qv[4];
       {
-        long long n_ = q / P;
-        int p_ = (int)(q - n_ * P);
+        int n_ = cur_n, p_ = cur_p;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          qv[e] = (q + e) < p.Q;
-          nn[e] = (int)n_; pp[e] = p_;
+          qv[e] = n_ < p.N;
+          nn[e] = n_; pp[e] = p_;
           if (++p_ == P) { p_ = 0; ++n_; }
         }
+        cur_p += BK;
+        while (cur_p >= P) { cur_p -= P; ++cur_n; }
       }
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int o = m0 + r * 16 + rb;
+      for (int r = 0; r < 4; ++r) {
+        const int o = m0 + r * 32 + rb;
         float* vv = v + r * 4;
         vv[0] = vv[1] = vv[2] = vv[3] = 0.f;
         if (o < p.Og) {
           const long long ch = (long long)g * p.Og + o;
-          if (vec_ok && qv[3]) {
+          if (vec_ok && qv[3] && nn[3] == nn[0]) {
             const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.dy + ((long long)nn[0] * p.O + ch) * P + pp[0]));
             vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
           } else {
@@ -130,21 +141,27 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
         }
       }
     };
-    auto store_block = [&](int kb, const float (&v)[32]) {
+    long long pa_wait = 0, pa_store = 0;
+    const long long pa_t0 = clock64();
+    auto store_block = [&](int kb, const float (&v)[16]) {
       const int s = kb % STAGES, it = kb / STAGES;
+      const long long w0 = clock64();
       mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 40);
+      const long long w1 = clock64();
+      pa_wait += w1 - w0;
       const uint32_t a_hi = stage_a_hi(s) + kc * LBO_A, a_lo = stage_a_lo(s) + kc * LBO_A;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int row = r * 16 + rb;
+      for (int r = 0; r < 4; ++r) {
+        const int row = r * 32 + rb;
         store_chunk<SPLIT>(a_hi + row * 16, a_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      pa_store += clock64() - w1;
     };
     {
-      float va[32], vb[32];
+      float va[16], vb[16];
       load_block(0, va);
       int kb = 0;
       for (; kb + 2 <= nkb; kb += 2) {
@@ -155,8 +172,11 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
       if (kb < nkb) store_block(kb, va);
     }
+    const long long pa_t1 = clock64();
+    if (warp < 4) {
     // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced row stores ===========
     mbar_wait_backoff(bar_tmem, 0, 100);
+    const long long pa_t2 = clock64();
     tc_fence_after();
     // all MMAs have completed, so the pipeline stages are free: each warp uses a private 32 x 33 fp32 pad
     float* tpad = reinterpret_cast<float*>(smem) + warp * (32 * 33);
@@ -183,38 +203,57 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       __syncwarp();
     }
     tc_fence_before();
-  } else if (warp < 12) {
+    if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
+      p.prof[0] = pa_t1 - pa_t0; p.prof[1] = pa_wait; p.prof[2] = pa_store; p.prof[3] = pa_t2 - pa_t1; p.prof[4] = clock64() - pa_t2; p.prof[5] = nkb;
+    }
+    }
+  } else if (warp < WG_YW + WG_GW) {
     // ================= B producer: im2col gather of X, rows k'=(c,i,j), lanes along q ==================
-    const int t = tid - 128;
-    const int kc = t & 7, rb = t >> 3;
+    const int t = tid - WG_YW * 32;
+    const int kc = t & 7, rb = t >> 3;                 // rb in [0, 64)
     const bool vec_ok = X1X1 && (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0);
-    constexpr int RB = N_TILE / 32;
-    auto load_block = [&](int kb, float (&v)[RB * 4]) {
-      const long long q = (kb_begin + kb) * BK + kc * 4;
+    constexpr int RB = N_TILE >= 64 ? N_TILE / 64 : 1;
+    const bool row_active = rb < N_TILE;               // N_TILE = 32: upper half of the threads only arrive
+    int cur_n, cur_ho, cur_wo;
+    {
+      const long long q0 = kb_begin * BK + kc * 4;
+      cur_n = (int)(q0 / P);
+      const int p0 = (int)(q0 - (long long)cur_n * P);
+      cur_ho = p0 / p.Wo; cur_wo = p0 - cur_ho * p.Wo;
+    }
+    const long long img = (long long)p.C * HW;
+    auto load_block = [&](int /*kb*/, float (&v)[RB * 4]) {
       long long base[4];
       int ihb[4], iwb[4];
       bool qv[4];
       {
-        long long n_ = q / P;
-        int p_ = (int)(q - n_ * P);
-        int ho = p_ / p.Wo, wo = p_ - ho * p.Wo;
+        int n_ = cur_n, ho = cur_ho, wo = cur_wo;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          qv[e] = (q + e) < p.Q;
-          base[e] = n_ * (long long)p.C * HW;
+          qv[e] = n_ < p.N;
+          base[e] = n_ * img;
           ihb[e] = ho * p.sh - p.ph; iwb[e] = wo * p.sw - p.pw;
           if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++n_; } }
         }
+        // advance the cursor by BK pixels (32-bit divisions only)
+        int w2 = cur_wo + BK;
+        const int dh = w2 / p.Wo;
+        cur_wo = w2 - dh * p.Wo;
+        int h2 = cur_ho + dh;
+        const int dn = h2 / p.Ho;
+        cur_ho = h2 - dn * p.Ho;
+        cur_n += dn;
       }
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        const int2 rt = rowtab[r * 32 + rb];
         float* vv = v + r * 4;
         vv[0] = vv[1] = vv[2] = vv[3] = 0.f;
+        if (!row_active) continue;
+        const int2 rt = rowtab[r * 64 + rb];
         if (rt.x >= 0) {
           if (X1X1) {
             // k=1, s=1, p=0: X rows are contiguous in q exactly like dY
-            if (vec_ok && qv[3]) {
+            if (vec_ok && qv[3] && base[3] == base[0]) {
               const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.x + base[0] + rt.x + (long long)ihb[0] * p.W + iwb[0]));
               vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
             } else {
@@ -228,24 +267,32 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
             for (int e = 0; e < 4; ++e) {
               const int ih = ihb[e] + hoff, iw = iwb[e] + woff;
               if (qv[e] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W)
-                vv[e] = __ldg(p.x + base[e] + rt.x + (long long)ih * p.W + iw);
+                v[r * 4 + e] = __ldg(p.x + base[e] + rt.x + ih * p.W + iw);
             }
           }
         }
       }
     };
+    long long pb_wait = 0, pb_store = 0;
+    const long long pb_t0 = clock64();
     auto store_block = [&](int kb, const float (&v)[RB * 4]) {
       const int s = kb % STAGES, it = kb / STAGES;
+      const long long w0 = clock64();
       mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 40);
+      const long long w1 = clock64();
+      pb_wait += w1 - w0;
       const uint32_t b_hi = stage_b_hi(s) + kc * LBO_B, b_lo = stage_b_lo(s) + kc * LBO_B;
+      if (row_active) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const int row = r * 32 + rb;
-        store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
+        for (int r = 0; r < RB; ++r) {
+          const int row = r * 64 + rb;
+          store_chunk<SPLIT>(b_hi + row * 16, b_lo + row * 16, v[r * 4], v[r * 4 + 1], v[r * 4 + 2], v[r * 4 + 3]);
+        }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      pb_store += clock64() - w1;
     };
     {
       float va[RB * 4], vb[RB * 4];
@@ -259,12 +306,20 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
       if (kb < nkb) store_block(kb, va);
     }
+    if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == WG_YW * 32) {  // first X-gather thread
+      p.prof[8] = clock64() - pb_t0; p.prof[9] = pb_wait; p.prof[10] = pb_store;
+    }
   } else {
     // MMA issuer: whole warp converged, the elected lane issues (see elect_one() in tc_common.cuh)
     constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
+    long long mw = 0, mi = 0;
+    const long long m_t0 = clock64();
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES, it = kb / STAGES;
+      const long long f0 = clock64();
       mbar_wait(bar_full + 8 * s, it & 1);
+      const long long f1 = clock64();
+      mw += f1 - f0;
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -285,10 +340,12 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
         if (kb == nkb - 1) umma_commit(bar_tmem);
       }
       __syncwarp();
+      mi += clock64() - f1;
     }
+    if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) { p.prof[16] = clock64() - m_t0; p.prof[17] = mw; p.prof[18] = mi; }
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == WG_YW + WG_GW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, N_TILE);
   }
@@ -369,6 +426,11 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
   p.Ho = s.Ho; p.Wo = s.Wo;
   p.Q = (long long)s.N * s.Ho * s.Wo;
   p.kb_per_split = pl.kb_per_split; p.splits = pl.splits;
+  static long long* prof_buf = nullptr;
+  static int prof_on = -1;
+  if (prof_on < 0) { const char* e = getenv("B2C_PROF"); prof_on = e ? atoi(e) : 0; if (prof_on) cudaMalloc(&prof_buf, 32 * sizeof(long long)); }
+  p.prof = prof_on ? prof_buf : nullptr;
+  if (prof_on) cudaMemsetAsync(prof_buf, 0, 32 * sizeof(long long), st);
   const size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
   if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "wgrad: workspace too small");
   p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
@@ -380,6 +442,12 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
     default: rc = launch_wgrad_n<32>(p, s.G, math, s.is_1x1, st); break;
   }
   if (rc) return rc;
+  if (prof_on) {
+    long long h[32];
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[wprof] N_TILE=%d splits=%d nkb=%lld | dY-prod: loop=%lld wait_empty=%lld store=%lld wait_tmem=%lld epilogue=%lld | X-prod: loop=%lld wait_empty=%lld store=%lld | mma: total=%lld wait_full=%lld issue=%lld\n",
+            pl.n_tile, pl.splits, h[5], h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[16], h[17], h[18]);
+  }
   if (pl.splits > 1) {
     const long long n = (long long)s.O * s.Kd;
     wgrad_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(static_cast<const float*>(ws), pl.splits, n, dw);
