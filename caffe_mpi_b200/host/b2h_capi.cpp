@@ -2,9 +2,11 @@
 // (The C++ classes in b2caffe.hpp are the interface a Caffe maintainer codes against; this file only
 // marshals arrays so Python can drive them.)  Every function returns 0 / a handle, or -1 / NULL with the
 // message available from b2h_last_error().
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include "b2caffe.hpp"
+#include "prototxt.hpp"
 
 using namespace caffe;
 
@@ -189,5 +191,64 @@ int b2h_solver_step(void* hv) {
   });
 }
 int b2h_solver_iter(void* hv) { return static_cast<SolverHandle*>(hv)->solver->iter(); }
+
+// ---- prototxt / Net -----------------------------------------------------------------------------------------------
+void* b2h_net_create(const char* path_or_text, int is_text, int phase, int batch_override, int def_channels, int def_size) {
+  try {
+    PMessage m = is_text ? ParseTextProto(path_or_text) : ParseTextProtoFile(path_or_text);
+    return new Net(m, phase ? TEST : TRAIN, batch_override, def_channels, def_size);
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void b2h_net_destroy(void* h) { delete static_cast<Net*>(h); }
+int b2h_net_num_layers(void* h) { return (int)static_cast<Net*>(h)->layers().size(); }
+int b2h_net_layer(void* h, int i, char* name, char* type, int cap, int* naxes, int* top_shape) {
+  Net* n = static_cast<Net*>(h);
+  if (i < 0 || i >= (int)n->layers().size()) return -1;
+  const NetLayer& L = n->layers()[i];
+  snprintf(name, cap, "%s", L.param.name.c_str());
+  snprintf(type, cap, "%s", L.param.type.c_str());
+  const std::vector<int>& s = n->top_shape(i, 0);
+  *naxes = (int)s.size();
+  for (size_t k = 0; k < s.size() && k < 8; ++k) top_shape[k] = s[k];
+  return 0;
+}
+int b2h_net_num_convs(void* h) { return (int)static_cast<Net*>(h)->conv_layers().size(); }
+int b2h_net_conv(void* h, int i, b2c_conv_params* out, int* propagate_down, char* name, int cap) {
+  Net* n = static_cast<Net*>(h);
+  if (i < 0 || i >= (int)n->conv_layers().size()) return -1;
+  const ConvEntry& c = n->conv_layers()[i];
+  *out = c.p; *propagate_down = c.propagate_down ? 1 : 0;
+  snprintf(name, cap, "%s", c.name.c_str());
+  return 0;
+}
+int b2h_net_num_params(void* h) { return (int)static_cast<Net*>(h)->learnable_params().size(); }
+int b2h_net_param(void* h, int i, size_t* count, float* lr_mult, float* decay_mult, char* layer, int cap) {
+  Net* n = static_cast<Net*>(h);
+  if (i < 0 || i >= (int)n->learnable_params().size()) return -1;
+  const LearnableParam& p = n->learnable_params()[i];
+  *count = p.count; *lr_mult = p.lr_mult; *decay_mult = p.decay_mult;
+  snprintf(layer, cap, "%s", p.layer.c_str());
+  return 0;
+}
+int b2h_net_reduce_buckets(void* h) { return static_cast<Net*>(h)->reduce_buckets(); }
+
+// SolverParameter from a solver.prototxt; returns an SGDSolver handle (same as b2h_solver_create)
+void* b2h_solver_from_file(const char* path_or_text, int is_text, char* net_path, int cap) {
+  try {
+    PMessage m = is_text ? ParseTextProto(path_or_text) : ParseTextProtoFile(path_or_text);
+    std::string np;
+    SolverParameter p = ReadSolverParameter(m, &np);
+    if (net_path) snprintf(net_path, cap, "%s", np.c_str());
+    auto* h = new SolverHandle;
+    h->solver.reset(new SGDSolver(p));
+    return h;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+int b2h_solver_describe(void* hv, float* base_lr, float* momentum, float* weight_decay, int* max_iter, int* iter_size, char* policy, int cap) {
+  const SolverParameter& p = static_cast<SolverHandle*>(hv)->solver->param();
+  *base_lr = p.base_lr; *momentum = p.momentum; *weight_decay = p.weight_decay; *max_iter = p.max_iter; *iter_size = p.iter_size;
+  snprintf(policy, cap, "%s", p.lr_policy.c_str());
+  return 0;
+}
 
 }  // extern "C"

@@ -1,0 +1,92 @@
+// prototxt.hpp -- protobuf TEXT-format reader for the subset of caffe.proto the BASELINE models use, and the
+// Net graph builder on top of it (there is no protoc / libprotobuf in the toolchain, so
+// the reference's models/*.prototxt and solver.prototxt files are read by this hand-written parser, unmodified).
+//
+// Reference map:
+//   text format / ReadProtoFromTextFile      src/caffe/util/io.cpp, src/caffe/proto/caffe.proto
+//   NetParameter / LayerParameter / NetState  caffe.proto:88-146, 303-337, 368-481
+//   phase filtering (include / exclude)       Net::FilterNet, Net::StateMeetsRule  (src/caffe/net.cpp)
+//   graph build, shapes, need-backward,       Net::Init, Net::AppendTop/AppendBottom/AppendParam (net.cpp:64-667)
+//   learnable-parameter list in layer order
+//   SolverParameter                           caffe.proto:147-301
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "b2caffe.hpp"
+
+namespace caffe {
+
+// ---- generic text-format tree --------------------------------------------------------------------------------
+struct PMessage;
+struct PField {
+  std::string scalar;                 // for `name: value` (quotes removed)
+  std::shared_ptr<PMessage> msg;      // for `name { ... }`
+  bool is_msg() const { return (bool)msg; }
+};
+struct PMessage {
+  std::vector<std::pair<std::string, PField>> fields;   // in file order, repeated fields repeat
+  bool has(const std::string& k) const;
+  std::vector<const PField*> all(const std::string& k) const;
+  const PMessage* sub(const std::string& k) const;      // first sub-message or null
+  std::string str(const std::string& k, const std::string& d = "") const;
+  double num(const std::string& k, double d = 0) const;
+  long long integer(const std::string& k, long long d = 0) const;
+  bool boolean(const std::string& k, bool d = false) const;
+  std::vector<long long> ints(const std::string& k) const;
+};
+PMessage ParseTextProto(const std::string& text);        // throws FatalError with line number on bad input
+PMessage ParseTextProtoFile(const std::string& path);
+
+// ---- net description --------------------------------------------------------------------------------------------
+enum Phase { TRAIN = 0, TEST = 1 };
+
+struct PoolingParameter { int pool = 0, kernel_h = 0, kernel_w = 0, stride_h = 1, stride_w = 1, pad_h = 0, pad_w = 0; bool global_pooling = false; };
+
+struct NetLayer {                       // one LayerParameter after phase filtering
+  LayerParameter param;                 // name, type, bottom, top, ParamSpecs, convolution_param
+  PoolingParameter pooling;
+  int ip_num_output = 0;
+  bool ip_bias = true;
+  bool bn_scale_bias = false;           // NVCaffe BatchNormParameter.scale_bias
+  int concat_axis = 1;
+  int batch_size = 0, crop_size = 0;    // Data layers
+  std::vector<int> input_shape;         // Input / DummyData layers
+};
+
+struct LearnableParam { std::string layer; int layer_id, blob_id; size_t count; std::vector<int> shape; float lr_mult, decay_mult; };
+
+struct ConvEntry { std::string name; int layer_id; b2c_conv_params p; bool propagate_down; };
+
+class Net {
+ public:
+  // batch_override > 0 replaces the Data layer's batch_size (the reference divides the prototxt batch by the GPU
+  // count, parallel.cpp:284-293; callers pass the per-rank batch)
+  Net(const PMessage& net_param, Phase phase, int batch_override = 0, int default_channels = 3, int default_size = 224);
+  static Net FromFile(const std::string& path, Phase phase, int batch_override = 0);
+  const std::string& name() const { return name_; }
+  const std::vector<NetLayer>& layers() const { return layers_; }
+  const std::map<std::string, std::vector<int>>& blob_shapes() const { return shapes_; }
+  const std::vector<int>& top_shape(int layer, int top = 0) const { return layer_top_shapes_[layer][top]; }
+  const std::vector<LearnableParam>& learnable_params() const { return params_; }   // layer order (Net::AppendParam)
+  const std::vector<ConvEntry>& conv_layers() const { return convs_; }
+  int reduce_buckets() const { return reduce_buckets_; }
+  float global_grad_scale() const { return global_grad_scale_; }
+  size_t learnable_count() const;
+ private:
+  std::string name_;
+  std::vector<NetLayer> layers_;
+  std::map<std::string, std::vector<int>> shapes_;
+  std::vector<std::vector<std::vector<int>>> layer_top_shapes_;
+  std::vector<LearnableParam> params_;
+  std::vector<ConvEntry> convs_;
+  int reduce_buckets_ = 6;
+  float global_grad_scale_ = 1.f;
+};
+
+// caffe.proto SolverParameter -> the struct SGDSolver takes; `net_path` receives SolverParameter.net
+SolverParameter ReadSolverParameter(const PMessage& m, std::string* net_path = nullptr);
+
+}  // namespace caffe

@@ -181,3 +181,82 @@ def plan_buckets(counts, reduce_buckets=6):
 
 def divide_batch_size(total, solver_count):
     return lib().b2h_divide_batch_size(total, solver_count)
+
+
+# ---------------------------------------------------------------------------------------------- prototxt / Net
+class Net:
+    """caffe::Net graph built from a prototxt (file path, or text with is_text=True) by the C++ host layer."""
+
+    def __init__(self, path_or_text, phase="TRAIN", batch_override=0, is_text=False, default_channels=3, default_size=224):
+        L = lib()
+        L.b2h_net_create.restype = C.c_void_p
+        L.b2h_net_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        self._h = L.b2h_net_create(path_or_text.encode(), int(is_text), 1 if phase == "TEST" else 0, batch_override,
+                                   default_channels, default_size)
+        if not self._h:
+            raise HostError(L.b2h_last_error().decode())
+        for fn in ("b2h_net_num_layers", "b2h_net_num_convs", "b2h_net_num_params", "b2h_net_reduce_buckets", "b2h_net_destroy"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+
+    def layers(self):
+        L = lib()
+        L.b2h_net_layer.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        out = []
+        for i in range(L.b2h_net_num_layers(self._h)):
+            nm, ty = C.create_string_buffer(256), C.create_string_buffer(256)
+            na, shp = C.c_int(), (C.c_int * 8)()
+            L.b2h_net_layer(self._h, i, nm, ty, 256, C.byref(na), shp)
+            out.append((nm.value.decode(), ty.value.decode(), tuple(shp[k] for k in range(na.value))))
+        return out
+
+    def conv_layers(self):
+        L = lib()
+        L.b2h_net_conv.argtypes = [C.c_void_p, C.c_int, C.POINTER(capi.ConvParams), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        out = []
+        for i in range(L.b2h_net_num_convs(self._h)):
+            p, pd, nm = capi.ConvParams(), C.c_int(), C.create_string_buffer(256)
+            L.b2h_net_conv(self._h, i, C.byref(p), C.byref(pd), nm, 256)
+            out.append((nm.value.decode(), p, bool(pd.value)))
+        return out
+
+    def learnable_params(self):
+        L = lib()
+        L.b2h_net_param.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_char_p, C.c_int]
+        out = []
+        for i in range(L.b2h_net_num_params(self._h)):
+            cnt, lr, dc, nm = C.c_size_t(), C.c_float(), C.c_float(), C.create_string_buffer(256)
+            L.b2h_net_param(self._h, i, C.byref(cnt), C.byref(lr), C.byref(dc), nm, 256)
+            out.append((nm.value.decode(), cnt.value, lr.value, dc.value))
+        return out
+
+    def reduce_buckets(self):
+        return lib().b2h_net_reduce_buckets(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.b2h_net_destroy(self._h)
+            self._h = None
+
+
+def solver_from_prototxt(path_or_text, is_text=False):
+    """(SGDSolver, net_path) from a solver.prototxt."""
+    L = lib()
+    L.b2h_solver_from_file.restype = C.c_void_p
+    L.b2h_solver_from_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(512)
+    h = L.b2h_solver_from_file(path_or_text.encode(), int(is_text), buf, 512)
+    if not h:
+        raise HostError(L.b2h_last_error().decode())
+    s = SGDSolver.__new__(SGDSolver)
+    s._h = h
+    return s, buf.value.decode()
+
+
+def solver_describe(s):
+    L = lib()
+    L.b2h_solver_describe.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 3 + [C.POINTER(C.c_int)] * 2 + [C.c_char_p, C.c_int]
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    d, e = C.c_int(), C.c_int()
+    pol = C.create_string_buffer(64)
+    L.b2h_solver_describe(s._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), pol, 64)
+    return dict(base_lr=a.value, momentum=b.value, weight_decay=c.value, max_iter=d.value, iter_size=e.value, lr_policy=pol.value.decode())
