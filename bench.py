@@ -393,6 +393,8 @@ def run_ours(args):
                          "all_conv_kernels": {"achieved": ach_all, "frac": ach_all / tf32_peak},
                          "ms_per_step": {k: round(v, 3) for k, v in per.items()}},
         }
+        if world == 1 and not args.no_full_net:
+            out["full_net"] = full_net_measure(args, N)
         if world == 1:
             run, cores, kind, desc = reference_sample_runner()
             run(1)
@@ -407,6 +409,33 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def full_net_measure(args, N):
+    """Supplementary line: the WHOLE models/resnet50/train_val.prototxt graph -- conv, BatchNorm,
+    ReLU, pooling, Eltwise, InnerProduct, SoftmaxWithLoss forward + backward, SGD update -- through caffe::TrainNet
+    (host/train_net.cpp), timed with CUDA events on the net's own stream.  Not the headline while the non-conv kernels
+    are first-cut; reported so the distance between the hot path and the full training step is on record."""
+    try:
+        from caffe_mpi_b200 import capi, host_api, models
+        import torch
+        torch.cuda.empty_cache()
+        t = host_api.Trainer(models.resnet50_prototxt(N), models.RESNET50_SOLVER, batch=N,
+                             math=capi.MATH_TF32 if args.math == "tf32" else capi.MATH_FP32)
+        t.step(args.warmup)
+        t.sync()
+        ms = t.timed_steps(args.steps)
+        loss = t.loss()
+        t.step(1, copy_input=True)
+        ms_e2e = t.timed_steps(args.steps, copy_input=True, read_loss=True)
+        return {"metric": "images/sec ResNet-50 fp32 train, full prototxt graph (all layers fwd+bwd + SGD)",
+                "value": N * args.steps / (ms / 1e3), "unit": "images/sec", "ms_per_step": ms / args.steps,
+                "e2e": {"value": N * args.steps / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": t.input_bytes(),
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "loss_after_warmup": loss, "learnable_blobs": t.num_params(), "activation_floats": t.activation_floats(),
+                "accuracy_layers": "skipped (no gradient, not on the training path)"}
+    except Exception as e:                       # supplementary measurement: report, never mask
+        return {"error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -415,6 +444,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"],
                     help="fp32 = 3xTF32 split (fp32-equivalent results, the headline); tf32 = single-pass TF32 (informational)")
+    ap.add_argument("--no-full-net", action="store_true", help="skip the supplementary full-prototxt-graph measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -107,6 +107,17 @@ def lib():
         "b2c_sgd_update": (i, [sz, vp, vp, vp, f, f, f, i, f, i, vp]),
         "b2c_sgd_update_arena": (i, [i, C.POINTER(sz), C.POINTER(sz), C.POINTER(f), C.POINTER(f), vp, vp, vp,
                                      f, i, f, i, vp]),
+        "b2c_relu_forward": (i, [sz, vp, vp, f, vp]),
+        "b2c_relu_backward": (i, [sz, vp, vp, vp, f, vp]),
+        "b2c_bn_forward_train": (i, [i, i, i, vp, vp, vp, f, f, i, vp, vp, vp, vp, vp, vp, vp]),
+        "b2c_bn_backward": (i, [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "b2c_pool_forward": (i, [i] * 10 + [vp, vp, vp, vp]),
+        "b2c_pool_backward": (i, [i] * 10 + [vp, vp, vp, vp]),
+        "b2c_add": (i, [sz, vp, vp, vp, vp]),
+        "b2c_softmax_loss_forward": (i, [i, i, vp, vp, vp, vp, vp]),
+        "b2c_softmax_loss_backward": (i, [i, i, vp, vp, f, vp, vp]),
+        "b2c_bias_forward": (i, [i, i, i, vp, vp, vp]),
+        "b2c_bias_backward": (i, [i, i, i, vp, vp, vp]),
         "b2c_comm_get_unique_id": (i, [vp]),
         "b2c_comm_init": (i, [i, i, vp, C.POINTER(vp)]),
         "b2c_comm_destroy": (i, [vp]),

@@ -1,0 +1,362 @@
+// layers.cu -- the non-convolution layers on ResNet-50's training path, fp32 NCHW.
+// All are HBM-bound elementwise / reduction kernels; each entry point cites the reference CPU code whose
+// semantics it keeps (the parity oracle for them is oracle/layers_oracle.py).
+//
+//   ReLU            src/caffe/layers/relu_layer.cpp:10-41           y = max(x,0) + slope*min(x,0); dx = dy*(x>0 ? 1 : slope)
+//   BatchNorm       src/caffe/layers/batch_norm_layer.cpp:140-300   batch statistics (biased variance, eps added before the
+//                   (NVCaffe, scale_bias)                            inverse sqrt AND before the running average), x_norm kept
+//                                                                    for backward; dgamma/dbeta OVERWRITTEN (compute_sum_*)
+//   Pooling MAX/AVE src/caffe/layers/pooling_layer.cpp:129-318      ceil-mode extents, first-max index mask, AVE divides by the
+//                                                                    padded window size
+//   Eltwise SUM     src/caffe/layers/eltwise_layer.cpp
+//   SoftmaxWithLoss src/caffe/layers/softmax_loss_layer.cpp:96-160  loss = -sum log p[label] / N (VALID normalisation, no
+//                                                                    ignore_label); dx = (p - onehot) * loss_weight / N
+#include <float.h>
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum of two values (blockDim.x multiple of 32, <= 1024); result valid in every thread
+__device__ __forceinline__ void block_sum2(float& a, float& b) {
+  __shared__ float sa[32], sb[32];
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  a = lane < nw ? sa[lane] : 0.f; b = lane < nw ? sb[lane] : 0.f;
+  a = warp_sum(a); b = warp_sum(b);
+  __syncthreads();
+}
+
+// ---- ReLU ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relu_fwd_kernel(size_t n, const float* __restrict__ x, float* __restrict__ y, float slope) {
+  const size_t n4 = n / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  for (size_t i = tid; i < n4; i += step) {
+    float4 v = x4[i];
+    v.x = v.x > 0 ? v.x : v.x * slope; v.y = v.y > 0 ? v.y : v.y * slope; v.z = v.z > 0 ? v.z : v.z * slope; v.w = v.w > 0 ? v.w : v.w * slope;
+    y4[i] = v;
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += step) { const float v = x[i]; y[i] = v > 0 ? v : v * slope; }
+}
+__global__ void __launch_bounds__(256) relu_bwd_kernel(size_t n, const float* __restrict__ dy, const float* __restrict__ x,
+                                                       float* __restrict__ dx, float slope) {
+  const size_t n4 = n / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  const float4* d4 = reinterpret_cast<const float4*>(dy);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* o4 = reinterpret_cast<float4*>(dx);
+  for (size_t i = tid; i < n4; i += step) {
+    const float4 d = d4[i], v = x4[i];
+    float4 o;
+    o.x = d.x * (v.x > 0 ? 1.f : slope); o.y = d.y * (v.y > 0 ? 1.f : slope); o.z = d.z * (v.z > 0 ? 1.f : slope); o.w = d.w * (v.w > 0 ? 1.f : slope);
+    o4[i] = o;
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += step) dx[i] = dy[i] * (x[i] > 0 ? 1.f : slope);
+}
+
+// ---- BatchNorm --------------------------------------------------------------------------------------------------
+// one block per channel: two passes over the channel's N*S values (mean, then mean of squared deviations, as the
+// reference does -- not E[x^2]-E[x]^2), then the running-average update.
+__global__ void __launch_bounds__(512)
+bn_stats_kernel(int N, int C, int S, const float* __restrict__ x, float eps, float maf, int first,
+                float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
+  const int c = blockIdx.x;
+  const size_t cnt = (size_t)N * S;
+  float s = 0.f, dummy = 0.f;
+  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) { const size_t n = i / S, p = i - n * S; s += x[(n * C + c) * S + p]; }
+  block_sum2(s, dummy);
+  const float m = s / (float)cnt;
+  float v = 0.f;
+  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) { const size_t n = i / S, p = i - n * S; const float d = x[(n * C + c) * S + p] - m; v += d * d; }
+  block_sum2(v, dummy);
+  const float var_eps = v / (float)cnt + eps;          // batch_norm_layer.cpp:183-186 (eps folded in before the average)
+  if (threadIdx.x == 0) {
+    mean[c] = m;
+    invstd[c] = 1.0f / sqrtf(var_eps);
+    if (first) { run_mean[c] = m; run_var[c] = var_eps; }                         // iter_ <= 1: copy (:199-204)
+    else { run_mean[c] = (1.f - maf) * m + maf * run_mean[c]; run_var[c] = (1.f - maf) * var_eps + maf * run_var[c]; }
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_norm_kernel(size_t total, int C, int S, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ xnorm, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / S) % C);
+    const float xn = (x[i] - mean[c]) * invstd[c];
+    xnorm[i] = xn;
+    y[i] = gamma ? xn * gamma[c] + beta[c] : xn;
+  }
+}
+// per channel: dgamma = sum dy*xn, dbeta = sum dy (both OVERWRITTEN, batch_norm_layer.cpp:247-252)
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_kernel(int N, int C, int S, const float* __restrict__ dy, const float* __restrict__ xnorm,
+                     float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy) {
+  const int c = blockIdx.x;
+  const size_t cnt = (size_t)N * S;
+  float a = 0.f, b = 0.f;
+  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const size_t n = i / S, p = i - n * S, idx = (n * C + c) * S + p;
+    const float d = dy[idx];
+    a += d * xnorm[idx]; b += d;
+  }
+  block_sum2(a, b);
+  if (threadIdx.x == 0) { sum_dy_xn[c] = a; sum_dy[c] = b; }
+}
+// dx = gamma * invstd * (dy - mean(dy) - xn * mean(dy*xn))     (means over N*S; with gamma folded: :254-281)
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(size_t total, int C, int S, float inv_cnt, const float* __restrict__ dy, const float* __restrict__ xnorm,
+                 const float* __restrict__ gamma, const float* __restrict__ invstd, const float* __restrict__ sum_dy_xn,
+                 const float* __restrict__ sum_dy, float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / S) % C);
+    const float g = gamma ? gamma[c] : 1.f;
+    dx[i] = g * invstd[c] * (dy[i] - sum_dy[c] * inv_cnt - xnorm[i] * sum_dy_xn[c] * inv_cnt);
+  }
+}
+
+// ---- Pooling ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pool_max_fwd_kernel(size_t total, int H, int W, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                    const float* __restrict__ x, float* __restrict__ y, int* __restrict__ mask) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo), ho = (int)((i / Wo) % Ho);
+    const size_t nc = i / ((size_t)Wo * Ho);
+    int hs = ho * sh - ph, ws = wo * sw - pw;
+    const int he = min(hs + kh, H), we = min(ws + kw, W);
+    hs = max(hs, 0); ws = max(ws, 0);
+    const float* src = x + nc * H * W;
+    float best = -FLT_MAX;
+    int bi = -1;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) {
+        const float v = src[h * W + w];
+        if (v > best) { best = v; bi = h * W + w; }       // strict '>' keeps the FIRST maximum, as the reference
+      }
+    y[i] = best;
+    mask[i] = bi;
+  }
+}
+__global__ void __launch_bounds__(256)
+pool_max_bwd_kernel(size_t total, int H, int W, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                    const float* __restrict__ dy, const int* __restrict__ mask, float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const size_t nc = i / ((size_t)W * H);
+    const int phs = (h + ph < kh) ? 0 : (h + ph - kh) / sh + 1, phe = min((h + ph) / sh + 1, Ho);
+    const int pws = (w + pw < kw) ? 0 : (w + pw - kw) / sw + 1, pwe = min((w + pw) / sw + 1, Wo);
+    const float* d = dy + nc * Ho * Wo;
+    const int* m = mask + nc * Ho * Wo;
+    float g = 0.f;
+    for (int a = phs; a < phe; ++a)
+      for (int b = pws; b < pwe; ++b)
+        if (m[a * Wo + b] == h * W + w) g += d[a * Wo + b];
+    dx[i] = g;
+  }
+}
+__global__ void __launch_bounds__(256)
+pool_ave_fwd_kernel(size_t total, int H, int W, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                    const float* __restrict__ x, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo), ho = (int)((i / Wo) % Ho);
+    const size_t nc = i / ((size_t)Wo * Ho);
+    int hs = ho * sh - ph, ws = wo * sw - pw;
+    int he = min(hs + kh, H + ph), we = min(ws + kw, W + pw);
+    const int pool_size = (he - hs) * (we - ws);          // padded window size (pooling_layer.cpp:200-206)
+    hs = max(hs, 0); ws = max(ws, 0); he = min(he, H); we = min(we, W);
+    const float* src = x + nc * H * W;
+    float s = 0.f;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) s += src[h * W + w];
+    y[i] = s / pool_size;
+  }
+}
+__global__ void __launch_bounds__(256)
+pool_ave_bwd_kernel(size_t total, int H, int W, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
+                    const float* __restrict__ dy, float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W) + pw, h = (int)((i / W) % H) + ph;
+    const size_t nc = i / ((size_t)W * H);
+    const int phs = (h < kh) ? 0 : (h - kh) / sh + 1, phe = min(h / sh + 1, Ho);
+    const int pws = (w < kw) ? 0 : (w - kw) / sw + 1, pwe = min(w / sw + 1, Wo);
+    const float* d = dy + nc * Ho * Wo;
+    float g = 0.f;
+    for (int a = phs; a < phe; ++a)
+      for (int b = pws; b < pwe; ++b) {
+        const int hs = a * sh - ph, ws = b * sw - pw;
+        const int he = min(hs + kh, H + ph), we = min(ws + kw, W + pw);
+        g += d[a * Wo + b] / ((he - hs) * (we - ws));
+      }
+    dx[i] = g;
+  }
+}
+
+// ---- elementwise ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_kernel(size_t n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y) {
+  const size_t n4 = n / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = tid; i < n4; i += step) {
+    const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += step) y[i] = a[i] + b[i];
+}
+
+// ---- softmax with loss ------------------------------------------------------------------------------------------
+// one block per sample; prob[N,C]; loss_sum accumulates -log p[label] (caller zeroes it); labels are float class ids
+__global__ void __launch_bounds__(256)
+softmax_loss_fwd_kernel(int C, const float* __restrict__ logits, const float* __restrict__ labels, float* __restrict__ prob,
+                        float* __restrict__ loss_sum) {
+  const int n = blockIdx.x;
+  const float* z = logits + (size_t)n * C;
+  float mx = -FLT_MAX, dummy = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, z[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __shared__ float smx[32];
+  if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = smx[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, smx[w]);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { const float e = expf(z[c] - mx); prob[(size_t)n * C + c] = e; s += e; }
+  block_sum2(s, dummy);
+  const float inv = 1.f / s;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) prob[(size_t)n * C + c] *= inv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int lab = (int)labels[n];
+    atomicAdd(loss_sum, -logf(fmaxf(prob[(size_t)n * C + lab], FLT_MIN)));
+  }
+}
+__global__ void __launch_bounds__(256)
+softmax_loss_bwd_kernel(size_t total, int C, const float* __restrict__ prob, const float* __restrict__ labels, float scale,
+                        float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / C;
+    const int c = (int)(i - n * C);
+    dx[i] = (prob[i] - (c == (int)labels[n] ? 1.f : 0.f)) * scale;
+  }
+}
+__global__ void scale_scalar_kernel(float* v, float s) { *v *= s; }
+
+}  // namespace b2c
+
+using namespace b2c;
+#define NEED(cond, msg) if (!(cond)) return fail(B2C_ERR_INVALID, msg)
+
+extern "C" int b2c_relu_forward(size_t n, const float* x, float* y, float negative_slope, void* stream) {
+  NEED(x && y, "b2c_relu_forward: null");
+  if (!n) return B2C_OK;
+  relu_fwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(n, x, y, negative_slope);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_relu_backward(size_t n, const float* dy, const float* x, float* dx, float negative_slope, void* stream) {
+  NEED(dy && x && dx, "b2c_relu_backward: null");
+  if (!n) return B2C_OK;
+  relu_bwd_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(n, dy, x, dx, negative_slope);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_bn_forward_train(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                                    float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                                    float* save_mean, float* save_invstd, float* xnorm, float* y, void* stream) {
+  NEED(x && y && xnorm && save_mean && save_invstd && running_mean && running_var && N > 0 && C > 0 && S > 0, "b2c_bn_forward_train: bad argument");
+  NEED((gamma == nullptr) == (beta == nullptr), "b2c_bn_forward_train: gamma and beta go together");
+  bn_stats_kernel<<<C, 512, 0, as_stream(stream)>>>(N, C, S, x, eps, moving_average_fraction, first_iteration, save_mean, save_invstd,
+                                                    running_mean, running_var);
+  B2C_POST_LAUNCH();
+  const size_t total = (size_t)N * C * S;
+  bn_norm_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, C, S, x, save_mean, save_invstd, gamma, beta, xnorm, y);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_bn_backward(int N, int C, int S, const float* dy, const float* xnorm, const float* gamma, const float* save_invstd,
+                               float* dgamma, float* dbeta, float* dx, void* stream) {
+  NEED(dy && xnorm && save_invstd && dgamma && dbeta && dx, "b2c_bn_backward: null (dgamma/dbeta double as the reduction scratch)");
+  bn_bwd_reduce_kernel<<<C, 512, 0, as_stream(stream)>>>(N, C, S, dy, xnorm, dgamma, dbeta);
+  B2C_POST_LAUNCH();
+  const size_t total = (size_t)N * C * S;
+  bn_bwd_dx_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, C, S, 1.0f / ((float)N * S), dy, xnorm, gamma, save_invstd,
+                                                                      dgamma, dbeta, dx);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+static int pool_out(int in, int k, int s, int p) {
+  int o = (int)ceilf((float)(in + 2 * p - k) / s) + 1;
+  if (p > 0 && (o - 1) * s >= in + p) --o;
+  return o;
+}
+extern "C" int b2c_pool_forward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* x,
+                                float* y, int* mask, void* stream) {
+  NEED(x && y && NC > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0, "b2c_pool_forward: bad argument");
+  const int Ho = pool_out(H, kh, sh, ph), Wo = pool_out(W, kw, sw, pw);
+  const size_t total = (size_t)NC * Ho * Wo;
+  if (method == 0) {
+    NEED(mask, "b2c_pool_forward: MAX needs a mask buffer");
+    pool_max_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, x, y, mask);
+  } else if (method == 1) {
+    pool_ave_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, x, y);
+  } else {
+    return fail(B2C_ERR_INVALID, "b2c_pool_forward: STOCHASTIC pooling is outside this path");
+  }
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_pool_backward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* dy,
+                                 const int* mask, float* dx, void* stream) {
+  NEED(dy && dx && NC > 0, "b2c_pool_backward: bad argument");
+  const int Ho = pool_out(H, kh, sh, ph), Wo = pool_out(W, kw, sw, pw);
+  const size_t total = (size_t)NC * H * W;
+  if (method == 0) {
+    NEED(mask, "b2c_pool_backward: MAX needs the forward mask");
+    pool_max_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, dy, mask, dx);
+  } else if (method == 1) {
+    pool_ave_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, dy, dx);
+  } else {
+    return fail(B2C_ERR_INVALID, "b2c_pool_backward: STOCHASTIC pooling is outside this path");
+  }
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_add(size_t n, const float* a, const float* b, float* y, void* stream) {
+  NEED(a && b && y, "b2c_add: null");
+  if (!n) return B2C_OK;
+  add_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(n, a, b, y);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_softmax_loss_forward(int N, int C, const float* logits, const float* labels, float* prob, float* loss, void* stream) {
+  NEED(logits && labels && prob && loss && N > 0 && C > 0, "b2c_softmax_loss_forward: bad argument");
+  B2C_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), as_stream(stream)));
+  softmax_loss_fwd_kernel<<<N, 256, 0, as_stream(stream)>>>(C, logits, labels, prob, loss);
+  B2C_POST_LAUNCH();
+  scale_scalar_kernel<<<1, 1, 0, as_stream(stream)>>>(loss, 1.0f / (float)N);     // VALID normalisation, no ignore_label
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_softmax_loss_backward(int N, int C, const float* prob, const float* labels, float loss_weight, float* dx, void* stream) {
+  NEED(prob && labels && dx && N > 0 && C > 0, "b2c_softmax_loss_backward: bad argument");
+  const size_t total = (size_t)N * C;
+  softmax_loss_bwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, C, prob, labels, loss_weight / (float)N, dx);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+// y[n][o] += b[o] and db[o] += sum_n dy[n][o]: InnerProduct bias (inner_product_layer.cpp), via the conv bias kernels with P = 1
+namespace b2c {
+int launch_bias_add(int, int, int, const float*, float*, cudaStream_t);
+int launch_bias_grad(int, int, int, const float*, float*, cudaStream_t);
+}
+extern "C" int b2c_bias_forward(int N, int O, int P, const float* bias, float* y, void* stream) {
+  NEED(bias && y, "b2c_bias_forward: null");
+  return launch_bias_add(N, O, P, bias, y, as_stream(stream));
+}
+extern "C" int b2c_bias_backward(int N, int O, int P, const float* dy, float* db, void* stream) {
+  NEED(dy && db, "b2c_bias_backward: null");
+  return launch_bias_grad(N, O, P, dy, db, as_stream(stream));
+}

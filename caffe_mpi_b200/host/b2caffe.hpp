@@ -106,6 +106,7 @@ class Blob {
   // also re-homes data so the fused multi-tensor SGD sees one contiguous parameter space)
   void set_gpu_data(float* p);
   void set_gpu_diff(float* p);
+  void ShareData(Blob& other);        // alias other's device data without copying (Blob::ShareData, blob.hpp)
   void Update();                      // data -= diff (blob.cpp:129-154), on the thread stream
   void set_diff(float v);
 

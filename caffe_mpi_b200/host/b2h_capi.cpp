@@ -7,6 +7,7 @@
 #include <memory>
 #include "b2caffe.hpp"
 #include "prototxt.hpp"
+#include "train_net.hpp"
 
 using namespace caffe;
 
@@ -250,5 +251,84 @@ int b2h_solver_describe(void* hv, float* base_lr, float* momentum, float* weight
   snprintf(policy, cap, "%s", p.lr_policy.c_str());
   return 0;
 }
+
+// ---- TrainNet: the whole prototxt net + solver ------------------------------------------------------------------
+struct TrainerHandle {
+  std::unique_ptr<Net> desc;
+  std::unique_ptr<TrainNet> net;
+  std::unique_ptr<P2PSync> sync;
+};
+void* b2h_trainer_create(const char* net_src, int net_is_text, const char* solver_src, int solver_is_text, int batch, int num_classes,
+                         unsigned long long seed, int math, int def_channels, int def_size) {
+  try {
+    auto* h = new TrainerHandle;
+    PMessage nm = net_is_text ? ParseTextProto(net_src) : ParseTextProtoFile(net_src);
+    h->desc.reset(new Net(nm, TRAIN, batch, def_channels, def_size));
+    PMessage sm = solver_is_text ? ParseTextProto(solver_src) : ParseTextProtoFile(solver_src);
+    SolverParameter sp = ReadSolverParameter(sm);
+    sp.reduce_buckets = h->desc->reduce_buckets();
+    sp.global_grad_scale = h->desc->global_grad_scale();
+    h->net.reset(new TrainNet(*h->desc, sp, num_classes, seed, math));
+    return h;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void b2h_trainer_destroy(void* hv) { delete static_cast<TrainerHandle*>(hv); }
+int b2h_trainer_attach_sync(void* hv, int nranks, int rank, unsigned char* id, int create_id) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({
+    if (create_id) { B2C_CHECK(b2c_comm_get_unique_id(id)); return 0; }
+    unsigned char* idp = id;
+    h->sync.reset(new P2PSync(nranks, rank, [idp](void* buf, size_t bytes, int) { memcpy(buf, idp, bytes); }));
+    h->net->AttachSync(h->sync.get());
+  });
+}
+int b2h_trainer_step(void* hv, int nsteps, int copy_input) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ for (int i = 0; i < nsteps; ++i) h->net->Step(copy_input != 0); });
+}
+int b2h_trainer_timed_steps(void* hv, int nsteps, int copy_input, int read_loss, float* ms) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ *ms = h->net->TimedSteps(nsteps, copy_input != 0, read_loss != 0); });
+}
+long long b2h_trainer_input_bytes(void* hv) {
+  Blob* d = static_cast<TrainerHandle*>(hv)->net->blob("data");
+  return d ? (long long)d->count() * 4 : 0;
+}
+int b2h_trainer_forward_backward(void* hv, float* loss) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ *loss = h->net->ForwardBackward(); });
+}
+int b2h_trainer_sync(void* hv) { (void)hv; B2H_TRY({ CUDA_CHECK(cudaStreamSynchronize(Caffe::thread_stream())); CUDA_CHECK(cudaDeviceSynchronize()); }); }
+int b2h_trainer_loss(void* hv, float* loss) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ *loss = h->net->last_loss(); });
+}
+long long b2h_trainer_blob_count(void* hv, const char* name) {
+  Blob* b = static_cast<TrainerHandle*>(hv)->net->blob(name);
+  return b ? (long long)b->count() : -1;
+}
+int b2h_trainer_blob(void* hv, const char* name, int diff, int set, float* buf) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({
+    Blob* b = h->net->blob(name);
+    B2_CHECK(b != nullptr, std::string("no blob named ") + name);
+    if (set) memcpy(diff ? b->mutable_cpu_diff() : b->mutable_cpu_data(), buf, sizeof(float) * b->count());
+    else memcpy(buf, diff ? b->cpu_diff() : b->cpu_data(), sizeof(float) * b->count());
+  });
+}
+int b2h_trainer_num_params(void* hv) { return (int)static_cast<TrainerHandle*>(hv)->net->learnable_params().size(); }
+long long b2h_trainer_param_count(void* hv, int i) { return (long long)static_cast<TrainerHandle*>(hv)->net->learnable_params()[i]->count(); }
+int b2h_trainer_param(void* hv, int i, int what, int set, float* buf) {   // what: 0 data, 1 diff, 2 history
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({
+    Blob& b = *h->net->learnable_params()[i];
+    CUDA_CHECK(cudaDeviceSynchronize());
+    float* dev = what == 0 ? b.mutable_gpu_data() : what == 1 ? b.mutable_gpu_diff()
+                                                              : h->net->solver().arena().history() + h->net->solver().arena().offset(i);
+    if (set) CUDA_CHECK(cudaMemcpy(dev, buf, sizeof(float) * b.count(), cudaMemcpyHostToDevice));
+    else CUDA_CHECK(cudaMemcpy(buf, dev, sizeof(float) * b.count(), cudaMemcpyDeviceToHost));
+  });
+}
+long long b2h_trainer_activation_floats(void* hv) { return (long long)static_cast<TrainerHandle*>(hv)->net->activation_floats(); }
 
 }  // extern "C"

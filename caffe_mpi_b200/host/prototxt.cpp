@@ -3,6 +3,7 @@
 
 #include <cctype>
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
 #include <fstream>
 #include <set>
@@ -306,6 +307,8 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       B2_CHECK(ip != nullptr, "InnerProduct layer without inner_product_param");
       L.ip_num_output = (int)ip->integer("num_output");
       L.ip_bias = ip->boolean("bias_term", true);
+      L.ip_weight_filler = filler_of(ip->sub("weight_filler"));
+      L.ip_bias_filler = filler_of(ip->sub("bias_filler"));
       const std::vector<int>& bs = bottom_shape(0);
       const int K = (int)prod(bs, 1);
       tops.push_back({bs[0], L.ip_num_output});
@@ -313,7 +316,8 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       if (L.ip_bias) blobs.push_back({{L.ip_num_output}, 1});
     } else if (type == "BatchNorm") {
       const PMessage* bp = lp.sub("batch_norm_param");
-      L.bn_scale_bias = bp ? bp->boolean("scale_bias", false) : false;
+      L.bn_scale_bias = bp ? (bp->boolean("scale_bias", false) || bp->has("scale_filler") || bp->has("bias_filler")) : false;
+      if (bp) { L.bn_eps = std::max((float)bp->num("eps", 1e-5), 1e-5f); L.bn_maf = (float)bp->num("moving_average_fraction", 0.999); }
       const std::vector<int>& bs = bottom_shape(0);
       tops.push_back(bs);
       // blobs_[0..2] = running mean / variance / correction (statistics, not exchanged with the cuDNN engine:
@@ -339,6 +343,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       tops.push_back(s);
     } else if (type == "SoftmaxWithLoss" || type == "EuclideanLoss" || type == "SigmoidCrossEntropyLoss" || type == "Accuracy") {
       for (size_t i = 0; i < L.param.top.size(); ++i) tops.push_back({});
+    } else if (type == "ReLU" && (L.relu_slope = (float)(lp.sub("relu_param") ? lp.sub("relu_param")->num("negative_slope", 0.0) : 0.0), false)) {
     } else if (type == "ReLU" || type == "Dropout" || type == "LRN" || type == "Eltwise" || type == "Softmax" || type == "Sigmoid" ||
                type == "TanH" || type == "Power" || type == "Bias" || type == "ELU" || type == "PReLU" || type == "Split") {
       for (size_t i = 0; i < std::max<size_t>(1, L.param.top.size()); ++i) tops.push_back(bottom_shape(0));

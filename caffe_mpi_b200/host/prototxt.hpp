@@ -51,6 +51,9 @@ struct NetLayer {                       // one LayerParameter after phase filter
   int ip_num_output = 0;
   bool ip_bias = true;
   bool bn_scale_bias = false;           // NVCaffe BatchNormParameter.scale_bias
+  float bn_eps = 1e-5f, bn_maf = 0.999f; // BatchNormParameter.eps / moving_average_fraction
+  FillerParameter ip_weight_filler, ip_bias_filler;
+  float relu_slope = 0.f;
   int concat_axis = 1;
   int batch_size = 0, crop_size = 0;    // Data layers
   std::vector<int> input_shape;         // Input / DummyData layers

@@ -1,0 +1,314 @@
+// train_net.cpp -- see train_net.hpp.
+#include "train_net.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace caffe {
+
+static cudaStream_t S() { return Caffe::thread_stream(); }
+
+// ================================================================================================ ReLU
+void ReLULayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  B2C_CHECK(b2c_relu_forward(b[0]->count(), b[0]->gpu_data(), t[0]->mutable_gpu_data(), 0.f, S()));
+}
+void ReLULayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (!pd[0]) return;
+  // in place: bottom data == top data (post-activation), same (x > 0) mask for slope 0 (relu_layer.cpp:27-41)
+  B2C_CHECK(b2c_relu_backward(b[0]->count(), t[0]->gpu_diff(), b[0]->gpu_data(), b[0]->mutable_gpu_diff(), 0.f, S()));
+}
+
+// ================================================================================================ BatchNorm
+void BatchNormLayer::LayerSetUp(const vector<Blob*>& b, const vector<Blob*>&) {
+  const int C = b[0]->num_axes() > 1 ? b[0]->shape(1) : 1;
+  blobs_.resize(scale_bias_ ? 5 : 3);
+  blobs_[0].reset(new Blob(vector<int>{C}));      // running mean
+  blobs_[1].reset(new Blob(vector<int>{C}));      // running variance (+eps)
+  blobs_[2].reset(new Blob(vector<int>{1}));      // variance correction (kept for blob-count compatibility)
+  if (scale_bias_) {
+    blobs_[3].reset(new Blob(vector<int>{C}));
+    blobs_[4].reset(new Blob(vector<int>{C}));
+    FillerParameter one; one.type = "constant"; one.value = 1.f;
+    Fill(one, blobs_[3].get());                   // scale = 1, bias = 0 (batch_norm_layer.cpp:52-63)
+    FillerParameter zero;
+    Fill(zero, blobs_[4].get());
+  }
+  param_propagate_down_.assign(blobs_.size(), false);
+  if (scale_bias_) param_propagate_down_[3] = param_propagate_down_[4] = true;
+}
+void BatchNormLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
+  if (t[0] != b[0]) t[0]->ReshapeLike(*b[0]);
+  const int C = b[0]->shape(1);
+  xnorm_.ReshapeLike(*b[0]);
+  save_mean_.Reshape({C}); save_invstd_.Reshape({C}); scratch_.Reshape({2 * C});
+}
+void BatchNormLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
+  B2C_CHECK(b2c_bn_forward_train(N, C, Sp, b[0]->gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
+                                 scale_bias_ ? blobs_[4]->gpu_data() : nullptr, eps_, maf_, iter_ <= 1 ? 1 : 0,
+                                 blobs_[0]->mutable_gpu_data(), blobs_[1]->mutable_gpu_data(), save_mean_.mutable_gpu_data(),
+                                 save_invstd_.mutable_gpu_data(), xnorm_.mutable_gpu_data(), t[0]->mutable_gpu_data(), S()));
+  ++iter_;
+}
+void BatchNormLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>&, const vector<Blob*>& b) {
+  const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
+  float* dg = scale_bias_ ? blobs_[3]->mutable_gpu_diff() : scratch_.mutable_gpu_data();
+  float* db = scale_bias_ ? blobs_[4]->mutable_gpu_diff() : scratch_.mutable_gpu_data() + C;
+  B2C_CHECK(b2c_bn_backward(N, C, Sp, t[0]->gpu_diff(), xnorm_.gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
+                            save_invstd_.gpu_data(), dg, db, b[0]->mutable_gpu_diff(), S()));
+}
+
+// ================================================================================================ Pooling
+PoolingLayer::~PoolingLayer() { if (mask_) cudaFree(mask_); }
+static int pooled(int in, int k, int s, int p) {
+  int o = (int)std::ceil((float)(in + 2 * p - k) / s) + 1;
+  if (p > 0 && (o - 1) * s >= in + p) --o;
+  return o;
+}
+void PoolingLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
+  eff_ = q_;
+  if (q_.global_pooling) { eff_.kernel_h = b[0]->shape(2); eff_.kernel_w = b[0]->shape(3); eff_.stride_h = eff_.stride_w = 1; eff_.pad_h = eff_.pad_w = 0; }
+  t[0]->Reshape({b[0]->shape(0), b[0]->shape(1), pooled(b[0]->shape(2), eff_.kernel_h, eff_.stride_h, eff_.pad_h),
+                 pooled(b[0]->shape(3), eff_.kernel_w, eff_.stride_w, eff_.pad_w)});
+  if (eff_.pool == 0 && t[0]->count() > mask_cap_) {
+    if (mask_) CUDA_CHECK(cudaFree(mask_));
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&mask_), sizeof(int) * t[0]->count()));
+    mask_cap_ = t[0]->count();
+  }
+}
+void PoolingLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  B2C_CHECK(b2c_pool_forward(eff_.pool, b[0]->shape(0) * b[0]->shape(1), b[0]->shape(2), b[0]->shape(3), eff_.kernel_h, eff_.kernel_w,
+                             eff_.stride_h, eff_.stride_w, eff_.pad_h, eff_.pad_w, b[0]->gpu_data(), t[0]->mutable_gpu_data(), mask_, S()));
+}
+void PoolingLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (!pd[0]) return;
+  B2C_CHECK(b2c_pool_backward(eff_.pool, b[0]->shape(0) * b[0]->shape(1), b[0]->shape(2), b[0]->shape(3), eff_.kernel_h, eff_.kernel_w,
+                              eff_.stride_h, eff_.stride_w, eff_.pad_h, eff_.pad_w, t[0]->gpu_diff(), mask_, b[0]->mutable_gpu_diff(), S()));
+}
+
+// ================================================================================================ Eltwise SUM
+void EltwiseLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  B2_CHECK(b.size() >= 2, "Eltwise needs two bottoms");
+  B2C_CHECK(b2c_add(t[0]->count(), b[0]->gpu_data(), b[1]->gpu_data(), t[0]->mutable_gpu_data(), S()));
+  for (size_t i = 2; i < b.size(); ++i) B2C_CHECK(b2c_add(t[0]->count(), t[0]->gpu_data(), b[i]->gpu_data(), t[0]->mutable_gpu_data(), S()));
+}
+void EltwiseLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  for (size_t i = 0; i < b.size(); ++i)
+    if (pd[i]) CUDA_CHECK(cudaMemcpyAsync(b[i]->mutable_gpu_diff(), t[0]->gpu_diff(), sizeof(float) * t[0]->count(), cudaMemcpyDeviceToDevice, S()));
+}
+
+// ================================================================================================ InnerProduct
+void InnerProductLayer::LayerSetUp(const vector<Blob*>& b, const vector<Blob*>&) {
+  K_ = (int)b[0]->count(1);
+  blobs_.resize(bias_ ? 2 : 1);
+  blobs_[0].reset(new Blob(vector<int>{num_output_, K_}));
+  Fill(wf_, blobs_[0].get());
+  if (bias_) { blobs_[1].reset(new Blob(vector<int>{num_output_})); Fill(bf_, blobs_[1].get()); }
+  param_propagate_down_.assign(blobs_.size(), true);
+}
+void InnerProductLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
+  M_ = b[0]->shape(0);
+  B2_CHECK((int)b[0]->count(1) == K_, "Input size incompatible with inner product parameters.");
+  t[0]->Reshape({M_, num_output_});
+}
+void InnerProductLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  // y[M x N] = x[M x K] * W[N x K]^T (+ bias)   (inner_product_layer.cpp: caffe_gpu_gemm(NoTrans, Trans, M, N, K))
+  B2C_CHECK(b2c_sgemm(0, 1, M_, num_output_, K_, 1.f, b[0]->gpu_data(), blobs_[0]->gpu_data(), 0.f, t[0]->mutable_gpu_data(), S()));
+  if (bias_) B2C_CHECK(b2c_bias_forward(M_, num_output_, 1, blobs_[1]->gpu_data(), t[0]->mutable_gpu_data(), S()));
+}
+void InnerProductLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  // dW[N x K] += dy^T[N x M] * x[M x K];  db += sum_m dy;  dx[M x K] = dy[M x N] * W[N x K]
+  B2C_CHECK(b2c_sgemm(1, 0, num_output_, K_, M_, 1.f, t[0]->gpu_diff(), b[0]->gpu_data(), 1.f, blobs_[0]->mutable_gpu_diff(), S()));
+  if (bias_) B2C_CHECK(b2c_bias_backward(M_, num_output_, 1, t[0]->gpu_diff(), blobs_[1]->mutable_gpu_diff(), S()));
+  if (pd[0]) B2C_CHECK(b2c_sgemm(0, 0, M_, K_, num_output_, 1.f, t[0]->gpu_diff(), blobs_[0]->gpu_data(), 0.f, b[0]->mutable_gpu_diff(), S()));
+}
+
+// ================================================================================================ SoftmaxWithLoss
+void SoftmaxWithLossLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
+  prob_.ReshapeLike(*b[0]);
+  t[0]->Reshape({1});
+}
+void SoftmaxWithLossLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  B2C_CHECK(b2c_softmax_loss_forward(b[0]->shape(0), (int)b[0]->count(1), b[0]->gpu_data(), b[1]->gpu_data(), prob_.mutable_gpu_data(),
+                                     t[0]->mutable_gpu_data(), S()));
+}
+void SoftmaxWithLossLayer::Backward_gpu(const vector<Blob*>&, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (!pd[0]) return;
+  B2C_CHECK(b2c_softmax_loss_backward(b[0]->shape(0), (int)b[0]->count(1), prob_.gpu_data(), b[1]->gpu_data(), 1.f,
+                                      b[0]->mutable_gpu_diff(), S()));
+}
+
+// ================================================================================================ synthetic data
+SyntheticDataLayer::~SyntheticDataLayer() { if (host_) cudaFreeHost(host_); }
+void SyntheticDataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& t) {
+  std::mt19937 rng((uint32_t)seed_);
+  for (size_t i = 0; i < t.size(); ++i) t[i]->Reshape(shapes_[i]);
+  n0_ = t[0]->count();
+  CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_), sizeof(float) * n0_));
+  std::normal_distribution<float> g(0.f, 1.f);
+  for (size_t i = 0; i < n0_; ++i) host_[i] = g(rng);
+  memcpy(t[0]->mutable_cpu_data(), host_, sizeof(float) * n0_);
+  if (t.size() > 1) {
+    std::uniform_int_distribution<int> u(0, classes_ - 1);
+    float* l = t[1]->mutable_cpu_data();
+    for (size_t i = 0; i < t[1]->count(); ++i) l[i] = (float)u(rng);
+  }
+  for (Blob* b : t) b->gpu_data();   // upload once; the blobs stay resident
+}
+
+// ================================================================================================ TrainNet
+TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, uint64_t seed, int math) {
+  Caffe::set_random_seed(seed);
+  std::map<string, bool> need;
+  vector<ParamSpec> specs;
+  for (size_t li = 0; li < net.layers().size(); ++li) {
+    const NetLayer& L = net.layers()[li];
+    const string& type = L.param.type;
+    if (type == "Accuracy") continue;                       // TEST-phase metric, no gradient, not on the training path
+    Node node;
+    for (auto& bn : L.param.bottom) {
+      auto it = blobs_.find(bn);
+      B2_CHECK(it != blobs_.end(), "Unknown bottom blob '" + bn + "'");
+      node.bottom.push_back(it->second.get());
+    }
+    for (auto& tn : L.param.top) {
+      auto& sp_ = blobs_[tn];
+      if (!sp_) sp_.reset(new Blob());
+      node.top.push_back(sp_.get());
+    }
+    shared_ptr<LayerBase> layer;
+    if (type == "Data" || type == "Input" || type == "DummyData" || type == "ImageData") {
+      vector<vector<int>> shapes;
+      for (size_t t = 0; t < L.param.top.size(); ++t) shapes.push_back(net.top_shape((int)li, (int)t));
+      auto* d = new SyntheticDataLayer(L.param, shapes, num_classes, seed);
+      layer.reset(d);
+      data_ = d;
+    } else if (type == "Convolution") {
+      LayerParameter lp = L.param;
+      lp.convolution_param.math = math;
+      layer = LayerRegistry::CreateLayer(lp);
+    } else if (type == "ReLU") layer.reset(new ReLULayer(L.param));
+    else if (type == "BatchNorm") layer.reset(new BatchNormLayer(L.param, L.bn_scale_bias, L.bn_eps, L.bn_maf));
+    else if (type == "Pooling") layer.reset(new PoolingLayer(L.param, L.pooling));
+    else if (type == "Eltwise") layer.reset(new EltwiseLayer(L.param));
+    else if (type == "InnerProduct") layer.reset(new InnerProductLayer(L.param, L.ip_num_output, L.ip_bias, L.ip_weight_filler, L.ip_bias_filler));
+    else if (type == "SoftmaxWithLoss") layer.reset(new SoftmaxWithLossLayer(L.param));
+    else B2_CHECK(false, "TrainNet: layer type '" + type + "' is not built yet (SURVEY 8f rank 2 covers the ResNet-50 set)");
+    layer->SetUp(node.bottom, node.top);
+    // learnable blobs in layer order (Net::AppendParam): every blob the layer marks param_propagate_down
+    node.first_param = (int)learnable_.size();
+    for (size_t bi = 0; bi < layer->blobs().size(); ++bi) {
+      if (!layer->param_propagate_down((int)bi)) continue;
+      learnable_.push_back(layer->blobs()[bi]);
+      const size_t spec_idx = type == "BatchNorm" ? bi : (size_t)node.num_params;
+      specs.push_back(spec_idx < L.param.param.size() ? L.param.param[spec_idx] : ParamSpec());
+      ++node.num_params;
+    }
+    // need-backward analysis (net.cpp:160-283)
+    bool nb = false;
+    for (size_t i = 0; i < node.bottom.size(); ++i) {
+      const bool bneed = need.count(L.param.bottom[i]) ? need[L.param.bottom[i]] : false;
+      node.propagate_down.push_back(bneed && !(type == "SoftmaxWithLoss" && i == 1));
+      nb |= bneed;
+    }
+    for (int k = 0; k < node.num_params; ++k) nb |= specs[node.first_param + k].lr_mult != 0.f;
+    if (layer.get() == data_) nb = false;
+    node.need_backward = nb;
+    for (auto& tn : L.param.top) need[tn] = nb;
+    if (type == "SoftmaxWithLoss") loss_blob_ = node.top[0];
+    node.bottom_diff_tmp.assign(node.bottom.size(), nullptr);
+    layers_.push_back(layer);
+    nodes_.push_back(node);
+  }
+  // diff accumulation where a blob fans out (insert_splits.cpp / SplitLayer::Backward): the consumer that runs FIRST in
+  // the backward pass writes the blob's diff; every other consumer writes a shadow diff that is then added in
+  std::map<Blob*, int> writers;
+  for (int li = (int)nodes_.size() - 1; li >= 0; --li) {
+    Node& nd = nodes_[li];
+    if (!nd.need_backward) continue;
+    for (size_t i = 0; i < nd.bottom.size(); ++i) {
+      if (!nd.propagate_down[i]) continue;
+      const bool in_place = i < nd.top.size() && nd.top[i] == nd.bottom[i];
+      if (in_place) continue;
+      if (writers[nd.bottom[i]]++ > 0) {
+        tmp_diffs_.emplace_back(new Blob(nd.bottom[i]->shape()));
+        nd.bottom_diff_tmp[i] = tmp_diffs_.back().get();
+      }
+    }
+  }
+  solver_.reset(new SGDSolver(sp));
+  solver_->SetParams(learnable_, specs);
+  sched_.reset(new ReduceScheduler(solver_.get(), nullptr));
+  CUDA_CHECK(cudaStreamSynchronize(S()));
+}
+TrainNet::~TrainNet() {}
+
+void TrainNet::AttachSync(P2PSync* sync) {
+  sync_ = sync;
+  sync_->on_start(solver_->arena());
+  sched_.reset(new ReduceScheduler(solver_.get(), sync_));
+}
+Blob* TrainNet::blob(const string& name) {
+  auto it = blobs_.find(name);
+  return it == blobs_.end() ? nullptr : it->second.get();
+}
+size_t TrainNet::activation_floats() const {
+  size_t c = 0;
+  for (auto& kv : blobs_) c += kv.second->count();
+  return c;
+}
+void TrainNet::Forward(bool copy_input) {
+  if (copy_input && data_) {
+    Blob* d = nodes_[0].top[0];
+    CUDA_CHECK(cudaMemcpyAsync(d->mutable_gpu_data(), data_->host_batch(), sizeof(float) * data_->batch_floats(), cudaMemcpyHostToDevice, S()));
+  }
+  for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->Forward(nodes_[i].bottom, nodes_[i].top);
+}
+void TrainNet::Backward(bool update) {
+  for (int li = (int)layers_.size() - 1; li >= 0; --li) {
+    Node& nd = nodes_[li];
+    if (nd.need_backward) {
+      // redirect fan-out bottoms to their shadow blobs (data shared, private diff), run, then accumulate
+      vector<Blob*> bvec = nd.bottom;
+      for (size_t i = 0; i < bvec.size(); ++i)
+        if (nd.bottom_diff_tmp[i]) { nd.bottom_diff_tmp[i]->ShareData(*nd.bottom[i]); bvec[i] = nd.bottom_diff_tmp[i]; }
+      layers_[li]->Backward(nd.top, nd.propagate_down, bvec);
+      for (size_t i = 0; i < bvec.size(); ++i)
+        if (nd.bottom_diff_tmp[i])
+          B2C_CHECK(b2c_add(nd.bottom[i]->count(), nd.bottom[i]->gpu_diff(), nd.bottom_diff_tmp[i]->gpu_diff(), nd.bottom[i]->mutable_gpu_diff(), S()));
+    }
+    if (update && nd.num_params) sched_->on_param_ready(nd.first_param, S());     // net.cpp:738-746
+  }
+}
+float TrainNet::ForwardBackward() {
+  Forward(false);
+  Backward(false);              // diffs stay in place for inspection; Step() is the path that reduces + updates
+  return last_loss();
+}
+void TrainNet::Step(bool copy_input_from_host) {
+  Forward(copy_input_from_host);
+  Backward(true);
+  sched_->end_of_iteration(S());
+}
+float TrainNet::TimedSteps(int n, bool copy_input, bool read_loss) {
+  cudaEvent_t a, b;
+  CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+  CUDA_CHECK(cudaStreamSynchronize(S()));
+  CUDA_CHECK(cudaEventRecord(a, S()));
+  for (int i = 0; i < n; ++i) {
+    Step(copy_input);
+    if (read_loss) {                               // device -> host read of the step's result, on the same stream
+      CUDA_CHECK(cudaMemcpyAsync(&host_loss_, loss_blob_->gpu_data(), sizeof(float), cudaMemcpyDeviceToHost, S()));
+      CUDA_CHECK(cudaStreamSynchronize(S()));
+    }
+  }
+  CUDA_CHECK(cudaEventRecord(b, S()));
+  CUDA_CHECK(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return ms;
+}
+float TrainNet::last_loss() { return loss_blob_ ? loss_blob_->cpu_data()[0] : 0.f; }
+
+}  // namespace caffe

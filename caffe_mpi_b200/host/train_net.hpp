@@ -1,0 +1,150 @@
+// train_net.hpp -- the non-convolution layers of the BASELINE nets as caffe::LayerBase subclasses, and TrainNet: a
+// caffe::Net executor (forward / backward over the prototxt graph with automatic diff accumulation where a blob fans
+// out, i.e. what insert_splits.cpp + SplitLayer do in the reference) wired to SGDSolver / ReduceScheduler / P2PSync.
+//
+// Reference map: src/caffe/layers/{relu,batch_norm,pooling,eltwise,inner_product,softmax_loss,split}_layer.cpp,
+// Net::ForwardFromTo / BackwardFromToAu (src/caffe/net.cpp:669-751), Solver::Step (src/caffe/solver.cpp:187-353).
+#pragma once
+#include "b2caffe.hpp"
+#include "prototxt.hpp"
+
+namespace caffe {
+
+class ReLULayer : public LayerBase {
+ public:
+  using LayerBase::LayerBase;
+  const char* type() const override { return "ReLU"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { if (t[0] != b[0]) t[0]->ReshapeLike(*b[0]); }
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+};
+
+class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_bias (batch_norm_layer.cpp)
+ public:
+  BatchNormLayer(const LayerParameter& p, bool scale_bias, float eps, float maf) : LayerBase(p), scale_bias_(scale_bias), eps_(eps), maf_(maf) {}
+  const char* type() const override { return "BatchNorm"; }
+  void LayerSetUp(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  bool scale_bias_;
+  float eps_, maf_;
+  int iter_ = 0;
+  Blob xnorm_, save_mean_, save_invstd_, scratch_;
+};
+
+class PoolingLayer : public LayerBase {
+ public:
+  PoolingLayer(const LayerParameter& p, const PoolingParameter& q) : LayerBase(p), q_(q) {}
+  const char* type() const override { return "Pooling"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  PoolingParameter q_, eff_;
+  int* mask_ = nullptr;
+  size_t mask_cap_ = 0;
+ public:
+  ~PoolingLayer() override;
+};
+
+class EltwiseLayer : public LayerBase {        // SUM with unit coefficients (the only use in the BASELINE nets)
+ public:
+  using LayerBase::LayerBase;
+  const char* type() const override { return "Eltwise"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { t[0]->ReshapeLike(*b[0]); }
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+};
+
+class InnerProductLayer : public LayerBase {
+ public:
+  InnerProductLayer(const LayerParameter& p, int num_output, bool bias, const FillerParameter& wf, const FillerParameter& bf)
+      : LayerBase(p), num_output_(num_output), bias_(bias), wf_(wf), bf_(bf) {}
+  const char* type() const override { return "InnerProduct"; }
+  void LayerSetUp(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  int num_output_, K_ = 0, M_ = 0;
+  bool bias_;
+  FillerParameter wf_, bf_;
+};
+
+class SoftmaxWithLossLayer : public LayerBase {
+ public:
+  using LayerBase::LayerBase;
+  const char* type() const override { return "SoftmaxWithLoss"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  Blob prob_;
+};
+
+// Synthetic in-memory source standing in for DataLayer: N(0,1) images from mt19937(seed), uniform labels.
+class SyntheticDataLayer : public LayerBase {
+ public:
+  SyntheticDataLayer(const LayerParameter& p, const vector<vector<int>>& shapes, int num_classes, uint64_t seed)
+      : LayerBase(p), shapes_(shapes), classes_(num_classes), seed_(seed) {}
+  const char* type() const override { return "Data"; }
+  void LayerSetUp(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Reshape(const vector<Blob*>&, const vector<Blob*>&) override {}
+  float* host_batch() { return host_; }          // pinned staging buffer of top[0] (the e2e path copies it every step)
+  size_t batch_floats() const { return n0_; }
+  ~SyntheticDataLayer() override;
+ protected:
+  void Forward_gpu(const vector<Blob*>&, const vector<Blob*>&) override {}
+  void Backward_gpu(const vector<Blob*>&, const vector<bool>&, const vector<Blob*>&) override {}
+  vector<vector<int>> shapes_;
+  int classes_;
+  uint64_t seed_;
+  float* host_ = nullptr;
+  size_t n0_ = 0;
+};
+
+class TrainNet {
+ public:
+  TrainNet(const Net& net, const SolverParameter& sp, int num_classes, uint64_t seed, int math);
+  ~TrainNet();
+  void AttachSync(P2PSync* sync);                  // weights broadcast from rank 0, gradients exchanged per bucket
+  float ForwardBackward();                         // Net::ForwardBackward (net.cpp:711-716); returns the loss (host sync)
+  void Step(bool copy_input_from_host);            // one Solver::Step iteration, fully asynchronous on the thread stream
+  // n Steps bracketed by CUDA events on the thread stream; returns milliseconds (end-of-iteration makes the compute
+  // stream wait for the last update, so the closing event covers reduce + update too)
+  float TimedSteps(int n, bool copy_input, bool read_loss);
+  float last_loss();                               // device -> host read of the loss blob
+  SGDSolver& solver() { return *solver_; }
+  Blob* blob(const string& name);
+  int num_layers() const { return (int)layers_.size(); }
+  LayerBase* layer(int i) { return layers_[i].get(); }
+  const vector<shared_ptr<Blob>>& learnable_params() const { return learnable_; }
+  size_t activation_floats() const;
+ private:
+  struct Node {
+    vector<Blob*> bottom, top;
+    vector<bool> propagate_down;
+    vector<Blob*> bottom_diff_tmp;                 // per bottom: null = write the blob's own diff, else accumulate through this
+    bool need_backward = false;
+    int first_param = -1, num_params = 0;
+  };
+  void Forward(bool copy_input);
+  void Backward(bool update);
+  float host_loss_ = 0.f;
+  std::map<string, shared_ptr<Blob>> blobs_;
+  vector<shared_ptr<LayerBase>> layers_;
+  vector<Node> nodes_;
+  vector<shared_ptr<Blob>> tmp_diffs_;
+  vector<shared_ptr<Blob>> learnable_;
+  std::unique_ptr<SGDSolver> solver_;
+  std::unique_ptr<ReduceScheduler> sched_;
+  P2PSync* sync_ = nullptr;
+  Blob* loss_blob_ = nullptr;
+  SyntheticDataLayer* data_ = nullptr;
+};
+
+}  // namespace caffe

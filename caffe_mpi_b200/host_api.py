@@ -260,3 +260,102 @@ def solver_describe(s):
     pol = C.create_string_buffer(64)
     L.b2h_solver_describe(s._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), pol, 64)
     return dict(base_lr=a.value, momentum=b.value, weight_decay=c.value, max_iter=d.value, iter_size=e.value, lr_policy=pol.value.decode())
+
+
+# ---------------------------------------------------------------------------------------------- TrainNet
+class Trainer:
+    """caffe::TrainNet: the whole prototxt net (synthetic data source) + SGDSolver + ReduceScheduler, on the GPU."""
+
+    def __init__(self, net, solver, batch=0, num_classes=1000, seed=1701, math=capi.MATH_FP32, net_is_text=True,
+                 solver_is_text=True, default_channels=3, default_size=224):
+        L = lib()
+        L.b2h_trainer_create.restype = C.c_void_p
+        L.b2h_trainer_create.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_int, C.c_int, C.c_int]
+        self._h = L.b2h_trainer_create(net.encode(), int(net_is_text), solver.encode(), int(solver_is_text), batch, num_classes, seed,
+                                       math, default_channels, default_size)
+        if not self._h:
+            raise HostError(L.b2h_last_error().decode())
+        vp, i = C.c_void_p, C.c_int
+        L.b2h_trainer_destroy.argtypes = [vp]
+        L.b2h_trainer_attach_sync.argtypes = [vp, i, i, C.c_char_p, i]
+        L.b2h_trainer_step.argtypes = [vp, i, i]
+        L.b2h_trainer_forward_backward.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b2h_trainer_sync.argtypes = [vp]
+        L.b2h_trainer_loss.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b2h_trainer_blob_count.argtypes = [vp, C.c_char_p]
+        L.b2h_trainer_blob_count.restype = C.c_longlong
+        L.b2h_trainer_blob.argtypes = [vp, C.c_char_p, i, i, _f32]
+        L.b2h_trainer_num_params.argtypes = [vp]
+        L.b2h_trainer_param_count.argtypes = [vp, i]
+        L.b2h_trainer_param_count.restype = C.c_longlong
+        L.b2h_trainer_param.argtypes = [vp, i, i, i, _f32]
+        L.b2h_trainer_activation_floats.argtypes = [vp]
+        L.b2h_trainer_activation_floats.restype = C.c_longlong
+
+    def new_unique_id(self):
+        buf = C.create_string_buffer(128)
+        _ck(lib().b2h_trainer_attach_sync(self._h, 1, 0, buf, 1))
+        return buf.raw
+
+    def attach_sync(self, nranks, rank, id_bytes):
+        _ck(lib().b2h_trainer_attach_sync(self._h, nranks, rank, C.create_string_buffer(bytes(id_bytes), 128), 0))
+
+    def step(self, n=1, copy_input=False):
+        _ck(lib().b2h_trainer_step(self._h, n, int(copy_input)))
+
+    def timed_steps(self, n, copy_input=False, read_loss=False):
+        """n Solver::Step iterations bracketed by CUDA events on the net's stream -> milliseconds."""
+        L = lib()
+        L.b2h_trainer_timed_steps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        v = C.c_float()
+        _ck(L.b2h_trainer_timed_steps(self._h, n, int(copy_input), int(read_loss), C.byref(v)))
+        return v.value
+
+    def input_bytes(self):
+        L = lib()
+        L.b2h_trainer_input_bytes.argtypes = [C.c_void_p]
+        L.b2h_trainer_input_bytes.restype = C.c_longlong
+        return L.b2h_trainer_input_bytes(self._h)
+
+    def forward_backward(self):
+        v = C.c_float()
+        _ck(lib().b2h_trainer_forward_backward(self._h, C.byref(v)))
+        return v.value
+
+    def sync(self):
+        _ck(lib().b2h_trainer_sync(self._h))
+
+    def loss(self):
+        v = C.c_float()
+        _ck(lib().b2h_trainer_loss(self._h, C.byref(v)))
+        return v.value
+
+    def get_blob(self, name, diff=False):
+        n = lib().b2h_trainer_blob_count(self._h, name.encode())
+        if n < 0:
+            raise HostError("no blob " + name)
+        out = np.empty(n, np.float32)
+        _ck(lib().b2h_trainer_blob(self._h, name.encode(), int(diff), 0, out))
+        return out
+
+    def set_blob(self, name, arr, diff=False):
+        _ck(lib().b2h_trainer_blob(self._h, name.encode(), int(diff), 1, np.ascontiguousarray(arr, np.float32).reshape(-1)))
+
+    def num_params(self):
+        return lib().b2h_trainer_num_params(self._h)
+
+    def get_param(self, i, what=0):
+        out = np.empty(lib().b2h_trainer_param_count(self._h, i), np.float32)
+        _ck(lib().b2h_trainer_param(self._h, i, what, 0, out))
+        return out
+
+    def set_param(self, i, arr, what=0):
+        _ck(lib().b2h_trainer_param(self._h, i, what, 1, np.ascontiguousarray(arr, np.float32).reshape(-1)))
+
+    def activation_floats(self):
+        return lib().b2h_trainer_activation_floats(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.b2h_trainer_destroy(self._h)
+            self._h = None

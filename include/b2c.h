@@ -142,6 +142,35 @@ int b2c_sgemm(int transA, int transB, int M, int N, int K, float alpha, const fl
 int b2c_sgemv(int transA, int M, int N, float alpha, const float* A, const float* x,
               float beta, float* y, void* stream);
 
+/* ---- the non-convolution layers on ResNet-50's training path ----------------------------
+ * fp32 NCHW, asynchronous on `stream`.  Each keeps the semantics of the reference layer's CPU code.                */
+/* ReLULayer::Forward/Backward (src/caffe/layers/relu_layer.cpp:10-41); may run in place (y == x).                  */
+int b2c_relu_forward(size_t n, const float* x, float* y, float negative_slope, void* stream);
+int b2c_relu_backward(size_t n, const float* dy, const float* x, float* dx, float negative_slope, void* stream);
+/* BatchNormLayer (NVCaffe, src/caffe/layers/batch_norm_layer.cpp:140-300), TRAIN phase.  x,y,xnorm: [N,C,S].
+ * gamma/beta null <=> scale_bias false.  running_var stores (variance + eps) like the reference's blobs_[1].
+ * backward OVERWRITES dgamma/dbeta (also the reduction scratch when gamma is null) and dx.                          */
+int b2c_bn_forward_train(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                         float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                         float* save_mean, float* save_invstd, float* xnorm, float* y, void* stream);
+int b2c_bn_backward(int N, int C, int S, const float* dy, const float* xnorm, const float* gamma, const float* save_invstd,
+                    float* dgamma, float* dbeta, float* dx, void* stream);
+/* PoolingLayer (src/caffe/layers/pooling_layer.cpp:129-318): method 0 = MAX (mask = argmax index inside the H*W
+ * plane, first maximum), 1 = AVE.  NC = N*C planes; output extent is the reference's ceil mode.  dx overwritten.    */
+int b2c_pool_forward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* x,
+                     float* y, int* mask, void* stream);
+int b2c_pool_backward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* dy,
+                      const int* mask, float* dx, void* stream);
+/* y = a + b: EltwiseLayer SUM forward (eltwise_layer.cpp) and the diff accumulation of SplitLayer::Backward.        */
+int b2c_add(size_t n, const float* a, const float* b, float* y, void* stream);
+/* SoftmaxWithLossLayer (src/caffe/layers/softmax_loss_layer.cpp:96-160), VALID normalisation, labels as float ids:
+ * forward writes prob [N,C] and *loss (device scalar); backward writes dx = (prob - onehot) * loss_weight / N.       */
+int b2c_softmax_loss_forward(int N, int C, const float* logits, const float* labels, float* prob, float* loss, void* stream);
+int b2c_softmax_loss_backward(int N, int C, const float* prob, const float* labels, float loss_weight, float* dx, void* stream);
+/* y[n][o][p] += bias[o];  db[o] += sum_{n,p} dy[n][o][p]  (InnerProduct bias with P = 1; conv bias with P = Ho*Wo). */
+int b2c_bias_forward(int N, int O, int P, const float* bias, float* y, void* stream);
+int b2c_bias_backward(int N, int O, int P, const float* dy, float* db, void* stream);
+
 /* ---- fused SGD-momentum update -----------------------------------------------------------
  * h = momentum*h + local_rate*(grad_scale*g + local_decay*reg(w)); w -= h;
  * g = clear_grads ? 0 : h.   reg(w) = w (l2 != 0) or sign(w).

@@ -1,0 +1,128 @@
+"""CPU oracle for the non-convolution layers on ResNet-50's path -- TEST INFRASTRUCTURE ONLY (numpy restatements of
+the reference's *_cpu code; paths relative to /root/reference).  Parity status: pinned against closed forms /
+finite differences in tests/test_layers_cpu.py (the reference stores no golden tensors for these layers; its own
+tests use GradientChecker, which the finite-difference checks here restate)."""
+import numpy as np
+
+
+# ReLULayer::Forward_cpu / Backward_cpu, src/caffe/layers/relu_layer.cpp:10-41
+def relu_forward(x, slope=0.0):
+    return np.maximum(x, 0) + slope * np.minimum(x, 0)
+
+
+def relu_backward(dy, x, slope=0.0):
+    return dy * ((x > 0) + slope * (x <= 0))
+
+
+# BatchNormLayer::Forward_cpu (TRAIN), src/caffe/layers/batch_norm_layer.cpp:140-232
+def bn_forward_train(x, gamma, beta, eps, maf, run_mean, run_var, first):
+    x = x.astype(np.float32)
+    ax = (0,) + tuple(range(2, x.ndim))
+    shp = (1, -1) + (1,) * (x.ndim - 2)
+    mean = x.mean(axis=ax, dtype=np.float64).astype(np.float32)
+    xc = x - mean.reshape(shp)
+    var_eps = (xc.astype(np.float64) ** 2).mean(axis=ax).astype(np.float32) + np.float32(eps)   # eps added before the average (:183-186)
+    invstd = (1.0 / np.sqrt(var_eps)).astype(np.float32)
+    xnorm = xc * invstd.reshape(shp)
+    if first:                                    # iter_ <= 1: copy (:199-204)
+        nm, nv = mean.copy(), var_eps.copy()
+    else:
+        nm = (1 - maf) * mean + maf * run_mean
+        nv = (1 - maf) * var_eps + maf * run_var
+    y = xnorm * gamma.reshape(shp) + beta.reshape(shp) if gamma is not None else xnorm.copy()
+    return y.astype(np.float32), xnorm.astype(np.float32), mean, invstd, nm.astype(np.float32), nv.astype(np.float32)
+
+
+# BatchNormLayer::Backward_cpu, batch_norm_layer.cpp:234-283 (scale/shift diffs are OVERWRITTEN, not accumulated)
+def bn_backward(dy, xnorm, gamma, invstd):
+    ax = (0,) + tuple(range(2, dy.ndim))
+    shp = (1, -1) + (1,) * (dy.ndim - 2)
+    dgamma = (dy.astype(np.float64) * xnorm).sum(axis=ax)
+    dbeta = dy.astype(np.float64).sum(axis=ax)
+    g = gamma.reshape(shp) if gamma is not None else 1.0
+    cnt = dy.size / dy.shape[1]
+    dx = g * invstd.reshape(shp) * (dy - (dbeta / cnt).reshape(shp) - xnorm * (dgamma / cnt).reshape(shp))
+    return dgamma.astype(np.float32), dbeta.astype(np.float32), dx.astype(np.float32)
+
+
+def pooled_extent(n, k, s, p):                   # PoolingLayer::Reshape: ceil mode with the last-window clip
+    o = int(np.ceil((n + 2 * p - k) / s)) + 1
+    if p > 0 and (o - 1) * s >= n + p:
+        o -= 1
+    return o
+
+
+# PoolingLayer::Forward_cpu / Backward_cpu, src/caffe/layers/pooling_layer.cpp:129-318
+def pool_forward(x, method, k, s, p):
+    N, C, H, W = x.shape
+    Ho, Wo = pooled_extent(H, k[0], s[0], p[0]), pooled_extent(W, k[1], s[1], p[1])
+    y = np.zeros((N, C, Ho, Wo), np.float32)
+    mask = np.full((N, C, Ho, Wo), -1, np.int32)
+    for ho in range(Ho):
+        for wo in range(Wo):
+            hs, ws = ho * s[0] - p[0], wo * s[1] - p[1]
+            if method == 0:
+                he, we = min(hs + k[0], H), min(ws + k[1], W)
+                hs, ws = max(hs, 0), max(ws, 0)
+                win = x[:, :, hs:he, ws:we].reshape(N, C, -1)
+                idx = win.argmax(axis=2)                       # first maximum, like the strict '>' scan
+                y[:, :, ho, wo] = np.take_along_axis(win, idx[..., None], 2)[..., 0]
+                mask[:, :, ho, wo] = (hs + idx // (we - ws)) * W + (ws + idx % (we - ws))
+            else:
+                he, we = min(hs + k[0], H + p[0]), min(ws + k[1], W + p[1])
+                size = (he - hs) * (we - ws)
+                hs, ws, he, we = max(hs, 0), max(ws, 0), min(he, H), min(we, W)
+                y[:, :, ho, wo] = x[:, :, hs:he, ws:we].sum(axis=(2, 3), dtype=np.float64) / size
+    return y, mask
+
+
+def pool_backward(dy, mask, x_shape, method, k, s, p):
+    N, C, H, W = x_shape
+    Ho, Wo = dy.shape[2:]
+    dx = np.zeros(x_shape, np.float64)
+    for ho in range(Ho):
+        for wo in range(Wo):
+            if method == 0:
+                flat = dx.reshape(N, C, -1)
+                np.add.at(flat, (np.arange(N)[:, None], np.arange(C)[None, :], mask[:, :, ho, wo]), dy[:, :, ho, wo])
+            else:
+                hs, ws = ho * s[0] - p[0], wo * s[1] - p[1]
+                he, we = min(hs + k[0], H + p[0]), min(ws + k[1], W + p[1])
+                size = (he - hs) * (we - ws)
+                hs, ws, he, we = max(hs, 0), max(ws, 0), min(he, H), min(we, W)
+                dx[:, :, hs:he, ws:we] += (dy[:, :, ho, wo] / size)[:, :, None, None]
+    return dx.astype(np.float32)
+
+
+# SoftmaxWithLossLayer::Forward_cpu / Backward_cpu, src/caffe/layers/softmax_loss_layer.cpp:96-160 (VALID normalisation)
+def softmax_loss_forward(logits, labels):
+    z = logits.astype(np.float64)
+    z = z - z.max(axis=1, keepdims=True)
+    p = np.exp(z)
+    p /= p.sum(axis=1, keepdims=True)
+    lab = labels.astype(np.int64)
+    loss = -np.log(np.maximum(p[np.arange(len(lab)), lab], np.finfo(np.float32).tiny)).sum() / len(lab)
+    return p.astype(np.float32), np.float32(loss)
+
+
+def softmax_loss_backward(prob, labels, loss_weight=1.0):
+    d = prob.astype(np.float64).copy()
+    lab = labels.astype(np.int64)
+    d[np.arange(len(lab)), lab] -= 1.0
+    return (d * (loss_weight / len(lab))).astype(np.float32)
+
+
+# InnerProductLayer::Forward_cpu / Backward_cpu, src/caffe/layers/inner_product_layer.cpp (transpose = false)
+def ip_forward(x, w, b):
+    y = x.reshape(x.shape[0], -1).astype(np.float64) @ w.astype(np.float64).T
+    if b is not None:
+        y += b
+    return y.astype(np.float32)
+
+
+def ip_backward(x, w, dy):
+    x2 = x.reshape(x.shape[0], -1).astype(np.float64)
+    dw = dy.astype(np.float64).T @ x2
+    db = dy.astype(np.float64).sum(axis=0)
+    dx = (dy.astype(np.float64) @ w.astype(np.float64)).reshape(x.shape)
+    return dw.astype(np.float32), db.astype(np.float32), dx.astype(np.float32)

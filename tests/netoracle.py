@@ -1,0 +1,174 @@
+"""Whole-net CPU oracle for the trainer tests: a small layer-spec list is rendered to prototxt text (what the product
+parses) and interpreted in numpy with the oracle's per-layer restatements (oracle.conv_* and oracle.layers_oracle),
+including Net::Backward's diff accumulation where a blob fans out and the SGD update of Solver::Step.
+TEST INFRASTRUCTURE ONLY."""
+import numpy as np
+import oracle
+from oracle import layers_oracle as lo
+
+
+def bottleneck(spec, name, bottom, mid, out, stride, skip):
+    spec += [dict(t="conv", n=f"{name}.conv1", b=bottom, o=mid, k=1, s=stride, p=0), dict(t="bn", n=f"{name}.conv1/bn", b=f"{name}.conv1"),
+             dict(t="relu", n=f"{name}.conv1/relu", b=f"{name}.conv1/bn"),
+             dict(t="conv", n=f"{name}.conv2", b=f"{name}.conv1/bn", o=mid, k=3, s=1, p=1), dict(t="bn", n=f"{name}.conv2/bn", b=f"{name}.conv2"),
+             dict(t="relu", n=f"{name}.conv2/relu", b=f"{name}.conv2/bn"),
+             dict(t="conv", n=f"{name}.conv3", b=f"{name}.conv2/bn", o=out, k=1, s=1, p=0), dict(t="bn", n=f"{name}.conv3/bn", b=f"{name}.conv3")]
+    short = bottom
+    if skip:
+        spec += [dict(t="conv", n=f"{name}.skipConv", b=bottom, o=out, k=1, s=stride, p=0), dict(t="bn", n=f"{name}.skipConv/bn", b=f"{name}.skipConv")]
+        short = f"{name}.skipConv/bn"
+    spec += [dict(t="sum", n=f"{name}.sum", b=[f"{name}.conv3/bn", short]), dict(t="relu", n=f"{name}.relu", b=f"{name}.sum")]
+    return f"{name}.sum"
+
+
+def mini_resnet(batch=4, size=16, classes=10, conv_bias=False):
+    """conv-bn-relu-maxpool stem, a strided bottleneck with a projection shortcut, an identity bottleneck, ave-pool, fc, loss."""
+    spec = [dict(t="data", n="data", shape=(batch, 3, size, size)),
+            dict(t="conv", n="conv1", b="data", o=8, k=3, s=1, p=1, bias=conv_bias), dict(t="bn", n="conv1/bn", b="conv1"),
+            dict(t="relu", n="conv1/relu", b="conv1/bn"), dict(t="pool", n="pool1", b="conv1/bn", m="MAX", k=3, s=2, p=0)]
+    top = bottleneck(spec, "resA.1", "pool1", 4, 16, 2, True)
+    top = bottleneck(spec, "resA.2", top, 4, 16, 1, False)
+    hw = lo.pooled_extent(size, 3, 2, 0) // 2
+    spec += [dict(t="pool", n="pool2", b=top, m="AVE", k=hw, s=1, p=0), dict(t="fc", n="fc", b="pool2", o=classes),
+             dict(t="loss", n="loss", b=["fc", "label"])]
+    return spec
+
+
+def to_prototxt(spec, eps=1e-4, maf=0.9):
+    s = 'name: "mini"\n'
+    for L in spec:
+        t, n = L["t"], L["n"]
+        if t == "data":
+            N, Cc, H, W = L["shape"]
+            s += (f'layer {{ name: "data" type: "Input" top: "data" top: "label" input_param {{ shape {{ dim: {N} dim: {Cc} dim: {H} dim: {W} }} '
+                  f'shape {{ dim: {N} }} }} }}\n')
+        elif t == "conv":
+            s += (f'layer {{ name: "{n}" type: "Convolution" bottom: "{L["b"]}" top: "{n}" convolution_param {{ num_output: {L["o"]} '
+                  f'kernel_size: {L["k"]} stride: {L["s"]} pad: {L["p"]} bias_term: {"true" if L.get("bias") else "false"} weight_filler {{ type: "msra" }} }} }}\n')
+        elif t == "bn":
+            s += (f'layer {{ name: "{n}" type: "BatchNorm" bottom: "{L["b"]}" top: "{n}" batch_norm_param {{ moving_average_fraction: {maf} '
+                  f'eps: {eps} scale_bias: true }} }}\n')
+        elif t == "relu":
+            s += f'layer {{ name: "{n}" type: "ReLU" bottom: "{L["b"]}" top: "{L["b"]}" }}\n'
+        elif t == "pool":
+            s += (f'layer {{ name: "{n}" type: "Pooling" bottom: "{L["b"]}" top: "{n}" pooling_param {{ pool: {L["m"]} kernel_size: {L["k"]} '
+                  f'stride: {L["s"]} pad: {L["p"]} }} }}\n')
+        elif t == "sum":
+            s += f'layer {{ name: "{n}" type: "Eltwise" bottom: "{L["b"][0]}" bottom: "{L["b"][1]}" top: "{n}" eltwise_param {{ operation: SUM }} }}\n'
+        elif t == "fc":
+            s += (f'layer {{ name: "{n}" type: "InnerProduct" bottom: "{L["b"]}" top: "{n}" inner_product_param {{ num_output: {L["o"]} '
+                  f'weight_filler {{ type: "msra" }} bias_filler {{ type: "constant" value: 0 }} }} }}\n')
+        elif t == "loss":
+            s += f'layer {{ name: "{n}" type: "SoftmaxWithLoss" bottom: "{L["b"][0]}" bottom: "{L["b"][1]}" top: "{n}" }}\n'
+    return s
+
+
+def param_shapes(spec):
+    """Learnable blobs in Net::AppendParam order: conv w (,b), bn scale, bn shift, fc w, fc b."""
+    shapes, chan = [], {}
+    for L in spec:
+        t, n = L["t"], L["n"]
+        if t == "data":
+            chan["data"] = L["shape"]
+        elif t == "conv":
+            N, Cc, H, W = chan[L["b"]]
+            prm = oracle.ConvParams.make(N, Cc, H, W, L["o"], L["k"], L["s"], L["p"], 1, 1, bool(L.get("bias")))
+            L["prm"] = prm
+            shapes.append((n, "w", prm.w_shape()))
+            if L.get("bias"):
+                shapes.append((n, "b", (L["o"],)))
+            chan[n] = prm.y_shape()
+        elif t == "bn":
+            chan[n] = chan[L["b"]]
+            shapes += [(n, "scale", (chan[n][1],)), (n, "shift", (chan[n][1],))]
+        elif t == "pool":
+            N, Cc, H, W = chan[L["b"]]
+            chan[n] = (N, Cc, lo.pooled_extent(H, L["k"], L["s"], L["p"]), lo.pooled_extent(W, L["k"], L["s"], L["p"]))
+        elif t == "sum":
+            chan[n] = chan[L["b"][0]]
+        elif t == "fc":
+            x = chan[L["b"]]
+            shapes += [(n, "w", (L["o"], int(np.prod(x[1:])))), (n, "b", (L["o"],))]
+            chan[n] = (x[0], L["o"])
+    return shapes
+
+
+def forward_backward(spec, params, data, label, eps=1e-4):
+    """params: list of arrays in param_shapes order.  Returns (loss, grads list, blobs dict of forward values)."""
+    v, saved, pi, pidx = {"data": data, "label": label}, {}, 0, {}
+    for L in spec:
+        t, n = L["t"], L["n"]
+        if t == "conv":
+            w = params[pi]; pidx[n] = pi; pi += 1
+            b = None
+            if L.get("bias"):
+                b = params[pi]; pi += 1
+            saved[n] = v[L["b"]]
+            v[n] = oracle.conv_forward(L["prm"], v[L["b"]], w, b)
+        elif t == "bn":
+            pidx[n] = pi
+            y, xn, _, inv, _, _ = lo.bn_forward_train(v[L["b"]], params[pi], params[pi + 1], eps, 0.9, None, None, True)
+            pi += 2
+            saved[n] = (xn, inv)
+            v[n] = y
+        elif t == "relu":
+            v[L["b"]] = lo.relu_forward(v[L["b"]])
+        elif t == "pool":
+            saved[n] = v[L["b"]].shape
+            v[n], saved[n + "#m"] = lo.pool_forward(v[L["b"]], L["m"], (L["k"],) * 2, (L["s"],) * 2, (L["p"],) * 2)
+        elif t == "sum":
+            v[n] = v[L["b"][0]] + v[L["b"][1]]
+        elif t == "fc":
+            pidx[n] = pi; pi += 2
+            saved[n] = v[L["b"]]
+            v[n] = lo.ip_forward(v[L["b"]], params[pidx[n]], params[pidx[n] + 1])
+        elif t == "loss":
+            saved[n], loss = lo.softmax_loss_forward(v[L["b"][0]], label)
+    grads = [np.zeros_like(p) for p in params]
+    d = {}
+
+    def acc(name, g):
+        d[name] = g if name not in d else d[name] + g
+
+    for L in reversed(spec):
+        t, n = L["t"], L["n"]
+        if t == "loss":
+            acc(L["b"][0], lo.softmax_loss_backward(saved[n], label))
+        elif t == "fc":
+            dw, db, dx = lo.ip_backward(saved[n], params[pidx[n]], d[n])
+            grads[pidx[n]], grads[pidx[n] + 1] = dw.reshape(params[pidx[n]].shape), db
+            acc(L["b"], dx)
+        elif t == "sum":
+            acc(L["b"][0], d[n]); acc(L["b"][1], d[n])
+        elif t == "pool":
+            acc(L["b"], lo.pool_backward(d[n], saved[n + "#m"], saved[n], L["m"], (L["k"],) * 2, (L["s"],) * 2, (L["p"],) * 2))
+        elif t == "relu":
+            d[L["b"]] = lo.relu_backward(d[L["b"]], v[L["b"]])
+        elif t == "bn":
+            xn, inv = saved[n]
+            dg, dbt, dx = lo.bn_backward(d[n], xn, params[pidx[n]], inv)
+            grads[pidx[n]], grads[pidx[n] + 1] = dg, dbt
+            acc(L["b"], dx)
+        elif t == "conv":
+            want_dx = L["b"] != "data"
+            dw, db, dx = oracle.conv_backward(L["prm"], saved[n], params[pidx[n]], d[n], want_dx=want_dx)
+            grads[pidx[n]] = dw
+            if L.get("bias"):
+                grads[pidx[n] + 1] = db
+            if want_dx:
+                acc(L["b"], dx)
+    return float(loss), grads, v, d
+
+
+def sgd_steps(spec, params, data, label, steps, base_lr, momentum, wd):
+    """Solver::Step x steps with lr_policy fixed; returns (losses, params, history)."""
+    params = [p.copy() for p in params]
+    hist = [np.zeros_like(p) for p in params]
+    losses = []
+    for _ in range(steps):
+        loss, grads, _, _ = forward_backward(spec, params, data, label)
+        losses.append(loss)
+        for i, g in enumerate(grads):
+            _, w, h = oracle.sgd_update(g, params[i], hist[i], momentum, base_lr, wd)
+            params[i], hist[i] = w.reshape(params[i].shape), h.reshape(params[i].shape)
+    return losses, params, hist

@@ -132,3 +132,21 @@ def test_reference_solver_prototxts():
         assert net.endswith(".prototxt") and d["max_iter"] > 0
         if policy:
             assert d["lr_policy"] == policy and d["base_lr"] == pytest.approx(lr)
+
+
+def test_generated_resnet50_has_the_reference_inventory():
+    """caffe_mpi_b200.models.resnet50_prototxt (used on the GPU box, where the reference tree is absent) against the
+    inventory of models/resnet50/train_val.prototxt: SURVEY Appendix A numbers, and layer by layer when the file is here."""
+    import os
+    from caffe_mpi_b200 import host_api, models
+    net = host_api.Net(models.resnet50_prototxt(2), "TRAIN", is_text=True)
+    params = net.learnable_params()
+    assert len(net.conv_layers()) == 53 and len(params) == 161
+    assert sum(p[1] for p in params) == 25557032
+    ref = "/root/reference/models/resnet50/train_val.prototxt"
+    if os.path.exists(ref):
+        rnet = host_api.Net(ref, "TRAIN", batch_override=2)
+        assert net.layers() == [l for l in rnet.layers() if l[1] != "Accuracy"]
+        assert params == rnet.learnable_params()
+        a, b = net.conv_layers(), rnet.conv_layers()
+        assert [(n, bytes(p), pd) for n, p, pd in a] == [(n, bytes(p), pd) for n, p, pd in b]

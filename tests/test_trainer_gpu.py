@@ -1,0 +1,90 @@
+"""Whole-net parity on the GPU: TrainNet (prototxt -> layers -> ForwardBackward -> SGD) against tests/netoracle.py.
+Tolerance: 1e-3 relative (max|a-ref| / max|ref| per tensor), the north_star's bar for fp32 mode."""
+import numpy as np
+import pytest
+
+from caffe_mpi_b200 import capi, host_api, models
+import netoracle as no
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+SOLVER = 'base_lr: 0.05 lr_policy: "fixed" momentum: 0.9 weight_decay: 0.0005 max_iter: 100 solver_mode: GPU'
+
+
+def rel(a, ref):
+    return float(np.max(np.abs(a.reshape(-1) - ref.reshape(-1))) / max(np.max(np.abs(ref)), 1e-20))
+
+
+def make_trainer(spec, rng, classes=10, math=capi.MATH_FP32):
+    shapes = no.param_shapes(spec)
+    t = host_api.Trainer(no.to_prototxt(spec), SOLVER, num_classes=classes, math=math)
+    assert t.num_params() == len(shapes)
+    params = []
+    for i, (layer, kind, shp) in enumerate(shapes):
+        if kind == "w":
+            p = rng.standard_normal(shp).astype(np.float32) * np.float32(np.sqrt(2.0 / np.prod(shp[1:])))
+        elif kind == "scale":
+            p = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+        else:
+            p = rng.uniform(-0.2, 0.2, shp).astype(np.float32)
+        assert t.get_param(i).size == p.size
+        t.set_param(i, p)
+        params.append(p)
+    dshape = spec[0]["shape"]
+    data = rng.standard_normal(dshape).astype(np.float32)
+    label = rng.integers(0, classes, dshape[0]).astype(np.float32)
+    t.set_blob("data", data)
+    t.set_blob("label", label)
+    return t, params, data, label
+
+
+@pytest.mark.parametrize("conv_bias", [False, True])
+def test_forward_backward_matches_oracle(rng, conv_bias):
+    spec = no.mini_resnet(conv_bias=conv_bias)
+    t, params, data, label = make_trainer(spec, rng)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss)
+    for name in ("conv1", "pool1", "resA.1.sum", "resA.2.sum", "pool2", "fc"):
+        assert rel(t.get_blob(name), v[name]) <= TOL, name
+    for name in ("fc", "pool2", "resA.2.sum", "resA.1.conv1", "pool1", "conv1"):
+        assert rel(t.get_blob(name, diff=True), d[name]) <= TOL, name
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g) <= TOL, no.param_shapes(spec)[i]
+
+
+def test_sgd_steps_match_oracle(rng):
+    spec = no.mini_resnet()
+    t, params, data, label = make_trainer(spec, rng)
+    ref_losses, ref_params, ref_hist = no.sgd_steps(spec, params, data, label, 3, 0.05, 0.9, 0.0005)
+    losses = []
+    for _ in range(3):
+        t.step(1)
+        losses.append(t.loss())
+    np.testing.assert_allclose(losses, ref_losses, rtol=2 * TOL)
+    assert ref_losses[-1] < ref_losses[0]
+    for i, (p, h) in enumerate(zip(ref_params, ref_hist)):
+        assert rel(t.get_param(i, 0), p) <= 2 * TOL, i
+        assert rel(t.get_param(i, 2), h) <= 5 * TOL, i
+        assert not t.get_param(i, 1).any()            # diffs cleared by the update (sgd_solver.cu / clear_grads)
+
+
+def test_tf32_mode_within_its_tolerance(rng):
+    spec = no.mini_resnet()
+    t, params, data, label = make_trainer(spec, rng, math=capi.MATH_TF32)
+    loss = t.forward_backward()
+    ref_loss, grads, _, _ = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= 1e-2 * abs(ref_loss)
+
+
+def test_resnet50_one_step_runs_and_learns(rng):
+    """Full ResNet-50 train graph at batch 8, 224x224: loss starts near ln(1000) and goes down on a fixed batch."""
+    t = host_api.Trainer(models.resnet50_prototxt(8), 'base_lr: 0.01 lr_policy: "fixed" momentum: 0.9 weight_decay: 1e-4 max_iter: 10', batch=8)
+    assert t.num_params() == 161
+    t.step(1)
+    first = t.loss()
+    assert 5.0 < first < 9.5
+    t.step(4)
+    assert t.loss() < first
+    assert t.timed_steps(2, copy_input=True, read_loss=True) > 0
+    assert np.isfinite(t.get_param(0)).all()
