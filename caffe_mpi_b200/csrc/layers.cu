@@ -12,7 +12,10 @@
 //   SoftmaxWithLoss src/caffe/layers/softmax_loss_layer.cpp:96-160  loss = -sum log p[label] / N (VALID normalisation, no
 //                                                                    ignore_label); dx = (p - onehot) * loss_weight / N
 #include <float.h>
+#include <cooperative_groups.h>
 #include "b2c_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b2c {
 
@@ -61,62 +64,185 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(size_t n, const float* __
 }
 
 // ---- BatchNorm --------------------------------------------------------------------------------------------------
-// one block per channel: two passes over the channel's N*S values (mean, then mean of squared deviations, as the
-// reference does -- not E[x^2]-E[x]^2), then the running-average update.
-__global__ void __launch_bounds__(512)
+// Per-channel reductions run as one thread-block CLUSTER of 1..8 CTAs per channel (sized by the host from the channel's
+// extent): each CTA streams its share of the channel's N*S values (float4 when the planes are 16-byte aligned), the eight partial sums meet in rank 0 through
+// distributed shared memory in rank order (deterministic), no scratch buffer, no atomics, one launch.
+// Statistics use sums of (x - k) and (x - k)^2 with k = the channel's first value, combined in double: one pass over
+// HBM instead of the reference's two, without the cancellation of a raw E[x^2] - E[x]^2.
+constexpr int BN_CLUSTER = 8;
+constexpr int BN_THREADS = 256;
+
+template <bool VEC> struct PlaneCursor {       // walks a channel's planes: flattened unit index -> (image n, offset p)
+  unsigned n, p;
+  __device__ __forceinline__ void init(unsigned i, unsigned units) { n = i / units; p = i - n * units; }
+  __device__ __forceinline__ void advance(unsigned step, unsigned units) { p += step; while (p >= units) { p -= units; ++n; } }
+};
+
+// MODE 0: a = sum (x-k), b = sum (x-k)^2   (q unused)      MODE 1: a = sum dy*xn, b = sum dy   (x = dy, q = xnorm)
+template <bool VEC, int MODE>
+__device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, const float* __restrict__ x, const float* __restrict__ q,
+                                                   float k, unsigned rank, unsigned nranks, float& a, float& b) {
+  constexpr int U = 4;                                          // independent loads in flight per thread
+  const unsigned units = VEC ? S / 4 : S;                       // units per plane
+  const unsigned total = (unsigned)N * units;
+  const unsigned len = (total + nranks - 1) / nranks;
+  const unsigned lo = min(total, rank * len), hi = min(total, lo + len);
+  a = 0.f; b = 0.f;
+  float a2 = 0.f, b2 = 0.f;
+  PlaneCursor<VEC> cur;
+  unsigned i = lo + threadIdx.x;
+  if (i < hi) cur.init(i, units);
+  for (; i < hi; i += U * BN_THREADS) {
+    size_t off[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ok[u] = i + u * BN_THREADS < hi;
+      off[u] = ((size_t)cur.n * C + c) * units + cur.p;
+      cur.advance(BN_THREADS, units);
+    }
+    if (VEC) {
+      float4 v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(k, k, k, k);
+        if (MODE == 1) w[u] = ok[u] ? reinterpret_cast<const float4*>(q)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (MODE == 0) {
+          const float d0 = v[u].x - k, d1 = v[u].y - k, d2 = v[u].z - k, d3 = v[u].w - k;
+          a += d0 + d1; a2 += d2 + d3;
+          b = fmaf(d0, d0, b); b2 = fmaf(d1, d1, b2); b = fmaf(d2, d2, b); b2 = fmaf(d3, d3, b2);
+        } else {
+          a = fmaf(v[u].x, w[u].x, a); a2 = fmaf(v[u].y, w[u].y, a2); a = fmaf(v[u].z, w[u].z, a); a2 = fmaf(v[u].w, w[u].w, a2);
+          b += v[u].x + v[u].y; b2 += v[u].z + v[u].w;
+        }
+      }
+    } else {
+      float v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u] = ok[u] ? x[off[u]] : k;
+        if (MODE == 1) w[u] = ok[u] ? q[off[u]] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (MODE == 0) { const float d = v[u] - k; a += d; b = fmaf(d, d, b); }
+        else { a = fmaf(v[u], w[u], a); b += v[u]; }
+      }
+    }
+  }
+  a += a2; b += b2;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(BN_THREADS)
 bn_stats_kernel(int N, int C, int S, const float* __restrict__ x, float eps, float maf, int first,
                 float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
-  const int c = blockIdx.x;
-  const size_t cnt = (size_t)N * S;
-  float s = 0.f, dummy = 0.f;
-  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) { const size_t n = i / S, p = i - n * S; s += x[(n * C + c) * S + p]; }
-  block_sum2(s, dummy);
-  const float m = s / (float)cnt;
-  float v = 0.f;
-  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) { const size_t n = i / S, p = i - n * S; const float d = x[(n * C + c) * S + p] - m; v += d * d; }
-  block_sum2(v, dummy);
-  const float var_eps = v / (float)cnt + eps;          // batch_norm_layer.cpp:183-186 (eps folded in before the average)
-  if (threadIdx.x == 0) {
+  __shared__ float2 part;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int c = blockIdx.y;
+  const float k = x[(size_t)c * S];
+  float a, b;
+  bn_channel_partial<VEC, 0>(N, C, S, c, x, nullptr, k, rank, cluster.num_blocks(), a, b);
+  block_sum2(a, b);
+  if (threadIdx.x == 0) part = make_float2(a, b);
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
+    const double cnt = (double)N * S, m1 = s1 / cnt;
+    const float m = (float)((double)k + m1);
+    const float var_eps = (float)fmax(s2 / cnt - m1 * m1, 0.0) + eps;   // batch_norm_layer.cpp:183-186 (eps folded in before the average)
     mean[c] = m;
     invstd[c] = 1.0f / sqrtf(var_eps);
     if (first) { run_mean[c] = m; run_var[c] = var_eps; }                         // iter_ <= 1: copy (:199-204)
     else { run_mean[c] = (1.f - maf) * m + maf * run_mean[c]; run_var[c] = (1.f - maf) * var_eps + maf * run_var[c]; }
   }
-}
-__global__ void __launch_bounds__(256)
-bn_norm_kernel(size_t total, int C, int S, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
-               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ xnorm, float* __restrict__ y) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)((i / S) % C);
-    const float xn = (x[i] - mean[c]) * invstd[c];
-    xnorm[i] = xn;
-    y[i] = gamma ? xn * gamma[c] + beta[c] : xn;
-  }
+  cluster.sync();                                   // remote shared memory stays valid until rank 0 has read it
 }
 // per channel: dgamma = sum dy*xn, dbeta = sum dy (both OVERWRITTEN, batch_norm_layer.cpp:247-252)
-__global__ void __launch_bounds__(512)
+template <bool VEC>
+__global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_reduce_kernel(int N, int C, int S, const float* __restrict__ dy, const float* __restrict__ xnorm,
                      float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy) {
-  const int c = blockIdx.x;
-  const size_t cnt = (size_t)N * S;
-  float a = 0.f, b = 0.f;
-  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const size_t n = i / S, p = i - n * S, idx = (n * C + c) * S + p;
-    const float d = dy[idx];
-    a += d * xnorm[idx]; b += d;
-  }
+  __shared__ float2 part;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int c = blockIdx.y;
+  float a, b;
+  bn_channel_partial<VEC, 1>(N, C, S, c, dy, xnorm, 0.f, rank, cluster.num_blocks(), a, b);
   block_sum2(a, b);
-  if (threadIdx.x == 0) { sum_dy_xn[c] = a; sum_dy[c] = b; }
+  if (threadIdx.x == 0) part = make_float2(a, b);
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
+    sum_dy_xn[c] = (float)s1; sum_dy[c] = (float)s2;
+  }
+  cluster.sync();
+}
+
+// Elementwise passes: each block owns BN_EW_PER_THREAD * 256 consecutive units (float4 or float) of the NCHW tensor and
+// walks (plane, offset) incrementally, so there is one integer division per thread, not per element.
+constexpr int BN_EW_PER_THREAD = 8;
+template <bool VEC> struct ChanCursor {
+  unsigned p, c;
+  __device__ __forceinline__ void init(size_t i, unsigned units, unsigned C) { const size_t plane = i / units; p = (unsigned)(i - plane * units); c = (unsigned)(plane % C); }
+  __device__ __forceinline__ void advance(unsigned step, unsigned units, unsigned C) { p += step; while (p >= units) { p -= units; if (++c == C) c = 0; } }
+};
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+bn_norm_kernel(size_t total_units, int C, int S, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ xnorm, float* __restrict__ y) {
+  const unsigned units = VEC ? S / 4 : S;
+  size_t i = (size_t)blockIdx.x * (256 * BN_EW_PER_THREAD) + threadIdx.x;
+  if (i >= total_units) return;
+  ChanCursor<VEC> cur;
+  cur.init(i, units, C);
+#pragma unroll 2
+  for (int k = 0; k < BN_EW_PER_THREAD && i < total_units; ++k, i += 256) {
+    const float m = mean[cur.c], is = invstd[cur.c], g = gamma ? gamma[cur.c] : 1.f, bt = gamma ? beta[cur.c] : 0.f;
+    if (VEC) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      float4 n4, o4;
+      n4.x = (v.x - m) * is; n4.y = (v.y - m) * is; n4.z = (v.z - m) * is; n4.w = (v.w - m) * is;
+      o4.x = gamma ? n4.x * g + bt : n4.x; o4.y = gamma ? n4.y * g + bt : n4.y; o4.z = gamma ? n4.z * g + bt : n4.z; o4.w = gamma ? n4.w * g + bt : n4.w;
+      reinterpret_cast<float4*>(xnorm)[i] = n4;
+      reinterpret_cast<float4*>(y)[i] = o4;
+    } else {
+      const float xn = (x[i] - m) * is;
+      xnorm[i] = xn;
+      y[i] = gamma ? xn * g + bt : xn;
+    }
+    cur.advance(256, units, C);
+  }
 }
 // dx = gamma * invstd * (dy - mean(dy) - xn * mean(dy*xn))     (means over N*S; with gamma folded: :254-281)
+template <bool VEC>
 __global__ void __launch_bounds__(256)
-bn_bwd_dx_kernel(size_t total, int C, int S, float inv_cnt, const float* __restrict__ dy, const float* __restrict__ xnorm,
+bn_bwd_dx_kernel(size_t total_units, int C, int S, float inv_cnt, const float* __restrict__ dy, const float* __restrict__ xnorm,
                  const float* __restrict__ gamma, const float* __restrict__ invstd, const float* __restrict__ sum_dy_xn,
                  const float* __restrict__ sum_dy, float* __restrict__ dx) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)((i / S) % C);
-    const float g = gamma ? gamma[c] : 1.f;
-    dx[i] = g * invstd[c] * (dy[i] - sum_dy[c] * inv_cnt - xnorm[i] * sum_dy_xn[c] * inv_cnt);
+  const unsigned units = VEC ? S / 4 : S;
+  size_t i = (size_t)blockIdx.x * (256 * BN_EW_PER_THREAD) + threadIdx.x;
+  if (i >= total_units) return;
+  ChanCursor<VEC> cur;
+  cur.init(i, units, C);
+#pragma unroll 2
+  for (int k = 0; k < BN_EW_PER_THREAD && i < total_units; ++k, i += 256) {
+    const float gi = (gamma ? gamma[cur.c] : 1.f) * invstd[cur.c], mdy = sum_dy[cur.c] * inv_cnt, mdx = sum_dy_xn[cur.c] * inv_cnt;
+    if (VEC) {
+      const float4 d = reinterpret_cast<const float4*>(dy)[i], n4 = reinterpret_cast<const float4*>(xnorm)[i];
+      float4 o;
+      o.x = gi * (d.x - mdy - n4.x * mdx); o.y = gi * (d.y - mdy - n4.y * mdx); o.z = gi * (d.z - mdy - n4.z * mdx); o.w = gi * (d.w - mdy - n4.w * mdx);
+      reinterpret_cast<float4*>(dx)[i] = o;
+    } else {
+      dx[i] = gi * (dy[i] - mdy - xnorm[i] * mdx);
+    }
+    cur.advance(256, units, C);
   }
 }
 
@@ -263,27 +389,61 @@ extern "C" int b2c_relu_backward(size_t n, const float* dy, const float* x, floa
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
+// cluster size for the per-channel reductions: ~16K values per CTA, at least two CTAs per SM in flight, at most 8
+static unsigned bn_cluster_size(int N, int C, int S) {
+  const size_t E = (size_t)N * S;
+  unsigned cs = 1;
+  while (cs < BN_CLUSTER && E / (cs * 2) >= 16384) cs *= 2;
+  while (cs < BN_CLUSTER && (size_t)C * cs < 2u * (unsigned)sm_count()) cs *= 2;
+  return cs;
+}
+template <typename... Args>
+static void launch_clustered(void (*kernel)(Args...), unsigned cs, int C, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, C, 1);
+  cfg.blockDim = dim3(BN_THREADS, 1, 1);
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+static bool vec_ok(int S, std::initializer_list<const void*> ptrs) {
+  if (S % 4) return false;
+  for (const void* p : ptrs) if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+  return true;
+}
 extern "C" int b2c_bn_forward_train(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
                                     float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
                                     float* save_mean, float* save_invstd, float* xnorm, float* y, void* stream) {
   NEED(x && y && xnorm && save_mean && save_invstd && running_mean && running_var && N > 0 && C > 0 && S > 0, "b2c_bn_forward_train: bad argument");
   NEED((gamma == nullptr) == (beta == nullptr), "b2c_bn_forward_train: gamma and beta go together");
-  bn_stats_kernel<<<C, 512, 0, as_stream(stream)>>>(N, C, S, x, eps, moving_average_fraction, first_iteration, save_mean, save_invstd,
-                                                    running_mean, running_var);
+  NEED((size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_forward_train: channel extent out of range");
+  const bool vec = vec_ok(S, {x, y, xnorm});
+  const unsigned cs = bn_cluster_size(N, C, S);
+  launch_clustered(vec ? bn_stats_kernel<true> : bn_stats_kernel<false>, cs, C, stream, N, C, S, x, eps, moving_average_fraction, first_iteration,
+                   save_mean, save_invstd, running_mean, running_var);
   B2C_POST_LAUNCH();
-  const size_t total = (size_t)N * C * S;
-  bn_norm_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, C, S, x, save_mean, save_invstd, gamma, beta, xnorm, y);
+  const size_t units = (size_t)N * C * (vec ? S / 4 : S);
+  const unsigned blocks = (unsigned)((units + 256 * BN_EW_PER_THREAD - 1) / (256 * BN_EW_PER_THREAD));
+  if (vec) bn_norm_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(units, C, S, x, save_mean, save_invstd, gamma, beta, xnorm, y);
+  else bn_norm_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(units, C, S, x, save_mean, save_invstd, gamma, beta, xnorm, y);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
 extern "C" int b2c_bn_backward(int N, int C, int S, const float* dy, const float* xnorm, const float* gamma, const float* save_invstd,
                                float* dgamma, float* dbeta, float* dx, void* stream) {
   NEED(dy && xnorm && save_invstd && dgamma && dbeta && dx, "b2c_bn_backward: null (dgamma/dbeta double as the reduction scratch)");
-  bn_bwd_reduce_kernel<<<C, 512, 0, as_stream(stream)>>>(N, C, S, dy, xnorm, dgamma, dbeta);
+  NEED(N > 0 && C > 0 && S > 0 && (size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_backward: channel extent out of range");
+  const bool vec = vec_ok(S, {dy, xnorm, dx});
+  launch_clustered(vec ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, bn_cluster_size(N, C, S), C, stream, N, C, S, dy, xnorm, dgamma, dbeta);
   B2C_POST_LAUNCH();
-  const size_t total = (size_t)N * C * S;
-  bn_bwd_dx_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, C, S, 1.0f / ((float)N * S), dy, xnorm, gamma, save_invstd,
-                                                                      dgamma, dbeta, dx);
+  const size_t units = (size_t)N * C * (vec ? S / 4 : S);
+  const unsigned blocks = (unsigned)((units + 256 * BN_EW_PER_THREAD - 1) / (256 * BN_EW_PER_THREAD));
+  const float inv_cnt = 1.0f / ((float)N * S);
+  if (vec) bn_bwd_dx_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(units, C, S, inv_cnt, dy, xnorm, gamma, save_invstd, dgamma, dbeta, dx);
+  else bn_bwd_dx_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(units, C, S, inv_cnt, dy, xnorm, gamma, save_invstd, dgamma, dbeta, dx);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }

@@ -54,6 +54,7 @@ def pooled_extent(n, k, s, p):                   # PoolingLayer::Reshape: ceil m
 
 # PoolingLayer::Forward_cpu / Backward_cpu, src/caffe/layers/pooling_layer.cpp:129-318
 def pool_forward(x, method, k, s, p):
+    assert method in (0, 1), "method: 0 = MAX, 1 = AVE (PoolingParameter.PoolMethod)"
     N, C, H, W = x.shape
     Ho, Wo = pooled_extent(H, k[0], s[0], p[0]), pooled_extent(W, k[1], s[1], p[1])
     y = np.zeros((N, C, Ho, Wo), np.float32)
@@ -77,6 +78,7 @@ def pool_forward(x, method, k, s, p):
 
 
 def pool_backward(dy, mask, x_shape, method, k, s, p):
+    assert method in (0, 1)
     N, C, H, W = x_shape
     Ho, Wo = dy.shape[2:]
     dx = np.zeros(x_shape, np.float64)

@@ -6,6 +6,8 @@ import numpy as np
 import oracle
 from oracle import layers_oracle as lo
 
+POOL = {"MAX": 0, "AVE": 1}          # PoolingParameter.PoolMethod (caffe.proto)
+
 
 def bottleneck(spec, name, bottom, mid, out, stride, skip):
     spec += [dict(t="conv", n=f"{name}.conv1", b=bottom, o=mid, k=1, s=stride, p=0), dict(t="bn", n=f"{name}.conv1/bn", b=f"{name}.conv1"),
@@ -115,7 +117,7 @@ def forward_backward(spec, params, data, label, eps=1e-4):
             v[L["b"]] = lo.relu_forward(v[L["b"]])
         elif t == "pool":
             saved[n] = v[L["b"]].shape
-            v[n], saved[n + "#m"] = lo.pool_forward(v[L["b"]], L["m"], (L["k"],) * 2, (L["s"],) * 2, (L["p"],) * 2)
+            v[n], saved[n + "#m"] = lo.pool_forward(v[L["b"]], POOL[L["m"]], (L["k"],) * 2, (L["s"],) * 2, (L["p"],) * 2)
         elif t == "sum":
             v[n] = v[L["b"][0]] + v[L["b"][1]]
         elif t == "fc":
@@ -141,7 +143,7 @@ def forward_backward(spec, params, data, label, eps=1e-4):
         elif t == "sum":
             acc(L["b"][0], d[n]); acc(L["b"][1], d[n])
         elif t == "pool":
-            acc(L["b"], lo.pool_backward(d[n], saved[n + "#m"], saved[n], L["m"], (L["k"],) * 2, (L["s"],) * 2, (L["p"],) * 2))
+            acc(L["b"], lo.pool_backward(d[n], saved[n + "#m"], saved[n], POOL[L["m"]], (L["k"],) * 2, (L["s"],) * 2, (L["p"],) * 2))
         elif t == "relu":
             d[L["b"]] = lo.relu_backward(d[L["b"]], v[L["b"]])
         elif t == "bn":

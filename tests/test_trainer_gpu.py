@@ -11,8 +11,8 @@ TOL = 1e-3
 SOLVER = 'base_lr: 0.05 lr_policy: "fixed" momentum: 0.9 weight_decay: 0.0005 max_iter: 100 solver_mode: GPU'
 
 
-def rel(a, ref):
-    return float(np.max(np.abs(a.reshape(-1) - ref.reshape(-1))) / max(np.max(np.abs(ref)), 1e-20))
+def rel(a, ref, floor=1e-20):
+    return float(np.max(np.abs(a.reshape(-1) - ref.reshape(-1))) / max(np.max(np.abs(ref)), floor))
 
 
 def make_trainer(spec, rng, classes=10, math=capi.MATH_FP32):
@@ -49,8 +49,11 @@ def test_forward_backward_matches_oracle(rng, conv_bias):
         assert rel(t.get_blob(name), v[name]) <= TOL, name
     for name in ("fc", "pool2", "resA.2.sum", "resA.1.conv1", "pool1", "conv1"):
         assert rel(t.get_blob(name, diff=True), d[name]) <= TOL, name
+    # gradients that are mathematically zero (a conv bias in front of BatchNorm, whose mean subtraction cancels it) are
+    # rounding noise on both sides: the denominator is floored at 1e-3 of the largest gradient in the net
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
     for i, g in enumerate(grads):
-        assert rel(t.get_param(i, 1), g) <= TOL, no.param_shapes(spec)[i]
+        assert rel(t.get_param(i, 1), g, floor) <= TOL, no.param_shapes(spec)[i]
 
 
 def test_sgd_steps_match_oracle(rng):
@@ -63,9 +66,10 @@ def test_sgd_steps_match_oracle(rng):
         losses.append(t.loss())
     np.testing.assert_allclose(losses, ref_losses, rtol=2 * TOL)
     assert ref_losses[-1] < ref_losses[0]
+    hfloor = 1e-3 * max(float(np.max(np.abs(h))) for h in ref_hist)
     for i, (p, h) in enumerate(zip(ref_params, ref_hist)):
         assert rel(t.get_param(i, 0), p) <= 2 * TOL, i
-        assert rel(t.get_param(i, 2), h) <= 5 * TOL, i
+        assert rel(t.get_param(i, 2), h, hfloor) <= 5 * TOL, i
         assert not t.get_param(i, 1).any()            # diffs cleared by the update (sgd_solver.cu / clear_grads)
 
 

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Command-line shell in the shape of the reference's `caffe` tool (tools/caffe.cpp: train / time / device_query), over the
+C++ host layer -- SURVEY 8(f) rank 3.  Data layers are replaced by the synthetic in-memory source.
+
+  python tools/caffe.py train --solver=models/resnet50/solver.prototxt [--iterations=N] [--batch=B]     (1 GPU)
+  python -m torch.distributed.run --nproc-per-node N ... tools/caffe.py train --solver=...              (N GPUs, one rank each)
+  python tools/caffe.py time --model=models/resnet50/train_val.prototxt [--iterations=50] [--batch=B]
+  python tools/caffe.py device_query
+"""
+import argparse, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def log(msg):
+    t = time.localtime()
+    print("I%02d%02d %02d:%02d:%02d caffe.py] %s" % (t.tm_mon, t.tm_mday, t.tm_hour, t.tm_min, t.tm_sec, msg), flush=True)
+
+
+def cmd_device_query(_):
+    from caffe_mpi_b200 import capi
+    import ctypes as C
+    rt = C.CDLL("libcudart.so")
+    n = C.c_int()
+    if rt.cudaGetDeviceCount(C.byref(n)) != 0 or n.value == 0:
+        sys.exit("caffe.py: no CUDA device (there is no CPU mode)")
+    log("libb2c version %d, %d device(s)" % (capi.lib().b2c_version(), n.value))
+
+
+def build_trainer(args, net, net_is_text, solver, solver_is_text):
+    from caffe_mpi_b200 import host_api
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    batch = host_api.divide_batch_size(args.batch, world) if args.batch and world > 1 else args.batch
+    t = host_api.Trainer(net, solver, batch=batch or 0, num_classes=args.classes, seed=args.seed + rank, net_is_text=net_is_text,
+                         solver_is_text=solver_is_text)
+    if world > 1:                              # P2PSync: one solver per GPU, rank 0 is the root solver (parallel.cpp:26-60)
+        import torch, torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("gloo")
+        ids = [t.new_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        t.attach_sync(world, rank, ids[0])
+    return t, rank, world
+
+
+def cmd_train(args):
+    from caffe_mpi_b200 import host_api
+    if not args.solver:
+        sys.exit("caffe.py train: Need a solver definition to train (--solver=...)")
+    s, net_path = host_api.solver_from_prototxt(args.solver)
+    d = host_api.solver_describe(s)
+    net_path = args.model or net_path
+    if not os.path.exists(net_path):
+        sys.exit("caffe.py train: net file %r named by the solver does not exist (paths are relative to the working directory)" % net_path)
+    t, rank, world = build_trainer(args, net_path, False, args.solver, False)
+    iters = args.iterations or d["max_iter"]
+    if rank == 0:
+        log("Solving %s: %d learnable blobs, lr_policy %s base_lr %g momentum %g weight_decay %g, %d iteration(s) on %d GPU(s)" %
+            (net_path, t.num_params(), d["lr_policy"], d["base_lr"], d["momentum"], d["weight_decay"], iters, world))
+    done = 0
+    while done < iters:
+        n = min(args.display, iters - done)
+        ms = t.timed_steps(n, copy_input=True)
+        done += n
+        if rank == 0:
+            log("Iteration %d (%.2f iter/s), loss = %.6g" % (done, n / (ms / 1e3), t.loss()))
+    if rank == 0:
+        log("Optimization Done.")
+
+
+def cmd_time(args):
+    from caffe_mpi_b200 import models
+    if not args.model:
+        sys.exit("caffe.py time: Need a model definition to time (--model=...)")
+    t, rank, world = build_trainer(args, args.model, False, models.RESNET50_SOLVER, True)
+    t.step(3)
+    t.sync()
+    ms = t.timed_steps(args.iterations or 50)
+    if rank == 0:
+        log("Average Forward-Backward-Update: %.4f ms over %d iterations." % (ms / (args.iterations or 50), args.iterations or 50))
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("command", choices=["train", "time", "device_query"])
+    ap.add_argument("--solver", "-solver", default="")
+    ap.add_argument("--model", "-model", default="")
+    ap.add_argument("--iterations", "-iterations", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0, help="global batch size override (divided over the ranks like parallel.cpp:284-293)")
+    ap.add_argument("--classes", type=int, default=1000)
+    ap.add_argument("--display", type=int, default=20)
+    ap.add_argument("--seed", type=int, default=1701)
+    args = ap.parse_args()
+    {"train": cmd_train, "time": cmd_time, "device_query": cmd_device_query}[args.command](args)
+
+
+if __name__ == "__main__":
+    main()
