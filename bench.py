@@ -351,6 +351,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed_run(True, False)
     allreduce = time_allreduce()
+    full_net = None if args.no_full_net else full_net_measure(args, N, world, rank, dev)
 
     if rank == 0:
         pk = peaks()
@@ -393,8 +394,8 @@ def run_ours(args):
                          "all_conv_kernels": {"achieved": ach_all, "frac": ach_all / tf32_peak},
                          "ms_per_step": {k: round(v, 3) for k, v in per.items()}},
         }
-        if world == 1 and not args.no_full_net:
-            out["full_net"] = full_net_measure(args, N)
+        if full_net is not None:
+            out["full_net"] = full_net
         if world == 1:
             run, cores, kind, desc = reference_sample_runner()
             run(1)
@@ -409,27 +410,48 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def full_net_measure(args, N):
+def full_net_measure(args, N, world=1, rank=0, dev=None):
     """Supplementary line: the WHOLE models/resnet50/train_val.prototxt graph -- conv, BatchNorm,
-    ReLU, pooling, Eltwise, InnerProduct, SoftmaxWithLoss forward + backward, SGD update -- through caffe::TrainNet
-    (host/train_net.cpp), timed with CUDA events on the net's own stream.  Not the headline while the non-conv kernels
-    are first-cut; reported so the distance between the hot path and the full training step is on record."""
+    ReLU, pooling, Eltwise, InnerProduct, SoftmaxWithLoss forward + backward, bucketed gradient allreduce through the
+    C++ P2PSync / ReduceScheduler (N > 1) and the SGD update -- through caffe::TrainNet (host/train_net.cpp), timed with
+    CUDA events on the net's own stream, max over ranks.  Not the headline while the non-conv kernels are first-cut;
+    reported so the distance between the hot path and the full training step is on record."""
     try:
         from caffe_mpi_b200 import capi, host_api, models
         import torch
+        import torch.distributed as dist
         torch.cuda.empty_cache()
-        t = host_api.Trainer(models.resnet50_prototxt(N), models.RESNET50_SOLVER, batch=N,
+        t = host_api.Trainer(models.resnet50_prototxt(N), models.RESNET50_SOLVER, batch=N, seed=1701 + rank,
                              math=capi.MATH_TF32 if args.math == "tf32" else capi.MATH_FP32)
+        if world > 1:
+            ids = [t.new_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            t.attach_sync(world, rank, ids[0])
+
+        def mx(ms):
+            if world == 1:
+                return ms
+            v = torch.tensor([ms], device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            return float(v.item())
+
         t.step(args.warmup)
         t.sync()
-        ms = t.timed_steps(args.steps)
+        if world > 1:
+            dist.barrier()
+        ms = mx(t.timed_steps(args.steps))
         loss = t.loss()
         t.step(1, copy_input=True)
-        ms_e2e = t.timed_steps(args.steps, copy_input=True, read_loss=True)
-        return {"metric": "images/sec ResNet-50 fp32 train, full prototxt graph (all layers fwd+bwd + SGD)",
-                "value": N * args.steps / (ms / 1e3), "unit": "images/sec", "ms_per_step": ms / args.steps,
-                "e2e": {"value": N * args.steps / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": t.input_bytes(),
-                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        t.sync()
+        if world > 1:
+            dist.barrier()
+        ms_e2e = mx(t.timed_steps(args.steps, copy_input=True, read_loss=True))
+        imgs = N * world * args.steps
+        return {"metric": "images/sec ResNet-50 fp32 train, full prototxt graph (all layers fwd+bwd"
+                          + (" + bucketed allreduce" if world > 1 else "") + " + SGD)",
+                "value": imgs / (ms / 1e3), "unit": "images/sec", "ms_per_step": ms / args.steps, "n_gpus": world,
+                "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": t.input_bytes() * world,
+                        "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
                 "loss_after_warmup": loss, "learnable_blobs": t.num_params(), "activation_floats": t.activation_floats(),
                 "accuracy_layers": "skipped (no gradient, not on the training path)"}
     except Exception as e:                       # supplementary measurement: report, never mask
