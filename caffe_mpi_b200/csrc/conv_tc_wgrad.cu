@@ -8,6 +8,7 @@
 // smem tiles are filled "lanes along K": dY with 128-bit loads, X through the im2col gather.  The
 // reduction is split across CTAs (grid.x); partial tiles go to a workspace and a second, deterministic
 // kernel adds them to dW in split order (the reference accumulates image by image, also a fixed order).
+#include <cuda.h>
 #include <stdlib.h>
 #include "b2c_common.cuh"
 #include "tc_common.cuh"
@@ -361,6 +362,200 @@ wgrad_reduce_kernel(const float* __restrict__ part, int splits, long long n, flo
   }
 }
 
+// =====================================================================================================================
+// 1x1 / stride 1 / pad 0 layers (24 of ResNet-50's 53): per image both operands are plain row-major matrices with the
+// reduction axis q = (ho,wo) contiguous -- dY[n] is [O x P], X[n] is [C x P] -- so neither needs a gather:
+//   * one elected thread drops [128 x 32] (dY) and [N_TILE x 32] (X) fp32 boxes into shared memory with TMA
+//     (3-D tensor maps {P, rows, N}, SWIZZLE_128B = the canonical K-major UMMA layout; rows past O / C and columns
+//     past P are zero-filled by the TMA unit, which is exactly the padding the GEMM needs);
+//   * the RAW tile is the TF32 "hi" operand as it stands: kind::tf32 reads the top 19 bits of each fp32 word, i.e.
+//     a & 0xffffe000 -- the same truncation split_tf32() applies in software;
+//   * 8 converter warps produce the "lo" tiles, lo = a - (a & 0xffffe000), position by position (the copy is
+//     layout-agnostic: same swizzled offset in a second buffer), 12 x (LDS.128 + 8 ALU + STS.128) per thread and K block;
+//   * the MMA warp issues lo*hi + hi*lo + hi*hi from shared-memory descriptors as in the gather kernel.
+// K blocks are enumerated per image (ceil(P/32) chunks, the last one zero padded) and split across CTAs in one wave.
+// fp32-equivalent math only: single-pass TF32 mode needs round-to-nearest operands and keeps the gather kernel.
+constexpr int WT_CW = 8;                               // converter warps (warps 0-3 also run the epilogue)
+constexpr int WT_THREADS = (WT_CW + 2) * 32;           // + TMA warp + MMA warp
+
+struct WgradTmaParams {
+  int O, C;              // rows of dY / X per image (G = 1)
+  int cpi;               // K chunks of 32 per image = ceil(P / 32)
+  long long nkb_total;   // N * cpi
+  int kb_per_split, splits;
+  float* out;            // splits == 1: dW (accumulated);  else partials [splits][O*C] (overwritten)
+};
+
+template <int N_TILE>
+struct WgradTmaSmem {
+  static constexpr uint32_t A_BYTES = 128u * 128u;                     // [128 rows][32 fp32], SW128
+  static constexpr uint32_t B_BYTES = (uint32_t)N_TILE * 128u;
+  static constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;             // one TMA transaction pair
+  static constexpr uint32_t STAGE = 2u * RAW_BYTES;                    // raw (= hi) tiles, then lo tiles at +RAW_BYTES
+  static constexpr int STAGES_ = (int)((208u * 1024u) / STAGE);
+  static constexpr int STAGES = STAGES_ > 6 ? 6 : STAGES_;
+  static constexpr uint32_t BAR_OFF = STAGES * STAGE;
+  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;              // + 1024-byte alignment slack
+};
+
+__device__ __forceinline__ uint64_t wg_desc_sw128(uint32_t addr) {    // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void wg_tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void wg_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 wg_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wgrad1x1_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant__ CUtensorMap map_dy,
+                    const __grid_constant__ CUtensorMap map_x) {
+  using S = WgradTmaSmem<N_TILE>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SW128 tiles need 1024-byte alignment
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_raw = sbase + S::BAR_OFF;                         // TMA bytes have landed
+  const uint32_t bar_full = bar_raw + 8 * STAGES;                      // lo tiles written
+  const uint32_t bar_empty = bar_full + 8 * STAGES;                    // MMAs of the stage have completed
+  const uint32_t bar_tmem = bar_empty + 8 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 8 * (3 * STAGES + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int n0 = blockIdx.y * N_TILE;                                   // input-channel tile (GEMM N)
+  const int m0 = blockIdx.z * 128;                                      // output-channel tile (GEMM M)
+  const long long kb_begin = (long long)split * p.kb_per_split;
+  long long kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.nkb_total) kb_end = p.nkb_total;
+  const int nkb = (int)(kb_end - kb_begin);                             // >= 1 by construction
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_raw + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, WT_CW);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    fence_barrier_init();
+  }
+  if (warp == WT_CW + 1) tmem_alloc(smem_u32(tmem_slot), N_TILE);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_a = [&](int s) { return sbase + (uint32_t)s * S::STAGE; };            // raw dY tile (hi operand)
+  auto stage_b = [&](int s) { return sbase + (uint32_t)s * S::STAGE + S::A_BYTES; };  // raw X tile
+
+  if (warp < WT_CW) {
+    // ================= converters: lo = a - trunc_tf32(a), same offset in the lo half of the stage =============
+    constexpr int UNITS = (int)(S::RAW_BYTES / 16u);                   // 16-byte units per stage, multiple of 256
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait_backoff(bar_raw + 8 * s, it & 1, 20);
+      const uint32_t src = stage_a(s);
+#pragma unroll 4
+      for (int u = tid; u < UNITS; u += WT_CW * 32) {
+        const float4 v = wg_lds128(src + (uint32_t)u * 16u);
+        float h, l0, l1, l2, l3;
+        split_tf32(v.x, h, l0); split_tf32(v.y, h, l1); split_tf32(v.z, h, l2); split_tf32(v.w, h, l3);
+        sts128(src + S::RAW_BYTES + (uint32_t)u * 16u, l0, l1, l2, l3);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+    }
+    if (warp < 4) {
+      // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced row stores ==================
+      mbar_wait_backoff(bar_tmem, 0, 100);
+      tc_fence_after();
+      float* tpad = reinterpret_cast<float*>(sptr) + warp * (32 * 33);   // all MMAs done: the stages are free
+      float* obase = p.out + (p.splits > 1 ? (long long)split * p.O * p.C : 0LL) + (long long)(m0 + warp * 32) * p.C + n0;
+      const int rows_valid = p.O - (m0 + warp * 32);
+      const bool accumulate = p.splits == 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        if (n0 + c0 >= p.C) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tpad[lane * 33 + j] = v[j];
+        __syncwarp();
+        const bool colok = n0 + c0 + lane < p.C;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          if (r < rows_valid && colok) {
+            float* dst = obase + (long long)r * p.C + c0 + lane;
+            const float t = tpad[r * 33 + lane];
+            *dst = accumulate ? *dst + t : t;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+    }
+  } else if (warp == WT_CW) {
+    // ================= TMA producer (whole warp converged, one elected lane issues) ============================
+    int n = (int)(kb_begin / p.cpi), j = (int)(kb_begin - (long long)n * p.cpi);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 20);
+      if (elect_one()) {
+        wg_arrive_expect_tx(bar_raw + 8 * s, S::RAW_BYTES);
+        wg_tma_load_3d(stage_a(s), &map_dy, bar_raw + 8 * s, j * 32, m0, n);
+        wg_tma_load_3d(stage_b(s), &map_x, bar_raw + 8 * s, j * 32, n0, n);
+      }
+      __syncwarp();
+      if (++j == p.cpi) { j = 0; ++n; }
+    }
+  } else {
+    // ================= MMA issuer (whole warp converged, elect.sync) ============================================
+    constexpr uint32_t IDESC = idesc_tf32(128, N_TILE);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, it = kb / STAGES;
+      mbar_wait(bar_full + 8 * s, it & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t ah = wg_desc_sw128(stage_a(s) + kk * 32);
+          const uint64_t bh = wg_desc_sw128(stage_b(s) + kk * 32);
+          const uint64_t al = wg_desc_sw128(stage_a(s) + S::RAW_BYTES + kk * 32);
+          const uint64_t bl = wg_desc_sw128(stage_b(s) + S::RAW_BYTES + kk * 32);
+          umma_tf32(tmem_base, al, bh, IDESC, (kb | kk) != 0);
+          umma_tf32(tmem_base, ah, bl, IDESC, 1);
+          umma_tf32(tmem_base, ah, bh, IDESC, 1);
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (kb == nkb - 1) umma_commit(bar_tmem);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == WT_CW + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, N_TILE);
+  }
+}
+
 struct WgradPlan { int n_tile, splits, kb_per_split; };
 
 static WgradPlan wgrad_plan(const ConvShape& s) {
@@ -389,9 +584,114 @@ bool tc_wgrad_supported(const ConvShape& s) {
   return nkb < 0x7fffffffLL;
 }
 
+static WgradPlan wgrad_tma_plan(const ConvShape& s, int* cpi_out);
+static bool wgrad_tma_shape_ok(const ConvShape& s);
 size_t tc_wgrad_workspace(const ConvShape& s) {
   const WgradPlan pl = wgrad_plan(s);
-  return pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+  size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+  if (wgrad_tma_shape_ok(s)) {                       // the TMA path of 1x1 layers plans its own split count
+    const WgradPlan pt = wgrad_tma_plan(s, nullptr);
+    const size_t nt = pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    if (nt > need) need = nt;
+  }
+  return need;
+}
+
+// ---- TMA path for 1x1 layers: eligibility, plan, launch -----------------------------------------------------------
+static bool wgrad_tma_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_TMA"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+static bool wgrad_tma_shape_ok(const ConvShape& s) {
+  const long long P = (long long)s.Ho * s.Wo;
+  return wgrad_tma_enabled() && s.is_1x1 && s.G == 1 && P % 4 == 0 && P >= 32 && s.H == s.Ho && s.W == s.Wo;
+}
+static WgradPlan wgrad_tma_plan(const ConvShape& s, int* cpi_out) {
+  WgradPlan pl;
+  pl.n_tile = s.C > 128 ? 256 : s.C > 64 ? 128 : s.C > 32 ? 64 : 32;
+  const int cpi = (s.Ho * s.Wo + BK - 1) / BK;
+  const long long nkb = (long long)s.N * cpi;
+  const long long mn = (long long)((s.O + 127) / 128) * ((s.C + pl.n_tile - 1) / pl.n_tile);
+  long long splits = sm_count() / mn;
+  const long long max_splits = nkb / 8 > 0 ? nkb / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const long long per = (nkb + splits - 1) / splits;
+  pl.splits = (int)((nkb + per - 1) / per);
+  pl.kb_per_split = (int)per;
+  if (cpi_out) *cpi_out = cpi;
+  return pl;
+}
+typedef CUresult (*WgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WgEncodeTiledFn wg_encode_tiled() {
+  static WgEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WgEncodeTiledFn>(f);
+  }
+  return fn;
+}
+// [N][rows][P] fp32, box {32, box_rows, 1}, SWIZZLE_128B, out-of-bounds elements read as zero
+static int wg_make_map(CUtensorMap* map, const float* base, long long P, int rows, int N, int box_rows) {
+  WgEncodeTiledFn enc = wg_encode_tiled();
+  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)rows, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)P * 4, (cuuint64_t)P * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled (wgrad) failed (%d)", (int)r);
+  return B2C_OK;
+}
+template <int N_TILE>
+static int launch_wgrad_tma_inst(const WgradTmaParams& p, const CUtensorMap& mdy, const CUtensorMap& mx, cudaStream_t st) {
+  using S = WgradTmaSmem<N_TILE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2C_CUDA_OK(cudaFuncSetAttribute(wgrad1x1_tma_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(p.splits, (p.C + N_TILE - 1) / N_TILE, (p.O + 127) / 128);
+  wgrad1x1_tma_kernel<N_TILE><<<grid, WT_THREADS, S::TOTAL, st>>>(p, mdy, mx);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+static int launch_conv_tc_wgrad_tma(const ConvShape& s, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                                    cudaStream_t st) {
+  int cpi = 0;
+  const WgradPlan pl = wgrad_tma_plan(s, &cpi);
+  const long long P = (long long)s.Ho * s.Wo;
+  WgradTmaParams p;
+  p.O = s.O; p.C = s.C; p.cpi = cpi; p.nkb_total = (long long)s.N * cpi;
+  p.kb_per_split = pl.kb_per_split; p.splits = pl.splits;
+  const size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.C : 0;
+  if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "wgrad (tma): workspace too small");
+  p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
+  alignas(64) CUtensorMap mdy, mx;
+  int rc = wg_make_map(&mdy, dy, P, s.O, s.N, 128);
+  if (rc) return rc;
+  rc = wg_make_map(&mx, x, P, s.C, s.N, pl.n_tile);
+  if (rc) return rc;
+  switch (pl.n_tile) {
+    case 256: rc = launch_wgrad_tma_inst<256>(p, mdy, mx, st); break;
+    case 128: rc = launch_wgrad_tma_inst<128>(p, mdy, mx, st); break;
+    case 64: rc = launch_wgrad_tma_inst<64>(p, mdy, mx, st); break;
+    default: rc = launch_wgrad_tma_inst<32>(p, mdy, mx, st); break;
+  }
+  if (rc) return rc;
+  if (pl.splits > 1) {
+    const long long n = (long long)s.O * s.C;
+    wgrad_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(static_cast<const float*>(ws), pl.splits, n, dw);
+    B2C_POST_LAUNCH();
+  }
+  return B2C_OK;
 }
 
 template <int N_TILE, bool SPLIT, bool X1X1>
@@ -418,6 +718,8 @@ static int launch_wgrad_n(const WgradParams& p, int G, int math, bool x1, cudaSt
 
 int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const float* dy, float* dw, void* ws,
                          size_t ws_bytes, cudaStream_t st) {
+  if (math == B2C_MATH_FP32 && wgrad_tma_shape_ok(s) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15u) == 0)
+    return launch_conv_tc_wgrad_tma(s, x, dy, dw, ws, ws_bytes, st);
   const WgradPlan pl = wgrad_plan(s);
   WgradParams p;
   p.dy = dy; p.x = x;

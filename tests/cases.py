@@ -42,6 +42,13 @@ MODEL_CASES = [
     ("vgg_conv1_1", dict(N=1, Cin=3, H=64, W=64, O=64, k=3, s=1, p=1, d=1, G=1, bias=True)),
     ("googlenet_5x5", dict(N=2, Cin=16, H=28, W=28, O=32, k=5, s=1, p=2, d=1, G=1, bias=True)),
     ("googlenet_aux_4x4", dict(N=4, Cin=512, H=4, W=4, O=128, k=1, s=1, p=0, d=1, G=1, bias=True)),
+    # 1x1 / stride 1 layers whose H*W is a multiple of 4: the TMA-fed weight-gradient kernel (zero-filled K tail at
+    # 14x14 = 196, ragged O and C against the 128 x N_TILE tile, split-K with several CTAs per tile, bias)
+    ("resnet_res4_1x1_expand", dict(N=8, Cin=256, H=14, W=14, O=1024, k=1, s=1, p=0, d=1, G=1, bias=False)),
+    ("resnet_res4_1x1_reduce", dict(N=2, Cin=1024, H=14, W=14, O=256, k=1, s=1, p=0, d=1, G=1, bias=False)),
+    ("ragged_1x1_14", dict(N=3, Cin=96, H=14, W=14, O=72, k=1, s=1, p=0, d=1, G=1, bias=True)),
+    ("ragged_1x1_rect", dict(N=2, Cin=40, H=6, W=10, O=200, k=1, s=1, p=0, d=1, G=1, bias=True)),
+    ("resnet_res3_1x1_reduce", dict(N=2, Cin=512, H=28, W=28, O=128, k=1, s=1, p=0, d=1, G=1, bias=False)),
 ]
 
 ALL_CASES = REF_TEST_CASES + EDGE_CASES + MODEL_CASES

@@ -36,6 +36,15 @@ def mini_resnet(batch=4, size=16, classes=10, conv_bias=False):
     return spec
 
 
+def lenet(batch=64, classes=10):
+    """examples/mnist/lenet_train_test.prototxt (BASELINE configs[0]): conv(20,5) pool conv(50,5) pool ip(500) relu ip(10) loss."""
+    return [dict(t="data", n="data", shape=(batch, 1, 28, 28)),
+            dict(t="conv", n="conv1", b="data", o=20, k=5, s=1, p=0, bias=True), dict(t="pool", n="pool1", b="conv1", m="MAX", k=2, s=2, p=0),
+            dict(t="conv", n="conv2", b="pool1", o=50, k=5, s=1, p=0, bias=True), dict(t="pool", n="pool2", b="conv2", m="MAX", k=2, s=2, p=0),
+            dict(t="fc", n="ip1", b="pool2", o=500), dict(t="relu", n="relu1", b="ip1"), dict(t="fc", n="ip2", b="ip1", o=classes),
+            dict(t="loss", n="loss", b=["ip2", "label"])]
+
+
 def to_prototxt(spec, eps=1e-4, maf=0.9):
     s = 'name: "mini"\n'
     for L in spec:

@@ -56,6 +56,20 @@ def test_forward_backward_matches_oracle(rng, conv_bias):
         assert rel(t.get_param(i, 1), g, floor) <= TOL, no.param_shapes(spec)[i]
 
 
+def test_lenet_matches_oracle(rng):
+    """BASELINE configs[0]: LeNet on MNIST-shaped input, batch 64 -- loss, every gradient, then 2 SGD steps."""
+    spec = no.lenet()
+    t, params, data, label = make_trainer(spec, rng)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss)
+    for name in ("conv1", "pool1", "conv2", "pool2", "ip1", "ip2"):
+        assert rel(t.get_blob(name), v[name]) <= TOL, name
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g, floor) <= TOL, no.param_shapes(spec)[i]
+
+
 def test_sgd_steps_match_oracle(rng):
     spec = no.mini_resnet()
     t, params, data, label = make_trainer(spec, rng)
