@@ -74,12 +74,14 @@ struct FwdSmem {
   static constexpr uint32_t A_COL0 = ACC_BUFS * N_TILE;
   static constexpr uint32_t A_COLS = SPLIT ? 64u : 32u;
   static constexpr int TMEM_STAGES = (int)((512u - A_COL0) / A_COLS);
-  static constexpr int SMEM_STAGES = (int)((196u * 1024u) / STAGE);
+  static constexpr int SMEM_STAGES = (int)((164u * 1024u) / STAGE);         // leaves room for the epilogue staging below
   static constexpr int STAGES_ = TMEM_STAGES < SMEM_STAGES ? TMEM_STAGES : SMEM_STAGES;
   static constexpr int STAGES = STAGES_ > 6 ? 6 : STAGES_;
   static constexpr uint32_t BAR_OFF = STAGES * STAGE;
   static constexpr uint32_t TAB_OFF = BAR_OFF + 256;
-  static constexpr uint32_t TOTAL = TAB_OFF + TAB_ENTRIES * 8 + 1024;      // + alignment slack
+  static constexpr uint32_t EPI_OFF = TAB_OFF + TAB_ENTRIES * 8;           // 2 x [32 channels][128 pixels] fp32 (epilogue transpose)
+  static constexpr uint32_t EPI_BYTES = 2u * 32u * 128u * 4u;
+  static constexpr uint32_t TOTAL = EPI_OFF + EPI_BYTES + 1024;             // + alignment slack
   static constexpr uint32_t TX_BYTES = NP * B_BYTES;
 };
 
@@ -356,6 +358,10 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     const int P = p.Ho * p.Wo;
     int ti = 0;
     long long ep_wait = 0, ep_work = 0;
+    float* epi = reinterpret_cast<float*>(sptr + S::EPI_OFF);
+    int epi_chunk = 0;
+    const bool vec_epi = p.out_ws == 1 && p.out_hs == p.Wo && (P & 3) == 0 && (p.out_plane & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 && !(p.dbg & 16);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       int m0, n0, g;
       tile_coords(tile, m0, n0, g);
@@ -373,6 +379,44 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       const long long e1 = clock64();
       ep_wait += e1 - e0;
       tc_fence_after();
+      if (vec_epi) {
+        // Contiguous output planes: 4-byte stores (128 B per warp instruction, one per channel) left this kernel
+        // bound by the number of store requests in flight on the short-K 1x1 layers (8 000 cycles of stores per
+        // tile against 1 500 of MMA).  Transpose each 32-channel chunk through shared memory so that one warp
+        // instruction writes 128 consecutive pixels of a channel: 512 B per request, a quarter of the requests.
+        const int mv = m0 + lane * 4;                      // this lane's 4 pixels in the store phase
+        const bool mv_ok = mv < p.Mtot;                    // P % 4 == 0: the group is valid or not as a whole
+        const int nv = (mv_ok ? mv : 0) / P, pv = (mv_ok ? mv : 0) - nv * P;
+        float* vbase = p.out + ((long long)nv * p.Cout_tot + (long long)g * p.Ntot + n0) * p.out_plane + pv;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32, ++epi_chunk) {
+          if (n0 + c0 >= p.Ntot) break;   // uniform over the four epilogue warps
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N_TILE + c0), v);
+          if (c0 + 32 >= N_TILE || n0 + c0 + 32 >= p.Ntot) {   // accumulator fully read: hand it back before storing
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          }
+          float* E = epi + (epi_chunk & 1) * (32 * 128);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) E[j * 128 + r] = v[j];           // lanes = consecutive pixels: conflict-free
+          asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps
+          if (!(p.dbg & 4)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int ch = lg * 8 + q;
+              if (mv_ok && n0 + c0 + ch < p.Ntot) {
+                float4 t = *reinterpret_cast<const float4*>(E + ch * 128 + lane * 4);
+                if (brow) { const float b = __ldg(brow + c0 + ch); t.x += b; t.y += b; t.z += b; t.w += b; }
+                *reinterpret_cast<float4*>(vbase + (long long)(c0 + ch) * p.out_plane) = t;
+              }
+            }
+          }
+        }
+        ep_work += clock64() - e1;
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         if (n0 + c0 >= p.Ntot) break;   // warp-uniform
