@@ -351,7 +351,10 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed_run(True, False)
     allreduce = time_allreduce()
-    full_net = None if args.no_full_net else full_net_measure(args, N, world, rank, dev)
+    # whole-graph measurement: always at N = 1; at N > 1 only on request (the same data-parallel TrainNet path is
+    # exercised and checked by tools/trainer_multi.py -- profiles/r01_fullnet_2gpu.json -- and kept out of the default
+    # multi-rank bench so that nothing can stand between the scaling run and its headline line)
+    full_net = None if (args.no_full_net or (world > 1 and not args.full_net_multi)) else full_net_measure(args, N, world, rank, dev)
 
     if rank == 0:
         pk = peaks()
@@ -467,6 +470,7 @@ def main():
     ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"],
                     help="fp32 = 3xTF32 split (fp32-equivalent results, the headline); tf32 = single-pass TF32 (informational)")
     ap.add_argument("--no-full-net", action="store_true", help="skip the supplementary full-prototxt-graph measurement")
+    ap.add_argument("--full-net-multi", action="store_true", help="also run the full-graph measurement when N > 1 (P2PSync / ReduceScheduler)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
