@@ -347,9 +347,10 @@ def run_ours(args):
                 "nvlink_ref_gbs": 900.0}
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches = timed_run(False, True)
+    ms, launches = timed_run(False, False)        # headline: nothing but the step inside the timed region
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed_run(True, False)
+    timed_run(False, True)                        # per-op breakdown for the roofline block (two events around every conv call)
     allreduce = time_allreduce()
     # whole-graph measurement: always at N = 1; at N > 1 only on request (the same data-parallel TrainNet path is
     # exercised and checked by tools/trainer_multi.py -- profiles/r01_fullnet_2gpu.json -- and kept out of the default
@@ -390,7 +391,11 @@ def run_ours(args):
             "clocks": clocks,
             "allreduce": allreduce,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                         "traffic": None, "kernel": "igemm_fwd_kernel (tcgen05 implicit GEMM: 53 forward + 52 dgrad launches/step)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 105 launches of one step
+                         # (profiles/r01_final_launches.csv, ncu); algorithmic bytes per launch 100.5e6 -> no wasted re-reads
+                         "traffic": 72.2e6 if (args.math == "fp32" and N == 64) else None,
+                         "traffic_unit": "bytes per launch (mean; algorithmic 100.5e6; ncu, profiles/r01_final_launches.csv)",
+                         "kernel": "igemm_fwd_kernel (tcgen05 implicit GEMM: 53 forward + 52 dgrad launches/step)",
                          "peak_source": pk["source"] + ": bf16_tflops/2 (TF32 dense); fp32-equivalent mode issues 3 TF32 MMAs per "
                                         "algorithmic MAC, so its ceiling is peak/3",
                          "frac_of_3xtf32_ceiling": ach / (tf32_peak / 3.0) if args.math == "fp32" else None,
