@@ -1,7 +1,9 @@
 """CPU oracle for the non-convolution layers on ResNet-50's path -- TEST INFRASTRUCTURE ONLY (numpy restatements of
-the reference's *_cpu code; paths relative to /root/reference).  Parity status: pinned against closed forms /
-finite differences in tests/test_layers_cpu.py (the reference stores no golden tensors for these layers; its own
-tests use GradientChecker, which the finite-difference checks here restate)."""
+the reference's *_cpu code; paths relative to /root/reference).  Parity status: pooling is PINNED by the reference's own known-answer vectors
+(test_pooling_layer.cpp: TestForwardSquare / RectHigh / RectWide values and argmax masks, TestForwardMaxPadded,
+TestForwardAve, the three TestSetup shapes), BatchNorm by the reference test's statistic (zero mean / unit variance per
+channel), ReLU / InnerProduct / SoftmaxWithLoss by closed forms; every backward by finite differences, which is what
+the reference's own GradientChecker tests do (it stores no golden gradients).  All in tests/test_layers_cpu.py."""
 import numpy as np
 
 

@@ -92,3 +92,101 @@ def test_inner_product(rng):
     dw, db, dx = lo.ip_backward(x, w, dy)
     assert np.allclose(db, dy.sum(0), atol=1e-5) and dw.shape == w.shape and dx.shape == x.shape
     assert np.allclose((dx * x).sum(), (dw * w).sum(), rtol=1e-4)     # <dx,x> == <dw,w> == <dy, y - b>
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Known answers restated from the reference's own layer tests (numbers only): they pin oracle/layers_oracle.py, which
+# the GPU kernels are in turn compared with on random data (tests/test_layers_gpu.py).
+MAGIC6 = np.array([[35, 1, 6, 26, 19, 24], [3, 32, 7, 21, 23, 25], [31, 9, 2, 22, 27, 20],
+                   [8, 28, 33, 17, 10, 15], [30, 5, 34, 12, 14, 16], [4, 36, 29, 13, 18, 11]], np.float32)
+
+
+def _tile(plane, num=2, channels=2):
+    return np.broadcast_to(plane, (num, channels) + plane.shape).astype(np.float32).copy()
+
+
+def test_pool_max_square_known_answer():
+    """test_pooling_layer.cpp:53-124 (TestForwardSquare): 3x5 input, kernel 2 -> values and argmax mask."""
+    x = _tile(np.array([[1, 2, 5, 2, 3], [9, 4, 1, 4, 8], [1, 2, 5, 2, 3]], np.float32))
+    y, mask = lo.pool_forward(x, 0, (2, 2), (1, 1), (0, 0))
+    assert y.shape == (2, 2, 2, 4)
+    assert np.array_equal(y, _tile(np.array([[9, 5, 5, 8], [9, 5, 5, 8]], np.float32)))
+    assert np.array_equal(mask, np.broadcast_to(np.array([[5, 2, 2, 9], [5, 12, 12, 9]]), mask.shape))
+
+
+def test_pool_max_rect_high_known_answer():
+    """test_pooling_layer.cpp:126-250 (TestForwardRectHigh): magic(6), kernel 3x2."""
+    y, mask = lo.pool_forward(_tile(MAGIC6), 0, (3, 2), (1, 1), (0, 0))
+    want = np.array([[35, 32, 26, 27, 27], [32, 33, 33, 27, 27], [31, 34, 34, 27, 27], [36, 36, 34, 18, 18]], np.float32)
+    wmask = np.array([[0, 7, 3, 16, 16], [7, 20, 20, 16, 16], [12, 26, 26, 16, 16], [31, 31, 26, 34, 34]])
+    assert np.array_equal(y, _tile(want))
+    assert np.array_equal(mask, np.broadcast_to(wmask, mask.shape))
+
+
+def test_pool_max_rect_wide_known_answer():
+    """test_pooling_layer.cpp:252-380 (TestForwardRectWide): magic(6), kernel 2x3."""
+    y, mask = lo.pool_forward(_tile(MAGIC6), 0, (2, 3), (1, 1), (0, 0))
+    want = np.array([[35, 32, 26, 26], [32, 32, 27, 27], [33, 33, 33, 27], [34, 34, 34, 17], [36, 36, 34, 18]], np.float32)
+    wmask = np.array([[0, 7, 3, 3], [7, 7, 16, 16], [20, 20, 20, 16], [26, 26, 26, 21], [31, 31, 26, 34]])
+    assert np.array_equal(y, _tile(want))
+    assert np.array_equal(mask, np.broadcast_to(wmask, mask.shape))
+
+
+def test_pool_max_padded_known_answer():
+    """test_pooling_layer.cpp:483-527 (TestForwardMaxPadded): kernel 3, stride 2, pad 2 on 3x3."""
+    x = np.array([[1, 2, 4], [2, 3, 2], [4, 2, 1]], np.float32).reshape(1, 1, 3, 3)
+    y, _ = lo.pool_forward(x, 0, (3, 3), (2, 2), (2, 2))
+    assert np.array_equal(y.reshape(3, 3), np.array([[1, 4, 4], [4, 4, 4], [4, 4, 1]], np.float32))
+
+
+def test_pool_ave_known_answer():
+    """test_pooling_layer.cpp:547-578 (TestForwardAve): constant 2, kernel 3, stride 1, pad 1 -> the padded-window divisor."""
+    y, _ = lo.pool_forward(np.full((1, 1, 3, 3), 2, np.float32), 1, (3, 3), (1, 1), (1, 1))
+    want = np.array([[8 / 9, 4 / 3, 8 / 9], [4 / 3, 2.0, 4 / 3], [8 / 9, 4 / 3, 8 / 9]])
+    np.testing.assert_allclose(y.reshape(3, 3), want, atol=1e-5)
+
+
+def test_pool_setup_shapes():
+    """test_pooling_layer.cpp:382-425 (TestSetup / TestSetupPadded / TestSetupGlobalPooling) on the 2x3x6x5 fixture."""
+    assert (lo.pooled_extent(6, 3, 2, 0), lo.pooled_extent(5, 3, 2, 0)) == (3, 2)
+    assert (lo.pooled_extent(6, 3, 2, 1), lo.pooled_extent(5, 3, 2, 1)) == (4, 3)
+    assert (lo.pooled_extent(6, 6, 1, 0), lo.pooled_extent(5, 5, 1, 0)) == (1, 1)
+
+
+def test_batchnorm_forward_statistics():
+    """test_batch_norm_layer.cpp TestForward: without scale/bias every channel of the output has mean 0 and variance 1
+    (up to eps) over N*H*W."""
+    rng = np.random.default_rng(1701)
+    x = (rng.standard_normal((5, 2, 3, 4)) * 3 + 7).astype(np.float32)
+    y = lo.bn_forward_train(x, None, None, 1e-5, 0.999, None, None, True)[0]
+    for c in range(2):
+        v = y[:, c].astype(np.float64)
+        assert abs(v.mean()) < 1e-5 and abs(v.var() - 1.0) < 1e-3
+
+
+def test_relu_known_answer():
+    """test_neuron_layer.cpp TestReLU / TestReLUWithNegativeSlope (slope 0.01)."""
+    x = np.array([-2.0, -0.5, 0.0, 0.5, 3.0], np.float32)
+    assert np.array_equal(lo.relu_forward(x), np.array([0, 0, 0, 0.5, 3.0], np.float32))
+    np.testing.assert_allclose(lo.relu_forward(x, 0.01), np.array([-0.02, -0.005, 0, 0.5, 3.0], np.float32), rtol=1e-6)
+
+
+def test_inner_product_known_answer():
+    """inner_product_layer.cpp semantics on a hand-computed case: y = x W^T + b with W [num_output x K] (transpose false)."""
+    x = np.array([[1, 2, 3], [0, -1, 4]], np.float32)
+    w = np.array([[1, 0, -1], [2, 1, 0]], np.float32)
+    b = np.array([0.5, -1], np.float32)
+    assert np.array_equal(lo.ip_forward(x, w, b), np.array([[-1.5, 3], [-3.5, -2]], np.float32))
+    dw, db, dx = lo.ip_backward(x, w, np.ones((2, 2), np.float32))
+    assert np.array_equal(dw, np.array([[1, 1, 7], [1, 1, 7]], np.float32)) and np.array_equal(db, np.array([2, 2], np.float32))
+    assert np.array_equal(dx, np.array([[3, 1, -1], [3, 1, -1]], np.float32))
+
+
+def test_softmax_loss_known_answer():
+    """softmax_loss_layer.cpp:96-160: uniform logits over C classes give loss ln C; gradient (p - onehot) / N."""
+    z = np.zeros((4, 10), np.float32)
+    lab = np.array([0, 3, 9, 5], np.float32)
+    p, loss = lo.softmax_loss_forward(z, lab)
+    assert abs(float(loss) - np.log(10)) < 1e-6
+    d = lo.softmax_loss_backward(p, lab)
+    assert abs(d[0, 0] - (0.1 - 1) / 4) < 1e-7 and abs(d[0, 1] - 0.1 / 4) < 1e-7
