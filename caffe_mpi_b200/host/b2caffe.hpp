@@ -269,6 +269,8 @@ class SGDSolver {
   const SolverParameter& param() const { return param_; }
   int iter() const { return iter_; }
   void set_iter(int i) { iter_ = i; }
+  int current_step() const { return current_step_; }
+  void set_current_step(int s) { current_step_ = s; }
   float GetLearningRate();   // sgd_solver.cpp:24-65
   float GetMomentum();       // sgd_solver.cpp:68-91
   // Register the learnable blobs in layer order with their lr_mult / decay_mult (Net::AppendParam).

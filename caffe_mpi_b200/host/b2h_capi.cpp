@@ -8,6 +8,7 @@
 #include "b2caffe.hpp"
 #include "prototxt.hpp"
 #include "train_net.hpp"
+#include "proto_wire.hpp"
 
 using namespace caffe;
 
@@ -329,6 +330,82 @@ int b2h_trainer_param(void* hv, int i, int what, int set, float* buf) {   // wha
     else CUDA_CHECK(cudaMemcpy(buf, dev, sizeof(float) * b.count(), cudaMemcpyDeviceToHost));
   });
 }
+int b2h_trainer_snapshot(void* hv, const char* prefix, char* state_path, int len) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ const std::string p = h->net->Snapshot(prefix); snprintf(state_path, len, "%s", p.c_str()); });
+}
+int b2h_trainer_restore(void* hv, const char* state_path) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ h->net->Restore(state_path); });
+}
+int b2h_trainer_copy_from(void* hv, const char* model_path, int* copied) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ *copied = h->net->CopyTrainedLayersFrom(model_path); });
+}
+int b2h_trainer_iter(void* hv) { return static_cast<TrainerHandle*>(hv)->net->solver().iter(); }
+
+// ---- .caffemodel / .solverstate wire format on host arrays (no device needed; tests/test_snapshot_cpu.py) ----------------
+struct WireHandle { NetWeights net; SolverStateData st; };
+void* b2h_wire_new() { return new WireHandle; }
+void b2h_wire_destroy(void* hv) { delete static_cast<WireHandle*>(hv); }
+int b2h_wire_add_layer(void* hv, const char* name, const char* type) {
+  auto* h = static_cast<WireHandle*>(hv);
+  LayerWeights l; l.name = name; l.type = type;
+  h->net.layers.push_back(l);
+  return (int)h->net.layers.size() - 1;
+}
+int b2h_wire_add_blob(void* hv, int layer, int ndim, const int* shape, const float* data) {   // layer < 0: solver history
+  auto* h = static_cast<WireHandle*>(hv);
+  B2H_TRY({
+    BlobData b;
+    size_t cnt = 1;
+    for (int i = 0; i < ndim; ++i) { b.shape.push_back(shape[i]); cnt *= (size_t)shape[i]; }
+    b.data.assign(data, data + cnt);
+    if (layer < 0) h->st.history.push_back(b);
+    else { B2_CHECK(layer < (int)h->net.layers.size(), "no such layer"); h->net.layers[layer].blobs.push_back(b); }
+  });
+}
+int b2h_wire_save_model(void* hv, const char* path, const char* net_name, int raw) {
+  auto* h = static_cast<WireHandle*>(hv);
+  B2H_TRY({ h->net.name = net_name; WriteBinaryFile(path, SerializeNetWeights(h->net, raw != 0)); });
+}
+int b2h_wire_save_state(void* hv, const char* path, int iter, int current_step, const char* learned_net, int raw) {
+  auto* h = static_cast<WireHandle*>(hv);
+  B2H_TRY({ h->st.iter = iter; h->st.current_step = current_step; h->st.learned_net = learned_net; WriteBinaryFile(path, SerializeSolverState(h->st, raw != 0)); });
+}
+void* b2h_wire_load(const char* path, int is_state) {
+  try {
+    auto* h = new WireHandle;
+    if (is_state) h->st = ParseSolverState(ReadBinaryFile(path)); else h->net = ParseNetWeights(ReadBinaryFile(path));
+    return h;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+int b2h_wire_num_layers(void* hv) { return (int)static_cast<WireHandle*>(hv)->net.layers.size(); }
+int b2h_wire_layer(void* hv, int i, char* name, char* type, int len, int* nblobs) {
+  auto* h = static_cast<WireHandle*>(hv);
+  B2H_TRY({
+    const LayerWeights& l = h->net.layers.at(i);
+    snprintf(name, len, "%s", l.name.c_str()); snprintf(type, len, "%s", l.type.c_str());
+    *nblobs = (int)l.blobs.size();
+  });
+}
+int b2h_wire_num_history(void* hv) { return (int)static_cast<WireHandle*>(hv)->st.history.size(); }
+int b2h_wire_blob(void* hv, int layer, int j, int* ndim, int* shape, long long* count, float* data) {   // data may be null (query)
+  auto* h = static_cast<WireHandle*>(hv);
+  B2H_TRY({
+    const BlobData& b = layer < 0 ? h->st.history.at(j) : h->net.layers.at(layer).blobs.at(j);
+    *ndim = (int)b.shape.size();
+    for (size_t k = 0; k < b.shape.size() && k < 8; ++k) shape[k] = b.shape[k];
+    *count = (long long)b.data.size();
+    if (data) memcpy(data, b.data.data(), sizeof(float) * b.data.size());
+  });
+}
+int b2h_wire_state(void* hv, int* iter, int* current_step, char* learned_net, int len, char* net_name, int nlen) {
+  auto* h = static_cast<WireHandle*>(hv);
+  B2H_TRY({ *iter = h->st.iter; *current_step = h->st.current_step; snprintf(learned_net, len, "%s", h->st.learned_net.c_str());
+            snprintf(net_name, nlen, "%s", h->net.name.c_str()); });
+}
+
 long long b2h_trainer_activation_floats(void* hv) { return (long long)static_cast<TrainerHandle*>(hv)->net->activation_floats(); }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
 // train_net.cpp -- see train_net.hpp.
 #include "train_net.hpp"
+#include "proto_wire.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -158,6 +159,7 @@ void SyntheticDataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& t
 
 // ================================================================================================ TrainNet
 TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, uint64_t seed, int math) {
+  name_ = net.name();
   Caffe::set_random_seed(seed);
   std::map<string, bool> need;
   vector<ParamSpec> specs;
@@ -218,6 +220,8 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
     if (type == "SoftmaxWithLoss") loss_blob_ = node.top[0];
     node.bottom_diff_tmp.assign(node.bottom.size(), nullptr);
     layers_.push_back(layer);
+    layer_names_.push_back(L.param.name);
+    layer_types_.push_back(type);
     nodes_.push_back(node);
   }
   // diff accumulation where a blob fans out (insert_splits.cpp / SplitLayer::Backward): the consumer that runs FIRST in
@@ -308,6 +312,69 @@ float TrainNet::TimedSteps(int n, bool copy_input, bool read_loss) {
   CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
   cudaEventDestroy(a); cudaEventDestroy(b);
   return ms;
+}
+// ---- snapshot / restore -------------------------------------------------------------------------------------------
+static BlobData to_blob_data(const vector<int>& shape, const float* host, size_t count) {
+  BlobData b;
+  b.shape = shape;
+  b.data.assign(host, host + count);
+  return b;
+}
+string TrainNet::Snapshot(const string& prefix) {
+  CUDA_CHECK(cudaDeviceSynchronize());
+  NetWeights nw;
+  nw.name = name_;
+  for (size_t i = 0; i < layers_.size(); ++i) {
+    LayerWeights lw;
+    lw.name = layer_names_[i]; lw.type = layer_types_[i];
+    for (auto& b : layers_[i]->blobs()) lw.blobs.push_back(to_blob_data(b->shape(), b->cpu_data(), b->count()));
+    nw.layers.push_back(std::move(lw));
+  }
+  const string stem = prefix + "_iter_" + std::to_string(solver_->iter());
+  WriteBinaryFile(stem + ".caffemodel", SerializeNetWeights(nw));
+  SolverStateData st;
+  st.iter = solver_->iter(); st.current_step = solver_->current_step(); st.learned_net = stem + ".caffemodel";
+  ParamArena& ar = solver_->arena();
+  for (size_t i = 0; i < learnable_.size(); ++i) {
+    vector<float> h(learnable_[i]->count());
+    CUDA_CHECK(cudaMemcpy(h.data(), ar.history() + ar.offset((int)i), sizeof(float) * h.size(), cudaMemcpyDeviceToHost));
+    st.history.push_back(to_blob_data(learnable_[i]->shape(), h.data(), h.size()));
+  }
+  WriteBinaryFile(stem + ".solverstate", SerializeSolverState(st));
+  return stem + ".solverstate";
+}
+int TrainNet::CopyTrainedLayersFrom(const string& path) {
+  const NetWeights nw = ParseNetWeights(ReadBinaryFile(path));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  int copied = 0;
+  for (const LayerWeights& lw : nw.layers) {
+    size_t li = 0;
+    while (li < layer_names_.size() && layer_names_[li] != lw.name) ++li;
+    if (li == layer_names_.size() || lw.blobs.empty()) continue;          // "Ignoring source layer" (net.cpp)
+    auto& target = layers_[li]->blobs();
+    B2_CHECK(target.size() == lw.blobs.size(), "Incompatible number of blobs for layer " + lw.name);
+    for (size_t j = 0; j < target.size(); ++j) {
+      B2_CHECK(target[j]->count() == lw.blobs[j].data.size(), "Cannot copy param " + std::to_string(j) + " weights from layer '" + lw.name +
+                                                                  "'; shape mismatch.");
+      CUDA_CHECK(cudaMemcpy(target[j]->mutable_gpu_data(), lw.blobs[j].data.data(), sizeof(float) * target[j]->count(), cudaMemcpyHostToDevice));
+    }
+    ++copied;
+  }
+  return copied;
+}
+void TrainNet::Restore(const string& state_path) {
+  const SolverStateData st = ParseSolverState(ReadBinaryFile(state_path));
+  if (!st.learned_net.empty()) CopyTrainedLayersFrom(st.learned_net);
+  B2_CHECK(st.history.size() == learnable_.size(), "Incorrect length of history blobs.");      // sgd_solver.cpp:334
+  ParamArena& ar = solver_->arena();
+  for (size_t i = 0; i < learnable_.size(); ++i) {
+    B2_CHECK(st.history[i].data.size() == learnable_[i]->count(), "history blob " + std::to_string(i) + ": size mismatch");
+    CUDA_CHECK(cudaMemcpy(ar.history() + ar.offset((int)i), st.history[i].data.data(), sizeof(float) * learnable_[i]->count(), cudaMemcpyHostToDevice));
+  }
+  solver_->set_iter(st.iter);
+  solver_->set_current_step(st.current_step);
+  for (auto& l : layers_)
+    if (auto* bn = dynamic_cast<BatchNormLayer*>(l.get())) bn->set_iter(st.iter + 1);   // running statistics are warm
 }
 float TrainNet::last_loss() { return loss_blob_ ? loss_blob_->cpu_data()[0] : 0.f; }
 

@@ -32,6 +32,9 @@ class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_b
   bool scale_bias_;
   float eps_, maf_;
   int iter_ = 0;
+ public:
+  void set_iter(int i) { iter_ = i; }
+ protected:
   Blob xnorm_, save_mean_, save_invstd_, scratch_;
 };
 
@@ -124,6 +127,14 @@ class TrainNet {
   LayerBase* layer(int i) { return layers_[i].get(); }
   const vector<shared_ptr<Blob>>& learnable_params() const { return learnable_; }
   size_t activation_floats() const;
+  // Solver::Snapshot (solver.cpp:447-520): <prefix>_iter_<N>.caffemodel (every layer's blobs, NVCaffe raw BlobProto) and
+  // <prefix>_iter_<N>.solverstate (iter, learned_net, one history blob per learnable parameter, current_step).
+  // Returns the .solverstate path.
+  string Snapshot(const string& prefix);
+  void Restore(const string& solverstate_path);          // SGDSolver::RestoreSolverStateFromBinaryProto + weights
+  // Net::CopyTrainedLayersFrom (net.cpp): layers matched by name, blob shapes must agree; returns the number of layers copied
+  int CopyTrainedLayersFrom(const string& caffemodel_path);
+  const string& name() const { return name_; }
  private:
   struct Node {
     vector<Blob*> bottom, top;
@@ -135,6 +146,8 @@ class TrainNet {
   void Forward(bool copy_input);
   void Backward(bool update);
   float host_loss_ = 0.f;
+  string name_;
+  vector<string> layer_names_, layer_types_;
   std::map<string, shared_ptr<Blob>> blobs_;
   vector<shared_ptr<LayerBase>> layers_;
   vector<Node> nodes_;

@@ -355,6 +355,31 @@ class Trainer:
     def activation_floats(self):
         return lib().b2h_trainer_activation_floats(self._h)
 
+    def snapshot(self, prefix):
+        """Solver::Snapshot: writes <prefix>_iter_<N>.caffemodel and .solverstate; returns the .solverstate path."""
+        L = lib()
+        L.b2h_trainer_snapshot.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        buf = C.create_string_buffer(1024)
+        _ck(L.b2h_trainer_snapshot(self._h, prefix.encode(), buf, 1024))
+        return buf.value.decode()
+
+    def restore(self, solverstate_path):
+        L = lib()
+        L.b2h_trainer_restore.argtypes = [C.c_void_p, C.c_char_p]
+        _ck(L.b2h_trainer_restore(self._h, solverstate_path.encode()))
+
+    def copy_trained_layers_from(self, caffemodel_path):
+        L = lib()
+        L.b2h_trainer_copy_from.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+        n = C.c_int()
+        _ck(L.b2h_trainer_copy_from(self._h, caffemodel_path.encode(), C.byref(n)))
+        return n.value
+
+    def iter(self):
+        L = lib()
+        L.b2h_trainer_iter.argtypes = [C.c_void_p]
+        return L.b2h_trainer_iter(self._h)
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.b2h_trainer_destroy(self._h)

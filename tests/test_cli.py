@@ -18,6 +18,11 @@ def test_train_needs_a_solver():
     assert r.returncode != 0 and "Need a solver definition" in r.stderr      # tools/caffe.cpp:  CHECK_GT(FLAGS_solver.size(), 0)
 
 
+def test_snapshot_and_weights_are_exclusive():
+    r = run("train", "--solver=x", "--snapshot=a.solverstate", "--weights=b.caffemodel")
+    assert r.returncode != 0 and "but not both" in r.stderr                   # tools/caffe.cpp:166-168
+
+
 def test_time_needs_a_model():
     r = run("time")
     assert r.returncode != 0 and "Need a model definition" in r.stderr

@@ -3,6 +3,7 @@
 C++ host layer -- SURVEY 8(f) rank 3.  Data layers are replaced by the synthetic in-memory source.
 
   python tools/caffe.py train --solver=models/resnet50/solver.prototxt [--iterations=N] [--batch=B]     (1 GPU)
+         [--snapshot=<solverstate to resume from>] [--weights=<caffemodel to fine-tune from>] [--snapshot_prefix=P]
   python -m torch.distributed.run --nproc-per-node N ... tools/caffe.py train --solver=...              (N GPUs, one rank each)
   python tools/caffe.py time --model=models/resnet50/train_val.prototxt [--iterations=50] [--batch=B]
   python tools/caffe.py device_query
@@ -47,12 +48,22 @@ def cmd_train(args):
     from caffe_mpi_b200 import host_api
     if not args.solver:
         sys.exit("caffe.py train: Need a solver definition to train (--solver=...)")
+    if args.snapshot and args.weights:
+        sys.exit("caffe.py train: Give a snapshot to resume training or weights to finetune but not both.")   # tools/caffe.cpp:166
     s, net_path = host_api.solver_from_prototxt(args.solver)
     d = host_api.solver_describe(s)
     net_path = args.model or net_path
     if not os.path.exists(net_path):
         sys.exit("caffe.py train: net file %r named by the solver does not exist (paths are relative to the working directory)" % net_path)
     t, rank, world = build_trainer(args, net_path, False, args.solver, False)
+    if args.snapshot:
+        t.restore(args.snapshot)
+        if rank == 0:
+            log("Resuming from %s at iteration %d" % (args.snapshot, t.iter()))
+    elif args.weights:
+        n = t.copy_trained_layers_from(args.weights)
+        if rank == 0:
+            log("Finetuning from %s (%d layers copied)" % (args.weights, n))
     iters = args.iterations or d["max_iter"]
     if rank == 0:
         log("Solving %s: %d learnable blobs, lr_policy %s base_lr %g momentum %g weight_decay %g, %d iteration(s) on %d GPU(s)" %
@@ -64,6 +75,8 @@ def cmd_train(args):
         done += n
         if rank == 0:
             log("Iteration %d (%.2f iter/s), loss = %.6g" % (done, n / (ms / 1e3), t.loss()))
+    if rank == 0 and args.snapshot_prefix:                    # Solver::Snapshot after the last iteration (solver.cpp:340-345)
+        log("Snapshotting solver state to binary proto file %s" % t.snapshot(args.snapshot_prefix))
     if rank == 0:
         log("Optimization Done.")
 
@@ -90,6 +103,9 @@ def main():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--display", type=int, default=20)
     ap.add_argument("--seed", type=int, default=1701)
+    ap.add_argument("--snapshot", "-snapshot", default="", help="solver state (.solverstate) to resume training from")
+    ap.add_argument("--weights", "-weights", default="", help="pretrained weights (.caffemodel) to fine-tune from")
+    ap.add_argument("--snapshot_prefix", default="", help="write <prefix>_iter_<N>.caffemodel/.solverstate after the last iteration")
     args = ap.parse_args()
     {"train": cmd_train, "time": cmd_time, "device_query": cmd_device_query}[args.command](args)
 
