@@ -586,12 +586,21 @@ bool tc_wgrad_supported(const ConvShape& s) {
 
 static WgradPlan wgrad_tma_plan(const ConvShape& s, int* cpi_out);
 static bool wgrad_tma_shape_ok(const ConvShape& s);
+static bool wgrad_compact_shape_ok(const ConvShape& s);
+static ConvShape wgrad_compact_dense_shape(const ConvShape& s);
 size_t tc_wgrad_workspace(const ConvShape& s) {
   const WgradPlan pl = wgrad_plan(s);
   size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
   if (wgrad_tma_shape_ok(s)) {                       // the TMA path of 1x1 layers plans its own split count
     const WgradPlan pt = wgrad_tma_plan(s, nullptr);
     const size_t nt = pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    if (nt > need) need = nt;
+  }
+  if (wgrad_compact_shape_ok(s)) {                   // strided 1x1: compacted input + the TMA path's partials
+    const ConvShape d = wgrad_compact_dense_shape(s);
+    const WgradPlan pt = wgrad_tma_plan(d, nullptr);
+    const size_t nt = (pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0) + 256 +
+                      sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
     if (nt > need) need = nt;
   }
   return need;
@@ -694,6 +703,39 @@ static int launch_conv_tc_wgrad_tma(const ConvShape& s, const float* x, const fl
   return B2C_OK;
 }
 
+// ---- strided 1x1 layers (pad 0, stride > 1): subsample, then the TMA path ------------------------------------------
+// NOT YET RUN ON A GPU -- off unless B2C_WGRAD_COMPACT=1 (written after round 1's GPU budget was spent; first thing to
+// validate next round).  dW[o][c] = sum_q dY[o][q] * X[c][ho*sh][wo*sw]: the gather kernel reads X with 8-byte-strided
+// 4-byte loads (36 TFLOP/s on ResNet-50's six such layers, 0.92 ms per step against 0.17 ms of MMA).  Copying the
+// sampled pixels into a dense [N][C][Ho*Wo] buffer first is one HBM-bound pass over half of X's rows, after which the
+// layer is an ordinary 1x1 / stride 1 weight gradient for the TMA-fed kernel.
+static bool wgrad_compact_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_COMPACT"); on = e ? atoi(e) : 0; }
+  return on != 0;
+}
+static bool wgrad_compact_shape_ok(const ConvShape& s) {
+  const long long P = (long long)s.Ho * s.Wo;
+  return wgrad_compact_enabled() && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) &&
+         s.G == 1 && P % 4 == 0 && P >= 32;
+}
+static ConvShape wgrad_compact_dense_shape(const ConvShape& s) {
+  ConvShape d = s;
+  d.H = s.Ho; d.W = s.Wo; d.sh = d.sw = 1; d.is_1x1 = true;
+  return d;
+}
+__global__ void __launch_bounds__(256)
+subsample_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int H, int W, int Ho, int Wo, int sh, int sw) {
+  const long long total = planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const long long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    const long long pl = t / Ho;
+    y[i] = __ldg(x + (pl * H + (long long)ho * sh) * W + (long long)wo * sw);
+  }
+}
+
 template <int N_TILE, bool SPLIT, bool X1X1>
 static int launch_wgrad_inst(const WgradParams& p, int G, cudaStream_t st) {
   using S = WgradSmem<N_TILE, SPLIT>;
@@ -720,6 +762,21 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
                          size_t ws_bytes, cudaStream_t st) {
   if (math == B2C_MATH_FP32 && wgrad_tma_shape_ok(s) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15u) == 0)
     return launch_conv_tc_wgrad_tma(s, x, dy, dw, ws, ws_bytes, st);
+  if (math == B2C_MATH_FP32 && wgrad_compact_shape_ok(s) && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0 && ws) {
+    const ConvShape d = wgrad_compact_dense_shape(s);
+    const WgradPlan pt = wgrad_tma_plan(d, nullptr);
+    const size_t part = pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    const size_t xoff = (part + 255) & ~(size_t)255;
+    const size_t xbytes = sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
+    if (ws_bytes < xoff + xbytes) return fail(B2C_ERR_WORKSPACE, "wgrad (compact): workspace too small");
+    float* xc = reinterpret_cast<float*>(static_cast<char*>(ws) + xoff);       // cudaMalloc'ed workspace: 256-byte aligned base
+    if ((reinterpret_cast<uintptr_t>(xc) & 15u) == 0) {
+      const long long planes = (long long)s.N * s.C;
+      subsample_kernel<<<grid_for((size_t)(planes * s.Ho * s.Wo), 256), 256, 0, st>>>(x, xc, planes, s.H, s.W, s.Ho, s.Wo, s.sh, s.sw);
+      B2C_POST_LAUNCH();
+      return launch_conv_tc_wgrad_tma(d, xc, dy, dw, ws, part, st);
+    }
+  }
   const WgradPlan pl = wgrad_plan(s);
   WgradParams p;
   p.dy = dy; p.x = x;
