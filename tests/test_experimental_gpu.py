@@ -11,10 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(os.environ.get("B2C_RUN_EXPERIMENTAL") != "1", reason="experimental variants run only on request")
-@pytest.mark.parametrize("switch", ["B2C_WGRAD_COMPACT"])
+@pytest.mark.parametrize("switch", ["B2C_WGRAD_COMPACT", "B2C_WGRAD3_TMA"])
 def test_variant_passes_the_parity_cases(switch):
     env = dict(os.environ, **{switch: "1"})
     env.pop("B2C_RUN_EXPERIMENTAL")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
-                        "-k", "s2 or 1x1"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+                        "-k", "s2 or 1x1 or 3x3"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
