@@ -118,6 +118,10 @@ def lib():
         "b2c_softmax_loss_backward": (i, [i, i, vp, vp, f, vp, vp]),
         "b2c_bias_forward": (i, [i, i, i, vp, vp, vp]),
         "b2c_bias_backward": (i, [i, i, i, vp, vp, vp]),
+        "b2c_lrn_forward": (i, [i, i, i, i, f, f, f, vp, vp, vp, vp]),
+        "b2c_lrn_backward": (i, [i, i, i, i, f, f, vp, vp, vp, vp, vp, vp]),
+        "b2c_dropout_mask": (i, [sz, f, C.c_ulonglong, C.c_ulonglong, vp, vp]),
+        "b2c_mul": (i, [sz, vp, vp, vp, vp]),
         "b2c_comm_get_unique_id": (i, [vp]),
         "b2c_comm_init": (i, [i, i, vp, C.POINTER(vp)]),
         "b2c_comm_destroy": (i, [vp]),

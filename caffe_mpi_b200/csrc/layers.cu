@@ -246,6 +246,73 @@ bn_bwd_dx_kernel(size_t total_units, int C, int S, float inv_cnt, const float* _
   }
 }
 
+// ---- LRN across channels ------------------------------------------------------------------------------------------
+// one thread per (image, pixel): walks the channels with a running window sum, loads coalesced along the pixel axis
+__global__ void __launch_bounds__(256)
+lrn_fwd_kernel(int N, int C, int S, int size, float alpha_over_size, float beta, float k, const float* __restrict__ x,
+               float* __restrict__ scale, float* __restrict__ y) {
+  const long long total = (long long)N * S;
+  const int pre = (size - 1) / 2;                              // lrn_layer.cpp: pre_pad_
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / S, sp = i - n * S;
+    const float* xp = x + n * C * S + sp;
+    float* sc = scale + n * C * S + sp;
+    float* yp = y + n * C * S + sp;
+    float acc = 0.f;                                           // window of channel c: [c - pre, c - pre + size)
+    for (int c = 0; c < size - 1 - pre && c < C; ++c) { const float v = xp[(long long)c * S]; acc += v * v; }
+    for (int c = 0; c < C; ++c) {
+      const int head = c - pre + size - 1, tail = c - pre - 1;
+      if (head < C && head >= 0) { const float v = xp[(long long)head * S]; acc += v * v; }
+      if (tail >= 0 && tail < C) { const float v = xp[(long long)tail * S]; acc -= v * v; }
+      const float s_ = k + alpha_over_size * acc;
+      sc[(long long)c * S] = s_;
+      yp[(long long)c * S] = xp[(long long)c * S] * powf(s_, -beta);
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+lrn_bwd_kernel(int N, int C, int S, int size, float cache_ratio, float beta, const float* __restrict__ x, const float* __restrict__ y,
+               const float* __restrict__ scale, const float* __restrict__ dy, float* __restrict__ dx) {
+  const long long total = (long long)N * S;
+  const int ipp = size - (size + 1) / 2;                       // lrn_layer.cpp: inverse_pre_pad
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / S, sp = i - n * S, base = n * C * S + sp;
+    auto ratio = [&](int c) { const long long o = base + (long long)c * S; return dy[o] * y[o] / scale[o]; };
+    float acc = 0.f;                                           // window of channel c: [c - ipp, c - ipp + size)
+    for (int c = 0; c < size - 1 - ipp && c < C; ++c) acc += ratio(c);
+    for (int c = 0; c < C; ++c) {
+      const int head = c - ipp + size - 1, tail = c - ipp - 1;
+      if (head < C && head >= 0) acc += ratio(head);
+      if (tail >= 0 && tail < C) acc -= ratio(tail);
+      const long long o = base + (long long)c * S;
+      dx[o] = dy[o] * powf(scale[o], -beta) - cache_ratio * x[o] * acc;
+    }
+  }
+}
+
+// ---- Dropout mask / elementwise product ----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(size_t n, unsigned threshold24, float scale, unsigned long long seed, unsigned long long offset, float* __restrict__ mask) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned u = (unsigned)(splitmix64(seed + offset + i) >> 40);      // 24 uniform bits
+    mask[i] = u >= threshold24 ? scale : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256) mul_kernel(size_t n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y) {
+  const size_t n4 = n / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = tid; i < n4; i += step) {
+    const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(u.x * v.x, u.y * v.y, u.z * v.z, u.w * v.w);
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += step) y[i] = a[i] * b[i];
+}
+
 // ---- Pooling ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pool_max_fwd_kernel(size_t total, int H, int W, int Ho, int Wo, int kh, int kw, int sh, int sw, int ph, int pw,
@@ -444,6 +511,36 @@ extern "C" int b2c_bn_backward(int N, int C, int S, const float* dy, const float
   const float inv_cnt = 1.0f / ((float)N * S);
   if (vec) bn_bwd_dx_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(units, C, S, inv_cnt, dy, xnorm, gamma, save_invstd, dgamma, dbeta, dx);
   else bn_bwd_dx_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(units, C, S, inv_cnt, dy, xnorm, gamma, save_invstd, dgamma, dbeta, dx);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_lrn_forward(int N, int C, int S, int local_size, float alpha, float beta, float k, const float* x, float* scale,
+                               float* y, void* stream) {
+  NEED(x && scale && y && N > 0 && C > 0 && S > 0 && local_size > 0 && (local_size & 1), "b2c_lrn_forward: bad argument (LRN only supports odd values for local_size)");
+  lrn_fwd_kernel<<<grid_for((size_t)N * S, 256), 256, 0, as_stream(stream)>>>(N, C, S, local_size, alpha / local_size, beta, k, x, scale, y);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_lrn_backward(int N, int C, int S, int local_size, float alpha, float beta, const float* x, const float* y,
+                                const float* scale, const float* dy, float* dx, void* stream) {
+  NEED(x && y && scale && dy && dx && N > 0 && C > 0 && S > 0 && local_size > 0, "b2c_lrn_backward: bad argument");
+  lrn_bwd_kernel<<<grid_for((size_t)N * S, 256), 256, 0, as_stream(stream)>>>(N, C, S, local_size, 2.f * alpha * beta / local_size, beta, x, y, scale, dy, dx);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_dropout_mask(size_t n, float ratio, unsigned long long seed, unsigned long long offset, float* mask, void* stream) {
+  NEED(mask && ratio >= 0.f && ratio < 1.f, "b2c_dropout_mask: dropout_ratio must be in [0, 1)");
+  if (!n) return B2C_OK;
+  const unsigned thr = (unsigned)((double)ratio * 16777216.0);
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(n, thr, 1.0f / (1.0f - ratio), seed, offset, mask);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+extern "C" int b2c_mul(size_t n, const float* a, const float* b, float* y, void* stream) {
+  NEED(a && b && y, "b2c_mul: null");
+  if (!n) return B2C_OK;
+  NEED(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "b2c_mul: pointers must be 16-byte aligned");
+  mul_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(n, a, b, y);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }

@@ -206,6 +206,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
     NetLayer L;
     L.param.name = lp.str("name");
     L.param.type = lp.str("type");
+    for (const PField* f : lp.all("loss_weight")) L.loss_weight.push_back((float)std::atof(f->scalar.c_str()));
     for (auto* b : lp.all("bottom")) L.param.bottom.push_back(b->scalar);
     for (auto* t : lp.all("top")) L.param.top.push_back(t->scalar);
     for (auto* ps : lp.all("param")) {
@@ -344,6 +345,15 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
     } else if (type == "SoftmaxWithLoss" || type == "EuclideanLoss" || type == "SigmoidCrossEntropyLoss" || type == "Accuracy") {
       for (size_t i = 0; i < L.param.top.size(); ++i) tops.push_back({});
     } else if (type == "ReLU" && (L.relu_slope = (float)(lp.sub("relu_param") ? lp.sub("relu_param")->num("negative_slope", 0.0) : 0.0), false)) {
+    } else if ((type == "LRN" || type == "Dropout") && ([&] {
+                 if (const PMessage* q = lp.sub("lrn_param")) {
+                   L.lrn_size = (int)q->integer("local_size", 5); L.lrn_alpha = (float)q->num("alpha", 1.0); L.lrn_beta = (float)q->num("beta", 0.75);
+                   L.lrn_k = (float)q->num("k", 1.0);
+                   const std::string r = q->str("norm_region", "ACROSS_CHANNELS");
+                   L.lrn_region = (r == "WITHIN_CHANNEL" || r == "1") ? 1 : 0;
+                 }
+                 if (const PMessage* q = lp.sub("dropout_param")) L.dropout_ratio = (float)q->num("dropout_ratio", 0.5);
+               }(), false)) {
     } else if (type == "ReLU" || type == "Dropout" || type == "LRN" || type == "Eltwise" || type == "Softmax" || type == "Sigmoid" ||
                type == "TanH" || type == "Power" || type == "Bias" || type == "ELU" || type == "PReLU" || type == "Split") {
       for (size_t i = 0; i < std::max<size_t>(1, L.param.top.size()); ++i) tops.push_back(bottom_shape(0));

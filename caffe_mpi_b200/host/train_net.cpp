@@ -124,6 +124,58 @@ void InnerProductLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>&
   if (pd[0]) B2C_CHECK(b2c_sgemm(0, 0, M_, K_, num_output_, 1.f, t[0]->gpu_diff(), blobs_[0]->gpu_data(), 0.f, b[0]->mutable_gpu_diff(), S()));
 }
 
+// ================================================================================================ LRN / Dropout / Concat
+void LRNLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
+  B2C_CHECK(b2c_lrn_forward(N, C, Sp, size_, alpha_, beta_, k_, b[0]->gpu_data(), scale_.mutable_gpu_data(), t[0]->mutable_gpu_data(), S()));
+}
+void LRNLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (!pd[0]) return;
+  const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
+  B2C_CHECK(b2c_lrn_backward(N, C, Sp, size_, alpha_, beta_, b[0]->gpu_data(), t[0]->gpu_data(), scale_.gpu_data(), t[0]->gpu_diff(),
+                             b[0]->mutable_gpu_diff(), S()));
+}
+void DropoutLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  B2C_CHECK(b2c_dropout_mask(b[0]->count(), ratio_, seed_, offset_, mask_.mutable_gpu_data(), S()));
+  offset_ += b[0]->count();
+  B2C_CHECK(b2c_mul(b[0]->count(), b[0]->gpu_data(), mask_.gpu_data(), t[0]->mutable_gpu_data(), S()));
+}
+void DropoutLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (!pd[0]) return;
+  B2C_CHECK(b2c_mul(b[0]->count(), t[0]->gpu_diff(), mask_.gpu_data(), b[0]->mutable_gpu_diff(), S()));
+}
+void ConcatLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
+  vector<int> s = b[0]->shape();
+  B2_CHECK(s.size() >= 2, "Concat: need at least 2 axes");
+  for (size_t i = 1; i < b.size(); ++i) {
+    B2_CHECK(b[i]->shape().size() == s.size() && b[i]->shape(0) == s[0] && b[i]->count(2) == b[0]->count(2),
+             "All inputs must have the same shape, except at concat_axis.");
+    s[1] += b[i]->shape(1);
+  }
+  t[0]->Reshape(s);
+}
+void ConcatLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  const size_t inner = t[0]->count(2), N = t[0]->shape(0), Ct = t[0]->shape(1);
+  size_t coff = 0;
+  for (Blob* src : b) {
+    const size_t w = sizeof(float) * src->shape(1) * inner;
+    CUDA_CHECK(cudaMemcpy2DAsync(t[0]->mutable_gpu_data() + coff * inner, sizeof(float) * Ct * inner, src->gpu_data(), w, w, N,
+                                 cudaMemcpyDeviceToDevice, S()));
+    coff += src->shape(1);
+  }
+}
+void ConcatLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  const size_t inner = t[0]->count(2), N = t[0]->shape(0), Ct = t[0]->shape(1);
+  size_t coff = 0;
+  for (size_t i = 0; i < b.size(); ++i) {
+    const size_t w = sizeof(float) * b[i]->shape(1) * inner;
+    if (pd[i])
+      CUDA_CHECK(cudaMemcpy2DAsync(b[i]->mutable_gpu_diff(), w, t[0]->gpu_diff() + coff * inner, sizeof(float) * Ct * inner, w, N,
+                                   cudaMemcpyDeviceToDevice, S()));
+    coff += b[i]->shape(1);
+  }
+}
+
 // ================================================================================================ SoftmaxWithLoss
 void SoftmaxWithLossLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
   prob_.ReshapeLike(*b[0]);
@@ -135,7 +187,7 @@ void SoftmaxWithLossLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob
 }
 void SoftmaxWithLossLayer::Backward_gpu(const vector<Blob*>&, const vector<bool>& pd, const vector<Blob*>& b) {
   if (!pd[0]) return;
-  B2C_CHECK(b2c_softmax_loss_backward(b[0]->shape(0), (int)b[0]->count(1), prob_.gpu_data(), b[1]->gpu_data(), 1.f,
+  B2C_CHECK(b2c_softmax_loss_backward(b[0]->shape(0), (int)b[0]->count(1), prob_.gpu_data(), b[1]->gpu_data(), loss_weight_,
                                       b[0]->mutable_gpu_diff(), S()));
 }
 
@@ -194,7 +246,20 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
     else if (type == "Pooling") layer.reset(new PoolingLayer(L.param, L.pooling));
     else if (type == "Eltwise") layer.reset(new EltwiseLayer(L.param));
     else if (type == "InnerProduct") layer.reset(new InnerProductLayer(L.param, L.ip_num_output, L.ip_bias, L.ip_weight_filler, L.ip_bias_filler));
-    else if (type == "SoftmaxWithLoss") layer.reset(new SoftmaxWithLossLayer(L.param));
+    else if (type == "SoftmaxWithLoss") {
+      auto* sl = new SoftmaxWithLossLayer(L.param);
+      if (!L.loss_weight.empty()) sl->set_loss_weight(L.loss_weight[0]);      // GoogLeNet's auxiliary classifiers: 0.3
+      layer.reset(sl);
+    }
+    else if (type == "LRN") {
+      B2_CHECK(L.lrn_region == 0, "TrainNet: LRN WITHIN_CHANNEL is not built (the BASELINE nets use ACROSS_CHANNELS)");
+      layer.reset(new LRNLayer(L.param, L.lrn_size, L.lrn_alpha, L.lrn_beta, L.lrn_k));
+    }
+    else if (type == "Dropout") layer.reset(new DropoutLayer(L.param, L.dropout_ratio, seed * 0x100000001B3ull + li));
+    else if (type == "Concat") {
+      B2_CHECK(L.concat_axis == 1, "TrainNet: Concat is built for the channel axis only");
+      layer.reset(new ConcatLayer(L.param));
+    }
     else B2_CHECK(false, "TrainNet: layer type '" + type + "' is not built yet (SURVEY 8f rank 2 covers the ResNet-50 set)");
     layer->SetUp(node.bottom, node.top);
     // learnable blobs in layer order (Net::AppendParam): every blob the layer marks param_propagate_down

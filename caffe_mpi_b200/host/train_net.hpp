@@ -78,15 +78,55 @@ class InnerProductLayer : public LayerBase {
   FillerParameter wf_, bf_;
 };
 
+// ---- layers the AlexNet / GoogLeNet / VGG-16 nets add (not yet run on a GPU; see include/b2c.h) ---------------------
+class LRNLayer : public LayerBase {            // ACROSS_CHANNELS only (the BASELINE nets' use)
+ public:
+  LRNLayer(const LayerParameter& p, int size, float alpha, float beta, float k) : LayerBase(p), size_(size), alpha_(alpha), beta_(beta), k_(k) {}
+  const char* type() const override { return "LRN"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { t[0]->ReshapeLike(*b[0]); scale_.ReshapeLike(*b[0]); }
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  int size_;
+  float alpha_, beta_, k_;
+  Blob scale_;
+};
+
+class DropoutLayer : public LayerBase {        // TRAIN phase: y = x * mask, mask in {0, 1/(1-ratio)}
+ public:
+  DropoutLayer(const LayerParameter& p, float ratio, uint64_t seed) : LayerBase(p), ratio_(ratio), seed_(seed) {}
+  const char* type() const override { return "Dropout"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { if (t[0] != b[0]) t[0]->ReshapeLike(*b[0]); mask_.ReshapeLike(*b[0]); }
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  float ratio_;
+  uint64_t seed_, offset_ = 0;
+  Blob mask_;
+};
+
+class ConcatLayer : public LayerBase {         // along the channel axis (axis 1), strided 2-D copies
+ public:
+  using LayerBase::LayerBase;
+  const char* type() const override { return "Concat"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+};
+
 class SoftmaxWithLossLayer : public LayerBase {
  public:
   using LayerBase::LayerBase;
+  void set_loss_weight(float w) { loss_weight_ = w; }
+  float loss_weight() const { return loss_weight_; }
   const char* type() const override { return "SoftmaxWithLoss"; }
   void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
  protected:
   void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
   void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
   Blob prob_;
+  float loss_weight_ = 1.f;
 };
 
 // Synthetic in-memory source standing in for DataLayer: N(0,1) images from mt19937(seed), uniform labels.

@@ -170,6 +170,19 @@ int b2c_softmax_loss_backward(int N, int C, const float* prob, const float* labe
 /* y[n][o][p] += bias[o];  db[o] += sum_{n,p} dy[n][o][p]  (InnerProduct bias with P = 1; conv bias with P = Ho*Wo). */
 int b2c_bias_forward(int N, int O, int P, const float* bias, float* y, void* stream);
 int b2c_bias_backward(int N, int O, int P, const float* dy, float* db, void* stream);
+/* ---- layers the AlexNet / GoogLeNet / VGG-16 BASELINE nets add (second half) -- written in round 1
+ * after the GPU budget was spent: CPU-verified oracle, GPU parity tests run on request (tests/test_layers_extra_gpu.py).
+ * LRNLayer ACROSS_CHANNELS (src/caffe/layers/lrn_layer.cpp CrossChannelForward_cpu / CrossChannelBackward_cpu):
+ * scale = k + alpha/size * sum_{window} x^2, y = x * scale^-beta; x,y,scale,dy,dx: [N,C,S].                          */
+int b2c_lrn_forward(int N, int C, int S, int local_size, float alpha, float beta, float k, const float* x, float* scale,
+                    float* y, void* stream);
+int b2c_lrn_backward(int N, int C, int S, int local_size, float alpha, float beta, const float* x, const float* y,
+                     const float* scale, const float* dy, float* dx, void* stream);
+/* DropoutLayer TRAIN (src/caffe/layers/dropout_layer.cpp): mask[i] = keep ? 1/(1-ratio) : 0 with
+ * keep = (splitmix64(seed + offset + i) >> 40) >= ratio * 2^24  (counter based: reproducible, no state);
+ * forward y = x * mask and backward dx = dy * mask are b2c_mul.                                                        */
+int b2c_dropout_mask(size_t n, float ratio, unsigned long long seed, unsigned long long offset, float* mask, void* stream);
+int b2c_mul(size_t n, const float* a, const float* b, float* y, void* stream);
 
 /* ---- fused SGD-momentum update -----------------------------------------------------------
  * h = momentum*h + local_rate*(grad_scale*g + local_decay*reg(w)); w -= h;

@@ -130,3 +130,42 @@ def ip_backward(x, w, dy):
     db = dy.astype(np.float64).sum(axis=0)
     dx = (dy.astype(np.float64) @ w.astype(np.float64)).reshape(x.shape)
     return dw.astype(np.float32), db.astype(np.float32), dx.astype(np.float32)
+
+
+# LRNLayer ACROSS_CHANNELS: CrossChannelForward_cpu / CrossChannelBackward_cpu, src/caffe/layers/lrn_layer.cpp; the forward
+# is written the way the reference's own test states it (test_lrn_layer.cpp:61-91, ReferenceLRNForward, with k)
+def lrn_forward(x, size=5, alpha=1.0, beta=0.75, k=1.0):
+    N, C = x.shape[:2]
+    x64 = x.astype(np.float64)
+    scale = np.empty_like(x64)
+    for c in range(C):
+        lo_ = max(c - (size - 1) // 2, 0)
+        hi_ = min(c - (size - 1) // 2 + size, C)
+        scale[:, c] = k + (x64[:, lo_:hi_] ** 2).sum(axis=1) * alpha / size
+    y = x64 * scale ** (-beta)
+    return y.astype(np.float32), scale.astype(np.float32)
+
+
+def lrn_backward(x, y, scale, dy, size=5, alpha=1.0, beta=0.75):
+    C = x.shape[1]
+    x64, y64, s64, d64 = (a.astype(np.float64) for a in (x, y, scale, dy))
+    ratio = d64 * y64 / s64
+    ipp = size - (size + 1) // 2                       # inverse_pre_pad
+    dx = d64 * s64 ** (-beta)
+    for c in range(C):
+        lo_, hi_ = max(c - ipp, 0), min(c - ipp + size, C)
+        dx[:, c] -= 2.0 * alpha * beta / size * x64[:, c] * ratio[:, lo_:hi_].sum(axis=1)
+    return dx.astype(np.float32)
+
+
+# DropoutLayer TRAIN, src/caffe/layers/dropout_layer.cpp: y = x * mask * 1/(1-ratio).  The mask generator is this
+# repository's counter-based one (include/b2c.h b2c_dropout_mask): keep = (splitmix64(seed + offset + i) >> 40) >= ratio * 2^24
+def dropout_mask(n, ratio, seed, offset=0):
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + np.uint64(offset) + np.arange(n, dtype=np.uint64)) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.uint32)
+    thr = np.uint32(int(float(np.float32(ratio)) * 16777216.0))
+    return np.where(u >= thr, np.float32(1.0) / (np.float32(1.0) - np.float32(ratio)), np.float32(0.0)).astype(np.float32)

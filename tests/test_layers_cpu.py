@@ -190,3 +190,35 @@ def test_softmax_loss_known_answer():
     assert abs(float(loss) - np.log(10)) < 1e-6
     d = lo.softmax_loss_backward(p, lab)
     assert abs(d[0, 0] - (0.1 - 1) / 4) < 1e-7 and abs(d[0, 1] - 0.1 / 4) < 1e-7
+
+
+def test_lrn_matches_the_reference_tests_formula_and_its_gradient(rng):
+    """Forward against a literal per-element restatement of test_lrn_layer.cpp:61-91; backward by finite differences
+    (the reference uses GradientChecker: TestGradientAcrossChannels)."""
+    x = rng.standard_normal((2, 7, 3, 3)).astype(np.float32)
+    for size, alpha, beta in ((5, 1.0, 0.75), (3, 1e-4, 0.75), (15, 1.0, 0.75)):      # 15 > channels: TestForwardAcrossChannelsLargeRegion
+        y, scale = lo.lrn_forward(x, size, alpha, beta)
+        for (n, c, h, w) in ((0, 0, 0, 0), (1, 3, 2, 1), (0, 6, 1, 2)):
+            c0 = max(c - (size - 1) // 2, 0); c1 = min(c - (size - 1) // 2 + size, 7)
+            s = 1.0 + sum(float(x[n, i, h, w]) ** 2 * alpha / size for i in range(c0, c1))
+            assert abs(y[n, c, h, w] - x[n, c, h, w] / s ** beta) < 1e-5
+    size, alpha, beta = 5, 1.0, 0.75
+    y, scale = lo.lrn_forward(x, size, alpha, beta)
+    dy = rng.standard_normal(x.shape).astype(np.float32)
+    dx = lo.lrn_backward(x, y, scale, dy, size, alpha, beta)
+    for idx in ((0, 0, 0, 0), (1, 3, 1, 1), (0, 6, 2, 2), (1, 5, 0, 2)):
+        e = 1e-3
+        xp, xm = x.copy(), x.copy()
+        xp[idx] += e; xm[idx] -= e
+        fd = ((lo.lrn_forward(xp, size, alpha, beta)[0].astype(np.float64) - lo.lrn_forward(xm, size, alpha, beta)[0]) * dy).sum() / (2 * e)
+        assert abs(fd - dx[idx]) < 2e-3 * max(1.0, abs(fd))
+
+
+def test_dropout_mask_statistics_and_scale():
+    """dropout_layer.cpp: kept with probability 1 - ratio, kept values scaled by 1/(1 - ratio); reproducible per (seed, offset)."""
+    m = lo.dropout_mask(200000, 0.5, 1701)
+    assert set(np.unique(m)) == {0.0, 2.0} and abs((m > 0).mean() - 0.5) < 0.01
+    m3 = lo.dropout_mask(200000, 0.3, 7, offset=10)
+    assert abs((m3 > 0).mean() - 0.7) < 0.01 and abs(m3.max() - 1 / 0.7) < 1e-6
+    assert np.array_equal(m3[5:100], lo.dropout_mask(95, 0.3, 7, offset=15))        # counter based: offset + i
+    assert abs(m3.mean() - 1.0) < 0.01                                              # expectation preserved

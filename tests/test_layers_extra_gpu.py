@@ -1,0 +1,57 @@
+"""GPU parity of the AlexNet / GoogLeNet / VGG-16 extras (LRN, Dropout mask, elementwise product) against
+oracle/layers_oracle.py.  These kernels were written after round 1's GPU budget was spent: the tests run only with
+B2C_RUN_EXPERIMENTAL=1 until they have passed on a B200 once (then drop the switch)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import layers_oracle as lo
+from cases import rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B2C_RUN_EXPERIMENTAL") != "1", reason="not yet validated on a GPU; run on request")]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("shape,size,alpha,beta,k", [((2, 7, 3, 3), 5, 1.0, 0.75, 1.0), ((4, 96, 27, 27), 5, 1e-4, 0.75, 1.0),
+                                                   ((2, 3, 5, 5), 15, 1.0, 0.75, 2.0), ((3, 64, 8, 8), 3, 0.01, 0.5, 1.0)])
+def test_lrn(rng, shape, size, alpha, beta, k):
+    from caffe_mpi_b200 import capi
+    L = capi.lib()
+    x = rng.standard_normal(shape).astype(np.float32)
+    dy = rng.standard_normal(shape).astype(np.float32)
+    y_ref, s_ref = lo.lrn_forward(x, size, alpha, beta, k)
+    dx_ref = lo.lrn_backward(x, y_ref, s_ref, dy, size, alpha, beta)
+    N, Cc, S = shape[0], shape[1], shape[2] * shape[3]
+    X, DY = dev(x), dev(dy)
+    Y, SC, DX = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+    assert L.b2c_lrn_forward(N, Cc, S, size, alpha, beta, k, ptr(X), ptr(SC), ptr(Y), None) == 0
+    assert L.b2c_lrn_backward(N, Cc, S, size, alpha, beta, ptr(X), ptr(Y), ptr(SC), ptr(DY), ptr(DX), None) == 0
+    torch.cuda.synchronize()
+    assert rel_err(SC.cpu().numpy(), s_ref) < 1e-5
+    assert rel_err(Y.cpu().numpy(), y_ref) < 1e-5
+    assert rel_err(DX.cpu().numpy(), dx_ref) < 1e-4
+
+
+@pytest.mark.parametrize("n,ratio,seed,offset", [(100003, 0.5, 1701, 0), (4096, 0.3, 7, 123456789), (17, 0.9, 2 ** 40 + 5, 3)])
+def test_dropout_mask_is_bit_exact_and_mul(rng, n, ratio, seed, offset):
+    from caffe_mpi_b200 import capi
+    L = capi.lib()
+    M = torch.empty(n, device="cuda")
+    assert L.b2c_dropout_mask(n, ratio, seed, offset, ptr(M), None) == 0
+    m = M.cpu().numpy()
+    assert np.array_equal(m, lo.dropout_mask(n, ratio, seed, offset))
+    x = rng.standard_normal(n).astype(np.float32)
+    X, Y = dev(x), torch.empty(n, device="cuda")
+    assert L.b2c_mul(n, ptr(X), ptr(M), ptr(Y), None) == 0
+    assert np.array_equal(Y.cpu().numpy(), x * m)
