@@ -965,8 +965,8 @@ static int launch_conv_tc_wgrad3(const ConvShape& s, const float* x, const float
 }
 
 // ---- strided 1x1 layers (pad 0, stride > 1): subsample, then the TMA path ------------------------------------------
-// NOT YET RUN ON A GPU -- off unless B2C_WGRAD_COMPACT=1 (written after round 1's GPU budget was spent; first thing to
-// validate next round).  dW[o][c] = sum_q dY[o][q] * X[c][ho*sh][wo*sw]: the gather kernel reads X with 8-byte-strided
+// Off unless B2C_WGRAD_COMPACT=1: parity-green on a B200 (tests/test_experimental_gpu.py) but not yet timed -- measure
+// with tools/layer_sweep.py before making it the default.  dW[o][c] = sum_q dY[o][q] * X[c][ho*sh][wo*sw]: the gather kernel reads X with 8-byte-strided
 // 4-byte loads (36 TFLOP/s on ResNet-50's six such layers, 0.92 ms per step against 0.17 ms of MMA).  Copying the
 // sampled pixels into a dense [N][C][Ho*Wo] buffer first is one HBM-bound pass over half of X's rows, after which the
 // layer is an ordinary 1x1 / stride 1 weight gradient for the TMA-fed kernel.

@@ -170,8 +170,8 @@ int b2c_softmax_loss_backward(int N, int C, const float* prob, const float* labe
 /* y[n][o][p] += bias[o];  db[o] += sum_{n,p} dy[n][o][p]  (InnerProduct bias with P = 1; conv bias with P = Ho*Wo). */
 int b2c_bias_forward(int N, int O, int P, const float* bias, float* y, void* stream);
 int b2c_bias_backward(int N, int O, int P, const float* dy, float* db, void* stream);
-/* ---- layers the AlexNet / GoogLeNet / VGG-16 BASELINE nets add (second half) -- written in round 1
- * after the GPU budget was spent: CPU-verified oracle, GPU parity tests run on request (tests/test_layers_extra_gpu.py).
+/* ---- layers the AlexNet / GoogLeNet / VGG-16 BASELINE nets add (second half);
+ * GPU parity: tests/test_layers_extra_gpu.py.
  * LRNLayer ACROSS_CHANNELS (src/caffe/layers/lrn_layer.cpp CrossChannelForward_cpu / CrossChannelBackward_cpu):
  * scale = k + alpha/size * sum_{window} x^2, y = x * scale^-beta; x,y,scale,dy,dx: [N,C,S].                          */
 int b2c_lrn_forward(int N, int C, int S, int local_size, float alpha, float beta, float k, const float* x, float* scale,
