@@ -1,5 +1,7 @@
 """Shared convolution cases.  Names follow the reference's own tests
 (src/caffe/test/test_convolution_layer.cpp) and the BASELINE.json configs."""
+import os
+
 
 # (name, dict(N, Cin, H, W, O, k, s, p, d, G, bias))
 REF_TEST_CASES = [
@@ -49,10 +51,16 @@ MODEL_CASES = [
     ("ragged_1x1_14", dict(N=3, Cin=96, H=14, W=14, O=72, k=1, s=1, p=0, d=1, G=1, bias=True)),
     ("ragged_1x1_rect", dict(N=2, Cin=40, H=6, W=10, O=200, k=1, s=1, p=0, d=1, G=1, bias=True)),
     ("resnet_res3_1x1_reduce", dict(N=2, Cin=512, H=28, W=28, O=128, k=1, s=1, p=0, d=1, G=1, bias=False)),
-    # 3x3 / stride 1 / pad 1 with C % 32 == 0 and W % 4 == 0: the shapes the (still experimental) TMA 3x3 wgrad kernel takes
+]
+
+# 3x3 / stride 1 / pad 1 with C % 32 == 0 and W % 4 == 0: the shapes the (still experimental, off by default) TMA 3x3
+# weight-gradient kernel takes.  Part of the suite only when that kernel is switched on (tests/test_experimental_gpu.py).
+EXPERIMENTAL_CASES = [
     ("resnet_res3_3x3", dict(N=2, Cin=128, H=28, W=28, O=128, k=3, s=1, p=1, d=1, G=1, bias=False)),
     ("ragged_3x3_rect", dict(N=3, Cin=32, H=12, W=20, O=40, k=3, s=1, p=1, d=1, G=1, bias=True)),
 ]
+if os.environ.get("B2C_WGRAD3_TMA") == "1":
+    MODEL_CASES = MODEL_CASES + EXPERIMENTAL_CASES
 
 ALL_CASES = REF_TEST_CASES + EDGE_CASES + MODEL_CASES
 
