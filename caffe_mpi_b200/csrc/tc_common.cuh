@@ -30,47 +30,40 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-#ifndef B2C_MBAR_SPIN
-#define B2C_MBAR_SPIN 0
-#endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#if B2C_MBAR_SPIN
-  // non-blocking probe in a spin loop (experiment: is the suspended try_wait slow to wake?)
+// Every wait is bounded: a protocol bug (a missed arrive, a wrong parity) must fail the launch with a trap
+// ("unspecified launch failure" on the host) instead of hanging the GPU.  The bound is ~2^31 SM cycles (about a
+// second), three orders of magnitude beyond the longest legitimate wait in any of these kernels.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "B2C_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra B2C_DONE_%=;\n\t"
-      "bra B2C_WAIT_%=;\n\t"
-      "B2C_DONE_%=:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-#endif
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_timeout_trap(uint32_t, uint32_t) { asm volatile("trap;"); }
+constexpr long long MBAR_TIMEOUT_CYCLES = 1ll << 31;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > MBAR_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
+  }
 }
 // Waiters that are not on the critical path (epilogue warps waiting a whole tile for the accumulator,
 // producers waiting for a free stage) must not spin hot: the warp scheduler prefers high warp ids, and a
 // try_wait loop in 4-20 warps starves the single MMA-issuing thread of issue slots.  Back off with nanosleep.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
-  uint32_t done;
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
   for (;;) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
     __nanosleep(ns);
+    if (mbar_try(bar, parity)) break;
+    if ((++spins & 0xffu) == 0 && clock64() - t0 > MBAR_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

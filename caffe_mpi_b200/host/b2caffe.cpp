@@ -488,16 +488,19 @@ void SGDSolver::ApplyUpdate(int id_from, int id_to, cudaStream_t stream) {
   B2_CHECK(param_.regularization_type == "L2" || param_.regularization_type == "L1", "Unknown regularization type");
   const float rate = GetLearningRate();
   const float momentum = GetMomentum();
-  const int n = id_to - id_from + 1;
-  if (n <= 0) return;
-  vector<size_t> off(n), cnt(n);
-  vector<float> lr(n), dc(n);
-  for (int i = 0; i < n; ++i) {
-    off[i] = arena_.offset(id_from + i);
-    cnt[i] = arena_.count(id_from + i);
-    lr[i] = rate * specs_[id_from + i].lr_mult;                    // sgd_solver.cpp:208-210
-    dc[i] = param_.weight_decay * specs_[id_from + i].decay_mult;   // :254-259
+  if (id_to < id_from) return;
+  vector<size_t> off, cnt;
+  vector<float> lr, dc;
+  for (int id = id_from; id <= id_to; ++id) {
+    const float l = rate * specs_[id].lr_mult;                        // sgd_solver.cpp:208-210
+    const float d = param_.weight_decay * specs_[id].decay_mult;      // :254-259
+    // lr_mult = decay_mult = 0 (BatchNorm statistics, batch_norm_layer.cpp): history stays 0, the blob is unchanged
+    // and its diff is never written, so the update is the identity -- left out of the fused launch
+    if (specs_[id].statistic && l == 0.f && d == 0.f) continue;
+    off.push_back(arena_.offset(id)); cnt.push_back(arena_.count(id)); lr.push_back(l); dc.push_back(d);
   }
+  const int n = (int)off.size();
+  if (n == 0) return;
   const float grad_scale = 1.f / (float)Caffe::solver_count() / param_.global_grad_scale / (float)param_.iter_size;
   B2C_CHECK(b2c_sgd_update_arena(n, off.data(), cnt.data(), lr.data(), dc.data(), arena_.diff(), arena_.data(), arena_.history(),
                                  momentum, param_.regularization_type == "L2" ? 1 : 0, grad_scale, param_.snapshot_diff ? 0 : 1, stream));
@@ -571,7 +574,10 @@ int P2PSync::divide_batch_size(int total, int solver_count) {
 }
 
 // ================================================================================================ scheduler
-ReduceScheduler::ReduceScheduler(SGDSolver* solver, P2PSync* sync) : solver_(solver), sync_(sync) {
+void P2PSync::soft_barrier() { CUDA_CHECK(cudaStreamSynchronize(comm_stream_)); }
+void P2PSync::reduce_barrier() { CUDA_CHECK(cudaStreamSynchronize(comm_stream_)); }
+
+ReduceScheduler::ReduceScheduler(SGDSolver* solver, SolverCallback* sync) : solver_(solver), sync_(sync) {
   buckets_ = PlanBuckets(solver->arena(), solver->param().reduce_buckets);
   CUDA_CHECK(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));

@@ -147,7 +147,10 @@ struct ConvolutionParameter {   // caffe.proto:718-786 (same names / defaults)
   bool force_nd_im2col = false;
   int math = B2C_MATH_FP32;           // forward_math / backward_math analogue (b2c_math)
 };
-struct ParamSpec { float lr_mult = 1.f, decay_mult = 1.f; };
+struct ParamSpec {
+  float lr_mult = 1.f, decay_mult = 1.f;
+  bool statistic = false;   // set by TrainNet for blobs their layer never differentiates (BatchNorm mean / variance / correction)
+};
 struct LayerParameter {
   string name, type;
   vector<string> bottom, top;
@@ -297,16 +300,31 @@ vector<Bucket> PlanBuckets(const ParamArena& arena, int reduce_buckets);
 // One NCCL communicator per process over b2c_comm; carries the rank-0 weight broadcast and the bucket
 // allreduce.  The unique id travels through the `bcast_bytes` callable supplied by the launcher
 // (MPI_Bcast in the reference, parallel.cpp:42-45; torch.distributed / a file here).
-class P2PSync {
+// Solver::Callback (include/caffe/solver.hpp:81-97): what the solver invokes at fixed points of an iteration.  The
+// reference's P2PSync implements it with NCCL + host barriers; here the bucket exchange is stream-ordered, so the two
+// barriers have nothing to wait for on the host and only order the comm stream.
+class SolverCallback {
+ public:
+  virtual ~SolverCallback() {}
+  virtual void on_start(ParamArena& arena) = 0;                    // Callback::on_start: weights from the root solver
+  virtual void allreduce_bucket(float* buf, size_t count) = 0;     // Callback::allreduce_bucket (async, comm stream)
+  virtual void soft_barrier() {}                                    // Callback::soft_barrier
+  virtual void reduce_barrier() {}                                  // Callback::reduce_barrier
+  virtual cudaStream_t comm_stream() const = 0;
+};
+
+class P2PSync : public SolverCallback {
  public:
   typedef std::function<void(void* buf, size_t bytes, int root)> BcastBytes;
   P2PSync(int nranks, int rank, const BcastBytes& bcast);
   ~P2PSync();
   int nranks() const { return nranks_; }
   int rank() const { return rank_; }
-  cudaStream_t comm_stream() const { return comm_stream_; }
-  void on_start(ParamArena& arena);                                   // parallel.cpp:208-227
-  void allreduce_bucket(float* buf, size_t count);                    // parallel.cpp:245-253 (async, comm stream)
+  cudaStream_t comm_stream() const override { return comm_stream_; }
+  void on_start(ParamArena& arena) override;                          // parallel.cpp:208-227
+  void allreduce_bucket(float* buf, size_t count) override;           // parallel.cpp:245-253 (async, comm stream)
+  void soft_barrier() override;                                       // parallel.cpp: MPI_Barrier -> comm-stream drain
+  void reduce_barrier() override;
   // batch division of parallel.cpp:284-293: per-rank batch, rounded up to a multiple
   static int divide_batch_size(int total, int solver_count);
  private:
@@ -320,7 +338,7 @@ class P2PSync {
 // with the remaining backward work.  No host thread, no host barrier.
 class ReduceScheduler {
  public:
-  ReduceScheduler(SGDSolver* solver, P2PSync* sync);
+  ReduceScheduler(SGDSolver* solver, SolverCallback* sync);
   ~ReduceScheduler();
   const vector<Bucket>& buckets() const { return buckets_; }
   // call after the backward of the layer owning param `id` has been enqueued on `compute` (ids arrive in
@@ -331,7 +349,7 @@ class ReduceScheduler {
  private:
   void flush(int b, cudaStream_t compute);
   SGDSolver* solver_;
-  P2PSync* sync_;
+  SolverCallback* sync_;
   vector<Bucket> buckets_;
   int next_bucket_ = 0;
   cudaEvent_t ev_ready_ = nullptr, ev_done_ = nullptr;

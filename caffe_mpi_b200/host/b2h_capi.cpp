@@ -317,15 +317,22 @@ int b2h_trainer_blob(void* hv, const char* name, int diff, int set, float* buf) 
     else memcpy(buf, diff ? b->cpu_diff() : b->cpu_data(), sizeof(float) * b->count());
   });
 }
-int b2h_trainer_num_params(void* hv) { return (int)static_cast<TrainerHandle*>(hv)->net->learnable_params().size(); }
-long long b2h_trainer_param_count(void* hv, int i) { return (long long)static_cast<TrainerHandle*>(hv)->net->learnable_params()[i]->count(); }
+// parameter access by TRAINABLE index (conv / fc weights + biases, BatchNorm scale + bias -- the blobs the layers
+// differentiate); b2h_trainer_num_learnable counts every layer blob like Net::learnable_params() (BatchNorm: 5)
+int b2h_trainer_num_params(void* hv) { return (int)static_cast<TrainerHandle*>(hv)->net->trainable_ids().size(); }
+int b2h_trainer_num_learnable(void* hv) { return (int)static_cast<TrainerHandle*>(hv)->net->learnable_params().size(); }
+long long b2h_trainer_param_count(void* hv, int i) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  return (long long)h->net->learnable_params()[h->net->trainable_ids()[i]]->count();
+}
 int b2h_trainer_param(void* hv, int i, int what, int set, float* buf) {   // what: 0 data, 1 diff, 2 history
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({
-    Blob& b = *h->net->learnable_params()[i];
+    const int id = h->net->trainable_ids().at(i);
+    Blob& b = *h->net->learnable_params()[id];
     CUDA_CHECK(cudaDeviceSynchronize());
     float* dev = what == 0 ? b.mutable_gpu_data() : what == 1 ? b.mutable_gpu_diff()
-                                                              : h->net->solver().arena().history() + h->net->solver().arena().offset(i);
+                                                              : h->net->solver().arena().history() + h->net->solver().arena().offset(id);
     if (set) CUDA_CHECK(cudaMemcpy(dev, buf, sizeof(float) * b.count(), cudaMemcpyHostToDevice));
     else CUDA_CHECK(cudaMemcpy(buf, dev, sizeof(float) * b.count(), cudaMemcpyDeviceToHost));
   });

@@ -319,6 +319,8 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       const PMessage* bp = lp.sub("batch_norm_param");
       L.bn_scale_bias = bp ? (bp->boolean("scale_bias", false) || bp->has("scale_filler") || bp->has("bias_filler")) : false;
       if (bp) { L.bn_eps = std::max((float)bp->num("eps", 1e-5), 1e-5f); L.bn_maf = (float)bp->num("moving_average_fraction", 0.999); }
+      if (bp && bp->has("scale_filler")) { L.bn_scale_filler = filler_of(bp->sub("scale_filler")); L.bn_has_scale_filler = true; }
+      if (bp && bp->has("bias_filler")) { L.bn_bias_filler = filler_of(bp->sub("bias_filler")); L.bn_has_bias_filler = true; }
       const std::vector<int>& bs = bottom_shape(0);
       tops.push_back(bs);
       // blobs_[0..2] = running mean / variance / correction (statistics, not exchanged with the cuDNN engine:
@@ -353,6 +355,13 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
                    L.lrn_region = (r == "WITHIN_CHANNEL" || r == "1") ? 1 : 0;
                  }
                  if (const PMessage* q = lp.sub("dropout_param")) L.dropout_ratio = (float)q->num("dropout_ratio", 0.5);
+               }(), false)) {
+    } else if (type == "Eltwise" && ([&] {
+                 if (const PMessage* q = lp.sub("eltwise_param")) {
+                   const std::string op = q->str("operation", "SUM");
+                   L.eltwise_op = (op == "PROD" || op == "0") ? 0 : (op == "MAX" || op == "2") ? 2 : 1;
+                   for (auto* f : q->all("coeff")) if (!f->is_msg()) L.eltwise_coeff.push_back((float)std::atof(f->scalar.c_str()));
+                 }
                }(), false)) {
     } else if (type == "ReLU" || type == "Dropout" || type == "LRN" || type == "Eltwise" || type == "Softmax" || type == "Sigmoid" ||
                type == "TanH" || type == "Power" || type == "Bias" || type == "ELU" || type == "PReLU" || type == "Split") {

@@ -54,6 +54,9 @@ struct NetLayer {                       // one LayerParameter after phase filter
   float bn_eps = 1e-5f, bn_maf = 0.999f; // BatchNormParameter.eps / moving_average_fraction
   FillerParameter ip_weight_filler, ip_bias_filler;
   float relu_slope = 0.f;
+  int eltwise_op = 1;                   // EltwiseParameter.operation: PROD = 0, SUM = 1, MAX = 2
+  std::vector<float> eltwise_coeff;
+  FillerParameter bn_scale_filler, bn_bias_filler; bool bn_has_scale_filler = false, bn_has_bias_filler = false;
   int lrn_size = 5; float lrn_alpha = 1.f, lrn_beta = 0.75f, lrn_k = 1.f; int lrn_region = 0;   // LRNParameter (caffe.proto:1039-1055)
   float dropout_ratio = 0.5f;           // DropoutParameter.dropout_ratio
   std::vector<float> loss_weight;        // LayerParameter.loss_weight (one per top)

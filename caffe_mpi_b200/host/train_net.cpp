@@ -11,12 +11,12 @@ static cudaStream_t S() { return Caffe::thread_stream(); }
 
 // ================================================================================================ ReLU
 void ReLULayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
-  B2C_CHECK(b2c_relu_forward(b[0]->count(), b[0]->gpu_data(), t[0]->mutable_gpu_data(), 0.f, S()));
+  B2C_CHECK(b2c_relu_forward(b[0]->count(), b[0]->gpu_data(), t[0]->mutable_gpu_data(), slope_, S()));
 }
 void ReLULayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
   if (!pd[0]) return;
   // in place: bottom data == top data (post-activation), same (x > 0) mask for slope 0 (relu_layer.cpp:27-41)
-  B2C_CHECK(b2c_relu_backward(b[0]->count(), t[0]->gpu_diff(), b[0]->gpu_data(), b[0]->mutable_gpu_diff(), 0.f, S()));
+  B2C_CHECK(b2c_relu_backward(b[0]->count(), t[0]->gpu_diff(), b[0]->gpu_data(), b[0]->mutable_gpu_diff(), slope_, S()));
 }
 
 // ================================================================================================ BatchNorm
@@ -29,10 +29,8 @@ void BatchNormLayer::LayerSetUp(const vector<Blob*>& b, const vector<Blob*>&) {
   if (scale_bias_) {
     blobs_[3].reset(new Blob(vector<int>{C}));
     blobs_[4].reset(new Blob(vector<int>{C}));
-    FillerParameter one; one.type = "constant"; one.value = 1.f;
-    Fill(one, blobs_[3].get());                   // scale = 1, bias = 0 (batch_norm_layer.cpp:52-63)
-    FillerParameter zero;
-    Fill(zero, blobs_[4].get());
+    Fill(scale_filler_, blobs_[3].get());         // defaults: scale = 1, bias = 0 (batch_norm_layer.cpp:52-63)
+    Fill(bias_filler_, blobs_[4].get());
   }
   param_propagate_down_.assign(blobs_.size(), false);
   if (scale_bias_) param_propagate_down_[3] = param_propagate_down_[4] = true;
@@ -241,10 +239,19 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       LayerParameter lp = L.param;
       lp.convolution_param.math = math;
       layer = LayerRegistry::CreateLayer(lp);
-    } else if (type == "ReLU") layer.reset(new ReLULayer(L.param));
-    else if (type == "BatchNorm") layer.reset(new BatchNormLayer(L.param, L.bn_scale_bias, L.bn_eps, L.bn_maf));
+    } else if (type == "ReLU") layer.reset(new ReLULayer(L.param, L.relu_slope));
+    else if (type == "BatchNorm") {
+      auto* bn = new BatchNormLayer(L.param, L.bn_scale_bias, L.bn_eps, L.bn_maf);
+      if (L.bn_has_scale_filler) bn->set_scale_filler(L.bn_scale_filler);      // batch_norm_layer.cpp:52-63
+      if (L.bn_has_bias_filler) bn->set_bias_filler(L.bn_bias_filler);
+      layer.reset(bn);
+    }
     else if (type == "Pooling") layer.reset(new PoolingLayer(L.param, L.pooling));
-    else if (type == "Eltwise") layer.reset(new EltwiseLayer(L.param));
+    else if (type == "Eltwise") {
+      B2_CHECK(L.eltwise_op == 1, "TrainNet: Eltwise PROD / MAX are not built (the BASELINE nets use SUM)");
+      for (float c : L.eltwise_coeff) B2_CHECK(c == 1.f, "TrainNet: Eltwise SUM is built for unit coefficients only");
+      layer.reset(new EltwiseLayer(L.param));
+    }
     else if (type == "InnerProduct") layer.reset(new InnerProductLayer(L.param, L.ip_num_output, L.ip_bias, L.ip_weight_filler, L.ip_bias_filler));
     else if (type == "SoftmaxWithLoss") {
       auto* sl = new SoftmaxWithLossLayer(L.param);
@@ -262,13 +269,17 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
     }
     else B2_CHECK(false, "TrainNet: layer type '" + type + "' is not built yet (SURVEY 8f rank 2 covers the ResNet-50 set)");
     layer->SetUp(node.bottom, node.top);
-    // learnable blobs in layer order (Net::AppendParam): every blob the layer marks param_propagate_down
+    // learnable blobs in layer order: Net::AppendParam (net.cpp:573-606) appends EVERY blob of every layer, so param ids,
+    // reduce-bucket boundaries and the SolverState history list (5 blobs per BatchNorm layer) match the reference.
+    // Blobs the layer never differentiates (BatchNorm mean / variance / correction, batch_norm_layer.cpp: lr_mult forced
+    // to 0) are marked `statistic`; trainable_ids_ lists the rest for the trainer API.
     node.first_param = (int)learnable_.size();
     for (size_t bi = 0; bi < layer->blobs().size(); ++bi) {
-      if (!layer->param_propagate_down((int)bi)) continue;
+      ParamSpec ps = bi < L.param.param.size() ? L.param.param[bi] : ParamSpec();
+      if (!layer->param_propagate_down((int)bi)) { ps.lr_mult = 0.f; ps.decay_mult = 0.f; ps.statistic = true; }
+      else trainable_ids_.push_back((int)learnable_.size());
       learnable_.push_back(layer->blobs()[bi]);
-      const size_t spec_idx = type == "BatchNorm" ? bi : (size_t)node.num_params;
-      specs.push_back(spec_idx < L.param.param.size() ? L.param.param[spec_idx] : ParamSpec());
+      specs.push_back(ps);
       ++node.num_params;
     }
     // need-backward analysis (net.cpp:160-283)
@@ -355,8 +366,14 @@ float TrainNet::ForwardBackward() {
   return last_loss();
 }
 void TrainNet::Step(bool copy_input_from_host) {
-  Forward(copy_input_from_host);
-  Backward(true);
+  // Solver::Step (solver.cpp:277-288): iter_size micro-batches accumulate into the parameter diffs (weight / bias
+  // gradients are accumulated by every layer, as in the reference); only the last one releases parameters to the
+  // reduction queue (ForwardBackward(apply_update = i + 1 == iter_size)), and the update folds 1/iter_size in.
+  const int iter_size = std::max(1, solver_->param().iter_size);
+  for (int i = 0; i < iter_size; ++i) {
+    Forward(copy_input_from_host);
+    Backward(i + 1 == iter_size);
+  }
   sched_->end_of_iteration(S());
 }
 float TrainNet::TimedSteps(int n, bool copy_input, bool read_loss) {
@@ -392,7 +409,13 @@ string TrainNet::Snapshot(const string& prefix) {
   for (size_t i = 0; i < layers_.size(); ++i) {
     LayerWeights lw;
     lw.name = layer_names_[i]; lw.type = layer_types_[i];
-    for (auto& b : layers_[i]->blobs()) lw.blobs.push_back(to_blob_data(b->shape(), b->cpu_data(), b->count()));
+    // read the DEVICE copy explicitly: the fused SGD kernel updates the arena behind the Blob's back, so a blob whose
+    // head was left SYNCED by an earlier cpu_data() would hand out stale host values (second snapshot of a process)
+    for (auto& b : layers_[i]->blobs()) {
+      vector<float> h(b->count());
+      CUDA_CHECK(cudaMemcpy(h.data(), b->gpu_data(), sizeof(float) * h.size(), cudaMemcpyDeviceToHost));
+      lw.blobs.push_back(to_blob_data(b->shape(), h.data(), h.size()));
+    }
     nw.layers.push_back(std::move(lw));
   }
   const string stem = prefix + "_iter_" + std::to_string(solver_->iter());

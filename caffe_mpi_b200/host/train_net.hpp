@@ -12,17 +12,22 @@ namespace caffe {
 
 class ReLULayer : public LayerBase {
  public:
-  using LayerBase::LayerBase;
+  ReLULayer(const LayerParameter& p, float negative_slope) : LayerBase(p), slope_(negative_slope) {}
   const char* type() const override { return "ReLU"; }
   void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { if (t[0] != b[0]) t[0]->ReshapeLike(*b[0]); }
  protected:
   void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
   void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
+  float slope_;     // relu_param.negative_slope (relu_layer.cpp:13-16)
 };
 
 class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_bias (batch_norm_layer.cpp)
  public:
-  BatchNormLayer(const LayerParameter& p, bool scale_bias, float eps, float maf) : LayerBase(p), scale_bias_(scale_bias), eps_(eps), maf_(maf) {}
+  BatchNormLayer(const LayerParameter& p, bool scale_bias, float eps, float maf) : LayerBase(p), scale_bias_(scale_bias), eps_(eps), maf_(maf) {
+    scale_filler_.type = "constant"; scale_filler_.value = 1.f;
+  }
+  void set_scale_filler(const FillerParameter& f) { scale_filler_ = f; }
+  void set_bias_filler(const FillerParameter& f) { bias_filler_ = f; }
   const char* type() const override { return "BatchNorm"; }
   void LayerSetUp(const vector<Blob*>& b, const vector<Blob*>& t) override;
   void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override;
@@ -31,6 +36,7 @@ class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_b
   void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
   bool scale_bias_;
   float eps_, maf_;
+  FillerParameter scale_filler_, bias_filler_;
   int iter_ = 0;
  public:
   void set_iter(int i) { iter_ = i; }
@@ -165,7 +171,8 @@ class TrainNet {
   Blob* blob(const string& name);
   int num_layers() const { return (int)layers_.size(); }
   LayerBase* layer(int i) { return layers_[i].get(); }
-  const vector<shared_ptr<Blob>>& learnable_params() const { return learnable_; }
+  const vector<shared_ptr<Blob>>& learnable_params() const { return learnable_; }   // Net::learnable_params(): every layer blob
+  const vector<int>& trainable_ids() const { return trainable_ids_; }               // ids the layers differentiate
   size_t activation_floats() const;
   // Solver::Snapshot (solver.cpp:447-520): <prefix>_iter_<N>.caffemodel (every layer's blobs, NVCaffe raw BlobProto) and
   // <prefix>_iter_<N>.solverstate (iter, learned_net, one history blob per learnable parameter, current_step).
@@ -193,6 +200,7 @@ class TrainNet {
   vector<Node> nodes_;
   vector<shared_ptr<Blob>> tmp_diffs_;
   vector<shared_ptr<Blob>> learnable_;
+  vector<int> trainable_ids_;
   std::unique_ptr<SGDSolver> solver_;
   std::unique_ptr<ReduceScheduler> sched_;
   P2PSync* sync_ = nullptr;

@@ -286,6 +286,7 @@ class Trainer:
         L.b2h_trainer_blob_count.restype = C.c_longlong
         L.b2h_trainer_blob.argtypes = [vp, C.c_char_p, i, i, _f32]
         L.b2h_trainer_num_params.argtypes = [vp]
+        L.b2h_trainer_num_learnable.argtypes = [vp]
         L.b2h_trainer_param_count.argtypes = [vp, i]
         L.b2h_trainer_param_count.restype = C.c_longlong
         L.b2h_trainer_param.argtypes = [vp, i, i, i, _f32]
@@ -342,7 +343,12 @@ class Trainer:
         _ck(lib().b2h_trainer_blob(self._h, name.encode(), int(diff), 1, np.ascontiguousarray(arr, np.float32).reshape(-1)))
 
     def num_params(self):
+        """Blobs the layers differentiate (weights, biases, BatchNorm scale / bias); the index space of get/set_param."""
         return lib().b2h_trainer_num_params(self._h)
+
+    def num_learnable(self):
+        """Net::learnable_params() of the reference: every layer blob (BatchNorm contributes 5), = SolverState history length."""
+        return lib().b2h_trainer_num_learnable(self._h)
 
     def get_param(self, i, what=0):
         out = np.empty(lib().b2h_trainer_param_count(self._h, i), np.float32)

@@ -85,3 +85,27 @@ def rel_err(a, ref):
     import numpy as np
     den = float(np.abs(ref).max())
     return float(np.abs(a.astype(np.float64) - ref.astype(np.float64)).max()) / (den if den > 0 else 1.0)
+
+
+# BASELINE.json configurations at FULL size (the batch sizes the benchmark runs): the persistent multi-tile path of the
+# forward / dgrad kernel (several tiles per CTA, accumulator ping-pong, mbarrier phase wrap) and the N-dependent split-K
+# plans of the weight-gradient kernels.  Checked against the reference's im2col + OpenBLAS loop (oracle.ref_conv_fwd_bwd),
+# which finishes each of these in seconds.  Mirrors test_convolution_layer.cpp:228-264,481-509 at benchmark scale.
+FULL_SIZE_CASES = [
+    ("resnet50_res2_1x1_expand_n64", dict(N=64, Cin=64, H=56, W=56, O=256, k=1, s=1, p=0, d=1, G=1, bias=False)),   # 3136 tiles
+    ("resnet50_res2_1x1_reduce_n64", dict(N=64, Cin=256, H=56, W=56, O=64, k=1, s=1, p=0, d=1, G=1, bias=False)),
+    ("resnet50_res2_3x3_n64", dict(N=64, Cin=64, H=56, W=56, O=64, k=3, s=1, p=1, d=1, G=1, bias=False)),
+    ("resnet50_res3_3x3_n64", dict(N=64, Cin=128, H=28, W=28, O=128, k=3, s=1, p=1, d=1, G=1, bias=False)),
+    ("resnet50_res4_3x3_n64", dict(N=64, Cin=256, H=14, W=14, O=256, k=3, s=1, p=1, d=1, G=1, bias=False)),
+    ("resnet50_res4_1x1_expand_n64", dict(N=64, Cin=256, H=14, W=14, O=1024, k=1, s=1, p=0, d=1, G=1, bias=False)),
+    ("resnet50_res5_3x3_n64", dict(N=64, Cin=512, H=7, W=7, O=512, k=3, s=1, p=1, d=1, G=1, bias=False)),
+    ("resnet50_res5_1x1_reduce_n64", dict(N=64, Cin=2048, H=7, W=7, O=512, k=1, s=1, p=0, d=1, G=1, bias=False)),
+    ("resnet50_res3_1x1_s2_n64", dict(N=64, Cin=256, H=56, W=56, O=512, k=1, s=2, p=0, d=1, G=1, bias=False)),
+    ("resnet50_stem_7x7_n64", dict(N=64, Cin=3, H=224, W=224, O=64, k=7, s=2, p=3, d=1, G=1, bias=False)),
+    ("alexnet_conv2_g2_n256", dict(N=256, Cin=96, H=27, W=27, O=256, k=5, s=1, p=2, d=1, G=2, bias=True)),
+    ("alexnet_conv3_n256", dict(N=256, Cin=256, H=13, W=13, O=384, k=3, s=1, p=1, d=1, G=1, bias=True)),
+    ("vgg16_conv1_2_n32", dict(N=32, Cin=64, H=224, W=224, O=64, k=3, s=1, p=1, d=1, G=1, bias=True)),
+    ("vgg16_conv5_n32", dict(N=32, Cin=512, H=14, W=14, O=512, k=3, s=1, p=1, d=1, G=1, bias=True)),
+    ("googlenet_3a_5x5_n128", dict(N=128, Cin=16, H=28, W=28, O=32, k=5, s=1, p=2, d=1, G=1, bias=True)),
+    ("googlenet_3a_3x3_n128", dict(N=128, Cin=96, H=28, W=28, O=128, k=3, s=1, p=1, d=1, G=1, bias=True)),
+]

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle as o
-from cases import ALL_CASES, EDGE_CASES, MODEL_CASES, REF_TEST_CASES, make, tensors, rel_err
+from cases import ALL_CASES, EDGE_CASES, FULL_SIZE_CASES, MODEL_CASES, REF_TEST_CASES, make, tensors, rel_err
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -211,6 +211,49 @@ def test_golden_fixtures_from_reference_build():
                 DB = torch.zeros(prm.O, device="cuda")
                 d.backward_bias(DY, DB)
                 assert rel_err(host(DB), z[nm + "/db"]) < TOL_FP32, nm
+
+
+@pytest.mark.parametrize("name,case", FULL_SIZE_CASES, ids=[c[0] for c in FULL_SIZE_CASES])
+def test_full_size_vs_reference_loop(rng, name, case):
+    """The shapes and batch sizes the benchmark runs (BASELINE.json configs), forward + dgrad + wgrad (+ bias grad) in the
+    default fp32-equivalent mode against the reference's own CPU structure -- verbatim im2col.cpp + per-image/per-group
+    OpenBLAS sgemm (oracle/_ref) -- at 1e-4.  These launches run several tiles per persistent CTA (up to 3136 tiles on 148
+    SMs) and the split-K plans that depend on N, which the small cases above never reach."""
+    if o.ref() is None or not o.ref_blas_open(min(32, os.cpu_count() or 1)):
+        pytest.skip("oracle/_ref or OpenBLAS not available")
+    po, pc = make(o, case), make(capi, case)
+    x = rng.standard_normal(po.x_shape(), dtype=np.float32)
+    w = rng.standard_normal(po.w_shape(), dtype=np.float32) * np.float32((2.0 / po.Kd) ** 0.5)
+    b = (rng.standard_normal(po.O, dtype=np.float32) * np.float32(0.1)) if po.has_bias else None
+    dy = rng.standard_normal(po.y_shape(), dtype=np.float32)
+    dw0 = rng.standard_normal(po.w_shape(), dtype=np.float32) * np.float32(0.1)   # pre-existing diff: accumulated into
+    want_y = np.empty(po.y_shape(), np.float32)
+    want_dw = dw0.copy()
+    want_db = np.zeros(po.O, np.float32) if po.has_bias else None
+    want_dx = np.empty(po.x_shape(), np.float32)
+    o.ref_conv_fwd_bwd(po, x, w, b, y=want_y, dy=dy, dw=want_dw, db=want_db, dx=want_dx)
+    d = m.ConvDesc(pc)
+    strided_k = case["s"] != 1 and case["k"] != 1      # no BASELINE layer of this kind needs a bottom gradient (conv1 only)
+    for op in (0, 2) if strided_k else (0, 1, 2):
+        assert d.algo_used(op) == capi.ALGO_TCGEN05, "full-size BASELINE layers must run on the tcgen05 kernels"
+    X, Wt, Bv, DY = dev(x), dev(w), dev(b), dev(dy)
+    Y = torch.full(po.y_shape(), 3.0, device="cuda")
+    d.forward(X, Wt, Bv, Y)
+    DX = torch.full(po.x_shape(), 3.0, device="cuda")
+    d.backward_data(DY, Wt, DX)
+    DW = dev(dw0)
+    d.backward_filter(X, DY, DW)
+    for k, got, want in (("y", Y, want_y), ("dx", DX, want_dx), ("dw", DW, want_dw)):
+        e = rel_err(host(got), want)
+        assert e < TOL_FP32, (name, k, e)
+    if po.has_bias:
+        DB = torch.zeros(po.O, device="cuda")
+        d.backward_bias(DY, DB)
+        assert rel_err(host(DB), want_db) < TOL_FP32
+    # run-to-run determinism of the split-K reductions (the reference accumulates in a fixed order too)
+    DW2 = dev(dw0)
+    d.backward_filter(X, DY, DW2)
+    assert torch.equal(DW, DW2)
 
 
 def test_full_size_properties_resnet50_layer(rng):

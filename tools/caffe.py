@@ -25,7 +25,8 @@ def cmd_device_query(_):
     n = C.c_int()
     if rt.cudaGetDeviceCount(C.byref(n)) != 0 or n.value == 0:
         sys.exit("caffe.py: no CUDA device (there is no CPU mode)")
-    log("libb2c version %d, %d device(s)" % (capi.lib().b2c_version(), n.value))
+    v = capi.lib().b2c_version()
+    log("libb2c version %s, %d device(s)" % (v.decode() if isinstance(v, bytes) else v, n.value))
 
 
 def build_trainer(args, net, net_is_text, solver, solver_is_text):
