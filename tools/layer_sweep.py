@@ -11,11 +11,16 @@ model = sys.argv[1] if len(sys.argv) > 1 else "resnet50"
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 math = capi.MATH_TF32 if (len(sys.argv) > 3 and sys.argv[3] == "tf32") else capi.MATH_FP32
 reps = 5
+only = os.environ.get("B2C_SWEEP_ONLY", "").split()      # e.g. "k1 s2": keep layers whose label contains every token
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
 print(f"{'layer':34s} {'op':6s} {'us':>9s} {'TF/s':>7s} {'GB/s(alg)':>10s} {'hbm_us':>7s} {'mma_us':>7s}")
 first = True
 for (cnt, C, H, O, k, s, p, G, bias) in MODELS[model]:
+    label = f"C{C} H{H} O{O} k{k} s{s} g{G}"
+    if any(tok not in label.split() for tok in only):
+        first = False
+        continue
     prm = capi.ConvParams.make(N, C, H, H, O, k, s, p, 1, G, bias)
     d = m.ConvDesc(prm, capi.ENGINE_DEFAULT, math=math)
     x = torch.randn(prm.x_shape(), device="cuda"); w = torch.randn(prm.w_shape(), device="cuda") * 0.05
