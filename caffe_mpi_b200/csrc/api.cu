@@ -56,6 +56,11 @@ bool tc_conv_supported(const ConvShape&, int op);
 size_t tc_conv_workspace(const ConvShape&, int op, int math);
 int launch_conv_tc(const ConvShape&, int op, int math, const float* a, const float* b, const float* bias, float* out,
                    void* ws, size_t ws_bytes, cudaStream_t);
+// bulk-copy-staged bf16x3 kernel (conv_tc_stg.cu): forward / dgrad of stride-1 "same" convolutions
+bool tc_stg_supported(const ConvShape&, int op);
+size_t tc_stg_workspace(const ConvShape&, int op);
+int launch_conv_tc_stg(const ConvShape&, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
+                       size_t ws_bytes, cudaStream_t);
 bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K);
 int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta,
                     float* C, int math, cudaStream_t);
@@ -69,9 +74,16 @@ static bool have_device() {
   return ok == 1;
 }
 
+static bool use_staged(const b2c_conv_desc* d, int op) {
+  return d->engine != B2C_ENGINE_CAFFE && d->algo != B2C_ALGO_SIMT && d->math == B2C_MATH_FP32 && tc_stg_supported(d->s, op);
+}
+// math mode handed to the gather kernels (conv_tc.cu / conv_tc_wgrad.cu), which know FP32 (= 3xTF32) and TF32
+static int gather_math(const b2c_conv_desc* d) { return d->math == B2C_MATH_TF32 ? B2C_MATH_TF32 : B2C_MATH_FP32; }
+
 static int resolve_algo(const b2c_conv_desc* d, int op) {
   if (d->engine == B2C_ENGINE_CAFFE) return B2C_ALGO_SIMT;  // reported family of the explicit path's GEMM
   if (d->algo == B2C_ALGO_SIMT) return B2C_ALGO_SIMT;
+  if (use_staged(d, op)) return B2C_ALGO_TCGEN05;
   return tc_conv_supported(d->s, op) ? B2C_ALGO_TCGEN05 : B2C_ALGO_SIMT;
 }
 
@@ -83,7 +95,7 @@ extern "C" const char* b2c_last_error(void) { return last_error().c_str(); }
 extern "C" const char* b2c_version(void) { return "b2c 0.1 (sm_100a)"; }
 extern "C" uint64_t b2c_launch_count(void) { return g_launches.load(); }
 extern "C" int b2c_set_default_math(int m) {
-  if (m != B2C_MATH_FP32 && m != B2C_MATH_TF32) return fail(B2C_ERR_INVALID, "bad math mode %d", m);
+  if (m < B2C_MATH_FP32 || m > B2C_MATH_FP32_3XTF32) return fail(B2C_ERR_INVALID, "bad math mode %d", m);
   g_default_math = m;
   return B2C_OK;
 }
@@ -123,7 +135,7 @@ extern "C" int b2c_conv_desc_create(const b2c_conv_params* p, int engine, b2c_co
 }
 extern "C" int b2c_conv_desc_destroy(b2c_conv_desc* d) { delete d; return B2C_OK; }
 extern "C" int b2c_conv_desc_set_math(b2c_conv_desc* d, int m) {
-  if (!d || (m != B2C_MATH_FP32 && m != B2C_MATH_TF32)) return fail(B2C_ERR_INVALID, "set_math: bad argument");
+  if (!d || m < B2C_MATH_FP32 || m > B2C_MATH_FP32_3XTF32) return fail(B2C_ERR_INVALID, "set_math: bad argument");
   d->math = m;
   return B2C_OK;
 }
@@ -148,7 +160,11 @@ extern "C" size_t b2c_conv_workspace_bytes(const b2c_conv_desc* d, int op) {
   const ConvShape& s = d->s;
   if (d->engine == B2C_ENGINE_CAFFE)   // one image's col buffer [Kd*G, Ho, Wo] (base_conv_layer.cpp:225-233)
     return s.is_1x1 ? 0 : sizeof(float) * (size_t)s.Kd * s.G * s.Ho * s.Wo;
-  if (resolve_algo(d, op) == B2C_ALGO_TCGEN05) return tc_conv_workspace(s, op, d->math);
+  if (use_staged(d, op)) {   // the gather kernel is the fallback for unaligned activation pointers: size for both
+    const size_t a = tc_stg_workspace(s, op), b = tc_conv_supported(s, op) ? tc_conv_workspace(s, op, gather_math(d)) : 0;
+    return a > b ? a : b;
+  }
+  if (resolve_algo(d, op) == B2C_ALGO_TCGEN05) return tc_conv_workspace(s, op, gather_math(d));
   return 0;
 }
 
@@ -182,8 +198,10 @@ extern "C" int b2c_conv_forward(const b2c_conv_desc* d, const float* x, const fl
     if (bias) return launch_bias_add(s.N, s.O, P, bias, y, st);
     return B2C_OK;
   }
-  if (resolve_algo(d, B2C_OP_FORWARD) == B2C_ALGO_TCGEN05)
-    return launch_conv_tc(s, B2C_OP_FORWARD, d->math, x, w, bias, y, ws, ws_bytes, st);
+  if (use_staged(d, B2C_OP_FORWARD) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0)
+    return launch_conv_tc_stg(s, B2C_OP_FORWARD, x, w, bias, y, ws, ws_bytes, st);
+  if (tc_conv_supported(s, B2C_OP_FORWARD) && d->algo != B2C_ALGO_SIMT)
+    return launch_conv_tc(s, B2C_OP_FORWARD, gather_math(d), x, w, bias, y, ws, ws_bytes, st);
   return launch_conv_fwd_simt(s, x, w, bias, y, st);
 }
 
@@ -209,8 +227,10 @@ extern "C" int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, c
     }
     return B2C_OK;
   }
-  if (resolve_algo(d, B2C_OP_BACKWARD_DATA) == B2C_ALGO_TCGEN05)
-    return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, d->math, dy, w, nullptr, dx, ws, ws_bytes, st);
+  if (use_staged(d, B2C_OP_BACKWARD_DATA) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0)
+    return launch_conv_tc_stg(s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, st);
+  if (tc_conv_supported(s, B2C_OP_BACKWARD_DATA) && d->algo != B2C_ALGO_SIMT)
+    return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, gather_math(d), dy, w, nullptr, dx, ws, ws_bytes, st);
   return launch_conv_dgrad_simt(s, dy, w, dx, st);
 }
 
@@ -239,7 +259,7 @@ extern "C" int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, 
     return B2C_OK;
   }
   if (resolve_algo(d, B2C_OP_BACKWARD_FILTER) == B2C_ALGO_TCGEN05)
-    return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, d->math, x, dy, nullptr, dw, ws, ws_bytes, st);
+    return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, gather_math(d), x, dy, nullptr, dw, ws, ws_bytes, st);
   return launch_conv_wgrad_simt(s, x, dy, dw, st);
 }
 

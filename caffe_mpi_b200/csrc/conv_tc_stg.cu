@@ -1,0 +1,585 @@
+// conv_tc_stg.cu -- tcgen05 implicit-GEMM convolution with BULK-COPY-STAGED activations and bf16x3 math (sm_100a):
+// forward and data-gradient of stride-1 "same" convolutions (1x1 / pad 0, 3x3 / pad 1, 5x5 / pad 2 ...), which are
+// 43 of ResNet-50's 53 layers and every VGG-16 / GoogLeNet inception convolution with C % 32 == 0.
+//
+// Replaces cudnnConvolutionForward / cudnnConvolutionBackwardData as the reference's CuDNNConvolutionLayer calls them
+// (src/caffe/layers/cudnn_conv_layer.cu:25-29,118-123); same contract as conv_tc.cu: NCHW fp32 in and out, whole
+// batch per launch, y / dx overwritten, bias fused.
+//
+// Why a second kernel.  conv_tc.cu gathers the im2col rows with per-thread __ldg: ~1 400 cycles per 128x32 K block
+// against 768 cycles of MMA (profiles/README.md), and it re-reads every input pixel kh*kw times through L1/L2.  Here
+// no thread touches global memory for the activation operand:
+//   * GEMM rows are 128 CONSECUTIVE flattened pixels q = n*H*W + p.  For one input channel the pixels a tile needs --
+//     its own 128 plus a halo of pad*W + pad on either side, clipped to each image -- are one contiguous run of global
+//     memory per image, so the TMA unit brings them in with 1-D bulk copies (cp.async.bulk, one per channel and
+//     image segment, completion on an mbarrier): a "channel group" of 32 channels x (128 + 2*halo) floats per stage.
+//   * All kh*kw taps of those 32 channels are then served from that ONE staged copy: tap (i,j) of row r is the staged
+//     value at slot r + (i-pad)*W + (j-pad); rows whose tap falls outside the image (zero padding, image borders,
+//     row wrap) are masked with a per-row bit computed once per tile.  Global->smem traffic per tile is
+//     (128 + 2*halo)/128 of the input instead of kh*kw times it.
+//   * 16 converter warps read the staged fp32 values (lanes = consecutive pixels: conflict-free), split each into
+//     bf16 hi + bf16 lo (hi = rn(a), lo = rn(a - hi)), pack pairs along K and write the A operand straight into TENSOR
+//     MEMORY with tcgen05.st (lane = GEMM row), 64 K-elements per stage.
+//   * The filter is pre-split into bf16 hi / lo in GEMM-K order (channel group, tap, channel) by a prepass and streamed
+//     by TMA (SWIZZLE_128B, [N_TILE x 64] boxes); one converged warp issues tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32):
+//     lo*hi + hi*lo + hi*hi per K step -- three bf16 MMAs cost 1.5 TF32-MMA equivalents (3xTF32 costs 3), and the
+//     operand bytes in shared / tensor memory halve.  Dropped terms (lo*lo and the bf16 rounding of lo) are ~2^-17 per
+//     product: blob-level error ~1e-6..1e-5 against the double-accumulating oracle, 100x inside the 1e-3 bar.
+//   * Epilogue as in conv_tc.cu: double-buffered TMEM accumulators, tcgen05.ld, 32-channel chunks transposed through
+//     shared memory, 512-byte store instructions.
+// dgrad of a stride-1 same convolution is the same kernel on dY with the transposed + flipped filter.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <limits.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include "b2c_common.cuh"
+#include "tc_common.cuh"
+
+namespace b2c {
+using namespace tc;
+
+namespace stg {
+
+constexpr int NCW = 16;                       // converter warps
+constexpr int W_BTMA = NCW;                   // filter TMA warp
+constexpr int W_MMA = NCW + 1;                // MMA issuer (also owns the TMEM allocation)
+constexpr int W_STG = NCW + 2;                // activation bulk-copy warp
+constexpr int W_EPI0 = NCW + 3;               // first of 4 epilogue warps
+constexpr int THREADS = (NCW + 7) * 32;       // 736
+constexpr int CB = 32;                        // channels per staged group
+constexpr int BKE = 64;                       // bf16 K elements per pipeline stage (two (group, tap) half blocks)
+constexpr int STAGES = 3;                     // operand pipeline depth (B in smem, A in TMEM)
+constexpr uint32_t STG_POOL = 64u * 1024u;    // activation staging pool
+constexpr int MAX_TAPS = 32;                  // per-row validity mask is one 32-bit word
+
+struct Params {
+  const float* x;          // [Nimg, Ctot, H, W]; this launch reads channels [0, Cg) (G == 1)
+  int Ctot, Cg, H, W, HW;
+  int kh, kw, ph, pw;
+  int Mtot;                // Nimg * H * W (output pixel grid == input pixel grid)
+  int Ntot;                // GEMM columns (output channels)
+  int taps, groups;        // kh*kw, Cg / 32
+  int nhb, nkb;            // half blocks = groups * taps, K blocks = ceil(nhb / 2)
+  int halo, lead;          // pad*W + pad;  slot of (row 0, offset -halo): lead = 4 + (-halo mod 4), multiple-of-4 aligned total
+  int sp;                  // floats per staged channel row (multiple of 4)
+  int nstg;                // staging buffers in the pool (2..4)
+  float* out;              // [Nimg, Cout_tot, H, W]
+  int Cout_tot;
+  const float* bias;       // [Ntot] or null
+  int m_tiles, n_tiles, total_tiles;
+  long long* prof;
+};
+
+template <int N_TILE>
+struct Smem {
+  static constexpr uint32_t B_BYTES = (uint32_t)N_TILE * 128u;              // [N_TILE rows][64 bf16], SW128
+  static constexpr uint32_t STAGE = 2u * B_BYTES;                           // hi + lo
+  static constexpr uint32_t STG_OFF = STAGES * STAGE;
+  static constexpr uint32_t EPI_OFF = STG_OFF + STG_POOL;                   // 2 x [32 channels][128 pixels] fp32
+  static constexpr uint32_t EPI_BYTES = 2u * 32u * 128u * 4u;
+  static constexpr uint32_t BAR_OFF = EPI_OFF + EPI_BYTES;
+  static constexpr uint32_t TAP_OFF = BAR_OFF + 256;                        // int tap offsets [MAX_TAPS]
+  static constexpr uint32_t TOTAL = TAP_OFF + MAX_TAPS * 4 + 1024;          // + alignment slack
+  static constexpr uint32_t TX_BYTES = STAGE;
+  static constexpr uint32_t A_COL0 = 2u * N_TILE;                           // after the two accumulators
+  static constexpr uint32_t A_COLS = 64u;                                   // 32 packed hi columns + 32 packed lo columns
+  static_assert(A_COL0 + STAGES * A_COLS <= 512u, "TMEM budget");
+};
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D=F32, A=B=BF16, both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned addresses and size), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// fp32 pair (k even, k odd) -> packed bf16 hi word and packed bf16 lo word; element k sits in the LOW half
+// (tensor-memory A operand of kind::f16: two consecutive K elements per 32-bit column, little endian)
+__device__ __forceinline__ void split_pack_bf16(float e, float o, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(e, o);            // .x = e (low half), .y = o
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(e - hf.x, o - hf.y);   // a - hi is exact in fp32
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(THREADS, 1)
+igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap map_hi,
+                 const __grid_constant__ CUtensorMap map_lo) {
+  using S = Smem<N_TILE>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_full = sbase + S::BAR_OFF;                 // STAGES: 16 converter warps + the filter TMA's expect_tx
+  const uint32_t bar_empty = bar_full + 8 * STAGES;             // STAGES: tcgen05.commit
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;            // 2
+  const uint32_t bar_tempty = bar_tfull + 16;                   // 2
+  const uint32_t bar_sfull = bar_tempty + 16;                   // 4: staged group landed (bulk-copy bytes)
+  const uint32_t bar_sempty = bar_sfull + 32;                   // 4: converters are done with the staged group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 8 * (2 * STAGES + 4 + 8));
+  int* tapoff = reinterpret_cast<int*>(sptr + S::TAP_OFF);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t stg_bytes = (uint32_t)CB * (uint32_t)p.sp * 4u;     // one staged group (multiple of 16)
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, NCW + 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    for (int b = 0; b < 4; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, NCW); }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (tid < p.taps) {
+    const int i = tid / p.kw, j = tid - i * p.kw;
+    tapoff[tid] = (i - p.ph) * p.W + (j - p.pw);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_b_hi = [&](int s) { return sbase + (uint32_t)s * S::STAGE; };
+  auto stage_b_lo = [&](int s) { return sbase + (uint32_t)s * S::STAGE + S::B_BYTES; };
+  auto stage_a_col = [&](int s) { return S::A_COL0 + (uint32_t)s * S::A_COLS; };
+  auto stg_addr = [&](int slot) { return sbase + S::STG_OFF + (uint32_t)slot * stg_bytes; };
+  auto tile_coords = [&](int tile, int& m0, int& n0) {
+    const int nt = tile % p.n_tiles;
+    m0 = (tile / p.n_tiles) * 128; n0 = nt * N_TILE;
+  };
+  const bool prof = p.prof != nullptr && blockIdx.x == 0;
+
+  if (warp < NCW) {
+    // ================= converters: staged fp32 -> bf16 hi/lo -> tensor memory ===============================
+    const int rq = warp & 3, sub = warp >> 2;                 // TMEM lane quarter, channel octet [sub*8, sub*8+8) of every half block
+    const int row = rq * 32 + lane;
+    const uint32_t a_lane = (uint32_t)(rq * 32) << 16;
+    long long c_sfull = 0, c_empty = 0, c_t0 = 0;
+    if (prof) c_t0 = clock64();
+    int kbg = 0;                                               // K blocks processed by this CTA (stage ring position)
+    int gc_base = 0;                                           // staged groups consumed before this tile
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      // per-row tap validity (zero padding / image borders / row wrap), once per tile
+      uint32_t mask = 0;
+      {
+        const int q = m0 + row;
+        if (q < p.Mtot) {
+          const int n = q / p.HW, pp = q - n * p.HW;
+          const int h = pp / p.W, w = pp - h * p.W;
+          if (p.taps == 1) mask = 1u;
+          else {
+            int t = 0;
+            for (int i = 0; i < p.kh; ++i) {
+              const bool hok = (unsigned)(h + i - p.ph) < (unsigned)p.H;
+              for (int j = 0; j < p.kw; ++j, ++t)
+                if (hok && (unsigned)(w + j - p.pw) < (unsigned)p.W) mask |= 1u << t;
+            }
+          }
+        }
+      }
+      // slot of this row at tap offset 0, as a byte offset inside a staged channel row; + channel octet base
+      const uint32_t row_off = (uint32_t)(row + p.halo + p.lead) * 4u + (uint32_t)(sub * 8) * (uint32_t)p.sp * 4u;
+      int g = 0, tap = 0, released = 0;
+      for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (2 * kb + h < p.nhb) {
+            const int gc = gc_base + g;
+            const int slot = gc % p.nstg;
+            if (prof) { const long long t0 = clock64(); mbar_wait(bar_sfull + 8 * slot, (gc / p.nstg) & 1); c_sfull += clock64() - t0; }
+            else mbar_wait(bar_sfull + 8 * slot, (gc / p.nstg) & 1);
+            const bool ok = (mask >> tap) & 1u;
+            const uint32_t src = stg_addr(slot) + row_off + (uint32_t)(tapoff[tap] * 4);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = lds32(src + (uint32_t)e * (uint32_t)p.sp * 4u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = ok ? v[2 * e] : 0.f, a1 = ok ? v[2 * e + 1] : 0.f;
+              split_pack_bf16(a0, a1, hi[h * 4 + e], lo[h * 4 + e]);
+            }
+            if (++tap == p.taps) { tap = 0; ++g; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { hi[h * 4 + e] = 0u; lo[h * 4 + e] = 0u; }   // K padding: finite zeros
+          }
+        }
+        // staged groups fully consumed by this warp: hand them back to the bulk-copy warp
+        __syncwarp();
+        while (released < g) {
+          if (lane == 0) mbar_arrive(bar_sempty + 8 * ((gc_base + released) % p.nstg));
+          ++released;
+        }
+        const int s = kbg % STAGES, it = kbg / STAGES;
+        if (prof) { const long long t0 = clock64(); mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 32); c_empty += clock64() - t0; }
+        else mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 32);
+        tc_fence_after();
+        const uint32_t a0 = tmem_base + a_lane + stage_a_col(s) + (uint32_t)(sub * 4);
+        tmem_st4(a0, hi[0], hi[1], hi[2], hi[3]);
+        tmem_st4(a0 + 16, hi[4], hi[5], hi[6], hi[7]);
+        tmem_st4(a0 + 32, lo[0], lo[1], lo[2], lo[3]);
+        tmem_st4(a0 + 48, lo[4], lo[5], lo[6], lo[7]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      }
+      gc_base += p.groups;
+    }
+    if (prof && tid == 0) { p.prof[0] = clock64() - c_t0; p.prof[1] = c_sfull; p.prof[2] = c_empty; p.prof[3] = kbg; }
+  } else if (warp == W_BTMA) {
+    // ================= filter TMA producer ====================================================================
+    int kbg = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+        const int s = kbg % STAGES, it = kbg / STAGES;
+        mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 32);
+        if (elect_one()) {
+          arrive_expect_tx(bar_full + 8 * s, S::TX_BYTES);
+          tma_load_3d(stage_b_hi(s), &map_hi, bar_full + 8 * s, kb * BKE, n0, 0);
+          tma_load_3d(stage_b_lo(s), &map_lo, bar_full + 8 * s, kb * BKE, n0, 0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == W_STG) {
+    // ================= activation bulk-copy producer: lane = channel of the group ===============================
+    int gc = 0;
+    int last_m0 = -1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      (void)last_m0;
+      const int q_end = min(m0 + 128, p.Mtot);
+      const int n_first = m0 / p.HW, n_last = (q_end - 1) / p.HW;
+      for (int g = 0; g < p.groups; ++g, ++gc) {
+        const int slot = gc % p.nstg;
+        mbar_wait_backoff(bar_sempty + 8 * slot, ((gc / p.nstg) & 1) ^ 1, 32);
+        // bytes of this group: same segments for every channel
+        uint32_t seg_floats = 0;
+        for (int n = n_first; n <= n_last; ++n) {
+          const int q_lo = max(m0, n * p.HW), q_hi = min(q_end, (n + 1) * p.HW);
+          const int ps = max(0, q_lo - n * p.HW - p.halo) & ~3;
+          const int pe = min(p.HW, (q_hi - n * p.HW + p.halo + 3) & ~3);
+          seg_floats += (uint32_t)(pe - ps);
+        }
+        if (lane == 0) arrive_expect_tx(bar_sfull + 8 * slot, seg_floats * 4u * CB);
+        __syncwarp();
+        const uint32_t dst_row = stg_addr(slot) + (uint32_t)lane * (uint32_t)p.sp * 4u;
+        const float* src_ch = p.x + (size_t)(g * CB + lane) * p.HW;
+        for (int n = n_first; n <= n_last; ++n) {
+          const int q_lo = max(m0, n * p.HW), q_hi = min(q_end, (n + 1) * p.HW);
+          const int ps = max(0, q_lo - n * p.HW - p.halo) & ~3;
+          const int pe = min(p.HW, (q_hi - n * p.HW + p.halo + 3) & ~3);
+          const int slot0 = ps + n * p.HW - m0 + p.halo + p.lead;          // >= 1, multiple of 4
+          bulk_load_1d(dst_row + (uint32_t)slot0 * 4u, src_ch + (size_t)n * p.Ctot * p.HW + ps, (uint32_t)(pe - ps) * 4u, bar_sfull + 8 * slot);
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ================= MMA issuer ==============================================================================
+    constexpr uint32_t IDESC = idesc_bf16(128, N_TILE);
+    int kbg = 0, ti = 0;
+    long long m_full = 0, m_t0 = 0;
+    if (prof) m_t0 = clock64();
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1, use = ti >> 1;
+      mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
+      for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
+        const int s = kbg % STAGES, it = kbg / STAGES;
+        if (prof) { const long long t0 = clock64(); mbar_wait(bar_full + 8 * s, it & 1); m_full += clock64() - t0; }
+        else mbar_wait(bar_full + 8 * s, it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BKE / 16; ++kk) {
+            const uint32_t ah = tmem_base + stage_a_col(s) + (uint32_t)(kk * 8);
+            const uint64_t bh = desc_sw128(stage_b_hi(s) + kk * 32);
+            const uint64_t bl = desc_sw128(stage_b_lo(s) + kk * 32);
+            umma_bf16_ts(d_tmem, ah + 32, bh, IDESC, (kb | kk) != 0);   // lo * hi
+            umma_bf16_ts(d_tmem, ah, bl, IDESC, 1);                      // hi * lo
+            umma_bf16_ts(d_tmem, ah, bh, IDESC, 1);                      // hi * hi
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (kb == p.nkb - 1) umma_commit(bar_tfull + 8 * buf);
+        }
+        __syncwarp();
+      }
+    }
+    if (prof && lane == 0) { p.prof[8] = clock64() - m_t0; p.prof[9] = m_full; p.prof[10] = kbg; }
+  } else {
+    // ================= epilogue warps ============================================================================
+    // tcgen05.ld -> (+ bias) -> 32-channel chunk transposed into shared memory [channel][128 pixels] -> the TMA unit
+    // writes it out: one 1-D bulk store per channel and image segment (512 contiguous bytes of an NCHW plane), issued by
+    // the 32 lanes of the first epilogue warp.  The warps' own st.global path cost ~3 100 cycles per 128x128 tile on the
+    // short-K 1x1 layers (profiles/r01_prof_1x1_fwd_store_ablation.txt) against 768 cycles of MMA.
+    const int lg = warp & 3;                  // TMEM lane quarter this warp may read (warp id % 4)
+    const int r = lg * 32 + lane;
+    const bool issuer = warp == W_EPI0;
+    float* epi = reinterpret_cast<float*>(sptr + S::EPI_OFF);
+    int epi_chunk = 0, ti = 0;
+    long long e_wait = 0, e_work = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      const int buf = ti & 1, use = ti >> 1;
+      const int q_end = min(m0 + 128, p.Mtot);
+      const int n_first = m0 / p.HW, n_last = (q_end - 1) / p.HW;
+      const float* brow = p.bias ? p.bias + n0 : nullptr;
+      long long e0 = 0;
+      if (prof) e0 = clock64();
+      mbar_wait_backoff(bar_tfull + 8 * buf, use & 1, 128);
+      long long e1 = 0;
+      if (prof) { e1 = clock64(); e_wait += e1 - e0; }
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32, ++epi_chunk) {
+        if (n0 + c0 >= p.Ntot) break;                     // uniform over the four epilogue warps
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * N_TILE + c0), v);
+        if (c0 + 32 >= N_TILE || n0 + c0 + 32 >= p.Ntot) {   // accumulator fully read: hand it back before storing
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        if (brow) {
+          const int nb = min(32, p.Ntot - n0 - c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nb) v[j] += __ldg(brow + c0 + j);    // warp-uniform address: broadcast
+        }
+        // the bulk stores issued two chunks ago from this staging buffer have finished reading it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* E = epi + (epi_chunk & 1) * (32 * 128);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) E[j * 128 + r] = v[j];           // lanes = consecutive pixels: conflict-free
+        fence_proxy_async();                                           // generic-proxy writes -> visible to the bulk store
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          const int ch = n0 + c0 + lane;
+          if (ch < p.Ntot) {
+            for (int n = n_first; n <= n_last; ++n) {
+              const int q_lo = max(m0, n * p.HW), q_hi = min(q_end, (n + 1) * p.HW);
+              float* dst = p.out + ((size_t)n * p.Cout_tot + ch) * p.HW + (q_lo - n * p.HW);
+              const uint32_t src = smem_u32(E + lane * 128 + (q_lo - m0));
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           ::"l"(reinterpret_cast<uint64_t>(dst)), "r"(src), "r"((uint32_t)(q_hi - q_lo) * 4u) : "memory");
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (prof) e_work += clock64() - e1;
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (prof && r == 0) { p.prof[16] = e_wait; p.prof[17] = e_work; p.prof[18] = ti; }
+  }
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- filter prepass: GEMM-K order (channel group, tap, channel-in-group), bf16 hi / lo, zero padded to 64 ---------
+// mode 0 (forward): row = o, K channel = c;  mode 1 (dgrad): row = c, K channel = o, taps flipped.
+struct PrepParams {
+  const float* w;            // [O][C][taps]
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;         // [rows][Kp]
+  int O, C, taps, rows, kch, Kp, mode;
+};
+__global__ void __launch_bounds__(256)
+filter_prep_bf16_kernel(const PrepParams q) {
+  const long long total = (long long)q.rows * q.Kp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(idx % q.Kp);
+    const int row = (int)(idx / q.Kp);
+    float v = 0.f;
+    const int hb = kp >> 5, c32 = kp & 31;
+    const int g = hb / q.taps;
+    int tap = hb - g * q.taps;
+    const int ch = g * 32 + c32;
+    if (ch < q.kch) {
+      if (q.mode) tap = q.taps - 1 - tap;
+      const int o = q.mode ? ch : row, c = q.mode ? row : ch;
+      v = __ldg(q.w + ((long long)o * q.C + c) * q.taps + tap);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    q.hi[idx] = h;
+    q.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+}  // namespace stg
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*StgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static StgEncodeTiledFn stg_encode_tiled() {
+  static StgEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StgEncodeTiledFn>(f);
+  }
+  return fn;
+}
+static int stg_make_filter_map(CUtensorMap* map, const void* base, int Kp, int rows, int n_tile) {
+  StgEncodeTiledFn enc = stg_encode_tiled();
+  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)Kp * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled (staged conv filter) failed (%d)", (int)r);
+  return B2C_OK;
+}
+
+static bool stg_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_CONV_STAGED"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+
+// geometry shared by the eligibility test, the workspace size and the launch
+struct StgGeom { int Cin, Cout, halo, lead, sp, nstg, taps, groups, nhb, nkb, Kp; };
+static bool stg_geom(const ConvShape& s, int op, StgGeom* g) {
+  if (!stg_enabled()) return false;
+  if (op != B2C_OP_FORWARD && op != B2C_OP_BACKWARD_DATA) return false;
+  if (s.G != 1 || s.sh != 1 || s.sw != 1 || s.dh != 1 || s.dw != 1) return false;
+  if (s.Ho != s.H || s.Wo != s.W || 2 * s.ph != s.kh - 1 || 2 * s.pw != s.kw - 1) return false;     // "same" convolution
+  const long long HW = (long long)s.H * s.W;
+  if (HW % 4 != 0 || (long long)s.N * HW > 0x7fffffffLL - 256) return false;
+  const int Cin = op == B2C_OP_FORWARD ? s.C : s.O, Cout = op == B2C_OP_FORWARD ? s.O : s.C;
+  if (Cin % stg::CB != 0) return false;
+  const int taps = s.kh * s.kw;
+  if (taps > stg::MAX_TAPS) return false;
+  const int halo = s.ph * s.W + s.pw;
+  const int lead = 4 + ((4 - halo % 4) % 4);
+  const int sp = (128 + 2 * halo + lead + 3 + 3) & ~3;
+  const long long stg_bytes = (long long)stg::CB * sp * 4;
+  if (2 * stg_bytes > (long long)stg::STG_POOL) return false;
+  int nstg = (int)(stg::STG_POOL / stg_bytes);
+  if (nstg > 4) nstg = 4;
+  if (g) {
+    g->Cin = Cin; g->Cout = Cout; g->halo = halo; g->lead = lead; g->sp = sp; g->nstg = nstg; g->taps = taps;
+    g->groups = Cin / stg::CB; g->nhb = g->groups * taps; g->nkb = (g->nhb + 1) / 2; g->Kp = g->nkb * stg::BKE;
+  }
+  return true;
+}
+bool tc_stg_supported(const ConvShape& s, int op) { return stg_geom(s, op, nullptr); }
+size_t tc_stg_workspace(const ConvShape& s, int op) {
+  StgGeom g;
+  if (!stg_geom(s, op, &g)) return 0;
+  return 2 * sizeof(__nv_bfloat16) * (size_t)g.Cout * g.Kp + 256;
+}
+
+template <int N_TILE>
+static int stg_launch_inst(const stg::Params& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+  using S = stg::Smem<N_TILE>;
+  B2C_CUDA_OK(cudaFuncSetAttribute(stg::igemm_stg_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  stg::igemm_stg_kernel<N_TILE><<<grid, stg::THREADS, S::TOTAL, st>>>(p, mh, ml);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+// a = x (forward) or dy (dgrad); b = w; out = y or dx
+int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  StgGeom g;
+  if (!stg_geom(s, op, &g)) return fail(B2C_ERR_INVALID, "staged tcgen05 conv: shape not eligible");
+  if (!ws || ws_bytes < tc_stg_workspace(s, op)) return fail(B2C_ERR_WORKSPACE, "staged tcgen05 conv: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(a) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u))
+    return fail(B2C_ERR_INVALID, "staged tcgen05 conv: activations must be 16-byte aligned");
+  __nv_bfloat16* wbase = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const size_t plane = (size_t)g.Cout * g.Kp;
+  stg::PrepParams q;
+  q.w = w; q.hi = wbase; q.lo = wbase + plane; q.O = s.O; q.C = s.C; q.taps = g.taps; q.rows = g.Cout; q.kch = g.Cin; q.Kp = g.Kp;
+  q.mode = op == B2C_OP_FORWARD ? 0 : 1;
+  stg::filter_prep_bf16_kernel<<<grid_for(plane, 256), 256, 0, st>>>(q);
+  B2C_POST_LAUNCH();
+
+  stg::Params p;
+  p.x = a; p.Ctot = g.Cin; p.Cg = g.Cin; p.H = s.H; p.W = s.W; p.HW = s.H * s.W;
+  p.kh = s.kh; p.kw = s.kw; p.ph = s.ph; p.pw = s.pw;
+  p.Mtot = s.N * p.HW; p.Ntot = g.Cout;
+  p.taps = g.taps; p.groups = g.groups; p.nhb = g.nhb; p.nkb = g.nkb;
+  p.halo = g.halo; p.lead = g.lead; p.sp = g.sp; p.nstg = g.nstg;
+  p.out = out; p.Cout_tot = g.Cout; p.bias = op == B2C_OP_FORWARD ? bias : nullptr;
+  const int n_tile = g.Cout > 64 ? 128 : g.Cout > 32 ? 64 : 32;
+  p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (g.Cout + n_tile - 1) / n_tile; p.total_tiles = p.m_tiles * p.n_tiles;
+  static long long* prof_buf = nullptr;
+  static int prof_on = -1;
+  if (prof_on < 0) { const char* e = getenv("B2C_PROF"); prof_on = e ? atoi(e) : 0; if (prof_on) cudaMalloc(&prof_buf, 32 * sizeof(long long)); }
+  p.prof = prof_on ? prof_buf : nullptr;
+  if (prof_on) cudaMemsetAsync(prof_buf, 0, 32 * sizeof(long long), st);
+  alignas(64) CUtensorMap mh, ml;
+  if (int rc = stg_make_filter_map(&mh, q.hi, g.Kp, g.Cout, n_tile)) return rc;
+  if (int rc = stg_make_filter_map(&ml, q.lo, g.Kp, g.Cout, n_tile)) return rc;
+  int rc;
+  switch (n_tile) {
+    case 128: rc = stg_launch_inst<128>(p, mh, ml, st); break;
+    case 64: rc = stg_launch_inst<64>(p, mh, ml, st); break;
+    default: rc = stg_launch_inst<32>(p, mh, ml, st); break;
+  }
+  if (rc == B2C_OK && prof_on) {
+    long long h[32];
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[stg-prof] N_TILE=%d nkb=%d groups=%d taps=%d tiles=%d nstg=%d | conv(t0): total=%lld wait_staged=%lld wait_empty=%lld kblocks=%lld | mma: total=%lld wait_full=%lld | epi: wait=%lld work=%lld tiles=%lld\n",
+            n_tile, g.nkb, g.groups, g.taps, p.total_tiles, g.nstg, h[0], h[1], h[2], h[3], h[8], h[9], h[16], h[17], h[18]);
+  }
+  return rc;
+}
+
+}  // namespace b2c

@@ -556,194 +556,6 @@ wgrad1x1_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_const
   }
 }
 
-// =====================================================================================================================
-// 3x3 / stride 1 / pad 1 layers -- NOT YET RUN ON A GPU, off unless B2C_WGRAD3_TMA=1 (written after round 1's GPU budget
-// was spent; design notes in notes/README.md).  The gather kernel above spends ~2 900 cycles per K block producing the
-// im2col rows of X against 1 536 cycles of MMA; here nothing is gathered by threads:
-//   * a K block is 32 consecutive output pixels of ONE image taken as a (bw x bh) patch with bw*bh = 32
-//     ((32,1) for wide maps, (16,2) for 14x14, (8,4) for 7x7) so that both operands are TMA boxes:
-//       dY  : 4-D map {Wo, Ho, O, N}, box {bw, bh, 128, 1} at (wo0, ho0, o0, n)            -> [128 o][32 q], SW128 K-major
-//       X   : 4-D map {W, H, C, N},  box {bw, bh, 32, 1} at (wo0+j-1, ho0+i-1, c0, n), 9x  -> nine [32 c][32 q] tiles;
-//     coordinates outside the tensor read as zero, which IS the zero padding of the convolution and of the K tail;
-//   * the nine X tiles stack into one [288 rows][32] B operand (row = tap*32 + c): two MMAs per K step and product term,
-//     N = 256 (taps 0-7) and N = 32 (tap 8), accumulators in TMEM columns [0, 288);
-//   * raw tiles are the TF32 hi operands, converter warps write the lo tiles (as in the 1x1 kernel);
-//   * partial tiles go to the workspace tap-major ([split][tap][O][C], coalesced), wgrad3_reduce_kernel adds them into
-//     dW[o][c][tap] in split order (deterministic).
-constexpr int W3_CW = 8;
-constexpr int W3_THREADS = (W3_CW + 2) * 32;
-constexpr int W3_CT = 32;                               // input channels per tile
-constexpr int W3_BROWS = 9 * W3_CT;                     // 288 stacked B rows
-
-struct Wgrad3Params {
-  int O, C, N;
-  int bw, bh;            // pixel patch of one K block (bw * bh == 32)
-  int cs, rg;            // patches per row / patch rows per image: ceil(Wo / bw), ceil(Ho / bh)
-  long long nkb_total;   // N * rg * cs
-  int kb_per_split, splits;
-  float* part;           // [splits][9][O][C]
-};
-
-struct Wgrad3Smem {
-  static constexpr uint32_t A_BYTES = 128u * 128u;
-  static constexpr uint32_t B_BYTES = (uint32_t)W3_BROWS * 128u;        // 36 KB
-  static constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;             // 52 KB
-  static constexpr uint32_t STAGE = 2u * RAW_BYTES;                    // + lo tiles
-  static constexpr int STAGES = 2;
-  static constexpr uint32_t BAR_OFF = STAGES * STAGE;
-  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;
-};
-
-__device__ __forceinline__ void wg_tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-__global__ void __launch_bounds__(W3_THREADS, 1)
-wgrad3x3_tma_kernel(const __grid_constant__ Wgrad3Params p, const __grid_constant__ CUtensorMap map_dy,
-                    const __grid_constant__ CUtensorMap map_x) {
-  using S = Wgrad3Smem;
-  constexpr int STAGES = S::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar_raw = sbase + S::BAR_OFF;
-  const uint32_t bar_full = bar_raw + 8 * STAGES;
-  const uint32_t bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_tmem = bar_empty + 8 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 8 * (3 * STAGES + 1));
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.x;
-  const int c0 = blockIdx.y * W3_CT;
-  const int m0 = blockIdx.z * 128;
-  const long long kb_begin = (long long)split * p.kb_per_split;
-  long long kb_end = kb_begin + p.kb_per_split;
-  if (kb_end > p.nkb_total) kb_end = p.nkb_total;
-  const int nkb = (int)(kb_end - kb_begin);
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_raw + 8 * s, 1); mbar_init(bar_full + 8 * s, W3_CW); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_tmem, 1);
-    fence_barrier_init();
-  }
-  if (warp == W3_CW + 1) tmem_alloc(smem_u32(tmem_slot), 512);          // 288 accumulator columns (power-of-two allocation)
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  auto stage_a = [&](int s) { return sbase + (uint32_t)s * S::STAGE; };
-  auto stage_b = [&](int s) { return sbase + (uint32_t)s * S::STAGE + S::A_BYTES; };
-
-  if (warp < W3_CW) {
-    constexpr int UNITS = (int)(S::RAW_BYTES / 16u);                     // 3328 = 13 * 256
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait_backoff(bar_raw + 8 * s, it & 1, 20);
-      const uint32_t src = stage_a(s);
-#pragma unroll 4
-      for (int u = tid; u < UNITS; u += W3_CW * 32) {
-        const float4 v = wg_lds128(src + (uint32_t)u * 16u);
-        float h, l0, l1, l2, l3;
-        split_tf32(v.x, h, l0); split_tf32(v.y, h, l1); split_tf32(v.z, h, l2); split_tf32(v.w, h, l3);
-        sts128(src + S::RAW_BYTES + (uint32_t)u * 16u, l0, l1, l2, l3);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-    }
-    if (warp < 4) {
-      // epilogue: accumulator columns [tap*32, tap*32+32) -> part[split][tap][o][c0 .. c0+31], rows coalesced
-      mbar_wait_backoff(bar_tmem, 0, 100);
-      tc_fence_after();
-      float* tpad = reinterpret_cast<float*>(sptr) + warp * (32 * 33);
-      const int rows_valid = p.O - (m0 + warp * 32);
-      const bool colok = c0 + lane < p.C;
-#pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * 32), v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tpad[lane * 33 + j] = v[j];
-        __syncwarp();
-        float* obase = p.part + (((long long)split * 9 + tap) * p.O + (m0 + warp * 32)) * p.C + c0;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r)
-          if (r < rows_valid && colok) obase[(long long)r * p.C + lane] = tpad[r * 33 + lane];
-        __syncwarp();
-      }
-      tc_fence_before();
-    }
-  } else if (warp == W3_CW) {
-    // TMA producer: K block index -> (image, patch row, patch column)
-    const int per_img = p.rg * p.cs;
-    int n = (int)(kb_begin / per_img);
-    int rem = (int)(kb_begin - (long long)n * per_img);
-    int r = rem / p.cs, cc = rem - r * p.cs;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 20);
-      if (elect_one()) {
-        const int wo0 = cc * p.bw, ho0 = r * p.bh;
-        wg_arrive_expect_tx(bar_raw + 8 * s, S::RAW_BYTES);
-        wg_tma_load_4d(stage_a(s), &map_dy, bar_raw + 8 * s, wo0, ho0, m0, n);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap)
-          wg_tma_load_4d(stage_b(s) + (uint32_t)tap * (W3_CT * 128u), &map_x, bar_raw + 8 * s, wo0 + tap % 3 - 1, ho0 + tap / 3 - 1, c0, n);
-      }
-      __syncwarp();
-      if (++cc == p.cs) { cc = 0; if (++r == p.rg) { r = 0; ++n; } }
-    }
-  } else {
-    constexpr uint32_t IDESC_A = idesc_tf32(128, 256), IDESC_B = idesc_tf32(128, 32);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(bar_full + 8 * s, it & 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t ah = wg_desc_sw128(stage_a(s) + kk * 32), al = wg_desc_sw128(stage_a(s) + S::RAW_BYTES + kk * 32);
-          const uint32_t bh0 = stage_b(s) + kk * 32, bl0 = stage_b(s) + S::RAW_BYTES + kk * 32;
-          const uint32_t acc = (kb | kk) != 0;
-          // taps 0-7: rows [0, 256) of the stacked B tile -> columns [0, 256)
-          umma_tf32(tmem_base, al, wg_desc_sw128(bh0), IDESC_A, acc);
-          umma_tf32(tmem_base, ah, wg_desc_sw128(bl0), IDESC_A, 1);
-          umma_tf32(tmem_base, ah, wg_desc_sw128(bh0), IDESC_A, 1);
-          // tap 8: rows [256, 288) -> columns [256, 288)
-          umma_tf32(tmem_base + 256, al, wg_desc_sw128(bh0 + 256u * 128u), IDESC_B, acc);
-          umma_tf32(tmem_base + 256, ah, wg_desc_sw128(bl0 + 256u * 128u), IDESC_B, 1);
-          umma_tf32(tmem_base + 256, ah, wg_desc_sw128(bh0 + 256u * 128u), IDESC_B, 1);
-        }
-        umma_commit(bar_empty + 8 * s);
-        if (kb == nkb - 1) umma_commit(bar_tmem);
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (warp == W3_CW + 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// dW[o][c][tap] += sum_s part[s][tap][o][c], s ascending (deterministic)
-__global__ void __launch_bounds__(256)
-wgrad3_reduce_kernel(const float* __restrict__ part, int splits, int O, int C, float* __restrict__ dw) {
-  const long long n = (long long)O * C * 9, oc = (long long)O * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % 9);
-    const long long rc = i / 9;                       // o * C + c
-    float acc = 0.0f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(part + ((long long)s * 9 + tap) * oc + rc);
-    dw[i] += acc;
-  }
-}
-
 struct WgradPlan { int n_tile, splits, kb_per_split; };
 
 static WgradPlan wgrad_plan(const ConvShape& s) {
@@ -776,19 +588,12 @@ static WgradPlan wgrad_tma_plan(const ConvShape& s, int* cpi_out);
 static bool wgrad_tma_shape_ok(const ConvShape& s);
 static bool wgrad_compact_shape_ok(const ConvShape& s);
 static ConvShape wgrad_compact_dense_shape(const ConvShape& s);
-struct Wgrad3Plan;
-static bool wgrad3_shape_ok(const ConvShape& s);
-static size_t wgrad3_workspace(const ConvShape& s);
 size_t tc_wgrad_workspace(const ConvShape& s) {
   const WgradPlan pl = wgrad_plan(s);
   size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
   if (wgrad_tma_shape_ok(s)) {                       // the TMA path of 1x1 layers plans its own split count
     const WgradPlan pt = wgrad_tma_plan(s, nullptr);
     const size_t nt = pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
-    if (nt > need) need = nt;
-  }
-  if (wgrad3_shape_ok(s)) {
-    const size_t nt = wgrad3_workspace(s);
     if (nt > need) need = nt;
   }
   if (wgrad_compact_shape_ok(s)) {                   // strided 1x1: compacted input + the TMA path's partials
@@ -898,86 +703,23 @@ static int launch_conv_tc_wgrad_tma(const ConvShape& s, const float* x, const fl
   return B2C_OK;
 }
 
-// ---- TMA path for 3x3 / stride 1 / pad 1 layers (B2C_WGRAD3_TMA=1; not yet run on a GPU) ------------------------------
-static bool wgrad3_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("B2C_WGRAD3_TMA"); on = e ? atoi(e) : 0; }
-  return on != 0;
-}
-static bool wgrad3_shape_ok(const ConvShape& s) {
-  return wgrad3_enabled() && s.kh == 3 && s.kw == 3 && s.sh == 1 && s.sw == 1 && s.ph == 1 && s.pw == 1 && s.dh == 1 && s.dw == 1 &&
-         s.G == 1 && s.C % W3_CT == 0 && s.W % 4 == 0 && s.Wo % 4 == 0;      // TMA: 16-byte row pitches
-}
-struct Wgrad3Plan { int bw, bh, cs, rg, splits, kb_per_split; long long nkb; };
-static Wgrad3Plan wgrad3_plan(const ConvShape& s) {
-  Wgrad3Plan pl;
-  if (s.Wo >= 24) { pl.bw = 32; pl.bh = 1; } else if (s.Wo >= 12) { pl.bw = 16; pl.bh = 2; } else { pl.bw = 8; pl.bh = 4; }
-  pl.cs = (s.Wo + pl.bw - 1) / pl.bw; pl.rg = (s.Ho + pl.bh - 1) / pl.bh;
-  pl.nkb = (long long)s.N * pl.cs * pl.rg;
-  const long long mn = (long long)((s.O + 127) / 128) * (s.C / W3_CT);
-  long long splits = sm_count() / mn;
-  const long long max_splits = pl.nkb / 8 > 0 ? pl.nkb / 8 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  const long long per = (pl.nkb + splits - 1) / splits;
-  pl.splits = (int)((pl.nkb + per - 1) / per);
-  pl.kb_per_split = (int)per;
-  return pl;
-}
-// [N][rows][H][W] fp32, box {bw, bh, box_rows, 1}, SWIZZLE_128B (bw * bh * 4 = 128 bytes per row), zero fill outside
-static int wg_make_map_4d(CUtensorMap* map, const float* base, int W, int H, int rows, int N, int bw, int bh, int box_rows) {
-  WgEncodeTiledFn enc = wg_encode_tiled();
-  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)rows, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 4 * (cuuint64_t)rows};
-  cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled (wgrad 3x3) failed (%d)", (int)r);
-  return B2C_OK;
-}
-static size_t wgrad3_workspace(const ConvShape& s) { return sizeof(float) * (size_t)wgrad3_plan(s).splits * 9 * s.O * s.C; }
-static int launch_conv_tc_wgrad3(const ConvShape& s, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const Wgrad3Plan pl = wgrad3_plan(s);
-  const size_t need = sizeof(float) * (size_t)pl.splits * 9 * s.O * s.C;
-  if (!ws || ws_bytes < need) return fail(B2C_ERR_WORKSPACE, "wgrad (3x3 tma): workspace too small");
-  Wgrad3Params p;
-  p.O = s.O; p.C = s.C; p.N = s.N; p.bw = pl.bw; p.bh = pl.bh; p.cs = pl.cs; p.rg = pl.rg; p.nkb_total = pl.nkb;
-  p.kb_per_split = pl.kb_per_split; p.splits = pl.splits; p.part = static_cast<float*>(ws);
-  alignas(64) CUtensorMap mdy, mx;
-  int rc = wg_make_map_4d(&mdy, dy, s.Wo, s.Ho, s.O, s.N, pl.bw, pl.bh, 128);
-  if (rc) return rc;
-  rc = wg_make_map_4d(&mx, x, s.W, s.H, s.C, s.N, pl.bw, pl.bh, W3_CT);
-  if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CUDA_OK(cudaFuncSetAttribute(wgrad3x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Wgrad3Smem::TOTAL));
-    attr_set = true;
-  }
-  dim3 grid(pl.splits, s.C / W3_CT, (s.O + 127) / 128);
-  wgrad3x3_tma_kernel<<<grid, W3_THREADS, Wgrad3Smem::TOTAL, st>>>(p, mdy, mx);
-  B2C_POST_LAUNCH();
-  wgrad3_reduce_kernel<<<grid_for((size_t)s.O * s.C * 9, 256), 256, 0, st>>>(p.part, pl.splits, s.O, s.C, dw);
-  B2C_POST_LAUNCH();
-  return B2C_OK;
-}
-
 // ---- strided 1x1 layers (pad 0, stride > 1): subsample, then the TMA path ------------------------------------------
-// Off unless B2C_WGRAD_COMPACT=1: parity-green on a B200 (tests/test_experimental_gpu.py) but not yet timed -- measure
-// with tools/layer_sweep.py before making it the default.  dW[o][c] = sum_q dY[o][q] * X[c][ho*sh][wo*sw]: the gather kernel reads X with 8-byte-strided
+// On by default for layers with more than 128 output channels (B2C_WGRAD_COMPACT=0 switches it off, =2 forces it for every
+// eligible layer).  Measured on ResNet-50's strided projections at N = 64 (profiles/r02_c1_sweep_compact.txt): C256->O512@56
+// 183 -> 136 us, C512->O1024@28 196 -> 124 us, C512->O256@28 89 -> 72 us, but C256->O128@56 89 -> 97 us (the extra pass over X
+// costs more than the gather it replaces when the GEMM is that small).  dW[o][c] = sum_q dY[o][q] * X[c][ho*sh][wo*sw]: the gather kernel reads X with 8-byte-strided
 // 4-byte loads (36 TFLOP/s on ResNet-50's six such layers, 0.92 ms per step against 0.17 ms of MMA).  Copying the
 // sampled pixels into a dense [N][C][Ho*Wo] buffer first is one HBM-bound pass over half of X's rows, after which the
 // layer is an ordinary 1x1 / stride 1 weight gradient for the TMA-fed kernel.
-static bool wgrad_compact_enabled() {
+static int wgrad_compact_mode() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("B2C_WGRAD_COMPACT"); on = e ? atoi(e) : 0; }
-  return on != 0;
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_COMPACT"); on = e ? atoi(e) : 1; }
+  return on;
 }
 static bool wgrad_compact_shape_ok(const ConvShape& s) {
   const long long P = (long long)s.Ho * s.Wo;
-  return wgrad_compact_enabled() && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) &&
+  const int mode = wgrad_compact_mode();
+  return mode != 0 && (mode == 2 || s.O > 128) && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) &&
          s.G == 1 && P % 4 == 0 && P >= 32;
 }
 static ConvShape wgrad_compact_dense_shape(const ConvShape& s) {
@@ -1023,8 +765,6 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
                          size_t ws_bytes, cudaStream_t st) {
   if (math == B2C_MATH_FP32 && wgrad_tma_shape_ok(s) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15u) == 0)
     return launch_conv_tc_wgrad_tma(s, x, dy, dw, ws, ws_bytes, st);
-  if (math == B2C_MATH_FP32 && wgrad3_shape_ok(s) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15u) == 0)
-    return launch_conv_tc_wgrad3(s, x, dy, dw, ws, ws_bytes, st);
   if (math == B2C_MATH_FP32 && wgrad_compact_shape_ok(s) && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0 && ws) {
     const ConvShape d = wgrad_compact_dense_shape(s);
     const WgradPlan pt = wgrad_tma_plan(d, nullptr);

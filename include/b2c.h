@@ -44,9 +44,12 @@ typedef enum { B2C_ENGINE_DEFAULT = 0, B2C_ENGINE_CAFFE = 1, B2C_ENGINE_CUDNN = 
 
 /* Math mode of the tensor-core kernels (NetParameter default_forward_math /
  * default_backward_math, caffe.proto:124-127, is the reference's analogous knob).
- * FP32  : 3xTF32 split-precision tcgen05 MMA, fp32-equivalent results (default).
- * TF32  : single-pass TF32 (round-to-nearest operands), ~1e-3 relative.          */
-typedef enum { B2C_MATH_FP32 = 0, B2C_MATH_TF32 = 1 } b2c_math;
+ * FP32        : split-precision tcgen05 MMA, fp32-equivalent results (default): bf16 hi/lo split, three
+ *               kind::f16 MMAs per K step, on the layers the bulk-copy-staged kernel takes (stride-1 "same"
+ *               convolutions, forward and dgrad); 3xTF32 split everywhere else.  Blob error ~1e-6..1e-5.
+ * TF32        : single-pass TF32 (round-to-nearest operands), ~1e-3 relative.
+ * FP32_3XTF32 : the 3xTF32 split on every layer (the round-1 default; ~1e-7..4e-5).          */
+typedef enum { B2C_MATH_FP32 = 0, B2C_MATH_TF32 = 1, B2C_MATH_FP32_3XTF32 = 2 } b2c_math;
 
 /* Kernel family used by the implicit-GEMM engine (diagnostics / tests). */
 typedef enum { B2C_ALGO_AUTO = 0, B2C_ALGO_SIMT = 1, B2C_ALGO_TCGEN05 = 2 } b2c_algo;

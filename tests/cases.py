@@ -53,14 +53,16 @@ MODEL_CASES = [
     ("resnet_res3_1x1_reduce", dict(N=2, Cin=512, H=28, W=28, O=128, k=1, s=1, p=0, d=1, G=1, bias=False)),
 ]
 
-# 3x3 / stride 1 / pad 1 with C % 32 == 0 and W % 4 == 0: the shapes the (still experimental, off by default) TMA 3x3
-# weight-gradient kernel takes.  Part of the suite only when that kernel is switched on (tests/test_experimental_gpu.py).
-EXPERIMENTAL_CASES = [
+# 3x3 / stride 1 / pad 1 with C % 32 == 0 and H*W % 4 == 0, ragged against the 128-pixel tile and the image borders:
+# the shapes the bulk-copy-staged forward / dgrad kernel (conv_tc_stg.cu) takes, next to the ResNet ones above
+MODEL_CASES += [
     ("resnet_res3_3x3", dict(N=2, Cin=128, H=28, W=28, O=128, k=3, s=1, p=1, d=1, G=1, bias=False)),
     ("ragged_3x3_rect", dict(N=3, Cin=32, H=12, W=20, O=40, k=3, s=1, p=1, d=1, G=1, bias=True)),
+    ("staged_5x5_c32", dict(N=5, Cin=32, H=10, W=6, O=48, k=5, s=1, p=2, d=1, G=1, bias=True)),          # 60-pixel images: 3 per tile
+    ("staged_1x1_tiny_maps", dict(N=37, Cin=96, H=4, W=4, O=160, k=1, s=1, p=0, d=1, G=1, bias=True)),   # 16-pixel images: 8 per tile
+    ("staged_3x3_c96_odd_halfblocks", dict(N=2, Cin=96, H=8, W=16, O=64, k=3, s=1, p=1, d=1, G=1, bias=False)),   # 27 half blocks: K padding
+    ("staged_rect_1x3", dict(N=2, Cin=64, H=6, W=8, O=32, k=(1, 3), s=1, p=(0, 1), d=1, G=1, bias=True)),
 ]
-if os.environ.get("B2C_WGRAD3_TMA") == "1":
-    MODEL_CASES = MODEL_CASES + EXPERIMENTAL_CASES
 
 ALL_CASES = REF_TEST_CASES + EDGE_CASES + MODEL_CASES
 

@@ -243,9 +243,12 @@ def test_full_size_vs_reference_loop(rng, name, case):
     d.backward_data(DY, Wt, DX)
     DW = dev(dw0)
     d.backward_filter(X, DY, DW)
-    for k, got, want in (("y", Y, want_y), ("dx", DX, want_dx), ("dw", DW, want_dw)):
+    # y / dx reduce over K_dim <= 4608 terms: 1e-4.  dW reduces over N*Ho*Wo = 1.3e4 .. 1.6e6 terms in fp32 on BOTH sides (the
+    # tensor core's fp32 accumulator here, OpenBLAS sgemm + image-by-image accumulation in the reference), so the two fp32
+    # results drift apart with sqrt(terms): measured 1.02e-4 at 1.9e5 terms (AlexNet conv2, N = 256); bar 3e-4, a third of 1e-3.
+    for k, got, want, tol in (("y", Y, want_y, TOL_FP32), ("dx", DX, want_dx, TOL_FP32), ("dw", DW, want_dw, 3e-4)):
         e = rel_err(host(got), want)
-        assert e < TOL_FP32, (name, k, e)
+        assert e < tol, (name, k, e)
     if po.has_bias:
         DB = torch.zeros(po.O, device="cuda")
         d.backward_bias(DY, DB)
