@@ -106,3 +106,46 @@ def test_resnet50_one_step_runs_and_learns(rng):
     assert t.loss() < first
     assert t.timed_steps(2, copy_input=True, read_loss=True) > 0
     assert np.isfinite(t.get_param(0)).all()
+
+
+def test_snapshot_restore_roundtrip_on_device(rng, tmp_path):
+    """Solver::Snapshot / Restore (solver.cpp:447-604, sgd_solver.cpp:261-353) on the device: step, snapshot, step  ==  fresh
+    solver, restore, step -- bitwise, including BatchNorm running statistics and momentum history; a SECOND snapshot of the
+    same process holds the current weights (the fused update writes the arena behind the Blob's host mirror); the
+    .solverstate history list has one blob per Net::learnable_params() entry (5 per BatchNorm layer)."""
+    spec = no.mini_resnet()
+    t, params, data, label = make_trainer(spec, rng)
+    t.step(2)
+    state = t.snapshot(str(tmp_path / "snap"))
+    assert state.endswith("_iter_2.solverstate")
+    t.step(2)
+    want = [t.get_param(i, 0).copy() for i in range(t.num_params())]
+    want_h = [t.get_param(i, 2).copy() for i in range(t.num_params())]
+    want_loss = t.loss()
+    state2 = t.snapshot(str(tmp_path / "snap"))                  # iter 4: must contain the iter-4 weights, not the iter-2 ones
+    # fresh solver with different weights, same batch
+    t2, _, _, _ = make_trainer(spec, np.random.default_rng(7))
+    t2.set_blob("data", data)
+    t2.set_blob("label", label)
+    t2.restore(state)
+    assert t2.iter() == 2
+    t2.step(2)
+    assert t2.loss() == want_loss
+    for i in range(t.num_params()):
+        assert np.array_equal(t2.get_param(i, 0).view(np.uint32), want[i].view(np.uint32)), i
+        assert np.array_equal(t2.get_param(i, 2).view(np.uint32), want_h[i].view(np.uint32)), i
+    t3, _, _, _ = make_trainer(spec, np.random.default_rng(8))
+    t3.restore(state2)
+    assert t3.iter() == 4
+    for i in range(t.num_params()):
+        assert np.array_equal(t3.get_param(i, 0).view(np.uint32), want[i].view(np.uint32)), ("second snapshot is stale", i)
+    # history length = every layer blob, like the reference's SolverState
+    from caffe_mpi_b200 import host_api as ha
+    L = ha.lib()
+    L.b2h_wire_load.restype = __import__("ctypes").c_void_p
+    h = L.b2h_wire_load(state.encode(), 1)
+    assert h
+    L.b2h_wire_num_history.argtypes = [__import__("ctypes").c_void_p]
+    assert L.b2h_wire_num_history(h) == t.num_learnable() > t.num_params()
+    L.b2h_wire_destroy.argtypes = [__import__("ctypes").c_void_p]
+    L.b2h_wire_destroy(h)
