@@ -9,24 +9,29 @@
 // Why a second kernel.  conv_tc.cu gathers the im2col rows with per-thread __ldg: ~1 400 cycles per 128x32 K block
 // against 768 cycles of MMA (profiles/README.md), and it re-reads every input pixel kh*kw times through L1/L2.  Here
 // no thread touches global memory for the activation operand:
-//   * GEMM rows are 128 CONSECUTIVE flattened pixels q = n*H*W + p.  For one input channel the pixels a tile needs --
-//     its own 128 plus a halo of pad*W + pad on either side, clipped to each image -- are one contiguous run of global
-//     memory per image, so the TMA unit brings them in with 1-D bulk copies (cp.async.bulk, one per channel and
-//     image segment, completion on an mbarrier): a "channel group" of 32 channels x (128 + 2*halo) floats per stage.
+//   * GEMM rows are 128 CONSECUTIVE flattened pixels q = n*H*W + p.  For 32 input channels the pixels a tile needs --
+//     its own 128 plus a halo of pad*W + pad on either side -- are ONE TMA box per image the tile touches (at most two):
+//     a 3-D tensor map {H*W, C, N} over the NCHW blob, box {BWT pixels, 32 channels, 1 image}, start column
+//     p0 - halo; columns outside the image read as zero.  (A first version used one 1-D bulk copy per channel: the TMA
+//     unit retires ~1 small bulk operation per 90 cycles, 3 000 cycles per 32-channel group -- 1x1 layers ran 2-3x
+//     SLOWER than the gather kernel, profiles/r02_c2_*.)
 //   * All kh*kw taps of those 32 channels are then served from that ONE staged copy: tap (i,j) of row r is the staged
-//     value at slot r + (i-pad)*W + (j-pad); rows whose tap falls outside the image (zero padding, image borders,
-//     row wrap) are masked with a per-row bit computed once per tile.  Global->smem traffic per tile is
+//     value at column r + halo + (i-pad)*W + (j-pad); rows whose tap falls outside the image (zero padding, image
+//     borders, row wrap) are masked with a per-row bit computed once per tile.  Global->smem traffic per tile is
 //     (128 + 2*halo)/128 of the input instead of kh*kw times it.
-//   * 16 converter warps read the staged fp32 values (lanes = consecutive pixels: conflict-free), split each into
+//   * 16 converter warps read the staged fp32 values (lanes = consecutive pixels: conflict-free; the row pitch BWT is a
+//     template parameter so the eight channel loads of a thread are one base register + immediates), split each into
 //     bf16 hi + bf16 lo (hi = rn(a), lo = rn(a - hi)), pack pairs along K and write the A operand straight into TENSOR
 //     MEMORY with tcgen05.st (lane = GEMM row), 64 K-elements per stage.
 //   * The filter is pre-split into bf16 hi / lo in GEMM-K order (channel group, tap, channel) by a prepass and streamed
 //     by TMA (SWIZZLE_128B, [N_TILE x 64] boxes); one converged warp issues tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32):
 //     lo*hi + hi*lo + hi*hi per K step -- three bf16 MMAs cost 1.5 TF32-MMA equivalents (3xTF32 costs 3), and the
 //     operand bytes in shared / tensor memory halve.  Dropped terms (lo*lo and the bf16 rounding of lo) are ~2^-17 per
-//     product: blob-level error ~1e-6..1e-5 against the double-accumulating oracle, 100x inside the 1e-3 bar.
-//   * Epilogue as in conv_tc.cu: double-buffered TMEM accumulators, tcgen05.ld, 32-channel chunks transposed through
-//     shared memory, 512-byte store instructions.
+//     product: measured 5e-6..1.3e-5 blob-level against the 3xTF32 kernel (profiles/r02_c2_diag.log), 100x inside 1e-3.
+//   * Epilogue: double-buffered TMEM accumulators, tcgen05.ld, (+ bias), 32-channel chunks transposed through shared
+//     memory [channel][128 pixels] and written by the TMA unit: one tensor store per chunk and image (box {128, 32, 1} of
+//     the output blob, clipped by the hardware at the image end, the channel count and -- through a negative start
+//     column -- the image start).
 // dgrad of a stride-1 same convolution is the same kernel on dY with the transposed + flipped filter.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -44,38 +49,37 @@ namespace stg {
 constexpr int NCW = 16;                       // converter warps
 constexpr int W_BTMA = NCW;                   // filter TMA warp
 constexpr int W_MMA = NCW + 1;                // MMA issuer (also owns the TMEM allocation)
-constexpr int W_STG = NCW + 2;                // activation bulk-copy warp
+constexpr int W_STG = NCW + 2;                // activation TMA warp
 constexpr int W_EPI0 = NCW + 3;               // first of 4 epilogue warps
 constexpr int THREADS = (NCW + 7) * 32;       // 736
 constexpr int CB = 32;                        // channels per staged group
 constexpr int BKE = 64;                       // bf16 K elements per pipeline stage (two (group, tap) half blocks)
 constexpr int STAGES = 3;                     // operand pipeline depth (B in smem, A in TMEM)
-constexpr uint32_t STG_POOL = 64u * 1024u;    // activation staging pool
+constexpr uint32_t STG_POOL = 96u * 1024u;    // activation staging pool, carved into slots of one TMA box each
+constexpr int MAX_SLOTS = 6;
 constexpr int MAX_TAPS = 32;                  // per-row validity mask is one 32-bit word
 
 struct Params {
-  const float* x;          // [Nimg, Ctot, H, W]; this launch reads channels [0, Cg) (G == 1)
-  int Ctot, Cg, H, W, HW;
+  int HW, H, W;
   int kh, kw, ph, pw;
   int Mtot;                // Nimg * H * W (output pixel grid == input pixel grid)
   int Ntot;                // GEMM columns (output channels)
-  int taps, groups;        // kh*kw, Cg / 32
+  int taps, groups;        // kh*kw, Cin / 32
   int nhb, nkb;            // half blocks = groups * taps, K blocks = ceil(nhb / 2)
-  int halo, lead;          // pad*W + pad;  slot of (row 0, offset -halo): lead = 4 + (-halo mod 4), multiple-of-4 aligned total
-  int sp;                  // floats per staged channel row (multiple of 4)
-  int nstg;                // staging buffers in the pool (2..4)
-  float* out;              // [Nimg, Cout_tot, H, W]
-  int Cout_tot;
+  int halo;                // pad*W + pad
   const float* bias;       // [Ntot] or null
   int m_tiles, n_tiles, total_tiles;
   long long* prof;
 };
 
-template <int N_TILE>
+template <int N_TILE, int BWT>
 struct Smem {
   static constexpr uint32_t B_BYTES = (uint32_t)N_TILE * 128u;              // [N_TILE rows][64 bf16], SW128
   static constexpr uint32_t STAGE = 2u * B_BYTES;                           // hi + lo
   static constexpr uint32_t STG_OFF = STAGES * STAGE;
+  static constexpr uint32_t SLOT_BYTES = (uint32_t)CB * (uint32_t)BWT * 4u;  // one box: [32 channels][BWT pixels] fp32
+  static constexpr int NSLOT_ = (int)(STG_POOL / SLOT_BYTES);
+  static constexpr int NSLOT = NSLOT_ > MAX_SLOTS ? MAX_SLOTS : NSLOT_;
   static constexpr uint32_t EPI_OFF = STG_OFF + STG_POOL;                   // 2 x [32 channels][128 pixels] fp32
   static constexpr uint32_t EPI_BYTES = 2u * 32u * 128u * 4u;
   static constexpr uint32_t BAR_OFF = EPI_OFF + EPI_BYTES;
@@ -85,6 +89,7 @@ struct Smem {
   static constexpr uint32_t A_COL0 = 2u * N_TILE;                           // after the two accumulators
   static constexpr uint32_t A_COLS = 64u;                                   // 32 packed hi columns + 32 packed lo columns
   static_assert(A_COL0 + STAGES * A_COLS <= 512u, "TMEM budget");
+  static_assert(NSLOT >= 2, "a tile that spans two images needs two boxes per channel group");
 };
 
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
@@ -114,17 +119,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// 1-D bulk copy global -> shared (16-byte aligned addresses and size), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+template <int OFF>
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
   return v;
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -134,17 +139,19 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 // (tensor-memory A operand of kind::f16: two consecutive K elements per 32-bit column, little endian)
 __device__ __forceinline__ void split_pack_bf16(float e, float o, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(e, o);            // .x = e (low half), .y = o
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(e - hf.x, o - hf.y);   // a - hi is exact in fp32
-  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+  const float he = __uint_as_float(hb << 16), ho = __uint_as_float(hb & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(e - he, o - ho);   // a - hi is exact in fp32
+  hi = hb;
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int N_TILE>
+template <int N_TILE, int BWT>
 __global__ void __launch_bounds__(THREADS, 1)
-igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap map_hi,
-                 const __grid_constant__ CUtensorMap map_lo) {
-  using S = Smem<N_TILE>;
+igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                 const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
+  using S = Smem<N_TILE, BWT>;
+  constexpr int NSLOT = S::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -152,24 +159,23 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
   const uint32_t bar_empty = bar_full + 8 * STAGES;             // STAGES: tcgen05.commit
   const uint32_t bar_tfull = bar_empty + 8 * STAGES;            // 2
   const uint32_t bar_tempty = bar_tfull + 16;                   // 2
-  const uint32_t bar_sfull = bar_tempty + 16;                   // 4: staged group landed (bulk-copy bytes)
-  const uint32_t bar_sempty = bar_sfull + 32;                   // 4: converters are done with the staged group
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 8 * (2 * STAGES + 4 + 8));
+  const uint32_t bar_sfull = bar_tempty + 16;                   // MAX_SLOTS: staged box landed
+  const uint32_t bar_sempty = bar_sfull + 8 * MAX_SLOTS;        // MAX_SLOTS: the converters are done with the box
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 8 * (2 * STAGES + 4 + 2 * MAX_SLOTS));
   int* tapoff = reinterpret_cast<int*>(sptr + S::TAP_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t stg_bytes = (uint32_t)CB * (uint32_t)p.sp * 4u;     // one staged group (multiple of 16)
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, NCW + 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
-    for (int b = 0; b < 4; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, NCW); }
+    for (int b = 0; b < MAX_SLOTS; ++b) { mbar_init(bar_sfull + 8 * b, 1); mbar_init(bar_sempty + 8 * b, NCW); }
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
   if (tid < p.taps) {
     const int i = tid / p.kw, j = tid - i * p.kw;
-    tapoff[tid] = (i - p.ph) * p.W + (j - p.pw);
+    tapoff[tid] = ((i - p.ph) * p.W + (j - p.pw)) * 4;          // byte offset inside a staged channel row
   }
   tc_fence_before();
   __syncthreads();
@@ -179,10 +185,17 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
   auto stage_b_hi = [&](int s) { return sbase + (uint32_t)s * S::STAGE; };
   auto stage_b_lo = [&](int s) { return sbase + (uint32_t)s * S::STAGE + S::B_BYTES; };
   auto stage_a_col = [&](int s) { return S::A_COL0 + (uint32_t)s * S::A_COLS; };
-  auto stg_addr = [&](int slot) { return sbase + S::STG_OFF + (uint32_t)slot * stg_bytes; };
+  auto slot_addr = [&](int slot) { return sbase + S::STG_OFF + (uint32_t)slot * S::SLOT_BYTES; };
   auto tile_coords = [&](int tile, int& m0, int& n0) {
     const int nt = tile % p.n_tiles;
     m0 = (tile / p.n_tiles) * 128; n0 = nt * N_TILE;
+  };
+  // images a tile touches: 1 or 2 (H*W >= 128); the second one starts at tile row `split`
+  auto tile_images = [&](int m0, int& n_first, int& nseg, int& split) {
+    const int q_last = min(m0 + 128, p.Mtot) - 1;
+    n_first = m0 / p.HW;
+    nseg = q_last / p.HW - n_first + 1;
+    split = (n_first + 1) * p.HW - m0;                        // >= 128 when nseg == 1
   };
   const bool prof = p.prof != nullptr && blockIdx.x == 0;
 
@@ -191,19 +204,21 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     const int rq = warp & 3, sub = warp >> 2;                 // TMEM lane quarter, channel octet [sub*8, sub*8+8) of every half block
     const int row = rq * 32 + lane;
     const uint32_t a_lane = (uint32_t)(rq * 32) << 16;
-    long long c_sfull = 0, c_empty = 0, c_t0 = 0;
+    long long c_t0 = 0;
     if (prof) c_t0 = clock64();
     int kbg = 0;                                               // K blocks processed by this CTA (stage ring position)
-    int gc_base = 0;                                           // staged groups consumed before this tile
+    int u_base = 0;                                            // staged boxes consumed before this tile
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int m0, n0;
+      int m0, n0, n_first, nseg, split;
       tile_coords(tile, m0, n0);
+      tile_images(m0, n_first, nseg, split);
       // per-row tap validity (zero padding / image borders / row wrap), once per tile
       uint32_t mask = 0;
+      const int seg_r = row >= split ? 1 : 0;                  // which of the tile's images this row belongs to
       {
         const int q = m0 + row;
         if (q < p.Mtot) {
-          const int n = q / p.HW, pp = q - n * p.HW;
+          const int pp = q - (n_first + seg_r) * p.HW;
           const int h = pp / p.W, w = pp - h * p.W;
           if (p.taps == 1) mask = 1u;
           else {
@@ -216,43 +231,50 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
           }
         }
       }
-      // slot of this row at tap offset 0, as a byte offset inside a staged channel row; + channel octet base
-      const uint32_t row_off = (uint32_t)(row + p.halo + p.lead) * 4u + (uint32_t)(sub * 8) * (uint32_t)p.sp * 4u;
-      int g = 0, tap = 0, released = 0;
+      // byte offset of this row at tap offset 0 inside its image's box (column 0 of a box = first row of the segment - halo),
+      // plus the channel octet of this warp
+      const uint32_t row_off = (uint32_t)(row - (seg_r ? split : 0) + p.halo) * 4u + (uint32_t)(sub * 8) * (uint32_t)(BWT * 4);
+      int g = 0, tap = 0;
+      uint32_t src_base = 0;
       for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (2 * kb + h < p.nhb) {
-            const int gc = gc_base + g;
-            const int slot = gc % p.nstg;
-            if (prof) { const long long t0 = clock64(); mbar_wait(bar_sfull + 8 * slot, (gc / p.nstg) & 1); c_sfull += clock64() - t0; }
-            else mbar_wait(bar_sfull + 8 * slot, (gc / p.nstg) & 1);
+            const int u0 = u_base + g * nseg;
+            if (tap == 0) {                                    // first tap of a channel group: its box(es) must have landed
+              mbar_wait(bar_sfull + 8 * (u0 % NSLOT), (u0 / NSLOT) & 1);
+              if (nseg == 2) mbar_wait(bar_sfull + 8 * ((u0 + 1) % NSLOT), ((u0 + 1) / NSLOT) & 1);
+              src_base = slot_addr((u0 + seg_r) % NSLOT) + row_off;
+            }
             const bool ok = (mask >> tap) & 1u;
-            const uint32_t src = stg_addr(slot) + row_off + (uint32_t)(tapoff[tap] * 4);
+            const uint32_t src = src_base + (uint32_t)tapoff[tap];
             float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = lds32(src + (uint32_t)e * (uint32_t)p.sp * 4u);
+            v[0] = lds32<0>(src); v[1] = lds32<BWT * 4>(src); v[2] = lds32<2 * BWT * 4>(src); v[3] = lds32<3 * BWT * 4>(src);
+            v[4] = lds32<4 * BWT * 4>(src); v[5] = lds32<5 * BWT * 4>(src); v[6] = lds32<6 * BWT * 4>(src); v[7] = lds32<7 * BWT * 4>(src);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a0 = ok ? v[2 * e] : 0.f, a1 = ok ? v[2 * e + 1] : 0.f;
-              split_pack_bf16(a0, a1, hi[h * 4 + e], lo[h * 4 + e]);
+              uint32_t hw, lw;
+              split_pack_bf16(v[2 * e], v[2 * e + 1], hw, lw);
+              hi[h * 4 + e] = ok ? hw : 0u;                    // masked taps contribute exact zeros (never NaN from stale smem)
+              lo[h * 4 + e] = ok ? lw : 0u;
             }
-            if (++tap == p.taps) { tap = 0; ++g; }
+            if (++tap == p.taps) {                             // group fully consumed by this warp: hand its box(es) back
+              tap = 0;
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(bar_sempty + 8 * (u0 % NSLOT));
+                if (nseg == 2) mbar_arrive(bar_sempty + 8 * ((u0 + 1) % NSLOT));
+              }
+              ++g;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) { hi[h * 4 + e] = 0u; lo[h * 4 + e] = 0u; }   // K padding: finite zeros
           }
         }
-        // staged groups fully consumed by this warp: hand them back to the bulk-copy warp
-        __syncwarp();
-        while (released < g) {
-          if (lane == 0) mbar_arrive(bar_sempty + 8 * ((gc_base + released) % p.nstg));
-          ++released;
-        }
         const int s = kbg % STAGES, it = kbg / STAGES;
-        if (prof) { const long long t0 = clock64(); mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 32); c_empty += clock64() - t0; }
-        else mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 32);
+        mbar_wait_backoff(bar_empty + 8 * s, (it & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t a0 = tmem_base + a_lane + stage_a_col(s) + (uint32_t)(sub * 4);
         tmem_st4(a0, hi[0], hi[1], hi[2], hi[3]);
@@ -264,9 +286,9 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
-      gc_base += p.groups;
+      u_base += p.groups * nseg;
     }
-    if (prof && tid == 0) { p.prof[0] = clock64() - c_t0; p.prof[1] = c_sfull; p.prof[2] = c_empty; p.prof[3] = kbg; }
+    if (prof && tid == 0) { p.prof[0] = clock64() - c_t0; p.prof[3] = kbg; }
   } else if (warp == W_BTMA) {
     // ================= filter TMA producer ====================================================================
     int kbg = 0;
@@ -285,39 +307,28 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
       }
     }
   } else if (warp == W_STG) {
-    // ================= activation bulk-copy producer: lane = channel of the group ===============================
-    int gc = 0;
-    int last_m0 = -1;
+    // ================= activation TMA producer: one box per channel group and image ==============================
+    int u = 0;
+    long long s_wait = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int m0, n0;
+      int m0, n0, n_first, nseg, split;
       tile_coords(tile, m0, n0);
-      (void)last_m0;
-      const int q_end = min(m0 + 128, p.Mtot);
-      const int n_first = m0 / p.HW, n_last = (q_end - 1) / p.HW;
-      for (int g = 0; g < p.groups; ++g, ++gc) {
-        const int slot = gc % p.nstg;
-        mbar_wait_backoff(bar_sempty + 8 * slot, ((gc / p.nstg) & 1) ^ 1, 32);
-        // bytes of this group: same segments for every channel
-        uint32_t seg_floats = 0;
-        for (int n = n_first; n <= n_last; ++n) {
-          const int q_lo = max(m0, n * p.HW), q_hi = min(q_end, (n + 1) * p.HW);
-          const int ps = max(0, q_lo - n * p.HW - p.halo) & ~3;
-          const int pe = min(p.HW, (q_hi - n * p.HW + p.halo + 3) & ~3);
-          seg_floats += (uint32_t)(pe - ps);
-        }
-        if (lane == 0) arrive_expect_tx(bar_sfull + 8 * slot, seg_floats * 4u * CB);
-        __syncwarp();
-        const uint32_t dst_row = stg_addr(slot) + (uint32_t)lane * (uint32_t)p.sp * 4u;
-        const float* src_ch = p.x + (size_t)(g * CB + lane) * p.HW;
-        for (int n = n_first; n <= n_last; ++n) {
-          const int q_lo = max(m0, n * p.HW), q_hi = min(q_end, (n + 1) * p.HW);
-          const int ps = max(0, q_lo - n * p.HW - p.halo) & ~3;
-          const int pe = min(p.HW, (q_hi - n * p.HW + p.halo + 3) & ~3);
-          const int slot0 = ps + n * p.HW - m0 + p.halo + p.lead;          // >= 1, multiple of 4
-          bulk_load_1d(dst_row + (uint32_t)slot0 * 4u, src_ch + (size_t)n * p.Ctot * p.HW + ps, (uint32_t)(pe - ps) * 4u, bar_sfull + 8 * slot);
+      tile_images(m0, n_first, nseg, split);
+      for (int g = 0; g < p.groups; ++g) {
+        for (int seg = 0; seg < nseg; ++seg, ++u) {
+          const int slot = u % NSLOT;
+          if (prof) { const long long t0 = clock64(); mbar_wait_backoff(bar_sempty + 8 * slot, ((u / NSLOT) & 1) ^ 1, 32); s_wait += clock64() - t0; }
+          else mbar_wait_backoff(bar_sempty + 8 * slot, ((u / NSLOT) & 1) ^ 1, 32);
+          if (elect_one()) {
+            arrive_expect_tx(bar_sfull + 8 * slot, S::SLOT_BYTES);
+            const int col0 = (seg ? 0 : m0 - n_first * p.HW) - p.halo;     // negative / past-the-end columns read as zero
+            tma_load_3d(slot_addr(slot), &map_x, bar_sfull + 8 * slot, col0, g * CB, n_first + seg);
+          }
+          __syncwarp();
         }
       }
     }
+    if (prof && lane == 0) { p.prof[4] = s_wait; p.prof[5] = u; }
   } else if (warp == W_MMA) {
     // ================= MMA issuer ==============================================================================
     constexpr uint32_t IDESC = idesc_bf16(128, N_TILE);
@@ -353,10 +364,9 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     if (prof && lane == 0) { p.prof[8] = clock64() - m_t0; p.prof[9] = m_full; p.prof[10] = kbg; }
   } else {
     // ================= epilogue warps ============================================================================
-    // tcgen05.ld -> (+ bias) -> 32-channel chunk transposed into shared memory [channel][128 pixels] -> the TMA unit
-    // writes it out: one 1-D bulk store per channel and image segment (512 contiguous bytes of an NCHW plane), issued by
-    // the 32 lanes of the first epilogue warp.  The warps' own st.global path cost ~3 100 cycles per 128x128 tile on the
-    // short-K 1x1 layers (profiles/r01_prof_1x1_fwd_store_ablation.txt) against 768 cycles of MMA.
+    // tcgen05.ld -> (+ bias) -> 32-channel chunk transposed into shared memory [channel][128 pixels] -> one TMA tensor
+    // store per image the tile touches.  (The warps' own st.global path cost ~3 100 cycles per 128x128 tile on the
+    // short-K 1x1 layers, profiles/r01_prof_1x1_fwd_store_ablation.txt; 32 one-channel bulk stores per chunk cost ~2 900.)
     const int lg = warp & 3;                  // TMEM lane quarter this warp may read (warp id % 4)
     const int r = lg * 32 + lane;
     const bool issuer = warp == W_EPI0;
@@ -364,11 +374,10 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     int epi_chunk = 0, ti = 0;
     long long e_wait = 0, e_work = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-      int m0, n0;
+      int m0, n0, n_first, nseg, split;
       tile_coords(tile, m0, n0);
+      tile_images(m0, n_first, nseg, split);
       const int buf = ti & 1, use = ti >> 1;
-      const int q_end = min(m0 + 128, p.Mtot);
-      const int n_first = m0 / p.HW, n_last = (q_end - 1) / p.HW;
       const float* brow = p.bias ? p.bias + n0 : nullptr;
       long long e0 = 0;
       if (prof) e0 = clock64();
@@ -391,31 +400,25 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < nb) v[j] += __ldg(brow + c0 + j);    // warp-uniform address: broadcast
         }
-        // the bulk stores issued two chunks ago from this staging buffer have finished reading it
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the store issued two chunks ago from this staging buffer has finished reading it (elect.sync on a converged
+        // warp always elects the same lane, which owns the bulk-async groups)
+        if (issuer && elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         float* E = epi + (epi_chunk & 1) * (32 * 128);
 #pragma unroll
         for (int j = 0; j < 32; ++j) E[j * 128 + r] = v[j];           // lanes = consecutive pixels: conflict-free
-        fence_proxy_async();                                           // generic-proxy writes -> visible to the bulk store
+        fence_proxy_async();                                           // generic-proxy writes -> visible to the TMA store
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer) {
-          const int ch = n0 + c0 + lane;
-          if (ch < p.Ntot) {
-            for (int n = n_first; n <= n_last; ++n) {
-              const int q_lo = max(m0, n * p.HW), q_hi = min(q_end, (n + 1) * p.HW);
-              float* dst = p.out + ((size_t)n * p.Cout_tot + ch) * p.HW + (q_lo - n * p.HW);
-              const uint32_t src = smem_u32(E + lane * 128 + (q_lo - m0));
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                           ::"l"(reinterpret_cast<uint64_t>(dst)), "r"(src), "r"((uint32_t)(q_hi - q_lo) * 4u) : "memory");
-            }
-          }
+        if (issuer && elect_one()) {
+          // box column 0 = tile row 0: a negative start column (second image) and columns past the image end are clipped
+          tma_store_3d(&map_y, smem_u32(E), m0 - n_first * p.HW, n0 + c0, n_first);
+          if (nseg == 2) tma_store_3d(&map_y, smem_u32(E), m0 - (n_first + 1) * p.HW, n0 + c0, n_first + 1);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       if (prof) e_work += clock64() - e1;
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (issuer && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (prof && r == 0) { p.prof[16] = e_wait; p.prof[17] = e_work; p.prof[18] = ti; }
   }
   __syncthreads();
@@ -485,6 +488,21 @@ static int stg_make_filter_map(CUtensorMap* map, const void* base, int Kp, int r
   return B2C_OK;
 }
 
+// [N][rows][HW] fp32, box {bw, 32, 1}, no swizzle, out-of-range elements read as zero / are not written
+static int stg_make_act_map(CUtensorMap* map, const float* base, int HW, int rows, int N, int bw) {
+  StgEncodeTiledFn enc = stg_encode_tiled();
+  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)rows, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)stg::CB, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled (staged conv activations) failed (%d)", (int)r);
+  return B2C_OK;
+}
+
 static bool stg_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("B2C_CONV_STAGED"); on = e ? atoi(e) : 1; }
@@ -492,27 +510,24 @@ static bool stg_enabled() {
 }
 
 // geometry shared by the eligibility test, the workspace size and the launch
-struct StgGeom { int Cin, Cout, halo, lead, sp, nstg, taps, groups, nhb, nkb, Kp; };
+struct StgGeom { int Cin, Cout, halo, bwt, taps, groups, nhb, nkb, Kp; };
 static bool stg_geom(const ConvShape& s, int op, StgGeom* g) {
   if (!stg_enabled()) return false;
   if (op != B2C_OP_FORWARD && op != B2C_OP_BACKWARD_DATA) return false;
   if (s.G != 1 || s.sh != 1 || s.sw != 1 || s.dh != 1 || s.dw != 1) return false;
   if (s.Ho != s.H || s.Wo != s.W || 2 * s.ph != s.kh - 1 || 2 * s.pw != s.kw - 1) return false;     // "same" convolution
   const long long HW = (long long)s.H * s.W;
-  if (HW % 4 != 0 || (long long)s.N * HW > 0x7fffffffLL - 256) return false;
+  if (HW % 4 != 0 || HW < 128 || (long long)s.N * HW > 0x7fffffffLL - 256) return false;   // 16-byte TMA pitches; <= 2 images per tile
   const int Cin = op == B2C_OP_FORWARD ? s.C : s.O, Cout = op == B2C_OP_FORWARD ? s.O : s.C;
-  if (Cin % stg::CB != 0) return false;
+  if (Cin % stg::CB != 0 || Cout < 32) return false;
   const int taps = s.kh * s.kw;
   if (taps > stg::MAX_TAPS) return false;
   const int halo = s.ph * s.W + s.pw;
-  const int lead = 4 + ((4 - halo % 4) % 4);
-  const int sp = (128 + 2 * halo + lead + 3 + 3) & ~3;
-  const long long stg_bytes = (long long)stg::CB * sp * 4;
-  if (2 * stg_bytes > (long long)stg::STG_POOL) return false;
-  int nstg = (int)(stg::STG_POOL / stg_bytes);
-  if (nstg > 4) nstg = 4;
+  const int need = 128 + 2 * halo;                   // staged pixels per channel
+  const int bwt = need <= 128 ? 128 : need <= 160 ? 160 : need <= 192 ? 192 : need <= 256 ? 256 : 0;   // TMA boxes are <= 256 wide
+  if (!bwt) return false;
   if (g) {
-    g->Cin = Cin; g->Cout = Cout; g->halo = halo; g->lead = lead; g->sp = sp; g->nstg = nstg; g->taps = taps;
+    g->Cin = Cin; g->Cout = Cout; g->halo = halo; g->bwt = bwt; g->taps = taps;
     g->groups = Cin / stg::CB; g->nhb = g->groups * taps; g->nkb = (g->nhb + 1) / 2; g->Kp = g->nkb * stg::BKE;
   }
   return true;
@@ -524,14 +539,25 @@ size_t tc_stg_workspace(const ConvShape& s, int op) {
   return 2 * sizeof(__nv_bfloat16) * (size_t)g.Cout * g.Kp + 256;
 }
 
-template <int N_TILE>
-static int stg_launch_inst(const stg::Params& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
-  using S = stg::Smem<N_TILE>;
-  B2C_CUDA_OK(cudaFuncSetAttribute(stg::igemm_stg_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+template <int N_TILE, int BWT>
+static int stg_launch_inst(const stg::Params& p, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const CUtensorMap& my,
+                           cudaStream_t st) {
+  using S = stg::Smem<N_TILE, BWT>;
+  B2C_CUDA_OK(cudaFuncSetAttribute(stg::igemm_stg_kernel<N_TILE, BWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  stg::igemm_stg_kernel<N_TILE><<<grid, stg::THREADS, S::TOTAL, st>>>(p, mh, ml);
+  stg::igemm_stg_kernel<N_TILE, BWT><<<grid, stg::THREADS, S::TOTAL, st>>>(p, mh, ml, mx, my);
   B2C_POST_LAUNCH();
   return B2C_OK;
+}
+template <int N_TILE>
+static int stg_launch_n(int bwt, const stg::Params& p, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx,
+                        const CUtensorMap& my, cudaStream_t st) {
+  switch (bwt) {
+    case 128: return stg_launch_inst<N_TILE, 128>(p, mh, ml, mx, my, st);
+    case 160: return stg_launch_inst<N_TILE, 160>(p, mh, ml, mx, my, st);
+    case 192: return stg_launch_inst<N_TILE, 192>(p, mh, ml, mx, my, st);
+    default: return stg_launch_inst<N_TILE, 256>(p, mh, ml, mx, my, st);
+  }
 }
 
 // a = x (forward) or dy (dgrad); b = w; out = y or dx
@@ -551,12 +577,12 @@ int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* 
   B2C_POST_LAUNCH();
 
   stg::Params p;
-  p.x = a; p.Ctot = g.Cin; p.Cg = g.Cin; p.H = s.H; p.W = s.W; p.HW = s.H * s.W;
+  p.H = s.H; p.W = s.W; p.HW = s.H * s.W;
   p.kh = s.kh; p.kw = s.kw; p.ph = s.ph; p.pw = s.pw;
   p.Mtot = s.N * p.HW; p.Ntot = g.Cout;
   p.taps = g.taps; p.groups = g.groups; p.nhb = g.nhb; p.nkb = g.nkb;
-  p.halo = g.halo; p.lead = g.lead; p.sp = g.sp; p.nstg = g.nstg;
-  p.out = out; p.Cout_tot = g.Cout; p.bias = op == B2C_OP_FORWARD ? bias : nullptr;
+  p.halo = g.halo;
+  p.bias = op == B2C_OP_FORWARD ? bias : nullptr;
   const int n_tile = g.Cout > 64 ? 128 : g.Cout > 32 ? 64 : 32;
   p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (g.Cout + n_tile - 1) / n_tile; p.total_tiles = p.m_tiles * p.n_tiles;
   static long long* prof_buf = nullptr;
@@ -564,20 +590,22 @@ int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* 
   if (prof_on < 0) { const char* e = getenv("B2C_PROF"); prof_on = e ? atoi(e) : 0; if (prof_on) cudaMalloc(&prof_buf, 32 * sizeof(long long)); }
   p.prof = prof_on ? prof_buf : nullptr;
   if (prof_on) cudaMemsetAsync(prof_buf, 0, 32 * sizeof(long long), st);
-  alignas(64) CUtensorMap mh, ml;
+  alignas(64) CUtensorMap mh, ml, mx, my;
   if (int rc = stg_make_filter_map(&mh, q.hi, g.Kp, g.Cout, n_tile)) return rc;
   if (int rc = stg_make_filter_map(&ml, q.lo, g.Kp, g.Cout, n_tile)) return rc;
+  if (int rc = stg_make_act_map(&mx, a, p.HW, g.Cin, s.N, g.bwt)) return rc;
+  if (int rc = stg_make_act_map(&my, out, p.HW, g.Cout, s.N, 128)) return rc;
   int rc;
   switch (n_tile) {
-    case 128: rc = stg_launch_inst<128>(p, mh, ml, st); break;
-    case 64: rc = stg_launch_inst<64>(p, mh, ml, st); break;
-    default: rc = stg_launch_inst<32>(p, mh, ml, st); break;
+    case 128: rc = stg_launch_n<128>(g.bwt, p, mh, ml, mx, my, st); break;
+    case 64: rc = stg_launch_n<64>(g.bwt, p, mh, ml, mx, my, st); break;
+    default: rc = stg_launch_n<32>(g.bwt, p, mh, ml, mx, my, st); break;
   }
   if (rc == B2C_OK && prof_on) {
     long long h[32];
     cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[stg-prof] N_TILE=%d nkb=%d groups=%d taps=%d tiles=%d nstg=%d | conv(t0): total=%lld wait_staged=%lld wait_empty=%lld kblocks=%lld | mma: total=%lld wait_full=%lld | epi: wait=%lld work=%lld tiles=%lld\n",
-            n_tile, g.nkb, g.groups, g.taps, p.total_tiles, g.nstg, h[0], h[1], h[2], h[3], h[8], h[9], h[16], h[17], h[18]);
+    fprintf(stderr, "[stg-prof] N_TILE=%d BWT=%d nkb=%d groups=%d taps=%d tiles=%d | conv(t0): total=%lld kblocks=%lld | act-tma: wait_empty=%lld boxes=%lld | mma: total=%lld wait_full=%lld | epi: wait=%lld work=%lld tiles=%lld\n",
+            n_tile, g.bwt, g.nkb, g.groups, g.taps, p.total_tiles, h[0], h[3], h[4], h[5], h[8], h[9], h[16], h[17], h[18]);
   }
   return rc;
 }

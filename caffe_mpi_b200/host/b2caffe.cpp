@@ -201,6 +201,27 @@ vector<string> LayerRegistry::LayerTypeList() {
   return v;
 }
 
+// ================================================================================================ profiler
+EventProfiler::~EventProfiler() { for (auto& r : recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+size_t EventProfiler::begin(int op, cudaStream_t st) {
+  Rec r{layer_, op, nullptr, nullptr};
+  CUDA_CHECK(cudaEventCreate(&r.a)); CUDA_CHECK(cudaEventCreate(&r.b));
+  CUDA_CHECK(cudaEventRecord(r.a, st));
+  recs_.push_back(r);
+  return recs_.size() - 1;
+}
+void EventProfiler::end(size_t h, cudaStream_t st) { CUDA_CHECK(cudaEventRecord(recs_[h].b, st)); }
+void EventProfiler::collect(std::map<std::pair<int, int>, float>* out) {
+  CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& r : recs_) {
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    (*out)[{r.layer, r.op}] += ms;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  recs_.clear();
+}
+
 // ================================================================================================ Convolution
 shared_ptr<LayerBase> GetConvolutionLayer(const LayerParameter& p) {
   // layer_factory.cpp:53-88: DEFAULT resolves to the implicit-GEMM ("CUDNN") engine unless the layer is
@@ -363,15 +384,20 @@ void ConvolutionLayer::Backward_gpu(const vector<Blob*>& top, const vector<bool>
     const float* dy = top[i]->gpu_diff();
     if (desc_) {
       if (bias_term_ && param_propagate_down_[1]) B2C_CHECK(b2c_conv_backward_bias(desc_, dy, blobs_[1]->mutable_gpu_diff(), st));
+      EventProfiler* prof = Caffe::profiler();
       if (param_propagate_down_[0]) {
         const size_t need = b2c_conv_workspace_bytes(desc_, B2C_OP_BACKWARD_FILTER);
         void* ws = need ? workspace(need) : nullptr;
+        const size_t h = prof ? prof->begin(EventProfiler::WGRAD, st) : 0;
         B2C_CHECK(b2c_conv_backward_filter(desc_, bottom[i]->gpu_data(), dy, blobs_[0]->mutable_gpu_diff(), ws, ws_bytes_, st));
+        if (prof) prof->end(h, st);
       }
       if (propagate_down[i]) {
         const size_t need = b2c_conv_workspace_bytes(desc_, B2C_OP_BACKWARD_DATA);
         void* ws = need ? workspace(need) : nullptr;
+        const size_t h = prof ? prof->begin(EventProfiler::DGRAD, st) : 0;
         B2C_CHECK(b2c_conv_backward_data(desc_, dy, w, bottom[i]->mutable_gpu_diff(), ws, ws_bytes_, st));
+        if (prof) prof->end(h, st);
       }
       continue;
     }

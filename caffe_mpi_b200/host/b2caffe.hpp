@@ -52,9 +52,29 @@ void B2cCheck(int rc, const char* file, int line);   // NCCL_CHECK / CUBLAS_CHEC
 inline size_t even(size_t n) { return n + (n & 1); }
 
 // Thread-local runtime state, the part of the `Caffe` singleton (common.hpp:334-353) this path needs.
+// Per-call CUDA-event timing of a training step (the `caffe time` benchmark of the reference, tools/caffe.cpp:289-379, times
+// layers the same way, with host timers).  TrainNet brackets every layer's Forward / Backward; ConvolutionLayer additionally
+// brackets its weight-gradient and data-gradient calls.  Off (null) outside TrainNet::ProfileSteps.
+class EventProfiler {
+ public:
+  enum Op { FWD = 0, BWD = 1, WGRAD = 2, DGRAD = 3 };
+  struct Rec { int layer, op; cudaEvent_t a, b; };
+  ~EventProfiler();
+  void set_layer(int l) { layer_ = l; }
+  size_t begin(int op, cudaStream_t st);        // returns the record handle for end()
+  void end(size_t h, cudaStream_t st);
+  // synchronises, then sums elapsed ms per (layer, op); clears the records
+  void collect(std::map<std::pair<int, int>, float>* out);
+ private:
+  int layer_ = -1;
+  vector<Rec> recs_;
+};
+
 class Caffe {
  public:
   static Caffe& Get();
+  static EventProfiler* profiler() { return Get().profiler_; }
+  static void set_profiler(EventProfiler* p) { Get().profiler_ = p; }
   static cudaStream_t thread_stream() { return Get().stream_; }
   static void set_thread_stream(cudaStream_t s) { Get().stream_ = s; }
   static int solver_count() { return Get().solver_count_; }
@@ -66,6 +86,7 @@ class Caffe {
 
  private:
   cudaStream_t stream_ = nullptr;
+  EventProfiler* profiler_ = nullptr;
   int solver_count_ = 1;
   bool root_solver_ = true;
   std::mt19937 rng_{1701};

@@ -349,6 +349,21 @@ int b2h_trainer_copy_from(void* hv, const char* model_path, int* copied) {
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({ *copied = h->net->CopyTrainedLayersFrom(model_path); });
 }
+int b2h_trainer_num_layers(void* hv) { return static_cast<TrainerHandle*>(hv)->net->num_layers(); }
+int b2h_trainer_layer(void* hv, int i, char* name, char* type, int len) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ snprintf(name, len, "%s", h->net->layer_name(i).c_str()); snprintf(type, len, "%s", h->net->layer_type(i).c_str()); });
+}
+// per (layer, op) mean ms per step over nsteps profiled steps; op: 0 forward, 1 backward (whole layer), 2 conv wgrad, 3 conv dgrad
+int b2h_trainer_profile(void* hv, int nsteps, int cap, int* layer, int* op, float* ms, int* count) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({
+    std::vector<int> l; std::vector<int> o; std::vector<float> m;
+    h->net->ProfileSteps(nsteps, &l, &o, &m);
+    *count = (int)l.size();
+    for (int i = 0; i < *count && i < cap; ++i) { layer[i] = l[i]; op[i] = o[i]; ms[i] = m[i]; }
+  });
+}
 int b2h_trainer_iter(void* hv) { return static_cast<TrainerHandle*>(hv)->net->solver().iter(); }
 
 // ---- .caffemodel / .solverstate wire format on host arrays (no device needed; tests/test_snapshot_cpu.py) ----------------

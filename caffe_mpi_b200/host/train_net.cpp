@@ -342,11 +342,20 @@ void TrainNet::Forward(bool copy_input) {
     Blob* d = nodes_[0].top[0];
     CUDA_CHECK(cudaMemcpyAsync(d->mutable_gpu_data(), data_->host_batch(), sizeof(float) * data_->batch_floats(), cudaMemcpyHostToDevice, S()));
   }
-  for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->Forward(nodes_[i].bottom, nodes_[i].top);
+  EventProfiler* prof = Caffe::profiler();
+  for (size_t i = 0; i < layers_.size(); ++i) {
+    size_t h = 0;
+    if (prof) { prof->set_layer((int)i); h = prof->begin(EventProfiler::FWD, S()); }
+    layers_[i]->Forward(nodes_[i].bottom, nodes_[i].top);
+    if (prof) prof->end(h, S());
+  }
 }
 void TrainNet::Backward(bool update) {
   for (int li = (int)layers_.size() - 1; li >= 0; --li) {
     Node& nd = nodes_[li];
+    EventProfiler* prof = Caffe::profiler();
+    size_t ph = 0;
+    if (prof && nd.need_backward) { prof->set_layer(li); ph = prof->begin(EventProfiler::BWD, S()); }
     if (nd.need_backward) {
       // redirect fan-out bottoms to their shadow blobs (data shared, private diff), run, then accumulate
       vector<Blob*> bvec = nd.bottom;
@@ -356,6 +365,7 @@ void TrainNet::Backward(bool update) {
       for (size_t i = 0; i < bvec.size(); ++i)
         if (nd.bottom_diff_tmp[i])
           B2C_CHECK(b2c_add(nd.bottom[i]->count(), nd.bottom[i]->gpu_diff(), nd.bottom_diff_tmp[i]->gpu_diff(), nd.bottom[i]->mutable_gpu_diff(), S()));
+      if (prof) prof->end(ph, S());
     }
     if (update && nd.num_params) sched_->on_param_ready(nd.first_param, S());     // net.cpp:738-746
   }
@@ -394,6 +404,16 @@ float TrainNet::TimedSteps(int n, bool copy_input, bool read_loss) {
   CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
   cudaEventDestroy(a); cudaEventDestroy(b);
   return ms;
+}
+void TrainNet::ProfileSteps(int n, vector<int>* layer, vector<int>* op, vector<float>* ms) {
+  EventProfiler prof;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  Caffe::set_profiler(&prof);
+  try { for (int i = 0; i < n; ++i) Step(false); } catch (...) { Caffe::set_profiler(nullptr); throw; }
+  Caffe::set_profiler(nullptr);
+  std::map<std::pair<int, int>, float> acc;
+  prof.collect(&acc);
+  for (auto& kv : acc) { layer->push_back(kv.first.first); op->push_back(kv.first.second); ms->push_back(kv.second / (float)n); }
 }
 // ---- snapshot / restore -------------------------------------------------------------------------------------------
 static BlobData to_blob_data(const vector<int>& shape, const float* host, size_t count) {

@@ -166,6 +166,12 @@ class TrainNet {
   // n Steps bracketed by CUDA events on the thread stream; returns milliseconds (end-of-iteration makes the compute
   // stream wait for the last update, so the closing event covers reduce + update too)
   float TimedSteps(int n, bool copy_input, bool read_loss);
+  // n Steps with CUDA events around every layer call (and around the conv weight- / data-gradient calls inside Backward);
+  // per (layer, EventProfiler::Op) mean milliseconds per step.  Events serialise nothing, but the numbers are per-call device
+  // times on the compute stream, not a decomposition of the overlapped step.
+  void ProfileSteps(int n, vector<int>* layer, vector<int>* op, vector<float>* ms);
+  const string& layer_name(int i) const { return layer_names_[i]; }
+  const string& layer_type(int i) const { return layer_types_[i]; }
   float last_loss();                               // device -> host read of the loss blob
   SGDSolver& solver() { return *solver_; }
   Blob* blob(const string& name);

@@ -361,6 +361,29 @@ class Trainer:
     def activation_floats(self):
         return lib().b2h_trainer_activation_floats(self._h)
 
+    def layers(self):
+        """[(name, type)] of the net's layers in execution order."""
+        L = lib()
+        L.b2h_trainer_num_layers.argtypes = [C.c_void_p]
+        L.b2h_trainer_layer.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        out = []
+        for i in range(L.b2h_trainer_num_layers(self._h)):
+            a, b = C.create_string_buffer(256), C.create_string_buffer(256)
+            _ck(L.b2h_trainer_layer(self._h, i, a, b, 256))
+            out.append((a.value.decode(), b.value.decode()))
+        return out
+
+    def profile(self, nsteps=2):
+        """Mean ms per step of every layer call: [(layer index, op, ms)], op in fwd / bwd / wgrad / dgrad (the last two are the
+        conv layers' weight- and data-gradient calls, nested inside their bwd)."""
+        L = lib()
+        L.b2h_trainer_profile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        cap = 8192
+        la, op, ms, n = (C.c_int * cap)(), (C.c_int * cap)(), (C.c_float * cap)(), C.c_int()
+        _ck(L.b2h_trainer_profile(self._h, nsteps, cap, la, op, ms, C.byref(n)))
+        names = ("fwd", "bwd", "wgrad", "dgrad")
+        return [(la[i], names[op[i]], float(ms[i])) for i in range(min(n.value, cap))]
+
     def snapshot(self, prefix):
         """Solver::Snapshot: writes <prefix>_iter_<N>.caffemodel and .solverstate; returns the .solverstate path."""
         L = lib()

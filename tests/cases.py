@@ -58,10 +58,11 @@ MODEL_CASES = [
 MODEL_CASES += [
     ("resnet_res3_3x3", dict(N=2, Cin=128, H=28, W=28, O=128, k=3, s=1, p=1, d=1, G=1, bias=False)),
     ("ragged_3x3_rect", dict(N=3, Cin=32, H=12, W=20, O=40, k=3, s=1, p=1, d=1, G=1, bias=True)),
-    ("staged_5x5_c32", dict(N=5, Cin=32, H=10, W=6, O=48, k=5, s=1, p=2, d=1, G=1, bias=True)),          # 60-pixel images: 3 per tile
-    ("staged_1x1_tiny_maps", dict(N=37, Cin=96, H=4, W=4, O=160, k=1, s=1, p=0, d=1, G=1, bias=True)),   # 16-pixel images: 8 per tile
+    ("staged_5x5_c32", dict(N=5, Cin=32, H=10, W=14, O=48, k=5, s=1, p=2, d=1, G=1, bias=True)),         # 140-pixel images: most tiles span two
+    ("staged_1x1_small_maps", dict(N=7, Cin=96, H=12, W=11, O=160, k=1, s=1, p=0, d=1, G=1, bias=True)), # 132-pixel images, ragged O
     ("staged_3x3_c96_odd_halfblocks", dict(N=2, Cin=96, H=8, W=16, O=64, k=3, s=1, p=1, d=1, G=1, bias=False)),   # 27 half blocks: K padding
-    ("staged_rect_1x3", dict(N=2, Cin=64, H=6, W=8, O=32, k=(1, 3), s=1, p=(0, 1), d=1, G=1, bias=True)),
+    ("staged_rect_1x3", dict(N=2, Cin=64, H=12, W=12, O=32, k=(1, 3), s=1, p=(0, 1), d=1, G=1, bias=True)),
+    ("gather_1x1_tiny_maps", dict(N=37, Cin=96, H=4, W=4, O=160, k=1, s=1, p=0, d=1, G=1, bias=True)),   # H*W < 128: stays on the gather kernel
 ]
 
 ALL_CASES = REF_TEST_CASES + EDGE_CASES + MODEL_CASES

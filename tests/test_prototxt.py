@@ -150,3 +150,25 @@ def test_generated_resnet50_has_the_reference_inventory():
         assert params == rnet.learnable_params()
         a, b = net.conv_layers(), rnet.conv_layers()
         assert [(n, bytes(p), pd) for n, p, pd in a] == [(n, bytes(p), pd) for n, p, pd in b]
+
+
+GENERATED = [("alexnet", "models/bvlc_alexnet/train_val.prototxt", {}), ("vgg16", "models/vgg16/train_val.prototxt", {}),
+             ("googlenet", "models/bvlc_googlenet/train_val.prototxt", {}),
+             ("lenet", "examples/mnist/lenet_train_test.prototxt", dict(default_channels=1, default_size=28))]
+
+
+@pytest.mark.parametrize("name,ref,kw", GENERATED, ids=[g[0] for g in GENERATED])
+def test_generated_prototxt_has_the_reference_inventory(name, ref, kw):
+    """caffe_mpi_b200/models.py generators (what bench.py and the GPU box use, where /root/reference does not exist) against
+    the reference's own model files: same TRAIN-phase layer list (name, type), conv shapes and learnable-parameter list."""
+    from caffe_mpi_b200 import host_api, models
+    path = os.path.join("/root/reference", ref)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    r = host_api.Net(path, batch_override=8, **kw)
+    g = host_api.Net(models.PROTOTXT[name](8), is_text=True, **kw)
+    fields = lambda p: tuple(getattr(p, f) for f, _ in p._fields_)
+    assert [(n, fields(p), pd) for n, p, pd in r.conv_layers()] == [(n, fields(p), pd) for n, p, pd in g.conv_layers()]
+    assert [x[1:] for x in r.learnable_params()] == [x[1:] for x in g.learnable_params()]
+    keep = lambda net: [(n, t) for n, t, _ in net.layers() if t not in ("Accuracy", "Data", "Input")]
+    assert keep(r) == keep(g)

@@ -11,7 +11,7 @@ from caffe_mpi_b200 import capi
 def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
-shapes = [(2, 32, 8, 8, 32, 1, 0), (2, 64, 8, 8, 64, 1, 0), (2, 32, 8, 8, 32, 3, 1), (3, 64, 14, 14, 128, 3, 1), (2, 64, 56, 56, 256, 1, 0),
+shapes = [(2, 32, 12, 12, 32, 1, 0), (3, 64, 12, 11, 72, 1, 0), (2, 32, 12, 12, 32, 3, 1), (3, 64, 14, 14, 128, 3, 1), (5, 32, 10, 14, 48, 5, 2), (2, 64, 56, 56, 256, 1, 0),
           (4, 128, 28, 28, 128, 3, 1), (64, 256, 14, 14, 256, 3, 1), (64, 64, 56, 56, 64, 3, 1)]
 torch.manual_seed(0)
 for (N, C, H, W, O, k, p) in shapes:
