@@ -8,7 +8,7 @@ _SO = os.path.join(_HERE, "libb2c.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "b2c.h")
 
 ENGINE_DEFAULT, ENGINE_CAFFE, ENGINE_CUDNN = 0, 1, 2
-MATH_FP32, MATH_TF32 = 0, 1
+MATH_FP32, MATH_TF32, MATH_FP32_3XTF32 = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 OP_FORWARD, OP_BACKWARD_DATA, OP_BACKWARD_FILTER = 0, 1, 2
 UNIQUE_ID_BYTES = 128

@@ -7,7 +7,9 @@
 //                            (conv_tc.cu) when the shape qualifies, else the SIMT direct kernels.
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 #include "b2c_common.cuh"
+#include "filter_prep.cuh"
 
 namespace b2c {
 
@@ -55,12 +57,14 @@ int launch_bias_grad(int, int, int, const float*, float*, cudaStream_t);
 bool tc_conv_supported(const ConvShape&, int op);
 size_t tc_conv_workspace(const ConvShape&, int op, int math);
 int launch_conv_tc(const ConvShape&, int op, int math, const float* a, const float* b, const float* bias, float* out,
-                   void* ws, size_t ws_bytes, cudaStream_t);
+                   void* ws, size_t ws_bytes, const void* prepared, cudaStream_t);
+void tc_conv_prep_entry(const ConvShape&, int op, int math, const float* w, void* dst, PrepEntry* q);
+bool tc_stg_prep_entry(const ConvShape&, int op, const float* w, void* dst, PrepEntry* q);
 // bulk-copy-staged bf16x3 kernel (conv_tc_stg.cu): forward / dgrad of stride-1 "same" convolutions
 bool tc_stg_supported(const ConvShape&, int op);
 size_t tc_stg_workspace(const ConvShape&, int op);
 int launch_conv_tc_stg(const ConvShape&, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
-                       size_t ws_bytes, cudaStream_t);
+                       size_t ws_bytes, const void* prepared, cudaStream_t);
 bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K);
 int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta,
                     float* C, int math, cudaStream_t);
@@ -79,6 +83,23 @@ static bool use_staged(const b2c_conv_desc* d, int op) {
 }
 // math mode handed to the gather kernels (conv_tc.cu / conv_tc_wgrad.cu), which know FP32 (= 3xTF32) and TF32
 static int gather_math(const b2c_conv_desc* d) { return d->math == B2C_MATH_TF32 ? B2C_MATH_TF32 : B2C_MATH_FP32; }
+
+// ---- prepared-filter cache: [forward layout | dgrad layout], each region 256-byte aligned -------------------------------
+static size_t cache_region_bytes(const b2c_conv_desc* d, int op) {
+  if (d->engine == B2C_ENGINE_CAFFE || d->algo == B2C_ALGO_SIMT) return 0;
+  size_t n = 0;
+  if (use_staged(d, op)) n = tc_stg_workspace(d->s, op);
+  else if (tc_conv_supported(d->s, op)) n = tc_conv_workspace(d->s, op, gather_math(d));
+  return (n + 255) & ~(size_t)255;
+}
+static const void* prepared_filter(const b2c_conv_desc* d, int op) {
+  if (!d->filter_cache) return nullptr;
+  const char* base = static_cast<const char*>(d->filter_cache);
+  return op == B2C_OP_FORWARD ? base : base + cache_region_bytes(d, B2C_OP_FORWARD);
+}
+// true when `op` would take the staged kernel (so the cache holds the bf16 layout) but this call falls back to the gather
+// kernel because of unaligned activation pointers: the cache is then of no use to it
+static bool staged_geometry_only(const b2c_conv_desc* d, int op) { return use_staged(d, op); }
 
 static int resolve_algo(const b2c_conv_desc* d, int op) {
   if (d->engine == B2C_ENGINE_CAFFE) return B2C_ALGO_SIMT;  // reported family of the explicit path's GEMM
@@ -130,6 +151,7 @@ extern "C" int b2c_conv_desc_create(const b2c_conv_params* p, int engine, b2c_co
   d->engine = engine;
   d->math = g_default_math;
   d->algo = g_default_algo;
+  d->filter_cache = nullptr;
   *out = d;
   return B2C_OK;
 }
@@ -199,9 +221,9 @@ extern "C" int b2c_conv_forward(const b2c_conv_desc* d, const float* x, const fl
     return B2C_OK;
   }
   if (use_staged(d, B2C_OP_FORWARD) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0)
-    return launch_conv_tc_stg(s, B2C_OP_FORWARD, x, w, bias, y, ws, ws_bytes, st);
+    return launch_conv_tc_stg(s, B2C_OP_FORWARD, x, w, bias, y, ws, ws_bytes, prepared_filter(d, B2C_OP_FORWARD), st);
   if (tc_conv_supported(s, B2C_OP_FORWARD) && d->algo != B2C_ALGO_SIMT)
-    return launch_conv_tc(s, B2C_OP_FORWARD, gather_math(d), x, w, bias, y, ws, ws_bytes, st);
+    return launch_conv_tc(s, B2C_OP_FORWARD, gather_math(d), x, w, bias, y, ws, ws_bytes, staged_geometry_only(d, B2C_OP_FORWARD) ? nullptr : prepared_filter(d, B2C_OP_FORWARD), st);
   return launch_conv_fwd_simt(s, x, w, bias, y, st);
 }
 
@@ -228,9 +250,9 @@ extern "C" int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, c
     return B2C_OK;
   }
   if (use_staged(d, B2C_OP_BACKWARD_DATA) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0)
-    return launch_conv_tc_stg(s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, st);
+    return launch_conv_tc_stg(s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, prepared_filter(d, B2C_OP_BACKWARD_DATA), st);
   if (tc_conv_supported(s, B2C_OP_BACKWARD_DATA) && d->algo != B2C_ALGO_SIMT)
-    return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, gather_math(d), dy, w, nullptr, dx, ws, ws_bytes, st);
+    return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, gather_math(d), dy, w, nullptr, dx, ws, ws_bytes, staged_geometry_only(d, B2C_OP_BACKWARD_DATA) ? nullptr : prepared_filter(d, B2C_OP_BACKWARD_DATA), st);
   return launch_conv_dgrad_simt(s, dy, w, dx, st);
 }
 
@@ -259,8 +281,71 @@ extern "C" int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, 
     return B2C_OK;
   }
   if (resolve_algo(d, B2C_OP_BACKWARD_FILTER) == B2C_ALGO_TCGEN05)
-    return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, gather_math(d), x, dy, nullptr, dw, ws, ws_bytes, st);
+    return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, gather_math(d), x, dy, nullptr, dw, ws, ws_bytes, nullptr, st);
   return launch_conv_wgrad_simt(s, x, dy, dw, st);
+}
+
+namespace b2c {
+int debug_mbar_fwd(unsigned int*, int, int);
+int debug_mbar_stg(unsigned int*, int, int);
+int debug_mbar_wgrad(unsigned int*, int, int);
+}
+// out: three consecutive blocks of 128 words (gather fwd/dgrad kernel, staged kernel, weight-gradient kernels)
+extern "C" int b2c_debug_mbar_timeouts(unsigned int* out, int cap_words) {
+  REQUIRE_DEVICE();
+  if (!out || cap_words < 384) return fail(B2C_ERR_INVALID, "b2c_debug_mbar_timeouts: need 384 words");
+  const int a = debug_mbar_fwd(out, 128, -1), b = debug_mbar_stg(out + 128, 128, -1), c = debug_mbar_wgrad(out + 256, 128, -1);
+  return (a < 0 || b < 0 || c < 0) ? -1 : a + b + c;
+}
+extern "C" int b2c_debug_mbar_set_trap(int on) {
+  REQUIRE_DEVICE();
+  debug_mbar_fwd(nullptr, 0, on != 0); debug_mbar_stg(nullptr, 0, on != 0); debug_mbar_wgrad(nullptr, 0, on != 0);
+  return B2C_OK;
+}
+
+extern "C" size_t b2c_conv_filter_cache_bytes(const b2c_conv_desc* d) {
+  if (!d) return 0;
+  return cache_region_bytes(d, B2C_OP_FORWARD) + cache_region_bytes(d, B2C_OP_BACKWARD_DATA);
+}
+extern "C" int b2c_conv_desc_bind_filter_cache(b2c_conv_desc* d, const void* cache) {
+  if (!d) return fail(B2C_ERR_INVALID, "bind_filter_cache: null descriptor");
+  if (cache && (reinterpret_cast<uintptr_t>(cache) & 255u)) return fail(B2C_ERR_INVALID, "bind_filter_cache: the cache must be 256-byte aligned");
+  d->filter_cache = cache;
+  return B2C_OK;
+}
+static int collect_prep_entries(const b2c_conv_desc* d, const float* w, void* cache, PrepEntry* out) {
+  int n = 0;
+  char* base = static_cast<char*>(cache);
+  for (int op = B2C_OP_FORWARD; op <= B2C_OP_BACKWARD_DATA; ++op) {
+    const size_t bytes = cache_region_bytes(d, op);
+    if (!bytes) continue;
+    void* dst = op == B2C_OP_FORWARD ? base : base + cache_region_bytes(d, B2C_OP_FORWARD);
+    if (use_staged(d, op)) tc_stg_prep_entry(d->s, op, w, dst, &out[n++]);
+    else tc_conv_prep_entry(d->s, op, gather_math(d), w, dst, &out[n++]);
+  }
+  return n;
+}
+extern "C" int b2c_conv_prepare_filters(int n, const b2c_conv_desc* const* descs, const float* const* ws, void* const* caches,
+                                        void* stream) {
+  if (n < 0 || (n && (!descs || !ws || !caches))) return fail(B2C_ERR_INVALID, "b2c_conv_prepare_filters: bad argument");
+  REQUIRE_DEVICE();
+  std::vector<PrepEntry> entries;
+  entries.reserve(2 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    if (!descs[i] || !ws[i]) return fail(B2C_ERR_INVALID, "b2c_conv_prepare_filters: null entry %d", i);
+    if (!b2c_conv_filter_cache_bytes(descs[i])) continue;
+    if (!caches[i] || (reinterpret_cast<uintptr_t>(caches[i]) & 255u)) return fail(B2C_ERR_INVALID, "b2c_conv_prepare_filters: cache %d null or not 256-byte aligned", i);
+    PrepEntry e[2];
+    const int m = collect_prep_entries(descs[i], ws[i], caches[i], e);
+    for (int k = 0; k < m; ++k) entries.push_back(e[k]);
+  }
+  if (entries.empty()) return B2C_OK;
+  return launch_filter_prep(entries.data(), (int)entries.size(), as_stream(stream));
+}
+extern "C" int b2c_conv_prepare_filter(const b2c_conv_desc* d, const float* w, void* cache, size_t cache_bytes, void* stream) {
+  if (!d || !w) return fail(B2C_ERR_INVALID, "b2c_conv_prepare_filter: null pointer");
+  if (cache_bytes < b2c_conv_filter_cache_bytes(d)) return fail(B2C_ERR_WORKSPACE, "b2c_conv_prepare_filter: cache too small");
+  return b2c_conv_prepare_filters(1, &d, &w, &cache, stream);
 }
 
 extern "C" int b2c_conv_backward_bias(const b2c_conv_desc* d, const float* dy, float* db, void* stream) {

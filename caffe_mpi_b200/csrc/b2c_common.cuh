@@ -58,4 +58,5 @@ struct b2c_conv_desc {
   int engine;
   int math;
   int algo;
+  const void* filter_cache;   // b2c_conv_desc_bind_filter_cache: prepared forward / dgrad filters, or null
 };

@@ -34,6 +34,7 @@
 #include <stdio.h>
 #include "b2c_common.cuh"
 #include "tc_common.cuh"
+#include "filter_prep.cuh"
 
 namespace b2c {
 using namespace tc;
@@ -447,45 +448,6 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   }
 }
 
-// ---- filter prepass: GEMM-K ordering, TF32 split, zero padding -------------------------------------------
-// out_hi/out_lo [G][rows][Kp].  mode 0 (forward): row = o, K = (c,i,j) natural or (i,j,c) tap-major.
-// mode 1 (dgrad): row = c, K = (o,i',j') natural or (i',j',o) tap-major, filter flipped when flip != 0.
-struct PrepParams {
-  const float* w;
-  float* hi;
-  float* lo;       // null in TF32 mode
-  int G, Og, Cg, kh, kw, rows, K, Kp, mode, tap_major, flip;
-};
-
-__global__ void __launch_bounds__(256)
-filter_prep_kernel(const PrepParams q) {
-  const long long total = (long long)q.G * q.rows * q.Kp;
-  const int taps = q.kh * q.kw;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int kp = (int)(idx % q.Kp);
-    const int row = (int)((idx / q.Kp) % q.rows);
-    const int g = (int)(idx / ((long long)q.Kp * q.rows));
-    float v = 0.0f;
-    if (kp < q.K) {
-      const int inner = q.mode == 0 ? q.Cg : q.Og;    // the channel-like axis of K
-      int ch, tap;
-      if (q.tap_major) { const int cb = kp / (4 * taps); const int r = kp - cb * 4 * taps; tap = r >> 2; ch = cb * 4 + (r & 3); }
-      else { ch = kp / taps; tap = kp - ch * taps; }
-      if (q.flip) tap = taps - 1 - tap;
-      const int o = q.mode == 0 ? row : ch, c = q.mode == 0 ? ch : row;
-      v = __ldg(q.w + (((long long)g * q.Og + o) * q.Cg + c) * taps + tap);
-    }
-    if (q.lo) {
-      float h, l;
-      split_tf32(v, h, l);
-      q.hi[idx] = h; q.lo[idx] = l;
-    } else {
-      q.hi[idx] = to_tf32(v);
-    }
-  }
-}
-
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -579,14 +541,30 @@ size_t tc_conv_workspace(const ConvShape& s, int op, int math) {
   return tc_wgrad_workspace(s);
 }
 
+// The filter operand of `op` in this kernel's GEMM layout, written into `dst` (tc_conv_workspace(s, op, math) bytes).
+void tc_conv_prep_entry(const ConvShape& s, int op, int math, const float* w, void* dst, PrepEntry* q) {
+  float* wbase = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dst) + 255) & ~(uintptr_t)255);
+  const int chan = op == B2C_OP_FORWARD ? s.Cg : s.Og;
+  q->w = w; q->kind = 0; q->G = s.G; q->Og = s.Og; q->Cg = s.Cg; q->taps = s.kh * s.kw;
+  q->mode = op == B2C_OP_FORWARD ? 0 : 1;
+  q->rows = op == B2C_OP_FORWARD ? s.Og : s.Cg;
+  q->K = chan * s.kh * s.kw; q->Kp = padded_k(q->K);
+  q->tap_major = (chan % 4 == 0) ? 1 : 0;
+  q->flip = (op == B2C_OP_BACKWARD_DATA && dgrad_as_fwd(s)) ? 1 : 0;
+  q->kch = chan;
+  q->total = (long long)s.G * q->rows * q->Kp;
+  q->hi = wbase;
+  q->lo = math == B2C_MATH_FP32 ? static_cast<void*>(wbase + q->total) : nullptr;
+}
+
+// `prepared`: the filter already in GEMM layout (b2c_conv_prepare_filter) or null = run the prepass here into `ws`
 int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const float* b, const float* bias, float* out,
-                   void* ws, size_t ws_bytes, cudaStream_t st) {
+                   void* ws, size_t ws_bytes, const void* prepared, cudaStream_t st) {
   if (op == B2C_OP_BACKWARD_FILTER) return launch_conv_tc_wgrad(s, math, a, b, out, ws, ws_bytes, st);
-  if (ws_bytes < tc_conv_workspace(s, op, math) || !ws) return fail(B2C_ERR_WORKSPACE, "tcgen05 conv: workspace too small");
+  if (!prepared && (ws_bytes < tc_conv_workspace(s, op, math) || !ws)) return fail(B2C_ERR_WORKSPACE, "tcgen05 conv: workspace too small");
   FwdParams p;
-  PrepParams q;
-  q.w = b; q.G = s.G; q.Og = s.Og; q.Cg = s.Cg; q.kh = s.kh; q.kw = s.kw;
-  float* wbase = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  PrepEntry q;
+  tc_conv_prep_entry(s, op, math, b, prepared ? const_cast<void*>(prepared) : ws, &q);
   if (op == B2C_OP_FORWARD) {
     p.x = a; p.Cin_tot = s.C; p.H = s.H; p.W = s.W; p.Cg = s.Cg;
     p.kh = s.kh; p.kw = s.kw; p.sh = s.sh; p.sw = s.sw; p.ph = s.ph; p.pw = s.pw; p.dh = s.dh; p.dw = s.dw;
@@ -594,13 +572,11 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
     p.Ntot = s.Og; p.K = s.Kd;
     p.out = out; p.Cout_tot = s.O; p.out_plane = (long long)s.Ho * s.Wo; p.out_hs = s.Wo; p.out_ws = 1;
     p.bias = bias;
-    q.mode = 0; q.rows = s.Og; q.flip = 0;
   } else {
     // a = dy [N,O,Ho,Wo], b = w, out = dx [N,C,H,W]
     p.x = a; p.Cin_tot = s.O; p.Cg = s.Og;
     p.Ntot = s.Cg; p.K = s.Og * s.kh * s.kw;
     p.out = out; p.Cout_tot = s.C; p.out_plane = (long long)s.H * s.W; p.bias = nullptr;
-    q.mode = 1; q.rows = s.Cg;
     if (dgrad_as_fwd(s)) {
       // stride-1 conv of dY with the flipped filter, pad' = (k-1)*d - p, rows = bottom pixels
       p.H = s.Ho; p.W = s.Wo;
@@ -608,7 +584,6 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
       p.ph = (s.kh - 1) * s.dh - s.ph; p.pw = (s.kw - 1) * s.dw - s.pw;
       p.Ho = s.H; p.Wo = s.W; p.Mtot = s.N * s.H * s.W;
       p.out_hs = s.W; p.out_ws = 1;
-      q.flip = 1;
     } else {
       // 1x1, stride > 1, pad 0: rows = top pixels, scatter to bottom[ho*sh][wo*sw]; the rest of dx is 0
       B2C_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)s.N * s.C * s.H * s.W, st));
@@ -616,7 +591,6 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
       p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1; p.dh = 1; p.dw = 1; p.ph = 0; p.pw = 0;
       p.Ho = s.Ho; p.Wo = s.Wo; p.Mtot = s.N * s.Ho * s.Wo;
       p.out_hs = s.sh * s.W; p.out_ws = s.sw;
-      q.flip = 0;
     }
   }
   p.Kp = padded_k(p.K);
@@ -626,12 +600,8 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
   p.prof = prof_on ? prof_buf : nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2C_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   const int kmode = (p.Cg % 4 == 0) ? 1 : 0;
-  q.tap_major = kmode; q.K = p.K; q.Kp = p.Kp;
-  const size_t plane = (size_t)s.G * q.rows * p.Kp;
-  q.hi = wbase;
-  q.lo = math == B2C_MATH_FP32 ? wbase + plane : nullptr;
-  filter_prep_kernel<<<grid_for(plane, 256), 256, 0, st>>>(q);
-  B2C_POST_LAUNCH();
+  if (!prepared)
+    if (int rc = launch_filter_prep(&q, 1, st)) return rc;
 
   int n_tile = pick_n_tile(p.Mtot, p.Ntot, s.G, p.Kp, math);
   { static int force = -1; if (force < 0) { const char* e = getenv("B2C_NTILE"); force = e ? atoi(e) : 0; }
@@ -639,8 +609,8 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
   p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (p.Ntot + n_tile - 1) / n_tile; p.G = s.G;
   p.total_tiles = p.m_tiles * p.n_tiles * p.G;
   alignas(64) CUtensorMap mh, ml;
-  if (int rc = make_filter_map(&mh, q.hi, p.Kp, q.rows, s.G, n_tile)) return rc;
-  if (int rc = make_filter_map(&ml, q.lo ? q.lo : q.hi, p.Kp, q.rows, s.G, n_tile)) return rc;
+  if (int rc = make_filter_map(&mh, static_cast<const float*>(q.hi), p.Kp, q.rows, s.G, n_tile)) return rc;
+  if (int rc = make_filter_map(&ml, static_cast<const float*>(q.lo ? q.lo : q.hi), p.Kp, q.rows, s.G, n_tile)) return rc;
   if (prof_on) {
     cudaMemsetAsync(prof_buf, 0, 32 * sizeof(long long), st);
     int rc = n_tile == 128 ? launch_fwd_n<128>(p, mh, ml, math, kmode, st) : n_tile == 64 ? launch_fwd_n<64>(p, mh, ml, math, kmode, st) : launch_fwd_n<32>(p, mh, ml, math, kmode, st);
@@ -662,5 +632,7 @@ bool tc_gemm_supported(bool, bool, int, int, int) { return false; }
 int launch_sgemm_tc(bool, bool, int, int, int, float, const float*, const float*, float, float*, int, cudaStream_t) {
   return fail(B2C_ERR_INVALID, "tcgen05 GEMM not built");
 }
+
+TC_DEBUG_EXPORT(debug_mbar_fwd)
 
 }  // namespace b2c

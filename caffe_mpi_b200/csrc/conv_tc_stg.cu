@@ -39,7 +39,9 @@
 #include <stdlib.h>
 #include <stdio.h>
 #include "b2c_common.cuh"
+#define B2C_MBAR_DEBUG 1     // this kernel records stuck mbarrier waits (tc_common.cuh)
 #include "tc_common.cuh"
+#include "filter_prep.cuh"
 
 namespace b2c {
 using namespace tc;
@@ -68,7 +70,9 @@ struct Params {
   int nhb, nkb;            // half blocks = groups * taps, K blocks = ceil(nhb / 2)
   int halo;                // pad*W + pad
   const float* bias;       // [Ntot] or null
+  float* out;              // [Nimg, Ntot, H, W]: the epilogue's st.global path (tiles that span two images)
   int m_tiles, n_tiles, total_tiles;
+  int dbg;                 // B2C_STG_DBG bit 0: never use TMA stores (st.global epilogue for every tile)
   long long* prof;
 };
 
@@ -231,9 +235,12 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
           }
         }
       }
-      // byte offset of this row at tap offset 0 inside its image's box (column 0 of a box = first row of the segment - halo),
-      // plus the channel octet of this warp
-      const uint32_t row_off = (uint32_t)(row - (seg_r ? split : 0) + p.halo) * 4u + (uint32_t)(sub * 8) * (uint32_t)(BWT * 4);
+      // byte offset of this row at tap offset 0 inside its image's box, plus the channel octet of this warp.  Box column 0
+      // is pixel max(first pixel of the segment - halo, 0) of the image: start columns are never negative (the TMA unit
+      // zero-fills past the image END; taps that reach before pixel 0 are masked rows, whatever they read is discarded)
+      const int pp_r = m0 + row - (n_first + seg_r) * p.HW;                       // this row's pixel inside its image
+      const int start_r = seg_r ? 0 : max(m0 - n_first * p.HW - p.halo, 0);
+      const uint32_t row_off = (uint32_t)((pp_r - start_r) * 4) + (uint32_t)(sub * 8) * (uint32_t)(BWT * 4);
       int g = 0, tap = 0;
       uint32_t src_base = 0;
       for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
@@ -321,7 +328,7 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
           else mbar_wait_backoff(bar_sempty + 8 * slot, ((u / NSLOT) & 1) ^ 1, 32);
           if (elect_one()) {
             arrive_expect_tx(bar_sfull + 8 * slot, S::SLOT_BYTES);
-            const int col0 = (seg ? 0 : m0 - n_first * p.HW) - p.halo;     // negative / past-the-end columns read as zero
+            const int col0 = seg ? 0 : max(m0 - n_first * p.HW - p.halo, 0);   // columns past the image end read as zero
             tma_load_3d(slot_addr(slot), &map_x, bar_sfull + 8 * slot, col0, g * CB, n_first + seg);
           }
           __syncwarp();
@@ -409,12 +416,25 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
         for (int j = 0; j < 32; ++j) E[j * 128 + r] = v[j];           // lanes = consecutive pixels: conflict-free
         fence_proxy_async();                                           // generic-proxy writes -> visible to the TMA store
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (issuer && elect_one()) {
-          // box column 0 = tile row 0: a negative start column (second image) and columns past the image end are clipped
-          tma_store_3d(&map_y, smem_u32(E), m0 - n_first * p.HW, n0 + c0, n_first);
-          if (nseg == 2) tma_store_3d(&map_y, smem_u32(E), m0 - (n_first + 1) * p.HW, n0 + c0, n_first + 1);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (nseg == 1 && !(p.dbg & 1)) {
+          // the tile lies inside one image: box column 0 = tile row 0 = pixel m0 - n*HW >= 0; columns past the image end
+          // (last tile of an image, rows past the batch) and channels past Ntot are clipped by the TMA unit
+          if (issuer && elect_one()) tma_store_3d(&map_y, smem_u32(E), m0 - n_first * p.HW, n0 + c0, n_first);
+        } else {
+          // the tile spans two images (1 in 24 tiles at 56x56, 2 in 3 at 14x14): 16-byte st.global from the staged chunk
+          const int mv = m0 + lane * 4;                    // this lane's 4 pixels (H*W % 4 == 0: never across an image end)
+          if (mv < p.Mtot) {
+            const int nv = mv / p.HW, pv = mv - nv * p.HW;
+            float* vbase = p.out + ((size_t)nv * p.Ntot + n0 + c0) * p.HW + pv;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int ch = lg * 8 + q;
+              if (n0 + c0 + ch < p.Ntot)
+                *reinterpret_cast<float4*>(vbase + (size_t)ch * p.HW) = *reinterpret_cast<const float4*>(E + ch * 128 + lane * 4);
+            }
+          }
         }
+        if (issuer && elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // one (possibly empty) group per chunk
       }
       if (prof) e_work += clock64() - e1;
     }
@@ -425,36 +445,6 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ---- filter prepass: GEMM-K order (channel group, tap, channel-in-group), bf16 hi / lo, zero padded to 64 ---------
-// mode 0 (forward): row = o, K channel = c;  mode 1 (dgrad): row = c, K channel = o, taps flipped.
-struct PrepParams {
-  const float* w;            // [O][C][taps]
-  __nv_bfloat16* hi;
-  __nv_bfloat16* lo;         // [rows][Kp]
-  int O, C, taps, rows, kch, Kp, mode;
-};
-__global__ void __launch_bounds__(256)
-filter_prep_bf16_kernel(const PrepParams q) {
-  const long long total = (long long)q.rows * q.Kp;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int kp = (int)(idx % q.Kp);
-    const int row = (int)(idx / q.Kp);
-    float v = 0.f;
-    const int hb = kp >> 5, c32 = kp & 31;
-    const int g = hb / q.taps;
-    int tap = hb - g * q.taps;
-    const int ch = g * 32 + c32;
-    if (ch < q.kch) {
-      if (q.mode) tap = q.taps - 1 - tap;
-      const int o = q.mode ? ch : row, c = q.mode ? row : ch;
-      v = __ldg(q.w + ((long long)o * q.C + c) * q.taps + tap);
-    }
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    q.hi[idx] = h;
-    q.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
@@ -560,21 +550,30 @@ static int stg_launch_n(int bwt, const stg::Params& p, const CUtensorMap& mh, co
   }
 }
 
-// a = x (forward) or dy (dgrad); b = w; out = y or dx
+// The filter operand of `op` in this kernel's GEMM layout, written into `dst` (tc_stg_workspace(s, op) bytes).
+bool tc_stg_prep_entry(const ConvShape& s, int op, const float* w, void* dst, PrepEntry* q) {
+  StgGeom g;
+  if (!stg_geom(s, op, &g)) return false;
+  __nv_bfloat16* wbase = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(dst) + 255) & ~(uintptr_t)255);
+  q->w = w; q->kind = 1; q->G = 1; q->Og = s.O; q->Cg = s.C; q->taps = g.taps; q->rows = g.Cout; q->K = g.Cin * g.taps; q->Kp = g.Kp;
+  q->mode = op == B2C_OP_FORWARD ? 0 : 1; q->tap_major = 0; q->flip = q->mode; q->kch = g.Cin;
+  q->total = (long long)g.Cout * g.Kp;
+  q->hi = wbase; q->lo = wbase + q->total;
+  return true;
+}
+
+// a = x (forward) or dy (dgrad); b = w; out = y or dx; `prepared`: filter already in GEMM layout, or null = prepass here
 int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
-                       size_t ws_bytes, cudaStream_t st) {
+                       size_t ws_bytes, const void* prepared, cudaStream_t st) {
   StgGeom g;
   if (!stg_geom(s, op, &g)) return fail(B2C_ERR_INVALID, "staged tcgen05 conv: shape not eligible");
-  if (!ws || ws_bytes < tc_stg_workspace(s, op)) return fail(B2C_ERR_WORKSPACE, "staged tcgen05 conv: workspace too small");
+  if (!prepared && (!ws || ws_bytes < tc_stg_workspace(s, op))) return fail(B2C_ERR_WORKSPACE, "staged tcgen05 conv: workspace too small");
   if ((reinterpret_cast<uintptr_t>(a) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u))
     return fail(B2C_ERR_INVALID, "staged tcgen05 conv: activations must be 16-byte aligned");
-  __nv_bfloat16* wbase = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const size_t plane = (size_t)g.Cout * g.Kp;
-  stg::PrepParams q;
-  q.w = w; q.hi = wbase; q.lo = wbase + plane; q.O = s.O; q.C = s.C; q.taps = g.taps; q.rows = g.Cout; q.kch = g.Cin; q.Kp = g.Kp;
-  q.mode = op == B2C_OP_FORWARD ? 0 : 1;
-  stg::filter_prep_bf16_kernel<<<grid_for(plane, 256), 256, 0, st>>>(q);
-  B2C_POST_LAUNCH();
+  PrepEntry q;
+  tc_stg_prep_entry(s, op, w, prepared ? const_cast<void*>(prepared) : ws, &q);
+  if (!prepared)
+    if (int rc = launch_filter_prep(&q, 1, st)) return rc;
 
   stg::Params p;
   p.H = s.H; p.W = s.W; p.HW = s.H * s.W;
@@ -583,6 +582,8 @@ int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* 
   p.taps = g.taps; p.groups = g.groups; p.nhb = g.nhb; p.nkb = g.nkb;
   p.halo = g.halo;
   p.bias = op == B2C_OP_FORWARD ? bias : nullptr;
+  p.out = out;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2C_STG_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   const int n_tile = g.Cout > 64 ? 128 : g.Cout > 32 ? 64 : 32;
   p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (g.Cout + n_tile - 1) / n_tile; p.total_tiles = p.m_tiles * p.n_tiles;
   static long long* prof_buf = nullptr;
@@ -609,5 +610,7 @@ int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* 
   }
   return rc;
 }
+
+TC_DEBUG_EXPORT(debug_mbar_stg)
 
 }  // namespace b2c

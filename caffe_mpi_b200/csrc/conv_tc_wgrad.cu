@@ -818,4 +818,6 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
   return B2C_OK;
 }
 
+TC_DEBUG_EXPORT(debug_mbar_wgrad)
+
 }  // namespace b2c

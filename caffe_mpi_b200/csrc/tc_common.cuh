@@ -43,14 +43,50 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
 }
+// Timeout handling (cold path).  Default: kill the kernel with `trap` (the host sees "illegal instruction").
+// A translation unit that defines B2C_MBAR_DEBUG before including this header records the stuck waits instead:
+// g_mbar_dbg[0] = number of timeouts, then up to 31 records of {block, thread, barrier smem address, parity}; with
+// B2C_MBAR_TRAP=0 (b2c_debug_mbar_set_trap) the wait then gives up, so a deadlocked kernel drains and
+// b2c_debug_mbar_timeouts() can say which role was stuck on which barrier.  (Off by default: the out-of-line call costs the
+// register-tight gather kernels a few spilled registers.)
+#ifdef B2C_MBAR_DEBUG
+static __device__ unsigned int g_mbar_dbg[128];
+static __device__ unsigned int g_mbar_trap = 1;
+__device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+  const unsigned int slot = atomicAdd(&g_mbar_dbg[0], 1u);
+  if (slot < 31u) {
+    unsigned int* r = &g_mbar_dbg[4 + 4 * slot];
+    r[0] = blockIdx.x | (blockIdx.y << 16); r[1] = threadIdx.x; r[2] = bar; r[3] = parity;
+  }
+  __threadfence_system();
+  if (g_mbar_trap) asm volatile("trap;");
+}
+#define TC_DEBUG_EXPORT(name)                                                                                   \
+  int name(unsigned int* out, int cap_words, int set_trap) {                                                    \
+    if (set_trap >= 0) { const unsigned int v = set_trap ? 1u : 0u; cudaMemcpyToSymbol(::b2c::tc::g_mbar_trap, &v, sizeof(v)); } \
+    if (!out) return 0;                                                                                          \
+    unsigned int h[128];                                                                                         \
+    if (cudaMemcpyFromSymbol(h, ::b2c::tc::g_mbar_dbg, sizeof(h)) != cudaSuccess) return -1;                    \
+    for (int i = 0; i < cap_words && i < 128; ++i) out[i] = h[i];                                                \
+    unsigned int z[128] = {0};                                                                                   \
+    cudaMemcpyToSymbol(::b2c::tc::g_mbar_dbg, z, sizeof(z));                                                     \
+    return (int)h[0];                                                                                            \
+  }
+#else
 __device__ __forceinline__ void mbar_timeout_trap(uint32_t, uint32_t) { asm volatile("trap;"); }
+#define TC_DEBUG_EXPORT(name)                                                          \
+  int name(unsigned int* out, int cap_words, int) {                                    \
+    for (int i = 0; out && i < cap_words && i < 128; ++i) out[i] = 0;                  \
+    return 0;                                                                          \
+  }
+#endif
 constexpr long long MBAR_TIMEOUT_CYCLES = 1ll << 31;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > MBAR_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > MBAR_TIMEOUT_CYCLES) { mbar_timeout_trap(bar, parity); return; }
   }
 }
 // Waiters that are not on the critical path (epilogue warps waiting a whole tile for the accumulator,
@@ -63,7 +99,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
   for (;;) {
     __nanosleep(ns);
     if (mbar_try(bar, parity)) break;
-    if ((++spins & 0xffu) == 0 && clock64() - t0 > MBAR_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
+    if ((++spins & 0xffu) == 0 && clock64() - t0 > MBAR_TIMEOUT_CYCLES) { mbar_timeout_trap(bar, parity); return; }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

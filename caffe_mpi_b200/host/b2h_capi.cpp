@@ -349,6 +349,7 @@ int b2h_trainer_copy_from(void* hv, const char* model_path, int* copied) {
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({ *copied = h->net->CopyTrainedLayersFrom(model_path); });
 }
+long long b2h_trainer_arena_floats(void* hv) { return (long long)static_cast<TrainerHandle*>(hv)->net->solver().arena().total(); }
 int b2h_trainer_num_layers(void* hv) { return static_cast<TrainerHandle*>(hv)->net->num_layers(); }
 int b2h_trainer_layer(void* hv, int i, char* name, char* type, int len) {
   auto* h = static_cast<TrainerHandle*>(hv);

@@ -361,6 +361,13 @@ class Trainer:
     def activation_floats(self):
         return lib().b2h_trainer_activation_floats(self._h)
 
+    def arena_floats(self):
+        """Elements of the contiguous parameter arena (= the buffer the gradient allreduce covers)."""
+        L = lib()
+        L.b2h_trainer_arena_floats.argtypes = [C.c_void_p]
+        L.b2h_trainer_arena_floats.restype = C.c_longlong
+        return L.b2h_trainer_arena_floats(self._h)
+
     def layers(self):
         """[(name, type)] of the net's layers in execution order."""
         L = lib()

@@ -95,6 +95,22 @@ size_t b2c_conv_workspace_bytes(const b2c_conv_desc* d, int op);
 /* which kernel family the op will run (b2c_algo) -- lets tests assert "tcgen05 ran". */
 int b2c_conv_algo_used(const b2c_conv_desc* d, int op);
 
+/* Prepared filters.  The tcgen05 forward / dgrad kernels read the filter through TMA in a GEMM-ordered, hi/lo-split copy
+ * that b2c_conv_forward / b2c_conv_backward_data otherwise rebuild on every call.  Weights change once per iteration
+ * (SGDSolver::ApplyUpdate, sgd_solver.cpp:143-149), so a caller that owns the iteration can build the copies ONCE:
+ *   bytes = b2c_conv_filter_cache_bytes(d);            cudaMalloc(&cache, bytes)  (256-byte aligned; 0 = nothing to cache)
+ *   b2c_conv_desc_bind_filter_cache(d, cache);          forward / backward_data now trust the cache
+ *   b2c_conv_prepare_filters(n, descs, ws, caches, s)   after every weight update: ONE multi-tensor launch per 24 layouts
+ * Binding NULL restores the self-contained behaviour.  The cache is the caller's promise that it was prepared from the `w`
+ * passed to forward / backward_data; nothing checks it.  (cuDNN's analogue: cudnnTransformFilter + a persistent
+ * filter descriptor; the reference re-reads the blob each call, cudnn_conv_layer.cu:25-29.) */
+size_t b2c_conv_filter_cache_bytes(const b2c_conv_desc* d);
+int b2c_conv_desc_bind_filter_cache(b2c_conv_desc* d, const void* cache);
+int b2c_conv_prepare_filter(const b2c_conv_desc* d, const float* w, void* cache, size_t cache_bytes, void* stream);
+int b2c_conv_prepare_filters(int n, const b2c_conv_desc* const* descs, const float* const* ws, void* const* caches,
+                             void* stream);
+
+
 /* Y = conv(X, W) (+ bias).  y OVERWRITTEN.
  * Replaces ConvolutionLayer::Forward_gpu (conv_layer.cu:7-23) = forward_gpu_gemm +
  * forward_gpu_bias (base_conv_layer.hpp:105-128) and CuDNNConvolutionLayer::Forward_gpu
@@ -211,6 +227,13 @@ int b2c_sgd_update_arena(int nseg, const size_t* offset, const size_t* count,
  * bootstrap (src/caffe/clusters.cpp:8-16; parallel.cpp:42-45,163-172).  One communicator per
  * process (one process per GPU).  The 128-byte id is produced on rank 0 and carried to the
  * other ranks by the caller (MPI_Bcast in the reference; any byte transport here).           */
+/* Debugging aid for the mbarrier-synchronised kernels: every wait is bounded (~1 s); a timeout records
+ * {block, thread, barrier, parity} and kills the kernel with a trap.  b2c_debug_mbar_set_trap(0) makes timeouts non-fatal so
+ * that a deadlocked kernel drains; b2c_debug_mbar_timeouts fills three 128-word blocks (gather fwd/dgrad kernel, staged
+ * kernel, weight-gradient kernels), each {count, -, -, -, records...}, clears them and returns the total count (cap_words >= 384). */
+int b2c_debug_mbar_timeouts(unsigned int* out, int cap_words);
+int b2c_debug_mbar_set_trap(int on);
+
 #define B2C_UNIQUE_ID_BYTES 128
 int b2c_comm_get_unique_id(void* id_out /* B2C_UNIQUE_ID_BYTES */);
 int b2c_comm_init(int nranks, int rank, const void* id, b2c_comm** out);
