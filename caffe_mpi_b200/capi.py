@@ -206,6 +206,33 @@ class ConvDesc:
         check(lib().b2c_conv_backward_bias(self._h, _p(dy), _p(db), _stream(stream)))
         return db
 
+    # ---- prepared filters (include/b2c.h): build the GEMM-ordered filter copies once per weight change ----
+    def filter_cache_bytes(self):
+        L = lib()
+        L.b2c_conv_filter_cache_bytes.restype = C.c_size_t
+        L.b2c_conv_filter_cache_bytes.argtypes = [C.c_void_p]
+        return int(L.b2c_conv_filter_cache_bytes(self._h))
+
+    def prepare_filter(self, w, stream=None):
+        """Allocates (once) and fills the cache from `w`, binds it: forward / backward_data then skip their own prepass."""
+        import torch
+        need = self.filter_cache_bytes()
+        if need == 0:
+            return False
+        if getattr(self, "_fcache", None) is None or self._fcache.numel() < need:
+            self._fcache = torch.empty(need, dtype=torch.uint8, device=w.device)
+        L = lib()
+        L.b2c_conv_prepare_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(L.b2c_conv_prepare_filter(self._h, _p(w), C.c_void_p(self._fcache.data_ptr()), need, _stream(stream)))
+        L.b2c_conv_desc_bind_filter_cache.argtypes = [C.c_void_p, C.c_void_p]
+        check(L.b2c_conv_desc_bind_filter_cache(self._h, C.c_void_p(self._fcache.data_ptr())))
+        return True
+
+    def unbind_filter_cache(self):
+        L = lib()
+        L.b2c_conv_desc_bind_filter_cache.argtypes = [C.c_void_p, C.c_void_p]
+        check(L.b2c_conv_desc_bind_filter_cache(self._h, None))
+
 
 def im2col(im, col, k, s, p, d, stream=None):
     Cc, H, W = im.shape

@@ -234,6 +234,20 @@ REGISTER_LAYER_CREATOR(Convolution, GetConvolutionLayer);
 ConvolutionLayer::~ConvolutionLayer() {
   if (desc_) b2c_conv_desc_destroy(desc_);
   if (ws_) cudaFree(ws_);
+  if (fcache_) cudaFree(fcache_);
+}
+bool ConvolutionLayer::EnableFilterCache() {
+  fcache_on_ = true;
+  if (!desc_) return false;
+  const size_t need = b2c_conv_filter_cache_bytes(desc_);
+  if (!need) { B2C_CHECK(b2c_conv_desc_bind_filter_cache(desc_, nullptr)); return false; }
+  if (need > fcache_bytes_) {
+    if (fcache_) CUDA_CHECK(cudaFree(fcache_));
+    CUDA_CHECK(cudaMalloc(&fcache_, need));          // cudaMalloc: 256-byte aligned
+    fcache_bytes_ = need;
+  }
+  B2C_CHECK(b2c_conv_desc_bind_filter_cache(desc_, fcache_));
+  return true;
 }
 
 static void per_axis(const char* what, const vector<int>& rep, int h, int w, int naxes, int dflt, bool need, vector<int>* out) {
@@ -320,6 +334,7 @@ void ConvolutionLayer::Reshape(const vector<Blob*>& bottom, const vector<Blob*>&
       B2C_CHECK(b2c_conv_desc_create(&p, layer_param_.convolution_param.engine, &desc_));
       B2C_CHECK(b2c_conv_desc_set_math(desc_, layer_param_.convolution_param.math));
       desc_params_ = p;
+      if (fcache_on_) EnableFilterCache();           // new descriptor (shape change): re-bind; the owner re-prepares
     }
   }
 }

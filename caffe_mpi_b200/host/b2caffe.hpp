@@ -234,6 +234,12 @@ class ConvolutionLayer : public LayerBase {
   bool EqualNumBottomTopBlobs() const override { return true; }
   bool bias_term() const override { return bias_term_; }
   int algo_used(int op) const;
+  // Prepared-filter cache (include/b2c.h "Prepared filters"): an owner of the iteration (TrainNet) enables it and then calls
+  // b2c_conv_prepare_filters for all layers after every weight change; without it every Forward / Backward call re-derives
+  // the GEMM-ordered filter copy itself.  Returns false when the layer has nothing to cache (CAFFE engine, SIMT, N-D).
+  bool EnableFilterCache();
+  const b2c_conv_desc* desc() const { return desc_; }
+  void* filter_cache() const { return fcache_; }
 
  protected:
   void Forward_gpu(const vector<Blob*>& bottom, const vector<Blob*>& top) override;     // conv_layer.cu:7-23
@@ -249,6 +255,9 @@ class ConvolutionLayer : public LayerBase {
   b2c_conv_params desc_params_{};
   void* ws_ = nullptr;
   size_t ws_bytes_ = 0;
+  void* fcache_ = nullptr;
+  size_t fcache_bytes_ = 0;
+  bool fcache_on_ = false;
 };
 shared_ptr<LayerBase> GetConvolutionLayer(const LayerParameter& p);   // layer_factory.cpp:53-88
 

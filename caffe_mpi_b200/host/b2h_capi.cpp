@@ -333,7 +333,7 @@ int b2h_trainer_param(void* hv, int i, int what, int set, float* buf) {   // wha
     CUDA_CHECK(cudaDeviceSynchronize());
     float* dev = what == 0 ? b.mutable_gpu_data() : what == 1 ? b.mutable_gpu_diff()
                                                               : h->net->solver().arena().history() + h->net->solver().arena().offset(id);
-    if (set) CUDA_CHECK(cudaMemcpy(dev, buf, sizeof(float) * b.count(), cudaMemcpyHostToDevice));
+    if (set) { CUDA_CHECK(cudaMemcpy(dev, buf, sizeof(float) * b.count(), cudaMemcpyHostToDevice)); if (what == 0) h->net->MarkParamsDirty(); }
     else CUDA_CHECK(cudaMemcpy(buf, dev, sizeof(float) * b.count(), cudaMemcpyDeviceToHost));
   });
 }

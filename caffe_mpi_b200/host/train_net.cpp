@@ -318,6 +318,9 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
   }
   solver_.reset(new SGDSolver(sp));
   solver_->SetParams(learnable_, specs);
+  for (auto& l : layers_)
+    if (auto* c = dynamic_cast<ConvolutionLayer*>(l.get()))
+      if (c->EnableFilterCache()) cached_convs_.push_back(c);
   sched_.reset(new ReduceScheduler(solver_.get(), nullptr));
   CUDA_CHECK(cudaStreamSynchronize(S()));
 }
@@ -326,6 +329,7 @@ TrainNet::~TrainNet() {}
 void TrainNet::AttachSync(P2PSync* sync) {
   sync_ = sync;
   sync_->on_start(solver_->arena());
+  filters_dirty_ = true;
   sched_.reset(new ReduceScheduler(solver_.get(), sync_));
 }
 Blob* TrainNet::blob(const string& name) {
@@ -337,7 +341,20 @@ size_t TrainNet::activation_floats() const {
   for (auto& kv : blobs_) c += kv.second->count();
   return c;
 }
+void TrainNet::PrepareFilters() {
+  // one multi-tensor launch per 24 filter layouts instead of one prepass per forward and per dgrad call
+  vector<const b2c_conv_desc*> descs;
+  vector<const float*> ws;
+  vector<void*> caches;
+  for (ConvolutionLayer* c : cached_convs_) {
+    if (!c->desc() || !c->filter_cache()) continue;
+    descs.push_back(c->desc()); ws.push_back(c->blobs()[0]->gpu_data()); caches.push_back(c->filter_cache());
+  }
+  if (!descs.empty()) B2C_CHECK(b2c_conv_prepare_filters((int)descs.size(), descs.data(), ws.data(), caches.data(), S()));
+  filters_dirty_ = false;
+}
 void TrainNet::Forward(bool copy_input) {
+  if (filters_dirty_) PrepareFilters();
   if (copy_input && data_) {
     Blob* d = nodes_[0].top[0];
     CUDA_CHECK(cudaMemcpyAsync(d->mutable_gpu_data(), data_->host_batch(), sizeof(float) * data_->batch_floats(), cudaMemcpyHostToDevice, S()));
@@ -385,6 +402,7 @@ void TrainNet::Step(bool copy_input_from_host) {
     Backward(i + 1 == iter_size);
   }
   sched_->end_of_iteration(S());
+  filters_dirty_ = true;          // the update changed every weight: the next Forward re-prepares (after the compute stream's wait)
 }
 float TrainNet::TimedSteps(int n, bool copy_input, bool read_loss) {
   cudaEvent_t a, b;
@@ -468,6 +486,7 @@ int TrainNet::CopyTrainedLayersFrom(const string& path) {
     }
     ++copied;
   }
+  filters_dirty_ = true;
   return copied;
 }
 void TrainNet::Restore(const string& state_path) {

@@ -198,6 +198,12 @@ class TrainNet {
   };
   void Forward(bool copy_input);
   void Backward(bool update);
+  void PrepareFilters();                           // b2c_conv_prepare_filters over every cached conv layer (weights changed)
+ public:
+  void MarkParamsDirty() { filters_dirty_ = true; } // call after writing parameter data behind the net's back
+ private:
+  bool filters_dirty_ = true;
+  vector<ConvolutionLayer*> cached_convs_;
   float host_loss_ = 0.f;
   string name_;
   vector<string> layer_names_, layer_types_;

@@ -168,6 +168,40 @@ def test_conv_tf32_mode_within_1e3(rng, name, case):
         assert rel_err(got[k], want[k]) < TOL_TF32, (k, rel_err(got[k], want[k]))
 
 
+PREP_CASES = ["resnet_res2_3x3", "resnet_res2_1x1_expand", "resnet_res3_1x1_s2", "alexnet_conv2_g2", "resnet_stem", "resnet_res5_3x3",
+              "staged_5x5_c32", "lenet_conv1"]
+
+
+@pytest.mark.parametrize("name", PREP_CASES)
+def test_prepared_filter_cache_is_bitwise_equivalent(rng, name):
+    """b2c_conv_prepare_filter + bind: forward / backward_data read the cached GEMM-ordered filter instead of re-deriving it;
+    results must be bit-identical to the self-contained calls, and a stale cache must be the caller's problem only (new
+    weights + re-prepare == fresh result)."""
+    case = dict(ALL_CASES)[name]
+    po, pc = make(o, case), make(capi, case)
+    x, w, b, dy = tensors(rng, po)
+    X, Wt, Bv, DY = dev(x), dev(w), dev(b), dev(dy)
+    plain, cached = m.ConvDesc(pc), m.ConvDesc(pc)
+    Y0, Y1 = torch.empty(po.y_shape(), device="cuda"), torch.empty(po.y_shape(), device="cuda")
+    DX0, DX1 = torch.empty(po.x_shape(), device="cuda"), torch.empty(po.x_shape(), device="cuda")
+    plain.forward(X, Wt, Bv, Y0); plain.backward_data(DY, Wt, DX0)
+    has_cache = cached.prepare_filter(Wt)
+    assert has_cache == (capi.ALGO_TCGEN05 in (cached.algo_used(0), cached.algo_used(1)))
+    before = m.lib().b2c_launch_count()
+    cached.forward(X, Wt, Bv, Y1); cached.backward_data(DY, Wt, DX1)
+    launched = m.lib().b2c_launch_count() - before
+    assert torch.equal(Y0, Y1) and torch.equal(DX0, DX1)
+    if has_cache and cached.algo_used(0) == capi.ALGO_TCGEN05 and cached.algo_used(1) == capi.ALGO_TCGEN05:
+        assert launched <= 3          # two conv kernels (+ the memset-free scatter path's none): no per-call prepass
+    W2 = dev((w * 0.5 + 0.01).astype(np.float32))
+    cached.prepare_filter(W2)
+    plain.forward(X, W2, Bv, Y0); cached.forward(X, W2, Bv, Y1)
+    assert torch.equal(Y0, Y1)
+    cached.unbind_filter_cache()
+    cached.forward(X, Wt, Bv, Y1); plain.forward(X, Wt, Bv, Y0)
+    assert torch.equal(Y0, Y1)
+
+
 def test_sobel_known_answer(rng):
     # test_convolution_layer.cpp:511-604 / CuDNN variant :1013-1110, tol 1e-4
     x = rng.standard_normal((2, 3, 6, 4)).astype(np.float32)
