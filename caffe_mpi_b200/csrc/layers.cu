@@ -481,6 +481,15 @@ static bool vec_ok(int S, std::initializer_list<const void*> ptrs) {
   for (const void* p : ptrs) if (reinterpret_cast<uintptr_t>(p) & 15) return false;
   return true;
 }
+namespace b2c {
+int launch_bn_stats(int N, int C, int S, const float* x, float eps, float maf, int first, float* mean, float* invstd, float* run_mean,
+                    float* run_var, bool vec, void* stream) {
+  const unsigned cs = bn_cluster_size(N, C, S);
+  launch_clustered(vec ? bn_stats_kernel<true> : bn_stats_kernel<false>, cs, C, stream, N, C, S, x, eps, maf, first, mean, invstd, run_mean, run_var);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+}  // namespace b2c
 extern "C" int b2c_bn_forward_train(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
                                     float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
                                     float* save_mean, float* save_invstd, float* xnorm, float* y, void* stream) {

@@ -1,0 +1,304 @@
+// layers_fused.cu -- fused forms of the BatchNorm / ReLU / Eltwise chain of a residual block (HBM-bound passes; fusion is the
+// only lever left once each pass runs at 60-95% of the HBM roofline, profiles/r01_fullnet_launches.csv):
+//
+//   b2c_bn_forward_train_fused : batch statistics + y = [max(0, .)] (gamma * x_norm + beta).  x_norm is NOT written: the
+//                                backward pass recomputes it from the layer's input x and the saved mean / inverse std
+//                                (8 B/element instead of 12; the reference keeps x_norm_, batch_norm_layer.cu:60-75).
+//   b2c_bn_backward_fused      : dgamma / dbeta / dx with the ReLU mask folded in: the mask (top > 0) equals
+//                                (gamma * x_norm + beta > 0) recomputed with the forward's own expression, so the result is
+//                                bit-identical to ReLU::Backward followed by BatchNorm::Backward (relu_layer.cpp:27-41,
+//                                batch_norm_layer.cpp:230-300) at 20 B/element instead of 32.
+//   b2c_add_relu               : y = max(0, a + b)                      (Eltwise SUM + in-place ReLU, one pass instead of two)
+//   b2c_relu_backward2         : dx_a = dx_b = dy * (y > 0)             (ReLU backward + Eltwise SUM backward's two copies)
+#include <cooperative_groups.h>
+#include <initializer_list>
+#include "b2c_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace b2c {
+
+static __device__ __forceinline__ float fwarp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static __device__ __forceinline__ void fblock_sum2(float& a, float& b) {
+  __shared__ float sa[32], sb[32];
+  a = fwarp_sum(a); b = fwarp_sum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  a = lane < nw ? sa[lane] : 0.f; b = lane < nw ? sb[lane] : 0.f;
+  a = fwarp_sum(a); b = fwarp_sum(b);
+  __syncthreads();
+}
+
+constexpr int FB_CLUSTER = 8;
+constexpr int FB_THREADS = 256;
+constexpr int FB_EW = 8;           // units per thread of the elementwise passes
+
+struct FPlaneCursor {               // flattened unit index of a channel -> (image, offset)
+  unsigned n, p;
+  __device__ __forceinline__ void init(unsigned i, unsigned units) { n = i / units; p = i - n * units; }
+  __device__ __forceinline__ void advance(unsigned step, unsigned units) { p += step; while (p >= units) { p -= units; ++n; } }
+};
+struct FChanCursor {                // flattened unit index of the tensor -> (offset in plane, channel)
+  unsigned p, c;
+  __device__ __forceinline__ void init(size_t i, unsigned units, unsigned C) { const size_t plane = i / units; p = (unsigned)(i - plane * units); c = (unsigned)(plane % C); }
+  __device__ __forceinline__ void advance(unsigned step, unsigned units, unsigned C) { p += step; while (p >= units) { p -= units; if (++c == C) c = 0; } }
+};
+
+// the forward's expression, verbatim in both passes so that the recomputed mask and x_norm carry the same bits
+__device__ __forceinline__ float bn_xn(float x, float m, float is) { return (x - m) * is; }
+__device__ __forceinline__ float bn_y(float xn, float g, float bt, bool affine) { return affine ? xn * g + bt : xn; }
+
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(256)
+bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
+  const unsigned units = VEC ? S / 4 : S;
+  size_t i = (size_t)blockIdx.x * (256 * FB_EW) + threadIdx.x;
+  if (i >= total_units) return;
+  FChanCursor cur;
+  cur.init(i, units, C);
+  const bool affine = gamma != nullptr;
+#pragma unroll 2
+  for (int k = 0; k < FB_EW && i < total_units; ++k, i += 256) {
+    const float m = mean[cur.c], is = invstd[cur.c], g = affine ? gamma[cur.c] : 1.f, bt = affine ? beta[cur.c] : 0.f;
+    if (VEC) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      float4 o;
+      o.x = bn_y(bn_xn(v.x, m, is), g, bt, affine); o.y = bn_y(bn_xn(v.y, m, is), g, bt, affine);
+      o.z = bn_y(bn_xn(v.z, m, is), g, bt, affine); o.w = bn_y(bn_xn(v.w, m, is), g, bt, affine);
+      if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      reinterpret_cast<float4*>(y)[i] = o;
+    } else {
+      const float o = bn_y(bn_xn(x[i], m, is), g, bt, affine);
+      y[i] = RELU ? fmaxf(o, 0.f) : o;
+    }
+    cur.advance(256, units, C);
+  }
+}
+
+// per channel: sum dy_eff * x_norm, sum dy_eff with dy_eff = RELU ? (y_pre > 0 ? dy : 0) : dy, one thread-block cluster per channel
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(FB_THREADS)
+bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy) {
+  __shared__ float2 part;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+  const int c = blockIdx.y;
+  const bool affine = gamma != nullptr;
+  const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
+  constexpr int U = 4;
+  const unsigned units = VEC ? S / 4 : S;
+  const unsigned total = (unsigned)N * units;
+  const unsigned len = (total + nranks - 1) / nranks;
+  const unsigned lo = min(total, rank * len), hi = min(total, lo + len);
+  float a = 0.f, b = 0.f, a2 = 0.f, b2 = 0.f;
+  FPlaneCursor cur;
+  unsigned i = lo + threadIdx.x;
+  if (i < hi) cur.init(i, units);
+  auto acc = [&](float d, float xv, float& sa, float& sb) {
+    const float xn = bn_xn(xv, m, is);
+    if (RELU && !(bn_y(xn, g, bt, affine) > 0.f)) d = 0.f;
+    sa = fmaf(d, xn, sa); sb += d;
+  };
+  for (; i < hi; i += U * FB_THREADS) {
+    size_t off[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ok[u] = i + u * FB_THREADS < hi;
+      off[u] = ((size_t)cur.n * C + c) * units + cur.p;
+      cur.advance(FB_THREADS, units);
+    }
+    if (VEC) {
+      float4 d[U], v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        d[u] = ok[u] ? reinterpret_cast<const float4*>(dy)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(m, m, m, m);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { acc(d[u].x, v[u].x, a, b); acc(d[u].y, v[u].y, a2, b2); acc(d[u].z, v[u].z, a, b); acc(d[u].w, v[u].w, a2, b2); }
+    } else {
+      float d[U], v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { d[u] = ok[u] ? dy[off[u]] : 0.f; v[u] = ok[u] ? x[off[u]] : m; }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc(d[u], v[u], a, b);
+    }
+  }
+  a += a2; b += b2;
+  fblock_sum2(a, b);
+  if (threadIdx.x == 0) part = make_float2(a, b);
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned r = 0; r < nranks; ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
+    sum_dy_xn[c] = (float)s1; sum_dy[c] = (float)s2;
+  }
+  cluster.sync();
+}
+
+// dx = gamma * invstd * (dy_eff - mean(dy_eff) - x_norm * mean(dy_eff * x_norm))
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_fused_kernel(size_t total_units, int C, int S, float inv_cnt, const float* __restrict__ dy, const float* __restrict__ x,
+                       const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ sum_dy_xn, const float* __restrict__ sum_dy, float* __restrict__ dx) {
+  const unsigned units = VEC ? S / 4 : S;
+  size_t i = (size_t)blockIdx.x * (256 * FB_EW) + threadIdx.x;
+  if (i >= total_units) return;
+  FChanCursor cur;
+  cur.init(i, units, C);
+  const bool affine = gamma != nullptr;
+#pragma unroll 2
+  for (int k = 0; k < FB_EW && i < total_units; ++k, i += 256) {
+    const float m = mean[cur.c], is = invstd[cur.c], g = affine ? gamma[cur.c] : 1.f, bt = affine ? beta[cur.c] : 0.f;
+    const float gi = g * is, mdy = sum_dy[cur.c] * inv_cnt, mdx = sum_dy_xn[cur.c] * inv_cnt;
+    auto one = [&](float d, float xv) {
+      const float xn = bn_xn(xv, m, is);
+      if (RELU && !(bn_y(xn, g, bt, affine) > 0.f)) d = 0.f;
+      return gi * (d - mdy - xn * mdx);
+    };
+    if (VEC) {
+      const float4 d = reinterpret_cast<const float4*>(dy)[i], v = reinterpret_cast<const float4*>(x)[i];
+      reinterpret_cast<float4*>(dx)[i] = make_float4(one(d.x, v.x), one(d.y, v.y), one(d.z, v.z), one(d.w, v.w));
+    } else {
+      dx[i] = one(dy[i], x[i]);
+    }
+    cur.advance(256, units, C);
+  }
+}
+
+__global__ void __launch_bounds__(256) add_relu_kernel(size_t n, int vec, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y) {
+  const size_t n4 = vec ? n / 4 : 0, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = tid; i < n4; i += step) {
+    const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(fmaxf(u.x + v.x, 0.f), fmaxf(u.y + v.y, 0.f), fmaxf(u.z + v.z, 0.f), fmaxf(u.w + v.w, 0.f));
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += step) y[i] = fmaxf(a[i] + b[i], 0.f);
+}
+__global__ void __launch_bounds__(256)
+relu_bwd2_kernel(size_t n, int vec, const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dxa, float* __restrict__ dxb) {
+  const size_t n4 = vec ? n / 4 : 0, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = tid; i < n4; i += step) {
+    const float4 d = reinterpret_cast<const float4*>(dy)[i], v = reinterpret_cast<const float4*>(y)[i];
+    const float4 o = make_float4(d.x * (v.x > 0 ? 1.f : 0.f), d.y * (v.y > 0 ? 1.f : 0.f), d.z * (v.z > 0 ? 1.f : 0.f), d.w * (v.w > 0 ? 1.f : 0.f));
+    if (dxa) reinterpret_cast<float4*>(dxa)[i] = o;
+    if (dxb) reinterpret_cast<float4*>(dxb)[i] = o;
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += step) {
+    const float o = dy[i] * (y[i] > 0 ? 1.f : 0.f);
+    if (dxa) dxa[i] = o;
+    if (dxb) dxb[i] = o;
+  }
+}
+
+// the statistics kernel of layers.cu (same launch for the fused and the unfused forward)
+int launch_bn_stats(int N, int C, int S, const float* x, float eps, float maf, int first, float* mean, float* invstd, float* run_mean,
+                    float* run_var, bool vec, void* stream);
+
+static unsigned fb_cluster_size(int N, int C, int S) {
+  const size_t E = (size_t)N * S;
+  unsigned cs = 1;
+  while (cs < FB_CLUSTER && E / (cs * 2) >= 16384) cs *= 2;
+  while (cs < FB_CLUSTER && (size_t)C * cs < 2u * (unsigned)sm_count()) cs *= 2;
+  return cs;
+}
+template <typename... Args>
+static void fb_launch_clustered(void (*kernel)(Args...), unsigned cs, int C, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, C, 1);
+  cfg.blockDim = dim3(FB_THREADS, 1, 1);
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+static bool fb_vec_ok(int S, std::initializer_list<const void*> ptrs) {
+  if (S % 4) return false;
+  for (const void* p : ptrs) if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+  return true;
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+#define FNEED(cond, msg) do { if (!(cond)) return fail(B2C_ERR_INVALID, msg); } while (0)
+
+extern "C" int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                                          float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                                          float* save_mean, float* save_invstd, float* y, int relu, void* stream) {
+  FNEED(x && y && save_mean && save_invstd && running_mean && running_var && N > 0 && C > 0 && S > 0, "b2c_bn_forward_train_fused: bad argument");
+  FNEED((gamma == nullptr) == (beta == nullptr), "b2c_bn_forward_train_fused: gamma and beta go together");
+  FNEED((size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_forward_train_fused: channel extent out of range");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  const bool vec = fb_vec_ok(S, {x, y});
+  if (int rc = launch_bn_stats(N, C, S, x, eps, moving_average_fraction, first_iteration, save_mean, save_invstd, running_mean, running_var, vec, stream)) return rc;
+  const size_t units = (size_t)N * C * (vec ? S / 4 : S);
+  const unsigned blocks = (unsigned)((units + 256 * FB_EW - 1) / (256 * FB_EW));
+  cudaStream_t st = as_stream(stream);
+  if (vec) { if (relu) bn_norm_fused_kernel<true, true><<<blocks, 256, 0, st>>>(units, C, S, x, save_mean, save_invstd, gamma, beta, y);
+             else bn_norm_fused_kernel<true, false><<<blocks, 256, 0, st>>>(units, C, S, x, save_mean, save_invstd, gamma, beta, y); }
+  else { if (relu) bn_norm_fused_kernel<false, true><<<blocks, 256, 0, st>>>(units, C, S, x, save_mean, save_invstd, gamma, beta, y);
+         else bn_norm_fused_kernel<false, false><<<blocks, 256, 0, st>>>(units, C, S, x, save_mean, save_invstd, gamma, beta, y); }
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+extern "C" int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                     const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream) {
+  FNEED(dy && x && save_mean && save_invstd && dgamma && dbeta && dx, "b2c_bn_backward_fused: null (dgamma/dbeta double as the reduction scratch)");
+  FNEED((gamma == nullptr) == (beta == nullptr), "b2c_bn_backward_fused: gamma and beta go together");
+  FNEED(N > 0 && C > 0 && S > 0 && (size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_backward_fused: channel extent out of range");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  const bool vec = fb_vec_ok(S, {dy, x, dx});
+  const unsigned cs = fb_cluster_size(N, C, S);
+  if (vec) { if (relu) fb_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+             else fb_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  else { if (relu) fb_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+         else fb_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  B2C_POST_LAUNCH();
+  const size_t units = (size_t)N * C * (vec ? S / 4 : S);
+  const unsigned blocks = (unsigned)((units + 256 * FB_EW - 1) / (256 * FB_EW));
+  const float inv_cnt = 1.0f / ((float)N * S);
+  cudaStream_t st = as_stream(stream);
+  if (vec) { if (relu) bn_bwd_dx_fused_kernel<true, true><<<blocks, 256, 0, st>>>(units, C, S, inv_cnt, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx);
+             else bn_bwd_dx_fused_kernel<true, false><<<blocks, 256, 0, st>>>(units, C, S, inv_cnt, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx); }
+  else { if (relu) bn_bwd_dx_fused_kernel<false, true><<<blocks, 256, 0, st>>>(units, C, S, inv_cnt, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx);
+         else bn_bwd_dx_fused_kernel<false, false><<<blocks, 256, 0, st>>>(units, C, S, inv_cnt, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx); }
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+extern "C" int b2c_add_relu(size_t n, const float* a, const float* b, float* y, void* stream) {
+  FNEED(a && b && y, "b2c_add_relu: null pointer");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (!n) return B2C_OK;
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  add_relu_kernel<<<grid_for(al ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(n, al ? 1 : 0, a, b, y);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+extern "C" int b2c_relu_backward2(size_t n, const float* dy, const float* y, float* dx_a, float* dx_b, void* stream) {
+  FNEED(dy && y && (dx_a || dx_b), "b2c_relu_backward2: null pointer");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (!n) return B2C_OK;
+  const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx_a) | reinterpret_cast<uintptr_t>(dx_b)) & 15) == 0;
+  relu_bwd2_kernel<<<grid_for(al ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(n, al ? 1 : 0, dy, y, dx_a, dx_b);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}

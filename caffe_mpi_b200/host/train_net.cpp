@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace caffe {
 
@@ -11,10 +12,11 @@ static cudaStream_t S() { return Caffe::thread_stream(); }
 
 // ================================================================================================ ReLU
 void ReLULayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  if (fused_away_) return;
   B2C_CHECK(b2c_relu_forward(b[0]->count(), b[0]->gpu_data(), t[0]->mutable_gpu_data(), slope_, S()));
 }
 void ReLULayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
-  if (!pd[0]) return;
+  if (!pd[0] || fused_away_) return;
   // in place: bottom data == top data (post-activation), same (x > 0) mask for slope 0 (relu_layer.cpp:27-41)
   B2C_CHECK(b2c_relu_backward(b[0]->count(), t[0]->gpu_diff(), b[0]->gpu_data(), b[0]->mutable_gpu_diff(), slope_, S()));
 }
@@ -38,11 +40,21 @@ void BatchNormLayer::LayerSetUp(const vector<Blob*>& b, const vector<Blob*>&) {
 void BatchNormLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
   if (t[0] != b[0]) t[0]->ReshapeLike(*b[0]);
   const int C = b[0]->shape(1);
-  xnorm_.ReshapeLike(*b[0]);
+  if (!(recompute_ && t[0] != b[0])) xnorm_.ReshapeLike(*b[0]);
   save_mean_.Reshape({C}); save_invstd_.Reshape({C}); scratch_.Reshape({2 * C});
 }
 void BatchNormLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
+  if (recompute_ && t[0] != b[0]) {
+    // fused form: no x_norm blob (backward recomputes it from the bottom), optional ReLU on the way out
+    B2C_CHECK(b2c_bn_forward_train_fused(N, C, Sp, b[0]->gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
+                                         scale_bias_ ? blobs_[4]->gpu_data() : nullptr, eps_, maf_, iter_ <= 1 ? 1 : 0,
+                                         blobs_[0]->mutable_gpu_data(), blobs_[1]->mutable_gpu_data(), save_mean_.mutable_gpu_data(),
+                                         save_invstd_.mutable_gpu_data(), t[0]->mutable_gpu_data(), fuse_relu_ ? 1 : 0, S()));
+    ++iter_;
+    return;
+  }
+  B2_CHECK(!fuse_relu_, "BatchNorm: ReLU fusion needs the recompute form (top != bottom)");
   B2C_CHECK(b2c_bn_forward_train(N, C, Sp, b[0]->gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
                                  scale_bias_ ? blobs_[4]->gpu_data() : nullptr, eps_, maf_, iter_ <= 1 ? 1 : 0,
                                  blobs_[0]->mutable_gpu_data(), blobs_[1]->mutable_gpu_data(), save_mean_.mutable_gpu_data(),
@@ -53,6 +65,12 @@ void BatchNormLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>&, c
   const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
   float* dg = scale_bias_ ? blobs_[3]->mutable_gpu_diff() : scratch_.mutable_gpu_data();
   float* db = scale_bias_ ? blobs_[4]->mutable_gpu_diff() : scratch_.mutable_gpu_data() + C;
+  if (recompute_ && t[0] != b[0]) {
+    B2C_CHECK(b2c_bn_backward_fused(N, C, Sp, t[0]->gpu_diff(), b[0]->gpu_data(), save_mean_.gpu_data(), save_invstd_.gpu_data(),
+                                    scale_bias_ ? blobs_[3]->gpu_data() : nullptr, scale_bias_ ? blobs_[4]->gpu_data() : nullptr, dg, db,
+                                    b[0]->mutable_gpu_diff(), fuse_relu_ ? 1 : 0, S()));
+    return;
+  }
   B2C_CHECK(b2c_bn_backward(N, C, Sp, t[0]->gpu_diff(), xnorm_.gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
                             save_invstd_.gpu_data(), dg, db, b[0]->mutable_gpu_diff(), S()));
 }
@@ -88,10 +106,20 @@ void PoolingLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, 
 // ================================================================================================ Eltwise SUM
 void EltwiseLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   B2_CHECK(b.size() >= 2, "Eltwise needs two bottoms");
+  if (fuse_relu_ && b.size() == 2) {        // y = max(0, a + b): the in-place ReLU that follows is folded in
+    B2C_CHECK(b2c_add_relu(t[0]->count(), b[0]->gpu_data(), b[1]->gpu_data(), t[0]->mutable_gpu_data(), S()));
+    return;
+  }
   B2C_CHECK(b2c_add(t[0]->count(), b[0]->gpu_data(), b[1]->gpu_data(), t[0]->mutable_gpu_data(), S()));
   for (size_t i = 2; i < b.size(); ++i) B2C_CHECK(b2c_add(t[0]->count(), t[0]->gpu_data(), b[i]->gpu_data(), t[0]->mutable_gpu_data(), S()));
 }
 void EltwiseLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (fuse_relu_ && b.size() == 2) {        // dx_a = dx_b = dy * (y > 0): ReLU backward + the two copies of SUM's backward
+    if (pd[0] || pd[1])
+      B2C_CHECK(b2c_relu_backward2(t[0]->count(), t[0]->gpu_diff(), t[0]->gpu_data(), pd[0] ? b[0]->mutable_gpu_diff() : nullptr,
+                                   pd[1] ? b[1]->mutable_gpu_diff() : nullptr, S()));
+    return;
+  }
   for (size_t i = 0; i < b.size(); ++i)
     if (pd[i]) CUDA_CHECK(cudaMemcpyAsync(b[i]->mutable_gpu_diff(), t[0]->gpu_diff(), sizeof(float) * t[0]->count(), cudaMemcpyDeviceToDevice, S()));
 }
@@ -299,6 +327,33 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
     layer_names_.push_back(L.param.name);
     layer_types_.push_back(type);
     nodes_.push_back(node);
+  }
+  // Fusion pass (B2C_FUSE=0 disables): BatchNorm -> in-place ReLU and Eltwise(SUM, 2 bottoms) -> in-place ReLU run as one
+  // kernel each way, and BatchNorm stops materialising x_norm (csrc/layers_fused.cu).  The ReLU layer stays in the graph as a
+  // no-op so that layer indices, names and blobs are those of the prototxt.  Results are bit-identical to the unfused graph.
+  {
+    const char* e = getenv("B2C_FUSE");
+    const bool fuse = !e || atoi(e) != 0;
+    for (size_t i = 0; fuse && i < layers_.size(); ++i) {
+      auto* bn = dynamic_cast<BatchNormLayer*>(layers_[i].get());
+      auto* el = dynamic_cast<EltwiseLayer*>(layers_[i].get());
+      if (!bn && !el) continue;
+      const bool out_of_place = nodes_[i].top[0] != nodes_[i].bottom[0];
+      ReLULayer* relu = nullptr;
+      if (i + 1 < layers_.size()) {
+        relu = dynamic_cast<ReLULayer*>(layers_[i + 1].get());
+        if (relu && !(nodes_[i + 1].bottom[0] == nodes_[i].top[0] && nodes_[i + 1].top[0] == nodes_[i].top[0] && relu->negative_slope() == 0.f))
+          relu = nullptr;
+      }
+      if (bn && out_of_place) {
+        bn->set_fusion(true, relu != nullptr);
+        bn->Reshape(nodes_[i].bottom, nodes_[i].top);
+        if (relu) relu->set_fused_away(true);
+      } else if (el && relu && nodes_[i].bottom.size() == 2) {
+        el->set_fuse_relu(true);
+        relu->set_fused_away(true);
+      }
+    }
   }
   // diff accumulation where a blob fans out (insert_splits.cpp / SplitLayer::Backward): the consumer that runs FIRST in
   // the backward pass writes the blob's diff; every other consumer writes a shadow diff that is then added in

@@ -19,6 +19,10 @@ class ReLULayer : public LayerBase {
   void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
   void Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) override;
   float slope_;     // relu_param.negative_slope (relu_layer.cpp:13-16)
+  bool fused_away_ = false;
+ public:
+  float negative_slope() const { return slope_; }
+  void set_fused_away(bool v) { fused_away_ = v; }   // the producing BatchNorm / Eltwise layer applies (and back-propagates) this ReLU
 };
 
 class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_bias (batch_norm_layer.cpp)
@@ -37,9 +41,12 @@ class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_b
   bool scale_bias_;
   float eps_, maf_;
   FillerParameter scale_filler_, bias_filler_;
+  bool fuse_relu_ = false;   // an in-place ReLU on the top blob is folded into this layer's kernels (TrainNet's fusion pass)
+  bool recompute_ = false;   // do not store x_norm: backward recomputes it from the bottom blob (needs top != bottom)
   int iter_ = 0;
  public:
   void set_iter(int i) { iter_ = i; }
+  void set_fusion(bool recompute_xnorm, bool fuse_relu) { recompute_ = recompute_xnorm; fuse_relu_ = fuse_relu; }
  protected:
   Blob xnorm_, save_mean_, save_invstd_, scratch_;
 };
@@ -62,6 +69,10 @@ class PoolingLayer : public LayerBase {
 class EltwiseLayer : public LayerBase {        // SUM with unit coefficients (the only use in the BASELINE nets)
  public:
   using LayerBase::LayerBase;
+  void set_fuse_relu(bool v) { fuse_relu_ = v; }
+ protected:
+  bool fuse_relu_ = false;
+ public:
   const char* type() const override { return "Eltwise"; }
   void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { t[0]->ReshapeLike(*b[0]); }
  protected:

@@ -176,6 +176,15 @@ int b2c_bn_backward(int N, int C, int S, const float* dy, const float* xnorm, co
                     float* dgamma, float* dbeta, float* dx, void* stream);
 /* PoolingLayer (src/caffe/layers/pooling_layer.cpp:129-318): method 0 = MAX (mask = argmax index inside the H*W
  * plane, first maximum), 1 = AVE.  NC = N*C planes; output extent is the reference's ceil mode.  dx overwritten.    */
+/* Fused forms of the BatchNorm -> ReLU and Eltwise(SUM) -> ReLU chains (csrc/layers_fused.cu): bit-identical to the unfused
+ * layer sequence, one HBM pass less each way; x_norm is recomputed in backward from the layer input and the saved statistics. */
+int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                               float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                               float* save_mean, float* save_invstd, float* y, int relu, void* stream);
+int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                          const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream);
+int b2c_add_relu(size_t n, const float* a, const float* b, float* y, void* stream);
+int b2c_relu_backward2(size_t n, const float* dy, const float* y, float* dx_a, float* dx_b, void* stream);
 int b2c_pool_forward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* x,
                      float* y, int* mask, void* stream);
 int b2c_pool_backward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* dy,

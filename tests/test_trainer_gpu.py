@@ -15,9 +15,21 @@ def rel(a, ref, floor=1e-20):
     return float(np.max(np.abs(a.reshape(-1) - ref.reshape(-1))) / max(np.max(np.abs(ref)), floor))
 
 
-def make_trainer(spec, rng, classes=10, math=capi.MATH_FP32):
+def make_trainer(spec, rng, classes=10, math=capi.MATH_FP32, fuse=None):
+    """fuse: None = library default (fusion pass on), False = B2C_FUSE=0 (the prototxt's layers one by one)."""
+    import os
     shapes = no.param_shapes(spec)
-    t = host_api.Trainer(no.to_prototxt(spec), SOLVER, num_classes=classes, math=math)
+    old = os.environ.get("B2C_FUSE")
+    if fuse is not None:
+        os.environ["B2C_FUSE"] = "1" if fuse else "0"
+    try:
+        t = host_api.Trainer(no.to_prototxt(spec), SOLVER, num_classes=classes, math=math)
+    finally:
+        if fuse is not None:
+            if old is None:
+                os.environ.pop("B2C_FUSE", None)
+            else:
+                os.environ["B2C_FUSE"] = old
     assert t.num_params() == len(shapes)
     params = []
     for i, (layer, kind, shp) in enumerate(shapes):
@@ -38,16 +50,19 @@ def make_trainer(spec, rng, classes=10, math=capi.MATH_FP32):
     return t, params, data, label
 
 
+@pytest.mark.parametrize("fuse", [False, True], ids=["unfused", "fused"])
 @pytest.mark.parametrize("conv_bias", [False, True])
-def test_forward_backward_matches_oracle(rng, conv_bias):
+def test_forward_backward_matches_oracle(rng, conv_bias, fuse):
     spec = no.mini_resnet(conv_bias=conv_bias)
-    t, params, data, label = make_trainer(spec, rng)
+    t, params, data, label = make_trainer(spec, rng, fuse=fuse)
     loss = t.forward_backward()
     ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
     assert abs(loss - ref_loss) <= TOL * abs(ref_loss)
     for name in ("conv1", "pool1", "resA.1.sum", "resA.2.sum", "pool2", "fc"):
         assert rel(t.get_blob(name), v[name]) <= TOL, name
-    for name in ("fc", "pool2", "resA.2.sum", "resA.1.conv1", "pool1", "conv1"):
+    # with the fusion pass on, the diff of a blob that an in-place ReLU follows holds dL/d(post-ReLU): the ReLU mask is applied
+    # inside the fused backward kernel instead of in place (the oracle's d[] is the masked one)
+    for name in ("fc", "pool2", "resA.1.conv1", "pool1", "conv1") + (() if fuse else ("resA.2.sum",)):
         assert rel(t.get_blob(name, diff=True), d[name]) <= TOL, name
     # gradients that are mathematically zero (a conv bias in front of BatchNorm, whose mean subtraction cancels it) are
     # rounding noise on both sides: the denominator is floored at 1e-3 of the largest gradient in the net
@@ -149,3 +164,22 @@ def test_snapshot_restore_roundtrip_on_device(rng, tmp_path):
     assert L.b2h_wire_num_history(h) == t.num_learnable() > t.num_params()
     L.b2h_wire_destroy.argtypes = [__import__("ctypes").c_void_p]
     L.b2h_wire_destroy(h)
+
+
+def test_fusion_pass_is_bitwise_neutral(rng):
+    """BatchNorm+ReLU / Eltwise+ReLU fusion and x_norm recomputation (csrc/layers_fused.cu) against the unfused graph: loss,
+    every parameter gradient and three SGD steps, bit for bit."""
+    spec = no.mini_resnet()
+    a, params, data, label = make_trainer(spec, rng, fuse=False)
+    b, _, _, _ = make_trainer(spec, np.random.default_rng(3), fuse=True)
+    for i, p in enumerate(params):
+        b.set_param(i, p)
+    b.set_blob("data", data)
+    b.set_blob("label", label)
+    assert a.forward_backward() == b.forward_backward()
+    for i in range(a.num_params()):
+        assert np.array_equal(a.get_param(i, 1).view(np.uint32), b.get_param(i, 1).view(np.uint32)), i
+    a.step(3); b.step(3)
+    assert a.loss() == b.loss()
+    for i in range(a.num_params()):
+        assert np.array_equal(a.get_param(i, 0).view(np.uint32), b.get_param(i, 0).view(np.uint32)), i
