@@ -10,9 +10,13 @@
 #include <nccl.h>
 #include "b2c_common.cuh"
 
+#include <stdlib.h>
+#include <vector>
+
 struct b2c_comm {
   ncclComm_t comm;
   int nranks, rank;
+  std::vector<void*> handles;      // ncclCommRegister handles, released at destroy
 };
 
 #define B2C_NCCL_OK(expr)                                                                          \
@@ -37,8 +41,13 @@ extern "C" int b2c_comm_init(int nranks, int rank, const void* id, b2c_comm** ou
     return b2c::fail(B2C_ERR_INVALID, "b2c_comm_init: bad argument");
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
-  b2c_comm* c = new b2c_comm{nullptr, nranks, rank};
-  ncclResult_t r = ncclCommInitRank(&c->comm, nranks, uid, rank);
+  b2c_comm* c = new b2c_comm{nullptr, nranks, rank, {}};
+  // B2C_NCCL_MAX_CTAS: cap the CTAs NCCL may use per collective.  The tcgen05 conv kernels are persistent with one CTA per
+  // SM, so an allreduce overlapped with backward only gets SMs at kernel tails; fewer, NVLS-fed CTAs disturb them less.
+  ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+  if (const char* e = getenv("B2C_NCCL_MAX_CTAS")) { const int v = atoi(e); if (v > 0) cfg.maxCTAs = v; }
+  if (const char* e = getenv("B2C_NCCL_MIN_CTAS")) { const int v = atoi(e); if (v > 0) cfg.minCTAs = v; }
+  ncclResult_t r = ncclCommInitRankConfig(&c->comm, nranks, uid, rank, &cfg);
   if (r != ncclSuccess) {
     delete c;
     return b2c::fail(B2C_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
@@ -49,6 +58,7 @@ extern "C" int b2c_comm_init(int nranks, int rank, const void* id, b2c_comm** ou
 
 extern "C" int b2c_comm_destroy(b2c_comm* c) {
   if (!c) return B2C_OK;
+  for (void* h : c->handles) ncclCommDeregister(c->comm, h);
   ncclCommDestroy(c->comm);
   delete c;
   return B2C_OK;
@@ -65,5 +75,27 @@ extern "C" int b2c_comm_bcast(b2c_comm* c, float* buf, size_t count, int root, v
 extern "C" int b2c_comm_allreduce_sum(b2c_comm* c, float* buf, size_t count, void* stream) {
   if (!c || !buf) return b2c::fail(B2C_ERR_INVALID, "b2c_comm_allreduce_sum: null");
   B2C_NCCL_OK(ncclAllReduce(buf, buf, count, ncclFloat, ncclSum, c->comm, b2c::as_stream(stream)));
+  return B2C_OK;
+}
+
+// ---- NVLS-friendly buffers ------------------------------------------------------------------------------------------------
+// ncclMemAlloc hands out memory that can be mapped into the NVSwitch multicast space, ncclCommRegister registers it with a
+// communicator: an in-place allreduce on such a buffer can use NVLS (in-switch reduction) without staging through NCCL's own
+// buffers.  The host layer allocates the contiguous diff arena this way (ParamArena) and registers it in P2PSync::on_start.
+extern "C" int b2c_comm_mem_alloc(void** ptr, size_t bytes) {
+  if (!ptr || !bytes) return b2c::fail(B2C_ERR_INVALID, "b2c_comm_mem_alloc: bad argument");
+  B2C_NCCL_OK(ncclMemAlloc(ptr, bytes));
+  return B2C_OK;
+}
+extern "C" int b2c_comm_mem_free(void* ptr) {
+  if (!ptr) return B2C_OK;
+  B2C_NCCL_OK(ncclMemFree(ptr));
+  return B2C_OK;
+}
+extern "C" int b2c_comm_register(b2c_comm* c, void* buf, size_t bytes) {
+  if (!c || !buf || !bytes) return b2c::fail(B2C_ERR_INVALID, "b2c_comm_register: bad argument");
+  void* h = nullptr;
+  B2C_NCCL_OK(ncclCommRegister(c->comm, buf, bytes, &h));
+  c->handles.push_back(h);
   return B2C_OK;
 }

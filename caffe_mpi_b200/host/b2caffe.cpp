@@ -455,7 +455,7 @@ void ConvolutionLayer::Backward_gpu(const vector<Blob*>& top, const vector<bool>
 // ================================================================================================ arena
 ParamArena::~ParamArena() {
   if (data_) cudaFree(data_);
-  if (diff_) cudaFree(diff_);
+  if (diff_) { if (diff_nccl_) b2c_comm_mem_free(diff_); else cudaFree(diff_); }
   if (hist_) cudaFree(hist_);
 }
 void ParamArena::InitLayout(const vector<size_t>& counts) {
@@ -476,7 +476,13 @@ void ParamArena::Init(const vector<shared_ptr<Blob>>& params) {
   total_ = off;
   const size_t bytes = sizeof(float) * (total_ ? total_ : 1);
   CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&data_), bytes));
-  CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&diff_), bytes));
+  // the diff arena is what the gradient allreduce runs on: allocate it with ncclMemAlloc so that, once registered with the
+  // communicator (P2PSync::on_start), NCCL can reduce it inside the NVSwitch (NVLS) in place.  B2C_NCCL_ARENA=0: cudaMalloc.
+  {
+    const char* e = getenv("B2C_NCCL_ARENA");
+    if ((!e || atoi(e) != 0) && b2c_comm_mem_alloc(reinterpret_cast<void**>(&diff_), bytes) == B2C_OK) diff_nccl_ = true;
+    else { diff_ = nullptr; CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&diff_), bytes)); }
+  }
   CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&hist_), bytes));
   CUDA_CHECK(cudaMemset(data_, 0, bytes));
   CUDA_CHECK(cudaMemset(diff_, 0, bytes));     // net.cpp:1367
@@ -603,6 +609,12 @@ void P2PSync::on_start(ParamArena& arena) {
   // the reference broadcasts blob by blob; the arena makes it one call
   B2C_CHECK(b2c_comm_bcast(comm_, arena.data(), arena.total(), 0, comm_stream_));
   CUDA_CHECK(cudaStreamSynchronize(comm_stream_));
+  if (arena.diff_is_nccl_memory()) {
+    // user-buffer registration of the whole diff arena (every bucket is a sub-range of it); a failure only costs the
+    // zero-copy path, so it is reported on stderr and training goes on
+    if (b2c_comm_register(comm_, arena.diff(), sizeof(float) * arena.total()) != B2C_OK)
+      fprintf(stderr, "P2PSync: ncclCommRegister of the diff arena failed (%s); continuing unregistered\n", b2c_last_error());
+  }
 }
 void P2PSync::allreduce_bucket(float* buf, size_t count) {
   B2C_CHECK(b2c_comm_allreduce_sum(comm_, buf, count, comm_stream_));

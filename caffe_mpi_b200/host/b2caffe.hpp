@@ -276,10 +276,12 @@ class ParamArena {
   float* data() const { return data_; }
   float* diff() const { return diff_; }
   float* history() const { return hist_; }
+  bool diff_is_nccl_memory() const { return diff_nccl_; }
  private:
   vector<size_t> offset_, count_;
   size_t total_ = 0;
   float *data_ = nullptr, *diff_ = nullptr, *hist_ = nullptr;
+  bool diff_nccl_ = false;
 };
 
 // ---------------------------------------------------------------------------------------------- solver

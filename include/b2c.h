@@ -252,6 +252,12 @@ int b2c_comm_nranks(const b2c_comm* c);
 int b2c_comm_bcast(b2c_comm* c, float* buf, size_t count, int root, void* stream);
 /* in-place ncclSum allreduce of a diff bucket (P2PSync::allreduce_bucket, parallel.cpp:245-253) */
 int b2c_comm_allreduce_sum(b2c_comm* c, float* buf, size_t count, void* stream);
+/* NVLS-capable buffers: ncclMemAlloc / ncclMemFree and ncclCommRegister (handles are released by b2c_comm_destroy).  An
+ * in-place allreduce on a registered ncclMemAlloc buffer can be reduced inside the NVSwitch without NCCL's staging copies.
+ * Environment: B2C_NCCL_MAX_CTAS / B2C_NCCL_MIN_CTAS set ncclConfig_t.maxCTAs / minCTAs of b2c_comm_init. */
+int b2c_comm_mem_alloc(void** ptr, size_t bytes);
+int b2c_comm_mem_free(void* ptr);
+int b2c_comm_register(b2c_comm* c, void* buf, size_t bytes);
 
 #ifdef __cplusplus
 }
