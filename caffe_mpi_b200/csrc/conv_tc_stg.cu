@@ -236,10 +236,12 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
         }
       }
       // byte offset of this row at tap offset 0 inside its image's box, plus the channel octet of this warp.  Box column 0
-      // is pixel max(first pixel of the segment - halo, 0) of the image: start columns are never negative (the TMA unit
-      // zero-fills past the image END; taps that reach before pixel 0 are masked rows, whatever they read is discarded)
+      // is pixel max(first pixel of the segment - halo, 0) of the image rounded DOWN to a multiple of 4: the innermost TMA
+      // coordinate has to be 16-byte aligned (an odd start column is an illegal-instruction fault, measured) and never
+      // negative; the TMA unit zero-fills past the image END; taps that reach before pixel 0 belong to masked rows, whatever
+      // they read is discarded
       const int pp_r = m0 + row - (n_first + seg_r) * p.HW;                       // this row's pixel inside its image
-      const int start_r = seg_r ? 0 : max(m0 - n_first * p.HW - p.halo, 0);
+      const int start_r = seg_r ? 0 : max((m0 - n_first * p.HW - p.halo) & ~3, 0);
       const uint32_t row_off = (uint32_t)((pp_r - start_r) * 4) + (uint32_t)(sub * 8) * (uint32_t)(BWT * 4);
       int g = 0, tap = 0;
       uint32_t src_base = 0;
@@ -328,7 +330,7 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
           else mbar_wait_backoff(bar_sempty + 8 * slot, ((u / NSLOT) & 1) ^ 1, 32);
           if (elect_one()) {
             arrive_expect_tx(bar_sfull + 8 * slot, S::SLOT_BYTES);
-            const int col0 = seg ? 0 : max(m0 - n_first * p.HW - p.halo, 0);   // columns past the image end read as zero
+            const int col0 = seg ? 0 : max((m0 - n_first * p.HW - p.halo) & ~3, 0);   // 16-byte aligned; columns past the image end read as zero
             tma_load_3d(slot_addr(slot), &map_x, bar_sfull + 8 * slot, col0, g * CB, n_first + seg);
           }
           __syncwarp();
@@ -513,7 +515,7 @@ static bool stg_geom(const ConvShape& s, int op, StgGeom* g) {
   const int taps = s.kh * s.kw;
   if (taps > stg::MAX_TAPS) return false;
   const int halo = s.ph * s.W + s.pw;
-  const int need = 128 + 2 * halo;                   // staged pixels per channel
+  const int need = 128 + 2 * halo + 3;               // staged pixels per channel (+3: the box start is rounded down to 16 bytes)
   const int bwt = need <= 128 ? 128 : need <= 160 ? 160 : need <= 192 ? 192 : need <= 256 ? 256 : 0;   // TMA boxes are <= 256 wide
   if (!bwt) return false;
   if (g) {

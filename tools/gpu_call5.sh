@@ -4,6 +4,8 @@ cd "$(dirname "$0")/.."
 timeout 200 python tools/stg_debug.py > gpurun_out/c5_debug.log 2>&1
 B2C_STG_DBG=1 timeout 200 python tools/stg_debug.py > gpurun_out/c5_debug_nostore.log 2>&1
 timeout 200 python tools/stg_debug.py 2 32 12 12 32 3 1 >> gpurun_out/c5_debug.log 2>&1
+timeout 200 python tools/stg_debug.py 5 32 10 14 48 5 2 >> gpurun_out/c5_debug.log 2>&1
+timeout 200 python tools/stg_debug.py 4 128 28 28 128 3 1 >> gpurun_out/c5_debug.log 2>&1
 if grep -q "raised\|timeouts recorded: [1-9-]" gpurun_out/c5_debug.log; then
   timeout 300 compute-sanitizer --tool memcheck python tools/stg_debug.py 2 32 12 12 32 3 1 > gpurun_out/c5_sanitizer.log 2>&1
   echo "debug failed"; exit 0
