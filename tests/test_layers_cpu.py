@@ -222,3 +222,32 @@ def test_dropout_mask_statistics_and_scale():
     assert abs((m3 > 0).mean() - 0.7) < 0.01 and abs(m3.max() - 1 / 0.7) < 1e-6
     assert np.array_equal(m3[5:100], lo.dropout_mask(95, 0.3, 7, offset=15))        # counter based: offset + i
     assert abs(m3.mean() - 1.0) < 0.01                                              # expectation preserved
+
+
+def test_net_oracle_inception_style_finite_differences():
+    """tests/netoracle.py with the AlexNet / GoogLeNet layer kinds (grouped conv, LRN, Concat, Dropout, two weighted losses): the
+    analytic gradient of every parameter blob against central differences of 1.0 * loss + 0.3 * aux loss -- what the reference's
+    GradientChecker does per layer (test_gradient_check_util.hpp), here through the whole graph."""
+    import netoracle as no
+    spec = no.mini_inception()
+    shapes = no.param_shapes(spec)
+    rng = np.random.default_rng(1)
+    params = [(rng.standard_normal(s) * 0.3).astype(np.float32) for _, _, s in shapes]
+    data = rng.standard_normal(spec[0]["shape"]).astype(np.float32)
+    label = rng.integers(0, 10, spec[0]["shape"][0]).astype(np.float32)
+    _, grads, _, _ = no.forward_backward(spec, params, data, label)
+
+    def total(ps):
+        l, _, vv, _ = no.forward_backward(spec, ps, data, label)
+        return float(l) + 0.3 * float(vv["aux/loss1"])
+
+    eps = 3e-3
+    for i, g in enumerate(grads):
+        idx = np.unravel_index(np.argmax(np.abs(g)), g.shape)
+        p2 = [q.copy() for q in params]
+        p2[i][idx] += eps
+        up = total(p2)
+        p2[i][idx] -= 2 * eps
+        dn = total(p2)
+        fd = (up - dn) / (2 * eps)
+        assert abs(fd - g[idx]) <= 2e-3 * max(1.0, abs(g[idx])), (shapes[i], fd, g[idx])

@@ -183,3 +183,33 @@ def test_fusion_pass_is_bitwise_neutral(rng):
     assert a.loss() == b.loss()
     for i in range(a.num_params()):
         assert np.array_equal(a.get_param(i, 0).view(np.uint32), b.get_param(i, 0).view(np.uint32)), i
+
+
+def test_inception_style_net_matches_oracle(rng):
+    """The layer kinds AlexNet / GoogLeNet / VGG-16 add (grouped conv, LRN, Concat, Dropout, two losses with loss_weight 0.3 / 1)
+    through TrainNet against the net oracle: both losses, blobs on every branch, every parameter gradient (the auxiliary
+    classifier's 0.3 included), then two SGD steps with fresh dropout masks per iteration."""
+    spec = no.mini_inception()
+    t, params, data, label = make_trainer(spec, rng)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= TOL * abs(ref_loss)
+    assert abs(float(t.get_blob("aux/loss1")[0]) - float(v["aux/loss1"])) <= TOL * abs(float(v["aux/loss1"]))
+    for name in ("conv1", "norm1", "pool1", "inc/3x3", "inc/5x5", "inc/pool_proj", "inc/output", "aux/fc", "pool5", "cls"):
+        assert rel(t.get_blob(name), v[name]) <= TOL, name
+    for name in ("cls", "aux/cls", "inc/output", "pool1", "norm1"):
+        assert rel(t.get_blob(name, diff=True), d[name]) <= TOL, name
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g, floor) <= TOL, no.param_shapes(spec)[i]
+    # two iterations of Solver::Step: the dropout streams advance by the blob size per iteration
+    p, h = [q.copy() for q in params], [np.zeros_like(q) for q in params]
+    import oracle
+    for it in range(2):
+        _, g, _, _ = no.forward_backward(spec, p, data, label, iteration=it + 1)     # iteration 0 was the forward_backward above
+        for i in range(len(p)):
+            _, w, hh = oracle.sgd_update(g[i], p[i], h[i], 0.9, 0.05, 0.0005)
+            p[i], h[i] = w.reshape(p[i].shape), hh.reshape(p[i].shape)
+        t.step(1)
+    for i in range(len(p)):
+        assert rel(t.get_param(i, 0), p[i]) <= 2 * TOL, i
