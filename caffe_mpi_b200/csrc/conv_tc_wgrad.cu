@@ -6,8 +6,8 @@
 // GEMM view: M = output channels of one group (tile 128), N = K_dim = (C/g)*kh*kw (tile N_TILE), the
 // reduction runs over q = N*Ho*Wo, which is the CONTIGUOUS axis of both operands in NCHW memory, so both
 // smem tiles are filled "lanes along K": dY with 128-bit loads, X through the im2col gather.  The
-// reduction is split across CTAs (grid.x); partial tiles go to a workspace and a second, deterministic
-// kernel adds them to dW in split order (the reference accumulates image by image, also a fixed order).
+// reduction is split across CTAs (grid.x); partial tiles go to a workspace and the tile's CTAs then add them
+// to dW in split order (splitk_fused_reduce; the reference accumulates image by image, also a fixed order).
 #include <cuda.h>
 #include <stdlib.h>
 #include "b2c_common.cuh"
@@ -29,6 +29,8 @@ struct WgradParams {
   int kb_per_split;  // k-blocks (of 32 q) per split
   int splits;
   float* out;        // splits == 1: dW (accumulated);  else partials [splits][O*Kd] (overwritten)
+  float* grad;       // splits > 1: the gradient blob the fused reduction accumulates into
+  unsigned int* counters;   // splits > 1: one zeroed arrival counter per output tile
   long long* prof;   // optional cycle counters from CTA (0,0,0) (B2C_PROF=1)
 };
 
@@ -43,6 +45,41 @@ struct WgradSmem {
   static constexpr uint32_t TAB_OFF = BAR_OFF + 256;
   static constexpr uint32_t TOTAL = TAB_OFF + TABLE;
 };
+
+// ---- split-K reduction fused into the tile's own CTAs ---------------------------------------------------------------------
+// Round 1 ran a second kernel per layer (wgrad_reduce_kernel, 53 launches / 0.58 ms per ResNet-50 step).  Here the `splits` CTAs
+// of an output tile meet at a counter in the workspace once their partial tiles are in global memory -- the whole grid is one
+// wave by construction (wgrad_plan: never more CTAs than SMs), so every CTA of the tile is resident -- and then each CTA adds
+// up its 1/splits slice of the tile over the partials IN SPLIT ORDER and accumulates it into dW: the summation order of every
+// element is fixed, so the result is bit-reproducible and equal to what the separate kernel produced.
+__device__ __forceinline__ void splitk_fused_reduce(const float* __restrict__ part, float* __restrict__ dw, unsigned int* counter,
+                                                    int split, int splits, long long plane, long long tile_base, int ld, int nrows, int ncols) {
+  __syncthreads();                                   // this CTA's partial tile is complete (epilogue warps)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen < (unsigned)splits) {
+        __nanosleep(64);
+        if (clock64() - t0 > tc::MBAR_TIMEOUT_CYCLES) asm volatile("trap;");
+      }
+    } while (seen < (unsigned)splits);
+  }
+  __syncthreads();
+  const int total = nrows * ncols;
+  const int per = (total + splits - 1) / splits;
+  const int e_end = min(total, (split + 1) * per);
+  for (int e = split * per + (int)threadIdx.x; e < e_end; e += (int)blockDim.x) {
+    const int r = e / ncols, c = e - r * ncols;
+    const long long idx = tile_base + (long long)r * ld + c;
+    float acc = 0.0f;
+    for (int s2 = 0; s2 < splits; ++s2) acc += __ldcg(part + (long long)s2 * plane + idx);
+    dw[idx] += acc;
+  }
+}
 
 template <int N_TILE, bool SPLIT, bool X1X1>
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -345,20 +382,15 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams p) {
     }
     if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) { p.prof[16] = clock64() - m_t0; p.prof[17] = mw; p.prof[18] = mi; }
   }
+  if (p.splits > 1) {
+    const int tile_id = blockIdx.z * gridDim.y + blockIdx.y;
+    splitk_fused_reduce(p.out, p.grad, p.counters + tile_id, split, p.splits, (long long)p.O * p.Kd,
+                        ((long long)g * p.Og + m0) * p.Kd + n0, p.Kd, min(128, p.Og - m0), min(N_TILE, p.Kd - n0));
+  }
   __syncthreads();
   if (warp == WG_YW + WG_GW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, N_TILE);
-  }
-}
-
-// dw[i] += sum_s part[s][i], s ascending (deterministic)
-__global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ dw) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float acc = 0.0f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(part + (long long)s * n + i);
-    dw[i] += acc;
   }
 }
 
@@ -384,6 +416,8 @@ struct WgradTmaParams {
   long long nkb_total;   // N * cpi
   int kb_per_split, splits;
   float* out;            // splits == 1: dW (accumulated);  else partials [splits][O*C] (overwritten)
+  float* grad;           // splits > 1: the gradient blob the fused reduction accumulates into
+  unsigned int* counters;   // splits > 1: one zeroed arrival counter per output tile
 };
 
 template <int N_TILE>
@@ -549,6 +583,11 @@ wgrad1x1_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_const
       __syncwarp();
     }
   }
+  if (p.splits > 1) {
+    const int tile_id = blockIdx.z * gridDim.y + blockIdx.y;
+    splitk_fused_reduce(p.out, p.grad, p.counters + tile_id, split, p.splits, (long long)p.O * p.C, (long long)m0 * p.C + n0, p.C,
+                        min(128, p.O - m0), min(N_TILE, p.C - n0));
+  }
   __syncthreads();
   if (warp == WT_CW + 1) {
     tc_fence_after();
@@ -588,18 +627,19 @@ static WgradPlan wgrad_tma_plan(const ConvShape& s, int* cpi_out);
 static bool wgrad_tma_shape_ok(const ConvShape& s);
 static bool wgrad_compact_shape_ok(const ConvShape& s);
 static ConvShape wgrad_compact_dense_shape(const ConvShape& s);
+constexpr size_t WG_COUNTER_BYTES = 1024;      // arrival counters of the fused split-K reduction: one u32 per output tile (<= #SMs)
 size_t tc_wgrad_workspace(const ConvShape& s) {
   const WgradPlan pl = wgrad_plan(s);
-  size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+  size_t need = pl.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
   if (wgrad_tma_shape_ok(s)) {                       // the TMA path of 1x1 layers plans its own split count
     const WgradPlan pt = wgrad_tma_plan(s, nullptr);
-    const size_t nt = pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    const size_t nt = pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
     if (nt > need) need = nt;
   }
   if (wgrad_compact_shape_ok(s)) {                   // strided 1x1: compacted input + the TMA path's partials
     const ConvShape d = wgrad_compact_dense_shape(s);
     const WgradPlan pt = wgrad_tma_plan(d, nullptr);
-    const size_t nt = (pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0) + 256 +
+    const size_t nt = (pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0) + 256 +
                       sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
     if (nt > need) need = nt;
   }
@@ -680,9 +720,12 @@ static int launch_conv_tc_wgrad_tma(const ConvShape& s, const float* x, const fl
   WgradTmaParams p;
   p.O = s.O; p.C = s.C; p.cpi = cpi; p.nkb_total = (long long)s.N * cpi;
   p.kb_per_split = pl.kb_per_split; p.splits = pl.splits;
-  const size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.C : 0;
+  const size_t need = pl.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * s.O * s.C : 0;
   if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "wgrad (tma): workspace too small");
-  p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
+  p.out = pl.splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(ws) + WG_COUNTER_BYTES) : dw;
+  p.grad = dw;
+  p.counters = static_cast<unsigned int*>(ws);
+  if (pl.splits > 1) B2C_CUDA_OK(cudaMemsetAsync(ws, 0, WG_COUNTER_BYTES, st));
   alignas(64) CUtensorMap mdy, mx;
   int rc = wg_make_map(&mdy, dy, P, s.O, s.N, 128);
   if (rc) return rc;
@@ -695,11 +738,6 @@ static int launch_conv_tc_wgrad_tma(const ConvShape& s, const float* x, const fl
     default: rc = launch_wgrad_tma_inst<32>(p, mdy, mx, st); break;
   }
   if (rc) return rc;
-  if (pl.splits > 1) {
-    const long long n = (long long)s.O * s.C;
-    wgrad_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(static_cast<const float*>(ws), pl.splits, n, dw);
-    B2C_POST_LAUNCH();
-  }
   return B2C_OK;
 }
 
@@ -768,7 +806,7 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
   if (math == B2C_MATH_FP32 && wgrad_compact_shape_ok(s) && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0 && ws) {
     const ConvShape d = wgrad_compact_dense_shape(s);
     const WgradPlan pt = wgrad_tma_plan(d, nullptr);
-    const size_t part = pt.splits > 1 ? sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    const size_t part = pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
     const size_t xoff = (part + 255) & ~(size_t)255;
     const size_t xbytes = sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
     if (ws_bytes < xoff + xbytes) return fail(B2C_ERR_WORKSPACE, "wgrad (compact): workspace too small");
@@ -793,9 +831,12 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
   if (prof_on < 0) { const char* e = getenv("B2C_PROF"); prof_on = e ? atoi(e) : 0; if (prof_on) cudaMalloc(&prof_buf, 32 * sizeof(long long)); }
   p.prof = prof_on ? prof_buf : nullptr;
   if (prof_on) cudaMemsetAsync(prof_buf, 0, 32 * sizeof(long long), st);
-  const size_t need = pl.splits > 1 ? sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+  const size_t need = pl.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
   if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "wgrad: workspace too small");
-  p.out = pl.splits > 1 ? static_cast<float*>(ws) : dw;
+  p.out = pl.splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(ws) + WG_COUNTER_BYTES) : dw;
+  p.grad = dw;
+  p.counters = static_cast<unsigned int*>(ws);
+  if (pl.splits > 1) B2C_CUDA_OK(cudaMemsetAsync(ws, 0, WG_COUNTER_BYTES, st));
   int rc;
   switch (pl.n_tile) {
     case 256: rc = launch_wgrad_n<256>(p, s.G, math, s.is_1x1, st); break;
@@ -809,11 +850,6 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
     cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[wprof] N_TILE=%d splits=%d nkb=%lld | dY-prod: loop=%lld wait_empty=%lld store=%lld wait_tmem=%lld epilogue=%lld | X-prod: loop=%lld wait_empty=%lld store=%lld | mma: total=%lld wait_full=%lld issue=%lld\n",
             pl.n_tile, pl.splits, h[5], h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[16], h[17], h[18]);
-  }
-  if (pl.splits > 1) {
-    const long long n = (long long)s.O * s.Kd;
-    wgrad_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(static_cast<const float*>(ws), pl.splits, n, dw);
-    B2C_POST_LAUNCH();
   }
   return B2C_OK;
 }
