@@ -200,6 +200,24 @@ relu_bwd2_kernel(size_t n, int vec, const float* __restrict__ dy, const float* _
   }
 }
 
+// ---- Accuracy (src/caffe/layers/accuracy_layer.cpp:44-100): a sample counts when its label is among the top_k scores; ties are
+// ordered like std::greater<pair<float,int>> (equal scores: the HIGHER class index ranks first).  One warp per sample.
+__global__ void __launch_bounds__(256)
+accuracy_kernel(int N, int C, int top_k, const float* __restrict__ scores, const float* __restrict__ labels, unsigned int* __restrict__ hits) {
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const int lab = (int)labels[warp];
+  if (lab < 0 || lab >= C) return;                       // the reference DCHECKs the range; out-of-range labels never hit
+  const float* z = scores + (size_t)warp * C;
+  const float zl = z[lab];
+  int above = 0;
+  for (int j = lane; j < C; j += 32) { const float v = z[j]; above += (v > zl || (v == zl && j > lab)) ? 1 : 0; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+  if (lane == 0 && above < top_k) atomicAdd(hits, 1u);
+}
+__global__ void accuracy_finish_kernel(const unsigned int* hits, int N, float* acc) { *acc = (float)*hits / (float)N; }
+
 // the statistics kernel of layers.cu (same launch for the fused and the unfused forward)
 int launch_bn_stats(int N, int C, int S, const float* x, float eps, float maf, int first, float* mean, float* invstd, float* run_mean,
                     float* run_var, bool vec, void* stream);
@@ -299,6 +317,20 @@ extern "C" int b2c_relu_backward2(size_t n, const float* dy, const float* y, flo
   if (!n) return B2C_OK;
   const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx_a) | reinterpret_cast<uintptr_t>(dx_b)) & 15) == 0;
   relu_bwd2_kernel<<<grid_for(al ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(n, al ? 1 : 0, dy, y, dx_a, dx_b);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+// accuracy = (#samples whose label is in the top_k scores) / N; `scratch` is 4 bytes of device memory
+extern "C" int b2c_accuracy(int N, int C, int top_k, const float* scores, const float* labels, float* accuracy, void* scratch, void* stream) {
+  FNEED(scores && labels && accuracy && scratch && N > 0 && C > 0 && top_k > 0 && top_k <= C, "b2c_accuracy: bad argument");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  cudaStream_t st = as_stream(stream);
+  B2C_CUDA_OK(cudaMemsetAsync(scratch, 0, 4, st));
+  accuracy_kernel<<<(N * 32 + 255) / 256, 256, 0, st>>>(N, C, top_k, scores, labels, static_cast<unsigned int*>(scratch));
+  B2C_POST_LAUNCH();
+  accuracy_finish_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned int*>(scratch), N, accuracy);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }

@@ -345,6 +345,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       }
       tops.push_back(s);
     } else if (type == "SoftmaxWithLoss" || type == "EuclideanLoss" || type == "SigmoidCrossEntropyLoss" || type == "Accuracy") {
+      if (const PMessage* ap = lp.sub("accuracy_param")) L.accuracy_top_k = (int)ap->integer("top_k", 1);
       for (size_t i = 0; i < L.param.top.size(); ++i) tops.push_back({});
     } else if (type == "ReLU" && (L.relu_slope = (float)(lp.sub("relu_param") ? lp.sub("relu_param")->num("negative_slope", 0.0) : 0.0), false)) {
     } else if ((type == "LRN" || type == "Dropout") && ([&] {

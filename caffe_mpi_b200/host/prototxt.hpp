@@ -61,6 +61,7 @@ struct NetLayer {                       // one LayerParameter after phase filter
   float dropout_ratio = 0.5f;           // DropoutParameter.dropout_ratio
   std::vector<float> loss_weight;        // LayerParameter.loss_weight (one per top)
   int concat_axis = 1;
+  int accuracy_top_k = 1;               // AccuracyParameter.top_k
   int batch_size = 0, crop_size = 0;    // Data layers
   std::vector<int> input_shape;         // Input / DummyData layers
 };

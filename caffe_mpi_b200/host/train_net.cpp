@@ -217,6 +217,12 @@ void SoftmaxWithLossLayer::Backward_gpu(const vector<Blob*>&, const vector<bool>
                                       b[0]->mutable_gpu_diff(), S()));
 }
 
+// ================================================================================================ Accuracy
+void AccuracyLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
+  B2C_CHECK(b2c_accuracy(b[0]->shape(0), (int)b[0]->count(1), top_k_, b[0]->gpu_data(), b[1]->gpu_data(), t[0]->mutable_gpu_data(),
+                         hits_.mutable_gpu_data(), S()));
+}
+
 // ================================================================================================ synthetic data
 SyntheticDataLayer::~SyntheticDataLayer() { if (host_) cudaFreeHost(host_); }
 void SyntheticDataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& t) {
@@ -244,7 +250,6 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
   for (size_t li = 0; li < net.layers().size(); ++li) {
     const NetLayer& L = net.layers()[li];
     const string& type = L.param.type;
-    if (type == "Accuracy") continue;                       // TEST-phase metric, no gradient, not on the training path
     Node node;
     for (auto& bn : L.param.bottom) {
       auto it = blobs_.find(bn);
@@ -286,6 +291,7 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       if (!L.loss_weight.empty()) sl->set_loss_weight(L.loss_weight[0]);      // GoogLeNet's auxiliary classifiers: 0.3
       layer.reset(sl);
     }
+    else if (type == "Accuracy") layer.reset(new AccuracyLayer(L.param, L.accuracy_top_k));     // forward only, no gradient
     else if (type == "LRN") {
       B2_CHECK(L.lrn_region == 0, "TrainNet: LRN WITHIN_CHANNEL is not built (the BASELINE nets use ACROSS_CHANNELS)");
       layer.reset(new LRNLayer(L.param, L.lrn_size, L.lrn_alpha, L.lrn_beta, L.lrn_k));
@@ -318,7 +324,7 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       nb |= bneed;
     }
     for (int k = 0; k < node.num_params; ++k) nb |= specs[node.first_param + k].lr_mult != 0.f;
-    if (layer.get() == data_) nb = false;
+    if (layer.get() == data_ || type == "Accuracy") nb = false;      // Accuracy: forward-only metric (accuracy_layer.hpp: "cannot backpropagate")
     node.need_backward = nb;
     for (auto& tn : L.param.top) need[tn] = nb;
     if (type == "SoftmaxWithLoss") loss_blob_ = node.top[0];

@@ -146,6 +146,21 @@ class SoftmaxWithLossLayer : public LayerBase {
   float loss_weight_ = 1.f;
 };
 
+class AccuracyLayer : public LayerBase {       // forward only (accuracy_layer.cpp); top[0] is a scalar
+ public:
+  AccuracyLayer(const LayerParameter& p, int top_k) : LayerBase(p), top_k_(top_k) {}
+  const char* type() const override { return "Accuracy"; }
+  void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override {
+    B2_CHECK(top_k_ <= (int)(b[0]->count() / b[1]->count()), "top_k must be less than or equal to the number of classes.");
+    t[0]->Reshape({1}); hits_.Reshape({1});
+  }
+ protected:
+  void Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) override;
+  void Backward_gpu(const vector<Blob*>&, const vector<bool>&, const vector<Blob*>&) override {}   // "Accuracy cannot backpropagate"
+  int top_k_;
+  Blob hits_;
+};
+
 // Synthetic in-memory source standing in for DataLayer: N(0,1) images from mt19937(seed), uniform labels.
 class SyntheticDataLayer : public LayerBase {
  public:

@@ -183,6 +183,9 @@ int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float*
                                float* save_mean, float* save_invstd, float* y, int relu, void* stream);
 int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                           const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream);
+/* AccuracyLayer::Forward (accuracy_layer.cpp:44-100), labels as float class ids, ties ranked like the reference's
+ * std::greater<pair<score, index>>; `scratch`: 4 bytes of device memory. */
+int b2c_accuracy(int N, int C, int top_k, const float* scores, const float* labels, float* accuracy, void* scratch, void* stream);
 int b2c_add_relu(size_t n, const float* a, const float* b, float* y, void* stream);
 int b2c_relu_backward2(size_t n, const float* dy, const float* y, float* dx_a, float* dx_b, void* stream);
 int b2c_pool_forward(int method, int NC, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, const float* x,

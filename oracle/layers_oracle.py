@@ -169,3 +169,13 @@ def dropout_mask(n, ratio, seed, offset=0):
     u = (z >> np.uint64(40)).astype(np.uint32)
     thr = np.uint32(int(float(np.float32(ratio)) * 16777216.0))
     return np.where(u >= thr, np.float32(1.0) / (np.float32(1.0) - np.float32(ratio)), np.float32(0.0)).astype(np.float32)
+
+
+# AccuracyLayer::Forward_cpu, src/caffe/layers/accuracy_layer.cpp:44-100: partial_sort of (score, class) pairs with
+# std::greater, the label must be among the first top_k; returns hits / N
+def accuracy(scores, labels, top_k=1):
+    hits = 0
+    for i in range(scores.shape[0]):
+        pairs = sorted(((float(v), j) for j, v in enumerate(scores[i])), reverse=True)
+        hits += int(int(labels[i]) in [j for _, j in pairs[:top_k]])
+    return np.float32(hits / scores.shape[0])

@@ -52,3 +52,18 @@ def test_dropout_mask_is_bit_exact_and_mul(rng, n, ratio, seed, offset):
     X, Y = dev(x), torch.empty(n, device="cuda")
     assert L.b2c_mul(n, ptr(X), ptr(M), ptr(Y), None) == 0
     assert np.array_equal(Y.cpu().numpy(), x * m)
+
+
+@pytest.mark.parametrize("N,Cc,k", [(64, 1000, 1), (64, 1000, 5), (7, 10, 3), (33, 17, 17)])
+def test_accuracy_top_k(rng, N, Cc, k):
+    from caffe_mpi_b200 import capi
+    L = capi.lib()
+    z = rng.standard_normal((N, Cc)).astype(np.float32)
+    z[:, : Cc // 2] = np.round(z[:, : Cc // 2] * 2) / 2          # ties: equal scores rank the higher class index first
+    lab = rng.integers(0, Cc, N).astype(np.float32)
+    Z, LB = dev(z), dev(lab)
+    acc, scratch = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    L.b2c_accuracy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert L.b2c_accuracy(N, Cc, k, ptr(Z), ptr(LB), ptr(acc), ptr(scratch), None) == 0
+    torch.cuda.synchronize()
+    assert float(acc.item()) == float(lo.accuracy(z, lab, k))
