@@ -515,7 +515,7 @@ static bool stg_geom(const ConvShape& s, int op, StgGeom* g) {
   const int taps = s.kh * s.kw;
   if (taps > stg::MAX_TAPS) return false;
   const int halo = s.ph * s.W + s.pw;
-  const int need = 128 + 2 * halo + 3;               // staged pixels per channel (+3: the box start is rounded down to 16 bytes)
+  const int need = 128 + 2 * halo + ((4 - halo % 4) % 4);   // staged pixels per channel (+ what rounding the box start down to 16 bytes costs)
   const int bwt = need <= 128 ? 128 : need <= 160 ? 160 : need <= 192 ? 192 : need <= 256 ? 256 : 0;   // TMA boxes are <= 256 wide
   if (!bwt) return false;
   if (g) {

@@ -102,10 +102,11 @@ bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, co
   FPlaneCursor cur;
   unsigned i = lo + threadIdx.x;
   if (i < hi) cur.init(i, units);
-  auto acc = [&](float d, float xv, float& sa, float& sb) {
+  // masked upstream gradient and recomputed x_norm of one element
+  auto prep = [&](float& d, float xv) {
     const float xn = bn_xn(xv, m, is);
-    if (RELU && !(bn_y(xn, g, bt, affine) > 0.f)) d = 0.f;
-    sa = fmaf(d, xn, sa); sb += d;
+    if (RELU) d = d * (bn_y(xn, g, bt, affine) > 0.f ? 1.f : 0.f);      // relu_bwd_kernel's own expression (sign of zero included)
+    return xn;
   };
   for (; i < hi; i += U * FB_THREADS) {
     size_t off[U];
@@ -124,13 +125,18 @@ bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, co
         v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(m, m, m, m);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) { acc(d[u].x, v[u].x, a, b); acc(d[u].y, v[u].y, a2, b2); acc(d[u].z, v[u].z, a, b); acc(d[u].w, v[u].w, a2, b2); }
+      for (int u = 0; u < U; ++u) {
+        // the accumulation order of layers.cu's bn_channel_partial<MODE 1>, so that fused == unfused bit for bit
+        const float nx = prep(d[u].x, v[u].x), ny = prep(d[u].y, v[u].y), nz = prep(d[u].z, v[u].z), nw = prep(d[u].w, v[u].w);
+        a = fmaf(d[u].x, nx, a); a2 = fmaf(d[u].y, ny, a2); a = fmaf(d[u].z, nz, a); a2 = fmaf(d[u].w, nw, a2);
+        b += d[u].x + d[u].y; b2 += d[u].z + d[u].w;
+      }
     } else {
       float d[U], v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) { d[u] = ok[u] ? dy[off[u]] : 0.f; v[u] = ok[u] ? x[off[u]] : m; }
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc(d[u], v[u], a, b);
+      for (int u = 0; u < U; ++u) { const float xn = prep(d[u], v[u]); a = fmaf(d[u], xn, a); b += d[u]; }
     }
   }
   a += a2; b += b2;
@@ -163,7 +169,7 @@ bn_bwd_dx_fused_kernel(size_t total_units, int C, int S, float inv_cnt, const fl
     const float gi = g * is, mdy = sum_dy[cur.c] * inv_cnt, mdx = sum_dy_xn[cur.c] * inv_cnt;
     auto one = [&](float d, float xv) {
       const float xn = bn_xn(xv, m, is);
-      if (RELU && !(bn_y(xn, g, bt, affine) > 0.f)) d = 0.f;
+      if (RELU) d = d * (bn_y(xn, g, bt, affine) > 0.f ? 1.f : 0.f);
       return gi * (d - mdy - xn * mdx);
     };
     if (VEC) {
