@@ -197,6 +197,15 @@ class ConvDesc:
         check(lib().b2c_conv_backward_data(self._h, _p(dy), _p(w), _p(dx), ws, n, _stream(stream)))
         return dx
 
+    def backward_data_accumulate_supported(self):
+        return bool(lib().b2c_conv_backward_data_accumulate_supported(self._h))
+
+    def backward_data_accumulate(self, dy, w, dx, stream=None):
+        """dx += bottom gradient (the fan-out accumulation of Net::Backward folded into the kernel's TMA reduce-add store)."""
+        ws, n = self._workspace(OP_BACKWARD_DATA, dy)
+        check(lib().b2c_conv_backward_data_accumulate(self._h, _p(dy), _p(w), _p(dx), ws, n, _stream(stream)))
+        return dx
+
     def backward_filter(self, x, dy, dw, stream=None):
         ws, n = self._workspace(OP_BACKWARD_FILTER, x)
         check(lib().b2c_conv_backward_filter(self._h, _p(x), _p(dy), _p(dw), ws, n, _stream(stream)))

@@ -64,7 +64,7 @@ bool tc_stg_prep_entry(const ConvShape&, int op, const float* w, void* dst, Prep
 bool tc_stg_supported(const ConvShape&, int op);
 size_t tc_stg_workspace(const ConvShape&, int op);
 int launch_conv_tc_stg(const ConvShape&, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
-                       size_t ws_bytes, const void* prepared, cudaStream_t);
+                       size_t ws_bytes, const void* prepared, bool accumulate, cudaStream_t);
 bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K);
 int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta,
                     float* C, int math, cudaStream_t);
@@ -221,7 +221,7 @@ extern "C" int b2c_conv_forward(const b2c_conv_desc* d, const float* x, const fl
     return B2C_OK;
   }
   if (use_staged(d, B2C_OP_FORWARD) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0)
-    return launch_conv_tc_stg(s, B2C_OP_FORWARD, x, w, bias, y, ws, ws_bytes, prepared_filter(d, B2C_OP_FORWARD), st);
+    return launch_conv_tc_stg(s, B2C_OP_FORWARD, x, w, bias, y, ws, ws_bytes, prepared_filter(d, B2C_OP_FORWARD), false, st);
   if (tc_conv_supported(s, B2C_OP_FORWARD) && d->algo != B2C_ALGO_SIMT)
     return launch_conv_tc(s, B2C_OP_FORWARD, gather_math(d), x, w, bias, y, ws, ws_bytes, staged_geometry_only(d, B2C_OP_FORWARD) ? nullptr : prepared_filter(d, B2C_OP_FORWARD), st);
   return launch_conv_fwd_simt(s, x, w, bias, y, st);
@@ -250,10 +250,27 @@ extern "C" int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, c
     return B2C_OK;
   }
   if (use_staged(d, B2C_OP_BACKWARD_DATA) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0)
-    return launch_conv_tc_stg(s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, prepared_filter(d, B2C_OP_BACKWARD_DATA), st);
+    return launch_conv_tc_stg(s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, prepared_filter(d, B2C_OP_BACKWARD_DATA), false, st);
   if (tc_conv_supported(s, B2C_OP_BACKWARD_DATA) && d->algo != B2C_ALGO_SIMT)
     return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, gather_math(d), dy, w, nullptr, dx, ws, ws_bytes, staged_geometry_only(d, B2C_OP_BACKWARD_DATA) ? nullptr : prepared_filter(d, B2C_OP_BACKWARD_DATA), st);
   return launch_conv_dgrad_simt(s, dy, w, dx, st);
+}
+
+// dx += dgrad(dy, w): the accumulation Net::Backward performs where a blob fans out (SplitLayer::Backward in the reference),
+// folded into the kernel's TMA reduce-add store.  Only the staged kernel has it; the caller asks first.
+extern "C" int b2c_conv_backward_data_accumulate_supported(const b2c_conv_desc* d) {
+  return d && use_staged(d, B2C_OP_BACKWARD_DATA) ? 1 : 0;
+}
+extern "C" int b2c_conv_backward_data_accumulate(const b2c_conv_desc* d, const float* dy, const float* w, float* dx, void* ws,
+                                                 size_t ws_bytes, void* stream) {
+  if (!d || !dy || !w || !dx) return fail(B2C_ERR_INVALID, "b2c_conv_backward_data_accumulate: null pointer");
+  REQUIRE_DEVICE();
+  if (!use_staged(d, B2C_OP_BACKWARD_DATA) || ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u))
+    return fail(B2C_ERR_INVALID, "b2c_conv_backward_data_accumulate: not available for this layer (see ..._accumulate_supported)");
+  const size_t need = b2c_conv_workspace_bytes(d, B2C_OP_BACKWARD_DATA);
+  if (!prepared_filter(d, B2C_OP_BACKWARD_DATA) && (ws_bytes < need || (need && !ws))) return fail(B2C_ERR_WORKSPACE, "backward_data workspace too small");
+  return launch_conv_tc_stg(d->s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, prepared_filter(d, B2C_OP_BACKWARD_DATA), true,
+                            as_stream(stream));
 }
 
 extern "C" int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, const float* dy, float* dw, void* ws,

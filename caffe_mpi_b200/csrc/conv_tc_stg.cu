@@ -73,6 +73,7 @@ struct Params {
   float* out;              // [Nimg, Ntot, H, W]: the epilogue's st.global path (tiles that span two images)
   int m_tiles, n_tiles, total_tiles;
   int dbg;                 // B2C_STG_DBG bit 0: never use TMA stores (st.global epilogue for every tile)
+  int accumulate;          // out += result instead of out = result (TMA reduce-add store; the fan-out accumulation of Net::Backward)
   long long* prof;
 };
 
@@ -125,6 +126,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// out[box] += smem tile: the TMA unit's reduction store (fp32 add in L2), same clipping as the plain store
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -421,7 +427,10 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
         if (nseg == 1 && !(p.dbg & 1)) {
           // the tile lies inside one image: box column 0 = tile row 0 = pixel m0 - n*HW >= 0; columns past the image end
           // (last tile of an image, rows past the batch) and channels past Ntot are clipped by the TMA unit
-          if (issuer && elect_one()) tma_store_3d(&map_y, smem_u32(E), m0 - n_first * p.HW, n0 + c0, n_first);
+          if (issuer && elect_one()) {
+            if (p.accumulate) tma_reduce_add_3d(&map_y, smem_u32(E), m0 - n_first * p.HW, n0 + c0, n_first);
+            else tma_store_3d(&map_y, smem_u32(E), m0 - n_first * p.HW, n0 + c0, n_first);
+          }
         } else {
           // the tile spans two images (1 in 24 tiles at 56x56, 2 in 3 at 14x14): 16-byte st.global from the staged chunk
           const int mv = m0 + lane * 4;                    // this lane's 4 pixels (H*W % 4 == 0: never across an image end)
@@ -431,8 +440,12 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int ch = lg * 8 + q;
-              if (n0 + c0 + ch < p.Ntot)
-                *reinterpret_cast<float4*>(vbase + (size_t)ch * p.HW) = *reinterpret_cast<const float4*>(E + ch * 128 + lane * 4);
+              if (n0 + c0 + ch < p.Ntot) {
+                float4 t = *reinterpret_cast<const float4*>(E + ch * 128 + lane * 4);
+                float4* dst = reinterpret_cast<float4*>(vbase + (size_t)ch * p.HW);
+                if (p.accumulate) { const float4 o = *dst; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+                *dst = t;
+              }
             }
           }
         }
@@ -566,7 +579,7 @@ bool tc_stg_prep_entry(const ConvShape& s, int op, const float* w, void* dst, Pr
 
 // a = x (forward) or dy (dgrad); b = w; out = y or dx; `prepared`: filter already in GEMM layout, or null = prepass here
 int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
-                       size_t ws_bytes, const void* prepared, cudaStream_t st) {
+                       size_t ws_bytes, const void* prepared, bool accumulate, cudaStream_t st) {
   StgGeom g;
   if (!stg_geom(s, op, &g)) return fail(B2C_ERR_INVALID, "staged tcgen05 conv: shape not eligible");
   if (!prepared && (!ws || ws_bytes < tc_stg_workspace(s, op))) return fail(B2C_ERR_WORKSPACE, "staged tcgen05 conv: workspace too small");
@@ -585,6 +598,7 @@ int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* 
   p.halo = g.halo;
   p.bias = op == B2C_OP_FORWARD ? bias : nullptr;
   p.out = out;
+  p.accumulate = accumulate ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2C_STG_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   const int n_tile = g.Cout > 64 ? 128 : g.Cout > 32 ? 64 : 32;
   p.m_tiles = (p.Mtot + 127) / 128; p.n_tiles = (g.Cout + n_tile - 1) / n_tile; p.total_tiles = p.m_tiles * p.n_tiles;

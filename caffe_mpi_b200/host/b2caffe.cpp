@@ -411,7 +411,10 @@ void ConvolutionLayer::Backward_gpu(const vector<Blob*>& top, const vector<bool>
         const size_t need = b2c_conv_workspace_bytes(desc_, B2C_OP_BACKWARD_DATA);
         void* ws = need ? workspace(need) : nullptr;
         const size_t h = prof ? prof->begin(EventProfiler::DGRAD, st) : 0;
-        B2C_CHECK(b2c_conv_backward_data(desc_, dy, w, bottom[i]->mutable_gpu_diff(), ws, ws_bytes_, st));
+        if (i < accumulate_bottom_.size() && accumulate_bottom_[i])
+          B2C_CHECK(b2c_conv_backward_data_accumulate(desc_, dy, w, bottom[i]->mutable_gpu_diff(), ws, ws_bytes_, st));
+        else
+          B2C_CHECK(b2c_conv_backward_data(desc_, dy, w, bottom[i]->mutable_gpu_diff(), ws, ws_bytes_, st));
         if (prof) prof->end(h, st);
       }
       continue;

@@ -199,6 +199,10 @@ class LayerBase {
   virtual bool EqualNumBottomTopBlobs() const { return false; }
   virtual bool bias_term() const { return false; }
   bool param_propagate_down(int i) const { return i < (int)param_propagate_down_.size() ? param_propagate_down_[i] : false; }
+  // Net::Backward's fan-out accumulation folded into the layer: when true for bottom i, Backward ADDS its gradient to
+  // bottom[i]'s diff instead of overwriting it.  Only layers that answer SupportsBottomDiffAccumulate() may be asked to.
+  virtual bool SupportsBottomDiffAccumulate(int /*bottom*/) const { return false; }
+  void set_accumulate_bottom_diff(const vector<bool>& v) { accumulate_bottom_ = v; }
   void set_param_propagate_down(int i, bool v) { if ((int)param_propagate_down_.size() <= i) param_propagate_down_.resize(i + 1, true); param_propagate_down_[i] = v; }
 
  protected:
@@ -207,6 +211,7 @@ class LayerBase {
   LayerParameter layer_param_;
   vector<shared_ptr<Blob>> blobs_;
   vector<bool> param_propagate_down_;
+  vector<bool> accumulate_bottom_;       // per bottom; empty = overwrite everywhere (the reference's semantics)
 };
 
 class LayerRegistry {   // layer_factory.hpp:114-202
@@ -238,6 +243,7 @@ class ConvolutionLayer : public LayerBase {
   // b2c_conv_prepare_filters for all layers after every weight change; without it every Forward / Backward call re-derives
   // the GEMM-ordered filter copy itself.  Returns false when the layer has nothing to cache (CAFFE engine, SIMT, N-D).
   bool EnableFilterCache();
+  bool SupportsBottomDiffAccumulate(int) const override { return desc_ && b2c_conv_backward_data_accumulate_supported(desc_) != 0; }
   const b2c_conv_desc* desc() const { return desc_; }
   void* filter_cache() const { return fcache_; }
 

@@ -340,6 +340,7 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
   {
     const char* e = getenv("B2C_FUSE");
     const bool fuse = !e || atoi(e) != 0;
+    fuse_fanout_ = fuse;
     for (size_t i = 0; fuse && i < layers_.size(); ++i) {
       auto* bn = dynamic_cast<BatchNormLayer*>(layers_[i].get());
       auto* el = dynamic_cast<EltwiseLayer*>(layers_[i].get());
@@ -372,8 +373,13 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       const bool in_place = i < nd.top.size() && nd.top[i] == nd.bottom[i];
       if (in_place) continue;
       if (writers[nd.bottom[i]]++ > 0) {
-        tmp_diffs_.emplace_back(new Blob(nd.bottom[i]->shape()));
-        nd.bottom_diff_tmp[i] = tmp_diffs_.back().get();
+        if (fuse_fanout_ && layers_[li]->SupportsBottomDiffAccumulate((int)i)) {
+          nd.accumulate_bottom.resize(nd.bottom.size(), false);       // the layer adds into the blob's diff itself
+          nd.accumulate_bottom[i] = true;
+        } else {
+          tmp_diffs_.emplace_back(new Blob(nd.bottom[i]->shape()));
+          nd.bottom_diff_tmp[i] = tmp_diffs_.back().get();
+        }
       }
     }
   }
@@ -439,6 +445,7 @@ void TrainNet::Backward(bool update) {
       vector<Blob*> bvec = nd.bottom;
       for (size_t i = 0; i < bvec.size(); ++i)
         if (nd.bottom_diff_tmp[i]) { nd.bottom_diff_tmp[i]->ShareData(*nd.bottom[i]); bvec[i] = nd.bottom_diff_tmp[i]; }
+      if (!nd.accumulate_bottom.empty()) layers_[li]->set_accumulate_bottom_diff(nd.accumulate_bottom);
       layers_[li]->Backward(nd.top, nd.propagate_down, bvec);
       for (size_t i = 0; i < bvec.size(); ++i)
         if (nd.bottom_diff_tmp[i])

@@ -219,6 +219,7 @@ class TrainNet {
     vector<Blob*> bottom, top;
     vector<bool> propagate_down;
     vector<Blob*> bottom_diff_tmp;                 // per bottom: null = write the blob's own diff, else accumulate through this
+    vector<bool> accumulate_bottom;                // per bottom: the layer itself adds into the blob's diff (no shadow blob)
     bool need_backward = false;
     int first_param = -1, num_params = 0;
   };
@@ -229,6 +230,7 @@ class TrainNet {
   void MarkParamsDirty() { filters_dirty_ = true; } // call after writing parameter data behind the net's back
  private:
   bool filters_dirty_ = true;
+  bool fuse_fanout_ = true;                        // B2C_FUSE: conv layers add their bottom gradient into a fan-out blob's diff directly
   vector<ConvolutionLayer*> cached_convs_;
   float host_loss_ = 0.f;
   string name_;

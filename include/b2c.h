@@ -125,6 +125,12 @@ int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, const float*
 /* dW += conv_bwd_filter(X, dY).  dw ACCUMULATED (beta = 1).
  * Replaces weight_gpu_gemm (base_conv_layer.hpp:148-162) /
  * cudnnConvolutionBackwardFilter beta=1 (cudnn_conv_layer.cu:95-99).                 */
+/* dx += the bottom gradient (instead of dx = ...): where a blob feeds several layers the reference sums their bottom diffs
+ * in SplitLayer::Backward (split_layer.cpp); here the second and later writers add straight into the blob's diff through
+ * the kernel's TMA reduce-add store.  Available for the layers the staged kernel takes; ask first. */
+int b2c_conv_backward_data_accumulate_supported(const b2c_conv_desc* d);
+int b2c_conv_backward_data_accumulate(const b2c_conv_desc* d, const float* dy, const float* w, float* dx,
+                                      void* ws, size_t ws_bytes, void* stream);
 int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, const float* dy, float* dw,
                              void* ws, size_t ws_bytes, void* stream);
 /* db[o] += sum_{n,h,w} dY.  db ACCUMULATED (beta = 1).

@@ -202,6 +202,28 @@ def test_prepared_filter_cache_is_bitwise_equivalent(rng, name):
     assert torch.equal(Y0, Y1)
 
 
+@pytest.mark.parametrize("name", ["resnet_res2_3x3", "resnet_res2_1x1_expand", "resnet_res4_3x3", "staged_5x5_c32", "resnet_res3_3x3"])
+def test_backward_data_accumulate(rng, name):
+    """dx += dgrad through the TMA reduce-add store == (dx0 + dgrad) computed separately, bit for bit (one fp32 add either way);
+    covers tiles inside one image (TMA path) and tiles that span two (read-modify-write path)."""
+    case = dict(ALL_CASES)[name]
+    po, pc = make(o, case), make(capi, case)
+    x, w, b, dy = tensors(rng, po)
+    d = m.ConvDesc(pc)
+    assert d.backward_data_accumulate_supported()
+    dx0 = rng.standard_normal(po.x_shape()).astype(np.float32)
+    Wt, DY = dev(w), dev(dy)
+    DX = torch.empty(po.x_shape(), device="cuda")
+    d.backward_data(DY, Wt, DX)
+    want = dev(dx0) + DX
+    ACC = dev(dx0)
+    d.backward_data_accumulate(DY, Wt, ACC)
+    assert torch.equal(ACC, want)
+    # a layer the staged kernel does not take reports so, and the call refuses instead of silently overwriting
+    d2 = m.ConvDesc(make(capi, dict(ALL_CASES)["resnet_res3_1x1_s2"]))
+    assert not d2.backward_data_accumulate_supported()
+
+
 def test_sobel_known_answer(rng):
     # test_convolution_layer.cpp:511-604 / CuDNN variant :1013-1110, tol 1e-4
     x = rng.standard_normal((2, 3, 6, 4)).astype(np.float32)
