@@ -65,6 +65,10 @@ bool tc_stg_supported(const ConvShape&, int op);
 size_t tc_stg_workspace(const ConvShape&, int op);
 int launch_conv_tc_stg(const ConvShape&, int op, const float* a, const float* w, const float* bias, float* out, void* ws,
                        size_t ws_bytes, const void* prepared, bool accumulate, cudaStream_t);
+// TMA-staged bf16x3 weight gradient (conv_tc_wgrad_stg.cu): stride-1 "same" convolutions with 1 or 9 taps
+bool tc_wgrad_stg_supported(const ConvShape&);
+size_t tc_wgrad_stg_workspace(const ConvShape&);
+int launch_conv_tc_wgrad_stg(const ConvShape&, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
 bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K);
 int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta,
                     float* C, int math, cudaStream_t);
@@ -79,7 +83,8 @@ static bool have_device() {
 }
 
 static bool use_staged(const b2c_conv_desc* d, int op) {
-  return d->engine != B2C_ENGINE_CAFFE && d->algo != B2C_ALGO_SIMT && d->math == B2C_MATH_FP32 && tc_stg_supported(d->s, op);
+  if (d->engine == B2C_ENGINE_CAFFE || d->algo == B2C_ALGO_SIMT || d->math != B2C_MATH_FP32) return false;
+  return op == B2C_OP_BACKWARD_FILTER ? tc_wgrad_stg_supported(d->s) : tc_stg_supported(d->s, op);
 }
 // math mode handed to the gather kernels (conv_tc.cu / conv_tc_wgrad.cu), which know FP32 (= 3xTF32) and TF32
 static int gather_math(const b2c_conv_desc* d) { return d->math == B2C_MATH_TF32 ? B2C_MATH_TF32 : B2C_MATH_FP32; }
@@ -183,7 +188,8 @@ extern "C" size_t b2c_conv_workspace_bytes(const b2c_conv_desc* d, int op) {
   if (d->engine == B2C_ENGINE_CAFFE)   // one image's col buffer [Kd*G, Ho, Wo] (base_conv_layer.cpp:225-233)
     return s.is_1x1 ? 0 : sizeof(float) * (size_t)s.Kd * s.G * s.Ho * s.Wo;
   if (use_staged(d, op)) {   // the gather kernel is the fallback for unaligned activation pointers: size for both
-    const size_t a = tc_stg_workspace(s, op), b = tc_conv_supported(s, op) ? tc_conv_workspace(s, op, gather_math(d)) : 0;
+    const size_t a = op == B2C_OP_BACKWARD_FILTER ? tc_wgrad_stg_workspace(s) : tc_stg_workspace(s, op);
+    const size_t b = tc_conv_supported(s, op) ? tc_conv_workspace(s, op, gather_math(d)) : 0;
     return a > b ? a : b;
   }
   if (resolve_algo(d, op) == B2C_ALGO_TCGEN05) return tc_conv_workspace(s, op, gather_math(d));
@@ -297,7 +303,9 @@ extern "C" int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, 
     }
     return B2C_OK;
   }
-  if (resolve_algo(d, B2C_OP_BACKWARD_FILTER) == B2C_ALGO_TCGEN05)
+  if (use_staged(d, B2C_OP_BACKWARD_FILTER) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15u) == 0)
+    return launch_conv_tc_wgrad_stg(s, x, dy, dw, ws, ws_bytes, st);
+  if (tc_conv_supported(s, B2C_OP_BACKWARD_FILTER) && d->algo != B2C_ALGO_SIMT)
     return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, gather_math(d), x, dy, nullptr, dw, ws, ws_bytes, nullptr, st);
   return launch_conv_wgrad_simt(s, x, dy, dw, st);
 }
@@ -306,17 +314,20 @@ namespace b2c {
 int debug_mbar_fwd(unsigned int*, int, int);
 int debug_mbar_stg(unsigned int*, int, int);
 int debug_mbar_wgrad(unsigned int*, int, int);
+int debug_mbar_wstg(unsigned int*, int, int);
 }
-// out: three consecutive blocks of 128 words (gather fwd/dgrad kernel, staged kernel, weight-gradient kernels)
+// out: four consecutive blocks of 128 words (gather fwd/dgrad kernel, staged fwd/dgrad kernel, gather weight-gradient kernels,
+// staged weight-gradient kernel)
 extern "C" int b2c_debug_mbar_timeouts(unsigned int* out, int cap_words) {
   REQUIRE_DEVICE();
-  if (!out || cap_words < 384) return fail(B2C_ERR_INVALID, "b2c_debug_mbar_timeouts: need 384 words");
-  const int a = debug_mbar_fwd(out, 128, -1), b = debug_mbar_stg(out + 128, 128, -1), c = debug_mbar_wgrad(out + 256, 128, -1);
-  return (a < 0 || b < 0 || c < 0) ? -1 : a + b + c;
+  if (!out || cap_words < 512) return fail(B2C_ERR_INVALID, "b2c_debug_mbar_timeouts: need 512 words");
+  const int a = debug_mbar_fwd(out, 128, -1), b = debug_mbar_stg(out + 128, 128, -1), c = debug_mbar_wgrad(out + 256, 128, -1),
+            e = debug_mbar_wstg(out + 384, 128, -1);
+  return (a < 0 || b < 0 || c < 0 || e < 0) ? -1 : a + b + c + e;
 }
 extern "C" int b2c_debug_mbar_set_trap(int on) {
   REQUIRE_DEVICE();
-  debug_mbar_fwd(nullptr, 0, on != 0); debug_mbar_stg(nullptr, 0, on != 0); debug_mbar_wgrad(nullptr, 0, on != 0);
+  debug_mbar_fwd(nullptr, 0, on != 0); debug_mbar_stg(nullptr, 0, on != 0); debug_mbar_wgrad(nullptr, 0, on != 0); debug_mbar_wstg(nullptr, 0, on != 0);
   return B2C_OK;
 }
 

@@ -1,0 +1,484 @@
+// conv_tc_wgrad_stg.cu -- tcgen05 weight gradient with TMA-STAGED operands and bf16x3 math (sm_100a), for the stride-1
+// "same" convolutions with 1 or 9 taps (1x1 / pad 0 and 3x3 / pad 1: 40 of ResNet-50's 53 layers, all of VGG-16's).
+//
+// Replaces cudnnConvolutionBackwardFilter beta=1 (reference src/caffe/layers/cudnn_conv_layer.cu:95-99) and, semantically,
+// the per-image weight_gpu_gemm loop (base_conv_layer.hpp:148-162):
+//     dW[o][c][tap] += sum_{n,p} dY[n][o][p] * X[n][c][p + off(tap)]        (X read as zero outside the image)
+// GEMM view: M = 128 output channels, N = CN input channels x T taps (columns ordered (c, tap) = dW's own memory order, so
+// a tile row is one contiguous run of dW), K = pixels.  The gather kernel (conv_tc_wgrad.cu) builds the X operand with
+// per-thread predicated 4-byte loads: ~2 900 cycles per 32-pixel K block against 1 536 of MMA (profiles/README.md), 50-110
+// TFLOP/s on the 3x3 layers.  Here, per K block of 64 pixels of one image:
+//   * TMA brings in dY as two [128 o][32 px] fp32 boxes (SWIZZLE_128B) and X as ONE [CN c][64 + 2*halo px] fp32 box; pixels
+//     past the image end and channels past O / C read as zero, which is the padding both the K tail and the M / N tails need;
+//   * 16 converter warps split dY into bf16 hi / lo and write it into TENSOR MEMORY as the A operand (tcgen05.st, lane =
+//     output channel; the swizzled 16-byte chunks make the row-wise ld.shared.v4 conflict-free), and build the B operand in
+//     shared memory: row (c, tap) of the K-major SWIZZLE_128B tile is the staged row of channel c shifted by the tap offset,
+//     masked where the tap leaves the image (zero padding / row wrap; one bit per pixel and tap, computed once per K block),
+//     split into bf16 hi / lo; lanes run along the pixels, so both the reads and the 4-byte writes are conflict-free;
+//   * one converged warp issues tcgen05.mma.kind::f16: lo*hi + hi*lo + hi*hi per 16-pixel K step, N = 256 (+ 32 for the 288
+//     columns of a 3x3 tile), accumulators in TMEM for the whole K range of the CTA;
+//   * the reduction over pixels is split across CTAs in one wave; partial tiles meet through the fused, deterministic
+//     split-K reduction of conv_tc_wgrad.cu (arrival counter + per-CTA slice, fixed split order).
+// Three bf16 MMAs per MAC cost 1.5 TF32 MMAs (3xTF32: 3); dropped terms ~2^-17 per product.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include "b2c_common.cuh"
+#define B2C_MBAR_DEBUG 1     // this kernel records stuck mbarrier waits (tc_common.cuh)
+#include "tc_common.cuh"
+
+namespace b2c {
+using namespace tc;
+
+namespace wstg {
+
+constexpr int NCW = 16;                       // converter warps (warps 0-3 also run the epilogue)
+constexpr int W_TMA = NCW;
+constexpr int W_MMA = NCW + 1;
+constexpr int THREADS = (NCW + 2) * 32;       // 576
+constexpr int KPX = 64;                       // pixels per K block
+constexpr uint32_t DY_BYTES = 2u * 128u * 128u;   // two [128 rows][32 px] fp32 boxes
+
+struct Params {
+  int HW, H, W, C, O;
+  int halo;                // pad*W + pad
+  int bwx;                 // staged pixels per X channel row (multiple of 4)
+  int bpi;                 // K blocks per image = ceil(HW / 64)
+  long long nkb_total;     // N * bpi
+  int kb_per_split, splits;
+  int Kd;                  // C * T (row length of dW)
+  float* out;              // splits == 1: dW (accumulated); else partials [splits][O*Kd] (overwritten)
+  float* grad;             // dW (fused reduction target when splits > 1)
+  unsigned int* counters;
+};
+
+template <int T, int CN>
+struct Cfg {
+  static constexpr int NROWS = T * CN;                                  // B rows = GEMM N
+  static constexpr int N0 = NROWS > 256 ? 256 : NROWS;                  // first MMA
+  static constexpr int N1 = NROWS - N0;                                 // second MMA (0 or 32)
+  static constexpr uint32_t B_PLANE = (uint32_t)NROWS * 128u;           // [NROWS][64 bf16]
+  static constexpr uint32_t B_STAGE = 2u * B_PLANE;                     // hi + lo
+  static constexpr int BSTAGES = 2;
+  static constexpr uint32_t XMAX = (uint32_t)CN * (T == 1 ? 64u : 256u) * 4u;   // raw X box upper bound (1x1: no halo; else bwx <= 256)
+  static constexpr int NRAW = (BSTAGES * B_STAGE + 2u * (DY_BYTES + XMAX) <= 208u * 1024u) ? 2 : 1;
+  static constexpr uint32_t RAW_STAGE = DY_BYTES + XMAX;
+  static constexpr uint32_t B_OFF = 0;
+  static constexpr uint32_t RAW_OFF = BSTAGES * B_STAGE;
+  static constexpr uint32_t BAR_OFF = RAW_OFF + NRAW * RAW_STAGE;
+  static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr uint32_t D_COLS = NROWS;                             // fp32 accumulator columns
+  static constexpr uint32_t A_COL0 = ((NROWS + 31) / 32) * 32;
+  static_assert(A_COL0 + BSTAGES * 64 <= 512, "TMEM budget");
+  static_assert(NROWS % 16 == 0 && N0 % 16 == 0 && (N1 == 0 || N1 % 16 == 0), "UMMA N granularity");
+  static_assert(TOTAL <= 227u * 1024u, "shared memory budget");
+};
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// fp32 pair (k even, k odd) -> packed bf16 hi word and packed bf16 lo word (element k in the low half)
+__device__ __forceinline__ void split_pack_bf16(float e, float o, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(e, o);
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+  const float he = __uint_as_float(hb << 16), ho = __uint_as_float(hb & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(e - he, o - ho);
+  hi = hb;
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+// the deterministic split-K reduction shared with the other weight-gradient kernels (conv_tc_wgrad.cu has the twin)
+__device__ __forceinline__ void splitk_fused_reduce(const float* __restrict__ part, float* __restrict__ dw, unsigned int* counter,
+                                                    int split, int splits, long long plane, long long tile_base, int ld, int nrows, int ncols) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen < (unsigned)splits) {
+        __nanosleep(64);
+        if (clock64() - t0 > MBAR_TIMEOUT_CYCLES) asm volatile("trap;");
+      }
+    } while (seen < (unsigned)splits);
+  }
+  __syncthreads();
+  const int total = nrows * ncols;
+  const int per = (total + splits - 1) / splits;
+  const int e_end = min(total, (split + 1) * per);
+  for (int e = split * per + (int)threadIdx.x; e < e_end; e += (int)blockDim.x) {
+    const int r = e / ncols, c = e - r * ncols;
+    const long long idx = tile_base + (long long)r * ld + c;
+    float acc = 0.0f;
+    for (int s2 = 0; s2 < splits; ++s2) acc += __ldcg(part + (long long)s2 * plane + idx);
+    dw[idx] += acc;
+  }
+}
+
+template <int T, int CN>
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x) {
+  using S = Cfg<T, CN>;
+  constexpr int NROWS = S::NROWS, NRAW = S::NRAW, BST = S::BSTAGES;
+  constexpr int KW = T == 1 ? 1 : 3;                      // taps are 1x1 or 3x3
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_raw_full = sbase + S::BAR_OFF;        // NRAW: TMA bytes landed
+  const uint32_t bar_raw_empty = bar_raw_full + 16;        // NRAW: converters have read the raw stage
+  const uint32_t bar_b_full = bar_raw_empty + 16;          // BST: A in TMEM + B tile written
+  const uint32_t bar_b_empty = bar_b_full + 16;            // BST: MMAs of the stage completed
+  const uint32_t bar_done = bar_b_empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 96);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int c0 = blockIdx.y * CN;                          // input-channel tile
+  const int m0 = blockIdx.z * 128;                         // output-channel tile
+  const long long kb_begin = (long long)split * p.kb_per_split;
+  long long kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.nkb_total) kb_end = p.nkb_total;
+  const int nkb = (int)(kb_end - kb_begin);                // >= 1 by construction
+  const uint32_t x_bytes = (uint32_t)CN * (uint32_t)p.bwx * 4u;
+
+  if (tid == 0) {
+    for (int s = 0; s < NRAW; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, NCW); }
+    for (int s = 0; s < BST; ++s) { mbar_init(bar_b_full + 8 * s, NCW); mbar_init(bar_b_empty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto b_hi = [&](int s) { return sbase + S::B_OFF + (uint32_t)s * S::B_STAGE; };
+  auto b_lo = [&](int s) { return sbase + S::B_OFF + (uint32_t)s * S::B_STAGE + S::B_PLANE; };
+  auto raw_dy = [&](int r) { return sbase + S::RAW_OFF + (uint32_t)r * S::RAW_STAGE; };
+  auto raw_x = [&](int r) { return sbase + S::RAW_OFF + (uint32_t)r * S::RAW_STAGE + DY_BYTES; };
+  auto a_col = [&](int s) { return S::A_COL0 + (uint32_t)s * 64u; };
+  // first pixel of the staged X row for K block j of an image: 16-byte aligned, never negative
+  auto x_start = [&](int j) { return max((j * KPX - p.halo) & ~3, 0); };
+
+  if (warp < NCW) {
+    // ================= converters ===============================================================================
+    const int rq = warp & 3, cg = warp >> 2;               // dY: TMEM lane quarter / 16-pixel column group
+    const int row = rq * 32 + lane;
+    const uint32_t a_lane = (uint32_t)(rq * 32) << 16;
+    int n_img = (int)(kb_begin / p.bpi), j = (int)(kb_begin - (long long)n_img * p.bpi);
+    for (int i = 0; i < nkb; ++i) {
+      const int r = i % NRAW, s = i % BST;
+      mbar_wait(bar_raw_full + 8 * r, (i / NRAW) & 1);
+      // ---- (a) dY -> bf16 hi / lo -> tensor memory: this thread's row (output channel), pixels [cg*16, cg*16 + 16)
+      uint32_t hi[8], lo[8];
+      {
+        const uint32_t box = raw_dy(r) + (uint32_t)(cg >> 1) * (128u * 128u) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)((cg & 1) * 4 + q) ^ (uint32_t)(row & 7);
+          const float4 v = lds128(box + chunk * 16u);
+          split_pack_bf16(v.x, v.y, hi[2 * q], lo[2 * q]);
+          split_pack_bf16(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+        }
+      }
+      mbar_wait_backoff(bar_b_empty + 8 * s, ((i / BST) & 1) ^ 1, 32);
+      tc_fence_after();
+      {
+        const uint32_t a0 = tmem_base + a_lane + a_col(s) + (uint32_t)(cg * 8);
+        tmem_st8u(a0, hi);
+        tmem_st8u(a0 + 32, lo);
+      }
+      // ---- (b) X -> B tile rows (c, tap): lanes run along the pixels, two adjacent pixels per lane
+      uint32_t m0bits = 1u, m1bits = 1u;                    // per-pixel tap validity (bit t); 1x1: always valid
+      if (T > 1) {
+        m0bits = 0u; m1bits = 0u;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int pp = j * KPX + 2 * lane + e;
+          uint32_t mb = 0u;
+          if (pp < p.HW) {
+            const int h = pp / p.W, w = pp - h * p.W;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const int ti = t / KW, tj = t - ti * KW;
+              if ((unsigned)(h + ti - 1) < (unsigned)p.H && (unsigned)(w + tj - 1) < (unsigned)p.W) mb |= 1u << t;
+            }
+          }
+          if (e == 0) m0bits = mb; else m1bits = mb;
+        }
+      }
+      const int col0 = j * KPX - x_start(j) + 2 * lane;       // staged column of this lane's first pixel at tap offset 0
+      const uint32_t xr = raw_x(r);
+      const uint32_t wr_off = (uint32_t)(lane & 3) * 4u;      // byte inside the 16-byte chunk; chunk = lane >> 2
+#pragma unroll 2
+      for (int n = warp; n < NROWS; n += NCW) {
+        const int cl = n / T, tap = n - cl * T;
+        int off = 0;
+        if (T > 1) { const int ti = tap / KW, tj = tap - ti * KW; off = (ti - 1) * p.W + (tj - 1); }
+        const uint32_t src = xr + (uint32_t)((cl * p.bwx + col0 + off) * 4);
+        const float v0 = lds32(src), v1 = lds32(src + 4u);
+        uint32_t hw, lw;
+        split_pack_bf16(v0, v1, hw, lw);
+        if (T > 1) {
+          const uint32_t mw = (((m0bits >> tap) & 1u) ? 0x0000ffffu : 0u) | (((m1bits >> tap) & 1u) ? 0xffff0000u : 0u);
+          hw &= mw; lw &= mw;
+        }
+        const uint32_t dst = (uint32_t)n * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)(n & 7)) * 16u) + wr_off;
+        sts32(b_hi(s) + dst, hw);
+        sts32(b_lo(s) + dst, lw);
+      }
+      // raw stage fully read by this warp: hand it back to the TMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_raw_empty + 8 * r);
+      fence_proxy_async();                                  // st.shared B tile -> visible to the MMA's async-proxy reads
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_b_full + 8 * s);
+      if (++j == p.bpi) { j = 0; ++n_img; }
+    }
+    if (warp < 4) {
+      // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced row stores of the partial tile ===
+      mbar_wait_backoff(bar_done, 0, 128);
+      tc_fence_after();
+      float* tpad = reinterpret_cast<float*>(sptr) + warp * (32 * 33);     // all MMAs done: the B stages are free
+      float* obase = p.out + (p.splits > 1 ? (long long)split * p.O * p.Kd : 0LL) + (long long)(m0 + warp * 32) * p.Kd + (long long)c0 * T;
+      const int rows_valid = p.O - (m0 + warp * 32);
+      const int cols_valid = min(NROWS, (p.C - c0) * T);
+      const bool accumulate = p.splits == 1;
+#pragma unroll 1
+      for (int q0 = 0; q0 < NROWS; q0 += 32) {
+        if (q0 >= cols_valid) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)q0, v);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) tpad[lane * 33 + jj] = v[jj];
+        __syncwarp();
+        const bool colok = q0 + lane < cols_valid;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < rows_valid && colok) {
+            float* dst = obase + (long long)rr * p.Kd + q0 + lane;
+            const float t = tpad[rr * 33 + lane];
+            *dst = accumulate ? *dst + t : t;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+    }
+  } else if (warp == W_TMA) {
+    // ================= TMA producer ================================================================================
+    int n_img = (int)(kb_begin / p.bpi), j = (int)(kb_begin - (long long)n_img * p.bpi);
+    for (int i = 0; i < nkb; ++i) {
+      const int r = i % NRAW;
+      mbar_wait_backoff(bar_raw_empty + 8 * r, ((i / NRAW) & 1) ^ 1, 32);
+      if (elect_one()) {
+        arrive_expect_tx(bar_raw_full + 8 * r, DY_BYTES + x_bytes);
+        tma_load_3d(raw_dy(r), &map_dy, bar_raw_full + 8 * r, j * KPX, m0, n_img);
+        tma_load_3d(raw_dy(r) + 128u * 128u, &map_dy, bar_raw_full + 8 * r, j * KPX + 32, m0, n_img);
+        tma_load_3d(raw_x(r), &map_x, bar_raw_full + 8 * r, x_start(j), c0, n_img);
+      }
+      __syncwarp();
+      if (++j == p.bpi) { j = 0; ++n_img; }
+    }
+  } else {
+    // ================= MMA issuer ===================================================================================
+    constexpr uint32_t IDESC0 = idesc_bf16(128, S::N0);
+    constexpr uint32_t IDESC1 = idesc_bf16(128, S::N1 > 0 ? S::N1 : 16);
+    int j = (int)(kb_begin % p.bpi);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % BST;
+      mbar_wait(bar_b_full + 8 * s, (i / BST) & 1);
+      tc_fence_after();
+      const int valid = min(KPX, p.HW - j * KPX);
+      const int ks = (valid + 15) >> 4;                      // K steps with any in-image pixel (the rest is all zero)
+      if (elect_one()) {
+        for (int kk = 0; kk < ks; ++kk) {
+          const uint32_t ah = tmem_base + a_col(s) + (uint32_t)(kk * 8);
+          const uint64_t bh = desc_sw128(b_hi(s) + kk * 32), bl = desc_sw128(b_lo(s) + kk * 32);
+          const uint32_t acc = (i | kk) != 0;
+          umma_bf16_ts(tmem_base, ah + 32, bh, IDESC0, acc);      // lo * hi
+          umma_bf16_ts(tmem_base, ah, bl, IDESC0, 1);              // hi * lo
+          umma_bf16_ts(tmem_base, ah, bh, IDESC0, 1);              // hi * hi
+          if (S::N1 > 0) {
+            const uint64_t bh1 = desc_sw128(b_hi(s) + 256u * 128u + kk * 32), bl1 = desc_sw128(b_lo(s) + 256u * 128u + kk * 32);
+            umma_bf16_ts(tmem_base + 256, ah + 32, bh1, IDESC1, acc);
+            umma_bf16_ts(tmem_base + 256, ah, bl1, IDESC1, 1);
+            umma_bf16_ts(tmem_base + 256, ah, bh1, IDESC1, 1);
+          }
+        }
+        umma_commit(bar_b_empty + 8 * s);
+        if (i == nkb - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++j == p.bpi) j = 0;
+    }
+  }
+  if (p.splits > 1) {
+    const int tile_id = blockIdx.z * gridDim.y + blockIdx.y;
+    splitk_fused_reduce(p.out, p.grad, p.counters + tile_id, split, p.splits, (long long)p.O * p.Kd, (long long)m0 * p.Kd + (long long)c0 * T, p.Kd,
+                        min(128, p.O - m0), min(NROWS, (p.C - c0) * T));
+  }
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace wstg
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WsEncodeTiledFn ws_encode_tiled() {
+  static WsEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WsEncodeTiledFn>(f);
+  }
+  return fn;
+}
+// [N][rows][HW] fp32, box {bw, box_rows, 1}
+static int ws_make_map(CUtensorMap* map, const float* base, int HW, int rows, int N, int bw, int box_rows, bool swizzle128) {
+  WsEncodeTiledFn enc = ws_encode_tiled();
+  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)rows, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled (staged wgrad) failed (%d)", (int)r);
+  return B2C_OK;
+}
+
+static bool wstg_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+struct WstgPlan { int T, cn, bwx, bpi, splits, kb_per_split; long long nkb; };
+static bool wstg_plan(const ConvShape& s, WstgPlan* pl) {
+  if (!wstg_enabled()) return false;
+  if (s.G != 1 || s.sh != 1 || s.sw != 1 || s.dh != 1 || s.dw != 1 || s.Ho != s.H || s.Wo != s.W) return false;
+  const bool k1 = s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0;
+  const bool k3 = s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1;
+  if (!k1 && !k3) return false;
+  const long long HW = (long long)s.H * s.W;
+  if (HW % 4 != 0 || HW < 64 || (long long)s.N * HW > 0x7fffffffLL - 256) return false;
+  const int T = k1 ? 1 : 9;
+  const int halo = s.ph * s.W + s.pw;
+  const int need = wstg::KPX + 2 * halo + ((4 - halo % 4) % 4);
+  if (need > 256) return false;
+  if (!pl) return true;
+  pl->T = T;
+  pl->cn = k1 ? (s.C > 64 ? 128 : 64) : 32;
+  pl->bwx = (need + 3) & ~3;
+  pl->bpi = (int)((HW + wstg::KPX - 1) / wstg::KPX);
+  pl->nkb = (long long)s.N * pl->bpi;
+  const long long mn = (long long)((s.O + 127) / 128) * ((s.C + pl->cn - 1) / pl->cn);
+  long long splits = sm_count() / mn;
+  const long long max_splits = pl->nkb / 4 > 0 ? pl->nkb / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const long long per = (pl->nkb + splits - 1) / splits;
+  pl->splits = (int)((pl->nkb + per - 1) / per);
+  pl->kb_per_split = (int)per;
+  return true;
+}
+constexpr size_t WSTG_COUNTER_BYTES = 1024;
+bool tc_wgrad_stg_supported(const ConvShape& s) { return wstg_plan(s, nullptr); }
+size_t tc_wgrad_stg_workspace(const ConvShape& s) {
+  WstgPlan pl;
+  if (!wstg_plan(s, &pl)) return 0;
+  return pl.splits > 1 ? WSTG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
+}
+
+template <int T, int CN>
+static int wstg_launch(const wstg::Params& p, const CUtensorMap& mdy, const CUtensorMap& mx, int c_tiles, int o_tiles, cudaStream_t st) {
+  using S = wstg::Cfg<T, CN>;
+  B2C_CUDA_OK(cudaFuncSetAttribute(wstg::wgrad_stg_kernel<T, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+  dim3 grid(p.splits, c_tiles, o_tiles);
+  wstg::wgrad_stg_kernel<T, CN><<<grid, wstg::THREADS, S::TOTAL, st>>>(p, mdy, mx);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
+
+int launch_conv_tc_wgrad_stg(const ConvShape& s, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WstgPlan pl;
+  if (!wstg_plan(s, &pl)) return fail(B2C_ERR_INVALID, "staged wgrad: shape not eligible");
+  const size_t need = tc_wgrad_stg_workspace(s);
+  if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "staged wgrad: workspace too small");
+  wstg::Params p;
+  p.HW = s.H * s.W; p.H = s.H; p.W = s.W; p.C = s.C; p.O = s.O;
+  p.halo = s.ph * s.W + s.pw; p.bwx = pl.bwx; p.bpi = pl.bpi; p.nkb_total = pl.nkb;
+  p.kb_per_split = pl.kb_per_split; p.splits = pl.splits; p.Kd = s.Kd;
+  p.out = pl.splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(ws) + WSTG_COUNTER_BYTES) : dw;
+  p.grad = dw;
+  p.counters = static_cast<unsigned int*>(ws);
+  if (pl.splits > 1) B2C_CUDA_OK(cudaMemsetAsync(ws, 0, WSTG_COUNTER_BYTES, st));
+  alignas(64) CUtensorMap mdy, mx;
+  if (int rc = ws_make_map(&mdy, dy, p.HW, s.O, s.N, 32, 128, true)) return rc;
+  if (int rc = ws_make_map(&mx, x, p.HW, s.C, s.N, pl.bwx, pl.cn, false)) return rc;
+  const int c_tiles = (s.C + pl.cn - 1) / pl.cn, o_tiles = (s.O + 127) / 128;
+  if (pl.T == 9) return wstg_launch<9, 32>(p, mdy, mx, c_tiles, o_tiles, st);
+  if (pl.cn == 128) return wstg_launch<1, 128>(p, mdy, mx, c_tiles, o_tiles, st);
+  return wstg_launch<1, 64>(p, mdy, mx, c_tiles, o_tiles, st);
+}
+
+TC_DEBUG_EXPORT(debug_mbar_wstg)
+
+}  // namespace b2c

@@ -247,8 +247,9 @@ int b2c_sgd_update_arena(int nseg, const size_t* offset, const size_t* count,
  * other ranks by the caller (MPI_Bcast in the reference; any byte transport here).           */
 /* Debugging aid for the mbarrier-synchronised kernels: every wait is bounded (~1 s); a timeout records
  * {block, thread, barrier, parity} and kills the kernel with a trap.  b2c_debug_mbar_set_trap(0) makes timeouts non-fatal so
- * that a deadlocked kernel drains; b2c_debug_mbar_timeouts fills three 128-word blocks (gather fwd/dgrad kernel, staged
- * kernel, weight-gradient kernels), each {count, -, -, -, records...}, clears them and returns the total count (cap_words >= 384). */
+ * that a deadlocked kernel drains; b2c_debug_mbar_timeouts fills four 128-word blocks (gather fwd/dgrad, staged fwd/dgrad,
+ * gather weight-gradient, staged weight-gradient kernels), each {count, -, -, -, records...}, clears them and returns the
+ * total count (cap_words >= 512). */
 int b2c_debug_mbar_timeouts(unsigned int* out, int cap_words);
 int b2c_debug_mbar_set_trap(int on);
 
