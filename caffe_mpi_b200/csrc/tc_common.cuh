@@ -52,7 +52,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 #ifdef B2C_MBAR_DEBUG
 static __device__ unsigned int g_mbar_dbg[128];
 static __device__ unsigned int g_mbar_trap = 1;
-__device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
   const unsigned int slot = atomicAdd(&g_mbar_dbg[0], 1u);
   if (slot < 31u) {
     unsigned int* r = &g_mbar_dbg[4 + 4 * slot];
