@@ -407,7 +407,7 @@ static int ws_make_map(CUtensorMap* map, const float* base, int HW, int rows, in
 
 static bool wstg_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED"); on = e ? atoi(e) : 1; }
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED"); on = e ? atoi(e) : 0; }   // off until validated on a B200
   return on != 0;
 }
 struct WstgPlan { int T, cn, bwx, bpi, splits, kb_per_split; long long nkb; };
