@@ -291,10 +291,7 @@ int b2h_trainer_timed_steps(void* hv, int nsteps, int copy_input, int read_loss,
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({ *ms = h->net->TimedSteps(nsteps, copy_input != 0, read_loss != 0); });
 }
-long long b2h_trainer_input_bytes(void* hv) {
-  Blob* d = static_cast<TrainerHandle*>(hv)->net->blob("data");
-  return d ? (long long)d->count() * 4 : 0;
-}
+long long b2h_trainer_input_bytes(void* hv) { return (long long)static_cast<TrainerHandle*>(hv)->net->input_bytes(); }
 int b2h_trainer_forward_backward(void* hv, float* loss) {
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({ *loss = h->net->ForwardBackward(); });

@@ -233,6 +233,12 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       const PMessage* tp = lp.sub("transform_param");
       L.batch_size = batch_override > 0 ? batch_override : (int)(dp ? dp->integer("batch_size", 1) : 1);
       L.crop_size = (int)(tp ? tp->integer("crop_size", 0) : 0);
+      if (tp) {
+        L.has_transform = true;
+        L.mirror = tp->boolean("mirror", false);
+        L.transform_scale = (float)tp->num("scale", 1.0);
+        for (auto* f : tp->all("mean_value")) if (!f->is_msg()) L.mean_value.push_back((float)std::atof(f->scalar.c_str()));
+      }
       const int sz = L.crop_size > 0 ? L.crop_size : default_size;
       tops.push_back({L.batch_size, default_channels, sz, sz});
       tops.push_back({L.batch_size});

@@ -63,6 +63,9 @@ struct NetLayer {                       // one LayerParameter after phase filter
   int concat_axis = 1;
   int accuracy_top_k = 1;               // AccuracyParameter.top_k
   int batch_size = 0, crop_size = 0;    // Data layers
+  bool has_transform = false, mirror = false;   // TransformationParameter (caffe.proto:436-470)
+  float transform_scale = 1.f;
+  std::vector<float> mean_value;
   std::vector<int> input_shape;         // Input / DummyData layers
 };
 

@@ -224,21 +224,81 @@ void AccuracyLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) 
 }
 
 // ================================================================================================ synthetic data
-SyntheticDataLayer::~SyntheticDataLayer() { if (host_) cudaFreeHost(host_); }
+SyntheticDataLayer::~SyntheticDataLayer() {
+  if (host_) cudaFreeHost(host_);
+  if (host_u8_) cudaFreeHost(host_u8_);
+  if (host_off_) cudaFreeHost(host_off_);
+  if (dev_u8_) cudaFree(dev_u8_);
+  if (dev_off_) cudaFree(dev_off_);
+  if (dev_mean_) cudaFree(dev_mean_);
+}
+static inline uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 void SyntheticDataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& t) {
   std::mt19937 rng((uint32_t)seed_);
   for (size_t i = 0; i < t.size(); ++i) t[i]->Reshape(shapes_[i]);
   n0_ = t[0]->count();
-  CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_), sizeof(float) * n0_));
-  std::normal_distribution<float> g(0.f, 1.f);
-  for (size_t i = 0; i < n0_; ++i) host_[i] = g(rng);
-  memcpy(t[0]->mutable_cpu_data(), host_, sizeof(float) * n0_);
   if (t.size() > 1) {
     std::uniform_int_distribution<int> u(0, classes_ - 1);
     float* l = t[1]->mutable_cpu_data();
     for (size_t i = 0; i < t[1]->count(); ++i) l[i] = (float)u(rng);
   }
+  datum_mode_ = tf_.on && tf_.crop > 0 && shapes_[0].size() == 4 && shapes_[0][2] == tf_.crop && shapes_[0][3] == tf_.crop;
+  if (datum_mode_) {
+    const int N = shapes_[0][0], C = shapes_[0][1];
+    hd_ = wd_ = tf_.crop + 32;
+    u8_bytes_ = (size_t)N * C * hd_ * wd_;
+    CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_u8_), u8_bytes_));
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev_u8_), u8_bytes_));
+    CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_off_), sizeof(int) * 3 * N));
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev_off_), sizeof(int) * 3 * N));
+    for (size_t i = 0; i < u8_bytes_; i += 8) {          // uniform bytes, 8 per draw
+      uint64_t r = splitmix64(seed_ * 0x100000001B3ull + i);
+      for (size_t k = 0; k < 8 && i + k < u8_bytes_; ++k, r >>= 8) host_u8_[i + k] = (unsigned char)(r & 0xff);
+    }
+    if (!tf_.mean_value.empty()) {
+      B2_CHECK(tf_.mean_value.size() == 1 || (int)tf_.mean_value.size() == C, "Specify either 1 mean_value or as many as channels");
+      vector<float> mv(C, tf_.mean_value[0]);
+      if ((int)tf_.mean_value.size() == C) mv = tf_.mean_value;
+      CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev_mean_), sizeof(float) * C));
+      CUDA_CHECK(cudaMemcpy(dev_mean_, mv.data(), sizeof(float) * C, cudaMemcpyHostToDevice));
+    }
+    for (Blob* b : t) b->gpu_data();
+    LoadBatch(t[0], Caffe::thread_stream());              // the resident batch of the non-e2e steps
+    CUDA_CHECK(cudaStreamSynchronize(Caffe::thread_stream()));
+    return;
+  }
+  CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_), sizeof(float) * n0_));
+  std::normal_distribution<float> g(0.f, 1.f);
+  for (size_t i = 0; i < n0_; ++i) host_[i] = g(rng);
+  memcpy(t[0]->mutable_cpu_data(), host_, sizeof(float) * n0_);
   for (Blob* b : t) b->gpu_data();   // upload once; the blobs stay resident
+}
+void SyntheticDataLayer::LoadBatch(Blob* top, cudaStream_t st) {
+  if (!datum_mode_) {
+    CUDA_CHECK(cudaMemcpyAsync(top->mutable_gpu_data(), host_, sizeof(float) * n0_, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  const int N = shapes_[0][0], C = shapes_[0][1];
+  // DataTransformer's draws (data_transformer.cpp:129-135,187,224-225): mirror = rand0 % 2, offsets = rand % (extent - crop + 1)
+  unsigned char* mir = reinterpret_cast<unsigned char*>(host_off_ + 2 * N);
+  for (int i = 0; i < N; ++i) {
+    const uint64_t base = (draws_ * (uint64_t)N + (uint64_t)i) * 3;
+    const unsigned r0 = (unsigned)(splitmix64(seed_ + base) >> 33) + 1, r1 = (unsigned)(splitmix64(seed_ + base + 1) >> 33) + 1,
+                   r2 = (unsigned)(splitmix64(seed_ + base + 2) >> 33) + 1;
+    mir[i] = (tf_.mirror && (r0 % 2)) ? 1 : 0;
+    host_off_[i] = (int)(r1 % (unsigned)(hd_ - tf_.crop + 1));
+    host_off_[N + i] = (int)(r2 % (unsigned)(wd_ - tf_.crop + 1));
+  }
+  ++draws_;
+  CUDA_CHECK(cudaMemcpyAsync(dev_u8_, host_u8_, u8_bytes_, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dev_off_, host_off_, sizeof(int) * 3 * N, cudaMemcpyHostToDevice, st));
+  B2C_CHECK(b2c_transform_u8(dev_u8_, N, C, hd_, wd_, tf_.crop, tf_.crop, dev_off_, dev_off_ + N,
+                             reinterpret_cast<const unsigned char*>(dev_off_ + 2 * N), dev_mean_, nullptr, tf_.scale, top->mutable_gpu_data(), st));
 }
 
 // ================================================================================================ TrainNet
@@ -265,7 +325,9 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
     if (type == "Data" || type == "Input" || type == "DummyData" || type == "ImageData") {
       vector<vector<int>> shapes;
       for (size_t t = 0; t < L.param.top.size(); ++t) shapes.push_back(net.top_shape((int)li, (int)t));
-      auto* d = new SyntheticDataLayer(L.param, shapes, num_classes, seed);
+      SyntheticDataLayer::Transform tf;
+      tf.on = L.has_transform; tf.mirror = L.mirror; tf.crop = L.crop_size; tf.scale = L.transform_scale; tf.mean_value = L.mean_value;
+      auto* d = new SyntheticDataLayer(L.param, shapes, num_classes, seed, tf);
       layer.reset(d);
       data_ = d;
     } else if (type == "Convolution") {
@@ -422,10 +484,7 @@ void TrainNet::PrepareFilters() {
 }
 void TrainNet::Forward(bool copy_input) {
   if (filters_dirty_) PrepareFilters();
-  if (copy_input && data_) {
-    Blob* d = nodes_[0].top[0];
-    CUDA_CHECK(cudaMemcpyAsync(d->mutable_gpu_data(), data_->host_batch(), sizeof(float) * data_->batch_floats(), cudaMemcpyHostToDevice, S()));
-  }
+  if (copy_input && data_) data_->LoadBatch(nodes_[0].top[0], S());     // H2D of the batch (+ the device transform of uint8 datums)
   EventProfiler* prof = Caffe::profiler();
   for (size_t i = 0; i < layers_.size(); ++i) {
     size_t h = 0;

@@ -161,16 +161,24 @@ class AccuracyLayer : public LayerBase {       // forward only (accuracy_layer.c
   Blob hits_;
 };
 
-// Synthetic in-memory source standing in for DataLayer: N(0,1) images from mt19937(seed), uniform labels.
+// Synthetic in-memory source standing in for DataLayer's LMDB reader.  Two forms:
+//   * float: N(0,1) images from mt19937(seed), uniform labels (Input / DummyData layers, nets without transform_param);
+//   * datum: a pinned batch of uint8 datums (crop_size + 32 on a side, like the 256x256 ImageNet LMDBs for a 224 crop) that
+//     goes through the reference's own path every e2e step: host -> device copy of the BYTES, then DataTransformer::Transform
+//     on the device (b2c_transform_u8: random crop window and mirror per image drawn with Caffe's rule rand % (extent), mean
+//     values, scale) into the float data blob.
 class SyntheticDataLayer : public LayerBase {
  public:
-  SyntheticDataLayer(const LayerParameter& p, const vector<vector<int>>& shapes, int num_classes, uint64_t seed)
-      : LayerBase(p), shapes_(shapes), classes_(num_classes), seed_(seed) {}
+  struct Transform { bool on = false, mirror = false; int crop = 0; float scale = 1.f; vector<float> mean_value; };
+  SyntheticDataLayer(const LayerParameter& p, const vector<vector<int>>& shapes, int num_classes, uint64_t seed, const Transform& tf)
+      : LayerBase(p), shapes_(shapes), classes_(num_classes), seed_(seed), tf_(tf) {}
   const char* type() const override { return "Data"; }
   void LayerSetUp(const vector<Blob*>& b, const vector<Blob*>& t) override;
   void Reshape(const vector<Blob*>&, const vector<Blob*>&) override {}
-  float* host_batch() { return host_; }          // pinned staging buffer of top[0] (the e2e path copies it every step)
-  size_t batch_floats() const { return n0_; }
+  // one batch from pinned host memory into top[0] on `stream` (the e2e step): float copy, or uint8 copy + device transform
+  void LoadBatch(Blob* top, cudaStream_t stream);
+  size_t h2d_bytes() const { return datum_mode_ ? u8_bytes_ + 9 * (size_t)shapes_[0][0] : sizeof(float) * n0_; }
+  bool datum_mode() const { return datum_mode_; }
   ~SyntheticDataLayer() override;
  protected:
   void Forward_gpu(const vector<Blob*>&, const vector<Blob*>&) override {}
@@ -178,8 +186,19 @@ class SyntheticDataLayer : public LayerBase {
   vector<vector<int>> shapes_;
   int classes_;
   uint64_t seed_;
+  Transform tf_;
   float* host_ = nullptr;
   size_t n0_ = 0;
+  // datum mode
+  bool datum_mode_ = false;
+  int hd_ = 0, wd_ = 0;
+  size_t u8_bytes_ = 0;
+  unsigned char* host_u8_ = nullptr;      // pinned [N][C][hd][wd]
+  unsigned char* dev_u8_ = nullptr;
+  int* host_off_ = nullptr;               // pinned: h_off[N], w_off[N], then mirror[N] as bytes
+  int* dev_off_ = nullptr;
+  float* dev_mean_ = nullptr;
+  uint64_t draws_ = 0;                    // batches drawn so far (crop / mirror stream position)
 };
 
 class TrainNet {
@@ -206,6 +225,7 @@ class TrainNet {
   const vector<shared_ptr<Blob>>& learnable_params() const { return learnable_; }   // Net::learnable_params(): every layer blob
   const vector<int>& trainable_ids() const { return trainable_ids_; }               // ids the layers differentiate
   size_t activation_floats() const;
+  size_t input_bytes() const { return data_ ? data_->h2d_bytes() : 0; }   // host -> device bytes of one e2e step's batch
   // Solver::Snapshot (solver.cpp:447-520): <prefix>_iter_<N>.caffemodel (every layer's blobs, NVCaffe raw BlobProto) and
   // <prefix>_iter_<N>.solverstate (iter, learned_net, one history blob per learnable parameter, current_step).
   // Returns the .solverstate path.

@@ -22,7 +22,7 @@ def _relu(name, blob):
 def resnet50_prototxt(batch=32, crop=224, num_classes=1000):
     s = 'name: "Resnet50"\n'
     s += (f'layer {{ name: "data" type: "Data" top: "data" top: "label" data_param {{ source: "synthetic" batch_size: {batch} backend: LMDB }}\n'
-          f'  transform_param {{ crop_size: {crop} mirror: true }} include: {{ phase: TRAIN }} }}\n')
+          f'  transform_param {{ crop_size: {crop} mirror: true mean_value: 104 mean_value: 117 mean_value: 123 }} include: {{ phase: TRAIN }} }}\n')
     s += _conv("conv1", "data", "conv1", 64, 7, 2, 3) + _bn("conv1/bn", "conv1", "conv1/bn") + _relu("conv1/relu", "conv1/bn")
     s += 'layer { name: "pool1" type: "Pooling" bottom: "conv1/bn" top: "pool1" pooling_param { pool: MAX kernel_size: 3 stride: 2 } }\n'
     prev = "pool1"
@@ -55,7 +55,7 @@ RESNET50_SOLVER = ('base_lr: 0.001 lr_policy: "poly" power: 2.0 momentum: 0.9 we
 # ---- AlexNet / VGG-16 / GoogLeNet / LeNet: the same graphs as the reference's models/*/train_val.prototxt (TRAIN phase) ----
 def _data(batch, crop):
     return (f'layer {{ name: "data" type: "Data" top: "data" top: "label" data_param {{ source: "synthetic" batch_size: {batch} backend: LMDB }}\n'
-            f'  transform_param {{ crop_size: {crop} mirror: true }} include: {{ phase: TRAIN }} }}\n')
+            f'  transform_param {{ crop_size: {crop} mirror: true mean_value: 104 mean_value: 117 mean_value: 123 }} include: {{ phase: TRAIN }} }}\n')
 
 
 _SPECS = ""     # ParamSpecs emitted by _convb / _ip; set per net (the NVCaffe AlexNet / VGG files carry none)

@@ -182,6 +182,13 @@ int b2c_bn_backward(int N, int C, int S, const float* dy, const float* xnorm, co
                     float* dgamma, float* dbeta, float* dx, void* stream);
 /* PoolingLayer (src/caffe/layers/pooling_layer.cpp:129-318): method 0 = MAX (mask = argmax index inside the H*W
  * plane, first maximum), 1 = AVE.  NC = N*C planes; output extent is the reference's ceil mode.  dx overwritten.    */
+/* DataTransformer::Transform on a batch of uint8 datums (data_transformer.cpp:178-312): crop window and mirror flag per image
+ * (device arrays of N), per-channel mean_values[C] or a per-pixel mean_image[C*Hd*Wd] in datum coordinates (or neither), scale.
+ * out[n][c][h][w] = (datum[n][c][h_off[n]+h][w_off[n] + (mirror[n] ? crop_w-1-w : w)] - mean) * scale. */
+int b2c_transform_u8(const unsigned char* src, int N, int C, int Hd, int Wd, int crop_h, int crop_w, const int* h_off,
+                     const int* w_off, const unsigned char* mirror, const float* mean_values, const float* mean_image,
+                     float scale, float* dst, void* stream);
+
 /* Fused forms of the BatchNorm -> ReLU and Eltwise(SUM) -> ReLU chains (csrc/layers_fused.cu): bit-identical to the unfused
  * layer sequence, one HBM pass less each way; x_norm is recomputed in backward from the layer input and the saved statistics. */
 int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,

@@ -179,3 +179,20 @@ def accuracy(scores, labels, top_k=1):
         pairs = sorted(((float(v), j) for j, v in enumerate(scores[i])), reverse=True)
         hits += int(int(labels[i]) in [j for _, j in pairs[:top_k]])
     return np.float32(hits / scores.shape[0])
+
+
+# DataTransformer<Dtype>::Transform(const Datum&, Dtype*, rand), src/caffe/data_transformer.cpp:178-312 (uint8 branch), batched:
+# crop window + mirror per image, mean_value per channel or mean image in datum coordinates, scale
+def transform_u8(src, crop, h_off, w_off, mirror, mean_values=None, mean_image=None, scale=1.0):
+    N, Cc, Hd, Wd = src.shape
+    ch, cw = crop
+    out = np.empty((N, Cc, ch, cw), np.float32)
+    for n in range(N):
+        win = src[n, :, h_off[n]:h_off[n] + ch, w_off[n]:w_off[n] + cw].astype(np.float32)
+        if mean_image is not None:
+            win = win - mean_image[:, h_off[n]:h_off[n] + ch, w_off[n]:w_off[n] + cw].astype(np.float32)
+        elif mean_values is not None:
+            win = win - np.asarray(mean_values, np.float32).reshape(Cc, 1, 1)
+        win = (win * np.float32(scale)).astype(np.float32)
+        out[n] = win[:, :, ::-1] if mirror[n] else win
+    return out

@@ -251,3 +251,24 @@ def test_net_oracle_inception_style_finite_differences():
         dn = total(p2)
         fd = (up - dn) / (2 * eps)
         assert abs(fd - g[idx]) <= 2e-3 * max(1.0, abs(g[idx])), (shapes[i], fd, g[idx])
+
+
+def test_transform_oracle_matches_the_reference_loops(rng):
+    """oracle.layers_oracle.transform_u8 (numpy) against a literal transcription of DataTransformer::Transform's index walk
+    (data_transformer.cpp:233-283: top_index running backwards under mirror, data_index in datum coordinates)."""
+    src = rng.integers(0, 256, (2, 3, 6, 7), dtype=np.uint8)
+    crop, ho, wo, mir, mv, sc = (4, 5), np.array([1, 2]), np.array([0, 2]), np.array([1, 0]), [10.0, 20.0, 30.0], 0.5
+    want = np.empty((2, 3, 4, 5), np.float32)
+    for n in range(2):
+        data, td = src[n].reshape(-1), np.empty(3 * 4 * 5, np.float32)
+        for c in range(3):
+            cdho, ch = c * 6 + ho[n], c * 4
+            for h in range(4):
+                top = (ch + h + 1) * 5 - 1 if mir[n] else (ch + h) * 5
+                di = (cdho + h) * 7 + wo[n]
+                for _ in range(5):
+                    td[top] = (np.float32(data[di]) - np.float32(mv[c])) * np.float32(sc)
+                    di += 1
+                    top += -1 if mir[n] else 1
+        want[n] = td.reshape(3, 4, 5)
+    assert np.array_equal(lo.transform_u8(src, crop, ho, wo, mir, mv, None, sc), want)

@@ -67,3 +67,28 @@ def test_accuracy_top_k(rng, N, Cc, k):
     assert L.b2c_accuracy(N, Cc, k, ptr(Z), ptr(LB), ptr(acc), ptr(scratch), None) == 0
     torch.cuda.synchronize()
     assert float(acc.item()) == float(lo.accuracy(z, lab, k))
+
+
+@pytest.mark.parametrize("shape,crop,mean,scale", [((5, 3, 40, 36), (32, 32), "values", 0.0078125), ((3, 1, 28, 28), (28, 28), None, 0.00390625),
+                                                   ((4, 3, 19, 23), (17, 21), "image", 1.0), ((2, 3, 256, 256), (224, 224), "values", 1.0)])
+def test_transform_u8_is_bit_exact(rng, shape, crop, mean, scale):
+    from caffe_mpi_b200 import capi
+    L = capi.lib()
+    N, Cc, Hd, Wd = shape
+    src = rng.integers(0, 256, shape, dtype=np.uint8)
+    ho = rng.integers(0, Hd - crop[0] + 1, N).astype(np.int32)
+    wo = rng.integers(0, Wd - crop[1] + 1, N).astype(np.int32)
+    mir = rng.integers(0, 2, N).astype(np.uint8)
+    mv = np.array([104.0, 117.0, 123.0][:Cc], np.float32) if mean == "values" else None
+    mi = rng.uniform(90, 130, (Cc, Hd, Wd)).astype(np.float32) if mean == "image" else None
+    want = lo.transform_u8(src, crop, ho, wo, mir, mv, mi, scale)
+    S, HO, WO, MIR = dev(src), dev(ho), dev(wo), dev(mir)
+    MV = dev(mv) if mv is not None else None
+    MI = dev(mi) if mi is not None else None
+    out = torch.empty((N, Cc) + crop, device="cuda")
+    L.b2c_transform_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    assert L.b2c_transform_u8(ptr(S), N, Cc, Hd, Wd, crop[0], crop[1], ptr(HO), ptr(WO), ptr(MIR), ptr(MV) if MV is not None else None,
+                              ptr(MI) if MI is not None else None, scale, ptr(out), None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
