@@ -388,7 +388,10 @@ extern "C" int b2c_sgemm(int transA, int transB, int M, int N, int K, float alph
   REQUIRE_DEVICE();
   if (M == 0 || N == 0) return B2C_OK;
   const bool tA = transA != 0, tB = transB != 0;
-  if (g_default_algo != B2C_ALGO_SIMT && tc_gemm_supported(tA, tB, M, N, K))
+  // NoTrans x Trans products (InnerProduct forward) on the tensor cores, fp32-equivalent bf16x3 math; everything else -- and any
+  // alpha / beta / alignment the staged kernel does not take -- on the exact-fp32 FFMA kernel
+  if (g_default_algo != B2C_ALGO_SIMT && g_default_math == B2C_MATH_FP32 && alpha == 1.0f && (beta == 0.0f || beta == 1.0f) &&
+      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0 && tc_gemm_supported(tA, tB, M, N, K))
     return launch_sgemm_tc(tA, tB, M, N, K, alpha, A, B, beta, C, g_default_math, as_stream(stream));
   return launch_sgemm_simt(tA, tB, M, N, K, alpha, A, tA ? M : K, B, tB ? K : N, beta, C, N, as_stream(stream));
 }

@@ -628,11 +628,6 @@ int launch_conv_tc(const ConvShape& s, int op, int math, const float* a, const f
   }
 }
 
-bool tc_gemm_supported(bool, bool, int, int, int) { return false; }
-int launch_sgemm_tc(bool, bool, int, int, int, float, const float*, const float*, float, float*, int, cudaStream_t) {
-  return fail(B2C_ERR_INVALID, "tcgen05 GEMM not built");
-}
-
 TC_DEBUG_EXPORT(debug_mbar_fwd)
 
 }  // namespace b2c

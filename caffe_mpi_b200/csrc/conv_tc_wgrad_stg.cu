@@ -457,10 +457,40 @@ static int wstg_launch(const wstg::Params& p, const CUtensorMap& mdy, const CUte
   return B2C_OK;
 }
 
+static int launch_wstg_planned(const ConvShape& s, const WstgPlan& pl, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                               cudaStream_t st);
 int launch_conv_tc_wgrad_stg(const ConvShape& s, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st) {
   WstgPlan pl;
   if (!wstg_plan(s, &pl)) return fail(B2C_ERR_INVALID, "staged wgrad: shape not eligible");
-  const size_t need = tc_wgrad_stg_workspace(s);
+  return launch_wstg_planned(s, pl, x, dy, dw, ws, ws_bytes, st);
+}
+
+// ---- caffe_gpu_gemm, NoTrans x Trans (math_functions.cu:11-26 as InnerProductLayer::Forward_gpu calls it): C[M][N] (+)= A[M][K] * B[N][K]^T.
+// Both operands have the reduction axis contiguous, which is exactly the 1x1 weight-gradient problem with one "image" of K
+// "pixels": A plays dY (rows = M), B plays X (rows = N), C is dW with row length N.  No workspace in the BLAS signature, so
+// the reduction is not split (one CTA per 128 x 128 output tile walks all of K).
+bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K) {
+  return wstg_enabled() && !tA && tB && M > 0 && N > 0 && K >= 64 && K % 4 == 0 && (long long)M * N * 4 < (1ll << 40);
+}
+int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta, float* Cm, int math,
+                    cudaStream_t st) {
+  (void)math;
+  if (!tc_gemm_supported(tA, tB, M, N, K) || alpha != 1.0f || (beta != 0.0f && beta != 1.0f) ||
+      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u))
+    return fail(B2C_ERR_INVALID, "tcgen05 GEMM: only C (+)= A * B^T with alpha = 1, beta in {0, 1}, K %% 4 == 0 and 16-byte aligned operands");
+  if (beta == 0.0f) B2C_CUDA_OK(cudaMemsetAsync(Cm, 0, sizeof(float) * (size_t)M * N, st));
+  ConvShape s{};
+  s.N = 1; s.C = N; s.H = 1; s.W = K; s.O = M; s.G = 1; s.kh = s.kw = 1; s.sh = s.sw = 1; s.ph = s.pw = 0; s.dh = s.dw = 1; s.has_bias = 0;
+  s.Ho = 1; s.Wo = K; s.Cg = N; s.Og = M; s.Kd = N; s.is_1x1 = true;
+  WstgPlan pl;
+  pl.T = 1; pl.cn = N > 64 ? 128 : 64; pl.bwx = wstg::KPX; pl.bpi = (K + wstg::KPX - 1) / wstg::KPX; pl.nkb = pl.bpi;
+  pl.splits = 1; pl.kb_per_split = pl.bpi;
+  return launch_wstg_planned(s, pl, B, A, Cm, nullptr, 0, st);
+}
+
+static int launch_wstg_planned(const ConvShape& s, const WstgPlan& pl, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                               cudaStream_t st) {
+  const size_t need = pl.splits > 1 ? WSTG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
   if (need && (!ws || ws_bytes < need)) return fail(B2C_ERR_WORKSPACE, "staged wgrad: workspace too small");
   wstg::Params p;
   p.HW = s.H * s.W; p.H = s.H; p.W = s.W; p.C = s.C; p.O = s.O;

@@ -120,7 +120,10 @@ def test_sgemm_random_vs_oracle(rng, M, N, K, tA, tB):
         want = o.gemm(tA, tB, M, N, K, alpha, A, B, beta, C0, acc64=True)
         Cm = dev(C0.copy())
         capi.sgemm(tA, tB, M, N, K, alpha, dev(A), dev(B), beta, Cm)
-        assert rel_err(host(Cm), want) < TOL_SIMT
+        # NoTrans x Trans products with alpha = 1 and beta in {0, 1} (InnerProduct forward) may run on the tensor cores with the
+        # fp32-equivalent bf16x3 split (1e-4 bar, like the convolutions); everything else is the exact-fp32 FFMA kernel
+        tc = (tA, tB) == (0, 1) and K % 4 == 0 and K >= 64 and alpha == 1.0 and beta in (0.0, 1.0)
+        assert rel_err(host(Cm), want) < (TOL_FP32 if tc else TOL_SIMT)
 
 
 # ---------------------------------------------------------------------------------------------- conv
