@@ -207,7 +207,7 @@ def ncu_traffic(kernel_substr):
             iname, imet, ival, iunit = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
             iid = hdr.index("ID")
             rd, wr, ids = 0.0, 0.0, set()
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "B": 1.0, "KB": 1e3, "MB": 1e6, "GB": 1e9}
             for r in rows[1:]:
                 if kernel_substr not in r[iname]:
                     continue
