@@ -482,12 +482,9 @@ static int make_filter_map(CUtensorMap* map, const float* base, int Kp, int rows
 template <int N_TILE, bool SPLIT, int KMODE>
 static int launch_fwd_inst(const FwdParams& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
   using S = FwdSmem<N_TILE, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CUDA_OK(cudaFuncSetAttribute(igemm_fwd_kernel<N_TILE, SPLIT, KMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // per-device attribute: set on every launch (a process may drive several GPUs)
+  B2C_CUDA_OK(cudaFuncSetAttribute(igemm_fwd_kernel<N_TILE, SPLIT, KMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)S::TOTAL));
-    attr_set = true;
-  }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   igemm_fwd_kernel<N_TILE, SPLIT, KMODE><<<grid, FW_THREADS, S::TOTAL, st>>>(p, mh, ml);
   B2C_POST_LAUNCH();

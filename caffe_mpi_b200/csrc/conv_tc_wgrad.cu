@@ -702,11 +702,8 @@ static int wg_make_map(CUtensorMap* map, const float* base, long long P, int row
 template <int N_TILE>
 static int launch_wgrad_tma_inst(const WgradTmaParams& p, const CUtensorMap& mdy, const CUtensorMap& mx, cudaStream_t st) {
   using S = WgradTmaSmem<N_TILE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CUDA_OK(cudaFuncSetAttribute(wgrad1x1_tma_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
-    attr_set = true;
-  }
+  // per-device attribute: set on every launch (a process may drive several GPUs)
+  B2C_CUDA_OK(cudaFuncSetAttribute(wgrad1x1_tma_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
   dim3 grid(p.splits, (p.C + N_TILE - 1) / N_TILE, (p.O + 127) / 128);
   wgrad1x1_tma_kernel<N_TILE><<<grid, WT_THREADS, S::TOTAL, st>>>(p, mdy, mx);
   B2C_POST_LAUNCH();
@@ -780,12 +777,9 @@ subsample_kernel(const float* __restrict__ x, float* __restrict__ y, long long p
 template <int N_TILE, bool SPLIT, bool X1X1>
 static int launch_wgrad_inst(const WgradParams& p, int G, cudaStream_t st) {
   using S = WgradSmem<N_TILE, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2C_CUDA_OK(cudaFuncSetAttribute(igemm_wgrad_kernel<N_TILE, SPLIT, X1X1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // per-device attribute: set on every launch (a process may drive several GPUs)
+  B2C_CUDA_OK(cudaFuncSetAttribute(igemm_wgrad_kernel<N_TILE, SPLIT, X1X1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)S::TOTAL));
-    attr_set = true;
-  }
   dim3 grid(p.splits, (p.Kd + N_TILE - 1) / N_TILE, G * ((p.Og + 127) / 128));
   igemm_wgrad_kernel<N_TILE, SPLIT, X1X1><<<grid, WG_THREADS, S::TOTAL, st>>>(p);
   B2C_POST_LAUNCH();

@@ -422,7 +422,8 @@ softmax_loss_fwd_kernel(int C, const float* __restrict__ logits, const float* __
   for (int c = threadIdx.x; c < C; c += blockDim.x) prob[(size_t)n * C + c] *= inv;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int lab = (int)labels[n];
+    // the reference DCHECKs 0 <= label < C (softmax_loss_layer.cpp:108-109); an out-of-range label must not read out of bounds
+    const int lab = min(max((int)labels[n], 0), C - 1);
     atomicAdd(loss_sum, -logf(fmaxf(prob[(size_t)n * C + lab], FLT_MIN)));
   }
 }
