@@ -75,8 +75,17 @@ __device__ __forceinline__ void splitk_fused_reduce(const float* __restrict__ pa
   for (int e = split * per + (int)threadIdx.x; e < e_end; e += (int)blockDim.x) {
     const int r = e / ncols, c = e - r * ncols;
     const long long idx = tile_base + (long long)r * ld + c;
+    // loads of 8 splits in flight, added in split order (the order, not the batching, fixes the rounding)
     float acc = 0.0f;
-    for (int s2 = 0; s2 < splits; ++s2) acc += __ldcg(part + (long long)s2 * plane + idx);
+    int s2 = 0;
+    for (; s2 + 8 <= splits; s2 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(part + (long long)(s2 + u) * plane + idx);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; s2 < splits; ++s2) acc += __ldcg(part + (long long)s2 * plane + idx);
     dw[idx] += acc;
   }
 }

@@ -205,11 +205,15 @@ def test_prepared_filter_cache_is_bitwise_equivalent(rng, name):
     assert torch.equal(Y0, Y1)
 
 
-@pytest.mark.parametrize("name", ["resnet_res2_3x3", "resnet_res2_1x1_expand", "resnet_res4_3x3", "staged_5x5_c32", "resnet_res3_3x3"])
+ACC_CASES = dict(ALL_CASES)
+ACC_CASES["staged_5x5_o64"] = dict(N=5, Cin=32, H=10, W=14, O=64, k=5, s=1, p=2, d=1, G=1, bias=True)   # dgrad reduces over O: O % 32 == 0
+
+
+@pytest.mark.parametrize("name", ["resnet_res2_3x3", "resnet_res2_1x1_expand", "resnet_res4_3x3", "staged_5x5_o64", "resnet_res3_3x3"])
 def test_backward_data_accumulate(rng, name):
     """dx += dgrad through the TMA reduce-add store == (dx0 + dgrad) computed separately, bit for bit (one fp32 add either way);
     covers tiles inside one image (TMA path) and tiles that span two (read-modify-write path)."""
-    case = dict(ALL_CASES)[name]
+    case = ACC_CASES[name]
     po, pc = make(o, case), make(capi, case)
     x, w, b, dy = tensors(rng, po)
     d = m.ConvDesc(pc)
