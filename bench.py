@@ -335,7 +335,11 @@ def run_ours(args):
                                         "bf16x3 kernel (three bf16 MMAs = 1.5 TF32 MMAs per MAC), 1/3 for the 3xTF32 kernels",
                          "families": {k: {"tflops": (v[0] / (v[1] / 1e3) / 1e12 if v[1] > 0 else None), "ms_per_step": round(v[1], 3),
                                           "frac": (v[0] / (v[1] / 1e3) / 1e12 / tf32_peak if v[1] > 0 else None)} for k, v in fam.items()},
-                         "conv_ms_per_step": {k: round(v, 3) for k, v in conv_ms.items()}},
+                         "conv_ms_per_step": {k: round(v, 3) for k, v in conv_ms.items()},
+                         # BASELINE.json configs[1] quotes AlexNet as "conv fwd/bwd only": the conv layers' share of this same step
+                         "conv_only": {"ms_per_step": round(sum(conv_ms.values()), 3),
+                                       "images_per_sec": (N / (sum(conv_ms.values()) / 1e3) if sum(conv_ms.values()) > 0 else None),
+                                       "tflops": (sum(conv_fl.values()) / (sum(conv_ms.values()) / 1e3) / 1e12 if sum(conv_ms.values()) > 0 else None)}},
             "layer_ms_per_step": {k: round(v, 3) for k, v in sorted(by_type.items(), key=lambda kv: -kv[1])},
         }
         if world == 1 and not args.no_cpu_baseline:
