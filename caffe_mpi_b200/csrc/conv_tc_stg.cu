@@ -60,6 +60,7 @@ constexpr int STAGES = 3;                     // operand pipeline depth (B in sm
 constexpr uint32_t STG_POOL = 96u * 1024u;    // activation staging pool, carved into slots of one TMA box each
 constexpr int MAX_SLOTS = 6;
 constexpr int MAX_TAPS = 32;                  // per-row validity mask is one 32-bit word
+constexpr int PLANE_IMGS = 4;                 // plane mode: images per staging slot (a 128-row tile of 7x7 maps touches <= 4)
 
 struct Params {
   int HW, H, W;
@@ -82,7 +83,14 @@ struct Smem {
   static constexpr uint32_t B_BYTES = (uint32_t)N_TILE * 128u;              // [N_TILE rows][64 bf16], SW128
   static constexpr uint32_t STAGE = 2u * B_BYTES;                           // hi + lo
   static constexpr uint32_t STG_OFF = STAGES * STAGE;
-  static constexpr uint32_t SLOT_BYTES = (uint32_t)CB * (uint32_t)BWT * 4u;  // one box: [32 channels][BWT pixels] fp32
+  // BWT >= 128: one box = [32 channels][BWT pixels] fp32.  BWT < 128 ("plane mode", maps of BWT = H*W pixels whose
+  // channel pitch TMA cannot address, 7x7 = 196 bytes): one slot = up to PLANE_IMGS whole images x [32 channels][H*W]
+  static constexpr bool PLANE = BWT < 128;
+  static constexpr uint32_t IMG_BYTES = (uint32_t)CB * (uint32_t)BWT * 4u;
+  static constexpr uint32_t SLOT_BYTES = PLANE ? PLANE_IMGS * IMG_BYTES : IMG_BYTES;
+  static constexpr uint32_t PITCH = (uint32_t)BWT * 4u;                     // bytes between channels of a staged box
+  static_assert(!PLANE || IMG_BYTES % 128u == 0, "TMA destinations are 128-byte aligned");
+  static_assert(!PLANE || 127 / BWT + 2 <= PLANE_IMGS, "a 128-row tile touches at most PLANE_IMGS images");
   static constexpr int NSLOT_ = (int)(STG_POOL / SLOT_BYTES);
   static constexpr int NSLOT = NSLOT_ > MAX_SLOTS ? MAX_SLOTS : NSLOT_;
   static constexpr uint32_t EPI_OFF = STG_OFF + STG_POOL;                   // 2 x [32 channels][128 pixels] fp32
@@ -162,6 +170,7 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
                  const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
   using S = Smem<N_TILE, BWT>;
   constexpr int NSLOT = S::NSLOT;
+  constexpr bool PLANE = S::PLANE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -201,11 +210,13 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     m0 = (tile / p.n_tiles) * 128; n0 = nt * N_TILE;
   };
   // images a tile touches: 1 or 2 (H*W >= 128); the second one starts at tile row `split`
-  auto tile_images = [&](int m0, int& n_first, int& nseg, int& split) {
+  // plane mode: nseg = 1 (all the tile's images share one slot), nimg = how many of them there are (<= PLANE_IMGS)
+  auto tile_images = [&](int m0, int& n_first, int& nseg, int& split, int& nimg) {
     const int q_last = min(m0 + 128, p.Mtot) - 1;
     n_first = m0 / p.HW;
-    nseg = q_last / p.HW - n_first + 1;
-    split = (n_first + 1) * p.HW - m0;                        // >= 128 when nseg == 1
+    nimg = q_last / p.HW - n_first + 1;
+    nseg = PLANE ? 1 : nimg;
+    split = PLANE ? 128 : (n_first + 1) * p.HW - m0;          // >= 128 when nseg == 1
   };
   const bool prof = p.prof != nullptr && blockIdx.x == 0;
 
@@ -219,16 +230,18 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     int kbg = 0;                                               // K blocks processed by this CTA (stage ring position)
     int u_base = 0;                                            // staged boxes consumed before this tile
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int m0, n0, n_first, nseg, split;
+      int m0, n0, n_first, nseg, split, nimg;
       tile_coords(tile, m0, n0);
-      tile_images(m0, n_first, nseg, split);
+      tile_images(m0, n_first, nseg, split, nimg);
       // per-row tap validity (zero padding / image borders / row wrap), once per tile
       uint32_t mask = 0;
       const int seg_r = row >= split ? 1 : 0;                  // which of the tile's images this row belongs to
+      // plane mode: the row's image relative to the tile's first one (rows past the batch: any staged address will do)
+      const int img_r = PLANE ? (m0 + row < p.Mtot ? (m0 + row) / p.HW - n_first : 0) : seg_r;
       {
         const int q = m0 + row;
         if (q < p.Mtot) {
-          const int pp = q - (n_first + seg_r) * p.HW;
+          const int pp = q - (n_first + img_r) * p.HW;
           const int h = pp / p.W, w = pp - h * p.W;
           if (p.taps == 1) mask = 1u;
           else {
@@ -246,9 +259,10 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
       // coordinate has to be 16-byte aligned (an odd start column is an illegal-instruction fault, measured) and never
       // negative; the TMA unit zero-fills past the image END; taps that reach before pixel 0 belong to masked rows, whatever
       // they read is discarded
-      const int pp_r = m0 + row - (n_first + seg_r) * p.HW;                       // this row's pixel inside its image
-      const int start_r = seg_r ? 0 : max((m0 - n_first * p.HW - p.halo) & ~3, 0);
-      const uint32_t row_off = (uint32_t)((pp_r - start_r) * 4) + (uint32_t)(sub * 8) * (uint32_t)(BWT * 4);
+      // plane mode: whole images are staged, [image][32 channels][H*W]
+      const int pp_r = m0 + row - (n_first + img_r) * p.HW;                       // this row's pixel inside its image
+      const int start_r = (PLANE || seg_r) ? 0 : max((m0 - n_first * p.HW - p.halo) & ~3, 0);
+      const uint32_t row_off = (uint32_t)((pp_r - start_r) * 4) + (uint32_t)(sub * 8) * S::PITCH + (PLANE ? (uint32_t)img_r * S::IMG_BYTES : 0u);
       int g = 0, tap = 0;
       uint32_t src_base = 0;
       for (int kb = 0; kb < p.nkb; ++kb, ++kbg) {
@@ -265,8 +279,9 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
             const bool ok = (mask >> tap) & 1u;
             const uint32_t src = src_base + (uint32_t)tapoff[tap];
             float v[8];
-            v[0] = lds32<0>(src); v[1] = lds32<BWT * 4>(src); v[2] = lds32<2 * BWT * 4>(src); v[3] = lds32<3 * BWT * 4>(src);
-            v[4] = lds32<4 * BWT * 4>(src); v[5] = lds32<5 * BWT * 4>(src); v[6] = lds32<6 * BWT * 4>(src); v[7] = lds32<7 * BWT * 4>(src);
+            constexpr int CP = (int)S::PITCH;
+            v[0] = lds32<0>(src); v[1] = lds32<CP>(src); v[2] = lds32<2 * CP>(src); v[3] = lds32<3 * CP>(src);
+            v[4] = lds32<4 * CP>(src); v[5] = lds32<5 * CP>(src); v[6] = lds32<6 * CP>(src); v[7] = lds32<7 * CP>(src);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               uint32_t hw, lw;
@@ -326,18 +341,26 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     int u = 0;
     long long s_wait = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int m0, n0, n_first, nseg, split;
+      int m0, n0, n_first, nseg, split, nimg;
       tile_coords(tile, m0, n0);
-      tile_images(m0, n_first, nseg, split);
+      tile_images(m0, n_first, nseg, split, nimg);
       for (int g = 0; g < p.groups; ++g) {
         for (int seg = 0; seg < nseg; ++seg, ++u) {
           const int slot = u % NSLOT;
           if (prof) { const long long t0 = clock64(); mbar_wait_backoff(bar_sempty + 8 * slot, ((u / NSLOT) & 1) ^ 1, 32); s_wait += clock64() - t0; }
           else mbar_wait_backoff(bar_sempty + 8 * slot, ((u / NSLOT) & 1) ^ 1, 32);
           if (elect_one()) {
-            arrive_expect_tx(bar_sfull + 8 * slot, S::SLOT_BYTES);
-            const int col0 = seg ? 0 : max((m0 - n_first * p.HW - p.halo) & ~3, 0);   // 16-byte aligned; columns past the image end read as zero
-            tma_load_3d(slot_addr(slot), &map_x, bar_sfull + 8 * slot, col0, g * CB, n_first + seg);
+            if constexpr (PLANE) {
+              // the blob viewed as {4*H*W, C/4, N} (four channels per row: a 16-byte multiple pitch); box {4*H*W, 8, 1} is
+              // 32 channels of one image, contiguous
+              arrive_expect_tx(bar_sfull + 8 * slot, (uint32_t)nimg * S::IMG_BYTES);
+              for (int k = 0; k < nimg; ++k)
+                tma_load_3d(slot_addr(slot) + (uint32_t)k * S::IMG_BYTES, &map_x, bar_sfull + 8 * slot, 0, g * (CB / 4), n_first + k);
+            } else {
+              arrive_expect_tx(bar_sfull + 8 * slot, S::SLOT_BYTES);
+              const int col0 = seg ? 0 : max((m0 - n_first * p.HW - p.halo) & ~3, 0);   // 16-byte aligned; columns past the image end read as zero
+              tma_load_3d(slot_addr(slot), &map_x, bar_sfull + 8 * slot, col0, g * CB, n_first + seg);
+            }
           }
           __syncwarp();
         }
@@ -389,9 +412,9 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     int epi_chunk = 0, ti = 0;
     long long e_wait = 0, e_work = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-      int m0, n0, n_first, nseg, split;
+      int m0, n0, n_first, nseg, split, nimg;
       tile_coords(tile, m0, n0);
-      tile_images(m0, n_first, nseg, split);
+      tile_images(m0, n_first, nseg, split, nimg);
       const int buf = ti & 1, use = ti >> 1;
       const float* brow = p.bias ? p.bias + n0 : nullptr;
       long long e0 = 0;
@@ -414,6 +437,20 @@ igemm_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
           const int nb = min(32, p.Ntot - n0 - c0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < nb) v[j] += __ldg(brow + c0 + j);    // warp-uniform address: broadcast
+        }
+        if constexpr (PLANE) {
+          // lanes = consecutive pixels of an image plane: every channel's store is one (unaligned) 128-byte run per warp,
+          // straight from the registers
+          const int q = m0 + r;
+          if (q < p.Mtot) {
+            const int nq = q / p.HW;
+            float* ob = p.out + ((size_t)nq * p.Ntot + n0 + c0) * p.HW + (q - nq * p.HW);
+            const int nb = min(32, p.Ntot - n0 - c0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nb) { float* d = ob + (size_t)j * p.HW; *d = p.accumulate ? *d + v[j] : v[j]; }
+          }
+          continue;
         }
         // the store issued two chunks ago from this staging buffer has finished reading it (elect.sync on a converged
         // warp always elects the same lane, which owns the bulk-async groups)
@@ -508,9 +545,30 @@ static int stg_make_act_map(CUtensorMap* map, const float* base, int HW, int row
   return B2C_OK;
 }
 
+// plane mode: the [N][C][HW] blob viewed as {4*HW, C/4, N}; box {4*HW, 8, 1} = 32 channels of one image
+static int stg_make_plane_map(CUtensorMap* map, const float* base, int HW, int C, int N) {
+  StgEncodeTiledFn enc = stg_encode_tiled();
+  if (!enc) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)HW * 4, (cuuint64_t)C / 4, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)HW * 16, (cuuint64_t)HW * 4 * (cuuint64_t)C};
+  cuuint32_t box[3] = {(cuuint32_t)HW * 4, (cuuint32_t)stg::CB / 4, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2C_ERR_CUDA, "cuTensorMapEncodeTiled (staged conv, plane mode) failed (%d)", (int)r);
+  return B2C_OK;
+}
+
 static bool stg_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("B2C_CONV_STAGED"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+
+static bool stg_plane_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_CONV_STAGED_PLANE"); on = e ? atoi(e) : 0; }
   return on != 0;
 }
 
@@ -522,15 +580,24 @@ static bool stg_geom(const ConvShape& s, int op, StgGeom* g) {
   if (s.G != 1 || s.sh != 1 || s.sw != 1 || s.dh != 1 || s.dw != 1) return false;
   if (s.Ho != s.H || s.Wo != s.W || 2 * s.ph != s.kh - 1 || 2 * s.pw != s.kw - 1) return false;     // "same" convolution
   const long long HW = (long long)s.H * s.W;
-  if (HW % 4 != 0 || HW < 128 || (long long)s.N * HW > 0x7fffffffLL - 256) return false;   // 16-byte TMA pitches; <= 2 images per tile
+  if ((long long)s.N * HW > 0x7fffffffLL - 256) return false;
   const int Cin = op == B2C_OP_FORWARD ? s.C : s.O, Cout = op == B2C_OP_FORWARD ? s.O : s.C;
   if (Cin % stg::CB != 0 || Cout < 32) return false;
   const int taps = s.kh * s.kw;
   if (taps > stg::MAX_TAPS) return false;
   const int halo = s.ph * s.W + s.pw;
-  const int need = 128 + 2 * halo + ((4 - halo % 4) % 4);   // staged pixels per channel (+ what rounding the box start down to 16 bytes costs)
-  const int bwt = need <= 128 ? 128 : need <= 160 ? 160 : need <= 192 ? 192 : need <= 256 ? 256 : 0;   // TMA boxes are <= 256 wide
-  if (!bwt) return false;
+  int bwt;
+  if (HW == 49) {
+    // 7x7 maps (ResNet-50 res5, GoogLeNet inception 5): a 196-byte channel pitch is not a TMA stride; whole image planes are
+    // staged instead ("plane mode", template parameter BWT = H*W)
+    if (!stg_plane_enabled()) return false;
+    bwt = 49;
+  } else {
+    if (HW % 4 != 0 || HW < 128) return false;               // 16-byte TMA pitches; <= 2 images per tile
+    const int need = 128 + 2 * halo + ((4 - halo % 4) % 4);   // staged pixels per channel (+ what rounding the box start down to 16 bytes costs)
+    bwt = need <= 128 ? 128 : need <= 160 ? 160 : need <= 192 ? 192 : need <= 256 ? 256 : 0;   // TMA boxes are <= 256 wide
+    if (!bwt) return false;
+  }
   if (g) {
     g->Cin = Cin; g->Cout = Cout; g->halo = halo; g->bwt = bwt; g->taps = taps;
     g->groups = Cin / stg::CB; g->nhb = g->groups * taps; g->nkb = (g->nhb + 1) / 2; g->Kp = g->nkb * stg::BKE;
@@ -558,6 +625,7 @@ template <int N_TILE>
 static int stg_launch_n(int bwt, const stg::Params& p, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx,
                         const CUtensorMap& my, cudaStream_t st) {
   switch (bwt) {
+    case 49: return stg_launch_inst<N_TILE, 49>(p, mh, ml, mx, my, st);
     case 128: return stg_launch_inst<N_TILE, 128>(p, mh, ml, mx, my, st);
     case 160: return stg_launch_inst<N_TILE, 160>(p, mh, ml, mx, my, st);
     case 192: return stg_launch_inst<N_TILE, 192>(p, mh, ml, mx, my, st);
@@ -610,8 +678,13 @@ int launch_conv_tc_stg(const ConvShape& s, int op, const float* a, const float* 
   alignas(64) CUtensorMap mh, ml, mx, my;
   if (int rc = stg_make_filter_map(&mh, q.hi, g.Kp, g.Cout, n_tile)) return rc;
   if (int rc = stg_make_filter_map(&ml, q.lo, g.Kp, g.Cout, n_tile)) return rc;
-  if (int rc = stg_make_act_map(&mx, a, p.HW, g.Cin, s.N, g.bwt)) return rc;
-  if (int rc = stg_make_act_map(&my, out, p.HW, g.Cout, s.N, 128)) return rc;
+  if (g.bwt < 128) {
+    if (int rc = stg_make_plane_map(&mx, a, p.HW, g.Cin, s.N)) return rc;
+    my = mx;                                                  // plane mode stores with st.global
+  } else {
+    if (int rc = stg_make_act_map(&mx, a, p.HW, g.Cin, s.N, g.bwt)) return rc;
+    if (int rc = stg_make_act_map(&my, out, p.HW, g.Cout, s.N, 128)) return rc;
+  }
   int rc;
   switch (n_tile) {
     case 128: rc = stg_launch_n<128>(g.bwt, p, mh, ml, mx, my, st); break;

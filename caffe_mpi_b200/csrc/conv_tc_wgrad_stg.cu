@@ -61,12 +61,18 @@ struct Cfg {
   static constexpr uint32_t B_PLANE = (uint32_t)NROWS * 128u;           // [NROWS][64 bf16]
   static constexpr uint32_t B_STAGE = 2u * B_PLANE;                     // hi + lo
   static constexpr int BSTAGES = 2;
+  // raw operands as TMA delivers them.  dY and X have their own rings: the converters are done with a dY stage after the
+  // first fifth of a K block (it goes to tensor memory), so ONE dY stage reloads in the shadow of the B-tile build, while X
+  // is read until the end of the block and wants two.  3x3: X pool = 2 x [32 c][184 px] (W <= 56; wider maps, up to the
+  // 256-column TMA box, run with one X stage).
+  static constexpr int NDY = T == 1 ? 2 : 1;
   static constexpr uint32_t XMAX = (uint32_t)CN * (T == 1 ? 64u : 256u) * 4u;   // raw X box upper bound (1x1: no halo; else bwx <= 256)
-  static constexpr int NRAW = (BSTAGES * B_STAGE + 2u * (DY_BYTES + XMAX) <= 208u * 1024u) ? 2 : 1;
-  static constexpr uint32_t RAW_STAGE = DY_BYTES + XMAX;
+  static constexpr uint32_t XPOOL = T == 1 ? 2u * XMAX : 2u * (uint32_t)CN * 184u * 4u;
+  static_assert(XPOOL >= XMAX, "one X stage always fits");
   static constexpr uint32_t B_OFF = 0;
-  static constexpr uint32_t RAW_OFF = BSTAGES * B_STAGE;
-  static constexpr uint32_t BAR_OFF = RAW_OFF + NRAW * RAW_STAGE;
+  static constexpr uint32_t DY_OFF = BSTAGES * B_STAGE;
+  static constexpr uint32_t X_OFF = DY_OFF + NDY * DY_BYTES;
+  static constexpr uint32_t BAR_OFF = X_OFF + XPOOL;
   static constexpr uint32_t TOTAL = BAR_OFF + 256 + 1024;
   static constexpr uint32_t D_COLS = NROWS;                             // fp32 accumulator columns
   static constexpr uint32_t A_COL0 = ((NROWS + 31) / 32) * 32;
@@ -112,6 +118,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds32i(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
@@ -174,17 +191,18 @@ template <int T, int CN>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x) {
   using S = Cfg<T, CN>;
-  constexpr int NROWS = S::NROWS, NRAW = S::NRAW, BST = S::BSTAGES;
-  constexpr int KW = T == 1 ? 1 : 3;                      // taps are 1x1 or 3x3
+  constexpr int NROWS = S::NROWS, NDY = S::NDY, BST = S::BSTAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar_raw_full = sbase + S::BAR_OFF;        // NRAW: TMA bytes landed
-  const uint32_t bar_raw_empty = bar_raw_full + 16;        // NRAW: converters have read the raw stage
-  const uint32_t bar_b_full = bar_raw_empty + 16;          // BST: A in TMEM + B tile written
+  const uint32_t bar_dy_full = sbase + S::BAR_OFF;         // 2: dY boxes landed
+  const uint32_t bar_dy_empty = bar_dy_full + 16;          // 2: converters have read the dY stage
+  const uint32_t bar_x_full = bar_dy_empty + 16;           // 2: X box landed
+  const uint32_t bar_x_empty = bar_x_full + 16;            // 2: converters have read the X stage
+  const uint32_t bar_b_full = bar_x_empty + 16;            // BST: A in TMEM + B tile written
   const uint32_t bar_b_empty = bar_b_full + 16;            // BST: MMAs of the stage completed
   const uint32_t bar_done = bar_b_empty + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 96);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sptr + S::BAR_OFF + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x;
@@ -195,9 +213,13 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
   if (kb_end > p.nkb_total) kb_end = p.nkb_total;
   const int nkb = (int)(kb_end - kb_begin);                // >= 1 by construction
   const uint32_t x_bytes = (uint32_t)CN * (uint32_t)p.bwx * 4u;
+  const int nx = 2u * x_bytes <= S::XPOOL ? 2 : 1;         // X stages
 
   if (tid == 0) {
-    for (int s = 0; s < NRAW; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, NCW); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_dy_full + 8 * s, 1); mbar_init(bar_dy_empty + 8 * s, NCW);
+      mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, NCW);
+    }
     for (int s = 0; s < BST; ++s) { mbar_init(bar_b_full + 8 * s, NCW); mbar_init(bar_b_empty + 8 * s, 1); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
@@ -210,8 +232,8 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
 
   auto b_hi = [&](int s) { return sbase + S::B_OFF + (uint32_t)s * S::B_STAGE; };
   auto b_lo = [&](int s) { return sbase + S::B_OFF + (uint32_t)s * S::B_STAGE + S::B_PLANE; };
-  auto raw_dy = [&](int r) { return sbase + S::RAW_OFF + (uint32_t)r * S::RAW_STAGE; };
-  auto raw_x = [&](int r) { return sbase + S::RAW_OFF + (uint32_t)r * S::RAW_STAGE + DY_BYTES; };
+  auto raw_dy = [&](int r) { return sbase + S::DY_OFF + (uint32_t)r * DY_BYTES; };
+  auto raw_x = [&](int r) { return sbase + S::X_OFF + (uint32_t)r * x_bytes; };
   auto a_col = [&](int s) { return S::A_COL0 + (uint32_t)s * 64u; };
   // first pixel of the staged X row for K block j of an image: 16-byte aligned, never negative
   auto x_start = [&](int j) { return max((j * KPX - p.halo) & ~3, 0); };
@@ -222,13 +244,14 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     const int row = rq * 32 + lane;
     const uint32_t a_lane = (uint32_t)(rq * 32) << 16;
     int n_img = (int)(kb_begin / p.bpi), j = (int)(kb_begin - (long long)n_img * p.bpi);
+    const uint32_t lq = (uint32_t)lane >> 2, wr_off = (uint32_t)(lane & 3) * 4u;   // 16-byte chunk / byte inside it of this lane's pixel pair
     for (int i = 0; i < nkb; ++i) {
-      const int r = i % NRAW, s = i % BST;
-      mbar_wait(bar_raw_full + 8 * r, (i / NRAW) & 1);
+      const int rd = i % NDY, rx = i % nx, s = i % BST;
+      mbar_wait(bar_dy_full + 8 * rd, (i / NDY) & 1);
       // ---- (a) dY -> bf16 hi / lo -> tensor memory: this thread's row (output channel), pixels [cg*16, cg*16 + 16)
       uint32_t hi[8], lo[8];
       {
-        const uint32_t box = raw_dy(r) + (uint32_t)(cg >> 1) * (128u * 128u) + (uint32_t)row * 128u;
+        const uint32_t box = raw_dy(rd) + (uint32_t)(cg >> 1) * (128u * 128u) + (uint32_t)row * 128u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t chunk = (uint32_t)((cg & 1) * 4 + q) ^ (uint32_t)(row & 7);
@@ -237,6 +260,8 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
           split_pack_bf16(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dy_empty + 8 * rd);      // the dY stage reloads while the B tile is built
       mbar_wait_backoff(bar_b_empty + 8 * s, ((i / BST) & 1) ^ 1, 32);
       tc_fence_after();
       {
@@ -245,47 +270,72 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
         tmem_st8u(a0 + 32, lo);
       }
       // ---- (b) X -> B tile rows (c, tap): lanes run along the pixels, two adjacent pixels per lane
-      uint32_t m0bits = 1u, m1bits = 1u;                    // per-pixel tap validity (bit t); 1x1: always valid
-      if (T > 1) {
-        m0bits = 0u; m1bits = 0u;
+      const int col0 = j * KPX - x_start(j) + 2 * lane;       // staged column of this lane's first pixel at tap offset 0
+      const uint32_t bh = b_hi(s);
+      if constexpr (T == 9) {
+        // per-tap validity of this lane's two pixels as an AND mask over the packed pair (zero padding, image borders, row
+        // wrap, pixels past the image end), once per K block
+        uint32_t mw[9];
+        {
+          uint32_t rb[2], cb[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int pp = j * KPX + 2 * lane + e;
-          uint32_t mb = 0u;
-          if (pp < p.HW) {
+          for (int e = 0; e < 2; ++e) {
+            const int pp = j * KPX + 2 * lane + e;
             const int h = pp / p.W, w = pp - h * p.W;
+            rb[e] = pp < p.HW ? ((h > 0 ? 1u : 0u) | 2u | (h + 1 < p.H ? 4u : 0u)) : 0u;
+            cb[e] = (w > 0 ? 1u : 0u) | 2u | (w + 1 < p.W ? 4u : 0u);
+          }
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-              const int ti = t / KW, tj = t - ti * KW;
-              if ((unsigned)(h + ti - 1) < (unsigned)p.H && (unsigned)(w + tj - 1) < (unsigned)p.W) mb |= 1u << t;
+          for (int t = 0; t < 9; ++t)
+            mw[t] = (((rb[0] >> (t / 3)) & (cb[0] >> (t % 3)) & 1u) ? 0x0000ffffu : 0u) |
+                    (((rb[1] >> (t / 3)) & (cb[1] >> (t % 3)) & 1u) ? 0xffff0000u : 0u);
+        }
+        mbar_wait(bar_x_full + 8 * rx, (i / nx) & 1);
+        constexpr int CPW = CN / NCW;                           // channels per warp (all 9 taps of each)
+        const int w4 = p.W * 4;
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+          const int cl = warp * CPW + c;
+          const uint32_t srcc = raw_x(rx) + (uint32_t)((cl * p.bwx + col0) * 4);
+          const uint32_t n0 = (uint32_t)cl * 9u;
+#pragma unroll
+          for (int ti = 0; ti < 3; ++ti) {
+            // the three taps of a filter row read a 4-pixel window [-1, +2] around the pair
+            const uint32_t srow = srcc + (uint32_t)((ti - 1) * w4);
+            float v[4];
+            v[0] = lds32i<-4>(srow); v[1] = lds32i<0>(srow); v[2] = lds32i<4>(srow); v[3] = lds32i<8>(srow);
+#pragma unroll
+            for (int tj = 0; tj < 3; ++tj) {
+              const int t = ti * 3 + tj;
+              uint32_t hw, lw;
+              split_pack_bf16(v[tj], v[tj + 1], hw, lw);
+              hw &= mw[t]; lw &= mw[t];                         // exact zeros whatever the staged bytes were
+              const uint32_t n = n0 + (uint32_t)t;
+              const uint32_t dst = bh + n * 128u + ((lq ^ (n & 7u)) << 4) + wr_off;
+              sts32(dst, hw);
+              sts32(dst + S::B_PLANE, lw);
             }
           }
-          if (e == 0) m0bits = mb; else m1bits = mb;
+        }
+      } else {
+        mbar_wait(bar_x_full + 8 * rx, (i / nx) & 1);
+        constexpr int RPW = CN / NCW;                           // channels (= B rows) per warp
+        // 1x1: no halo, the box starts at the K block's first pixel: the pair is 8-byte aligned
+        const uint32_t srcw = raw_x(rx) + (uint32_t)((warp * RPW * KPX + 2 * lane) * 4);
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+          const float2 v = lds64(srcw + (uint32_t)(k * KPX * 4));
+          uint32_t hw, lw;
+          split_pack_bf16(v.x, v.y, hw, lw);
+          const uint32_t n = (uint32_t)(warp * RPW + k);
+          const uint32_t dst = bh + n * 128u + ((lq ^ (n & 7u)) << 4) + wr_off;
+          sts32(dst, hw);
+          sts32(dst + S::B_PLANE, lw);
         }
       }
-      const int col0 = j * KPX - x_start(j) + 2 * lane;       // staged column of this lane's first pixel at tap offset 0
-      const uint32_t xr = raw_x(r);
-      const uint32_t wr_off = (uint32_t)(lane & 3) * 4u;      // byte inside the 16-byte chunk; chunk = lane >> 2
-#pragma unroll 2
-      for (int n = warp; n < NROWS; n += NCW) {
-        const int cl = n / T, tap = n - cl * T;
-        int off = 0;
-        if (T > 1) { const int ti = tap / KW, tj = tap - ti * KW; off = (ti - 1) * p.W + (tj - 1); }
-        const uint32_t src = xr + (uint32_t)((cl * p.bwx + col0 + off) * 4);
-        const float v0 = lds32(src), v1 = lds32(src + 4u);
-        uint32_t hw, lw;
-        split_pack_bf16(v0, v1, hw, lw);
-        if (T > 1) {
-          const uint32_t mw = (((m0bits >> tap) & 1u) ? 0x0000ffffu : 0u) | (((m1bits >> tap) & 1u) ? 0xffff0000u : 0u);
-          hw &= mw; lw &= mw;
-        }
-        const uint32_t dst = (uint32_t)n * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)(n & 7)) * 16u) + wr_off;
-        sts32(b_hi(s) + dst, hw);
-        sts32(b_lo(s) + dst, lw);
-      }
-      // raw stage fully read by this warp: hand it back to the TMA warp
+      // X stage fully read by this warp: hand it back to the TMA warp
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_raw_empty + 8 * r);
+      if (lane == 0) mbar_arrive(bar_x_empty + 8 * rx);
       fence_proxy_async();                                  // st.shared B tile -> visible to the MMA's async-proxy reads
       tmem_st_wait();
       tc_fence_before();
@@ -327,13 +377,18 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
     // ================= TMA producer ================================================================================
     int n_img = (int)(kb_begin / p.bpi), j = (int)(kb_begin - (long long)n_img * p.bpi);
     for (int i = 0; i < nkb; ++i) {
-      const int r = i % NRAW;
-      mbar_wait_backoff(bar_raw_empty + 8 * r, ((i / NRAW) & 1) ^ 1, 32);
+      const int rd = i % NDY, rx = i % nx;
+      mbar_wait_backoff(bar_x_empty + 8 * rx, ((i / nx) & 1) ^ 1, 32);
       if (elect_one()) {
-        arrive_expect_tx(bar_raw_full + 8 * r, DY_BYTES + x_bytes);
-        tma_load_3d(raw_dy(r), &map_dy, bar_raw_full + 8 * r, j * KPX, m0, n_img);
-        tma_load_3d(raw_dy(r) + 128u * 128u, &map_dy, bar_raw_full + 8 * r, j * KPX + 32, m0, n_img);
-        tma_load_3d(raw_x(r), &map_x, bar_raw_full + 8 * r, x_start(j), c0, n_img);
+        arrive_expect_tx(bar_x_full + 8 * rx, x_bytes);
+        tma_load_3d(raw_x(rx), &map_x, bar_x_full + 8 * rx, x_start(j), c0, n_img);
+      }
+      __syncwarp();
+      mbar_wait_backoff(bar_dy_empty + 8 * rd, ((i / NDY) & 1) ^ 1, 32);
+      if (elect_one()) {
+        arrive_expect_tx(bar_dy_full + 8 * rd, DY_BYTES);
+        tma_load_3d(raw_dy(rd), &map_dy, bar_dy_full + 8 * rd, j * KPX, m0, n_img);
+        tma_load_3d(raw_dy(rd) + 128u * 128u, &map_dy, bar_dy_full + 8 * rd, j * KPX + 32, m0, n_img);
       }
       __syncwarp();
       if (++j == p.bpi) { j = 0; ++n_img; }
@@ -416,7 +471,7 @@ static int ws_make_map(CUtensorMap* map, const float* base, int HW, int rows, in
 
 static bool wstg_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED"); on = e ? atoi(e) : 0; }   // off until validated on a B200
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED"); on = e ? atoi(e) : 1; }
   return on != 0;
 }
 struct WstgPlan { int T, cn, bwx, bpi, splits, kb_per_split; long long nkb; };

@@ -410,10 +410,10 @@ __global__ void __launch_bounds__(256) add_kernel(size_t n, const float* __restr
 }
 
 // ---- softmax with loss ------------------------------------------------------------------------------------------
-// one block per sample; prob[N,C]; loss_sum accumulates -log p[label] (caller zeroes it); labels are float class ids
+// one block per sample; prob[N,C]; labels are float class ids.  The loss itself is summed by softmax_loss_sum_kernel in a fixed
+// order (an atomicAdd per sample made the last bit of the reported loss depend on block scheduling)
 __global__ void __launch_bounds__(256)
-softmax_loss_fwd_kernel(int C, const float* __restrict__ logits, const float* __restrict__ labels, float* __restrict__ prob,
-                        float* __restrict__ loss_sum) {
+softmax_loss_fwd_kernel(int C, const float* __restrict__ logits, float* __restrict__ prob) {
   const int n = blockIdx.x;
   const float* z = logits + (size_t)n * C;
   float mx = -FLT_MAX, dummy = 0.f;
@@ -430,12 +430,18 @@ softmax_loss_fwd_kernel(int C, const float* __restrict__ logits, const float* __
   block_sum2(s, dummy);
   const float inv = 1.f / s;
   for (int c = threadIdx.x; c < C; c += blockDim.x) prob[(size_t)n * C + c] *= inv;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // the reference DCHECKs 0 <= label < C (softmax_loss_layer.cpp:108-109); an out-of-range label must not read out of bounds
+}
+// loss = scale * sum_n -log(max(prob[n][label[n]], FLT_MIN))   (softmax_loss_layer.cpp:100-116); one block, fixed summation order
+__global__ void __launch_bounds__(256)
+softmax_loss_sum_kernel(int N, int C, const float* __restrict__ prob, const float* __restrict__ labels, float scale, float* __restrict__ loss) {
+  float s = 0.f, dummy = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    // the reference DCHECKs 0 <= label < C (:108-109); an out-of-range label must not read out of bounds
     const int lab = min(max((int)labels[n], 0), C - 1);
-    atomicAdd(loss_sum, -logf(fmaxf(prob[(size_t)n * C + lab], FLT_MIN)));
+    s += -logf(fmaxf(prob[(size_t)n * C + lab], FLT_MIN));
   }
+  block_sum2(s, dummy);
+  if (threadIdx.x == 0) *loss = s * scale;
 }
 __global__ void __launch_bounds__(256)
 softmax_loss_bwd_kernel(size_t total, int C, const float* __restrict__ prob, const float* __restrict__ labels, float scale,
@@ -446,7 +452,6 @@ softmax_loss_bwd_kernel(size_t total, int C, const float* __restrict__ prob, con
     dx[i] = (prob[i] - (c == (int)labels[n] ? 1.f : 0.f)) * scale;
   }
 }
-__global__ void scale_scalar_kernel(float* v, float s) { *v *= s; }
 
 }  // namespace b2c
 
@@ -616,10 +621,9 @@ extern "C" int b2c_add(size_t n, const float* a, const float* b, float* y, void*
 }
 extern "C" int b2c_softmax_loss_forward(int N, int C, const float* logits, const float* labels, float* prob, float* loss, void* stream) {
   NEED(logits && labels && prob && loss && N > 0 && C > 0, "b2c_softmax_loss_forward: bad argument");
-  B2C_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), as_stream(stream)));
-  softmax_loss_fwd_kernel<<<N, 256, 0, as_stream(stream)>>>(C, logits, labels, prob, loss);
+  softmax_loss_fwd_kernel<<<N, 256, 0, as_stream(stream)>>>(C, logits, prob);
   B2C_POST_LAUNCH();
-  scale_scalar_kernel<<<1, 1, 0, as_stream(stream)>>>(loss, 1.0f / (float)N);     // VALID normalisation, no ignore_label
+  softmax_loss_sum_kernel<<<1, 256, 0, as_stream(stream)>>>(N, C, prob, labels, 1.0f / (float)N, loss);   // VALID normalisation, no ignore_label
   B2C_POST_LAUNCH();
   return B2C_OK;
 }

@@ -12,11 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(os.environ.get("B2C_RUN_EXPERIMENTAL") != "1", reason="experimental variants run only on request")
-@pytest.mark.parametrize("switch", ["B2C_WGRAD_COMPACT=2", "B2C_WGRAD_TMA=0", "B2C_CONV_STAGED=0"])
+@pytest.mark.parametrize("switch", ["B2C_WGRAD_COMPACT=2", "B2C_WGRAD_TMA=0", "B2C_CONV_STAGED=0", "B2C_CONV_STAGED_PLANE=1",
+                                    "B2C_WGRAD_STAGED=1"])
 def test_variant_passes_the_parity_cases(switch):
     name, val = switch.split("=")
     env = dict(os.environ, **{name: val})
     env.pop("B2C_RUN_EXPERIMENTAL")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
-                        "-k", "s2 or 1x1 or 3x3"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+                        "-k", "s2 or 1x1 or 3x3 or 5x5 or full_size"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]

@@ -10,7 +10,7 @@ from caffe_mpi_b200 import capi
 L = m.lib()
 L.b2c_debug_mbar_set_trap(0)
 shapes = [(2, 64, 8, 8, 64, 1, 0), (2, 32, 12, 12, 40, 3, 1), (3, 96, 14, 14, 72, 1, 0), (4, 64, 28, 28, 64, 3, 1), (2, 64, 56, 56, 256, 1, 0),
-          (64, 256, 14, 14, 256, 3, 1), (64, 64, 56, 56, 64, 3, 1), (64, 256, 56, 56, 64, 1, 0)]
+          (64, 256, 14, 14, 256, 3, 1), (64, 64, 56, 56, 64, 3, 1), (64, 256, 56, 56, 64, 1, 0), (2, 32, 8, 80, 32, 3, 1), (5, 32, 4, 13, 40, 3, 1)]
 if len(sys.argv) >= 8:
     shapes = [tuple(int(a) for a in sys.argv[1:8])]
 torch.manual_seed(0)
@@ -33,7 +33,8 @@ for (N, Cc, H, W, O, k, p) in shapes:
         print("  timeouts recorded:", n)
         blk = buf[384:512]
         role = lambda t: "conv%d" % (t // 32) if t < 512 else ("TMA" if t // 32 == 16 else "MMA")
-        names = {0: "raw_full[0]", 8: "raw_full[1]", 16: "raw_empty[0]", 24: "raw_empty[1]", 32: "b_full[0]", 40: "b_full[1]", 48: "b_empty[0]", 56: "b_empty[1]", 64: "done"}
+        names = {0: "dy_full[0]", 8: "dy_full[1]", 16: "dy_empty[0]", 24: "dy_empty[1]", 32: "x_full[0]", 40: "x_full[1]", 48: "x_empty[0]", 56: "x_empty[1]",
+                 64: "b_full[0]", 72: "b_full[1]", 80: "b_empty[0]", 88: "b_empty[1]", 96: "done"}
         for i in range(min(blk[0], 31)):
             bb, t, bar, par = blk[4 + 4 * i: 8 + 4 * i]
             print(f"    block {bb & 0xffff},{bb >> 16} thread {t} ({role(t)} lane {t % 32}) stuck on {names.get(bar & 0xff, hex(bar & 0xff))} parity {par}")
