@@ -14,27 +14,11 @@
 #include <float.h>
 #include <cooperative_groups.h>
 #include "b2c_common.cuh"
+#include "bn_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace b2c {
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// block-wide sum of two values (blockDim.x multiple of 32, <= 1024); result valid in every thread
-__device__ __forceinline__ void block_sum2(float& a, float& b) {
-  __shared__ float sa[32], sb[32];
-  a = warp_sum(a); b = warp_sum(b);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (lane == 0) { sa[w] = a; sb[w] = b; }
-  __syncthreads();
-  a = lane < nw ? sa[lane] : 0.f; b = lane < nw ? sb[lane] : 0.f;
-  a = warp_sum(a); b = warp_sum(b);
-  __syncthreads();
-}
 
 // ---- ReLU ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) relu_fwd_kernel(size_t n, const float* __restrict__ x, float* __restrict__ y, float slope) {
@@ -69,72 +53,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(size_t n, const float* __
 // distributed shared memory in rank order (deterministic), no scratch buffer, no atomics, one launch.
 // Statistics use sums of (x - k) and (x - k)^2 with k = the channel's first value, combined in double: one pass over
 // HBM instead of the reference's two, without the cancellation of a raw E[x^2] - E[x]^2.
-constexpr int BN_CLUSTER = 8;
-constexpr int BN_THREADS = 256;
-
-template <bool VEC> struct PlaneCursor {       // walks a channel's planes: flattened unit index -> (image n, offset p)
-  unsigned n, p;
-  __device__ __forceinline__ void init(unsigned i, unsigned units) { n = i / units; p = i - n * units; }
-  __device__ __forceinline__ void advance(unsigned step, unsigned units) { p += step; while (p >= units) { p -= units; ++n; } }
-};
-
-// MODE 0: a = sum (x-k), b = sum (x-k)^2   (q unused)      MODE 1: a = sum dy*xn, b = sum dy   (x = dy, q = xnorm)
-template <bool VEC, int MODE>
-__device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, const float* __restrict__ x, const float* __restrict__ q,
-                                                   float k, unsigned rank, unsigned nranks, float& a, float& b) {
-  constexpr int U = 4;                                          // independent loads in flight per thread
-  const unsigned units = VEC ? S / 4 : S;                       // units per plane
-  const unsigned total = (unsigned)N * units;
-  const unsigned len = (total + nranks - 1) / nranks;
-  const unsigned lo = min(total, rank * len), hi = min(total, lo + len);
-  a = 0.f; b = 0.f;
-  float a2 = 0.f, b2 = 0.f;
-  PlaneCursor<VEC> cur;
-  unsigned i = lo + threadIdx.x;
-  if (i < hi) cur.init(i, units);
-  for (; i < hi; i += U * BN_THREADS) {
-    size_t off[U];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      ok[u] = i + u * BN_THREADS < hi;
-      off[u] = ((size_t)cur.n * C + c) * units + cur.p;
-      cur.advance(BN_THREADS, units);
-    }
-    if (VEC) {
-      float4 v[U], w[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(k, k, k, k);
-        if (MODE == 1) w[u] = ok[u] ? reinterpret_cast<const float4*>(q)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (MODE == 0) {
-          const float d0 = v[u].x - k, d1 = v[u].y - k, d2 = v[u].z - k, d3 = v[u].w - k;
-          a += d0 + d1; a2 += d2 + d3;
-          b = fmaf(d0, d0, b); b2 = fmaf(d1, d1, b2); b = fmaf(d2, d2, b); b2 = fmaf(d3, d3, b2);
-        } else {
-          a = fmaf(v[u].x, w[u].x, a); a2 = fmaf(v[u].y, w[u].y, a2); a = fmaf(v[u].z, w[u].z, a); a2 = fmaf(v[u].w, w[u].w, a2);
-          b += v[u].x + v[u].y; b2 += v[u].z + v[u].w;
-        }
-      }
-    } else {
-      float v[U], w[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        v[u] = ok[u] ? x[off[u]] : k;
-        if (MODE == 1) w[u] = ok[u] ? q[off[u]] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (MODE == 0) { const float d = v[u] - k; a += d; b = fmaf(d, d, b); }
-        else { a = fmaf(v[u], w[u], a); b += v[u]; }
-      }
-    }
-  }
-  a += a2; b += b2;
-}
+// (geometry, cursors and block sums: bn_common.cuh, shared with the fused kernels of layers_fused.cu)
 
 template <bool VEC>
 __global__ void __launch_bounds__(BN_THREADS)
@@ -472,25 +391,9 @@ extern "C" int b2c_relu_backward(size_t n, const float* dy, const float* x, floa
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
-// cluster size for the per-channel reductions: ~16K values per CTA, at least two CTAs per SM in flight, at most 8
-static unsigned bn_cluster_size(int N, int C, int S) {
-  const size_t E = (size_t)N * S;
-  unsigned cs = 1;
-  while (cs < BN_CLUSTER && E / (cs * 2) >= 16384) cs *= 2;
-  while (cs < BN_CLUSTER && (size_t)C * cs < 2u * (unsigned)sm_count()) cs *= 2;
-  return cs;
-}
 template <typename... Args>
 static void launch_clustered(void (*kernel)(Args...), unsigned cs, int C, void* stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, C, 1);
-  cfg.blockDim = dim3(BN_THREADS, 1, 1);
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, args...);
+  bn_launch_clustered(kernel, cs, C, 0, stream, args...);
 }
 static bool vec_ok(int S, std::initializer_list<const void*> ptrs) {
   if (S % 4) return false;

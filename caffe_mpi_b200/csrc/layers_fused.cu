@@ -3,46 +3,30 @@
 //
 //   b2c_bn_forward_train_fused : batch statistics + y = [max(0, .)] (gamma * x_norm + beta).  x_norm is NOT written: the
 //                                backward pass recomputes it from the layer's input x and the saved mean / inverse std
-//                                (8 B/element instead of 12; the reference keeps x_norm_, batch_norm_layer.cu:60-75).
+//                                (the reference keeps x_norm_, batch_norm_layer.cu:60-75).
 //   b2c_bn_backward_fused      : dgamma / dbeta / dx with the ReLU mask folded in: the mask (top > 0) equals
 //                                (gamma * x_norm + beta > 0) recomputed with the forward's own expression, so the result is
 //                                bit-identical to ReLU::Backward followed by BatchNorm::Backward (relu_layer.cpp:27-41,
-//                                batch_norm_layer.cpp:230-300) at 20 B/element instead of 32.
+//                                batch_norm_layer.cpp:230-300).
+//     Both are ONE launch: a thread-block cluster per channel reduces its slice of the channel (phase 1), the partial sums
+//     meet in rank 0 through distributed shared memory, the result is broadcast back the same way, and every CTA walks ITS
+//     OWN slice again for the elementwise pass (phase 2).  The slice is ~100 KB per CTA and at most two CTAs run per SM
+//     (bounded by a dynamic-shared-memory pad), so the 30-90 MB in flight sit in the 126 MB L2 and the second walk does not
+//     go to HBM: 8 B/element forward (read x, write y) and 12 B/element backward (read dy, x, write dx) instead of 12 / 20
+//     for the two-launch form (B2C_BN_ONEPASS=0), 12 / 32 for the unfused layers.
 //   b2c_add_relu               : y = max(0, a + b)                      (Eltwise SUM + in-place ReLU, one pass instead of two)
 //   b2c_relu_backward2         : dx_a = dx_b = dy * (y > 0)             (ReLU backward + Eltwise SUM backward's two copies)
 #include <cooperative_groups.h>
 #include <initializer_list>
+#include <stdlib.h>
 #include "b2c_common.cuh"
+#include "bn_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace b2c {
 
-static __device__ __forceinline__ float fwarp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-static __device__ __forceinline__ void fblock_sum2(float& a, float& b) {
-  __shared__ float sa[32], sb[32];
-  a = fwarp_sum(a); b = fwarp_sum(b);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (lane == 0) { sa[w] = a; sb[w] = b; }
-  __syncthreads();
-  a = lane < nw ? sa[lane] : 0.f; b = lane < nw ? sb[lane] : 0.f;
-  a = fwarp_sum(a); b = fwarp_sum(b);
-  __syncthreads();
-}
-
-constexpr int FB_CLUSTER = 8;
-constexpr int FB_THREADS = 256;
-constexpr int FB_EW = 8;           // units per thread of the elementwise passes
-
-struct FPlaneCursor {               // flattened unit index of a channel -> (image, offset)
-  unsigned n, p;
-  __device__ __forceinline__ void init(unsigned i, unsigned units) { n = i / units; p = i - n * units; }
-  __device__ __forceinline__ void advance(unsigned step, unsigned units) { p += step; while (p >= units) { p -= units; ++n; } }
-};
+constexpr int FB_EW = 8;           // units per thread of the elementwise passes (two-launch form)
 struct FChanCursor {                // flattened unit index of the tensor -> (offset in plane, channel)
   unsigned p, c;
   __device__ __forceinline__ void init(size_t i, unsigned units, unsigned C) { const size_t plane = i / units; p = (unsigned)(i - plane * units); c = (unsigned)(plane % C); }
@@ -82,24 +66,19 @@ bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__
 }
 
 // per channel: sum dy_eff * x_norm, sum dy_eff with dy_eff = RELU ? (y_pre > 0 ? dy : 0) : dy, one thread-block cluster per channel
+// this CTA's share of sum dy_eff * x_norm (a) and sum dy_eff (b) of channel c
 template <bool VEC, bool RELU>
-__global__ void __launch_bounds__(FB_THREADS)
-bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                           const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                           float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy) {
-  __shared__ float2 part;
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
-  const int c = blockIdx.y;
-  const bool affine = gamma != nullptr;
-  const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
-  constexpr int U = 4;
+__device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c, const float* __restrict__ dy, const float* __restrict__ x,
+                                                     float m, float is, float g, float bt, bool affine, unsigned rank, unsigned nranks,
+                                                     float& a, float& b) {
+  constexpr int U = BN_U;
+  constexpr int FB_THREADS = BN_THREADS;
   const unsigned units = VEC ? S / 4 : S;
-  const unsigned total = (unsigned)N * units;
-  const unsigned len = (total + nranks - 1) / nranks;
-  const unsigned lo = min(total, rank * len), hi = min(total, lo + len);
-  float a = 0.f, b = 0.f, a2 = 0.f, b2 = 0.f;
-  FPlaneCursor cur;
+  unsigned lo, hi;
+  bn_slice((unsigned)N * units, rank, nranks, lo, hi);
+  a = 0.f; b = 0.f;
+  float a2 = 0.f, b2 = 0.f;
+  PlaneCursor cur;
   unsigned i = lo + threadIdx.x;
   if (i < hi) cur.init(i, units);
   // masked upstream gradient and recomputed x_norm of one element
@@ -140,7 +119,22 @@ bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, co
     }
   }
   a += a2; b += b2;
-  fblock_sum2(a, b);
+}
+
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy) {
+  __shared__ float2 part;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+  const int c = blockIdx.y;
+  const bool affine = gamma != nullptr;
+  const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
+  float a, b;
+  bn_bwd_partial_fused<VEC, RELU>(N, C, S, c, dy, x, m, is, g, bt, affine, rank, nranks, a, b);
+  block_sum2(a, b);
   if (threadIdx.x == 0) part = make_float2(a, b);
   cluster.sync();
   if (rank == 0 && threadIdx.x == 0) {
@@ -149,6 +143,130 @@ bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, co
     sum_dy_xn[c] = (float)s1; sum_dy[c] = (float)s2;
   }
   cluster.sync();
+}
+
+// ---- one-launch forms -----------------------------------------------------------------------------------------------------
+// elementwise walk of this CTA's slice of channel c: f(unit offset) for every unit, BN_U independent units in flight
+template <typename F>
+__device__ __forceinline__ void bn_walk_slice(int N, int C, unsigned units, int c, unsigned rank, unsigned nranks, F&& f) {
+  unsigned lo, hi;
+  bn_slice((unsigned)N * units, rank, nranks, lo, hi);
+  PlaneCursor cur;
+  unsigned i = lo + threadIdx.x;
+  if (i < hi) cur.init(i, units);
+  for (; i < hi; i += BN_U * BN_THREADS) {
+    size_t off[BN_U];
+    bool ok[BN_U];
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      ok[u] = i + u * BN_THREADS < hi;
+      off[u] = ((size_t)cur.n * C + c) * units + cur.p;
+      cur.advance(BN_THREADS, units);
+    }
+    f(off, ok);
+  }
+}
+
+// statistics (bn_stats_kernel's code and order) + normalisation [+ ReLU] of one channel per cluster
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_fwd_onepass_kernel(int N, int C, int S, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float eps, float maf, int first, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean,
+                      float* __restrict__ run_var, float* __restrict__ y) {
+  __shared__ float2 part, stat;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+  const int c = blockIdx.y;
+  const float k = x[(size_t)c * S];
+  float a, b;
+  bn_channel_partial<VEC, 0>(N, C, S, c, x, nullptr, k, rank, nranks, a, b);
+  block_sum2(a, b);
+  if (threadIdx.x == 0) part = make_float2(a, b);
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned r = 0; r < nranks; ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
+    const double cnt = (double)N * S, m1 = s1 / cnt;
+    const float m = (float)((double)k + m1);
+    const float var_eps = (float)fmax(s2 / cnt - m1 * m1, 0.0) + eps;   // batch_norm_layer.cpp:183-186 (eps folded in before the average)
+    const float is = 1.0f / sqrtf(var_eps);
+    mean[c] = m;
+    invstd[c] = is;
+    if (first) { run_mean[c] = m; run_var[c] = var_eps; }                         // iter_ <= 1: copy (:199-204)
+    else { run_mean[c] = (1.f - maf) * m + maf * run_mean[c]; run_var[c] = (1.f - maf) * var_eps + maf * run_var[c]; }
+    for (unsigned r = 0; r < nranks; ++r) *cluster.map_shared_rank(&stat, r) = make_float2(m, is);
+  }
+  cluster.sync();                                   // partial sums read, statistics delivered to every CTA of the cluster
+  const float m = stat.x, is = stat.y;
+  const bool affine = gamma != nullptr;
+  const float g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
+  auto one = [&](float v) { const float o = bn_y(bn_xn(v, m, is), g, bt, affine); return RELU ? fmaxf(o, 0.f) : o; };
+  bn_walk_slice(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[BN_U], const bool (&ok)[BN_U]) {
+    if (VEC) {
+      float4 v[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) if (ok[u]) v[u] = reinterpret_cast<const float4*>(x)[off[u]];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u)
+        if (ok[u]) reinterpret_cast<float4*>(y)[off[u]] = make_float4(one(v[u].x), one(v[u].y), one(v[u].z), one(v[u].w));
+    } else {
+      float v[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) if (ok[u]) v[u] = x[off[u]];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) if (ok[u]) y[off[u]] = one(v[u]);
+    }
+  });
+}
+
+// dgamma / dbeta reduction + dx of one channel per cluster
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, const float* __restrict__ dy, const float* __restrict__ x,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy, float* __restrict__ dx) {
+  __shared__ float2 part, sums;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+  const int c = blockIdx.y;
+  const bool affine = gamma != nullptr;
+  const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
+  float a, b;
+  bn_bwd_partial_fused<VEC, RELU>(N, C, S, c, dy, x, m, is, g, bt, affine, rank, nranks, a, b);
+  block_sum2(a, b);
+  if (threadIdx.x == 0) part = make_float2(a, b);
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (unsigned r = 0; r < nranks; ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
+    const float2 out = make_float2((float)s1, (float)s2);
+    sum_dy_xn[c] = out.x; sum_dy[c] = out.y;
+    for (unsigned r = 0; r < nranks; ++r) *cluster.map_shared_rank(&sums, r) = out;
+  }
+  cluster.sync();
+  const float gi = g * is, mdy = sums.y * inv_cnt, mdx = sums.x * inv_cnt;
+  auto one = [&](float d, float xv) {
+    const float xn = bn_xn(xv, m, is);
+    if (RELU) d = d * (bn_y(xn, g, bt, affine) > 0.f ? 1.f : 0.f);
+    return gi * (d - mdy - xn * mdx);
+  };
+  bn_walk_slice(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[BN_U], const bool (&ok)[BN_U]) {
+    if (VEC) {
+      float4 d[BN_U], v[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u)
+        if (ok[u]) { d[u] = reinterpret_cast<const float4*>(dy)[off[u]]; v[u] = reinterpret_cast<const float4*>(x)[off[u]]; }
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u)
+        if (ok[u]) reinterpret_cast<float4*>(dx)[off[u]] = make_float4(one(d[u].x, v[u].x), one(d[u].y, v[u].y), one(d[u].z, v[u].z), one(d[u].w, v[u].w));
+    } else {
+      float d[BN_U], v[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) if (ok[u]) { d[u] = dy[off[u]]; v[u] = x[off[u]]; }
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) if (ok[u]) dx[off[u]] = one(d[u], v[u]);
+    }
+  });
 }
 
 // dx = gamma * invstd * (dy_eff - mean(dy_eff) - x_norm * mean(dy_eff * x_norm))
@@ -228,24 +346,29 @@ __global__ void accuracy_finish_kernel(const unsigned int* hits, int N, float* a
 int launch_bn_stats(int N, int C, int S, const float* x, float eps, float maf, int first, float* mean, float* invstd, float* run_mean,
                     float* run_var, bool vec, void* stream);
 
-static unsigned fb_cluster_size(int N, int C, int S) {
-  const size_t E = (size_t)N * S;
-  unsigned cs = 1;
-  while (cs < FB_CLUSTER && E / (cs * 2) >= 16384) cs *= 2;
-  while (cs < FB_CLUSTER && (size_t)C * cs < 2u * (unsigned)sm_count()) cs *= 2;
-  return cs;
+// B2C_BN_ONEPASS (default 1): statistics / reduction and the elementwise pass in one launch per BatchNorm direction
+static bool bn_onepass() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_BN_ONEPASS"); on = e ? atoi(e) : 1; }
+  return on != 0;
 }
-template <typename... Args>
-static void fb_launch_clustered(void (*kernel)(Args...), unsigned cs, int C, void* stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, C, 1);
-  cfg.blockDim = dim3(FB_THREADS, 1, 1);
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, args...);
+// dynamic shared memory nobody touches: bounds the CTAs per SM (B2C_BN_OCC, default 2) so that what the clusters in flight
+// read in phase 1 is still in L2 when they read it again in phase 2
+static size_t bn_onepass_pad() {
+  static long pad = -1;
+  if (pad < 0) {
+    const char* e = getenv("B2C_BN_OCC");
+    int occ = e ? atoi(e) : 2;
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    pad = occ >= 4 ? 0 : (long)(227 * 1024 / occ) - 3 * 1024;
+  }
+  return (size_t)pad;
+}
+template <typename K>
+static int bn_onepass_attr(K kernel) {
+  B2C_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bn_onepass_pad()));
+  return B2C_OK;
 }
 static bool fb_vec_ok(int S, std::initializer_list<const void*> ptrs) {
   if (S % 4) return false;
@@ -267,6 +390,18 @@ extern "C" int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, c
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   const bool vec = fb_vec_ok(S, {x, y});
+  if (bn_onepass()) {
+    const unsigned cs = bn_cluster_size(N, C, S);
+    const size_t pad = bn_onepass_pad();
+#define B2C_FWD1(V, R) do { if (int rc = bn_onepass_attr(bn_fwd_onepass_kernel<V, R>)) return rc; \
+    bn_launch_clustered(bn_fwd_onepass_kernel<V, R>, cs, C, pad, stream, N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
+                        save_mean, save_invstd, running_mean, running_var, y); } while (0)
+    if (vec) { if (relu) B2C_FWD1(true, true); else B2C_FWD1(true, false); }
+    else { if (relu) B2C_FWD1(false, true); else B2C_FWD1(false, false); }
+#undef B2C_FWD1
+    B2C_POST_LAUNCH();
+    return B2C_OK;
+  }
   if (int rc = launch_bn_stats(N, C, S, x, eps, moving_average_fraction, first_iteration, save_mean, save_invstd, running_mean, running_var, vec, stream)) return rc;
   const size_t units = (size_t)N * C * (vec ? S / 4 : S);
   const unsigned blocks = (unsigned)((units + 256 * FB_EW - 1) / (256 * FB_EW));
@@ -287,11 +422,22 @@ extern "C" int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   const bool vec = fb_vec_ok(S, {dy, x, dx});
-  const unsigned cs = fb_cluster_size(N, C, S);
-  if (vec) { if (relu) fb_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
-             else fb_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
-  else { if (relu) fb_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
-         else fb_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  const unsigned cs = bn_cluster_size(N, C, S);
+  if (bn_onepass()) {
+    const size_t pad = bn_onepass_pad();
+    const float inv_cnt1 = 1.0f / ((float)N * S);
+#define B2C_BWD1(V, R) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, R>)) return rc; \
+    bn_launch_clustered(bn_bwd_onepass_kernel<V, R>, cs, C, pad, stream, N, C, S, inv_cnt1, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx); } while (0)
+    if (vec) { if (relu) B2C_BWD1(true, true); else B2C_BWD1(true, false); }
+    else { if (relu) B2C_BWD1(false, true); else B2C_BWD1(false, false); }
+#undef B2C_BWD1
+    B2C_POST_LAUNCH();
+    return B2C_OK;
+  }
+  if (vec) { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+             else bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  else { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+         else bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
   B2C_POST_LAUNCH();
   const size_t units = (size_t)N * C * (vec ? S / 4 : S);
   const unsigned blocks = (unsigned)((units + 256 * FB_EW - 1) / (256 * FB_EW));

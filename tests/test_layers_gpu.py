@@ -71,6 +71,45 @@ def test_batchnorm_train(rng, shape):
     assert rel_err(host(DG), dg) < TOL and rel_err(host(DB), db) < TOL and rel_err(host(DX), dx) < 5e-5   # overwritten, not += 9
 
 
+@pytest.mark.parametrize("relu", [0, 1])
+@pytest.mark.parametrize("shape", [(4, 3, 5, 5), (8, 64, 14, 14), (2, 256, 7, 7), (3, 5, 1, 1), (8, 16, 64, 64), (64, 64, 56, 56), (37, 40, 30, 30)])
+def test_batchnorm_fused_is_bitwise_the_unfused_chain(rng, shape, relu):
+    """b2c_bn_forward_train_fused / b2c_bn_backward_fused (one launch each: cluster reduction + elementwise walk of the same slice)
+    against BatchNorm [+ ReLU] run as separate layers: same bits for y, the saved and running statistics, dgamma, dbeta and dx.
+    Shapes cover one CTA per channel, clusters of 2..8, float4 and scalar planes, slices that end inside a plane."""
+    N, Cc, H, W = shape
+    S = H * W
+    L = m.lib()
+    X = dev((rng.standard_normal(shape) * 1.5 + 0.3).astype(np.float32))
+    G, B = dev(rng.standard_normal(Cc).astype(np.float32)), dev(rng.standard_normal(Cc).astype(np.float32))
+    DY = dev(rng.standard_normal(shape).astype(np.float32))
+    out = []
+    for fused in (0, 1):
+        RM, RV = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+        SM, SI = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+        Y, DX = torch.empty_like(X), torch.empty_like(X)
+        DG, DB = torch.full((Cc,), 9.0, device="cuda"), torch.full((Cc,), 9.0, device="cuda")
+        for first in (1, 0):
+            if fused:
+                capi.check(L.b2c_bn_forward_train_fused(N, Cc, S, p(X), p(G), p(B), 1e-4, 0.9, first, p(RM), p(RV), p(SM), p(SI), p(Y), relu, st()))
+            else:
+                XN = torch.empty_like(X)
+                capi.check(L.b2c_bn_forward_train(N, Cc, S, p(X), p(G), p(B), 1e-4, 0.9, first, p(RM), p(RV), p(SM), p(SI), p(XN), p(Y), st()))
+                if relu:
+                    capi.check(L.b2c_relu_forward(X.numel(), p(Y), p(Y), 0.0, st()))
+        if fused:
+            capi.check(L.b2c_bn_backward_fused(N, Cc, S, p(DY), p(X), p(SM), p(SI), p(G), p(B), p(DG), p(DB), p(DX), relu, st()))
+        else:
+            D = DY
+            if relu:
+                D = torch.empty_like(DY)
+                capi.check(L.b2c_relu_backward(X.numel(), p(DY), p(Y), p(D), 0.0, st()))
+            capi.check(L.b2c_bn_backward(N, Cc, S, p(D), p(XN), p(G), p(SI), p(DG), p(DB), p(DX), st()))
+        out.append([host(t) for t in (Y, SM, SI, RM, RV, DG, DB, DX)])
+    for name, a, b in zip(("y", "mean", "invstd", "run_mean", "run_var", "dgamma", "dbeta", "dx"), out[0], out[1]):
+        assert np.array_equal(a, b), name
+
+
 @pytest.mark.parametrize("H,k,s,pad,method", [(112, 3, 2, 0, 0), (7, 7, 1, 0, 1), (8, 3, 2, 1, 0), (9, 2, 2, 0, 1), (13, 3, 2, 0, 0), (14, 3, 1, 1, 0)])
 def test_pooling(rng, H, k, s, pad, method):
     x = rng.standard_normal((2, 5, H, H)).astype(np.float32)

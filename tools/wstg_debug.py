@@ -10,7 +10,7 @@ from caffe_mpi_b200 import capi
 L = m.lib()
 L.b2c_debug_mbar_set_trap(0)
 shapes = [(2, 64, 8, 8, 64, 1, 0), (2, 32, 12, 12, 40, 3, 1), (3, 96, 14, 14, 72, 1, 0), (4, 64, 28, 28, 64, 3, 1), (2, 64, 56, 56, 256, 1, 0),
-          (64, 256, 14, 14, 256, 3, 1), (64, 64, 56, 56, 64, 3, 1), (64, 256, 56, 56, 64, 1, 0), (2, 32, 8, 80, 32, 3, 1), (5, 32, 4, 13, 40, 3, 1)]
+          (64, 256, 14, 14, 256, 3, 1), (64, 64, 56, 56, 64, 3, 1), (64, 256, 56, 56, 64, 1, 0), (2, 32, 8, 80, 32, 3, 1), (5, 32, 8, 13, 40, 3, 1)]
 if len(sys.argv) >= 8:
     shapes = [tuple(int(a) for a in sys.argv[1:8])]
 torch.manual_seed(0)
