@@ -241,7 +241,10 @@ def run_ours(args):
     model, N = args.model, args.batch
     math = {"fp32": capi.MATH_FP32, "tf32": capi.MATH_TF32, "3xtf32": capi.MATH_FP32_3XTF32}[args.math]
     kw = dict(default_channels=1, default_size=28, num_classes=10) if model == "lenet" else {}
-    t = host_api.Trainer(models.PROTOTXT[model](N), models.SOLVERS[model], batch=N, seed=1701 + rank, math=math, **kw)   # seed + rank, parallel.cpp:179-187
+    net_text = models.PROTOTXT[model](N)
+    if args.buckets > 0:
+        net_text = f"reduce_buckets: {args.buckets}\n" + net_text
+    t = host_api.Trainer(net_text, models.SOLVERS[model], batch=N, seed=1701 + rank, math=math, **kw)   # seed + rank, parallel.cpp:179-187
     if world > 1:
         ids = [t.new_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -317,6 +320,7 @@ def run_ours(args):
                                    + (f"bucketed NCCL allreduce of the {t.arena_floats() * 4 / 1e6:.1f} MB diff arena through P2PSync / ReduceScheduler overlapped with backward, "
                                       if world > 1 else "") + f"fused SGD-momentum update of {t.num_learnable()} learnable blobs; N={N}/GPU",
                        "model": model, "per_gpu_batch": N, "global_batch": N * world, "parallelism": f"dp{world}",
+                       "reduce_buckets": args.buckets if args.buckets > 0 else 6,
                        "math": {"fp32": "fp32-equivalent: bf16x3 split (staged fwd/dgrad kernel) and 3xTF32 split (all other conv kernels), fp32 accumulate",
                                 "tf32": "tf32 single pass (informational)", "3xtf32": "fp32-equivalent: 3xTF32 split everywhere"}[args.math],
                        "l2_policy": f"per-step activation working set {t.activation_floats() * 4 / 1e9:.2f} GB exceeds the 126 MB L2; every layer has its own blobs"},
@@ -396,6 +400,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE.json config of the model)")
     ap.add_argument("--math", default="fp32", choices=["fp32", "tf32", "3xtf32"],
                     help="fp32 = fp32-equivalent split-precision tensor-core math (the headline); tf32 = single-pass TF32 (informational)")
+    ap.add_argument("--buckets", type=int, default=0,
+                    help="NetParameter.reduce_buckets of the generated prototxt (0 = the reference's default, 6; caffe.proto:140)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (N = 1 only)")
     args = ap.parse_args()
     if not args.batch:

@@ -28,6 +28,18 @@ __device__ __forceinline__ void block_sum2(float& a, float& b) {
   __syncthreads();
 }
 
+// The elementwise expressions of the BatchNorm / ReLU / Eltwise chain, spelled with explicit-rounding intrinsics: nvcc contracts
+// a * b + c into an FMA wherever it sees one, and WHICH products it sees depends on the surrounding code (the unfused dx kernel
+// folded sum_dy * inv_cnt into the subtraction, the fused one folded the ReLU mask instead: 1-ulp differences in dx, found by
+// tests/test_layers_gpu.py).  Every kernel that claims the same bits goes through these.
+__device__ __forceinline__ float bn_xn(float x, float m, float is) { return __fmul_rn(__fsub_rn(x, m), is); }
+__device__ __forceinline__ float bn_y(float xn, float g, float bt, bool affine) { return affine ? __fmaf_rn(xn, g, bt) : xn; }
+__device__ __forceinline__ float relu_mask(float d, float y) { return __fmul_rn(d, y > 0.f ? 1.f : 0.f); }      // ReLU backward, slope 0
+__device__ __forceinline__ float bn_mean_term(float sum, float inv_cnt) { return __fmul_rn(sum, inv_cnt); }
+__device__ __forceinline__ float bn_dx(float d, float xn, float gi, float mdy, float mdx) {
+  return __fmul_rn(gi, __fmaf_rn(-xn, mdx, __fsub_rn(d, mdy)));
+}
+
 struct PlaneCursor {       // walks a channel's planes: flattened unit index -> (image n, offset p)
   unsigned n, p;
   __device__ __forceinline__ void init(unsigned i, unsigned units) { n = i / units; p = i - n * units; }
@@ -41,9 +53,11 @@ __device__ __forceinline__ void bn_slice(unsigned total, unsigned rank, unsigned
 }
 
 // MODE 0: a = sum (x-k), b = sum (x-k)^2   (q unused)      MODE 1: a = sum dy*xn, b = sum dy   (x = dy, q = xnorm)
-template <bool VEC, int MODE>
+// CACHE: every unit of x this thread loads is also parked in shared memory at [unit index - slice start] (the one-launch kernels
+// of layers_fused.cu read it back in their elementwise phase: same thread, same index, no barrier needed)
+template <bool VEC, int MODE, bool CACHE = false>
 __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, const float* __restrict__ x, const float* __restrict__ q,
-                                                   float k, unsigned rank, unsigned nranks, float& a, float& b) {
+                                                   float k, unsigned rank, unsigned nranks, float& a, float& b, void* cache = nullptr) {
   constexpr int U = BN_U;                                       // independent loads in flight per thread
   const unsigned units = VEC ? S / 4 : S;                       // units per plane
   unsigned lo, hi;
@@ -68,6 +82,7 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
       for (int u = 0; u < U; ++u) {
         v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(k, k, k, k);
         if (MODE == 1) w[u] = ok[u] ? reinterpret_cast<const float4*>(q)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CACHE && ok[u]) static_cast<float4*>(cache)[i + u * BN_THREADS - lo] = v[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -86,6 +101,7 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
       for (int u = 0; u < U; ++u) {
         v[u] = ok[u] ? x[off[u]] : k;
         if (MODE == 1) w[u] = ok[u] ? q[off[u]] : 0.f;
+        if (CACHE && ok[u]) static_cast<float*>(cache)[i + u * BN_THREADS - lo] = v[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {

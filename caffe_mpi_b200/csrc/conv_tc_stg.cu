@@ -568,7 +568,7 @@ static bool stg_enabled() {
 
 static bool stg_plane_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("B2C_CONV_STAGED_PLANE"); on = e ? atoi(e) : 0; }
+  if (on < 0) { const char* e = getenv("B2C_CONV_STAGED_PLANE"); on = e ? atoi(e) : 1; }
   return on != 0;
 }
 

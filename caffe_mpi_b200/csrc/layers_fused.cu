@@ -33,10 +33,6 @@ struct FChanCursor {                // flattened unit index of the tensor -> (of
   __device__ __forceinline__ void advance(unsigned step, unsigned units, unsigned C) { p += step; while (p >= units) { p -= units; if (++c == C) c = 0; } }
 };
 
-// the forward's expression, verbatim in both passes so that the recomputed mask and x_norm carry the same bits
-__device__ __forceinline__ float bn_xn(float x, float m, float is) { return (x - m) * is; }
-__device__ __forceinline__ float bn_y(float xn, float g, float bt, bool affine) { return affine ? xn * g + bt : xn; }
-
 template <bool VEC, bool RELU>
 __global__ void __launch_bounds__(256)
 bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__ x, const float* __restrict__ mean,
@@ -67,11 +63,14 @@ bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__
 
 // per channel: sum dy_eff * x_norm, sum dy_eff with dy_eff = RELU ? (y_pre > 0 ? dy : 0) : dy, one thread-block cluster per channel
 // this CTA's share of sum dy_eff * x_norm (a) and sum dy_eff (b) of channel c
-template <bool VEC, bool RELU>
+// MASK: 0 = dy as it is, 1 = ReLU mask recomputed from the forward's expression, 2 = ReLU mask from the tensor `ym` (the
+// post-activation output of the Eltwise sum this BatchNorm feeds: ym > 0)
+// CACHE: 1 = park every loaded unit of x in shared memory (cx[unit index - slice start]), 2 = x and the MASKED gradient (cd)
+// U: loads in flight per thread and stream; a thread visits its units in the same order whatever U is, so U does not change the sums
+template <bool VEC, int MASK, int CACHE = 0, int U = BN_U>
 __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c, const float* __restrict__ dy, const float* __restrict__ x,
-                                                     float m, float is, float g, float bt, bool affine, unsigned rank, unsigned nranks,
-                                                     float& a, float& b) {
-  constexpr int U = BN_U;
+                                                     const float* __restrict__ ym, float m, float is, float g, float bt, bool affine,
+                                                     unsigned rank, unsigned nranks, float& a, float& b, void* cx = nullptr, void* cd = nullptr) {
   constexpr int FB_THREADS = BN_THREADS;
   const unsigned units = VEC ? S / 4 : S;
   unsigned lo, hi;
@@ -82,9 +81,10 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
   unsigned i = lo + threadIdx.x;
   if (i < hi) cur.init(i, units);
   // masked upstream gradient and recomputed x_norm of one element
-  auto prep = [&](float& d, float xv) {
+  auto prep = [&](float& d, float xv, float yv) {
     const float xn = bn_xn(xv, m, is);
-    if (RELU) d = d * (bn_y(xn, g, bt, affine) > 0.f ? 1.f : 0.f);      // relu_bwd_kernel's own expression (sign of zero included)
+    if (MASK == 1) d = relu_mask(d, bn_y(xn, g, bt, affine));                 // the mask ReLU::Backward applies, from the recomputed pre-activation
+    if (MASK == 2) d = relu_mask(d, yv);
     return xn;
   };
   for (; i < hi; i += U * FB_THREADS) {
@@ -97,25 +97,32 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
       cur.advance(FB_THREADS, units);
     }
     if (VEC) {
-      float4 d[U], v[U];
+      float4 d[U], v[U], t[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         d[u] = ok[u] ? reinterpret_cast<const float4*>(dy)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
         v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(m, m, m, m);
+        t[u] = (MASK == 2 && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         // the accumulation order of layers.cu's bn_channel_partial<MODE 1>, so that fused == unfused bit for bit
-        const float nx = prep(d[u].x, v[u].x), ny = prep(d[u].y, v[u].y), nz = prep(d[u].z, v[u].z), nw = prep(d[u].w, v[u].w);
+        const float nx = prep(d[u].x, v[u].x, t[u].x), ny = prep(d[u].y, v[u].y, t[u].y), nz = prep(d[u].z, v[u].z, t[u].z), nw = prep(d[u].w, v[u].w, t[u].w);
         a = fmaf(d[u].x, nx, a); a2 = fmaf(d[u].y, ny, a2); a = fmaf(d[u].z, nz, a); a2 = fmaf(d[u].w, nw, a2);
         b += d[u].x + d[u].y; b2 += d[u].z + d[u].w;
+        if (CACHE >= 1 && ok[u]) static_cast<float4*>(cx)[i + u * FB_THREADS - lo] = v[u];
+        if (CACHE == 2 && ok[u]) static_cast<float4*>(cd)[i + u * FB_THREADS - lo] = d[u];
       }
     } else {
-      float d[U], v[U];
+      float d[U], v[U], t[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) { d[u] = ok[u] ? dy[off[u]] : 0.f; v[u] = ok[u] ? x[off[u]] : m; }
+      for (int u = 0; u < U; ++u) { d[u] = ok[u] ? dy[off[u]] : 0.f; v[u] = ok[u] ? x[off[u]] : m; t[u] = (MASK == 2 && ok[u]) ? ym[off[u]] : 0.f; }
 #pragma unroll
-      for (int u = 0; u < U; ++u) { const float xn = prep(d[u], v[u]); a = fmaf(d[u], xn, a); b += d[u]; }
+      for (int u = 0; u < U; ++u) {
+        const float xn = prep(d[u], v[u], t[u]); a = fmaf(d[u], xn, a); b += d[u];
+        if (CACHE >= 1 && ok[u]) static_cast<float*>(cx)[i + u * FB_THREADS - lo] = v[u];
+        if (CACHE == 2 && ok[u]) static_cast<float*>(cd)[i + u * FB_THREADS - lo] = d[u];
+      }
     }
   }
   a += a2; b += b2;
@@ -133,7 +140,7 @@ bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, co
   const bool affine = gamma != nullptr;
   const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
   float a, b;
-  bn_bwd_partial_fused<VEC, RELU>(N, C, S, c, dy, x, m, is, g, bt, affine, rank, nranks, a, b);
+  bn_bwd_partial_fused<VEC, RELU ? 1 : 0>(N, C, S, c, dy, x, nullptr, m, is, g, bt, affine, rank, nranks, a, b);
   block_sum2(a, b);
   if (threadIdx.x == 0) part = make_float2(a, b);
   cluster.sync();
@@ -146,127 +153,184 @@ bn_bwd_reduce_fused_kernel(int N, int C, int S, const float* __restrict__ dy, co
 }
 
 // ---- one-launch forms -----------------------------------------------------------------------------------------------------
-// elementwise walk of this CTA's slice of channel c: f(unit offset) for every unit, BN_U independent units in flight
-template <typename F>
+// A cluster of 1..8 CTAs per channel.  Phase 1: every CTA streams its slice of the channel through the reduction (the very code
+// and order of the two-launch kernels) and parks what it read in SHARED MEMORY (slices are <= ~100 KB at the BASELINE shapes; the
+// host picks the cached variant when the slice fits).  The partial sums meet through distributed shared memory: after one
+// cluster barrier EVERY thread adds the <= 8 partials in rank order (same bits everywhere, no second barrier for a broadcast).
+// Phase 2: the elementwise pass over the same slice reads the parked copy -- the tensor crosses HBM once per direction
+// (forward: read x, write y; backward: read dy [, mask], x, write dx [, d_res]) whatever the L2 does.  A closing cluster
+// barrier keeps the partials alive until every rank has read them.
+// elementwise walk of this CTA's slice of channel c: f(global unit offsets, slice-relative unit indices, validity)
+template <int U, typename F>
 __device__ __forceinline__ void bn_walk_slice(int N, int C, unsigned units, int c, unsigned rank, unsigned nranks, F&& f) {
   unsigned lo, hi;
   bn_slice((unsigned)N * units, rank, nranks, lo, hi);
   PlaneCursor cur;
   unsigned i = lo + threadIdx.x;
   if (i < hi) cur.init(i, units);
-  for (; i < hi; i += BN_U * BN_THREADS) {
-    size_t off[BN_U];
-    bool ok[BN_U];
+  for (; i < hi; i += U * BN_THREADS) {
+    size_t off[U];
+    unsigned idx[U];
+    bool ok[U];
 #pragma unroll
-    for (int u = 0; u < BN_U; ++u) {
+    for (int u = 0; u < U; ++u) {
       ok[u] = i + u * BN_THREADS < hi;
+      idx[u] = i + u * BN_THREADS - lo;
       off[u] = ((size_t)cur.n * C + c) * units + cur.p;
       cur.advance(BN_THREADS, units);
     }
-    f(off, ok);
+    f(off, idx, ok);
   }
 }
+// the cluster's partial (a, b) pairs added in rank order, by every thread
+__device__ __forceinline__ void bn_cluster_sum(cg::cluster_group& cluster, float2* part, unsigned nranks, double& s1, double& s2) {
+  float2 v[BN_CLUSTER];
+#pragma unroll
+  for (unsigned r = 0; r < (unsigned)BN_CLUSTER; ++r) v[r] = r < nranks ? *cluster.map_shared_rank(part, r) : make_float2(0.f, 0.f);
+  s1 = 0.0; s2 = 0.0;
+#pragma unroll
+  for (unsigned r = 0; r < (unsigned)BN_CLUSTER; ++r) if (r < nranks) { s1 += v[r].x; s2 += v[r].y; }
+}
 
-// statistics (bn_stats_kernel's code and order) + normalisation [+ ReLU] of one channel per cluster
-template <bool VEC, bool RELU>
-__global__ void __launch_bounds__(BN_THREADS)
+// statistics (bn_stats_kernel's code and order) + normalisation [+ residual add] [+ ReLU] of one channel per cluster
+// RES: y = [max(0, .)] (BatchNorm(x) + res) -- the Eltwise SUM (and its in-place ReLU) that consumes this layer, folded in
+// CACHE: the slice is parked in dynamic shared memory between the phases (else phase 2 reads x again from global memory / L2)
+template <bool VEC, bool RELU, bool RES, bool CACHE>
+__global__ void __launch_bounds__(BN_THREADS, 2)
 bn_fwd_onepass_kernel(int N, int C, int S, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float eps, float maf, int first, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean,
-                      float* __restrict__ run_var, float* __restrict__ y) {
-  __shared__ float2 part, stat;
+                      float* __restrict__ run_var, const float* __restrict__ res, float* __restrict__ y) {
+  extern __shared__ float4 bn_cache[];
+  __shared__ float2 part;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
   const int c = blockIdx.y;
   const float k = x[(size_t)c * S];
   float a, b;
-  bn_channel_partial<VEC, 0>(N, C, S, c, x, nullptr, k, rank, nranks, a, b);
+  bn_channel_partial<VEC, 0, CACHE>(N, C, S, c, x, nullptr, k, rank, nranks, a, b, bn_cache);
   block_sum2(a, b);
   if (threadIdx.x == 0) part = make_float2(a, b);
   cluster.sync();
+  double s1, s2;
+  bn_cluster_sum(cluster, &part, nranks, s1, s2);
+  const double cnt = (double)N * S, m1 = s1 / cnt;
+  const float m = (float)((double)k + m1);
+  const float var_eps = (float)fmax(s2 / cnt - m1 * m1, 0.0) + eps;   // batch_norm_layer.cpp:183-186 (eps folded in before the average)
+  const float is = 1.0f / sqrtf(var_eps);
   if (rank == 0 && threadIdx.x == 0) {
-    double s1 = 0.0, s2 = 0.0;
-    for (unsigned r = 0; r < nranks; ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
-    const double cnt = (double)N * S, m1 = s1 / cnt;
-    const float m = (float)((double)k + m1);
-    const float var_eps = (float)fmax(s2 / cnt - m1 * m1, 0.0) + eps;   // batch_norm_layer.cpp:183-186 (eps folded in before the average)
-    const float is = 1.0f / sqrtf(var_eps);
     mean[c] = m;
     invstd[c] = is;
     if (first) { run_mean[c] = m; run_var[c] = var_eps; }                         // iter_ <= 1: copy (:199-204)
     else { run_mean[c] = (1.f - maf) * m + maf * run_mean[c]; run_var[c] = (1.f - maf) * var_eps + maf * run_var[c]; }
-    for (unsigned r = 0; r < nranks; ++r) *cluster.map_shared_rank(&stat, r) = make_float2(m, is);
   }
-  cluster.sync();                                   // partial sums read, statistics delivered to every CTA of the cluster
-  const float m = stat.x, is = stat.y;
   const bool affine = gamma != nullptr;
   const float g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
-  auto one = [&](float v) { const float o = bn_y(bn_xn(v, m, is), g, bt, affine); return RELU ? fmaxf(o, 0.f) : o; };
-  bn_walk_slice(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[BN_U], const bool (&ok)[BN_U]) {
+  auto one = [&](float v, float r) {
+    float o = bn_y(bn_xn(v, m, is), g, bt, affine);
+    if (RES) o = __fadd_rn(o, r);                     // add_relu_kernel's a + b
+    return RELU ? fmaxf(o, 0.f) : o;
+  };
+  bn_walk_slice<BN_U>(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[BN_U], const unsigned (&idx)[BN_U], const bool (&ok)[BN_U]) {
     if (VEC) {
-      float4 v[BN_U];
+      float4 v[BN_U], r[BN_U];
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) if (ok[u]) v[u] = reinterpret_cast<const float4*>(x)[off[u]];
+      for (int u = 0; u < BN_U; ++u) {
+        if (ok[u]) v[u] = CACHE ? bn_cache[idx[u]] : reinterpret_cast<const float4*>(x)[off[u]];
+        r[u] = (RES && ok[u]) ? reinterpret_cast<const float4*>(res)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < BN_U; ++u)
-        if (ok[u]) reinterpret_cast<float4*>(y)[off[u]] = make_float4(one(v[u].x), one(v[u].y), one(v[u].z), one(v[u].w));
+        if (ok[u]) reinterpret_cast<float4*>(y)[off[u]] = make_float4(one(v[u].x, r[u].x), one(v[u].y, r[u].y), one(v[u].z, r[u].z), one(v[u].w, r[u].w));
     } else {
-      float v[BN_U];
+      const float* cache1 = reinterpret_cast<const float*>(bn_cache);
+      float v[BN_U], r[BN_U];
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) if (ok[u]) v[u] = x[off[u]];
+      for (int u = 0; u < BN_U; ++u) { if (ok[u]) v[u] = CACHE ? cache1[idx[u]] : x[off[u]]; r[u] = (RES && ok[u]) ? res[off[u]] : 0.f; }
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) if (ok[u]) y[off[u]] = one(v[u]);
+      for (int u = 0; u < BN_U; ++u) if (ok[u]) y[off[u]] = one(v[u], r[u]);
     }
   });
+  cluster.sync();                                   // nobody leaves while a peer may still be reading its partial sums
 }
 
 // dgamma / dbeta reduction + dx of one channel per cluster
-template <bool VEC, bool RELU>
-__global__ void __launch_bounds__(BN_THREADS)
-bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, const float* __restrict__ dy, const float* __restrict__ x,
-                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, float* __restrict__ sum_dy_xn, float* __restrict__ sum_dy, float* __restrict__ dx) {
-  __shared__ float2 part, sums;
+// MASK == 2 (residual form): dy is the diff of the Eltwise sum's top, ym its (post-ReLU) data; the masked gradient is also what the
+// sum's OTHER bottom receives: written to d_res when that is not null (EltwiseLayer::Backward's second copy)
+// CACHE: 0 = phase 2 reads everything again, 1 = x parked in shared memory, 2 = x and the masked gradient parked
+template <bool VEC, int MASK, int CACHE>
+__global__ void __launch_bounds__(BN_THREADS, 2)
+bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, const float* __restrict__ dy, const float* __restrict__ x,
+                      const float* __restrict__ ym, const float* __restrict__ mean, const float* __restrict__ invstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sum_dy_xn,
+                      float* __restrict__ sum_dy, float* __restrict__ dx, float* __restrict__ d_res) {
+  constexpr int U = MASK == 2 ? 2 : BN_U;           // three input streams in the residual form: fewer units in flight per stream (64 registers)
+  extern __shared__ float4 bn_cache[];
+  __shared__ float2 part;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
   const int c = blockIdx.y;
   const bool affine = gamma != nullptr;
   const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
+  // the two parked streams: x first, the masked gradient behind it (slice_units units each)
+  void* cx = bn_cache;
+  void* cd = VEC ? static_cast<void*>(bn_cache + slice_units) : static_cast<void*>(reinterpret_cast<float*>(bn_cache) + slice_units);
   float a, b;
-  bn_bwd_partial_fused<VEC, RELU>(N, C, S, c, dy, x, m, is, g, bt, affine, rank, nranks, a, b);
+  bn_bwd_partial_fused<VEC, MASK, CACHE, U>(N, C, S, c, dy, x, ym, m, is, g, bt, affine, rank, nranks, a, b, cx, cd);
   block_sum2(a, b);
   if (threadIdx.x == 0) part = make_float2(a, b);
   cluster.sync();
-  if (rank == 0 && threadIdx.x == 0) {
-    double s1 = 0.0, s2 = 0.0;
-    for (unsigned r = 0; r < nranks; ++r) { const float2 v = *cluster.map_shared_rank(&part, r); s1 += v.x; s2 += v.y; }
-    const float2 out = make_float2((float)s1, (float)s2);
-    sum_dy_xn[c] = out.x; sum_dy[c] = out.y;
-    for (unsigned r = 0; r < nranks; ++r) *cluster.map_shared_rank(&sums, r) = out;
-  }
-  cluster.sync();
-  const float gi = g * is, mdy = sums.y * inv_cnt, mdx = sums.x * inv_cnt;
-  auto one = [&](float d, float xv) {
+  double s1, s2;
+  bn_cluster_sum(cluster, &part, nranks, s1, s2);
+  const float sdx = (float)s1, sdy = (float)s2;
+  if (rank == 0 && threadIdx.x == 0) { sum_dy_xn[c] = sdx; sum_dy[c] = sdy; }
+  const float gi = __fmul_rn(g, is), mdy = bn_mean_term(sdy, inv_cnt), mdx = bn_mean_term(sdx, inv_cnt);
+  // upstream gradient (masked in place unless it comes from the cache, where it already is) -> dx
+  auto one = [&](float& d, float xv, float yv) {
     const float xn = bn_xn(xv, m, is);
-    if (RELU) d = d * (bn_y(xn, g, bt, affine) > 0.f ? 1.f : 0.f);
-    return gi * (d - mdy - xn * mdx);
+    if (CACHE != 2) {
+      if (MASK == 1) d = relu_mask(d, bn_y(xn, g, bt, affine));
+      if (MASK == 2) d = relu_mask(d, yv);
+    }
+    return bn_dx(d, xn, gi, mdy, mdx);
   };
-  bn_walk_slice(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[BN_U], const bool (&ok)[BN_U]) {
+  bn_walk_slice<U>(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[U], const unsigned (&idx)[U], const bool (&ok)[U]) {
     if (VEC) {
-      float4 d[BN_U], v[BN_U];
+      float4 d[U], v[U], t[U];
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u)
-        if (ok[u]) { d[u] = reinterpret_cast<const float4*>(dy)[off[u]]; v[u] = reinterpret_cast<const float4*>(x)[off[u]]; }
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+          d[u] = CACHE == 2 ? static_cast<const float4*>(cd)[idx[u]] : reinterpret_cast<const float4*>(dy)[off[u]];
+          v[u] = CACHE >= 1 ? static_cast<const float4*>(cx)[idx[u]] : reinterpret_cast<const float4*>(x)[off[u]];
+        }
+        t[u] = (MASK == 2 && CACHE != 2 && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u)
-        if (ok[u]) reinterpret_cast<float4*>(dx)[off[u]] = make_float4(one(d[u].x, v[u].x), one(d[u].y, v[u].y), one(d[u].z, v[u].z), one(d[u].w, v[u].w));
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) {
+          float4 o;
+          o.x = one(d[u].x, v[u].x, t[u].x); o.y = one(d[u].y, v[u].y, t[u].y); o.z = one(d[u].z, v[u].z, t[u].z); o.w = one(d[u].w, v[u].w, t[u].w);
+          reinterpret_cast<float4*>(dx)[off[u]] = o;
+          if (MASK == 2 && d_res) reinterpret_cast<float4*>(d_res)[off[u]] = d[u];
+        }
     } else {
-      float d[BN_U], v[BN_U];
+      float d[U], v[U], t[U];
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) if (ok[u]) { d[u] = dy[off[u]]; v[u] = x[off[u]]; }
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+          d[u] = CACHE == 2 ? static_cast<const float*>(cd)[idx[u]] : dy[off[u]];
+          v[u] = CACHE >= 1 ? static_cast<const float*>(cx)[idx[u]] : x[off[u]];
+        }
+        t[u] = (MASK == 2 && CACHE != 2 && ok[u]) ? ym[off[u]] : 0.f;
+      }
 #pragma unroll
-      for (int u = 0; u < BN_U; ++u) if (ok[u]) dx[off[u]] = one(d[u], v[u]);
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) {
+          dx[off[u]] = one(d[u], v[u], t[u]);
+          if (MASK == 2 && d_res) d_res[off[u]] = d[u];
+        }
     }
   });
+  cluster.sync();                                   // nobody leaves while a peer may still be reading its partial sums
 }
 
 // dx = gamma * invstd * (dy_eff - mean(dy_eff) - x_norm * mean(dy_eff * x_norm))
@@ -284,11 +348,11 @@ bn_bwd_dx_fused_kernel(size_t total_units, int C, int S, float inv_cnt, const fl
 #pragma unroll 2
   for (int k = 0; k < FB_EW && i < total_units; ++k, i += 256) {
     const float m = mean[cur.c], is = invstd[cur.c], g = affine ? gamma[cur.c] : 1.f, bt = affine ? beta[cur.c] : 0.f;
-    const float gi = g * is, mdy = sum_dy[cur.c] * inv_cnt, mdx = sum_dy_xn[cur.c] * inv_cnt;
+    const float gi = __fmul_rn(g, is), mdy = bn_mean_term(sum_dy[cur.c], inv_cnt), mdx = bn_mean_term(sum_dy_xn[cur.c], inv_cnt);
     auto one = [&](float d, float xv) {
       const float xn = bn_xn(xv, m, is);
-      if (RELU) d = d * (bn_y(xn, g, bt, affine) > 0.f ? 1.f : 0.f);
-      return gi * (d - mdy - xn * mdx);
+      if (RELU) d = relu_mask(d, bn_y(xn, g, bt, affine));
+      return bn_dx(d, xn, gi, mdy, mdx);
     };
     if (VEC) {
       const float4 d = reinterpret_cast<const float4*>(dy)[i], v = reinterpret_cast<const float4*>(x)[i];
@@ -313,12 +377,12 @@ relu_bwd2_kernel(size_t n, int vec, const float* __restrict__ dy, const float* _
   const size_t n4 = vec ? n / 4 : 0, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
   for (size_t i = tid; i < n4; i += step) {
     const float4 d = reinterpret_cast<const float4*>(dy)[i], v = reinterpret_cast<const float4*>(y)[i];
-    const float4 o = make_float4(d.x * (v.x > 0 ? 1.f : 0.f), d.y * (v.y > 0 ? 1.f : 0.f), d.z * (v.z > 0 ? 1.f : 0.f), d.w * (v.w > 0 ? 1.f : 0.f));
+    const float4 o = make_float4(relu_mask(d.x, v.x), relu_mask(d.y, v.y), relu_mask(d.z, v.z), relu_mask(d.w, v.w));
     if (dxa) reinterpret_cast<float4*>(dxa)[i] = o;
     if (dxb) reinterpret_cast<float4*>(dxb)[i] = o;
   }
   for (size_t i = n4 * 4 + tid; i < n; i += step) {
-    const float o = dy[i] * (y[i] > 0 ? 1.f : 0.f);
+    const float o = relu_mask(dy[i], y[i]);
     if (dxa) dxa[i] = o;
     if (dxb) dxb[i] = o;
   }
@@ -352,22 +416,22 @@ static bool bn_onepass() {
   if (on < 0) { const char* e = getenv("B2C_BN_ONEPASS"); on = e ? atoi(e) : 1; }
   return on != 0;
 }
-// dynamic shared memory nobody touches: bounds the CTAs per SM (B2C_BN_OCC, default 2) so that what the clusters in flight
-// read in phase 1 is still in L2 when they read it again in phase 2
-static size_t bn_onepass_pad() {
-  static long pad = -1;
-  if (pad < 0) {
-    const char* e = getenv("B2C_BN_OCC");
-    int occ = e ? atoi(e) : 2;
-    if (occ < 1) occ = 1;
-    if (occ > 4) occ = 4;
-    pad = occ >= 4 ? 0 : (long)(227 * 1024 / occ) - 3 * 1024;
-  }
-  return (size_t)pad;
+// bytes of one parked stream of the largest slice (rank 0's) of a channel, and the shared-memory budget of one CTA when two
+// share an SM (228 KB per SM, 1 KB reserved per CTA, the kernels' static arrays)
+static size_t bn_slice_bytes(int N, int S, bool vec, unsigned cs, unsigned* units_out) {
+  const size_t total = (size_t)N * (vec ? S / 4 : S);
+  const size_t units = (total + cs - 1) / cs;
+  if (units_out) *units_out = (unsigned)units;
+  return units * (vec ? 16 : 4);
+}
+static size_t bn_cache_budget() {
+  static long v = -1;
+  if (v < 0) { const char* e = getenv("B2C_BN_CACHE_KB"); v = e ? atol(e) * 1024 : 110 * 1024; }   // 0: never park (phase 2 re-reads global memory)
+  return (size_t)v;
 }
 template <typename K>
-static int bn_onepass_attr(K kernel) {
-  B2C_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bn_onepass_pad()));
+static int bn_onepass_attr(K kernel, size_t smem) {
+  B2C_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B2C_OK;
 }
 static bool fb_vec_ok(int S, std::initializer_list<const void*> ptrs) {
@@ -381,24 +445,30 @@ static bool fb_vec_ok(int S, std::initializer_list<const void*> ptrs) {
 using namespace b2c;
 #define FNEED(cond, msg) do { if (!(cond)) return fail(B2C_ERR_INVALID, msg); } while (0)
 
-extern "C" int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
-                                          float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
-                                          float* save_mean, float* save_invstd, float* y, int relu, void* stream) {
+static int bn_forward_fused_impl(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                                 float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                                 float* save_mean, float* save_invstd, const float* residual, float* y, int relu, void* stream) {
   FNEED(x && y && save_mean && save_invstd && running_mean && running_var && N > 0 && C > 0 && S > 0, "b2c_bn_forward_train_fused: bad argument");
   FNEED((gamma == nullptr) == (beta == nullptr), "b2c_bn_forward_train_fused: gamma and beta go together");
   FNEED((size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_forward_train_fused: channel extent out of range");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
-  const bool vec = fb_vec_ok(S, {x, y});
-  if (bn_onepass()) {
+  const bool vec = fb_vec_ok(S, {x, y, residual});
+  if (bn_onepass() || residual) {
     const unsigned cs = bn_cluster_size(N, C, S);
-    const size_t pad = bn_onepass_pad();
-#define B2C_FWD1(V, R) do { if (int rc = bn_onepass_attr(bn_fwd_onepass_kernel<V, R>)) return rc; \
-    bn_launch_clustered(bn_fwd_onepass_kernel<V, R>, cs, C, pad, stream, N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
-                        save_mean, save_invstd, running_mean, running_var, y); } while (0)
-    if (vec) { if (relu) B2C_FWD1(true, true); else B2C_FWD1(true, false); }
-    else { if (relu) B2C_FWD1(false, true); else B2C_FWD1(false, false); }
+    const size_t slice = bn_slice_bytes(N, S, vec, cs, nullptr);
+    const bool park = slice <= bn_cache_budget();
+    const size_t smem = park ? slice : 0;
+#define B2C_FWD0(V, R, Q, P) do { if (int rc = bn_onepass_attr(bn_fwd_onepass_kernel<V, R, Q, P>, smem)) return rc; \
+    bn_launch_clustered(bn_fwd_onepass_kernel<V, R, Q, P>, cs, C, smem, stream, N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
+                        save_mean, save_invstd, running_mean, running_var, residual, y); } while (0)
+#define B2C_FWD1(V, R, Q) do { if (park) B2C_FWD0(V, R, Q, true); else B2C_FWD0(V, R, Q, false); } while (0)
+#define B2C_FWD2(V, R) do { if (residual) B2C_FWD1(V, R, true); else B2C_FWD1(V, R, false); } while (0)
+    if (vec) { if (relu) B2C_FWD2(true, true); else B2C_FWD2(true, false); }
+    else { if (relu) B2C_FWD2(false, true); else B2C_FWD2(false, false); }
+#undef B2C_FWD2
 #undef B2C_FWD1
+#undef B2C_FWD0
     B2C_POST_LAUNCH();
     return B2C_OK;
   }
@@ -414,23 +484,45 @@ extern "C" int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, c
   return B2C_OK;
 }
 
-extern "C" int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
-                                     const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream) {
+extern "C" int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                                          float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                                          float* save_mean, float* save_invstd, float* y, int relu, void* stream) {
+  return bn_forward_fused_impl(N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, running_mean, running_var, save_mean,
+                               save_invstd, nullptr, y, relu, stream);
+}
+// y = [max(0, .)] (BatchNorm(x) + residual): BatchNorm -> Eltwise SUM [-> in-place ReLU] in one launch
+extern "C" int b2c_bn_forward_train_fused_res(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                                              float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                                              float* save_mean, float* save_invstd, const float* residual, float* y, int relu, void* stream) {
+  FNEED(residual, "b2c_bn_forward_train_fused_res: null residual");
+  return bn_forward_fused_impl(N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, running_mean, running_var, save_mean,
+                               save_invstd, residual, y, relu, stream);
+}
+
+static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const float* x, const float* y_mask, const float* save_mean,
+                                  const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx,
+                                  float* d_residual, int relu, void* stream) {
   FNEED(dy && x && save_mean && save_invstd && dgamma && dbeta && dx, "b2c_bn_backward_fused: null (dgamma/dbeta double as the reduction scratch)");
   FNEED((gamma == nullptr) == (beta == nullptr), "b2c_bn_backward_fused: gamma and beta go together");
   FNEED(N > 0 && C > 0 && S > 0 && (size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_backward_fused: channel extent out of range");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
-  const bool vec = fb_vec_ok(S, {dy, x, dx});
+  const bool vec = fb_vec_ok(S, {dy, x, dx, y_mask, d_residual});
   const unsigned cs = bn_cluster_size(N, C, S);
-  if (bn_onepass()) {
-    const size_t pad = bn_onepass_pad();
+  if (bn_onepass() || y_mask) {
+    unsigned slice_units = 0;
+    const size_t slice = bn_slice_bytes(N, S, vec, cs, &slice_units);
+    const int park = 2 * slice <= bn_cache_budget() ? 2 : slice <= bn_cache_budget() ? 1 : 0;      // x and the masked gradient, x only, nothing
+    const size_t smem = (size_t)park * slice;
     const float inv_cnt1 = 1.0f / ((float)N * S);
-#define B2C_BWD1(V, R) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, R>)) return rc; \
-    bn_launch_clustered(bn_bwd_onepass_kernel<V, R>, cs, C, pad, stream, N, C, S, inv_cnt1, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx); } while (0)
-    if (vec) { if (relu) B2C_BWD1(true, true); else B2C_BWD1(true, false); }
-    else { if (relu) B2C_BWD1(false, true); else B2C_BWD1(false, false); }
+#define B2C_BWD0(V, M, P) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P>, smem)) return rc; \
+    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
+                        gamma, beta, dgamma, dbeta, dx, d_residual); } while (0)
+#define B2C_BWD1(V, M) do { if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
+    if (vec) { if (y_mask) B2C_BWD1(true, 2); else if (relu) B2C_BWD1(true, 1); else B2C_BWD1(true, 0); }
+    else { if (y_mask) B2C_BWD1(false, 2); else if (relu) B2C_BWD1(false, 1); else B2C_BWD1(false, 0); }
 #undef B2C_BWD1
+#undef B2C_BWD0
     B2C_POST_LAUNCH();
     return B2C_OK;
   }
@@ -449,6 +541,20 @@ extern "C" int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const
          else bn_bwd_dx_fused_kernel<false, false><<<blocks, 256, 0, st>>>(units, C, S, inv_cnt, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx); }
   B2C_POST_LAUNCH();
   return B2C_OK;
+}
+
+extern "C" int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
+                                     const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream) {
+  return bn_backward_fused_impl(N, C, S, dy, x, nullptr, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx, nullptr, relu, stream);
+}
+// backward of BatchNorm -> Eltwise SUM -> ReLU run as one layer: d_sum / y_sum are the diff and the (post-ReLU) data of the sum's top;
+// dx = BatchNorm backward of d_sum * (y_sum > 0); that masked gradient is also written to d_residual (the sum's other bottom) when
+// d_residual is not null
+extern "C" int b2c_bn_backward_fused_res(int N, int C, int S, const float* d_sum, const float* y_sum, const float* x, const float* save_mean,
+                                         const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
+                                         float* dx, float* d_residual, void* stream) {
+  FNEED(y_sum, "b2c_bn_backward_fused_res: null y_sum");
+  return bn_backward_fused_impl(N, C, S, d_sum, x, y_sum, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx, d_residual, 1, stream);
 }
 
 extern "C" int b2c_add_relu(size_t n, const float* a, const float* b, float* y, void* stream) {

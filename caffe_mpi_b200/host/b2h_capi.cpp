@@ -296,6 +296,10 @@ int b2h_trainer_forward_backward(void* hv, float* loss) {
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({ *loss = h->net->ForwardBackward(); });
 }
+int b2h_trainer_clear_param_diffs(void* hv) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ h->net->ClearParamDiffs(); });
+}
 int b2h_trainer_sync(void* hv) { (void)hv; B2H_TRY({ CUDA_CHECK(cudaStreamSynchronize(Caffe::thread_stream())); CUDA_CHECK(cudaDeviceSynchronize()); }); }
 int b2h_trainer_loss(void* hv, float* loss) {
   auto* h = static_cast<TrainerHandle*>(hv);

@@ -45,6 +45,15 @@ void BatchNormLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) {
 }
 void BatchNormLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
+  if (res_sum_) {
+    // residual tail: sum_top = max(0, BatchNorm(x) + other); this layer's own top blob is not materialised
+    B2C_CHECK(b2c_bn_forward_train_fused_res(N, C, Sp, b[0]->gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
+                                             scale_bias_ ? blobs_[4]->gpu_data() : nullptr, eps_, maf_, iter_ <= 1 ? 1 : 0,
+                                             blobs_[0]->mutable_gpu_data(), blobs_[1]->mutable_gpu_data(), save_mean_.mutable_gpu_data(),
+                                             save_invstd_.mutable_gpu_data(), res_other_->gpu_data(), res_sum_->mutable_gpu_data(), 1, S()));
+    ++iter_;
+    return;
+  }
   if (recompute_ && t[0] != b[0]) {
     // fused form: no x_norm blob (backward recomputes it from the bottom), optional ReLU on the way out
     B2C_CHECK(b2c_bn_forward_train_fused(N, C, Sp, b[0]->gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
@@ -65,6 +74,13 @@ void BatchNormLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>&, c
   const int N = b[0]->shape(0), C = b[0]->shape(1), Sp = (int)(b[0]->count() / ((size_t)N * C));
   float* dg = scale_bias_ ? blobs_[3]->mutable_gpu_diff() : scratch_.mutable_gpu_data();
   float* db = scale_bias_ ? blobs_[4]->mutable_gpu_diff() : scratch_.mutable_gpu_data() + C;
+  if (res_sum_) {
+    B2C_CHECK(b2c_bn_backward_fused_res(N, C, Sp, res_sum_->gpu_diff(), res_sum_->gpu_data(), b[0]->gpu_data(), save_mean_.gpu_data(),
+                                        save_invstd_.gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
+                                        scale_bias_ ? blobs_[4]->gpu_data() : nullptr, dg, db, b[0]->mutable_gpu_diff(),
+                                        res_prop_ ? res_other_->mutable_gpu_diff() : nullptr, S()));
+    return;
+  }
   if (recompute_ && t[0] != b[0]) {
     B2C_CHECK(b2c_bn_backward_fused(N, C, Sp, t[0]->gpu_diff(), b[0]->gpu_data(), save_mean_.gpu_data(), save_invstd_.gpu_data(),
                                     scale_bias_ ? blobs_[3]->gpu_data() : nullptr, scale_bias_ ? blobs_[4]->gpu_data() : nullptr, dg, db,
@@ -106,6 +122,7 @@ void PoolingLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, 
 // ================================================================================================ Eltwise SUM
 void EltwiseLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   B2_CHECK(b.size() >= 2, "Eltwise needs two bottoms");
+  if (fused_away_) return;
   if (fuse_relu_ && b.size() == 2) {        // y = max(0, a + b): the in-place ReLU that follows is folded in
     B2C_CHECK(b2c_add_relu(t[0]->count(), b[0]->gpu_data(), b[1]->gpu_data(), t[0]->mutable_gpu_data(), S()));
     return;
@@ -114,6 +131,7 @@ void EltwiseLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   for (size_t i = 2; i < b.size(); ++i) B2C_CHECK(b2c_add(t[0]->count(), t[0]->gpu_data(), b[i]->gpu_data(), t[0]->mutable_gpu_data(), S()));
 }
 void EltwiseLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
+  if (fused_away_) return;
   if (fuse_relu_ && b.size() == 2) {        // dx_a = dx_b = dy * (y > 0): ReLU backward + the two copies of SUM's backward
     if (pd[0] || pd[1])
       B2C_CHECK(b2c_relu_backward2(t[0]->count(), t[0]->gpu_diff(), t[0]->gpu_data(), pd[0] ? b[0]->mutable_gpu_diff() : nullptr,
@@ -449,6 +467,41 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       }
     }
   }
+  // Residual tails (B2C_FUSE_RES=0 disables): BatchNorm -> Eltwise(SUM, 2 bottoms) -> in-place ReLU.  The BatchNorm that runs LAST
+  // among the producers of the sum's bottoms takes over the sum and the ReLU in both directions (csrc/layers_fused.cu, *_res): its
+  // top is not materialised, four passes over a block-output-sized tensor go away per block and step.  Conditions: the
+  // BatchNorm's top has no other consumer, nothing between it and the sum rewrites the other operand, the sum is the first
+  // backward writer of both bottoms (no shadow diffs).
+  {
+    const char* e = getenv("B2C_FUSE");
+    const char* er = getenv("B2C_FUSE_RES");
+    const bool fuse_res = (!e || atoi(e) != 0) && (!er || atoi(er) != 0);
+    for (size_t i = 0; fuse_res && i < layers_.size(); ++i) {
+      auto* el = dynamic_cast<EltwiseLayer*>(layers_[i].get());
+      Node& en = nodes_[i];
+      if (!el || !el->fuse_relu() || en.bottom.size() != 2 || !en.need_backward) continue;
+      if (!en.accumulate_bottom.empty() || en.bottom_diff_tmp[0] || en.bottom_diff_tmp[1]) continue;
+      int prod[2] = {-1, -1};
+      for (int k = 0; k < 2; ++k)
+        for (int j = (int)i - 1; j >= 0 && prod[k] < 0; --j)
+          for (Blob* tb : nodes_[j].top) if (tb == en.bottom[k]) prod[k] = j;
+      if (prod[0] < 0 || prod[1] < 0 || prod[0] == prod[1]) continue;
+      const int k = prod[0] > prod[1] ? 0 : 1, j = prod[k];
+      auto* bn = dynamic_cast<BatchNormLayer*>(layers_[j].get());
+      if (!bn || !bn->recompute() || bn->fuse_relu() || nodes_[j].top[0] == nodes_[j].bottom[0] || !en.propagate_down[k]) continue;
+      int consumers = 0;
+      for (size_t l = 0; l < nodes_.size(); ++l)
+        for (Blob* bb : nodes_[l].bottom) if (bb == en.bottom[k]) ++consumers;
+      bool other_rewritten = false;
+      for (size_t l = (size_t)j + 1; l < i; ++l) {       // ... nor reads it (its backward would add into a diff this layer has yet to write)
+        for (Blob* tb : nodes_[l].top) if (tb == en.bottom[1 - k]) other_rewritten = true;
+        for (Blob* bb : nodes_[l].bottom) if (bb == en.bottom[1 - k]) other_rewritten = true;
+      }
+      if (consumers != 1 || other_rewritten) continue;
+      bn->set_residual(en.bottom[1 - k], en.top[0], en.propagate_down[1 - k]);
+      el->set_fused_away(true);
+    }
+  }
   solver_.reset(new SGDSolver(sp));
   solver_->SetParams(learnable_, specs);
   for (auto& l : layers_)
@@ -522,6 +575,11 @@ float TrainNet::ForwardBackward() {
   Forward(false);
   Backward(false);              // diffs stay in place for inspection; Step() is the path that reduces + updates
   return last_loss();
+}
+void TrainNet::ClearParamDiffs() {
+  // the reference's solver relies on ApplyUpdate clearing the diffs (solver.cpp:237-239) and so does Step(); a caller that
+  // ran ForwardBackward() for inspection clears them before stepping, as with Net::ClearParamDiffs
+  CUDA_CHECK(cudaMemsetAsync(solver_->arena().diff(), 0, sizeof(float) * solver_->arena().total(), S()));
 }
 void TrainNet::Step(bool copy_input_from_host) {
   // Solver::Step (solver.cpp:277-288): iter_size micro-batches accumulate into the parameter diffs (weight / bias

@@ -47,7 +47,15 @@ class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_b
  public:
   void set_iter(int i) { iter_ = i; }
   void set_fusion(bool recompute_xnorm, bool fuse_relu) { recompute_ = recompute_xnorm; fuse_relu_ = fuse_relu; }
+  bool recompute() const { return recompute_; }
+  bool fuse_relu() const { return fuse_relu_; }
+  // Residual tail: this layer also does the Eltwise SUM (+ in-place ReLU) that consumes its top.  Forward writes
+  // max(0, BatchNorm(x) + other) into sum_top; backward takes sum_top's diff / data and also writes other's diff.
+  void set_residual(Blob* other, Blob* sum_top, bool propagate_other) { res_other_ = other; res_sum_ = sum_top; res_prop_ = propagate_other; }
  protected:
+  Blob* res_other_ = nullptr;
+  Blob* res_sum_ = nullptr;
+  bool res_prop_ = false;
   Blob xnorm_, save_mean_, save_invstd_, scratch_;
 };
 
@@ -70,8 +78,11 @@ class EltwiseLayer : public LayerBase {        // SUM with unit coefficients (th
  public:
   using LayerBase::LayerBase;
   void set_fuse_relu(bool v) { fuse_relu_ = v; }
+  bool fuse_relu() const { return fuse_relu_; }
+  void set_fused_away(bool v) { fused_away_ = v; }     // the BatchNorm layer that produces one of the bottoms does the sum (TrainNet's fusion pass)
  protected:
   bool fuse_relu_ = false;
+  bool fused_away_ = false;
  public:
   const char* type() const override { return "Eltwise"; }
   void Reshape(const vector<Blob*>& b, const vector<Blob*>& t) override { t[0]->ReshapeLike(*b[0]); }
@@ -207,6 +218,7 @@ class TrainNet {
   ~TrainNet();
   void AttachSync(P2PSync* sync);                  // weights broadcast from rank 0, gradients exchanged per bucket
   float ForwardBackward();                         // Net::ForwardBackward (net.cpp:711-716); returns the loss (host sync)
+  void ClearParamDiffs();                          // Net::ClearParamDiffs (net.cpp:1256-1270): zero every learnable blob's diff
   void Step(bool copy_input_from_host);            // one Solver::Step iteration, fully asynchronous on the thread stream
   // n Steps bracketed by CUDA events on the thread stream; returns milliseconds (end-of-iteration makes the compute
   // stream wait for the last update, so the closing event covers reduce + update too)

@@ -280,6 +280,7 @@ class Trainer:
         L.b2h_trainer_attach_sync.argtypes = [vp, i, i, C.c_char_p, i]
         L.b2h_trainer_step.argtypes = [vp, i, i]
         L.b2h_trainer_forward_backward.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b2h_trainer_clear_param_diffs.argtypes = [vp]
         L.b2h_trainer_sync.argtypes = [vp]
         L.b2h_trainer_loss.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2h_trainer_blob_count.argtypes = [vp, C.c_char_p]
@@ -322,6 +323,11 @@ class Trainer:
         v = C.c_float()
         _ck(lib().b2h_trainer_forward_backward(self._h, C.byref(v)))
         return v.value
+
+    def clear_param_diffs(self):
+        """Net::ClearParamDiffs: Step() expects zeroed diffs (the update clears them); call this after a forward_backward() made
+        for inspection."""
+        _ck(lib().b2h_trainer_clear_param_diffs(self._h))
 
     def sync(self):
         _ck(lib().b2h_trainer_sync(self._h))

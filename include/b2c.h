@@ -196,6 +196,16 @@ int b2c_bn_forward_train_fused(int N, int C, int S, const float* x, const float*
                                float* save_mean, float* save_invstd, float* y, int relu, void* stream);
 int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                           const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream);
+/* The residual tail of a ResNet block -- BatchNorm -> Eltwise(SUM, 2 bottoms) -> in-place ReLU (batch_norm_layer.cpp,
+ * eltwise_layer.cpp:47-60,100-140, relu_layer.cpp) -- as one launch each way.  Forward: y = [max(0, .)] (BatchNorm(x) + residual).
+ * Backward: d_sum / y_sum are the diff and the post-ReLU data of the sum's top; dx = BatchNorm::Backward of d_sum * (y_sum > 0), and
+ * that masked gradient is also written to d_residual (the sum's other bottom) unless it is null.  Same bits as the three layers. */
+int b2c_bn_forward_train_fused_res(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
+                                   float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
+                                   float* save_mean, float* save_invstd, const float* residual, float* y, int relu, void* stream);
+int b2c_bn_backward_fused_res(int N, int C, int S, const float* d_sum, const float* y_sum, const float* x, const float* save_mean,
+                              const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
+                              float* dx, float* d_residual, void* stream);
 /* AccuracyLayer::Forward (accuracy_layer.cpp:44-100), labels as float class ids, ties ranked like the reference's
  * std::greater<pair<score, index>>; `scratch`: 4 bytes of device memory. */
 int b2c_accuracy(int N, int C, int top_k, const float* scores, const float* labels, float* accuracy, void* scratch, void* stream);

@@ -110,7 +110,39 @@ def test_batchnorm_fused_is_bitwise_the_unfused_chain(rng, shape, relu):
         assert np.array_equal(a, b), name
 
 
-@pytest.mark.parametrize("H,k,s,pad,method", [(112, 3, 2, 0, 0), (7, 7, 1, 0, 1), (8, 3, 2, 1, 0), (9, 2, 2, 0, 1), (13, 3, 2, 0, 0), (14, 3, 1, 1, 0)])
+@pytest.mark.parametrize("shape", [(4, 3, 5, 5), (8, 64, 14, 14), (2, 256, 7, 7), (8, 16, 64, 64), (64, 256, 56, 56), (37, 40, 30, 30)])
+def test_batchnorm_residual_tail_is_bitwise_the_three_layers(rng, shape):
+    """b2c_bn_forward_train_fused_res / b2c_bn_backward_fused_res (BatchNorm -> Eltwise SUM -> in-place ReLU as one launch each way)
+    against the three layers run one after the other: same bits for the sum's top, the statistics, dgamma, dbeta, the BatchNorm
+    bottom diff and the diff handed to the sum's other bottom."""
+    N, Cc, H, W = shape
+    S = H * W
+    L = m.lib()
+    X = dev((rng.standard_normal(shape) * 1.5 + 0.3).astype(np.float32))
+    R = dev(rng.standard_normal(shape).astype(np.float32))
+    G, B = dev(rng.standard_normal(Cc).astype(np.float32)), dev(rng.standard_normal(Cc).astype(np.float32))
+    DS = dev(rng.standard_normal(shape).astype(np.float32))
+    out = []
+    for fused in (0, 1):
+        RM, RV = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+        SM, SI = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+        YS, DX, DR = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+        DG, DB = torch.full((Cc,), 9.0, device="cuda"), torch.full((Cc,), 9.0, device="cuda")
+        if fused:
+            capi.check(L.b2c_bn_forward_train_fused_res(N, Cc, S, p(X), p(G), p(B), 1e-4, 0.9, 1, p(RM), p(RV), p(SM), p(SI), p(R), p(YS), 1, st()))
+            capi.check(L.b2c_bn_backward_fused_res(N, Cc, S, p(DS), p(YS), p(X), p(SM), p(SI), p(G), p(B), p(DG), p(DB), p(DX), p(DR), st()))
+        else:
+            XN, YB, DA = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+            capi.check(L.b2c_bn_forward_train(N, Cc, S, p(X), p(G), p(B), 1e-4, 0.9, 1, p(RM), p(RV), p(SM), p(SI), p(XN), p(YB), st()))
+            capi.check(L.b2c_add_relu(X.numel(), p(YB), p(R), p(YS), st()))
+            capi.check(L.b2c_relu_backward2(X.numel(), p(DS), p(YS), p(DA), p(DR), st()))
+            capi.check(L.b2c_bn_backward(N, Cc, S, p(DA), p(XN), p(G), p(SI), p(DG), p(DB), p(DX), st()))
+        out.append([host(t) for t in (YS, SM, SI, RM, RV, DG, DB, DX, DR)])
+    for name, a, b in zip(("y_sum", "mean", "invstd", "run_mean", "run_var", "dgamma", "dbeta", "dx", "d_residual"), out[0], out[1]):
+        assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("H,k,s,pad,method", [(112, 3, 2, 0, 0), (7, 7, 1, 0, 1), (8, 3, 2, 1, 0), (9, 2, 2, 0, 1), (13, 3, 2, 0, 0), (14, 3, 1, 1, 0), (12, 3, 1, 1, 0), (16, 2, 2, 0, 0), (28, 3, 2, 0, 0), (20, 3, 2, 1, 0)])
 def test_pooling(rng, H, k, s, pad, method):
     x = rng.standard_normal((2, 5, H, H)).astype(np.float32)
     y, mask = lo.pool_forward(x, method, (k, k), (s, s), (pad, pad))

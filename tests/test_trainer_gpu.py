@@ -203,6 +203,7 @@ def test_inception_style_net_matches_oracle(rng):
     for i, g in enumerate(grads):
         assert rel(t.get_param(i, 1), g, floor) <= TOL, no.param_shapes(spec)[i]
     # two iterations of Solver::Step: the dropout streams advance by the blob size per iteration
+    t.clear_param_diffs()                       # Step() accumulates into the diffs and relies on the update clearing them (solver.cpp:237-239)
     p, h = [q.copy() for q in params], [np.zeros_like(q) for q in params]
     import oracle
     for it in range(2):
