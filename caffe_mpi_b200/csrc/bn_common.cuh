@@ -113,12 +113,14 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
   a += a2; b += b2;
 }
 
-// cluster size for the per-channel kernels: ~16K values per CTA, at least two CTAs per SM in flight, at most 8
+// cluster size for the per-channel kernels: ~16K values per CTA, at least one CTA per SM, at most 8.  (Two CTAs per SM as the
+// floor put the 14x14 layers of ResNet-50 -- 256 channels, 12.5K values each -- on 512 three-iteration CTAs in two waves:
+// ~20 us per launch whatever the tensor size, profiles/r02_c8_bn_sweep.log.)
 static inline unsigned bn_cluster_size(int N, int C, int S) {
   const size_t E = (size_t)N * S;
   unsigned cs = 1;
   while (cs < BN_CLUSTER && E / (cs * 2) >= 16384) cs *= 2;
-  while (cs < BN_CLUSTER && (size_t)C * cs < 2u * (unsigned)sm_count()) cs *= 2;
+  while (cs < BN_CLUSTER && (size_t)C * cs < (unsigned)sm_count()) cs *= 2;
   return cs;
 }
 // one cluster of `cs` CTAs per channel; `smem_pad` bytes of (unused) dynamic shared memory bound the CTAs per SM
