@@ -633,6 +633,10 @@ bool tc_wgrad_supported(const ConvShape& s) {
 }
 
 static WgradPlan wgrad_tma_plan(const ConvShape& s, int* cpi_out);
+// the TMA-staged bf16x3 kernel (conv_tc_wgrad_stg.cu): the dense 1x1 problem a compacted strided layer turns into goes there when it can
+bool tc_wgrad_stg_supported(const ConvShape&);
+size_t tc_wgrad_stg_workspace(const ConvShape&);
+int launch_conv_tc_wgrad_stg(const ConvShape&, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
 static bool wgrad_tma_shape_ok(const ConvShape& s);
 static bool wgrad_compact_shape_ok(const ConvShape& s);
 static ConvShape wgrad_compact_dense_shape(const ConvShape& s);
@@ -648,8 +652,9 @@ size_t tc_wgrad_workspace(const ConvShape& s) {
   if (wgrad_compact_shape_ok(s)) {                   // strided 1x1: compacted input + the TMA path's partials
     const ConvShape d = wgrad_compact_dense_shape(s);
     const WgradPlan pt = wgrad_tma_plan(d, nullptr);
-    const size_t nt = (pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0) + 256 +
-                      sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
+    size_t part = pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    if (tc_wgrad_stg_supported(d)) part = tc_wgrad_stg_workspace(d);
+    const size_t nt = part + 256 + sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
     if (nt > need) need = nt;
   }
   return need;
@@ -763,8 +768,13 @@ static int wgrad_compact_mode() {
 static bool wgrad_compact_shape_ok(const ConvShape& s) {
   const long long P = (long long)s.Ho * s.Wo;
   const int mode = wgrad_compact_mode();
-  return mode != 0 && (mode == 2 || s.O > 128) && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) &&
-         s.G == 1 && P % 4 == 0 && P >= 32;
+  if (!(mode != 0 && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) && s.G == 1 && P % 4 == 0 && P >= 32))
+    return false;
+  // with the staged kernel behind it the extra pass over X pays for every layer it takes; with the 3xTF32 TMA kernel only for
+  // the wide ones (measurements above)
+  ConvShape d = s;
+  d.H = s.Ho; d.W = s.Wo; d.sh = d.sw = 1; d.is_1x1 = true;
+  return mode == 2 || s.O > 128 || tc_wgrad_stg_supported(d);
 }
 static ConvShape wgrad_compact_dense_shape(const ConvShape& s) {
   ConvShape d = s;
@@ -809,7 +819,8 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
   if (math == B2C_MATH_FP32 && wgrad_compact_shape_ok(s) && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0 && ws) {
     const ConvShape d = wgrad_compact_dense_shape(s);
     const WgradPlan pt = wgrad_tma_plan(d, nullptr);
-    const size_t part = pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
+    const bool staged = tc_wgrad_stg_supported(d);
+    const size_t part = staged ? tc_wgrad_stg_workspace(d) : pt.splits > 1 ? WG_COUNTER_BYTES + sizeof(float) * (size_t)pt.splits * s.O * s.C : 0;
     const size_t xoff = (part + 255) & ~(size_t)255;
     const size_t xbytes = sizeof(float) * (size_t)s.N * s.C * s.Ho * s.Wo;
     if (ws_bytes < xoff + xbytes) return fail(B2C_ERR_WORKSPACE, "wgrad (compact): workspace too small");
@@ -818,6 +829,7 @@ int launch_conv_tc_wgrad(const ConvShape& s, int math, const float* x, const flo
       const long long planes = (long long)s.N * s.C;
       subsample_kernel<<<grid_for((size_t)(planes * s.Ho * s.Wo), 256), 256, 0, st>>>(x, xc, planes, s.H, s.W, s.Ho, s.Wo, s.sh, s.sw);
       B2C_POST_LAUNCH();
+      if (staged) return launch_conv_tc_wgrad_stg(d, xc, dy, dw, ws, part, st);
       return launch_conv_tc_wgrad_tma(d, xc, dy, dw, ws, part, st);
     }
   }

@@ -187,7 +187,10 @@ __device__ __forceinline__ void splitk_fused_reduce(const float* __restrict__ pa
   }
 }
 
-template <int T, int CN>
+// PLANE (7x7 maps: a 196-byte channel pitch is not a TMA stride): one K block = one whole image.  The blobs are viewed as
+// {4*H*W, channels/4, N} (four channels per tensor row), so a box of 32 rows is 128 channels x H*W pixels, contiguous; dY is read
+// with 4-byte loads (odd word pitch: conflict-free), pixels H*W..63 of the 64-wide K block are written as zeros on both operands.
+template <int T, int CN, bool PLANE>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x) {
   using S = Cfg<T, CN>;
@@ -212,7 +215,8 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
   long long kb_end = kb_begin + p.kb_per_split;
   if (kb_end > p.nkb_total) kb_end = p.nkb_total;
   const int nkb = (int)(kb_end - kb_begin);                // >= 1 by construction
-  const uint32_t x_bytes = (uint32_t)CN * (uint32_t)p.bwx * 4u;
+  const uint32_t x_bytes = (uint32_t)CN * (uint32_t)p.bwx * 4u;      // plane mode: bwx = H*W (the channel pitch of the box)
+  const uint32_t dy_bytes = PLANE ? 128u * (uint32_t)p.HW * 4u : DY_BYTES;
   const int nx = 2u * x_bytes <= S::XPOOL ? 2 : 1;         // X stages
 
   if (tid == 0) {
@@ -250,7 +254,17 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
       mbar_wait(bar_dy_full + 8 * rd, (i / NDY) & 1);
       // ---- (a) dY -> bf16 hi / lo -> tensor memory: this thread's row (output channel), pixels [cg*16, cg*16 + 16)
       uint32_t hi[8], lo[8];
-      {
+      if constexpr (PLANE) {
+        const uint32_t rowb = raw_dy(rd) + (uint32_t)row * (uint32_t)(p.HW * 4) + (uint32_t)(cg * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = cg * 16 + q * 4 + e < p.HW ? lds32(rowb + (uint32_t)((q * 4 + e) * 4)) : 0.f;
+          split_pack_bf16(v[0], v[1], hi[2 * q], lo[2 * q]);
+          split_pack_bf16(v[2], v[3], hi[2 * q + 1], lo[2 * q + 1]);
+        }
+      } else {
         const uint32_t box = raw_dy(rd) + (uint32_t)(cg >> 1) * (128u * 128u) + (uint32_t)row * 128u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -324,7 +338,15 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
         const uint32_t srcw = raw_x(rx) + (uint32_t)((warp * RPW * KPX + 2 * lane) * 4);
 #pragma unroll
         for (int k = 0; k < RPW; ++k) {
-          const float2 v = lds64(srcw + (uint32_t)(k * KPX * 4));
+          float2 v;
+          if constexpr (PLANE) {
+            // channel pitch H*W*4 bytes (4-byte aligned only); pixels past the image are the next channel's: zeros instead
+            const uint32_t a = raw_x(rx) + (uint32_t)(((warp * RPW + k) * p.HW + 2 * lane) * 4);
+            v.x = 2 * lane < p.HW ? lds32(a) : 0.f;
+            v.y = 2 * lane + 1 < p.HW ? lds32(a + 4u) : 0.f;
+          } else {
+            v = lds64(srcw + (uint32_t)(k * KPX * 4));
+          }
           uint32_t hw, lw;
           split_pack_bf16(v.x, v.y, hw, lw);
           const uint32_t n = (uint32_t)(warp * RPW + k);
@@ -381,14 +403,19 @@ wgrad_stg_kernel(const __grid_constant__ Params p, const __grid_constant__ CUten
       mbar_wait_backoff(bar_x_empty + 8 * rx, ((i / nx) & 1) ^ 1, 32);
       if (elect_one()) {
         arrive_expect_tx(bar_x_full + 8 * rx, x_bytes);
-        tma_load_3d(raw_x(rx), &map_x, bar_x_full + 8 * rx, x_start(j), c0, n_img);
+        if constexpr (PLANE) tma_load_3d(raw_x(rx), &map_x, bar_x_full + 8 * rx, 0, c0 / 4, n_img);
+        else tma_load_3d(raw_x(rx), &map_x, bar_x_full + 8 * rx, x_start(j), c0, n_img);
       }
       __syncwarp();
       mbar_wait_backoff(bar_dy_empty + 8 * rd, ((i / NDY) & 1) ^ 1, 32);
       if (elect_one()) {
-        arrive_expect_tx(bar_dy_full + 8 * rd, DY_BYTES);
-        tma_load_3d(raw_dy(rd), &map_dy, bar_dy_full + 8 * rd, j * KPX, m0, n_img);
-        tma_load_3d(raw_dy(rd) + 128u * 128u, &map_dy, bar_dy_full + 8 * rd, j * KPX + 32, m0, n_img);
+        arrive_expect_tx(bar_dy_full + 8 * rd, dy_bytes);
+        if constexpr (PLANE) {
+          tma_load_3d(raw_dy(rd), &map_dy, bar_dy_full + 8 * rd, 0, m0 / 4, n_img);
+        } else {
+          tma_load_3d(raw_dy(rd), &map_dy, bar_dy_full + 8 * rd, j * KPX, m0, n_img);
+          tma_load_3d(raw_dy(rd) + 128u * 128u, &map_dy, bar_dy_full + 8 * rd, j * KPX + 32, m0, n_img);
+        }
       }
       __syncwarp();
       if (++j == p.bpi) { j = 0; ++n_img; }
@@ -474,7 +501,12 @@ static bool wstg_enabled() {
   if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED"); on = e ? atoi(e) : 1; }
   return on != 0;
 }
-struct WstgPlan { int T, cn, bwx, bpi, splits, kb_per_split; long long nkb; };
+struct WstgPlan { int T, cn, bwx, bpi, splits, kb_per_split; long long nkb; bool plane; };
+static bool wstg_plane_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED_PLANE"); on = e ? atoi(e) : 0; }   // off until validated on a B200
+  return on != 0;
+}
 static bool wstg_plan(const ConvShape& s, WstgPlan* pl) {
   if (!wstg_enabled()) return false;
   if (s.G != 1 || s.sh != 1 || s.sw != 1 || s.dh != 1 || s.dw != 1 || s.Ho != s.H || s.Wo != s.W) return false;
@@ -482,15 +514,19 @@ static bool wstg_plan(const ConvShape& s, WstgPlan* pl) {
   const bool k3 = s.kh == 3 && s.kw == 3 && s.ph == 1 && s.pw == 1;
   if (!k1 && !k3) return false;
   const long long HW = (long long)s.H * s.W;
-  if (HW % 4 != 0 || HW < 64 || (long long)s.N * HW > 0x7fffffffLL - 256) return false;
+  if ((long long)s.N * HW > 0x7fffffffLL - 256) return false;
+  // 7x7 maps: plane mode (one image per K block, blobs viewed four channels per tensor row)
+  const bool plane = HW == 49 && s.C % 4 == 0 && s.O % 4 == 0 && wstg_plane_enabled();
+  if (!plane && (HW % 4 != 0 || HW < 64)) return false;
   const int T = k1 ? 1 : 9;
   const int halo = s.ph * s.W + s.pw;
   const int need = wstg::KPX + 2 * halo + ((4 - halo % 4) % 4);
-  if (need > 256) return false;
+  if (!plane && need > 256) return false;
   if (!pl) return true;
   pl->T = T;
+  pl->plane = plane;
   pl->cn = k1 ? (s.C > 64 ? 128 : 64) : 32;
-  pl->bwx = (need + 3) & ~3;
+  pl->bwx = plane ? (int)HW : (need + 3) & ~3;
   pl->bpi = (int)((HW + wstg::KPX - 1) / wstg::KPX);
   pl->nkb = (long long)s.N * pl->bpi;
   const long long mn = (long long)((s.O + 127) / 128) * ((s.C + pl->cn - 1) / pl->cn);
@@ -511,12 +547,12 @@ size_t tc_wgrad_stg_workspace(const ConvShape& s) {
   return pl.splits > 1 ? WSTG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * s.O * s.Kd : 0;
 }
 
-template <int T, int CN>
+template <int T, int CN, bool PLANE>
 static int wstg_launch(const wstg::Params& p, const CUtensorMap& mdy, const CUtensorMap& mx, int c_tiles, int o_tiles, cudaStream_t st) {
   using S = wstg::Cfg<T, CN>;
-  B2C_CUDA_OK(cudaFuncSetAttribute(wstg::wgrad_stg_kernel<T, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
+  B2C_CUDA_OK(cudaFuncSetAttribute(wstg::wgrad_stg_kernel<T, CN, PLANE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL));
   dim3 grid(p.splits, c_tiles, o_tiles);
-  wstg::wgrad_stg_kernel<T, CN><<<grid, wstg::THREADS, S::TOTAL, st>>>(p, mdy, mx);
+  wstg::wgrad_stg_kernel<T, CN, PLANE><<<grid, wstg::THREADS, S::TOTAL, st>>>(p, mdy, mx);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
@@ -547,7 +583,7 @@ int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const fl
   s.N = 1; s.C = N; s.H = 1; s.W = K; s.O = M; s.G = 1; s.kh = s.kw = 1; s.sh = s.sw = 1; s.ph = s.pw = 0; s.dh = s.dw = 1; s.has_bias = 0;
   s.Ho = 1; s.Wo = K; s.Cg = N; s.Og = M; s.Kd = N; s.is_1x1 = true;
   WstgPlan pl;
-  pl.T = 1; pl.cn = N > 64 ? 128 : 64; pl.bwx = wstg::KPX; pl.bpi = (K + wstg::KPX - 1) / wstg::KPX; pl.nkb = pl.bpi;
+  pl.T = 1; pl.plane = false; pl.cn = N > 64 ? 128 : 64; pl.bwx = wstg::KPX; pl.bpi = (K + wstg::KPX - 1) / wstg::KPX; pl.nkb = pl.bpi;
   pl.splits = 1; pl.kb_per_split = pl.bpi;
   return launch_wstg_planned(s, pl, B, A, Cm, nullptr, 0, st);
 }
@@ -565,12 +601,20 @@ static int launch_wstg_planned(const ConvShape& s, const WstgPlan& pl, const flo
   p.counters = static_cast<unsigned int*>(ws);
   if (pl.splits > 1) B2C_CUDA_OK(cudaMemsetAsync(ws, 0, WSTG_COUNTER_BYTES, st));
   alignas(64) CUtensorMap mdy, mx;
+  const int c_tiles = (s.C + pl.cn - 1) / pl.cn, o_tiles = (s.O + 127) / 128;
+  if (pl.plane) {
+    // {4*HW, channels/4, N}: four channels per tensor row (a 16-byte-multiple pitch); box rows = tile channels / 4
+    if (int rc = ws_make_map(&mdy, dy, p.HW * 4, s.O / 4, s.N, p.HW * 4, 32, false)) return rc;
+    if (int rc = ws_make_map(&mx, x, p.HW * 4, s.C / 4, s.N, p.HW * 4, pl.cn / 4, false)) return rc;
+    if (pl.T == 9) return wstg_launch<9, 32, true>(p, mdy, mx, c_tiles, o_tiles, st);
+    if (pl.cn == 128) return wstg_launch<1, 128, true>(p, mdy, mx, c_tiles, o_tiles, st);
+    return wstg_launch<1, 64, true>(p, mdy, mx, c_tiles, o_tiles, st);
+  }
   if (int rc = ws_make_map(&mdy, dy, p.HW, s.O, s.N, 32, 128, true)) return rc;
   if (int rc = ws_make_map(&mx, x, p.HW, s.C, s.N, pl.bwx, pl.cn, false)) return rc;
-  const int c_tiles = (s.C + pl.cn - 1) / pl.cn, o_tiles = (s.O + 127) / 128;
-  if (pl.T == 9) return wstg_launch<9, 32>(p, mdy, mx, c_tiles, o_tiles, st);
-  if (pl.cn == 128) return wstg_launch<1, 128>(p, mdy, mx, c_tiles, o_tiles, st);
-  return wstg_launch<1, 64>(p, mdy, mx, c_tiles, o_tiles, st);
+  if (pl.T == 9) return wstg_launch<9, 32, false>(p, mdy, mx, c_tiles, o_tiles, st);
+  if (pl.cn == 128) return wstg_launch<1, 128, false>(p, mdy, mx, c_tiles, o_tiles, st);
+  return wstg_launch<1, 64, false>(p, mdy, mx, c_tiles, o_tiles, st);
 }
 
 TC_DEBUG_EXPORT(debug_mbar_wstg)

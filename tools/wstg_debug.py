@@ -11,6 +11,8 @@ L = m.lib()
 L.b2c_debug_mbar_set_trap(0)
 shapes = [(2, 64, 8, 8, 64, 1, 0), (2, 32, 12, 12, 40, 3, 1), (3, 96, 14, 14, 72, 1, 0), (4, 64, 28, 28, 64, 3, 1), (2, 64, 56, 56, 256, 1, 0),
           (64, 256, 14, 14, 256, 3, 1), (64, 64, 56, 56, 64, 3, 1), (64, 256, 56, 56, 64, 1, 0), (2, 32, 8, 80, 32, 3, 1), (5, 32, 8, 13, 40, 3, 1)]
+if os.environ.get("B2C_WGRAD_STAGED_PLANE") == "1":      # 7x7 maps: plane mode
+    shapes = [(9, 64, 7, 7, 72, 3, 1), (11, 96, 7, 7, 160, 1, 0), (3, 512, 7, 7, 512, 3, 1), (64, 2048, 7, 7, 512, 1, 0), (64, 512, 7, 7, 2048, 1, 0)]
 if len(sys.argv) >= 8:
     shapes = [tuple(int(a) for a in sys.argv[1:8])]
 torch.manual_seed(0)
