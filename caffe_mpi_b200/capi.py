@@ -114,7 +114,7 @@ def lib():
         "b2c_bn_forward_train_fused": (i, [i, i, i, vp, vp, vp, f, f, i, vp, vp, vp, vp, vp, i, vp]),
         "b2c_bn_backward_fused": (i, [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, vp]),
         "b2c_bn_forward_train_fused_res": (i, [i, i, i, vp, vp, vp, f, f, i, vp, vp, vp, vp, vp, vp, i, vp]),
-        "b2c_bn_backward_fused_res": (i, [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "b2c_bn_backward_fused_res": (i, [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "b2c_add_relu": (i, [sz, vp, vp, vp, vp]),
         "b2c_relu_backward2": (i, [sz, vp, vp, vp, vp, vp]),
         "b2c_pool_forward": (i, [i] * 10 + [vp, vp, vp, vp]),

@@ -72,8 +72,9 @@ bool tc_wgrad_stg_supported(const ConvShape&);
 size_t tc_wgrad_stg_workspace(const ConvShape&);
 int launch_conv_tc_wgrad_stg(const ConvShape&, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
 bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K);
+size_t tc_gemm_workspace(bool tA, bool tB, int M, int N, int K);
 int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta,
-                    float* C, int math, cudaStream_t);
+                    float* C, int math, void* ws, size_t ws_bytes, cudaStream_t);
 
 static bool have_device() {
   static int ok = -1;
@@ -384,8 +385,16 @@ extern "C" int b2c_conv_backward_bias(const b2c_conv_desc* d, const float* dy, f
   return launch_bias_grad(d->s.N, d->s.O, d->s.Ho * d->s.Wo, dy, db, as_stream(stream));
 }
 
+extern "C" size_t b2c_sgemm_workspace_bytes(int transA, int transB, int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0 || !have_device()) return 0;
+  return tc_gemm_workspace(transA != 0, transB != 0, M, N, K);
+}
 extern "C" int b2c_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* B,
                          float beta, float* C, void* stream) {
+  return b2c_sgemm_ex(transA, transB, M, N, K, alpha, A, B, beta, C, nullptr, 0, stream);
+}
+extern "C" int b2c_sgemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* B,
+                            float beta, float* C, void* workspace, size_t workspace_bytes, void* stream) {
   if (!A || !B || !C || M < 0 || N < 0 || K < 0) return fail(B2C_ERR_INVALID, "b2c_sgemm: bad argument");
   REQUIRE_DEVICE();
   if (M == 0 || N == 0) return B2C_OK;
@@ -394,6 +403,6 @@ extern "C" int b2c_sgemm(int transA, int transB, int M, int N, int K, float alph
   // alpha / beta / alignment the staged kernel does not take -- on the exact-fp32 FFMA kernel
   if (g_default_algo != B2C_ALGO_SIMT && g_default_math == B2C_MATH_FP32 && alpha == 1.0f && (beta == 0.0f || beta == 1.0f) &&
       ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0 && tc_gemm_supported(tA, tB, M, N, K))
-    return launch_sgemm_tc(tA, tB, M, N, K, alpha, A, B, beta, C, g_default_math, as_stream(stream));
+    return launch_sgemm_tc(tA, tB, M, N, K, alpha, A, B, beta, C, g_default_math, workspace, workspace_bytes, as_stream(stream));
   return launch_sgemm_simt(tA, tB, M, N, K, alpha, A, tA ? M : K, B, tB ? K : N, beta, C, N, as_stream(stream));
 }

@@ -572,8 +572,26 @@ int launch_conv_tc_wgrad_stg(const ConvShape& s, const float* x, const float* dy
 bool tc_gemm_supported(bool tA, bool tB, int M, int N, int K) {
   return wstg_enabled() && !tA && tB && M > 0 && N > 0 && K >= 64 && K % 4 == 0 && (long long)M * N * 4 < (1ll << 40);
 }
+// split count of the K loop when the caller brings a workspace (b2c_sgemm_ex): one wave of CTAs, >= 4 K blocks per split
+static void gemm_tc_plan(int M, int N, int K, WstgPlan* pl) {
+  pl->T = 1; pl->plane = false; pl->cn = N > 64 ? 128 : 64; pl->bwx = wstg::KPX; pl->bpi = (K + wstg::KPX - 1) / wstg::KPX; pl->nkb = pl->bpi;
+  const long long mn = (long long)((M + 127) / 128) * ((N + pl->cn - 1) / pl->cn);
+  long long splits = sm_count() / mn;
+  const long long max_splits = pl->nkb / 4 > 0 ? pl->nkb / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const long long per = (pl->nkb + splits - 1) / splits;
+  pl->splits = (int)((pl->nkb + per - 1) / per);
+  pl->kb_per_split = (int)per;
+}
+size_t tc_gemm_workspace(bool tA, bool tB, int M, int N, int K) {
+  if (!tc_gemm_supported(tA, tB, M, N, K)) return 0;
+  WstgPlan pl;
+  gemm_tc_plan(M, N, K, &pl);
+  return pl.splits > 1 ? WSTG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * M * N : 0;
+}
 int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const float* A, const float* B, float beta, float* Cm, int math,
-                    cudaStream_t st) {
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
   (void)math;
   if (!tc_gemm_supported(tA, tB, M, N, K) || alpha != 1.0f || (beta != 0.0f && beta != 1.0f) ||
       ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u))
@@ -583,9 +601,10 @@ int launch_sgemm_tc(bool tA, bool tB, int M, int N, int K, float alpha, const fl
   s.N = 1; s.C = N; s.H = 1; s.W = K; s.O = M; s.G = 1; s.kh = s.kw = 1; s.sh = s.sw = 1; s.ph = s.pw = 0; s.dh = s.dw = 1; s.has_bias = 0;
   s.Ho = 1; s.Wo = K; s.Cg = N; s.Og = M; s.Kd = N; s.is_1x1 = true;
   WstgPlan pl;
-  pl.T = 1; pl.plane = false; pl.cn = N > 64 ? 128 : 64; pl.bwx = wstg::KPX; pl.bpi = (K + wstg::KPX - 1) / wstg::KPX; pl.nkb = pl.bpi;
-  pl.splits = 1; pl.kb_per_split = pl.bpi;
-  return launch_wstg_planned(s, pl, B, A, Cm, nullptr, 0, st);
+  gemm_tc_plan(M, N, K, &pl);
+  const size_t need = pl.splits > 1 ? WSTG_COUNTER_BYTES + sizeof(float) * (size_t)pl.splits * M * N : 0;
+  if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15u)) { pl.splits = 1; pl.kb_per_split = pl.bpi; ws = nullptr; ws_bytes = 0; }   // no workspace: one CTA per tile walks all of K
+  return launch_wstg_planned(s, pl, B, A, Cm, ws, ws_bytes, st);
 }
 
 static int launch_wstg_planned(const ConvShape& s, const WstgPlan& pl, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,

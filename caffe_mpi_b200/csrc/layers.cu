@@ -284,14 +284,17 @@ pool_max_bwd_kernel(int rows, int H, int W, int Ho, int Wo, int kh, int kw, int 
   }
 }
 // The common window shapes (3x3 / stride 2, 2x2 / stride 2, 3x3 / stride 1) with W % 4 == 0: one thread per FOUR consecutive input
-// columns, every candidate window's (mask, dy) pair loaded unconditionally -- 8..72 independent loads in flight per thread and
-// one 16-byte store, where the row kernel above has one element and two dependent round trips per thread (it ran at 0.35 TB/s:
-// 0.6 ms per ResNet-50 step, 5.9 ms per GoogLeNet step).  Same ascending (a, b) summation order: same bits.
+// columns.  The windows those four columns can sit in are MA rows x NB columns of the pooled map; their (mask, dy) pairs are loaded
+// ONCE, unconditionally (12 loads for 3x3 / 2), and each of the four elements picks its own from registers -- the row kernel
+// above has one element and two dependent round trips per thread (0.35 TB/s: 0.6 ms per ResNet-50 step, 5.9 ms per GoogLeNet
+// step); loading per element instead of per window ran into the load/store unit (32 loads per 16-byte store, 0.94 TB/s).
+// Same ascending (a, b) summation order: same bits.
 template <int KH, int KW, int SH, int SW>
 __global__ void __launch_bounds__(256)
 pool_max_bwd_q4_kernel(long long quads, int H, int W, int Ho, int Wo, int ph, int pw, const float* __restrict__ dy,
                        const int* __restrict__ mask, float* __restrict__ dx) {
-  constexpr int MA = (KH + SH - 1) / SH, MB = (KW + SW - 1) / SW;      // windows an input element can sit in, per axis
+  constexpr int MA = (KH + SH - 1) / SH;                        // pooled rows an input row can sit in
+  constexpr int NB = (3 + KW - 1) / SW + 1;                    // pooled columns four consecutive input columns can sit in
   const int Wq = W / 4;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
     const long long row = q / Wq;
@@ -299,8 +302,20 @@ pool_max_bwd_q4_kernel(long long quads, int H, int W, int Ho, int Wo, int ph, in
     const long long nc = row / H;
     const int h = (int)(row - nc * H);
     const int phs = (h + ph < KH) ? 0 : (h + ph - KH) / SH + 1, phe = min((h + ph) / SH + 1, Ho);
+    const int b0 = (w0 + pw < KW) ? 0 : (w0 + pw - KW) / SW + 1;                    // first pooled column of input column w0
     const float* d = dy + nc * Ho * Wo;
     const int* m = mask + nc * Ho * Wo;
+    int mm[MA][NB];
+    float dd[MA][NB];
+#pragma unroll
+    for (int a = 0; a < MA; ++a)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const bool ok = phs + a < phe && b0 + b < Wo;
+        const int idx = ok ? (phs + a) * Wo + b0 + b : 0;
+        mm[a][b] = ok ? __ldg(m + idx) : -1;                    // -1 never equals an element index
+        dd[a][b] = __ldg(d + idx);
+      }
     float g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -311,12 +326,9 @@ pool_max_bwd_q4_kernel(long long quads, int H, int W, int Ho, int Wo, int ph, in
 #pragma unroll
       for (int a = 0; a < MA; ++a)
 #pragma unroll
-        for (int b = 0; b < MB; ++b) {
-          const bool ok = phs + a < phe && pws + b < pwe;
-          const int idx = ok ? (phs + a) * Wo + pws + b : 0;
-          const int mm = __ldg(m + idx);
-          const float dd = __ldg(d + idx);
-          acc += (ok && mm == me) ? dd : 0.f;
+        for (int b = 0; b < NB; ++b) {
+          const int bb = b0 + b;
+          acc += (bb >= pws && bb < pwe && mm[a][b] == me) ? dd[a][b] : 0.f;
         }
       g[e] = acc;
     }

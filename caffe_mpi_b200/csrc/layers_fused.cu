@@ -67,10 +67,13 @@ bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__
 // post-activation output of the Eltwise sum this BatchNorm feeds: ym > 0)
 // CACHE: 1 = park every loaded unit of x in shared memory (cx[unit index - slice start]), 2 = x and the MASKED gradient (cd)
 // U: loads in flight per thread and stream; a thread visits its units in the same order whatever U is, so U does not change the sums
+// dy2 (may be null): a second part of the upstream gradient, added to dy element by element (the shadow diff of a blob that fans
+// out: SplitLayer::Backward's accumulation, b2c_add's a + b, folded into this read)
 template <bool VEC, int MASK, int CACHE = 0, int U = BN_U>
 __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c, const float* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ ym, float m, float is, float g, float bt, bool affine,
-                                                     unsigned rank, unsigned nranks, float& a, float& b, void* cx = nullptr, void* cd = nullptr) {
+                                                     unsigned rank, unsigned nranks, float& a, float& b, void* cx = nullptr, void* cd = nullptr,
+                                                     const float* __restrict__ dy2 = nullptr) {
   constexpr int FB_THREADS = BN_THREADS;
   const unsigned units = VEC ? S / 4 : S;
   unsigned lo, hi;
@@ -101,6 +104,10 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         d[u] = ok[u] ? reinterpret_cast<const float4*>(dy)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MASK == 2 && dy2 && ok[u]) {
+          const float4 e = reinterpret_cast<const float4*>(dy2)[off[u]];
+          d[u] = make_float4(__fadd_rn(d[u].x, e.x), __fadd_rn(d[u].y, e.y), __fadd_rn(d[u].z, e.z), __fadd_rn(d[u].w, e.w));
+        }
         v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(m, m, m, m);
         t[u] = (MASK == 2 && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -116,7 +123,11 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
     } else {
       float d[U], v[U], t[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) { d[u] = ok[u] ? dy[off[u]] : 0.f; v[u] = ok[u] ? x[off[u]] : m; t[u] = (MASK == 2 && ok[u]) ? ym[off[u]] : 0.f; }
+      for (int u = 0; u < U; ++u) {
+        d[u] = ok[u] ? dy[off[u]] : 0.f;
+        if (MASK == 2 && dy2 && ok[u]) d[u] = __fadd_rn(d[u], dy2[off[u]]);
+        v[u] = ok[u] ? x[off[u]] : m; t[u] = (MASK == 2 && ok[u]) ? ym[off[u]] : 0.f;
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float xn = prep(d[u], v[u], t[u]); a = fmaf(d[u], xn, a); b += d[u];
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2)
 bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, const float* __restrict__ dy, const float* __restrict__ x,
                       const float* __restrict__ ym, const float* __restrict__ mean, const float* __restrict__ invstd,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sum_dy_xn,
-                      float* __restrict__ sum_dy, float* __restrict__ dx, float* __restrict__ d_res) {
+                      float* __restrict__ sum_dy, float* __restrict__ dx, float* __restrict__ d_res, const float* __restrict__ dy2) {
   constexpr int U = MASK == 2 ? 2 : BN_U;           // three input streams in the residual form: fewer units in flight per stream (64 registers)
   extern __shared__ float4 bn_cache[];
   __shared__ float2 part;
@@ -275,7 +286,7 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
   void* cx = bn_cache;
   void* cd = VEC ? static_cast<void*>(bn_cache + slice_units) : static_cast<void*>(reinterpret_cast<float*>(bn_cache) + slice_units);
   float a, b;
-  bn_bwd_partial_fused<VEC, MASK, CACHE, U>(N, C, S, c, dy, x, ym, m, is, g, bt, affine, rank, nranks, a, b, cx, cd);
+  bn_bwd_partial_fused<VEC, MASK, CACHE, U>(N, C, S, c, dy, x, ym, m, is, g, bt, affine, rank, nranks, a, b, cx, cd, dy2);
   block_sum2(a, b);
   if (threadIdx.x == 0) part = make_float2(a, b);
   cluster.sync();
@@ -300,6 +311,10 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
       for (int u = 0; u < U; ++u) {
         if (ok[u]) {
           d[u] = CACHE == 2 ? static_cast<const float4*>(cd)[idx[u]] : reinterpret_cast<const float4*>(dy)[off[u]];
+          if (MASK == 2 && CACHE != 2 && dy2) {
+            const float4 e = reinterpret_cast<const float4*>(dy2)[off[u]];
+            d[u] = make_float4(__fadd_rn(d[u].x, e.x), __fadd_rn(d[u].y, e.y), __fadd_rn(d[u].z, e.z), __fadd_rn(d[u].w, e.w));
+          }
           v[u] = CACHE >= 1 ? static_cast<const float4*>(cx)[idx[u]] : reinterpret_cast<const float4*>(x)[off[u]];
         }
         t[u] = (MASK == 2 && CACHE != 2 && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -318,6 +333,7 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
       for (int u = 0; u < U; ++u) {
         if (ok[u]) {
           d[u] = CACHE == 2 ? static_cast<const float*>(cd)[idx[u]] : dy[off[u]];
+          if (MASK == 2 && CACHE != 2 && dy2) d[u] = __fadd_rn(d[u], dy2[off[u]]);
           v[u] = CACHE >= 1 ? static_cast<const float*>(cx)[idx[u]] : x[off[u]];
         }
         t[u] = (MASK == 2 && CACHE != 2 && ok[u]) ? ym[off[u]] : 0.f;
@@ -499,7 +515,7 @@ extern "C" int b2c_bn_forward_train_fused_res(int N, int C, int S, const float* 
                                save_invstd, residual, y, relu, stream);
 }
 
-static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const float* x, const float* y_mask, const float* save_mean,
+static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const float* dy2, const float* x, const float* y_mask, const float* save_mean,
                                   const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx,
                                   float* d_residual, int relu, void* stream) {
   FNEED(dy && x && save_mean && save_invstd && dgamma && dbeta && dx, "b2c_bn_backward_fused: null (dgamma/dbeta double as the reduction scratch)");
@@ -507,7 +523,7 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
   FNEED(N > 0 && C > 0 && S > 0 && (size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_backward_fused: channel extent out of range");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) return fail(B2C_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
-  const bool vec = fb_vec_ok(S, {dy, x, dx, y_mask, d_residual});
+  const bool vec = fb_vec_ok(S, {dy, dy2, x, dx, y_mask, d_residual});
   const unsigned cs = bn_cluster_size(N, C, S);
   if (bn_onepass() || y_mask) {
     unsigned slice_units = 0;
@@ -517,7 +533,7 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     const float inv_cnt1 = 1.0f / ((float)N * S);
 #define B2C_BWD0(V, M, P) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P>, smem)) return rc; \
     bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
-                        gamma, beta, dgamma, dbeta, dx, d_residual); } while (0)
+                        gamma, beta, dgamma, dbeta, dx, d_residual, dy2); } while (0)
 #define B2C_BWD1(V, M) do { if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
     if (vec) { if (y_mask) B2C_BWD1(true, 2); else if (relu) B2C_BWD1(true, 1); else B2C_BWD1(true, 0); }
     else { if (y_mask) B2C_BWD1(false, 2); else if (relu) B2C_BWD1(false, 1); else B2C_BWD1(false, 0); }
@@ -545,16 +561,17 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
 
 extern "C" int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, const float* save_mean, const float* save_invstd,
                                      const float* gamma, const float* beta, float* dgamma, float* dbeta, float* dx, int relu, void* stream) {
-  return bn_backward_fused_impl(N, C, S, dy, x, nullptr, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx, nullptr, relu, stream);
+  return bn_backward_fused_impl(N, C, S, dy, nullptr, x, nullptr, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx, nullptr, relu, stream);
 }
-// backward of BatchNorm -> Eltwise SUM -> ReLU run as one layer: d_sum / y_sum are the diff and the (post-ReLU) data of the sum's top;
+// backward of BatchNorm -> Eltwise SUM -> ReLU run as one layer: d_sum (+ d_sum2 when not null: the second part of a fanned-out
+// blob's gradient, added on the fly) / y_sum are the diff and the (post-ReLU) data of the sum's top;
 // dx = BatchNorm backward of d_sum * (y_sum > 0); that masked gradient is also written to d_residual (the sum's other bottom) when
 // d_residual is not null
-extern "C" int b2c_bn_backward_fused_res(int N, int C, int S, const float* d_sum, const float* y_sum, const float* x, const float* save_mean,
-                                         const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
-                                         float* dx, float* d_residual, void* stream) {
+extern "C" int b2c_bn_backward_fused_res(int N, int C, int S, const float* d_sum, const float* d_sum2, const float* y_sum, const float* x,
+                                         const float* save_mean, const float* save_invstd, const float* gamma, const float* beta,
+                                         float* dgamma, float* dbeta, float* dx, float* d_residual, void* stream) {
   FNEED(y_sum, "b2c_bn_backward_fused_res: null y_sum");
-  return bn_backward_fused_impl(N, C, S, d_sum, x, y_sum, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx, d_residual, 1, stream);
+  return bn_backward_fused_impl(N, C, S, d_sum, d_sum2, x, y_sum, save_mean, save_invstd, gamma, beta, dgamma, dbeta, dx, d_residual, 1, stream);
 }
 
 extern "C" int b2c_add_relu(size_t n, const float* a, const float* b, float* y, void* stream) {

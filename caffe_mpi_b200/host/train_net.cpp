@@ -75,7 +75,8 @@ void BatchNormLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>&, c
   float* dg = scale_bias_ ? blobs_[3]->mutable_gpu_diff() : scratch_.mutable_gpu_data();
   float* db = scale_bias_ ? blobs_[4]->mutable_gpu_diff() : scratch_.mutable_gpu_data() + C;
   if (res_sum_) {
-    B2C_CHECK(b2c_bn_backward_fused_res(N, C, Sp, res_sum_->gpu_diff(), res_sum_->gpu_data(), b[0]->gpu_data(), save_mean_.gpu_data(),
+    B2C_CHECK(b2c_bn_backward_fused_res(N, C, Sp, res_sum_->gpu_diff(), res_part2_ ? res_part2_->gpu_diff() : nullptr, res_sum_->gpu_data(),
+                                        b[0]->gpu_data(), save_mean_.gpu_data(),
                                         save_invstd_.gpu_data(), scale_bias_ ? blobs_[3]->gpu_data() : nullptr,
                                         scale_bias_ ? blobs_[4]->gpu_data() : nullptr, dg, db, b[0]->mutable_gpu_diff(),
                                         res_prop_ ? res_other_->mutable_gpu_diff() : nullptr, S()));
@@ -155,10 +156,19 @@ void InnerProductLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) 
   M_ = b[0]->shape(0);
   B2_CHECK((int)b[0]->count(1) == K_, "Input size incompatible with inner product parameters.");
   t[0]->Reshape({M_, num_output_});
+  const size_t wsb = b2c_sgemm_workspace_bytes(0, 1, M_, num_output_, K_);
+  if (wsb) gemm_ws_.Reshape({(int)((wsb + 3) / 4)});
 }
 void InnerProductLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   // y[M x N] = x[M x K] * W[N x K]^T (+ bias)   (inner_product_layer.cpp: caffe_gpu_gemm(NoTrans, Trans, M, N, K))
-  B2C_CHECK(b2c_sgemm(0, 1, M_, num_output_, K_, 1.f, b[0]->gpu_data(), blobs_[0]->gpu_data(), 0.f, t[0]->mutable_gpu_data(), S()));
+  const float* w = blobs_[0]->gpu_data();
+  if ((reinterpret_cast<uintptr_t>(w) & 15u) && K_ >= 64 && K_ % 4 == 0) {     // arena slot on an 8-byte boundary: aligned copy for the TMA-fed GEMM
+    if (w_aligned_.count() != blobs_[0]->count()) w_aligned_.Reshape(blobs_[0]->shape());
+    CUDA_CHECK(cudaMemcpyAsync(w_aligned_.mutable_gpu_data(), w, sizeof(float) * blobs_[0]->count(), cudaMemcpyDeviceToDevice, S()));
+    w = w_aligned_.gpu_data();
+  }
+  B2C_CHECK(b2c_sgemm_ex(0, 1, M_, num_output_, K_, 1.f, b[0]->gpu_data(), w, 0.f, t[0]->mutable_gpu_data(),
+                         gemm_ws_.count() ? gemm_ws_.mutable_gpu_data() : nullptr, sizeof(float) * gemm_ws_.count(), S()));
   if (bias_) B2C_CHECK(b2c_bias_forward(M_, num_output_, 1, blobs_[1]->gpu_data(), t[0]->mutable_gpu_data(), S()));
 }
 void InnerProductLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
@@ -501,6 +511,26 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       bn->set_residual(en.bottom[1 - k], en.top[0], en.propagate_down[1 - k]);
       el->set_fused_away(true);
     }
+    // a fused tail's sum blob with a second backward writer: hand the shadow diff to the tail instead of adding it in a pass of its own
+    const char* ed = getenv("B2C_FUSE_SPLIT");
+    const bool fuse_split = fuse_res && (!ed || atoi(ed) != 0);
+    std::map<Blob*, BatchNormLayer*> tails;
+    for (size_t j = 0; j < layers_.size(); ++j)
+      if (auto* bn = dynamic_cast<BatchNormLayer*>(layers_[j].get()))
+        if (bn->residual_sum()) tails[bn->residual_sum()] = bn;
+    std::map<Blob*, int> shadows;
+    for (Node& nd : nodes_)
+      for (size_t i = 0; i < nd.bottom.size(); ++i) if (nd.bottom_diff_tmp[i]) ++shadows[nd.bottom[i]];
+    for (Node& nd : nodes_) {
+      nd.deferred_add.assign(nd.bottom.size(), false);
+      for (size_t i = 0; fuse_split && i < nd.bottom.size(); ++i) {
+        if (!nd.bottom_diff_tmp[i] || shadows[nd.bottom[i]] != 1) continue;       // exactly one shadow per blob
+        auto it = tails.find(nd.bottom[i]);
+        if (it == tails.end()) continue;
+        it->second->set_sum_diff_part2(nd.bottom_diff_tmp[i]);
+        nd.deferred_add[i] = true;
+      }
+    }
   }
   solver_.reset(new SGDSolver(sp));
   solver_->SetParams(learnable_, specs);
@@ -564,7 +594,7 @@ void TrainNet::Backward(bool update) {
       if (!nd.accumulate_bottom.empty()) layers_[li]->set_accumulate_bottom_diff(nd.accumulate_bottom);
       layers_[li]->Backward(nd.top, nd.propagate_down, bvec);
       for (size_t i = 0; i < bvec.size(); ++i)
-        if (nd.bottom_diff_tmp[i])
+        if (nd.bottom_diff_tmp[i] && !(i < nd.deferred_add.size() && nd.deferred_add[i]))
           B2C_CHECK(b2c_add(nd.bottom[i]->count(), nd.bottom[i]->gpu_diff(), nd.bottom_diff_tmp[i]->gpu_diff(), nd.bottom[i]->mutable_gpu_diff(), S()));
       if (prof) prof->end(ph, S());
     }

@@ -52,9 +52,14 @@ class BatchNormLayer : public LayerBase {      // NVCaffe BatchNorm with scale_b
   // Residual tail: this layer also does the Eltwise SUM (+ in-place ReLU) that consumes its top.  Forward writes
   // max(0, BatchNorm(x) + other) into sum_top; backward takes sum_top's diff / data and also writes other's diff.
   void set_residual(Blob* other, Blob* sum_top, bool propagate_other) { res_other_ = other; res_sum_ = sum_top; res_prop_ = propagate_other; }
+  Blob* residual_sum() const { return res_sum_; }
+  // the sum's top has a second consumer whose bottom gradient lands in a shadow blob: this layer's backward reads both parts and
+  // adds them on the fly instead of TrainNet running b2c_add over them first
+  void set_sum_diff_part2(Blob* shadow) { res_part2_ = shadow; }
  protected:
   Blob* res_other_ = nullptr;
   Blob* res_sum_ = nullptr;
+  Blob* res_part2_ = nullptr;
   bool res_prop_ = false;
   Blob xnorm_, save_mean_, save_invstd_, scratch_;
 };
@@ -104,6 +109,10 @@ class InnerProductLayer : public LayerBase {
   int num_output_, K_ = 0, M_ = 0;
   bool bias_;
   FillerParameter wf_, bf_;
+  // forward runs on the tensor-core NoTrans x Trans GEMM (b2c_sgemm_ex): split-K scratch, and a 16-byte aligned copy of the
+  // weights when their slot in the parameter arena is only 8-byte aligned (slots are padded to even counts, net.cpp:1356-1371;
+  // TMA wants 16).  The copy is 4 bytes per weight once per forward -- against a 4x slower FFMA kernel.
+  Blob gemm_ws_, w_aligned_;
 };
 
 // ---- layers the AlexNet / GoogLeNet / VGG-16 nets add (not yet run on a GPU; see include/b2c.h) ---------------------
@@ -252,6 +261,7 @@ class TrainNet {
     vector<bool> propagate_down;
     vector<Blob*> bottom_diff_tmp;                 // per bottom: null = write the blob's own diff, else accumulate through this
     vector<bool> accumulate_bottom;                // per bottom: the layer itself adds into the blob's diff (no shadow blob)
+    vector<bool> deferred_add;                     // per bottom: the shadow diff is added by the blob's producer (fused BatchNorm residual tail)
     bool need_backward = false;
     int first_param = -1, num_params = 0;
   };

@@ -162,6 +162,12 @@ int b2c_col2im_nd(const float* col, int num_axes, const int* im_shape, const int
  * Replaces caffe_gpu_gemm<float> -> cublasSgemm (src/caffe/util/math_functions.cu:11-26). */
 int b2c_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A,
               const float* B, float beta, float* C, void* stream);
+/* The same product with caller-provided scratch (b2c_sgemm_workspace_bytes(...) bytes, 16-byte aligned; may be null / short: then
+ * as b2c_sgemm).  With it the NoTrans x Trans tensor-core path splits the K loop over one wave of CTAs and reduces the partial
+ * tiles in a fixed order (deterministic) -- InnerProduct forward at small batch is otherwise one CTA per 128 x 128 output tile. */
+size_t b2c_sgemm_workspace_bytes(int transA, int transB, int M, int N, int K);
+int b2c_sgemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* B, float beta, float* C,
+                 void* workspace, size_t workspace_bytes, void* stream);
 /* y = alpha*op(A)*x + beta*y, A row-major MxN.
  * Replaces caffe_gpu_gemv<float> -> cublasSgemv (math_functions.cu:73-82).               */
 int b2c_sgemv(int transA, int M, int N, float alpha, const float* A, const float* x,
@@ -199,13 +205,15 @@ int b2c_bn_backward_fused(int N, int C, int S, const float* dy, const float* x, 
 /* The residual tail of a ResNet block -- BatchNorm -> Eltwise(SUM, 2 bottoms) -> in-place ReLU (batch_norm_layer.cpp,
  * eltwise_layer.cpp:47-60,100-140, relu_layer.cpp) -- as one launch each way.  Forward: y = [max(0, .)] (BatchNorm(x) + residual).
  * Backward: d_sum / y_sum are the diff and the post-ReLU data of the sum's top; dx = BatchNorm::Backward of d_sum * (y_sum > 0), and
- * that masked gradient is also written to d_residual (the sum's other bottom) unless it is null.  Same bits as the three layers. */
+ * that masked gradient is also written to d_residual (the sum's other bottom) unless it is null.  d_sum2 (may be null) is a second
+ * part of the sum's top diff -- the shadow diff of a blob with two consumers -- added to d_sum on the fly (SplitLayer::Backward's
+ * accumulation without its pass over memory).  Same bits as the layers run one by one. */
 int b2c_bn_forward_train_fused_res(int N, int C, int S, const float* x, const float* gamma, const float* beta, float eps,
                                    float moving_average_fraction, int first_iteration, float* running_mean, float* running_var,
                                    float* save_mean, float* save_invstd, const float* residual, float* y, int relu, void* stream);
-int b2c_bn_backward_fused_res(int N, int C, int S, const float* d_sum, const float* y_sum, const float* x, const float* save_mean,
-                              const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
-                              float* dx, float* d_residual, void* stream);
+int b2c_bn_backward_fused_res(int N, int C, int S, const float* d_sum, const float* d_sum2, const float* y_sum, const float* x,
+                              const float* save_mean, const float* save_invstd, const float* gamma, const float* beta,
+                              float* dgamma, float* dbeta, float* dx, float* d_residual, void* stream);
 /* AccuracyLayer::Forward (accuracy_layer.cpp:44-100), labels as float class ids, ties ranked like the reference's
  * std::greater<pair<score, index>>; `scratch`: 4 bytes of device memory. */
 int b2c_accuracy(int N, int C, int top_k, const float* scores, const float* labels, float* accuracy, void* scratch, void* stream);

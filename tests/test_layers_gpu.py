@@ -110,11 +110,13 @@ def test_batchnorm_fused_is_bitwise_the_unfused_chain(rng, shape, relu):
         assert np.array_equal(a, b), name
 
 
+@pytest.mark.parametrize("two_parts", [False, True], ids=["one_diff", "split_diff"])
 @pytest.mark.parametrize("shape", [(4, 3, 5, 5), (8, 64, 14, 14), (2, 256, 7, 7), (8, 16, 64, 64), (64, 256, 56, 56), (37, 40, 30, 30)])
-def test_batchnorm_residual_tail_is_bitwise_the_three_layers(rng, shape):
+def test_batchnorm_residual_tail_is_bitwise_the_three_layers(rng, shape, two_parts):
     """b2c_bn_forward_train_fused_res / b2c_bn_backward_fused_res (BatchNorm -> Eltwise SUM -> in-place ReLU as one launch each way)
     against the three layers run one after the other: same bits for the sum's top, the statistics, dgamma, dbeta, the BatchNorm
-    bottom diff and the diff handed to the sum's other bottom."""
+    bottom diff and the diff handed to the sum's other bottom.  split_diff: the sum's top diff arrives in two parts (a blob with two
+    consumers) -- the fused backward adds them on the fly, the unfused chain with b2c_add first."""
     N, Cc, H, W = shape
     S = H * W
     L = m.lib()
@@ -122,6 +124,7 @@ def test_batchnorm_residual_tail_is_bitwise_the_three_layers(rng, shape):
     R = dev(rng.standard_normal(shape).astype(np.float32))
     G, B = dev(rng.standard_normal(Cc).astype(np.float32)), dev(rng.standard_normal(Cc).astype(np.float32))
     DS = dev(rng.standard_normal(shape).astype(np.float32))
+    DS2 = dev(rng.standard_normal(shape).astype(np.float32)) if two_parts else None
     out = []
     for fused in (0, 1):
         RM, RV = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
@@ -130,12 +133,17 @@ def test_batchnorm_residual_tail_is_bitwise_the_three_layers(rng, shape):
         DG, DB = torch.full((Cc,), 9.0, device="cuda"), torch.full((Cc,), 9.0, device="cuda")
         if fused:
             capi.check(L.b2c_bn_forward_train_fused_res(N, Cc, S, p(X), p(G), p(B), 1e-4, 0.9, 1, p(RM), p(RV), p(SM), p(SI), p(R), p(YS), 1, st()))
-            capi.check(L.b2c_bn_backward_fused_res(N, Cc, S, p(DS), p(YS), p(X), p(SM), p(SI), p(G), p(B), p(DG), p(DB), p(DX), p(DR), st()))
+            capi.check(L.b2c_bn_backward_fused_res(N, Cc, S, p(DS), p(DS2) if two_parts else None, p(YS), p(X), p(SM), p(SI), p(G), p(B), p(DG), p(DB),
+                                                   p(DX), p(DR), st()))
         else:
             XN, YB, DA = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
             capi.check(L.b2c_bn_forward_train(N, Cc, S, p(X), p(G), p(B), 1e-4, 0.9, 1, p(RM), p(RV), p(SM), p(SI), p(XN), p(YB), st()))
             capi.check(L.b2c_add_relu(X.numel(), p(YB), p(R), p(YS), st()))
-            capi.check(L.b2c_relu_backward2(X.numel(), p(DS), p(YS), p(DA), p(DR), st()))
+            DT = DS
+            if two_parts:
+                DT = torch.empty_like(DS)
+                capi.check(L.b2c_add(X.numel(), p(DS), p(DS2), p(DT), st()))
+            capi.check(L.b2c_relu_backward2(X.numel(), p(DT), p(YS), p(DA), p(DR), st()))
             capi.check(L.b2c_bn_backward(N, Cc, S, p(DA), p(XN), p(G), p(SI), p(DG), p(DB), p(DX), st()))
         out.append([host(t) for t in (YS, SM, SI, RM, RV, DG, DB, DX, DR)])
     for name, a, b in zip(("y_sum", "mean", "invstd", "run_mean", "run_var", "dgamma", "dbeta", "dx", "d_residual"), out[0], out[1]):
