@@ -104,6 +104,8 @@ def lib():
         "b2c_col2im_nd": (i, [vp, i] + [C.POINTER(i)] * 6 + [vp, vp]),
         "b2c_sgemm": (i, [i, i, i, i, i, f, vp, vp, f, vp, vp]),
         "b2c_sgemv": (i, [i, i, i, f, vp, vp, f, vp, vp]),
+        "b2c_sgemm_workspace_bytes": (sz, [i, i, i, i, i]),
+        "b2c_sgemm_ex": (i, [i, i, i, i, i, f, vp, vp, f, vp, vp, sz, vp]),
         "b2c_sgd_update": (i, [sz, vp, vp, vp, f, f, f, i, f, i, vp]),
         "b2c_sgd_update_arena": (i, [i, C.POINTER(sz), C.POINTER(sz), C.POINTER(f), C.POINTER(f), vp, vp, vp,
                                      f, i, f, i, vp]),
@@ -282,6 +284,16 @@ def col2im_nd(col, im, k, s, p, d, stream=None):
 def sgemm(transA, transB, M, N, K, alpha, A, B, beta, Cm, stream=None):
     check(lib().b2c_sgemm(int(transA), int(transB), M, N, K, alpha, _p(A), _p(B), beta, _p(Cm), _stream(stream)))
     return Cm
+
+
+def sgemm_ex(transA, transB, M, N, K, alpha, A, B, beta, Cm, stream=None):
+    """b2c_sgemm_ex with the scratch b2c_sgemm_workspace_bytes asks for (split-K tensor-core path for NoTrans x Trans products)."""
+    import torch
+    L = lib()
+    nbytes = L.b2c_sgemm_workspace_bytes(int(transA), int(transB), M, N, K)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=Cm.device)
+    check(L.b2c_sgemm_ex(int(transA), int(transB), M, N, K, alpha, _p(A), _p(B), beta, _p(Cm), _p(ws), nbytes, _stream(stream)))
+    return Cm, nbytes
 
 
 def sgemv(transA, M, N, alpha, A, x, beta, y, stream=None):

@@ -126,6 +126,25 @@ def test_sgemm_random_vs_oracle(rng, M, N, K, tA, tB):
         assert rel_err(host(Cm), want) < (TOL_FP32 if tc else TOL_SIMT)
 
 
+@pytest.mark.parametrize("M,N,K", [(64, 1000, 2048), (32, 512, 4096), (256, 10, 800), (64, 500, 800), (7, 130, 68)])
+def test_sgemm_ex_split_k_vs_oracle(rng, M, N, K):
+    """InnerProduct forward shapes (y = x W^T) through b2c_sgemm_ex with its workspace: the K loop is split over CTAs and the partial
+    tiles reduced in a fixed order -- same tolerance as the unsplit tensor-core path, and bit-reproducible run to run."""
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) * (2.0 / K) ** 0.5).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    for beta in (0.0, 1.0):
+        want = o.gemm(0, 1, M, N, K, 1.0, A, B, beta, C0, acc64=True)
+        outs = []
+        for _ in range(2):
+            Cm = dev(C0.copy())
+            _, nbytes = capi.sgemm_ex(0, 1, M, N, K, 1.0, dev(A), dev(B), beta, Cm)
+            outs.append(host(Cm))
+        assert rel_err(outs[0], want) < TOL_FP32
+        assert np.array_equal(outs[0], outs[1])
+    assert nbytes > 0 or K < 512
+
+
 # ---------------------------------------------------------------------------------------------- conv
 ENGINES = [("caffe", capi.ENGINE_CAFFE, None), ("implicit_simt", capi.ENGINE_CUDNN, capi.ALGO_SIMT),
            ("implicit_auto", capi.ENGINE_DEFAULT, capi.ALGO_AUTO)]
