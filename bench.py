@@ -280,6 +280,21 @@ def run_ours(args):
     prof = t.profile(2)
     layers = t.layers()
     allreduce = time_allreduce(t, world, dev) if world > 1 else None
+    if world > 1:
+        # the same exchange inside the step: CUDA events around every bucket's allreduce on the comm stream, 3 steps, max over ranks
+        t.bucket_timing(True)
+        t.step(3)
+        recs = t.bucket_times()
+        t.bucket_timing(False)
+        nb = len(recs) // 3
+        if nb:
+            ms_b = torch.tensor([[recs[s_ * nb + b_][1] for b_ in range(nb)] for s_ in range(3)], device=dev).mean(0)
+            dist.all_reduce(ms_b, op=dist.ReduceOp.MAX)
+            by_b = [recs[b_][0] for b_ in range(nb)]
+            f = 2.0 * (world - 1) / world
+            allreduce["in_step_buckets"] = [{"bytes": by_b[b_], "ms": float(ms_b[b_]), "busbw_gbs": by_b[b_] * f / (float(ms_b[b_]) / 1e3) / 1e9}
+                                            for b_ in range(nb)]
+            allreduce["in_step_busbw_gbs"] = sum(by_b) * f / (float(ms_b.sum()) / 1e3) / 1e9
 
     if rank == 0:
         pk = peaks()
@@ -371,23 +386,42 @@ def time_allreduce(t, world, dev, reps=5):
     dist.broadcast_object_list(ids, src=0)
     comm = capi.Comm(world, rank, ids[0])
     n = t.arena_floats()
-    buf = torch.zeros(n, device=dev)
+    # the buffer the product path uses: ncclMemAlloc memory registered with the communicator (plain cudaMalloc memory if that fails)
+    import ctypes as C
+    L = capi.lib()
+    L.b2c_comm_mem_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.b2c_comm_mem_free.argtypes = [C.c_void_p]
+    L.b2c_comm_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.b2c_comm_allreduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     st = torch.cuda.Stream(device=dev)
+    ptr, registered = C.c_void_p(), False
+    if L.b2c_comm_mem_alloc(C.byref(ptr), n * 4) == 0:
+        registered = L.b2c_comm_register(comm._h, ptr, n * 4) == 0
+        buf = None
+    else:
+        buf = torch.zeros(n, device=dev)
+        ptr = C.c_void_p(buf.data_ptr())
+    sp = C.c_void_p(st.cuda_stream)
+
+    comm_allreduce = lambda: capi.check(L.b2c_comm_allreduce_sum(comm._h, ptr, n, sp))
     for _ in range(2):
-        comm.allreduce_sum(buf, stream=st)
+        comm_allreduce()
     st.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(st)
     for _ in range(reps):
-        comm.allreduce_sum(buf, stream=st)
+        comm_allreduce()
     b.record(st)
     st.synchronize()
     v = torch.tensor([a.elapsed_time(b) / reps], device=dev)
     dist.all_reduce(v, op=dist.ReduceOp.MAX)
     ms_ = float(v.item())
     comm.destroy()
+    if buf is None:
+        L.b2c_comm_mem_free(ptr)
     algbw = n * 4 / (ms_ / 1e3) / 1e9
-    return {"bytes": n * 4, "ms": ms_, "algbw_gbs": algbw, "busbw_gbs": algbw * 2 * (world - 1) / world, "nvlink_ref_gbs": 900.0}
+    return {"bytes": n * 4, "ms": ms_, "algbw_gbs": algbw, "busbw_gbs": algbw * 2 * (world - 1) / world, "nvlink_ref_gbs": 900.0,
+            "buffer": "ncclMemAlloc + ncclCommRegister" if registered else "cudaMalloc"}
 
 
 def main():

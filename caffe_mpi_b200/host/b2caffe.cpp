@@ -620,7 +620,23 @@ void P2PSync::on_start(ParamArena& arena) {
   }
 }
 void P2PSync::allreduce_bucket(float* buf, size_t count) {
+  if (!timing_) { B2C_CHECK(b2c_comm_allreduce_sum(comm_, buf, count, comm_stream_)); return; }
+  TimedBucket t{sizeof(float) * count, nullptr, nullptr};
+  CUDA_CHECK(cudaEventCreate(&t.a)); CUDA_CHECK(cudaEventCreate(&t.b));
+  CUDA_CHECK(cudaEventRecord(t.a, comm_stream_));
   B2C_CHECK(b2c_comm_allreduce_sum(comm_, buf, count, comm_stream_));
+  CUDA_CHECK(cudaEventRecord(t.b, comm_stream_));
+  timed_.push_back(t);
+}
+void P2PSync::collect_bucket_times(vector<size_t>* bytes, vector<float>* ms) {
+  CUDA_CHECK(cudaStreamSynchronize(comm_stream_));
+  for (TimedBucket& t : timed_) {
+    float v = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&v, t.a, t.b));
+    bytes->push_back(t.bytes); ms->push_back(v);
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  timed_.clear();
 }
 int P2PSync::divide_batch_size(int total, int solver_count) {
   // parallel.cpp:284-293: total/solver_count, rounded up so that no sample is dropped

@@ -365,10 +365,16 @@ class P2PSync : public SolverCallback {
   void reduce_barrier() override;
   // batch division of parallel.cpp:284-293: per-rank batch, rounded up to a multiple
   static int divide_batch_size(int total, int solver_count);
+  // measurement: CUDA events around every bucket's allreduce on the comm stream (off by default; bench.py's in-step bus bandwidth)
+  void set_bucket_timing(bool on) { timing_ = on; }
+  void collect_bucket_times(vector<size_t>* bytes, vector<float>* ms);   // drains the comm stream, returns and clears the records
  private:
   int nranks_, rank_;
   b2c_comm* comm_ = nullptr;
   cudaStream_t comm_stream_ = nullptr;
+  bool timing_ = false;
+  struct TimedBucket { size_t bytes; cudaEvent_t a, b; };
+  vector<TimedBucket> timed_;
 };
 
 // Event-driven Net::ReduceAndUpdate: after the backward pass has produced the diffs of bucket b on the

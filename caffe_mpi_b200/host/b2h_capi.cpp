@@ -283,6 +283,22 @@ int b2h_trainer_attach_sync(void* hv, int nranks, int rank, unsigned char* id, i
     h->net->AttachSync(h->sync.get());
   });
 }
+// in-step exchange timing: CUDA events around every bucket's allreduce on the comm stream (bench.py)
+int b2h_trainer_bucket_timing(void* hv, int on) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({ B2_CHECK(h->sync != nullptr, "bucket timing needs an attached P2PSync"); h->sync->set_bucket_timing(on != 0); });
+}
+int b2h_trainer_bucket_times(void* hv, int cap, unsigned long long* bytes, float* ms, int* count) {
+  auto* h = static_cast<TrainerHandle*>(hv);
+  B2H_TRY({
+    B2_CHECK(h->sync != nullptr, "bucket timing needs an attached P2PSync");
+    vector<size_t> by;
+    vector<float> t;
+    h->sync->collect_bucket_times(&by, &t);
+    *count = (int)by.size();
+    for (int i = 0; i < *count && i < cap; ++i) { bytes[i] = by[i]; ms[i] = t[i]; }
+  });
+}
 int b2h_trainer_step(void* hv, int nsteps, int copy_input) {
   auto* h = static_cast<TrainerHandle*>(hv);
   B2H_TRY({ for (int i = 0; i < nsteps; ++i) h->net->Step(copy_input != 0); });

@@ -281,6 +281,8 @@ class Trainer:
         L.b2h_trainer_step.argtypes = [vp, i, i]
         L.b2h_trainer_forward_backward.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2h_trainer_clear_param_diffs.argtypes = [vp]
+        L.b2h_trainer_bucket_timing.argtypes = [vp, C.c_int]
+        L.b2h_trainer_bucket_times.argtypes = [vp, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.b2h_trainer_sync.argtypes = [vp]
         L.b2h_trainer_loss.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2h_trainer_blob_count.argtypes = [vp, C.c_char_p]
@@ -323,6 +325,17 @@ class Trainer:
         v = C.c_float()
         _ck(lib().b2h_trainer_forward_backward(self._h, C.byref(v)))
         return v.value
+
+    def bucket_timing(self, on):
+        _ck(lib().b2h_trainer_bucket_timing(self._h, 1 if on else 0))
+
+    def bucket_times(self, cap=4096):
+        """[(bytes, ms)] of every bucket allreduce since bucket_timing(True), in issue order; drains the comm stream."""
+        by = (C.c_ulonglong * cap)()
+        ms = (C.c_float * cap)()
+        n = C.c_int()
+        _ck(lib().b2h_trainer_bucket_times(self._h, cap, by, ms, C.byref(n)))
+        return [(int(by[i]), float(ms[i])) for i in range(min(n.value, cap))]
 
     def clear_param_diffs(self):
         """Net::ClearParamDiffs: Step() expects zeroed diffs (the update clears them); call this after a forward_backward() made

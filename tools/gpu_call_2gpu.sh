@@ -1,10 +1,11 @@
 #!/bin/bash
-# 2 GPUs: multi-rank correctness through the C++ P2PSync / ReduceScheduler, data-parallel bench
+# 2 GPUs: multi-rank correctness through the C++ P2PSync / ReduceScheduler, data-parallel bench (default buckets and 2), allreduce sweep
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi -L > gpurun_out/m2_smi.txt 2>&1
 timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/m2_tests.log 2>&1; echo "rc=$?" >> gpurun_out/m2_tests.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/m2_bench.json 2> gpurun_out/m2_bench.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 10 --warmup 3 --buckets 2 > gpurun_out/m2_bench_b2.json 2> gpurun_out/m2_bench_b2.err
 NCCL_DEBUG=INFO timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 tools/allreduce_sweep.py > gpurun_out/m2_allreduce.log 2>&1
 grep -E "NVLS|Channel|Connected|Using network|comm 0x.*nranks|^\{" gpurun_out/m2_allreduce.log | head -60 > gpurun_out/m2_allreduce_summary.log
 echo done
