@@ -3,11 +3,12 @@
 // accumulation order.  Both files produce the same bits for the same input because they run the same code in the same order.
 #pragma once
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "b2c_common.cuh"
 
 namespace b2c {
 
-constexpr int BN_CLUSTER = 8;          // CTAs per channel (portable cluster limit)
+constexpr int BN_CLUSTER = 16;         // most CTAs per channel: 8 is the portable cluster limit, 16 needs the non-portable opt-in (bn_max_cluster())
 constexpr int BN_THREADS = 512;
 constexpr int BN_U = 4;                // independent 16-byte loads in flight per thread and stream
 
@@ -113,14 +114,44 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
   a += a2; b += b2;
 }
 
-// cluster size for the per-channel kernels: ~16K values per CTA, at least one CTA per SM, at most 8.  (Two CTAs per SM as the
-// floor put the 14x14 layers of ResNet-50 -- 256 channels, 12.5K values each -- on 512 three-iteration CTAs in two waves:
-// ~20 us per launch whatever the tensor size, profiles/r02_c8_bn_sweep.log.)
+// Largest cluster the per-channel kernels may use on this device: B2C_BN_CLUSTER (8 or 16, default 16) capped by what the
+// device schedules -- 16-CTA clusters are a non-portable size (cudaFuncAttributeNonPortableClusterSizeAllowed); the probe kernel
+// stands for the real ones (same block size, no dynamic shared memory: the hardware limit is per GPC, not per kernel).
+static __global__ void bn_cluster_probe_kernel() {}
+static inline unsigned bn_max_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2C_BN_CLUSTER");
+    int want = e ? atoi(e) : 16;
+    want = want >= 16 ? 16 : want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+    if (want > 8) {
+      int clusters = 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16, 1, 1); cfg.blockDim = dim3(BN_THREADS, 1, 1);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (cudaFuncSetAttribute(bn_cluster_probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+          cudaOccupancyMaxActiveClusters(&clusters, bn_cluster_probe_kernel, &cfg) != cudaSuccess || clusters < 1) {
+        (void)cudaGetLastError();
+        want = 8;
+      }
+    }
+    v = want;
+  }
+  return (unsigned)v;
+}
+// cluster size for the per-channel kernels: slices of at most 12 544 values (50 KB: the backward kernels park two streams of it
+// in shared memory with two CTAs per SM), at least one CTA per SM, at most bn_max_cluster().  (A floor of two CTAs per SM put the
+// 14x14 layers of ResNet-50 on 512 three-iteration CTAs in two waves: ~20 us per launch whatever the tensor size,
+// profiles/r02_c8_bn_sweep.log.)
 static inline unsigned bn_cluster_size(int N, int C, int S) {
   const size_t E = (size_t)N * S;
+  const unsigned maxc = bn_max_cluster();
   unsigned cs = 1;
-  while (cs < BN_CLUSTER && E / (cs * 2) >= 16384) cs *= 2;
-  while (cs < BN_CLUSTER && (size_t)C * cs < (unsigned)sm_count()) cs *= 2;
+  while (cs < maxc && E / cs > 12544) cs *= 2;
+  while (cs < maxc && (size_t)C * cs < (unsigned)sm_count()) cs *= 2;
   return cs;
 }
 // one cluster of `cs` CTAs per channel; `smem_pad` bytes of (unused) dynamic shared memory bound the CTAs per SM
@@ -135,6 +166,7 @@ static inline void bn_launch_clustered(void (*kernel)(Args...), unsigned cs, int
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cs > 8) cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

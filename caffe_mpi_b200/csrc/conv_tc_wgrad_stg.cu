@@ -504,7 +504,7 @@ static bool wstg_enabled() {
 struct WstgPlan { int T, cn, bwx, bpi, splits, kb_per_split; long long nkb; bool plane; };
 static bool wstg_plane_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED_PLANE"); on = e ? atoi(e) : 0; }   // off until validated on a B200
+  if (on < 0) { const char* e = getenv("B2C_WGRAD_STAGED_PLANE"); on = e ? atoi(e) : 1; }
   return on != 0;
 }
 static bool wstg_plan(const ConvShape& s, WstgPlan* pl) {

@@ -65,7 +65,7 @@ bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__
 // this CTA's share of sum dy_eff * x_norm (a) and sum dy_eff (b) of channel c
 // MASK: 0 = dy as it is, 1 = ReLU mask recomputed from the forward's expression, 2 = ReLU mask from the tensor `ym` (the
 // post-activation output of the Eltwise sum this BatchNorm feeds: ym > 0)
-// CACHE: 1 = park every loaded unit of x in shared memory (cx[unit index - slice start]), 2 = x and the MASKED gradient (cd)
+// CACHE bit 0: park every loaded unit of x in shared memory (cx[unit index - slice start]); bit 1: park the MASKED (and summed) gradient (cd)
 // U: loads in flight per thread and stream; a thread visits its units in the same order whatever U is, so U does not change the sums
 // dy2 (may be null): a second part of the upstream gradient, added to dy element by element (the shadow diff of a blob that fans
 // out: SplitLayer::Backward's accumulation, b2c_add's a + b, folded into this read)
@@ -117,8 +117,8 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
         const float nx = prep(d[u].x, v[u].x, t[u].x), ny = prep(d[u].y, v[u].y, t[u].y), nz = prep(d[u].z, v[u].z, t[u].z), nw = prep(d[u].w, v[u].w, t[u].w);
         a = fmaf(d[u].x, nx, a); a2 = fmaf(d[u].y, ny, a2); a = fmaf(d[u].z, nz, a); a2 = fmaf(d[u].w, nw, a2);
         b += d[u].x + d[u].y; b2 += d[u].z + d[u].w;
-        if (CACHE >= 1 && ok[u]) static_cast<float4*>(cx)[i + u * FB_THREADS - lo] = v[u];
-        if (CACHE == 2 && ok[u]) static_cast<float4*>(cd)[i + u * FB_THREADS - lo] = d[u];
+        if ((CACHE & 1) && ok[u]) static_cast<float4*>(cx)[i + u * FB_THREADS - lo] = v[u];
+        if ((CACHE & 2) && ok[u]) static_cast<float4*>(cd)[i + u * FB_THREADS - lo] = d[u];
       }
     } else {
       float d[U], v[U], t[U];
@@ -131,8 +131,8 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float xn = prep(d[u], v[u], t[u]); a = fmaf(d[u], xn, a); b += d[u];
-        if (CACHE >= 1 && ok[u]) static_cast<float*>(cx)[i + u * FB_THREADS - lo] = v[u];
-        if (CACHE == 2 && ok[u]) static_cast<float*>(cd)[i + u * FB_THREADS - lo] = d[u];
+        if ((CACHE & 1) && ok[u]) static_cast<float*>(cx)[i + u * FB_THREADS - lo] = v[u];
+        if ((CACHE & 2) && ok[u]) static_cast<float*>(cd)[i + u * FB_THREADS - lo] = d[u];
       }
     }
   }
@@ -267,7 +267,9 @@ bn_fwd_onepass_kernel(int N, int C, int S, const float* __restrict__ x, const fl
 // dgamma / dbeta reduction + dx of one channel per cluster
 // MASK == 2 (residual form): dy is the diff of the Eltwise sum's top, ym its (post-ReLU) data; the masked gradient is also what the
 // sum's OTHER bottom receives: written to d_res when that is not null (EltwiseLayer::Backward's second copy)
-// CACHE: 0 = phase 2 reads everything again, 1 = x parked in shared memory, 2 = x and the masked gradient parked
+// CACHE: bit 0 = x parked in shared memory, bit 1 = the masked (and summed) gradient parked; what is not parked is read again in
+// phase 2.  When only one stream fits, the residual form parks the gradient (it stands for up to three input streams: dy, dy2,
+// the mask source), the plain forms park x.
 template <bool VEC, int MASK, int CACHE>
 __global__ void __launch_bounds__(BN_THREADS, 2)
 bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, const float* __restrict__ dy, const float* __restrict__ x,
@@ -283,8 +285,10 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
   const bool affine = gamma != nullptr;
   const float m = mean[c], is = invstd[c], g = affine ? gamma[c] : 1.f, bt = affine ? beta[c] : 0.f;
   // the two parked streams: x first, the masked gradient behind it (slice_units units each)
+  constexpr bool PX = (CACHE & 1) != 0, PD = (CACHE & 2) != 0;
   void* cx = bn_cache;
-  void* cd = VEC ? static_cast<void*>(bn_cache + slice_units) : static_cast<void*>(reinterpret_cast<float*>(bn_cache) + slice_units);
+  void* cd = !PX ? static_cast<void*>(bn_cache)
+                 : VEC ? static_cast<void*>(bn_cache + slice_units) : static_cast<void*>(reinterpret_cast<float*>(bn_cache) + slice_units);
   float a, b;
   bn_bwd_partial_fused<VEC, MASK, CACHE, U>(N, C, S, c, dy, x, ym, m, is, g, bt, affine, rank, nranks, a, b, cx, cd, dy2);
   block_sum2(a, b);
@@ -298,7 +302,7 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
   // upstream gradient (masked in place unless it comes from the cache, where it already is) -> dx
   auto one = [&](float& d, float xv, float yv) {
     const float xn = bn_xn(xv, m, is);
-    if (CACHE != 2) {
+    if (!PD) {
       if (MASK == 1) d = relu_mask(d, bn_y(xn, g, bt, affine));
       if (MASK == 2) d = relu_mask(d, yv);
     }
@@ -310,14 +314,14 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (ok[u]) {
-          d[u] = CACHE == 2 ? static_cast<const float4*>(cd)[idx[u]] : reinterpret_cast<const float4*>(dy)[off[u]];
-          if (MASK == 2 && CACHE != 2 && dy2) {
+          d[u] = PD ? static_cast<const float4*>(cd)[idx[u]] : reinterpret_cast<const float4*>(dy)[off[u]];
+          if (MASK == 2 && !PD && dy2) {
             const float4 e = reinterpret_cast<const float4*>(dy2)[off[u]];
             d[u] = make_float4(__fadd_rn(d[u].x, e.x), __fadd_rn(d[u].y, e.y), __fadd_rn(d[u].z, e.z), __fadd_rn(d[u].w, e.w));
           }
-          v[u] = CACHE >= 1 ? static_cast<const float4*>(cx)[idx[u]] : reinterpret_cast<const float4*>(x)[off[u]];
+          v[u] = PX ? static_cast<const float4*>(cx)[idx[u]] : reinterpret_cast<const float4*>(x)[off[u]];
         }
-        t[u] = (MASK == 2 && CACHE != 2 && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        t[u] = (MASK == 2 && !PD && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -332,11 +336,11 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (ok[u]) {
-          d[u] = CACHE == 2 ? static_cast<const float*>(cd)[idx[u]] : dy[off[u]];
-          if (MASK == 2 && CACHE != 2 && dy2) d[u] = __fadd_rn(d[u], dy2[off[u]]);
-          v[u] = CACHE >= 1 ? static_cast<const float*>(cx)[idx[u]] : x[off[u]];
+          d[u] = PD ? static_cast<const float*>(cd)[idx[u]] : dy[off[u]];
+          if (MASK == 2 && !PD && dy2) d[u] = __fadd_rn(d[u], dy2[off[u]]);
+          v[u] = PX ? static_cast<const float*>(cx)[idx[u]] : x[off[u]];
         }
-        t[u] = (MASK == 2 && CACHE != 2 && ok[u]) ? ym[off[u]] : 0.f;
+        t[u] = (MASK == 2 && !PD && ok[u]) ? ym[off[u]] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -528,13 +532,14 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
   if (bn_onepass() || y_mask) {
     unsigned slice_units = 0;
     const size_t slice = bn_slice_bytes(N, S, vec, cs, &slice_units);
-    const int park = 2 * slice <= bn_cache_budget() ? 2 : slice <= bn_cache_budget() ? 1 : 0;      // x and the masked gradient, x only, nothing
-    const size_t smem = (size_t)park * slice;
+    // both streams, one (the gradient in the residual form, x otherwise), nothing
+    const int park = 2 * slice <= bn_cache_budget() ? 3 : slice <= bn_cache_budget() ? (y_mask ? 2 : 1) : 0;
+    const size_t smem = (size_t)(park == 3 ? 2 : park ? 1 : 0) * slice;
     const float inv_cnt1 = 1.0f / ((float)N * S);
 #define B2C_BWD0(V, M, P) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P>, smem)) return rc; \
     bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
                         gamma, beta, dgamma, dbeta, dx, d_residual, dy2); } while (0)
-#define B2C_BWD1(V, M) do { if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
+#define B2C_BWD1(V, M) do { if (park == 3) B2C_BWD0(V, M, 3); else if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
     if (vec) { if (y_mask) B2C_BWD1(true, 2); else if (relu) B2C_BWD1(true, 1); else B2C_BWD1(true, 0); }
     else { if (y_mask) B2C_BWD1(false, 2); else if (relu) B2C_BWD1(false, 1); else B2C_BWD1(false, 0); }
 #undef B2C_BWD1
