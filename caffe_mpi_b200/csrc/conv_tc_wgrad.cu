@@ -768,13 +768,15 @@ static int wgrad_compact_mode() {
 static bool wgrad_compact_shape_ok(const ConvShape& s) {
   const long long P = (long long)s.Ho * s.Wo;
   const int mode = wgrad_compact_mode();
-  if (!(mode != 0 && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) && s.G == 1 && P % 4 == 0 && P >= 32))
+  if (!(mode != 0 && wgrad_tma_enabled() && s.kh == 1 && s.kw == 1 && s.ph == 0 && s.pw == 0 && (s.sh > 1 || s.sw > 1) && s.G == 1))
     return false;
   // with the staged kernel behind it the extra pass over X pays for every layer it takes; with the 3xTF32 TMA kernel only for
-  // the wide ones (measurements above)
+  // the wide ones (measurements above).  7x7 outputs (P = 49) exist only on the staged kernel (plane mode).
   ConvShape d = s;
   d.H = s.Ho; d.W = s.Wo; d.sh = d.sw = 1; d.is_1x1 = true;
-  return mode == 2 || s.O > 128 || tc_wgrad_stg_supported(d);
+  const bool staged = tc_wgrad_stg_supported(d);
+  if (!(P % 4 == 0 && P >= 32)) return staged && P == 49;
+  return mode == 2 || s.O > 128 || staged;
 }
 static ConvShape wgrad_compact_dense_shape(const ConvShape& s) {
   ConvShape d = s;

@@ -66,6 +66,7 @@ MODEL_CASES += [
     # staged weight gradient: a map wide enough that only ONE X stage fits (W = 80), and an odd width (unaligned tap windows)
     ("wstg_wide_3x3", dict(N=2, Cin=32, H=8, W=80, O=32, k=3, s=1, p=1, d=1, G=1, bias=True)),
     ("wstg_oddw_3x3", dict(N=5, Cin=32, H=8, W=13, O=40, k=3, s=1, p=1, d=1, G=1, bias=False)),
+    ("strided_1x1_to_7x7", dict(N=5, Cin=64, H=14, W=14, O=96, k=1, s=2, p=0, d=1, G=1, bias=False)),   # wgrad: subsample, then plane mode
     # 7x7 maps: the staged kernel's plane mode (whole image planes staged, up to 4 images per 128-row tile)
     ("plane_3x3_7x7", dict(N=9, Cin=64, H=7, W=7, O=72, k=3, s=1, p=1, d=1, G=1, bias=True)),
     ("plane_1x1_7x7", dict(N=11, Cin=96, H=7, W=7, O=160, k=1, s=1, p=0, d=1, G=1, bias=True)),
