@@ -105,6 +105,8 @@ def lib():
         "b2c_sgemm": (i, [i, i, i, i, i, f, vp, vp, f, vp, vp]),
         "b2c_sgemv": (i, [i, i, i, f, vp, vp, f, vp, vp]),
         "b2c_sgemm_workspace_bytes": (sz, [i, i, i, i, i]),
+        "b2c_sgemm_tc_supported": (i, [i, i, i, i, i]),
+        "b2c_transpose": (i, [i, i, vp, vp, vp]),
         "b2c_sgemm_ex": (i, [i, i, i, i, i, f, vp, vp, f, vp, vp, sz, vp]),
         "b2c_sgd_update": (i, [sz, vp, vp, vp, f, f, f, i, f, i, vp]),
         "b2c_sgd_update_arena": (i, [i, C.POINTER(sz), C.POINTER(sz), C.POINTER(f), C.POINTER(f), vp, vp, vp,

@@ -385,6 +385,10 @@ extern "C" int b2c_conv_backward_bias(const b2c_conv_desc* d, const float* dy, f
   return launch_bias_grad(d->s.N, d->s.O, d->s.Ho * d->s.Wo, dy, db, as_stream(stream));
 }
 
+extern "C" int b2c_sgemm_tc_supported(int transA, int transB, int M, int N, int K) {
+  return M > 0 && N > 0 && K > 0 && have_device() && g_default_algo != B2C_ALGO_SIMT && g_default_math == B2C_MATH_FP32 &&
+         tc_gemm_supported(transA != 0, transB != 0, M, N, K) ? 1 : 0;
+}
 extern "C" size_t b2c_sgemm_workspace_bytes(int transA, int transB, int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0 || !have_device()) return 0;
   return tc_gemm_workspace(transA != 0, transB != 0, M, N, K);

@@ -114,7 +114,7 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
   a += a2; b += b2;
 }
 
-// Largest cluster the per-channel kernels may use on this device: B2C_BN_CLUSTER (8 or 16, default 16) capped by what the
+// Largest cluster the per-channel kernels may use on this device: B2C_BN_CLUSTER (1..16, default 8 = the portable limit) capped by what the
 // device schedules -- 16-CTA clusters are a non-portable size (cudaFuncAttributeNonPortableClusterSizeAllowed); the probe kernel
 // stands for the real ones (same block size, no dynamic shared memory: the hardware limit is per GPC, not per kernel).
 static __global__ void bn_cluster_probe_kernel() {}
@@ -122,7 +122,7 @@ static inline unsigned bn_max_cluster() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B2C_BN_CLUSTER");
-    int want = e ? atoi(e) : 16;
+    int want = e ? atoi(e) : 8;
     want = want >= 16 ? 16 : want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
     if (want > 8) {
       int clusters = 0;
@@ -142,15 +142,16 @@ static inline unsigned bn_max_cluster() {
   }
   return (unsigned)v;
 }
-// cluster size for the per-channel kernels: slices of at most 12 544 values (50 KB: the backward kernels park two streams of it
-// in shared memory with two CTAs per SM), at least one CTA per SM, at most bn_max_cluster().  (A floor of two CTAs per SM put the
-// 14x14 layers of ResNet-50 on 512 three-iteration CTAs in two waves: ~20 us per launch whatever the tensor size,
-// profiles/r02_c8_bn_sweep.log.)
+// cluster size for the per-channel kernels: ~16K values or more per CTA, at least one CTA per SM, at most bn_max_cluster().
+// Measured (profiles/r02_c11_bn_sweep.log, r02_c11_bench*.json): FEWER, FATTER CTAs win -- halving the slices (so that both
+// backward streams fit shared memory) cost 25 % on the 28x28 layers, 16-CTA clusters another 40 % on the 56x56 ones (co-scheduling
+// sixteen 512-thread CTAs in one GPC), and a floor of two CTAs per SM put the 14x14 layers on 512 three-iteration CTAs in two
+// waves (~20 us per launch whatever the tensor size, r02_c8_bn_sweep.log).
 static inline unsigned bn_cluster_size(int N, int C, int S) {
   const size_t E = (size_t)N * S;
   const unsigned maxc = bn_max_cluster();
   unsigned cs = 1;
-  while (cs < maxc && E / cs > 12544) cs *= 2;
+  while (cs < maxc && E / (cs * 2) >= 16384) cs *= 2;
   while (cs < maxc && (size_t)C * cs < (unsigned)sm_count()) cs *= 2;
   return cs;
 }

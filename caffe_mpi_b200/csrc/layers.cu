@@ -580,6 +580,32 @@ extern "C" int b2c_pool_backward(int method, int NC, int H, int W, int kh, int k
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
+// dst[c][r] = src[r][c]: 32 x 32 tiles through shared memory (padded: conflict-free both ways), coalesced reads and writes
+__global__ void __launch_bounds__(256)
+transpose_kernel(int rows, int cols, const float* __restrict__ src, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;             // 32 x 8 threads
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long r = r0 + ty + 8 * j, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + 8 * j][tx] = src[r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long c = c0 + ty + 8 * j, r = r0 + tx;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[tx][ty + 8 * j];
+  }
+}
+extern "C" int b2c_transpose(int rows, int cols, const float* src, float* dst, void* stream) {
+  NEED(src && dst && rows > 0 && cols > 0 && src != dst, "b2c_transpose: bad argument");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  NEED(grid.y <= 65535, "b2c_transpose: too many rows");
+  transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, cols, src, dst);
+  B2C_POST_LAUNCH();
+  return B2C_OK;
+}
 extern "C" int b2c_add(size_t n, const float* a, const float* b, float* y, void* stream) {
   NEED(a && b && y, "b2c_add: null");
   if (!n) return B2C_OK;

@@ -158,6 +158,15 @@ void InnerProductLayer::Reshape(const vector<Blob*>& b, const vector<Blob*>& t) 
   t[0]->Reshape({M_, num_output_});
   const size_t wsb = b2c_sgemm_workspace_bytes(0, 1, M_, num_output_, K_);
   if (wsb) gemm_ws_.Reshape({(int)((wsb + 3) / 4)});
+  // backward: dW = dy^T[N x M] * (x^T[K x M])^T (reduction over the batch), dx = dy[M x N] * (W^T[K x N])^T (reduction over the outputs)
+  const char* e = getenv("B2C_IP_BWD_TC");
+  const bool on = !e || atoi(e) != 0;
+  bwd_w_tc_ = on && b2c_sgemm_tc_supported(0, 1, num_output_, K_, M_) != 0;
+  bwd_x_tc_ = on && b2c_sgemm_tc_supported(0, 1, M_, K_, num_output_) != 0;
+  size_t bws = 0;
+  if (bwd_w_tc_) { dyt_.Reshape({num_output_, M_}); xt_.Reshape({K_, M_}); bws = std::max(bws, b2c_sgemm_workspace_bytes(0, 1, num_output_, K_, M_)); }
+  if (bwd_x_tc_) { wt_.Reshape({K_, num_output_}); bws = std::max(bws, b2c_sgemm_workspace_bytes(0, 1, M_, K_, num_output_)); }
+  if (bws) bwd_ws_.Reshape({(int)((bws + 3) / 4)});
 }
 void InnerProductLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) {
   // y[M x N] = x[M x K] * W[N x K]^T (+ bias)   (inner_product_layer.cpp: caffe_gpu_gemm(NoTrans, Trans, M, N, K))
@@ -173,9 +182,25 @@ void InnerProductLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>&
 }
 void InnerProductLayer::Backward_gpu(const vector<Blob*>& t, const vector<bool>& pd, const vector<Blob*>& b) {
   // dW[N x K] += dy^T[N x M] * x[M x K];  db += sum_m dy;  dx[M x K] = dy[M x N] * W[N x K]
-  B2C_CHECK(b2c_sgemm(1, 0, num_output_, K_, M_, 1.f, t[0]->gpu_diff(), b[0]->gpu_data(), 1.f, blobs_[0]->mutable_gpu_diff(), S()));
+  float* ws = bwd_ws_.count() ? bwd_ws_.mutable_gpu_data() : nullptr;
+  const size_t wsb = sizeof(float) * bwd_ws_.count();
+  float* dw = blobs_[0]->mutable_gpu_diff();
+  if (bwd_w_tc_) {                                  // (the GEMM's output has no alignment requirement: 4-byte stores)
+    B2C_CHECK(b2c_transpose(M_, num_output_, t[0]->gpu_diff(), dyt_.mutable_gpu_data(), S()));
+    B2C_CHECK(b2c_transpose(M_, K_, b[0]->gpu_data(), xt_.mutable_gpu_data(), S()));
+    B2C_CHECK(b2c_sgemm_ex(0, 1, num_output_, K_, M_, 1.f, dyt_.gpu_data(), xt_.gpu_data(), 1.f, dw, ws, wsb, S()));
+  } else {
+    B2C_CHECK(b2c_sgemm(1, 0, num_output_, K_, M_, 1.f, t[0]->gpu_diff(), b[0]->gpu_data(), 1.f, dw, S()));
+  }
   if (bias_) B2C_CHECK(b2c_bias_backward(M_, num_output_, 1, t[0]->gpu_diff(), blobs_[1]->mutable_gpu_diff(), S()));
-  if (pd[0]) B2C_CHECK(b2c_sgemm(0, 0, M_, K_, num_output_, 1.f, t[0]->gpu_diff(), blobs_[0]->gpu_data(), 0.f, b[0]->mutable_gpu_diff(), S()));
+  if (pd[0]) {
+    if (bwd_x_tc_) {
+      B2C_CHECK(b2c_transpose(num_output_, K_, blobs_[0]->gpu_data(), wt_.mutable_gpu_data(), S()));
+      B2C_CHECK(b2c_sgemm_ex(0, 1, M_, K_, num_output_, 1.f, t[0]->gpu_diff(), wt_.gpu_data(), 0.f, b[0]->mutable_gpu_diff(), ws, wsb, S()));
+    } else {
+      B2C_CHECK(b2c_sgemm(0, 0, M_, K_, num_output_, 1.f, t[0]->gpu_diff(), blobs_[0]->gpu_data(), 0.f, b[0]->mutable_gpu_diff(), S()));
+    }
+  }
 }
 
 // ================================================================================================ LRN / Dropout / Concat

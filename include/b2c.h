@@ -165,7 +165,13 @@ int b2c_sgemm(int transA, int transB, int M, int N, int K, float alpha, const fl
 /* The same product with caller-provided scratch (b2c_sgemm_workspace_bytes(...) bytes, 16-byte aligned; may be null / short: then
  * as b2c_sgemm).  With it the NoTrans x Trans tensor-core path splits the K loop over one wave of CTAs and reduces the partial
  * tiles in a fixed order (deterministic) -- InnerProduct forward at small batch is otherwise one CTA per 128 x 128 output tile. */
+/* 1 when b2c_sgemm / b2c_sgemm_ex would run this product (alpha = 1, beta in {0, 1}, 16-byte aligned operands) on the tensor cores:
+ * NoTrans x Trans, K >= 64, K % 4 == 0, default math = fp32-equivalent.  Callers that can choose their operand layout
+ * (InnerProductLayer::Backward_gpu with transposed copies) ask before preparing them. */
+int b2c_sgemm_tc_supported(int transA, int transB, int M, int N, int K);
 size_t b2c_sgemm_workspace_bytes(int transA, int transB, int M, int N, int K);
+/* dst[c][r] = src[r][c] (rows x cols -> cols x rows), src != dst. */
+int b2c_transpose(int rows, int cols, const float* src, float* dst, void* stream);
 int b2c_sgemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* B, float beta, float* C,
                  void* workspace, size_t workspace_bytes, void* stream);
 /* y = alpha*op(A)*x + beta*y, A row-major MxN.
