@@ -3,6 +3,9 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi -L > gpurun_out/m2_smi.txt 2>&1
+# the InnerProduct backward on the tensor-core GEMM is new in this build: check it first, fall back to the FFMA kernels for the rest if it fails
+timeout 600 python -m pytest tests/test_trainer_gpu.py tests/test_gpu_parity.py -m gpu -q -k "lenet or inception or forward_backward or sgd_steps or sgemm" > gpurun_out/m2_pretest.log 2>&1; echo "rc=$?" >> gpurun_out/m2_pretest.log
+if ! grep -q "^rc=0" gpurun_out/m2_pretest.log; then export B2C_IP_BWD_TC=0; echo "pretest failed: B2C_IP_BWD_TC=0" >> gpurun_out/m2_pretest.log; fi
 timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/m2_tests.log 2>&1; echo "rc=$?" >> gpurun_out/m2_tests.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/m2_bench.json 2> gpurun_out/m2_bench.err
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 10 --warmup 3 --buckets 2 > gpurun_out/m2_bench_b2.json 2> gpurun_out/m2_bench_b2.err
