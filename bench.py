@@ -199,7 +199,7 @@ def ncu_traffic(kernel_substr):
     """DRAM bytes per launch of the kernels whose name contains `kernel_substr`, from the newest committed ncu launch list of
     this round (profiles/r02_*launches*.csv: gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum per launch).
     Returns (read_bytes, write_bytes, launches, file) or None."""
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_*launches*.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_*launches*.csv")))      # r02_final_* sorts after the per-call r02_cN_* lists
     for path in reversed(files):
         try:
             rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
@@ -283,12 +283,18 @@ def run_ours(args):
     if world > 1:
         # the same exchange inside the step: CUDA events around every bucket's allreduce on the comm stream, 3 steps, max over ranks
         t.bucket_timing(True)
-        t.step(3)
+        t.step(1)                         # the first step after the profiled ones starts with the ranks out of step: not recorded
+        t.bucket_times()
+        barrier()
+        nst = 5
+        t.step(nst)
         recs = t.bucket_times()
         t.bucket_timing(False)
-        nb = len(recs) // 3
+        nb = len(recs) // nst
         if nb:
-            ms_b = torch.tensor([[recs[s_ * nb + b_][1] for b_ in range(nb)] for s_ in range(3)], device=dev).mean(0)
+            # per bucket: the fastest of the steps (an allreduce cannot finish before the slowest rank has produced its gradients, so
+            # every sample contains the ranks' skew; the minimum has the least of it), then the maximum over ranks
+            ms_b = torch.tensor([[recs[s_ * nb + b_][1] for b_ in range(nb)] for s_ in range(nst)], device=dev).min(0).values
             dist.all_reduce(ms_b, op=dist.ReduceOp.MAX)
             by_b = [recs[b_][0] for b_ in range(nb)]
             f = 2.0 * (world - 1) / world

@@ -256,6 +256,54 @@ pool_max_fwd_kernel(size_t total, int H, int W, int Ho, int Wo, int kh, int kw, 
     mask[i] = bi;
   }
 }
+// The common window shapes with Wo % Q == 0: one thread per Q consecutive outputs of a pooled row.  The (Q-1)*SW + KW input columns
+// those windows cover are loaded once per window row (27 loads instead of 36 for 3x3 / 2 with Q = 4), results leave as one 16- or
+// 8-byte store each for y and the mask.  Scan order and the strict '>' are those of the scalar kernel: same first maximum.
+template <int KH, int KW, int SH, int SW, int Q>
+__global__ void __launch_bounds__(256)
+pool_max_fwd_q_kernel(long long groups, int H, int W, int Ho, int Wo, int ph, int pw, const float* __restrict__ x,
+                      float* __restrict__ y, int* __restrict__ mask) {
+  constexpr int NCOL = (Q - 1) * SW + KW;
+  const int Wq = Wo / Q;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const long long orow = gidx / Wq;                             // pooled row index over (plane, ho)
+    const int wo0 = (int)(gidx - orow * Wq) * Q;
+    const long long nc = orow / Ho;
+    const int ho = (int)(orow - nc * Ho);
+    const int hs = ho * SH - ph, ws0 = wo0 * SW - pw;
+    const float* src = x + nc * H * W;
+    float best[Q];
+    int bi[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { best[q] = -FLT_MAX; bi[q] = -1; }
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+      const int h = hs + i;
+      const bool hok = (unsigned)h < (unsigned)H;
+      float v[NCOL];
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        const int w = ws0 + j;
+        v[j] = (hok && (unsigned)w < (unsigned)W) ? __ldg(src + (long long)h * W + w) : -FLT_MAX;
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+          const int w = ws0 + q * SW + j;
+          if (hok && (unsigned)w < (unsigned)W && v[q * SW + j] > best[q]) { best[q] = v[q * SW + j]; bi[q] = h * W + w; }
+        }
+    }
+    const long long o = orow * Wo + wo0;
+    if (Q == 4) {
+      *reinterpret_cast<float4*>(y + o) = make_float4(best[0], best[1], best[2], best[Q - 1]);
+      *reinterpret_cast<int4*>(mask + o) = make_int4(bi[0], bi[1], bi[2], bi[Q - 1]);
+    } else {
+      *reinterpret_cast<float2*>(y + o) = make_float2(best[0], best[Q - 1]);
+      *reinterpret_cast<int2*>(mask + o) = make_int2(bi[0], bi[Q - 1]);
+    }
+  }
+}
 // One block per input row (plane nc, row h): the row's window range in h is computed once, threads walk w.  (The first version
 // decoded a flat 64-bit element index with three runtime divisions per element and ran at 380 GB/s -- 0.67 ms per ResNet-50 step for
 // its one 3x3 / stride 2 pool, profiles/r02_c6_fullnet_launches.csv.)  Same ascending (a, b) summation order as before.
@@ -538,7 +586,21 @@ extern "C" int b2c_pool_forward(int method, int NC, int H, int W, int kh, int kw
   const size_t total = (size_t)NC * Ho * Wo;
   if (method == 0) {
     NEED(mask, "b2c_pool_forward: MAX needs a mask buffer");
-    pool_max_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, x, y, mask);
+    const bool common = kh == kw && sh == sw && ((kh == 3 && sh == 2) || (kh == 2 && sh == 2) || (kh == 3 && sh == 1));
+    const int q = Wo % 4 == 0 ? 4 : Wo % 2 == 0 ? 2 : 0;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(mask);
+    if (common && q && (al & (q == 4 ? 15 : 7)) == 0) {
+      const long long groups = (long long)NC * Ho * (Wo / q);
+      const unsigned grid = grid_for((size_t)groups, 256);
+      cudaStream_t s_ = as_stream(stream);
+#define B2C_POOLF(KH, S, Q) pool_max_fwd_q_kernel<KH, KH, S, S, Q><<<grid, 256, 0, s_>>>(groups, H, W, Ho, Wo, ph, pw, x, y, mask)
+      if (kh == 3 && sh == 2) { if (q == 4) B2C_POOLF(3, 2, 4); else B2C_POOLF(3, 2, 2); }
+      else if (kh == 2) { if (q == 4) B2C_POOLF(2, 2, 4); else B2C_POOLF(2, 2, 2); }
+      else { if (q == 4) B2C_POOLF(3, 1, 4); else B2C_POOLF(3, 1, 2); }
+#undef B2C_POOLF
+    } else {
+      pool_max_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, x, y, mask);
+    }
   } else if (method == 1) {
     pool_ave_fwd_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(total, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw, x, y);
   } else {
