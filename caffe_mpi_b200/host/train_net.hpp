@@ -120,7 +120,7 @@ class InnerProductLayer : public LayerBase {
   bool bwd_w_tc_ = false, bwd_x_tc_ = false;
 };
 
-// ---- layers the AlexNet / GoogLeNet / VGG-16 nets add (not yet run on a GPU; see include/b2c.h) ---------------------
+// ---- layers the AlexNet / GoogLeNet / VGG-16 nets add (parity: tests/test_layers_extra_gpu.py, test_inception_style_net_matches_oracle) ----
 class LRNLayer : public LayerBase {            // ACROSS_CHANNELS only (the BASELINE nets' use)
  public:
   LRNLayer(const LayerParameter& p, int size, float alpha, float beta, float k) : LayerBase(p), size_(size), alpha_(alpha), beta_(beta), k_(k) {}
