@@ -282,10 +282,16 @@ void AccuracyLayer::Forward_gpu(const vector<Blob*>& b, const vector<Blob*>& t) 
 // ================================================================================================ synthetic data
 SyntheticDataLayer::~SyntheticDataLayer() {
   if (host_) cudaFreeHost(host_);
+  if (copy_stream_) cudaStreamSynchronize(copy_stream_);
   if (host_u8_) cudaFreeHost(host_u8_);
-  if (host_off_) cudaFreeHost(host_off_);
-  if (dev_u8_) cudaFree(dev_u8_);
-  if (dev_off_) cudaFree(dev_off_);
+  for (Slot& sl : slot_) {
+    if (sl.host_off) cudaFreeHost(sl.host_off);
+    if (sl.dev_u8) cudaFree(sl.dev_u8);
+    if (sl.dev_off) cudaFree(sl.dev_off);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+    if (sl.consumed) cudaEventDestroy(sl.consumed);
+  }
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (dev_mean_) cudaFree(dev_mean_);
 }
 static inline uint64_t splitmix64(uint64_t z) {
@@ -309,9 +315,14 @@ void SyntheticDataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& t
     hd_ = wd_ = tf_.crop + 32;
     u8_bytes_ = (size_t)N * C * hd_ * wd_;
     CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_u8_), u8_bytes_));
-    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev_u8_), u8_bytes_));
-    CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_off_), sizeof(int) * 3 * N));
-    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev_off_), sizeof(int) * 3 * N));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (Slot& sl : slot_) {
+      CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&sl.dev_u8), u8_bytes_));
+      CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&sl.host_off), sizeof(int) * 3 * N));
+      CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&sl.dev_off), sizeof(int) * 3 * N));
+      CUDA_CHECK(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
+    }
     for (size_t i = 0; i < u8_bytes_; i += 8) {          // uniform bytes, 8 per draw
       uint64_t r = splitmix64(seed_ * 0x100000001B3ull + i);
       for (size_t k = 0; k < 8 && i + k < u8_bytes_; ++k, r >>= 8) host_u8_[i + k] = (unsigned char)(r & 0xff);
@@ -340,21 +351,38 @@ void SyntheticDataLayer::LoadBatch(Blob* top, cudaStream_t st) {
     return;
   }
   const int N = shapes_[0][0], C = shapes_[0][1];
+  Slot& sl = slot_[cur_];
+  if (!sl.in_flight) IssueCopy(cur_);                    // first batch, or nothing was prefetched
+  CUDA_CHECK(cudaStreamWaitEvent(st, sl.copied, 0));
+  B2C_CHECK(b2c_transform_u8(sl.dev_u8, N, C, hd_, wd_, tf_.crop, tf_.crop, sl.dev_off, sl.dev_off + N,
+                             reinterpret_cast<const unsigned char*>(sl.dev_off + 2 * N), dev_mean_, nullptr, tf_.scale, top->mutable_gpu_data(), st));
+  CUDA_CHECK(cudaEventRecord(sl.consumed, st));
+  sl.in_flight = false; sl.used = true;
+  cur_ ^= 1;
+  IssueCopy(cur_);                                       // the next batch travels while this one is being computed on
+}
+void SyntheticDataLayer::IssueCopy(int s) {
+  const int N = shapes_[0][0];
+  Slot& sl = slot_[s];
+  if (sl.used) {
+    CUDA_CHECK(cudaEventSynchronize(sl.copied));         // the previous copy out of this slot's pinned offsets finished long ago
+    CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, sl.consumed, 0));   // ... and the transform that read the slot has to be done before it is overwritten
+  }
   // DataTransformer's draws (data_transformer.cpp:129-135,187,224-225): mirror = rand0 % 2, offsets = rand % (extent - crop + 1)
-  unsigned char* mir = reinterpret_cast<unsigned char*>(host_off_ + 2 * N);
+  unsigned char* mir = reinterpret_cast<unsigned char*>(sl.host_off + 2 * N);
   for (int i = 0; i < N; ++i) {
     const uint64_t base = (draws_ * (uint64_t)N + (uint64_t)i) * 3;
     const unsigned r0 = (unsigned)(splitmix64(seed_ + base) >> 33) + 1, r1 = (unsigned)(splitmix64(seed_ + base + 1) >> 33) + 1,
                    r2 = (unsigned)(splitmix64(seed_ + base + 2) >> 33) + 1;
     mir[i] = (tf_.mirror && (r0 % 2)) ? 1 : 0;
-    host_off_[i] = (int)(r1 % (unsigned)(hd_ - tf_.crop + 1));
-    host_off_[N + i] = (int)(r2 % (unsigned)(wd_ - tf_.crop + 1));
+    sl.host_off[i] = (int)(r1 % (unsigned)(hd_ - tf_.crop + 1));
+    sl.host_off[N + i] = (int)(r2 % (unsigned)(wd_ - tf_.crop + 1));
   }
   ++draws_;
-  CUDA_CHECK(cudaMemcpyAsync(dev_u8_, host_u8_, u8_bytes_, cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaMemcpyAsync(dev_off_, host_off_, sizeof(int) * 3 * N, cudaMemcpyHostToDevice, st));
-  B2C_CHECK(b2c_transform_u8(dev_u8_, N, C, hd_, wd_, tf_.crop, tf_.crop, dev_off_, dev_off_ + N,
-                             reinterpret_cast<const unsigned char*>(dev_off_ + 2 * N), dev_mean_, nullptr, tf_.scale, top->mutable_gpu_data(), st));
+  CUDA_CHECK(cudaMemcpyAsync(sl.dev_u8, host_u8_, u8_bytes_, cudaMemcpyHostToDevice, copy_stream_));
+  CUDA_CHECK(cudaMemcpyAsync(sl.dev_off, sl.host_off, sizeof(int) * 3 * N, cudaMemcpyHostToDevice, copy_stream_));
+  CUDA_CHECK(cudaEventRecord(sl.copied, copy_stream_));
+  sl.in_flight = true;
 }
 
 // ================================================================================================ TrainNet

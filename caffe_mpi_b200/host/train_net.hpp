@@ -219,11 +219,21 @@ class SyntheticDataLayer : public LayerBase {
   int hd_ = 0, wd_ = 0;
   size_t u8_bytes_ = 0;
   unsigned char* host_u8_ = nullptr;      // pinned [N][C][hd][wd]
-  unsigned char* dev_u8_ = nullptr;
-  int* host_off_ = nullptr;               // pinned: h_off[N], w_off[N], then mirror[N] as bytes
-  int* dev_off_ = nullptr;
   float* dev_mean_ = nullptr;
   uint64_t draws_ = 0;                    // batches drawn so far (crop / mirror stream position)
+  // Prefetch (BasePrefetchingDataLayer's thread, as a copy stream): while step i computes, batch i+1's datums and its crop / mirror
+  // draws travel host -> device into the other of two slots; LoadBatch makes the compute stream wait for its slot, transforms out
+  // of it and starts the next copy.  Every step still moves one batch over PCIe; the copy no longer sits in front of the forward.
+  struct Slot {
+    unsigned char* dev_u8 = nullptr;
+    int* host_off = nullptr;              // pinned: h_off[N], w_off[N], then mirror[N] as bytes
+    int* dev_off = nullptr;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    bool in_flight = false, used = false;
+  } slot_[2];
+  int cur_ = 0;
+  cudaStream_t copy_stream_ = nullptr;
+  void IssueCopy(int s);
 };
 
 class TrainNet {
