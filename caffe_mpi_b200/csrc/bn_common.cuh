@@ -9,7 +9,7 @@
 namespace b2c {
 
 constexpr int BN_CLUSTER = 16;         // most CTAs per channel: 8 is the portable cluster limit, 16 needs the non-portable opt-in (bn_max_cluster())
-constexpr int BN_THREADS = 512;
+constexpr int BN_THREADS = 512;        // most threads per CTA (the kernels' launch bound); bn_threads() picks the launch size per shape
 constexpr int BN_U = 4;                // independent 16-byte loads in flight per thread and stream
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -60,6 +60,7 @@ template <bool VEC, int MODE, bool CACHE = false>
 __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, const float* __restrict__ x, const float* __restrict__ q,
                                                    float k, unsigned rank, unsigned nranks, float& a, float& b, void* cache = nullptr) {
   constexpr int U = BN_U;                                       // independent loads in flight per thread
+  const unsigned TH = blockDim.x;                               // the launch size fixes the summation order: bn_threads() on the host
   const unsigned units = VEC ? S / 4 : S;                       // units per plane
   unsigned lo, hi;
   bn_slice((unsigned)N * units, rank, nranks, lo, hi);
@@ -68,14 +69,14 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
   PlaneCursor cur;
   unsigned i = lo + threadIdx.x;
   if (i < hi) cur.init(i, units);
-  for (; i < hi; i += U * BN_THREADS) {
+  for (; i < hi; i += U * TH) {
     size_t off[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      ok[u] = i + u * BN_THREADS < hi;
+      ok[u] = i + u * TH < hi;
       off[u] = ((size_t)cur.n * C + c) * units + cur.p;
-      cur.advance(BN_THREADS, units);
+      cur.advance(TH, units);
     }
     if (VEC) {
       float4 v[U], w[U];
@@ -83,7 +84,7 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
       for (int u = 0; u < U; ++u) {
         v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(k, k, k, k);
         if (MODE == 1) w[u] = ok[u] ? reinterpret_cast<const float4*>(q)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CACHE && ok[u]) static_cast<float4*>(cache)[i + u * BN_THREADS - lo] = v[u];
+        if (CACHE && ok[u]) static_cast<float4*>(cache)[i + u * TH - lo] = v[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -102,7 +103,7 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
       for (int u = 0; u < U; ++u) {
         v[u] = ok[u] ? x[off[u]] : k;
         if (MODE == 1) w[u] = ok[u] ? q[off[u]] : 0.f;
-        if (CACHE && ok[u]) static_cast<float*>(cache)[i + u * BN_THREADS - lo] = v[u];
+        if (CACHE && ok[u]) static_cast<float*>(cache)[i + u * TH - lo] = v[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -156,11 +157,16 @@ static inline unsigned bn_cluster_size(int N, int C, int S) {
   return cs;
 }
 // one cluster of `cs` CTAs per channel; `smem_pad` bytes of (unused) dynamic shared memory bound the CTAs per SM
+// threads per CTA: 512, or 128 for channels of at most 4 096 values (ResNet-50's 7x7 layers: 2 048 channels x 3 136 values --
+// one 512-thread CTA per channel was seven waves of CTAs that are all set-up and barriers, ~85 us for a 26 MB tensor)
+static inline unsigned bn_threads(int N, int S) {
+  return (size_t)N * S <= 4096 ? 128u : (unsigned)BN_THREADS;
+}
 template <typename... Args>
-static inline void bn_launch_clustered(void (*kernel)(Args...), unsigned cs, int C, size_t smem_pad, void* stream, Args... args) {
+static inline void bn_launch_clustered(void (*kernel)(Args...), unsigned cs, int C, size_t smem_pad, void* stream, unsigned threads, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs, C, 1);
-  cfg.blockDim = dim3(BN_THREADS, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem_pad;
   cfg.stream = as_stream(stream);
   cudaLaunchAttribute attr[1];

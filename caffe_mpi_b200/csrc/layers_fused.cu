@@ -74,7 +74,7 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
                                                      const float* __restrict__ ym, float m, float is, float g, float bt, bool affine,
                                                      unsigned rank, unsigned nranks, float& a, float& b, void* cx = nullptr, void* cd = nullptr,
                                                      const float* __restrict__ dy2 = nullptr) {
-  constexpr int FB_THREADS = BN_THREADS;
+  const unsigned FB_THREADS = blockDim.x;
   const unsigned units = VEC ? S / 4 : S;
   unsigned lo, hi;
   bn_slice((unsigned)N * units, rank, nranks, lo, hi);
@@ -177,18 +177,19 @@ __device__ __forceinline__ void bn_walk_slice(int N, int C, unsigned units, int 
   unsigned lo, hi;
   bn_slice((unsigned)N * units, rank, nranks, lo, hi);
   PlaneCursor cur;
+  const unsigned TH = blockDim.x;
   unsigned i = lo + threadIdx.x;
   if (i < hi) cur.init(i, units);
-  for (; i < hi; i += U * BN_THREADS) {
+  for (; i < hi; i += U * TH) {
     size_t off[U];
     unsigned idx[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      ok[u] = i + u * BN_THREADS < hi;
-      idx[u] = i + u * BN_THREADS - lo;
+      ok[u] = i + u * TH < hi;
+      idx[u] = i + u * TH - lo;
       off[u] = ((size_t)cur.n * C + c) * units + cur.p;
-      cur.advance(BN_THREADS, units);
+      cur.advance(TH, units);
     }
     f(off, idx, ok);
   }
@@ -480,7 +481,7 @@ static int bn_forward_fused_impl(int N, int C, int S, const float* x, const floa
     const bool park = slice <= bn_cache_budget();
     const size_t smem = park ? slice : 0;
 #define B2C_FWD0(V, R, Q, P) do { if (int rc = bn_onepass_attr(bn_fwd_onepass_kernel<V, R, Q, P>, smem)) return rc; \
-    bn_launch_clustered(bn_fwd_onepass_kernel<V, R, Q, P>, cs, C, smem, stream, N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
+    bn_launch_clustered(bn_fwd_onepass_kernel<V, R, Q, P>, cs, C, smem, stream, bn_threads(N, S), N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
                         save_mean, save_invstd, running_mean, running_var, residual, y); } while (0)
 #define B2C_FWD1(V, R, Q) do { if (park) B2C_FWD0(V, R, Q, true); else B2C_FWD0(V, R, Q, false); } while (0)
 #define B2C_FWD2(V, R) do { if (residual) B2C_FWD1(V, R, true); else B2C_FWD1(V, R, false); } while (0)
@@ -537,7 +538,7 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     const size_t smem = (size_t)(park == 3 ? 2 : park ? 1 : 0) * slice;
     const float inv_cnt1 = 1.0f / ((float)N * S);
 #define B2C_BWD0(V, M, P) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P>, smem)) return rc; \
-    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
+    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, bn_threads(N, S), N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
                         gamma, beta, dgamma, dbeta, dx, d_residual, dy2); } while (0)
 #define B2C_BWD1(V, M) do { if (park == 3) B2C_BWD0(V, M, 3); else if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
     if (vec) { if (y_mask) B2C_BWD1(true, 2); else if (relu) B2C_BWD1(true, 1); else B2C_BWD1(true, 0); }
@@ -547,10 +548,10 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     B2C_POST_LAUNCH();
     return B2C_OK;
   }
-  if (vec) { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
-             else bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
-  else { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
-         else bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, (size_t)0, stream, N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  if (vec) { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+             else bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  else { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+         else bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
   B2C_POST_LAUNCH();
   const size_t units = (size_t)N * C * (vec ? S / 4 : S);
   const unsigned blocks = (unsigned)((units + 256 * FB_EW - 1) / (256 * FB_EW));
