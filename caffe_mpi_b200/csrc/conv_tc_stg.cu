@@ -29,9 +29,11 @@
 //     operand bytes in shared / tensor memory halve.  Dropped terms (lo*lo and the bf16 rounding of lo) are ~2^-17 per
 //     product: measured 5e-6..1.3e-5 blob-level against the 3xTF32 kernel (profiles/r02_c2_diag.log), 100x inside 1e-3.
 //   * Epilogue: double-buffered TMEM accumulators, tcgen05.ld, (+ bias), 32-channel chunks transposed through shared
-//     memory [channel][128 pixels] and written by the TMA unit: one tensor store per chunk and image (box {128, 32, 1} of
-//     the output blob, clipped by the hardware at the image end, the channel count and -- through a negative start
-//     column -- the image start).
+//     memory [channel][128 pixels] and written by the TMA unit when the tile lies inside one image: one tensor store per
+//     chunk (box {128, 32, 1} of the output blob, clipped by the hardware at the image end and the channel count; the start
+//     column is never negative -- a negative store coordinate is an illegal-instruction fault, measured).  Tiles that span
+//     two images write the staged chunk with 16-byte st.global.
+//   * Plane mode (BWT < 128): 7x7 maps, whole image planes staged -- see Smem below.
 // dgrad of a stride-1 same convolution is the same kernel on dY with the transposed + flipped filter.
 #include <cuda.h>
 #include <cuda_bf16.h>
