@@ -160,7 +160,10 @@ static inline unsigned bn_cluster_size(int N, int C, int S) {
 // threads per CTA: 512, or 128 for channels of at most 4 096 values (ResNet-50's 7x7 layers: 2 048 channels x 3 136 values --
 // one 512-thread CTA per channel was seven waves of CTAs that are all set-up and barriers, ~85 us for a 26 MB tensor)
 static inline unsigned bn_threads(int N, int S) {
-  return (size_t)N * S <= 4096 ? 128u : (unsigned)BN_THREADS;
+  static int mid = -1;                    // B2C_BN_THREADS_MID: launch size for channels of 4 097 .. 16 384 values (experiment knob, default 512)
+  if (mid < 0) { const char* e = getenv("B2C_BN_THREADS_MID"); mid = e ? atoi(e) : BN_THREADS; if (mid != 128 && mid != 256) mid = BN_THREADS; }
+  const size_t E = (size_t)N * S;
+  return E <= 4096 ? 128u : E <= 16384 ? (unsigned)mid : (unsigned)BN_THREADS;
 }
 template <typename... Args>
 static inline void bn_launch_clustered(void (*kernel)(Args...), unsigned cs, int C, size_t smem_pad, void* stream, unsigned threads, Args... args) {
