@@ -54,9 +54,10 @@ __device__ __forceinline__ void bn_slice(unsigned total, unsigned rank, unsigned
 }
 
 // MODE 0: a = sum (x-k), b = sum (x-k)^2   (q unused)      MODE 1: a = sum dy*xn, b = sum dy   (x = dy, q = xnorm)
-// CACHE: every unit of x this thread loads is also parked in shared memory at [unit index - slice start] (the one-launch kernels
-// of layers_fused.cu read it back in their elementwise phase: same thread, same index, no barrier needed)
-template <bool VEC, int MODE, bool CACHE = false>
+// CACHE 1: every unit of x this thread loads is also parked in shared memory at [unit index - slice start] (the one-launch kernels
+// of layers_fused.cu read it back in their elementwise phase: same thread, same index, no barrier needed).  CACHE 2: the units
+// are already there (the thread's own cp.async prefetch): read them from shared memory instead of global memory.
+template <bool VEC, int MODE, int CACHE = 0>
 __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, const float* __restrict__ x, const float* __restrict__ q,
                                                    float k, unsigned rank, unsigned nranks, float& a, float& b, void* cache = nullptr) {
   constexpr int U = BN_U;                                       // independent loads in flight per thread
@@ -82,9 +83,10 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
       float4 v[U], w[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(k, k, k, k);
+        if (CACHE == 2) v[u] = ok[u] ? static_cast<const float4*>(cache)[i + u * TH - lo] : make_float4(k, k, k, k);
+        else v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(k, k, k, k);
         if (MODE == 1) w[u] = ok[u] ? reinterpret_cast<const float4*>(q)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CACHE && ok[u]) static_cast<float4*>(cache)[i + u * TH - lo] = v[u];
+        if (CACHE == 1 && ok[u]) static_cast<float4*>(cache)[i + u * TH - lo] = v[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -101,9 +103,10 @@ __device__ __forceinline__ void bn_channel_partial(int N, int C, int S, int c, c
       float v[U], w[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        v[u] = ok[u] ? x[off[u]] : k;
+        if (CACHE == 2) v[u] = ok[u] ? static_cast<const float*>(cache)[i + u * TH - lo] : k;
+        else v[u] = ok[u] ? x[off[u]] : k;
         if (MODE == 1) w[u] = ok[u] ? q[off[u]] : 0.f;
-        if (CACHE && ok[u]) static_cast<float*>(cache)[i + u * TH - lo] = v[u];
+        if (CACHE == 1 && ok[u]) static_cast<float*>(cache)[i + u * TH - lo] = v[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -159,11 +162,11 @@ static inline unsigned bn_cluster_size(int N, int C, int S) {
 // one cluster of `cs` CTAs per channel; `smem_pad` bytes of (unused) dynamic shared memory bound the CTAs per SM
 // threads per CTA: 512, or 128 for channels of at most 4 096 values (ResNet-50's 7x7 layers: 2 048 channels x 3 136 values --
 // one 512-thread CTA per channel was seven waves of CTAs that are all set-up and barriers, ~85 us for a 26 MB tensor)
-static inline unsigned bn_threads(int N, int S) {
-  static int mid = -1;                    // B2C_BN_THREADS_MID: launch size for channels of 4 097 .. 16 384 values (experiment knob, default 512)
-  if (mid < 0) { const char* e = getenv("B2C_BN_THREADS_MID"); mid = e ? atoi(e) : BN_THREADS; if (mid != 128 && mid != 256) mid = BN_THREADS; }
+static inline unsigned bn_threads(int N, int S, bool forward) {
+  // 4 097 .. 16 384 values per channel (the 14x14 layers): 256 threads forward (C1024: 55 -> 43 us), 512 backward (256 is 6 % slower
+  // there: the parked streams leave room for two CTAs per SM either way) -- profiles/r02_c15_bn_threads.log
   const size_t E = (size_t)N * S;
-  return E <= 4096 ? 128u : E <= 16384 ? (unsigned)mid : (unsigned)BN_THREADS;
+  return E <= 4096 ? 128u : (E <= 16384 && forward) ? 256u : (unsigned)BN_THREADS;
 }
 template <typename... Args>
 static inline void bn_launch_clustered(void (*kernel)(Args...), unsigned cs, int C, size_t smem_pad, void* stream, unsigned threads, Args... args) {

@@ -511,7 +511,7 @@ namespace b2c {
 int launch_bn_stats(int N, int C, int S, const float* x, float eps, float maf, int first, float* mean, float* invstd, float* run_mean,
                     float* run_var, bool vec, void* stream) {
   const unsigned cs = bn_cluster_size(N, C, S);
-  launch_clustered(vec ? bn_stats_kernel<true> : bn_stats_kernel<false>, cs, C, stream, bn_threads(N, S), N, C, S, x, eps, maf, first, mean, invstd, run_mean, run_var);
+  launch_clustered(vec ? bn_stats_kernel<true> : bn_stats_kernel<false>, cs, C, stream, bn_threads(N, S, true), N, C, S, x, eps, maf, first, mean, invstd, run_mean, run_var);
   B2C_POST_LAUNCH();
   return B2C_OK;
 }
@@ -524,7 +524,7 @@ extern "C" int b2c_bn_forward_train(int N, int C, int S, const float* x, const f
   NEED((size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_forward_train: channel extent out of range");
   const bool vec = vec_ok(S, {x, y, xnorm});
   const unsigned cs = bn_cluster_size(N, C, S);
-  launch_clustered(vec ? bn_stats_kernel<true> : bn_stats_kernel<false>, cs, C, stream, bn_threads(N, S), N, C, S, x, eps, moving_average_fraction, first_iteration,
+  launch_clustered(vec ? bn_stats_kernel<true> : bn_stats_kernel<false>, cs, C, stream, bn_threads(N, S, true), N, C, S, x, eps, moving_average_fraction, first_iteration,
                    save_mean, save_invstd, running_mean, running_var);
   B2C_POST_LAUNCH();
   const size_t units = (size_t)N * C * (vec ? S / 4 : S);
@@ -539,7 +539,7 @@ extern "C" int b2c_bn_backward(int N, int C, int S, const float* dy, const float
   NEED(dy && xnorm && save_invstd && dgamma && dbeta && dx, "b2c_bn_backward: null (dgamma/dbeta double as the reduction scratch)");
   NEED(N > 0 && C > 0 && S > 0 && (size_t)N * S < (1ull << 31) && C <= 65535, "b2c_bn_backward: channel extent out of range");
   const bool vec = vec_ok(S, {dy, xnorm, dx});
-  launch_clustered(vec ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, bn_cluster_size(N, C, S), C, stream, bn_threads(N, S), N, C, S, dy, xnorm, dgamma, dbeta);
+  launch_clustered(vec ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, bn_cluster_size(N, C, S), C, stream, bn_threads(N, S, false), N, C, S, dy, xnorm, dgamma, dbeta);
   B2C_POST_LAUNCH();
   const size_t units = (size_t)N * C * (vec ? S / 4 : S);
   const unsigned blocks = (unsigned)((units + 256 * BN_EW_PER_THREAD - 1) / (256 * BN_EW_PER_THREAD));

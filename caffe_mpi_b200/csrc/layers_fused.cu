@@ -207,7 +207,16 @@ __device__ __forceinline__ void bn_cluster_sum(cg::cluster_group& cluster, float
 // statistics (bn_stats_kernel's code and order) + normalisation [+ residual add] [+ ReLU] of one channel per cluster
 // RES: y = [max(0, .)] (BatchNorm(x) + res) -- the Eltwise SUM (and its in-place ReLU) that consumes this layer, folded in
 // CACHE: the slice is parked in dynamic shared memory between the phases (else phase 2 reads x again from global memory / L2)
-template <bool VEC, bool RELU, bool RES, bool CACHE>
+// CACHE: 0 = phase 2 reads x again from global memory / L2; 1 = the slice is parked in dynamic shared memory by phase 1's loads;
+// 2 = the whole slice is first brought in with cp.async (every thread issues ALL its units' copies at once -- ~100 KB in flight
+// per CTA against 32 KB with four register loads per thread -- and waits for its own), both phases then read shared memory
+__device__ __forceinline__ void bn_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bn_cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+template <bool VEC, bool RELU, bool RES, int CACHE>
 __global__ void __launch_bounds__(BN_THREADS, 2)
 bn_fwd_onepass_kernel(int N, int C, int S, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float eps, float maf, int first, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean,
@@ -218,6 +227,17 @@ bn_fwd_onepass_kernel(int N, int C, int S, const float* __restrict__ x, const fl
   const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
   const int c = blockIdx.y;
   const float k = x[(size_t)c * S];
+  if (CACHE == 2) {
+    bn_walk_slice<BN_U>(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[BN_U], const unsigned (&idx)[BN_U], const bool (&ok)[BN_U]) {
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u)
+        if (ok[u]) {
+          if (VEC) bn_cp_async16(bn_cache + idx[u], reinterpret_cast<const float4*>(x) + off[u]);
+          else bn_cp_async4(reinterpret_cast<float*>(bn_cache) + idx[u], x + off[u]);
+        }
+    });
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  }
   float a, b;
   bn_channel_partial<VEC, 0, CACHE>(N, C, S, c, x, nullptr, k, rank, nranks, a, b, bn_cache);
   block_sum2(a, b);
@@ -478,12 +498,14 @@ static int bn_forward_fused_impl(int N, int C, int S, const float* x, const floa
   if (bn_onepass() || residual) {
     const unsigned cs = bn_cluster_size(N, C, S);
     const size_t slice = bn_slice_bytes(N, S, vec, cs, nullptr);
-    const bool park = slice <= bn_cache_budget();
+    static int prefetch = -1;             // B2C_BN_PREFETCH (default 1): cp.async the slice into shared memory before the reduction
+    if (prefetch < 0) { const char* e = getenv("B2C_BN_PREFETCH"); prefetch = e ? atoi(e) : 1; }
+    const int park = slice <= bn_cache_budget() ? (prefetch ? 2 : 1) : 0;
     const size_t smem = park ? slice : 0;
 #define B2C_FWD0(V, R, Q, P) do { if (int rc = bn_onepass_attr(bn_fwd_onepass_kernel<V, R, Q, P>, smem)) return rc; \
-    bn_launch_clustered(bn_fwd_onepass_kernel<V, R, Q, P>, cs, C, smem, stream, bn_threads(N, S), N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
+    bn_launch_clustered(bn_fwd_onepass_kernel<V, R, Q, P>, cs, C, smem, stream, bn_threads(N, S, true), N, C, S, x, gamma, beta, eps, moving_average_fraction, first_iteration, \
                         save_mean, save_invstd, running_mean, running_var, residual, y); } while (0)
-#define B2C_FWD1(V, R, Q) do { if (park) B2C_FWD0(V, R, Q, true); else B2C_FWD0(V, R, Q, false); } while (0)
+#define B2C_FWD1(V, R, Q) do { if (park == 2) B2C_FWD0(V, R, Q, 2); else if (park == 1) B2C_FWD0(V, R, Q, 1); else B2C_FWD0(V, R, Q, 0); } while (0)
 #define B2C_FWD2(V, R) do { if (residual) B2C_FWD1(V, R, true); else B2C_FWD1(V, R, false); } while (0)
     if (vec) { if (relu) B2C_FWD2(true, true); else B2C_FWD2(true, false); }
     else { if (relu) B2C_FWD2(false, true); else B2C_FWD2(false, false); }
@@ -538,7 +560,7 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     const size_t smem = (size_t)(park == 3 ? 2 : park ? 1 : 0) * slice;
     const float inv_cnt1 = 1.0f / ((float)N * S);
 #define B2C_BWD0(V, M, P) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P>, smem)) return rc; \
-    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, bn_threads(N, S), N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
+    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, bn_threads(N, S, false), N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
                         gamma, beta, dgamma, dbeta, dx, d_residual, dy2); } while (0)
 #define B2C_BWD1(V, M) do { if (park == 3) B2C_BWD0(V, M, 3); else if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
     if (vec) { if (y_mask) B2C_BWD1(true, 2); else if (relu) B2C_BWD1(true, 1); else B2C_BWD1(true, 0); }
@@ -548,10 +570,10 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     B2C_POST_LAUNCH();
     return B2C_OK;
   }
-  if (vec) { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
-             else bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
-  else { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
-         else bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, (size_t)0, stream, bn_threads(N, S), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  if (vec) { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, true>, cs, C, (size_t)0, stream, bn_threads(N, S, false), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+             else bn_launch_clustered(bn_bwd_reduce_fused_kernel<true, false>, cs, C, (size_t)0, stream, bn_threads(N, S, false), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
+  else { if (relu) bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, true>, cs, C, (size_t)0, stream, bn_threads(N, S, false), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta);
+         else bn_launch_clustered(bn_bwd_reduce_fused_kernel<false, false>, cs, C, (size_t)0, stream, bn_threads(N, S, false), N, C, S, dy, x, save_mean, save_invstd, gamma, beta, dgamma, dbeta); }
   B2C_POST_LAUNCH();
   const size_t units = (size_t)N * C * (vec ? S / 4 : S);
   const unsigned blocks = (unsigned)((units + 256 * FB_EW - 1) / (256 * FB_EW));
