@@ -69,7 +69,9 @@ bn_norm_fused_kernel(size_t total_units, int C, int S, const float* __restrict__
 // U: loads in flight per thread and stream; a thread visits its units in the same order whatever U is, so U does not change the sums
 // dy2 (may be null): a second part of the upstream gradient, added to dy element by element (the shadow diff of a blob that fans
 // out: SplitLayer::Backward's accumulation, b2c_add's a + b, folded into this read)
-template <bool VEC, int MASK, int CACHE = 0, int U = BN_U>
+// PRE: the parked streams were brought into shared memory by the thread's own cp.async prefetch (x in cx, the RAW gradient in cd):
+// they are read from there, and the masked gradient overwrites the raw one in place
+template <bool VEC, int MASK, int CACHE = 0, int U = BN_U, bool PRE = false>
 __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c, const float* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ ym, float m, float is, float g, float bt, bool affine,
                                                      unsigned rank, unsigned nranks, float& a, float& b, void* cx = nullptr, void* cd = nullptr,
@@ -103,12 +105,14 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
       float4 d[U], v[U], t[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        d[u] = ok[u] ? reinterpret_cast<const float4*>(dy)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PRE && (CACHE & 2)) d[u] = ok[u] ? static_cast<const float4*>(cd)[i + u * FB_THREADS - lo] : make_float4(0.f, 0.f, 0.f, 0.f);
+        else d[u] = ok[u] ? reinterpret_cast<const float4*>(dy)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
         if (MASK == 2 && dy2 && ok[u]) {
           const float4 e = reinterpret_cast<const float4*>(dy2)[off[u]];
           d[u] = make_float4(__fadd_rn(d[u].x, e.x), __fadd_rn(d[u].y, e.y), __fadd_rn(d[u].z, e.z), __fadd_rn(d[u].w, e.w));
         }
-        v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(m, m, m, m);
+        if (PRE && (CACHE & 1)) v[u] = ok[u] ? static_cast<const float4*>(cx)[i + u * FB_THREADS - lo] : make_float4(m, m, m, m);
+        else v[u] = ok[u] ? reinterpret_cast<const float4*>(x)[off[u]] : make_float4(m, m, m, m);
         t[u] = (MASK == 2 && ok[u]) ? reinterpret_cast<const float4*>(ym)[off[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -117,21 +121,24 @@ __device__ __forceinline__ void bn_bwd_partial_fused(int N, int C, int S, int c,
         const float nx = prep(d[u].x, v[u].x, t[u].x), ny = prep(d[u].y, v[u].y, t[u].y), nz = prep(d[u].z, v[u].z, t[u].z), nw = prep(d[u].w, v[u].w, t[u].w);
         a = fmaf(d[u].x, nx, a); a2 = fmaf(d[u].y, ny, a2); a = fmaf(d[u].z, nz, a); a2 = fmaf(d[u].w, nw, a2);
         b += d[u].x + d[u].y; b2 += d[u].z + d[u].w;
-        if ((CACHE & 1) && ok[u]) static_cast<float4*>(cx)[i + u * FB_THREADS - lo] = v[u];
+        if ((CACHE & 1) && !PRE && ok[u]) static_cast<float4*>(cx)[i + u * FB_THREADS - lo] = v[u];
         if ((CACHE & 2) && ok[u]) static_cast<float4*>(cd)[i + u * FB_THREADS - lo] = d[u];
       }
     } else {
       float d[U], v[U], t[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        d[u] = ok[u] ? dy[off[u]] : 0.f;
+        if (PRE && (CACHE & 2)) d[u] = ok[u] ? static_cast<const float*>(cd)[i + u * FB_THREADS - lo] : 0.f;
+        else d[u] = ok[u] ? dy[off[u]] : 0.f;
         if (MASK == 2 && dy2 && ok[u]) d[u] = __fadd_rn(d[u], dy2[off[u]]);
-        v[u] = ok[u] ? x[off[u]] : m; t[u] = (MASK == 2 && ok[u]) ? ym[off[u]] : 0.f;
+        if (PRE && (CACHE & 1)) v[u] = ok[u] ? static_cast<const float*>(cx)[i + u * FB_THREADS - lo] : m;
+        else v[u] = ok[u] ? x[off[u]] : m;
+        t[u] = (MASK == 2 && ok[u]) ? ym[off[u]] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float xn = prep(d[u], v[u], t[u]); a = fmaf(d[u], xn, a); b += d[u];
-        if ((CACHE & 1) && ok[u]) static_cast<float*>(cx)[i + u * FB_THREADS - lo] = v[u];
+        if ((CACHE & 1) && !PRE && ok[u]) static_cast<float*>(cx)[i + u * FB_THREADS - lo] = v[u];
         if ((CACHE & 2) && ok[u]) static_cast<float*>(cd)[i + u * FB_THREADS - lo] = d[u];
       }
     }
@@ -291,7 +298,8 @@ bn_fwd_onepass_kernel(int N, int C, int S, const float* __restrict__ x, const fl
 // CACHE: bit 0 = x parked in shared memory, bit 1 = the masked (and summed) gradient parked; what is not parked is read again in
 // phase 2.  When only one stream fits, the residual form parks the gradient (it stands for up to three input streams: dy, dy2,
 // the mask source), the plain forms park x.
-template <bool VEC, int MASK, int CACHE>
+// PRE: the parked streams come in by cp.async before the reduction (all of a thread's units in flight at once), see the forward kernel
+template <bool VEC, int MASK, int CACHE, bool PRE>
 __global__ void __launch_bounds__(BN_THREADS, 2)
 bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, const float* __restrict__ dy, const float* __restrict__ x,
                       const float* __restrict__ ym, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -310,8 +318,24 @@ bn_bwd_onepass_kernel(int N, int C, int S, float inv_cnt, unsigned slice_units, 
   void* cx = bn_cache;
   void* cd = !PX ? static_cast<void*>(bn_cache)
                  : VEC ? static_cast<void*>(bn_cache + slice_units) : static_cast<void*>(reinterpret_cast<float*>(bn_cache) + slice_units);
+  if (PRE && CACHE != 0) {
+    bn_walk_slice<U>(N, C, VEC ? S / 4 : S, c, rank, nranks, [&](const size_t (&off)[U], const unsigned (&idx)[U], const bool (&ok)[U]) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) {
+          if (VEC) {
+            if (PX) bn_cp_async16(static_cast<float4*>(cx) + idx[u], reinterpret_cast<const float4*>(x) + off[u]);
+            if (PD) bn_cp_async16(static_cast<float4*>(cd) + idx[u], reinterpret_cast<const float4*>(dy) + off[u]);
+          } else {
+            if (PX) bn_cp_async4(static_cast<float*>(cx) + idx[u], x + off[u]);
+            if (PD) bn_cp_async4(static_cast<float*>(cd) + idx[u], dy + off[u]);
+          }
+        }
+    });
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  }
   float a, b;
-  bn_bwd_partial_fused<VEC, MASK, CACHE, U>(N, C, S, c, dy, x, ym, m, is, g, bt, affine, rank, nranks, a, b, cx, cd, dy2);
+  bn_bwd_partial_fused<VEC, MASK, CACHE, U, PRE && CACHE != 0>(N, C, S, c, dy, x, ym, m, is, g, bt, affine, rank, nranks, a, b, cx, cd, dy2);
   block_sum2(a, b);
   if (threadIdx.x == 0) part = make_float2(a, b);
   cluster.sync();
@@ -559,14 +583,18 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     const int park = 2 * slice <= bn_cache_budget() ? 3 : slice <= bn_cache_budget() ? (y_mask ? 2 : 1) : 0;
     const size_t smem = (size_t)(park == 3 ? 2 : park ? 1 : 0) * slice;
     const float inv_cnt1 = 1.0f / ((float)N * S);
-#define B2C_BWD0(V, M, P) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P>, smem)) return rc; \
-    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P>, cs, C, smem, stream, bn_threads(N, S, false), N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
+    static int prefetch = -1;             // B2C_BN_PREFETCH_BWD (default 0 until measured): cp.async the parked streams before the reduction
+    if (prefetch < 0) { const char* e = getenv("B2C_BN_PREFETCH_BWD"); prefetch = e ? atoi(e) : 0; }
+#define B2C_BWDP(V, M, P, Q) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P, Q>, smem)) return rc; \
+    bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P, Q>, cs, C, smem, stream, bn_threads(N, S, false), N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
                         gamma, beta, dgamma, dbeta, dx, d_residual, dy2); } while (0)
+#define B2C_BWD0(V, M, P) do { if (prefetch && P) B2C_BWDP(V, M, P, true); else B2C_BWDP(V, M, P, false); } while (0)
 #define B2C_BWD1(V, M) do { if (park == 3) B2C_BWD0(V, M, 3); else if (park == 2) B2C_BWD0(V, M, 2); else if (park == 1) B2C_BWD0(V, M, 1); else B2C_BWD0(V, M, 0); } while (0)
     if (vec) { if (y_mask) B2C_BWD1(true, 2); else if (relu) B2C_BWD1(true, 1); else B2C_BWD1(true, 0); }
     else { if (y_mask) B2C_BWD1(false, 2); else if (relu) B2C_BWD1(false, 1); else B2C_BWD1(false, 0); }
 #undef B2C_BWD1
 #undef B2C_BWD0
+#undef B2C_BWDP
     B2C_POST_LAUNCH();
     return B2C_OK;
   }
