@@ -583,8 +583,8 @@ static int bn_backward_fused_impl(int N, int C, int S, const float* dy, const fl
     const int park = 2 * slice <= bn_cache_budget() ? 3 : slice <= bn_cache_budget() ? (y_mask ? 2 : 1) : 0;
     const size_t smem = (size_t)(park == 3 ? 2 : park ? 1 : 0) * slice;
     const float inv_cnt1 = 1.0f / ((float)N * S);
-    static int prefetch = -1;             // B2C_BN_PREFETCH_BWD (default 0 until measured): cp.async the parked streams before the reduction
-    if (prefetch < 0) { const char* e = getenv("B2C_BN_PREFETCH_BWD"); prefetch = e ? atoi(e) : 0; }
+    static int prefetch = -1;             // B2C_BN_PREFETCH_BWD (default 1; 16.03 -> 15.88 ms per ResNet-50 step): cp.async the parked streams before the reduction
+    if (prefetch < 0) { const char* e = getenv("B2C_BN_PREFETCH_BWD"); prefetch = e ? atoi(e) : 1; }
 #define B2C_BWDP(V, M, P, Q) do { if (int rc = bn_onepass_attr(bn_bwd_onepass_kernel<V, M, P, Q>, smem)) return rc; \
     bn_launch_clustered(bn_bwd_onepass_kernel<V, M, P, Q>, cs, C, smem, stream, bn_threads(N, S, false), N, C, S, inv_cnt1, slice_units, dy, x, y_mask, save_mean, save_invstd, \
                         gamma, beta, dgamma, dbeta, dx, d_residual, dy2); } while (0)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(os.environ.get("B2C_RUN_EXPERIMENTAL") != "1", reason="experimental variants run only on request")
 @pytest.mark.parametrize("switch", ["B2C_WGRAD_COMPACT=2", "B2C_WGRAD_TMA=0", "B2C_CONV_STAGED=0", "B2C_CONV_STAGED_PLANE=0",
-                                    "B2C_WGRAD_STAGED=0", "B2C_WGRAD_STAGED_PLANE=0", "B2C_BN_CLUSTER=16", "B2C_FUSE_SPLIT=0", "B2C_BN_ONEPASS=0", "B2C_BN_CACHE_KB=0", "B2C_FUSE_RES=0"])
+                                    "B2C_WGRAD_STAGED=0", "B2C_WGRAD_STAGED_PLANE=0", "B2C_BN_CLUSTER=16", "B2C_FUSE_SPLIT=0", "B2C_BN_ONEPASS=0", "B2C_BN_PREFETCH=0", "B2C_BN_PREFETCH_BWD=0", "B2C_BN_CACHE_KB=0", "B2C_FUSE_RES=0"])
 def test_variant_passes_the_parity_cases(switch):
     name, val = switch.split("=")
     env = dict(os.environ, **{name: val})
