@@ -1,0 +1,164 @@
+// data_reader.cpp -- see data_reader.hpp.
+#include "data_reader.hpp"
+
+#include <cstring>
+
+#include "b2caffe.hpp"
+
+namespace caffe {
+
+namespace {
+// CursorManager::next / rewind step the cursor one record at a time and restart from the first record when it runs off the
+// end (data_reader.cpp:246-258, 300-305); n steps on a ring of `entries` records end where n % entries steps do.
+void step(db::LMDBCursor* cur) {
+  cur->Next();
+  if (!cur->valid()) cur->SeekToFirst();
+}
+void advance(db::LMDBCursor* cur, size_t n, size_t entries) {
+  for (size_t i = n % entries; i > 0; --i) step(cur);
+}
+}  // namespace
+
+DataReader::DataReader(const DataReaderParam& p) : p_(p) {
+  B2_CHECK(p_.batch_size > 0, "DataReader: batch_size must be positive");
+  B2_CHECK(p_.solver_count > 0 && p_.solver_rank < p_.solver_count, "DataReader: solver_rank outside solver_count");
+  B2_CHECK(p_.node_count > 0 && p_.node_rank < p_.node_count, "DataReader: node_rank outside node_count");
+  if (p_.parser_threads == 0) p_.parser_threads = 1;
+  db_.reset(new db::LMDB());
+  db_->Open(p_.source, db::READ);
+  B2_CHECK(db_->entries() > 0, "DataReader: database " + p_.source + " is empty");
+  {  // DataReader::sample(): the first datum fixes the batch geometry
+    std::unique_ptr<db::LMDBCursor> cur(db_->NewCursor());
+    B2_CHECK(cur->valid(), "DataReader: database " + p_.source + " has no first record");
+    Datum d;
+    B2_CHECK(ParseDatum(cur->data(), cur->size(), &d), "Database cursor failed to parse Datum record");
+    B2_CHECK(!d.encoded, "DataReader: encoded (JPEG / PNG) datums need an image decoder, which this build does not have; "
+                         "convert the database with `convert_imageset` without --encoded");
+    B2_CHECK(d.channels > 0 && d.height > 0 && d.width > 0, "DataReader: first datum has no shape");
+    c_ = d.channels; h_ = d.height; w_ = d.width;
+  }
+  full_cycle_ = p_.parser_threads * (size_t)p_.batch_size * p_.solver_count * p_.node_count;
+  for (size_t t = 0; t < p_.parser_threads; ++t) {
+    free_.emplace_back(new Queue());
+    full_.emplace_back(new Queue());
+  }
+  for (size_t t = 0; t < p_.parser_threads; ++t) threads_.emplace_back(&DataReader::thread_entry, this, t);
+}
+
+DataReader::~DataReader() {
+  for (auto& q : free_) { std::lock_guard<std::mutex> g(q->m); stop_ = true; }
+  for (auto& q : free_) q->cv.notify_all();
+  for (auto& q : full_) q->cv.notify_all();
+  for (auto& th : threads_) th.join();
+}
+
+size_t DataReader::first_record_of_batch(size_t n) const {
+  const size_t P = p_.parser_threads, B = (size_t)p_.batch_size;
+  const size_t t = n % P, k = n / P;
+  const size_t rank_cycle_per_solver = P * B, rank_cycle_per_node = rank_cycle_per_solver * p_.solver_count;
+  return rank_cycle_per_solver * p_.solver_rank + rank_cycle_per_node * p_.node_rank + t * B + k * full_cycle_;
+}
+
+void DataReader::free_push(BatchBuf* b) {
+  Queue& q = *free_[pushed_ % p_.parser_threads];
+  ++pushed_;
+  { std::lock_guard<std::mutex> g(q.m); q.q.push_back(b); }
+  q.cv.notify_one();
+}
+
+BatchBuf* DataReader::full_pop() {
+  B2_CHECK(popped_ < pushed_, "DataReader::full_pop: no buffer is with the reader (free_push one first)");
+  Queue& q = *full_[popped_ % p_.parser_threads];
+  std::unique_lock<std::mutex> g(q.m);
+  q.cv.wait(g, [&] { return !q.q.empty() || stop_; });
+  if (q.q.empty()) {                       // a parser thread died
+    std::lock_guard<std::mutex> e(err_m_);
+    Fatal(__FILE__, __LINE__, "DataReader: " + (error_.empty() ? std::string("reader stopped") : error_));
+  }
+  BatchBuf* b = q.q.front();
+  q.q.pop_front();
+  ++popped_;
+  return b;
+}
+
+void DataReader::fill(db::LMDBCursor* cur, size_t rec_id, BatchBuf* b) {
+  const size_t B = (size_t)p_.batch_size, bytes = datum_bytes();
+  Datum d;
+  for (size_t j = 0; j < B; ++j) {
+    B2_CHECK(ParseDatum(cur->data(), cur->size(), &d), "Database cursor failed to parse Datum record");
+    B2_CHECK(!d.encoded, "DataReader: encoded datum in " + p_.source + " (no image decoder in this build)");
+    B2_CHECK(d.channels == c_, "Number of channels can't vary in the same batch");
+    B2_CHECK(d.height == h_, "Image height can't vary in the same batch (crop might help here)");   // data_layer.cpp:262-271; all
+    B2_CHECK(d.width == w_, "Image width can't vary in the same batch (crop might help here)");     // datums share the sample's shape
+    B2_CHECK(d.data_size == bytes, d.data_size == 0 && !d.float_data.empty()
+                                       ? "DataReader: float_data datums are not built (uint8 `data` only)"
+                                       : "DataReader: datum data size disagrees with channels*height*width");
+    const size_t item = (rec_id + j) % B;                              // data_layer.cpp:256
+    memcpy(b->data + item * bytes, d.data, bytes);
+    b->label[item] = (float)d.label;
+    if (b->record_id) b->record_id[item] = (uint32_t)(rec_id + j);
+    step(cur);
+  }
+}
+
+void DataReader::thread_entry(size_t t) {
+  try {
+    const size_t P = p_.parser_threads, B = (size_t)p_.batch_size, entries = db_->entries();
+    std::unique_ptr<db::LMDBCursor> cur(db_->NewCursor());
+    size_t rec_id = first_record_of_batch(t);                           // CursorManager::rewind
+    cur->SeekToFirst();
+    advance(cur.get(), rec_id, entries);
+    for (size_t k = 0;; ++k) {
+      Queue& fq = *free_[t];
+      BatchBuf* b = nullptr;
+      {
+        std::unique_lock<std::mutex> g(fq.m);
+        fq.cv.wait(g, [&] { return !fq.q.empty() || stop_; });
+        if (stop_) return;
+        b = fq.q.front();
+        fq.q.pop_front();
+      }
+      fill(cur.get(), rec_id, b);
+      b->batch_id = k * P + t;
+      advance(cur.get(), full_cycle_ - B, entries);                     // CursorManager::next: rec_id_ += full_cycle_ - batch_size_
+      rec_id += full_cycle_;
+      Queue& uq = *full_[t];
+      { std::lock_guard<std::mutex> g(uq.m); uq.q.push_back(b); }
+      uq.cv.notify_one();
+    }
+  } catch (const std::exception& e) {
+    { std::lock_guard<std::mutex> g(err_m_); if (error_.empty()) error_ = e.what(); }
+    for (auto& q : full_) { std::lock_guard<std::mutex> g(q->m); stop_ = true; }
+    for (auto& q : full_) q->cv.notify_all();
+    for (auto& q : free_) q->cv.notify_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TransformDraws
+void TransformDraws::Fill3Randoms(unsigned* r) {
+  r[0] = r[1] = r[2] = 0;
+  if (mirror_) r[0] = (unsigned)rng_() + 1u;
+  if (train_ && crop_) {
+    r[1] = (unsigned)rng_() + 1u;
+    r[2] = (unsigned)rng_() + 1u;
+  }
+}
+
+void TransformDraws::Draw(int datum_h, int datum_w, int* h_off, int* w_off, unsigned char* do_mirror) {
+  unsigned r[3];
+  Fill3Randoms(r);
+  *do_mirror = (mirror_ && (r[0] % 2)) ? 1 : 0;
+  *h_off = *w_off = 0;
+  if (crop_) {
+    B2_CHECK(datum_h >= crop_ && datum_w >= crop_, "crop_size larger than the datum");   // data_transformer.cpp:192-193
+    if (train_) {
+      *h_off = (int)(r[1] % (unsigned)(datum_h - crop_ + 1));
+      *w_off = (int)(r[2] % (unsigned)(datum_w - crop_ + 1));
+    } else {
+      *h_off = (datum_h - crop_) / 2;
+      *w_off = (datum_w - crop_) / 2;
+    }
+  }
+}
+
+}  // namespace caffe

@@ -1,0 +1,88 @@
+// lmdb_reader.hpp -- read-only LMDB environment + cursor (storage half of the input pipeline).
+//
+// Mirrors caffe::db::LMDB / LMDBCursor (reference include/caffe/util/db.hpp:12-52, db_lmdb.hpp:27-106,
+// src/caffe/util/db_lmdb.cpp:10-46) for Mode READ: Open(source, READ), NewCursor(), cursor SeekToFirst / Next / valid /
+// key / value / data / size.  There is no liblmdb in the toolchain, so the on-disk format is read directly:
+//
+//   data.mdb = array of pages of `psize` bytes (psize = meta.mm_dbs[FREE_DBI].md_pad, 4096 by default).
+//   page header, 16 bytes:  pgno u64 | pad u16 | flags u16 | lower u16, upper u16  (overflow pages: pages u32 instead)
+//       flags: P_BRANCH 0x01, P_LEAF 0x02, P_OVERFLOW 0x04, P_META 0x08, P_LEAF2 0x20, P_SUBP 0x40
+//       node offsets u16[] start at byte 16; number of keys = (lower - 16) / 2
+//   pages 0 and 1: meta pages; header, then magic u32 0xBEEFC0DE | version u32 (1) | address u64 | mapsize u64 |
+//       MDB_db[2] (free list, main) | last_pg u64 | txnid u64.  The meta with the larger txnid is the current one.
+//       MDB_db, 48 bytes: pad u32 | flags u16 | depth u16 | branch_pages u64 | leaf_pages u64 | overflow_pages u64 |
+//                         entries u64 | root u64 (~0 = empty tree)
+//   node, 8-byte header:  lo u16 | hi u16 | flags u16 | ksize u16 | key bytes | data
+//       branch node: child page = lo | hi << 16 | flags << 32;  leaf node: data size = lo | hi << 16
+//       leaf flag F_BIGDATA 0x01: the data is a u64 page number of an overflow run holding the value after its 16-byte header
+//   (LMDB 0.9.x, mdb.c: MDB_page, MDB_node, MDB_db, MDB_meta; little-endian 64-bit build, which is what Caffe's LMDBs are.)
+//
+// The whole file is mmap'ed PROT_READ / MAP_SHARED, like mdb_env_open(MDB_RDONLY | MDB_NOLOCK) does; values are returned as
+// pointers into the mapping (zero copy), so a parser thread moves a datum's bytes once: page cache -> pinned batch buffer.
+// Not built: named sub-databases, DUPSORT, write transactions, the lock file (Caffe opens with MDB_NOLOCK).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace caffe { namespace db {
+
+enum Mode { READ, WRITE, NEW };
+
+class LMDB;
+
+class LMDBCursor {
+ public:
+  explicit LMDBCursor(const LMDB* env);        // positioned on the first record, like the reference's (db_lmdb.hpp:29-33)
+  void SeekToFirst();
+  void Next();
+  bool valid() const { return valid_; }
+  std::string key() const { return std::string(reinterpret_cast<const char*>(key_), ksize_); }
+  std::string value() const { return std::string(reinterpret_cast<const char*>(data_), dsize_); }
+  const void* data() const { return data_; }   // into the mapping; stable while the LMDB object lives
+  size_t size() const { return dsize_; }
+  const void* key_data() const { return key_; }
+  size_t key_size() const { return ksize_; }
+ private:
+  struct Level { uint64_t pgno; int idx; };
+  void descend_leftmost(uint64_t pgno);        // push pages down to the leftmost leaf under pgno
+  void load();                                 // key_ / data_ from the top of the stack
+  const LMDB* env_;
+  std::vector<Level> stack_;                   // root .. leaf
+  const uint8_t* key_ = nullptr;
+  const uint8_t* data_ = nullptr;
+  size_t ksize_ = 0, dsize_ = 0;
+  bool valid_ = false;
+};
+
+class LMDB {
+ public:
+  LMDB() = default;
+  ~LMDB() { Close(); }
+  LMDB(const LMDB&) = delete;
+  LMDB& operator=(const LMDB&) = delete;
+  // `source` is the environment directory (holding data.mdb) or the data file itself.  Only READ is built; anything else,
+  // a missing / truncated file or a foreign format is fatal (caffe::FatalError), like MDB_CHECK in the reference.
+  void Open(const std::string& source, Mode mode = READ);
+  void Close();
+  LMDBCursor* NewCursor() const { return new LMDBCursor(this); }
+  size_t entries() const { return entries_; }          // MDB_stat.ms_entries of the main database
+  unsigned page_size() const { return psize_; }
+  unsigned depth() const { return depth_; }
+  uint64_t txnid() const { return txnid_; }
+  static bool Exists(const std::string& source);       // data.mdb present (directory form) or `source` is a regular file
+
+ private:
+  friend class LMDBCursor;
+  const uint8_t* page(uint64_t pgno) const;            // bounds-checked
+  const uint8_t* map_ = nullptr;
+  size_t map_bytes_ = 0;
+  unsigned psize_ = 0, depth_ = 0;
+  uint64_t root_ = ~0ull, last_pg_ = 0, txnid_ = 0;
+  size_t entries_ = 0;
+};
+
+}  // namespace db
+}  // namespace caffe

@@ -190,6 +190,53 @@ SolverStateData ParseSolverState(const std::string& bytes) {
   return st;
 }
 
+bool ParseDatum(const void* bytes, size_t n, Datum* d) {
+  *d = Datum();
+  try {
+    Cursor c{static_cast<const uint8_t*>(bytes), static_cast<const uint8_t*>(bytes) + n};
+    while (!c.done()) {
+      const uint64_t key = c.varint();
+      const int f = (int)(key >> 3), wt = (int)(key & 7);
+      if (f == 1 && wt == 0) d->channels = (int)(int64_t)c.varint();
+      else if (f == 2 && wt == 0) d->height = (int)(int64_t)c.varint();
+      else if (f == 3 && wt == 0) d->width = (int)(int64_t)c.varint();
+      else if (f == 4 && wt == 2) { Cursor b = c.sub(); d->data = b.p; d->data_size = (size_t)(b.end - b.p); }
+      else if (f == 5 && wt == 0) d->label = (int)(int64_t)c.varint();
+      else if (f == 6 && wt == 2) {
+        Cursor b = c.sub();
+        if ((b.end - b.p) % 4) return false;
+        const size_t k = (size_t)(b.end - b.p) / 4, at = d->float_data.size();
+        d->float_data.resize(at + k);
+        memcpy(d->float_data.data() + at, b.p, k * 4);
+      } else if (f == 6 && wt == 5) {
+        if (c.end - c.p < 4) return false;
+        float v; memcpy(&v, c.p, 4); c.p += 4; d->float_data.push_back(v);
+      }
+      else if (f == 7 && wt == 0) d->encoded = c.varint() != 0;
+      else if (f == 8 && wt == 0) d->record_id = (uint32_t)c.varint();
+      else if (f == 0) return false;
+      else c.skip(wt);
+    }
+  } catch (const FatalError&) { return false; }
+  return true;
+}
+
+std::string SerializeDatum(int channels, int height, int width, const void* data, size_t data_size, int label, bool encoded,
+                           const std::vector<float>* float_data) {
+  std::string o;
+  put_int(o, 1, channels); put_int(o, 2, height); put_int(o, 3, width);
+  if (data_size) put_bytes(o, 4, std::string(static_cast<const char*>(data), data_size));
+  put_int(o, 5, label);
+  if (float_data) for (float v : *float_data) { put_tag(o, 6, 5); o.append(reinterpret_cast<const char*>(&v), 4); }   // unpacked, as proto2 writes it
+  if (encoded) put_int(o, 7, 1);
+  return o;
+}
+
+BlobData ParseBlobProto(const std::string& bytes) {
+  return parse_blob(Cursor{reinterpret_cast<const uint8_t*>(bytes.data()), reinterpret_cast<const uint8_t*>(bytes.data()) + bytes.size()});
+}
+std::string SerializeBlobProto(const BlobData& b, bool raw) { return blob_bytes(b, raw); }
+
 void WriteBinaryFile(const std::string& path, const std::string& bytes) {
   std::ofstream f(path, std::ios::binary | std::ios::trunc);
   B2_CHECK((bool)f, "Cannot open " + path + " for writing");

@@ -9,6 +9,8 @@
 // data / double_data / raw_data (FLOAT, FLOAT16, DOUBLE) and the legacy num/channels/height/width dims;
 // Net::ToProto, Net::CopyTrainedLayersFrom (net.cpp), SGDSolver::SnapshotSolverStateToBinaryProto / RestoreSolverState.
 #pragma once
+#include <cstddef>
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -24,6 +26,24 @@ std::string SerializeNetWeights(const NetWeights& net, bool raw_format = true);
 NetWeights ParseNetWeights(const std::string& bytes);                 // throws FatalError on malformed input
 std::string SerializeSolverState(const SolverStateData& st, bool raw_format = true);
 SolverStateData ParseSolverState(const std::string& bytes);
+
+// Datum (caffe.proto:43-56), the record type of Caffe's LMDB / LevelDB image databases.  ParseDatum is the zero-copy form of
+// Datum::ParseFromArray: `data` is a view into the parsed buffer (for an LMDB value: into the file mapping), so a parser thread
+// copies the pixel bytes once, straight into the pinned batch buffer.  Returns false on malformed input, like ParseFromArray.
+struct Datum {
+  int channels = 0, height = 0, width = 0, label = 0;
+  const uint8_t* data = nullptr;          // field 4 (bytes), not owned
+  size_t data_size = 0;
+  std::vector<float> float_data;          // field 6, packed or unpacked
+  bool encoded = false;                   // field 7: `data` holds a compressed image (JPEG / PNG) -- not decodable here
+  uint32_t record_id = 0;                 // field 8: assigned by the reader (data_reader.cpp:224)
+};
+bool ParseDatum(const void* bytes, size_t n, Datum* d);
+std::string SerializeDatum(int channels, int height, int width, const void* data, size_t data_size, int label, bool encoded = false,
+                           const std::vector<float>* float_data = nullptr);
+// a bare BlobProto file: transform_param.mean_file (data_transformer.cpp:31-38 reads it with ReadProtoFromBinaryFileOrDie)
+BlobData ParseBlobProto(const std::string& bytes);
+std::string SerializeBlobProto(const BlobData& b, bool raw_format = false);
 
 void WriteBinaryFile(const std::string& path, const std::string& bytes);
 std::string ReadBinaryFile(const std::string& path);
