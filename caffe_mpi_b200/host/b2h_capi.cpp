@@ -232,6 +232,11 @@ int b2h_net_param(void* h, int i, size_t* count, float* lr_mult, float* decay_mu
   snprintf(layer, cap, "%s", p.layer.c_str());
   return 0;
 }
+// 1 when layer i is a Data layer whose data_param.source opened (it will read the database), 0 otherwise
+int b2h_net_layer_uses_database(void* h, int i) {
+  const auto& ls = static_cast<Net*>(h)->layers();
+  return i >= 0 && i < (int)ls.size() && ls[i].use_database ? 1 : 0;
+}
 int b2h_net_reduce_buckets(void* h) { return static_cast<Net*>(h)->reduce_buckets(); }
 
 // SolverParameter from a solver.prototxt; returns an SGDSolver handle (same as b2h_solver_create)
@@ -446,6 +451,11 @@ int b2h_wire_state(void* hv, int* iter, int* current_step, char* learned_net, in
             snprintf(net_name, nlen, "%s", h->net.name.c_str()); });
 }
 
+// batches the database-backed Data layer has loaded so far; -1 when the net runs on the synthetic source
+long long b2h_trainer_database_batches(void* hv) {
+  DataLayer* d = static_cast<TrainerHandle*>(hv)->net->database_layer();
+  return d ? (long long)d->batches_loaded() : -1;
+}
 long long b2h_trainer_activation_floats(void* hv) { return (long long)static_cast<TrainerHandle*>(hv)->net->activation_floats(); }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // data_reader.cpp -- see data_reader.hpp.
 #include "data_reader.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "b2caffe.hpp"
@@ -132,6 +133,28 @@ void DataReader::thread_entry(size_t t) {
     for (auto& q : full_) q->cv.notify_all();
     for (auto& q : free_) q->cv.notify_all();
   }
+}
+
+bool UseDatabase(const std::string& source, int backend) {
+  const char* e = std::getenv("B2C_DATA");
+  const std::string mode = e ? e : "auto";
+  if (mode == "synthetic" || source.empty()) return false;
+  const bool there = db::LMDB::Exists(source);
+  if (mode == "db") B2_CHECK(there, "Failed to open lmdb " + source + ": no data.mdb (B2C_DATA=db)");
+  if (!there) return false;
+  B2_CHECK(backend == 1, "Data layer source " + source + " exists but its backend is LEVELDB: only `backend: LMDB` is built");
+  return true;
+}
+
+void PeekDatumShape(const std::string& source, int* c, int* h, int* w) {
+  db::LMDB env;
+  env.Open(source, db::READ);
+  std::unique_ptr<db::LMDBCursor> cur(env.NewCursor());
+  B2_CHECK(cur->valid(), "database " + source + " is empty");
+  Datum d;
+  B2_CHECK(ParseDatum(cur->data(), cur->size(), &d), "Database cursor failed to parse Datum record");
+  B2_CHECK(d.channels > 0 && d.height > 0 && d.width > 0, "first datum of " + source + " has no shape (encoded datums are not built)");
+  *c = d.channels; *h = d.height; *w = d.width;
 }
 
 // ------------------------------------------------------------------------------------------------ TransformDraws

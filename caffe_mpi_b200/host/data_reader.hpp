@@ -91,6 +91,13 @@ class DataReader {
   std::string error_;
 };
 
+// Which source a Data layer reads.  B2C_DATA = "synthetic": never the database; "db": the database, a missing one is fatal (the
+// reference's behaviour, db_lmdb.cpp:19); unset / "auto": the database when <source>/data.mdb exists, else the synthetic source
+// (bench.py and the tests run the reference's prototxts on machines that do not hold ImageNet).
+bool UseDatabase(const std::string& source, int backend);
+// channels / height / width of the first datum (DataReader::sample())
+void PeekDatumShape(const std::string& source, int* c, int* h, int* w);
+
 // DataTransformer's random draws (src/caffe/data_transformer.cpp:127-137 Fill3Randoms, :187,219-226 their use, :729-749
 // InitRand / Rand): per datum  rand0 = Rand() + 1 if mirror;  rand1 = Rand() + 1, rand2 = Rand() + 1 if TRAIN and crop_size;
 // do_mirror = mirror && rand0 % 2;  h_off = rand1 % (H - crop + 1), w_off = rand2 % (W - crop + 1) in TRAIN, the centre

@@ -1,5 +1,6 @@
 // prototxt.cpp -- text-format protobuf reader + Net graph builder (see prototxt.hpp for the reference map).
 #include "prototxt.hpp"
+#include "data_reader.hpp"
 
 #include <cctype>
 #include <cmath>
@@ -239,8 +240,22 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
         L.transform_scale = (float)tp->num("scale", 1.0);
         for (auto* f : tp->all("mean_value")) if (!f->is_msg()) L.mean_value.push_back((float)std::atof(f->scalar.c_str()));
       }
-      const int sz = L.crop_size > 0 ? L.crop_size : default_size;
-      tops.push_back({L.batch_size, default_channels, sz, sz});
+      int dc = default_channels, dh = default_size, dw = default_size;
+      if (type == "Data" && dp) {
+        L.data_source = dp->str("source");
+        const std::string be = dp->str("backend", "LEVELDB");
+        L.data_backend = (be == "LMDB" || be == "1") ? 1 : 0;
+        L.parser_threads = (int)dp->integer("parser_threads", 0);
+        if (tp) { L.mean_file = tp->str("mean_file"); L.transform_random_seed = tp->integer("random_seed", -1); }
+        // DataLayerSetUp reads one datum to size the top blob (data_layer.cpp:176-183); so does this, when the database is there
+        L.use_database = UseDatabase(L.data_source, L.data_backend);
+        if (L.use_database) PeekDatumShape(L.data_source, &dc, &dh, &dw);
+      }
+      if (L.crop_size > 0) {
+        if (L.use_database) B2_CHECK(dh >= L.crop_size && dw >= L.crop_size, "crop_size larger than the datums of " + L.data_source);
+        dh = dw = L.crop_size;
+      }
+      tops.push_back({L.batch_size, dc, dh, dw});
       tops.push_back({L.batch_size});
     } else if (type == "Input" || type == "DummyData") {
       is_data = true;

@@ -66,6 +66,12 @@ struct NetLayer {                       // one LayerParameter after phase filter
   bool has_transform = false, mirror = false;   // TransformationParameter (caffe.proto:436-470)
   float transform_scale = 1.f;
   std::vector<float> mean_value;
+  // DataParameter / TransformationParameter fields the database-backed DataLayer reads (caffe.proto:436-470, 806-849)
+  std::string data_source, mean_file;
+  int data_backend = 0;                 // DataParameter.DB: LEVELDB = 0 (the proto's default), LMDB = 1
+  int parser_threads = 0;               // 0 = automatic in the reference; one parser thread here
+  long long transform_random_seed = -1; // TransformationParameter.random_seed
+  bool use_database = false;            // the source opened: this layer reads it (else the synthetic in-memory source stands in)
   std::vector<int> input_shape;         // Input / DummyData layers
 };
 

@@ -406,7 +406,14 @@ TrainNet::TrainNet(const Net& net, const SolverParameter& sp, int num_classes, u
       node.top.push_back(sp_.get());
     }
     shared_ptr<LayerBase> layer;
-    if (type == "Data" || type == "Input" || type == "DummyData" || type == "ImageData") {
+    if (type == "Data" && L.use_database) {
+      // data_param.source opened: the layer reads it (parser threads -> pinned batch -> device transform), data_layer.hpp
+      B2_CHECK(db_data_ == nullptr && data_ == nullptr, "TrainNet: one data source per net");
+      auto* d = new DataLayer(L, seed);
+      layer.reset(d);
+      db_data_ = d;
+      db_data_node_ = (int)layers_.size();
+    } else if (type == "Data" || type == "Input" || type == "DummyData" || type == "ImageData") {
       vector<vector<int>> shapes;
       for (size_t t = 0; t < L.param.top.size(); ++t) shapes.push_back(net.top_shape((int)li, (int)t));
       SyntheticDataLayer::Transform tf;
@@ -600,6 +607,7 @@ TrainNet::~TrainNet() {}
 
 void TrainNet::AttachSync(P2PSync* sync) {
   sync_ = sync;
+  if (db_data_) db_data_->set_solver(sync->nranks(), sync->rank());     // each solver reads its own stripe of the database
   sync_->on_start(solver_->arena());
   filters_dirty_ = true;
   sched_.reset(new ReduceScheduler(solver_.get(), sync_));
@@ -627,7 +635,9 @@ void TrainNet::PrepareFilters() {
 }
 void TrainNet::Forward(bool copy_input) {
   if (filters_dirty_) PrepareFilters();
-  if (copy_input && data_) data_->LoadBatch(nodes_[0].top[0], S());     // H2D of the batch (+ the device transform of uint8 datums)
+  if (db_data_) {                                                        // database source: a new batch per e2e step; the first one always
+    if (copy_input || !db_data_->loaded()) db_data_->LoadBatch(nodes_[db_data_node_].top, S());
+  } else if (copy_input && data_) data_->LoadBatch(nodes_[0].top[0], S());     // H2D of the batch (+ the device transform of uint8 datums)
   EventProfiler* prof = Caffe::profiler();
   for (size_t i = 0; i < layers_.size(); ++i) {
     size_t h = 0;

@@ -7,6 +7,7 @@
 #pragma once
 #include "b2caffe.hpp"
 #include "prototxt.hpp"
+#include "data_layer.hpp"
 
 namespace caffe {
 
@@ -261,7 +262,8 @@ class TrainNet {
   const vector<shared_ptr<Blob>>& learnable_params() const { return learnable_; }   // Net::learnable_params(): every layer blob
   const vector<int>& trainable_ids() const { return trainable_ids_; }               // ids the layers differentiate
   size_t activation_floats() const;
-  size_t input_bytes() const { return data_ ? data_->h2d_bytes() : 0; }   // host -> device bytes of one e2e step's batch
+  size_t input_bytes() const { return db_data_ ? db_data_->h2d_bytes() : data_ ? data_->h2d_bytes() : 0; }   // host -> device bytes of one e2e step's batch
+  DataLayer* database_layer() { return db_data_; }   // non-null when the net's Data layer reads its LMDB (data_layer.hpp)
   // Solver::Snapshot (solver.cpp:447-520): <prefix>_iter_<N>.caffemodel (every layer's blobs, NVCaffe raw BlobProto) and
   // <prefix>_iter_<N>.solverstate (iter, learned_net, one history blob per learnable parameter, current_step).
   // Returns the .solverstate path.
@@ -303,6 +305,8 @@ class TrainNet {
   P2PSync* sync_ = nullptr;
   Blob* loss_blob_ = nullptr;
   SyntheticDataLayer* data_ = nullptr;
+  DataLayer* db_data_ = nullptr;                   // the LMDB-backed source, when data_param.source opened
+  int db_data_node_ = 0;
 };
 
 }  // namespace caffe

@@ -232,6 +232,12 @@ class Net:
     def reduce_buckets(self):
         return lib().b2h_net_reduce_buckets(self._h)
 
+    def uses_database(self, layer_index=0):
+        """True when that Data layer's data_param.source opened and the layer will read it (else: synthetic source)."""
+        L = lib()
+        L.b2h_net_layer_uses_database.argtypes = [C.c_void_p, C.c_int]
+        return bool(L.b2h_net_layer_uses_database(self._h, layer_index))
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.b2h_net_destroy(self._h)
@@ -379,6 +385,13 @@ class Trainer:
 
     def activation_floats(self):
         return lib().b2h_trainer_activation_floats(self._h)
+
+    def database_batches(self):
+        """Batches the LMDB-backed Data layer has loaded so far, or -1 when the net runs on the synthetic source."""
+        L = lib()
+        L.b2h_trainer_database_batches.argtypes = [C.c_void_p]
+        L.b2h_trainer_database_batches.restype = C.c_longlong
+        return L.b2h_trainer_database_batches(self._h)
 
     def arena_floats(self):
         """Elements of the contiguous parameter arena (= the buffer the gradient allreduce covers)."""

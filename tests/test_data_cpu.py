@@ -343,3 +343,32 @@ def test_transform_draws_follow_fill3randoms(mirror, crop, train):
             assert (h[i], w[i]) == (0, 0)
     with pytest.raises(data_api.DataError, match="crop_size larger"):
         data_api.transform_draws(1, True, 40, True, 1, 32, 48)
+
+
+# ------------------------------------------------------------------------------------------------------------ Net shape from the database
+def test_net_sizes_the_data_top_from_the_first_datum(tmp_path, monkeypatch):
+    """DataLayerSetUp reads one datum to shape top[0] (data_layer.cpp:176-183); the prototxt graph builder does the same when the
+    source opens, and falls back to the synthetic defaults when it does not."""
+    from caffe_mpi_b200 import host_api
+    path, imgs, labels = _datum_db(tmp_path, 12, c=1, h=28, w=30, name="mnist_like")
+    proto = ('name: "t" layer { name: "d" type: "Data" top: "data" top: "label" data_param { source: "%s" backend: LMDB batch_size: 4 } %s }\n'
+             'layer { name: "ip" type: "InnerProduct" bottom: "data" top: "ip" inner_product_param { num_output: 10 } }\n'
+             'layer { name: "loss" type: "SoftmaxWithLoss" bottom: "ip" bottom: "label" top: "loss" }\n')
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    net = host_api.Net(proto % (path, 'transform_param { scale: 0.00390625 }'), is_text=True)
+    assert net.uses_database(0) and net.layers()[0][2] == (4, 1, 28, 30)
+    net = host_api.Net(proto % (path, 'transform_param { crop_size: 24 mirror: true }'), is_text=True)
+    assert net.layers()[0][2] == (4, 1, 24, 24)
+    with pytest.raises(host_api.HostError, match="crop_size larger"):
+        host_api.Net(proto % (path, 'transform_param { crop_size: 29 }'), is_text=True)
+    # no database at the source: synthetic stand-in with the caller's defaults
+    net = host_api.Net(proto % (str(tmp_path / "absent"), 'transform_param { crop_size: 24 }'), is_text=True, default_channels=3)
+    assert not net.uses_database(0) and net.layers()[0][2] == (4, 3, 24, 24)
+    monkeypatch.setenv("B2C_DATA", "synthetic")
+    assert not host_api.Net(proto % (path, ""), is_text=True).uses_database(0)
+    monkeypatch.setenv("B2C_DATA", "db")
+    with pytest.raises(host_api.HostError, match="Failed to open lmdb"):
+        host_api.Net(proto % (str(tmp_path / "absent"), ""), is_text=True)
+    monkeypatch.delenv("B2C_DATA")
+    with pytest.raises(host_api.HostError, match="LEVELDB"):
+        host_api.Net(proto.replace("backend: LMDB ", "") % (path, ""), is_text=True)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Command-line shell in the shape of the reference's `caffe` tool (tools/caffe.cpp: train / time / device_query), over the
-C++ host layer -- SURVEY 8(f) rank 3.  Data layers are replaced by the synthetic in-memory source.
+C++ host layer -- SURVEY 8(f) rank 3.  A Data layer whose data_param.source holds an LMDB (backend: LMDB, raw uint8 datums) reads
+it through the parser threads / device transform of host/data_layer.cpp; when the source is not on disk the synthetic in-memory
+source stands in.  B2C_DATA=db makes a missing database fatal, as in the reference; B2C_DATA=synthetic ignores it.
 
   python tools/caffe.py train --solver=models/resnet50/solver.prototxt [--iterations=N] [--batch=B]     (1 GPU)
          [--snapshot=<solverstate to resume from>] [--weights=<caffemodel to fine-tune from>] [--snapshot_prefix=P]
@@ -66,6 +68,8 @@ def cmd_train(args):
         if rank == 0:
             log("Finetuning from %s (%d layers copied)" % (args.weights, n))
     iters = args.iterations or d["max_iter"]
+    if rank == 0:
+        log("Data layer: %s" % ("reading the LMDB named by data_param.source" if t.database_batches() >= 0 else "synthetic in-memory source"))
     if rank == 0:
         log("Solving %s: %d learnable blobs, lr_policy %s base_lr %g momentum %g weight_decay %g, %d iteration(s) on %d GPU(s)" %
             (net_path, t.num_params(), d["lr_policy"], d["base_lr"], d["momentum"], d["weight_decay"], iters, world))
