@@ -85,3 +85,41 @@ def test_two_ranks_equal_one_rank_full_batch(tmp_path):
         _, b, h_b = o.sgd_update(db, b, h_b, 0.9, 0.1, 0.0)
     assert np.allclose(r0["w"], w, rtol=1e-5, atol=1e-6)
     assert np.allclose(r0["b"], b, rtol=1e-5, atol=1e-6)
+
+
+# ---- input side: product code (C++ DataReader) under a real process group ---------------------------------------------------
+def _reader_worker(rank, world, port, db_path, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from caffe_mpi_b200 import data_api
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, steps = 3, 5
+    rd = data_api.DataReader(db_path, B, solver_count=dist.get_world_size(), solver_rank=dist.get_rank())
+    mine = np.stack([rd.next()[2].astype(np.int64) for _ in range(steps)])            # [steps][B] record ids
+    sums = np.stack([rd.next()[0].astype(np.int64).sum(axis=(1, 2, 3)) for _ in range(1)])
+    rd.close()
+    gathered = [torch.zeros(steps, B, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(mine))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "ids.npy"), torch.stack(gathered).numpy())       # [world][steps][B]
+    dist.destroy_process_group()
+    assert sums.shape == (1, B)
+
+
+def test_two_ranks_read_the_global_batch_one_rank_would(tmp_path):
+    """Data-parallel input: rank r of S reads records [r*B, (r+1)*B) of every S*B-record cycle
+    (data_reader.cpp:288-305), so the ranks' batches concatenated in rank order are exactly the batches one solver with
+    batch S*B reads -- the input-side half of "N solvers x batch/N == one solver x batch"."""
+    from caffe_mpi_b200 import data_api, lmdb_io
+    world, B, steps = 2, 3, 5
+    rng = np.random.default_rng(8)
+    db = str(tmp_path / "db")
+    lmdb_io.write_datum_lmdb(db, rng.integers(0, 256, (20, 1, 4, 4), dtype=np.uint8), rng.integers(0, 10, 20))
+    mp.spawn(_reader_worker, args=(world, _free_port(), db, str(tmp_path)), nprocs=world, join=True)
+    ids = np.load(tmp_path / "ids.npy")                                               # [world][steps][B]
+    one = data_api.DataReader(db, world * B)
+    for k in range(steps):
+        want = one.next()[2].astype(np.int64)
+        assert np.array_equal(np.concatenate([ids[r, k] for r in range(world)]), want)
+    one.close()
