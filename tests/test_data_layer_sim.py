@@ -1,0 +1,214 @@
+"""DataLayer's slot protocol without a GPU: the product class (caffe_mpi_b200/host/data_layer.cpp, compiled unchanged) runs on a
+stream-order model of the CUDA runtime (tests/sim/fake_cuda.cpp) in which every stream executes either as LATE or as EARLY as the
+program's own dependencies -- event waits and host synchronisations -- allow.  Under each combination of extremes for the compute
+stream and the copy stream the layer must still deliver, bit for bit, the batches the reference's pipeline would
+(CursorManager's records, Fill3Randoms' crops and flips, DataTransformer::Transform's arithmetic): a missing wait between the
+parser threads' pinned buffers, the host -> device copies and the transform shows up as a wrong batch.
+
+What this does NOT cover: the transform kernel itself (a host closure stands in for it here; the real one is checked bit-exactly
+on hardware by tests/test_layers_extra_gpu.py) and real PCIe / driver behaviour -- tests/test_zz_data_layer_gpu.py is the same
+comparison on a B200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from caffe_mpi_b200 import capi, data_api, lmdb_io
+from oracle import layers_oracle as lo
+from test_data_cpu import oracle_batches
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NET = ('name: "sim" layer {{ name: "data" type: "Data" top: "data" top: "label" data_param {{ source: "{src}" backend: LMDB batch_size: {B} {dp} }} '
+       'transform_param {{ {tp} }} }}')
+
+
+@pytest.fixture(scope="module")
+def sim():
+    capi.lib()                                              # libb2c.so must exist (the simulator links it for the host layer's other symbols)
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "sim")], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.fail("tests/sim does not build:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+    L = C.CDLL(os.path.join(HERE, "sim", "libdatasim.so"))
+    L.sim_last_error.restype = C.c_char_p
+    L.sim_create.restype = C.c_void_p
+    L.sim_create.argtypes = [C.c_char_p, C.c_ulonglong, C.c_int, C.c_int]
+    L.sim_destroy.argtypes = [C.c_void_p]
+    L.sim_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.sim_load_batch.argtypes = [C.c_void_p]
+    L.sim_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sim_batches.argtypes = [C.c_void_p]
+    L.sim_batches.restype = C.c_longlong
+    L.sim_transform_log.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
+    L.fakecuda_set_eager.argtypes = [C.c_void_p, C.c_int]
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_pending.restype = C.c_ulonglong
+    for fn, args in (("cudaMalloc", [C.POINTER(C.c_void_p), C.c_size_t]), ("cudaMallocHost", [C.POINTER(C.c_void_p), C.c_size_t]),
+                     ("cudaStreamCreateWithFlags", [C.POINTER(C.c_void_p), C.c_uint]), ("cudaEventCreateWithFlags", [C.POINTER(C.c_void_p), C.c_uint]),
+                     ("cudaMemcpyAsync", [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]), ("cudaStreamSynchronize", [C.c_void_p]),
+                     ("cudaEventRecord", [C.c_void_p, C.c_void_p]), ("cudaStreamWaitEvent", [C.c_void_p, C.c_void_p, C.c_uint]),
+                     ("cudaEventSynchronize", [C.c_void_p]), ("cudaDeviceSynchronize", [])):
+        getattr(L, fn).argtypes = args
+    return L
+
+
+# ---- the simulator itself: it must SEE the hazards it is there to catch ------------------------------------------------------------
+def _buf(L, n, host=False):
+    p = C.c_void_p()
+    assert (L.cudaMallocHost if host else L.cudaMalloc)(C.byref(p), n) == 0
+    return p
+
+
+def _stream(L):
+    s = C.c_void_p()
+    assert L.cudaStreamCreateWithFlags(C.byref(s), 1) == 0
+    return s
+
+
+def _event(L):
+    e = C.c_void_p()
+    assert L.cudaEventCreateWithFlags(C.byref(e), 2) == 0
+    return e
+
+
+def test_simulator_reads_a_pinned_source_when_the_copy_runs(sim):
+    L = sim
+    L.fakecuda_set_all_eager(0)
+    src, dst, s = _buf(L, 4, host=True), _buf(L, 4), _stream(L)
+    C.memmove(src, b"AAAA", 4)
+    L.cudaMemcpyAsync(dst, src, 4, 1, s)
+    C.memmove(src, b"BBBB", 4)                               # refilled before the copy was known to have completed
+    L.cudaStreamSynchronize(s)
+    assert C.string_at(dst, 4) == b"BBBB"                    # the hazard is visible: a lazy copy stream delivers the refill
+    C.memmove(src, b"CCCC", 4)
+    L.cudaMemcpyAsync(dst, src, 4, 1, s)
+    e = _event(L)
+    L.cudaEventRecord(e, s)
+    L.cudaEventSynchronize(e)                                # the fix: wait for the copy, then refill
+    C.memmove(src, b"DDDD", 4)
+    L.cudaDeviceSynchronize()
+    assert C.string_at(dst, 4) == b"CCCC"
+
+
+def test_simulator_orders_streams_only_through_events(sim):
+    L = sim
+    a, b, out = _buf(L, 4), _buf(L, 4), _buf(L, 4, host=True)
+    prod, cons = _stream(L), _stream(L)
+    C.memmove(a, b"old!", 4)
+    new = _buf(L, 4, host=True)
+    C.memmove(new, b"new!", 4)
+    # consumer forgets to wait for the producer: under a lazy producer it reads the stale buffer
+    L.fakecuda_set_all_eager(0)
+    L.cudaMemcpyAsync(a, new, 4, 1, prod)
+    L.cudaMemcpyAsync(out, a, 4, 2, cons)
+    L.cudaStreamSynchronize(cons)
+    assert C.string_at(out, 4) == b"old!"
+    L.cudaDeviceSynchronize()
+    # with the event in place the synchronise on the consumer drags the producer along
+    C.memmove(a, b"old!", 4)
+    e = _event(L)
+    L.cudaMemcpyAsync(a, new, 4, 1, prod)
+    L.cudaEventRecord(e, prod)
+    L.cudaStreamWaitEvent(cons, e, 0)
+    L.cudaMemcpyAsync(out, a, 4, 2, cons)
+    L.cudaStreamSynchronize(cons)
+    assert C.string_at(out, 4) == b"new!"
+    # producer forgets to wait for the previous consumer: under an eager producer the live buffer is overwritten
+    C.memmove(a, b"live", 4)
+    L.fakecuda_set_eager(prod, 1)
+    L.cudaMemcpyAsync(out, a, 4, 2, cons)                    # consumer of "live", still pending (lazy)
+    L.cudaMemcpyAsync(a, new, 4, 1, prod)                    # runs at once
+    L.cudaStreamSynchronize(cons)
+    assert C.string_at(out, 4) == b"new!"                    # the hazard is visible
+    # an event wait holds an eager stream back until its dependency has run
+    C.memmove(a, b"live", 4)
+    L.cudaMemcpyAsync(out, a, 4, 2, cons)
+    L.cudaEventRecord(e, cons)
+    L.cudaStreamWaitEvent(prod, e, 0)
+    L.cudaMemcpyAsync(a, new, 4, 1, prod)
+    assert C.string_at(a, 4) == b"live" and L.fakecuda_pending() > 0
+    L.cudaStreamSynchronize(prod)
+    assert C.string_at(out, 4) == b"live" and C.string_at(a, 4) == b"new!"
+    L.fakecuda_set_all_eager(0)
+
+
+# ---- DataLayer on the simulator -----------------------------------------------------------------------------------------------------
+def _db(tmp_path, n, c, h, w):
+    rng = np.random.default_rng(200 + n)
+    imgs = rng.integers(0, 256, (n, c, h, w), dtype=np.uint8)
+    labels = rng.integers(0, 10, n)
+    path = str(tmp_path / "lmdb")
+    lmdb_io.write_datum_lmdb(path, imgs, labels)
+    return path, imgs, labels
+
+
+MODES = {"all-lazy": (0, 0), "all-eager": (1, 1), "compute-lazy_copy-eager": (0, 1), "compute-eager_copy-lazy": (1, 0)}
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("P,S,rank", [(1, 1, 0), (2, 1, 0), (3, 2, 1)])
+def test_data_layer_delivers_reference_batches_under_extreme_stream_orders(sim, tmp_path, monkeypatch, mode, P, S, rank):
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim
+    n, Cc, H, W, B, crop, seed, steps = 47, 3, 11, 9, 4, 7, 31, 14
+    path, imgs, labels = _db(tmp_path, n, Cc, H, W)
+    mean = [104.0, 117.0, 123.0]
+    net = NET.format(src=path, B=B, dp="parser_threads: %d" % P,
+                     tp="crop_size: %d mirror: true scale: 0.25 random_seed: %d %s" % (crop, seed, " ".join("mean_value: %g" % m for m in mean)))
+    L.fakecuda_set_all_eager(0)
+    h = L.sim_create(net.encode(), 1701, S, rank)
+    assert h, L.sim_last_error().decode()
+    compute_eager, copy_eager = MODES[mode]
+    L.fakecuda_set_all_eager(copy_eager)                     # every stream but the legacy (compute) one is the layer's copy stream
+    L.fakecuda_set_eager(None, compute_eager)
+    shp = (C.c_int * 4)()
+    L.sim_shape(h, shp)
+    assert tuple(shp) == (B, Cc, crop, crop)
+    want_batches = oracle_batches(n, steps, B, S, rank, P)
+    ho, wo, mir = data_api.transform_draws(seed, True, crop, True, B * steps, H, W)
+    got, lab = np.empty((B, Cc, crop, crop), np.float32), np.empty(B, np.float32)
+    log = (C.c_ulonglong * 64)()
+    L.sim_transform_log(log, 64, 1)
+    for i in range(steps):
+        assert L.sim_load_batch(h) == 0, L.sim_last_error().decode()
+        if i % 7 != 6 and i != steps - 1:
+            continue                  # most batches are never read back: several LoadBatch calls in a row meet pending work, and every
+                                      # slot is reused while transforms that read it may still be queued (K = P + 1 <= 4 slots)
+        assert L.sim_read(h, got.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p)) == 0, L.sim_last_error().decode()
+        pos = [p for p, _ in want_batches[i]]
+        want = lo.transform_u8(imgs[pos], (crop, crop), ho[B * i:B * i + B], wo[B * i:B * i + B], mir[B * i:B * i + B], mean, None, 0.25)
+        assert np.array_equal(got, want), f"{mode}: batch {i}"
+        assert np.array_equal(lab, labels[pos].astype(np.float32)), f"{mode}: labels of batch {i}"
+        assert L.sim_batches(h) == i + 1
+    # every transform, read back or not, consumed the bytes of ITS batch (a device slot overwritten early shows up here)
+    assert L.sim_transform_log(log, 64, 1) == steps
+    assert [int(log[i]) for i in range(steps)] == [int(imgs[[p for p, _ in want_batches[i]]].astype(np.uint64).sum()) for i in range(steps)]
+    L.sim_destroy(h)
+    L.fakecuda_set_all_eager(0)
+
+
+def test_data_layer_mean_file_and_no_crop_on_the_simulator(sim, tmp_path, monkeypatch):
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim
+    path, imgs, labels = _db(tmp_path, 10, 1, 6, 5)
+    mean = np.random.default_rng(1).uniform(90, 130, (1, 1, 6, 5)).astype(np.float32)
+    mp = str(tmp_path / "mean.binaryproto")
+    data_api.blobproto_save(mp, mean)
+    h = L.sim_create(NET.format(src=path, B=4, dp="", tp='mean_file: "%s" scale: 0.00390625' % mp).encode(), 1, 1, 0)
+    assert h, L.sim_last_error().decode()
+    got, lab = np.empty((4, 1, 6, 5), np.float32), np.empty(4, np.float32)
+    want_batches = oracle_batches(10, 4, 4, 1, 0, 1)
+    zeros = np.zeros(4, np.int32)
+    for i in range(4):                                       # batch 2 wraps: records 8, 9, 0, 1
+        assert L.sim_load_batch(h) == 0 and L.sim_read(h, got.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p)) == 0
+        pos = [p for p, _ in want_batches[i]]
+        assert np.array_equal(got, lo.transform_u8(imgs[pos], (6, 5), zeros, zeros, zeros, None, mean[0], 0.00390625))
+        assert np.array_equal(lab, labels[pos].astype(np.float32))
+    L.sim_destroy(h)
+    # what the layer refuses at set-up (data_transformer.cpp:21-22, :198-200)
+    bad = L.sim_create(NET.format(src=path, B=4, dp="", tp='mean_file: "%s" mean_value: 1' % mp).encode(), 1, 1, 0)
+    assert not bad and "Cannot specify mean_file and mean_value at the same time" in L.sim_last_error().decode()
+    data_api.blobproto_save(mp, np.zeros((1, 1, 5, 5), np.float32))
+    bad = L.sim_create(NET.format(src=path, B=4, dp="", tp='mean_file: "%s"' % mp).encode(), 1, 1, 0)
+    assert not bad and "does not have the datums'" in L.sim_last_error().decode()
