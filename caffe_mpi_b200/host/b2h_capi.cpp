@@ -258,6 +258,17 @@ int b2h_solver_describe(void* hv, float* base_lr, float* momentum, float* weight
   return 0;
 }
 
+// first scalar value of a top-level field of a text-format message (tools/caffe.py reads SolverParameter.display / snapshot /
+// snapshot_prefix / snapshot_after_train / random_seed with it); returns 1 if present, 0 if absent, -1 on a parse error
+int b2h_textproto_scalar(const char* path_or_text, int is_text, const char* key, char* value, int cap) {
+  try {
+    PMessage m = is_text ? ParseTextProto(path_or_text) : ParseTextProtoFile(path_or_text);
+    for (const PField* f : m.all(key))
+      if (!f->is_msg()) { snprintf(value, cap, "%s", f->scalar.c_str()); return 1; }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // ---- TrainNet: the whole prototxt net + solver ------------------------------------------------------------------
 struct TrainerHandle {
   std::unique_ptr<Net> desc;

@@ -258,6 +258,17 @@ def solver_from_prototxt(path_or_text, is_text=False):
     return s, buf.value.decode()
 
 
+def textproto_scalar(path_or_text, key, default=None, is_text=False):
+    """First scalar value (as str) of a top-level field of a text-format protobuf file, or `default` when the field is absent."""
+    L = lib()
+    L.b2h_textproto_scalar.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(1024)
+    r = L.b2h_textproto_scalar(path_or_text.encode(), int(is_text), key.encode(), buf, 1024)
+    if r < 0:
+        raise HostError(L.b2h_last_error().decode())
+    return buf.value.decode() if r else default
+
+
 def solver_describe(s):
     L = lib()
     L.b2h_solver_describe.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 3 + [C.POINTER(C.c_int)] * 2 + [C.c_char_p, C.c_int]

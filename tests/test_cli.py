@@ -46,3 +46,33 @@ def test_no_cpu_mode(tmp_path):
     r = run("train", "--solver=%s" % s, "--iterations=1")
     assert r.returncode != 0 and "CUDA" in r.stderr                         # fails loudly, no CPU fallback
     assert run("device_query").returncode != 0
+
+
+def test_train_schedule_follows_display_and_snapshot_intervals():
+    """solver.cpp:289-345: a loss line every `display` iterations, a snapshot whenever iter % snapshot == 0 after a step; the chunks
+    between those points run without the host looking at the device."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("caffe_cli", os.path.join(ROOT, "tools", "caffe.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    plan = list(cli.schedule(0, 25, 10, 0))
+    assert plan == [(10, 10, True, False), (10, 20, True, False), (5, 25, True, False)]
+    plan = list(cli.schedule(0, 12, 5, 4))
+    assert plan == [(4, 4, False, True), (1, 5, True, False), (3, 8, False, True), (2, 10, True, False), (2, 12, True, True)]
+    assert list(cli.schedule(7, 20, 0, 0)) == [(13, 20, True, False)]                      # no display: one chunk, one closing line
+    assert list(cli.schedule(18, 31, 10, 10)) == [(2, 20, True, True), (10, 30, True, True), (1, 31, True, False)]   # a resumed run
+    assert list(cli.schedule(5, 5, 10, 10)) == []
+    assert sum(n for n, *_ in cli.schedule(3, 1003, 7, 11)) == 1000
+
+
+def test_textproto_scalar_reads_solver_fields(tmp_path):
+    from caffe_mpi_b200 import host_api
+    s = tmp_path / "solver.prototxt"
+    s.write_text('net: "a/b.prototxt"\ndisplay: 100  # comment\nsnapshot: 2500\nsnapshot_prefix: "models/x/snap"\nsnapshot_after_train: false\nrandom_seed: 1\n'
+                 'stepvalue: 10 stepvalue: 20 train_state { level: 3 }')
+    g = lambda k, d=None: host_api.textproto_scalar(str(s), k, d)
+    assert (g("display"), g("snapshot"), g("snapshot_prefix"), g("snapshot_after_train"), g("random_seed")) == ("100", "2500", "models/x/snap", "false", "1")
+    assert g("stepvalue") == "10" and g("test_interval", "0") == "0" and g("train_state") is None
+    assert host_api.textproto_scalar('display: 7', "display", is_text=True) == "7"
+    with pytest.raises(host_api.HostError):
+        host_api.textproto_scalar("display: {", "display", is_text=True)

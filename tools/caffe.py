@@ -31,6 +31,19 @@ def cmd_device_query(_):
     log("libb2c version %s, %d device(s)" % (v.decode() if isinstance(v, bytes) else v, n.value))
 
 
+def schedule(it, end, display, snapshot):
+    """The shell's part of Solver::Step (solver.cpp:277-345) as a plan: yields (n, iter_after, show, snap) -- run n iterations,
+    after which the iteration counter reads iter_after; print the loss line if `show` (iter % display == 0, or the run is over, or
+    display is off and this is the only chunk), write a snapshot if `snap` (iter % snapshot == 0)."""
+    while it < end:
+        nxt = end
+        for every in (display, snapshot):
+            if every > 0:
+                nxt = min(nxt, (it // every + 1) * every)
+        n, it = nxt - it, nxt
+        yield n, it, (display > 0 and it % display == 0) or it == end, snapshot > 0 and it % snapshot == 0
+
+
 def build_trainer(args, net, net_is_text, solver, solver_is_text):
     from caffe_mpi_b200 import host_api
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -58,6 +71,10 @@ def cmd_train(args):
     net_path = args.model or net_path
     if not os.path.exists(net_path):
         sys.exit("caffe.py train: net file %r named by the solver does not exist (paths are relative to the working directory)" % net_path)
+    if args.seed < 0:
+        args.seed = int(host_api.textproto_scalar(args.solver, "random_seed", "1701"))     # Solver::Init seeds Caffe with it (solver.cpp:63-65)
+        if args.seed < 0:
+            args.seed = 1701
     t, rank, world = build_trainer(args, net_path, False, args.solver, False)
     if args.snapshot:
         t.restore(args.snapshot)
@@ -68,20 +85,32 @@ def cmd_train(args):
         if rank == 0:
             log("Finetuning from %s (%d layers copied)" % (args.weights, n))
     iters = args.iterations or d["max_iter"]
+    # SolverParameter fields of the shell (caffe.proto:147-301); command-line flags win where both exist
+    sp = lambda key, default: host_api.textproto_scalar(args.solver, key, default)
+    display = args.display if args.display > 0 else int(sp("display", "0"))
+    snap_every = int(sp("snapshot", "0"))
+    snap_prefix = args.snapshot_prefix or sp("snapshot_prefix", "")
+    snap_after = sp("snapshot_after_train", "true").lower() in ("true", "1")
     if rank == 0:
         log("Data layer: %s" % ("reading the LMDB named by data_param.source" if t.database_batches() >= 0 else "synthetic in-memory source"))
-    if rank == 0:
         log("Solving %s: %d learnable blobs, lr_policy %s base_lr %g momentum %g weight_decay %g, %d iteration(s) on %d GPU(s)" %
             (net_path, t.num_params(), d["lr_policy"], d["base_lr"], d["momentum"], d["weight_decay"], iters, world))
-    done = 0
-    while done < iters:
-        n = min(args.display, iters - done)
+    try:
+        batch = len(t.get_blob("label"))           # images per rank and step, for the img/s figure
+    except host_api.HostError:
+        batch = 0
+    end = t.iter() + args.iterations if args.iterations else max(d["max_iter"], t.iter())   # a resumed run goes on to max_iter
+    last_snapshot = -1
+    for n, it, show, snap in schedule(t.iter(), end, display, snap_every):
         ms = t.timed_steps(n, copy_input=True)
-        done += n
-        if rank == 0:
-            log("Iteration %d (%.2f iter/s), loss = %.6g" % (done, n / (ms / 1e3), t.loss()))
-    if rank == 0 and args.snapshot_prefix:                    # Solver::Snapshot after the last iteration (solver.cpp:340-345)
-        log("Snapshotting solver state to binary proto file %s" % t.snapshot(args.snapshot_prefix))
+        assert t.iter() == it
+        if rank == 0 and show:
+            log("Iteration %d (%.2f iter/s%s), loss = %.6g" % (it, n / (ms / 1e3), ", %.1f img/s" % (batch * world * n / (ms / 1e3)) if batch else "", t.loss()))
+        if rank == 0 and snap and snap_prefix:
+            log("Snapshotting solver state to binary proto file %s" % t.snapshot(snap_prefix))
+            last_snapshot = it
+    if rank == 0 and snap_prefix and last_snapshot != t.iter() and (snap_after or args.snapshot_prefix):   # solver.cpp:340-345
+        log("Snapshotting solver state to binary proto file %s" % t.snapshot(snap_prefix))
     if rank == 0:
         log("Optimization Done.")
 
@@ -90,6 +119,8 @@ def cmd_time(args):
     from caffe_mpi_b200 import models
     if not args.model:
         sys.exit("caffe.py time: Need a model definition to time (--model=...)")
+    if args.seed < 0:
+        args.seed = 1701
     t, rank, world = build_trainer(args, args.model, False, models.RESNET50_SOLVER, True)
     t.step(3)
     t.sync()
@@ -106,8 +137,8 @@ def main():
     ap.add_argument("--iterations", "-iterations", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0, help="global batch size override (divided over the ranks like parallel.cpp:284-293)")
     ap.add_argument("--classes", type=int, default=1000)
-    ap.add_argument("--display", type=int, default=20)
-    ap.add_argument("--seed", type=int, default=1701)
+    ap.add_argument("--display", type=int, default=0, help="iterations between loss lines (default: the solver file's `display`)")
+    ap.add_argument("--seed", type=int, default=-1, help="default: the solver file's random_seed, else 1701")
     ap.add_argument("--snapshot", "-snapshot", default="", help="solver state (.solverstate) to resume training from")
     ap.add_argument("--weights", "-weights", default="", help="pretrained weights (.caffemodel) to fine-tune from")
     ap.add_argument("--snapshot_prefix", default="", help="write <prefix>_iter_<N>.caffemodel/.solverstate after the last iteration")
