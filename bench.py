@@ -244,6 +244,9 @@ def run_ours(args):
     net_text = models.PROTOTXT[model](N)
     if args.buckets > 0:
         net_text = f"reduce_buckets: {args.buckets}\n" + net_text
+    if args.lmdb:                                    # opt-in: the Data layer reads this database (host/data_layer.cpp) instead of the synthetic source
+        os.environ["B2C_DATA"] = "db"
+        net_text = net_text.replace('source: "synthetic"', 'source: "%s"' % args.lmdb)
     t = host_api.Trainer(net_text, models.SOLVERS[model], batch=N, seed=1701 + rank, math=math, **kw)   # seed + rank, parallel.cpp:179-187
     if world > 1:
         ids = [t.new_unique_id() if rank == 0 else None]
@@ -336,7 +339,7 @@ def run_ours(args):
         out = {
             "metric": metric_name(model), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32", "data": "lmdb of raw uint8 datums (--lmdb)" if args.lmdb else "synthetic",
             "config": {"workload": f"{model}: full train_val graph, {len(layers)} layers forward + backward through caffe::TrainNet (C++), "
                                    + (f"bucketed NCCL allreduce of the {t.arena_floats() * 4 / 1e6:.1f} MB diff arena through P2PSync / ReduceScheduler overlapped with backward, "
                                       if world > 1 else "") + f"fused SGD-momentum update of {t.num_learnable()} learnable blobs; N={N}/GPU",
@@ -442,6 +445,8 @@ def main():
                     help="fp32 = fp32-equivalent split-precision tensor-core math (the headline); tf32 = single-pass TF32 (informational)")
     ap.add_argument("--buckets", type=int, default=0,
                     help="NetParameter.reduce_buckets of the generated prototxt (0 = the reference's default, 6; caffe.proto:140)")
+    ap.add_argument("--lmdb", default="", help="train from this LMDB of raw uint8 Datums (tools/make_lmdb.py writes one) instead of the "
+                                               "synthetic in-memory source; e2e then includes the parser threads and the database read")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (N = 1 only)")
     args = ap.parse_args()
     if not args.batch:

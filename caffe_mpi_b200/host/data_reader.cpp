@@ -138,7 +138,7 @@ void DataReader::thread_entry(size_t t) {
 bool UseDatabase(const std::string& source, int backend) {
   const char* e = std::getenv("B2C_DATA");
   const std::string mode = e ? e : "auto";
-  if (mode == "synthetic" || source.empty()) return false;
+  if (mode == "synthetic" || source.empty() || source == "synthetic") return false;   // "synthetic": the name caffe_mpi_b200/models.py gives its stand-in source
   const bool there = db::LMDB::Exists(source);
   if (mode == "db") B2_CHECK(there, "Failed to open lmdb " + source + ": no data.mdb (B2C_DATA=db)");
   if (!there) return false;
