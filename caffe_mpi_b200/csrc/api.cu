@@ -6,6 +6,8 @@
 //   engine DEFAULT/CUDNN  -> whole-batch implicit GEMM (the cuDNN role): tcgen05 kernels
 //                            (conv_tc.cu) when the shape qualifies, else the SIMT direct kernels.
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "b2c_common.cuh"
@@ -108,6 +110,21 @@ static const void* prepared_filter(const b2c_conv_desc* d, int op) {
 // true when `op` would take the staged kernel (so the cache holds the bf16 layout) but this call falls back to the gather
 // kernel because of unaligned activation pointers: the cache is then of no use to it
 static bool staged_geometry_only(const b2c_conv_desc* d, int op) { return use_staged(d, op); }
+
+// A layer of the implicit engine that no tensor-core kernel takes (K = C/g*kh*kw beyond the filter tile limit, a strided k > 1 data
+// gradient, ...) runs on the FFMA kernels: correct, an order of magnitude slower.  Say so instead of doing it silently -- the
+// first few times per process, on stderr; b2c_conv_algo_used() is the programmatic form.  B2C_QUIET=1 turns the notes off.
+static void note_simt_fallback(const b2c_conv_desc* d, int op) {
+  if (d->algo == B2C_ALGO_SIMT) return;                       // the caller asked for these kernels
+  static std::atomic<int> notes{0};
+  static const bool quiet = [] { const char* e = getenv("B2C_QUIET"); return e && *e && *e != '0'; }();
+  if (quiet || notes.fetch_add(1) >= 4) return;
+  const ConvShape& s = d->s;
+  static const char* const names[] = {"forward", "data gradient", "weight gradient"};   // b2c_conv_op order
+  fprintf(stderr, "b2c: note: convolution C=%d %dx%d -> O=%d k=%dx%d s=%dx%d p=%dx%d g=%d, %s: no tensor-core kernel takes this shape, "
+                  "using the FFMA kernels\n", s.C, s.H, s.W, s.O, s.kh, s.kw, s.sh, s.sw, s.ph, s.pw, s.G,
+          op >= 0 && op < 3 ? names[op] : "?");
+}
 
 static int resolve_algo(const b2c_conv_desc* d, int op) {
   if (d->engine == B2C_ENGINE_CAFFE) return B2C_ALGO_SIMT;  // reported family of the explicit path's GEMM
@@ -233,6 +250,7 @@ extern "C" int b2c_conv_forward(const b2c_conv_desc* d, const float* x, const fl
     return launch_conv_tc_stg(s, B2C_OP_FORWARD, x, w, bias, y, ws, ws_bytes, prepared_filter(d, B2C_OP_FORWARD), false, st);
   if (tc_conv_supported(s, B2C_OP_FORWARD) && d->algo != B2C_ALGO_SIMT)
     return launch_conv_tc(s, B2C_OP_FORWARD, gather_math(d), x, w, bias, y, ws, ws_bytes, staged_geometry_only(d, B2C_OP_FORWARD) ? nullptr : prepared_filter(d, B2C_OP_FORWARD), st);
+  note_simt_fallback(d, B2C_OP_FORWARD);
   return launch_conv_fwd_simt(s, x, w, bias, y, st);
 }
 
@@ -262,6 +280,7 @@ extern "C" int b2c_conv_backward_data(const b2c_conv_desc* d, const float* dy, c
     return launch_conv_tc_stg(s, B2C_OP_BACKWARD_DATA, dy, w, nullptr, dx, ws, ws_bytes, prepared_filter(d, B2C_OP_BACKWARD_DATA), false, st);
   if (tc_conv_supported(s, B2C_OP_BACKWARD_DATA) && d->algo != B2C_ALGO_SIMT)
     return launch_conv_tc(s, B2C_OP_BACKWARD_DATA, gather_math(d), dy, w, nullptr, dx, ws, ws_bytes, staged_geometry_only(d, B2C_OP_BACKWARD_DATA) ? nullptr : prepared_filter(d, B2C_OP_BACKWARD_DATA), st);
+  note_simt_fallback(d, B2C_OP_BACKWARD_DATA);
   return launch_conv_dgrad_simt(s, dy, w, dx, st);
 }
 
@@ -310,6 +329,7 @@ extern "C" int b2c_conv_backward_filter(const b2c_conv_desc* d, const float* x, 
     return launch_conv_tc_wgrad_stg(s, x, dy, dw, ws, ws_bytes, st);
   if (tc_conv_supported(s, B2C_OP_BACKWARD_FILTER) && d->algo != B2C_ALGO_SIMT)
     return launch_conv_tc(s, B2C_OP_BACKWARD_FILTER, gather_math(d), x, dy, nullptr, dw, ws, ws_bytes, nullptr, st);
+  note_simt_fallback(d, B2C_OP_BACKWARD_FILTER);
   return launch_conv_wgrad_simt(s, x, dy, dw, st);
 }
 
