@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 
+#include "../../include/b2h_data.h"
 #include "b2caffe.hpp"
 #include "data_reader.hpp"
 #include "lmdb_reader.hpp"

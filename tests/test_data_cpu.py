@@ -372,3 +372,14 @@ def test_net_sizes_the_data_top_from_the_first_datum(tmp_path, monkeypatch):
     monkeypatch.delenv("B2C_DATA")
     with pytest.raises(host_api.HostError, match="LEVELDB"):
         host_api.Net(proto.replace("backend: LMDB ", "") % (path, ""), is_text=True)
+
+
+def test_library_exports_every_symbol_b2h_data_h_declares():
+    import re
+    from caffe_mpi_b200 import host_api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "b2h_data.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(b2h_[a-z0-9_]+)\s*\(", txt)))
+    assert len(syms) == 19
+    L = host_api.lib()
+    assert not [s for s in syms if not hasattr(L, s)]
