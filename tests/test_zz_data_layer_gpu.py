@@ -13,7 +13,7 @@ from caffe_mpi_b200 import data_api, host_api, lmdb_io
 from oracle import layers_oracle as lo
 from test_data_cpu import oracle_batches
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]     # a protocol bug must fail, not hang the box
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]     # a protocol bug must end the run, not hang the box (the file sorts last)
 SOLVER = 'base_lr: 0.01 lr_policy: "fixed" momentum: 0.9 weight_decay: 0.0005 max_iter: 100 solver_mode: GPU'
 # crops and datum sizes below keep InnerProduct's K odd, i.e. on the exact-fp32 GEMM: this file is about the data layer
 NET = ('name: "db_net"\n'
