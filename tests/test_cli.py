@@ -76,3 +76,21 @@ def test_textproto_scalar_reads_solver_fields(tmp_path):
     assert host_api.textproto_scalar('display: 7', "display", is_text=True) == "7"
     with pytest.raises(host_api.HostError):
         host_api.textproto_scalar("display: {", "display", is_text=True)
+
+
+def test_rank_batch_divides_the_prototxt_batch_like_p2psync(tmp_path):
+    """parallel.cpp:284-316: the Data layer's batch_size is per node; each of its solvers takes 1/solver_count, rounded up."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("caffe_cli2", os.path.join(ROOT, "tools", "caffe.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    net = ('layer { name: "d" type: "Data" top: "data" top: "label" data_param { source: "nowhere" backend: LMDB batch_size: 50 } transform_param { crop_size: 8 } }\n'
+           'layer { name: "ip" type: "InnerProduct" bottom: "data" top: "ip" inner_product_param { num_output: 4 } }\n'
+           'layer { name: "loss" type: "SoftmaxWithLoss" bottom: "ip" bottom: "label" top: "loss" }\n')
+    assert cli.rank_batch(net, True, 0, 1) == 0                 # one solver: the prototxt's own batch
+    assert cli.rank_batch(net, True, 0, 2) == 25
+    assert cli.rank_batch(net, True, 0, 8) == 7                 # 50 -> 56 -> 7 per solver
+    assert cli.rank_batch(net, True, 512, 8) == 64              # --batch is the node's batch as well
+    assert cli.rank_batch(net, True, 96, 1) == 96
+    inp = 'layer { name: "in" type: "Input" top: "data" input_param { shape { dim: 6 dim: 3 dim: 8 dim: 8 } } }\n'
+    assert cli.rank_batch(inp, True, 0, 4) == 0                 # no data_param: left alone

@@ -44,10 +44,27 @@ def schedule(it, end, display, snapshot):
         yield n, it, (display > 0 and it % display == 0) or it == end, snapshot > 0 and it % snapshot == 0
 
 
+def rank_batch(net, net_is_text, override, solver_count):
+    """Per-solver batch size, or 0 for "what the prototxt says".  P2PSync::divide_batch_size (parallel.cpp:284-316): with more than
+    one solver (GPU) on the node, the batch_size of the net's Data layer -- or the --batch override -- is the NODE's batch and each
+    solver takes total / solver_count of it, the total first rounded up to a multiple of solver_count.  Nets fed by Input /
+    DummyData layers have no data_param and are left alone, as in the reference."""
+    from caffe_mpi_b200 import host_api
+    if solver_count <= 1:
+        return override
+    total = override
+    if not total:
+        data = [l for l in host_api.Net(net, is_text=net_is_text).layers() if l[1] == "Data"]
+        if not data:
+            return 0
+        total = data[0][2][0]
+    return host_api.divide_batch_size(total, solver_count)
+
+
 def build_trainer(args, net, net_is_text, solver, solver_is_text):
     from caffe_mpi_b200 import host_api
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    batch = host_api.divide_batch_size(args.batch, world) if args.batch and world > 1 else args.batch
+    batch = rank_batch(net, net_is_text, args.batch, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     t = host_api.Trainer(net, solver, batch=batch or 0, num_classes=args.classes, seed=args.seed + rank, net_is_text=net_is_text,
                          solver_is_text=solver_is_text)
     if world > 1:                              # P2PSync: one solver per GPU, rank 0 is the root solver (parallel.cpp:26-60)
