@@ -212,3 +212,83 @@ def test_data_layer_mean_file_and_no_crop_on_the_simulator(sim, tmp_path, monkey
     data_api.blobproto_save(mp, np.zeros((1, 1, 5, 5), np.float32))
     bad = L.sim_create(NET.format(src=path, B=4, dp="", tp='mean_file: "%s"' % mp).encode(), 1, 1, 0)
     assert not bad and "does not have the datums'" in L.sim_last_error().decode()
+
+
+# ---- the reference's own DataLayer tests (src/caffe/test/test_data_layer.cpp), on the simulator ------------------------------------------
+def _fill(tmp_path, unique_pixels):
+    """DataLayerTest::Fill (test_data_layer.cpp:44-70): five 2x3x4 datums under the keys "0".."4", label = index; either every pixel
+    of an image is unique and all images equal, or every image is one constant."""
+    items = []
+    for i in range(5):
+        data = np.array([j if unique_pixels else i for j in range(24)], np.uint8).reshape(2, 3, 4)
+        items.append((str(i).encode(), lmdb_io.datum_bytes(data, i)))
+    path = str(tmp_path / ("db%d" % unique_pixels))
+    lmdb_io.write_lmdb(path, items)
+    return path
+
+
+def _layer(L, path, tp, seed=1701):
+    h = L.sim_create(NET.format(src=path, B=5, dp="parser_threads: 3", tp=tp).encode(), seed, 1, 0)
+    assert h, L.sim_last_error().decode()
+    shp = (C.c_int * 4)()
+    L.sim_shape(h, shp)
+    return h, tuple(shp)
+
+
+def _forward(L, h, shape):
+    data, label = np.empty(shape, np.float32), np.empty(shape[0], np.float32)
+    assert L.sim_load_batch(h) == 0 and L.sim_read(h, data.ctypes.data_as(C.c_void_p), label.ctypes.data_as(C.c_void_p)) == 0
+    return data, label
+
+
+def test_reference_TestReadLMDB(sim, tmp_path, monkeypatch):
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim
+    h, shape = _layer(L, _fill(tmp_path, False), "scale: 3")
+    assert shape == (5, 2, 3, 4)
+    for _ in range(100):                                      # test_data_layer.cpp:98-109
+        data, label = _forward(L, h, shape)
+        assert label.tolist() == [0, 1, 2, 3, 4]
+        assert np.array_equal(data, np.broadcast_to((3.0 * np.arange(5, dtype=np.float32)).reshape(5, 1, 1, 1), shape))
+    L.sim_destroy(h)
+
+
+def test_reference_TestReadCropTrainLMDB(sim, tmp_path, monkeypatch):
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim
+    h, shape = _layer(L, _fill(tmp_path, True), "scale: 3 crop_size: 1")
+    assert shape == (5, 2, 1, 1)
+    for _ in range(2):                                        # test_data_layer.cpp:204-227, TRAIN branch
+        data, label = _forward(L, h, shape)
+        assert label.tolist() == [0, 1, 2, 3, 4]
+        centre = np.array([3.0 * 5, 3.0 * 17], np.float32)
+        assert int((data.reshape(5, 2) == centre).sum()) < 10   # not the centre crop all ten times
+        # every value is 3 x a pixel of its own channel (channel 0 holds 0..11, channel 1 holds 12..23)
+        px = data.reshape(5, 2) / 3
+        assert ((px[:, 0] >= 0) & (px[:, 0] < 12) & (px[:, 1] >= 12) & (px[:, 1] < 24)).all()
+    L.sim_destroy(h)
+
+
+def _crop_sequence(L, path, seed, tp="crop_size: 1 mirror: true"):
+    h, shape = _layer(L, path, tp, seed=seed)
+    seq = []
+    for _ in range(2):
+        data, label = _forward(L, h, shape)
+        assert label.tolist() == [0, 1, 2, 3, 4]
+        seq.append(data.reshape(-1).copy())
+    L.sim_destroy(h)
+    return np.concatenate(seq)
+
+
+def test_reference_TestReadCropTrainSequenceSeeded_and_Unseeded(sim, tmp_path, monkeypatch):
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim
+    path = _fill(tmp_path, True)
+    first = _crop_sequence(L, path, 1701)
+    assert np.array_equal(_crop_sequence(L, path, 1701), first)          # same seed, same crops and flips (:256-286)
+    other = _crop_sequence(L, path, 1702)                                # a solver that went on drawing: another stream (:328-352)
+    assert int((other == first).sum()) < 20
+    # transform_param.random_seed pins the stream whatever the solver's seed is (data_transformer.cpp:733-736)
+    a = _crop_sequence(L, path, 1, tp="crop_size: 1 mirror: true random_seed: 9")
+    b = _crop_sequence(L, path, 2, tp="crop_size: 1 mirror: true random_seed: 9")
+    assert np.array_equal(a, b)
