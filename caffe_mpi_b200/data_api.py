@@ -22,6 +22,10 @@ def lib():
         L.b2h_lmdb_exists.argtypes = [C.c_char_p]
         L.b2h_lmdb_open.restype = vp
         L.b2h_lmdb_open.argtypes = [C.c_char_p]
+        L.b2h_lmdb_open_mode.restype = vp
+        L.b2h_lmdb_open_mode.argtypes = [C.c_char_p, i]
+        L.b2h_lmdb_put.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.b2h_lmdb_commit.argtypes = [vp]
         L.b2h_lmdb_close.argtypes = [vp]
         L.b2h_lmdb_stat.argtypes = [vp, C.POINTER(ll), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
         for fn in ("b2h_lmdb_seek_to_first", "b2h_lmdb_next", "b2h_lmdb_valid"):
@@ -54,11 +58,19 @@ def lmdb_exists(source):
 
 
 class LMDB:
-    """caffe::db::LMDB opened READ plus one LMDBCursor on it."""
+    """caffe::db::LMDB (mode "READ", "WRITE" or "NEW") plus one LMDBCursor and one pending LMDBTransaction on it."""
 
-    def __init__(self, source):
-        self._h = lib().b2h_lmdb_open(source.encode())
+    def __init__(self, source, mode="READ"):
+        self._h = lib().b2h_lmdb_open_mode(source.encode(), {"READ": 0, "WRITE": 1, "NEW": 2}[mode])
         if not self._h:
+            raise _err()
+
+    def put(self, key, value):
+        if lib().b2h_lmdb_put(self._h, key, len(key), value, len(value)) != 0:
+            raise _err()
+
+    def commit(self):
+        if lib().b2h_lmdb_commit(self._h) != 0:
             raise _err()
 
     def stat(self):

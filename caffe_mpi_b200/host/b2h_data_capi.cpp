@@ -21,6 +21,7 @@ static thread_local std::string g_derr;
 struct LmdbHandle {
   db::LMDB env;
   std::unique_ptr<db::LMDBCursor> cur;
+  std::unique_ptr<db::LMDBTransaction> txn;
 };
 struct ReaderHandle {
   std::unique_ptr<DataReader> reader;
@@ -42,6 +43,34 @@ void* b2h_lmdb_open(const char* source) {
     h->cur.reset(h->env.NewCursor());
     return h.release();
   } catch (const std::exception& e) { g_derr = e.what(); return nullptr; }
+}
+// mode: 0 READ, 1 WRITE, 2 NEW (db::Mode)
+void* b2h_lmdb_open_mode(const char* source, int mode) {
+  try {
+    std::unique_ptr<LmdbHandle> h(new LmdbHandle);
+    h->env.Open(source, mode == 2 ? db::NEW : mode == 1 ? db::WRITE : db::READ);
+    h->cur.reset(h->env.NewCursor());
+    return h.release();
+  } catch (const std::exception& e) { g_derr = e.what(); return nullptr; }
+}
+// Transaction::Put on the handle's pending transaction (db_lmdb.cpp:52-55)
+int b2h_lmdb_put(void* hv, const void* key, size_t key_size, const void* value, size_t value_size) {
+  auto* h = static_cast<LmdbHandle*>(hv);
+  B2D_TRY({
+    if (!h->txn) h->txn.reset(h->env.NewTransaction());
+    h->txn->Put(std::string(static_cast<const char*>(key), key_size), std::string(static_cast<const char*>(value), value_size));
+  });
+}
+// Transaction::Commit (db_lmdb.cpp:57-96); the handle's cursor is re-created on the committed state, at the first record
+int b2h_lmdb_commit(void* hv) {
+  auto* h = static_cast<LmdbHandle*>(hv);
+  B2D_TRY({
+    if (!h->txn) h->txn.reset(h->env.NewTransaction());
+    h->cur.reset();
+    h->txn->Commit();
+    h->txn.reset();
+    h->cur.reset(h->env.NewCursor());
+  });
 }
 void b2h_lmdb_close(void* hv) { delete static_cast<LmdbHandle*>(hv); }
 int b2h_lmdb_stat(void* hv, long long* entries, unsigned* page_size, unsigned* depth, unsigned long long* txnid) {

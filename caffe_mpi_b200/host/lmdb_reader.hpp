@@ -1,8 +1,9 @@
-// lmdb_reader.hpp -- read-only LMDB environment + cursor (storage half of the input pipeline).
+// lmdb_reader.hpp -- LMDB environment, cursor and transaction (storage half of the input pipeline).
 //
-// Mirrors caffe::db::LMDB / LMDBCursor (reference include/caffe/util/db.hpp:12-52, db_lmdb.hpp:27-106,
-// src/caffe/util/db_lmdb.cpp:10-46) for Mode READ: Open(source, READ), NewCursor(), cursor SeekToFirst / Next / valid /
-// key / value / data / size.  There is no liblmdb in the toolchain, so the on-disk format is read directly:
+// Mirrors caffe::db::LMDB / LMDBCursor / LMDBTransaction (reference include/caffe/util/db.hpp:12-52, db_lmdb.hpp:27-106,
+// src/caffe/util/db_lmdb.cpp): Open(source, READ | WRITE | NEW), NewCursor(), cursor SeekToFirst / Next / valid / key / value /
+// data / size, NewTransaction(), Put, Commit.  There is no liblmdb in the toolchain, so the on-disk format is read and written
+// directly:
 //
 //   data.mdb = array of pages of `psize` bytes (psize = meta.mm_dbs[FREE_DBI].md_pad, 4096 by default).
 //   page header, 16 bytes:  pgno u64 | pad u16 | flags u16 | lower u16, upper u16  (overflow pages: pages u32 instead)
@@ -19,7 +20,16 @@
 //
 // The whole file is mmap'ed PROT_READ / MAP_SHARED, like mdb_env_open(MDB_RDONLY | MDB_NOLOCK) does; values are returned as
 // pointers into the mapping (zero copy), so a parser thread moves a datum's bytes once: page cache -> pinned batch buffer.
-// Not built: named sub-databases, DUPSORT, write transactions, the lock file (Caffe opens with MDB_NOLOCK).
+//
+// Writing (Mode NEW / WRITE; what convert_imageset and the reference's tests do through db::Transaction) is a bulk builder, not
+// LMDB's copy-on-write engine: a Commit whose keys all sort after the database's last key -- convert_imageset's "%08d_name" keys,
+// committed every 1 000 records -- APPENDS: values go to overflow runs and packed leaf pages as they come, only (first key, page)
+// per leaf stays in memory, and each Commit writes fresh branch pages plus the meta page of its transaction (meta page txnid & 1;
+// the previous transaction's tree stays intact, its branch pages become unreferenced: ~0.3 % of an ImageNet database at 1 000
+// records per commit).  Any other Commit (a key that sorts earlier, an overwrite, WRITE on a database this object did not build)
+// merges everything in memory and rewrites the file (data.mdb.tmp, then rename): fine for the small databases tests and tools
+// make, not for bulk loads in random key order.  One writer, no concurrent readers, no free-list reuse.
+// Not built: named sub-databases, DUPSORT, mdb_del, the lock file (Caffe opens readers with MDB_NOLOCK).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -57,17 +67,29 @@ class LMDBCursor {
   bool valid_ = false;
 };
 
+class LMDBTransaction {
+ public:
+  explicit LMDBTransaction(LMDB* env) : env_(env) {}
+  void Put(const std::string& key, const std::string& value) { keys_.push_back(key); values_.push_back(value); }   // db_lmdb.cpp:52-55
+  void Commit();                                                                                                     // db_lmdb.cpp:57-96
+ private:
+  LMDB* env_;
+  std::vector<std::string> keys_, values_;
+};
+
 class LMDB {
  public:
-  LMDB() = default;
-  ~LMDB() { Close(); }
+  LMDB();
+  ~LMDB();
   LMDB(const LMDB&) = delete;
   LMDB& operator=(const LMDB&) = delete;
-  // `source` is the environment directory (holding data.mdb) or the data file itself.  Only READ is built; anything else,
-  // a missing / truncated file or a foreign format is fatal (caffe::FatalError), like MDB_CHECK in the reference.
+  // `source` is the environment directory (holding data.mdb) or, for READ, the data file itself.  NEW creates the directory
+  // (mkdir must succeed, db_lmdb.cpp:12-14); WRITE opens an existing environment or creates an empty one in an existing directory.
+  // A missing / truncated file or a foreign format is fatal (caffe::FatalError), like MDB_CHECK in the reference.
   void Open(const std::string& source, Mode mode = READ);
   void Close();
-  LMDBCursor* NewCursor() const { return new LMDBCursor(this); }
+  LMDBCursor* NewCursor();
+  LMDBTransaction* NewTransaction();
   size_t entries() const { return entries_; }          // MDB_stat.ms_entries of the main database
   unsigned page_size() const { return psize_; }
   unsigned depth() const { return depth_; }
@@ -76,7 +98,16 @@ class LMDB {
 
  private:
   friend class LMDBCursor;
+  friend class LMDBTransaction;
+  struct Writer;                                       // bulk builder state (lmdb_reader.cpp)
+  void Map(const std::string& file);                   // mmap + meta selection
+  void Unmap();
+  void Commit(std::vector<std::string>& keys, std::vector<std::string>& values);
   const uint8_t* page(uint64_t pgno) const;            // bounds-checked
+  std::string file_;
+  Mode mode_ = READ;
+  std::unique_ptr<Writer> w_;
+  bool stale_ = false;                                 // the file changed since it was mapped
   const uint8_t* map_ = nullptr;
   size_t map_bytes_ = 0;
   unsigned psize_ = 0, depth_ = 0;

@@ -15,12 +15,17 @@ extern "C" {
 
 const char* b2h_data_last_error(void);
 
-/* ---- db::LMDB / db::LMDBCursor, Mode READ (include/caffe/util/db_lmdb.hpp:27-106, src/caffe/util/db_lmdb.cpp:10-46) ------------
+/* ---- db::LMDB / LMDBCursor / LMDBTransaction (include/caffe/util/db_lmdb.hpp:27-106, src/caffe/util/db_lmdb.cpp) --------------------
  * `source` is the environment directory (holding data.mdb) or the data file itself.  The handle owns the environment (an mmap of
  * the file, as mdb_env_open(MDB_RDONLY | MDB_NOLOCK) makes) and one cursor, positioned on the first record like LMDBCursor's
  * constructor leaves it. */
 int b2h_lmdb_exists(const char* source);                       /* data.mdb present?  (what B2C_DATA=auto tests) */
 void* b2h_lmdb_open(const char* source);                       /* LMDB::Open(source, READ) + NewCursor() */
+void* b2h_lmdb_open_mode(const char* source, int mode);        /* LMDB::Open(source, mode): 0 READ, 1 WRITE, 2 NEW (mkdir must succeed) */
+/* LMDBTransaction::Put / Commit (src/caffe/util/db_lmdb.cpp:52-96) on the handle's pending transaction.  A commit whose keys all sort
+ * after the database's last key appends (convert_imageset's pattern); any other rewrites the file -- see host/lmdb_reader.hpp. */
+int b2h_lmdb_put(void* env, const void* key, size_t key_size, const void* value, size_t value_size);
+int b2h_lmdb_commit(void* env);
 void b2h_lmdb_close(void* env);                                /* LMDB::Close() */
 int b2h_lmdb_stat(void* env, long long* entries, unsigned* page_size, unsigned* depth, unsigned long long* txnid);   /* mdb_env_stat */
 int b2h_lmdb_seek_to_first(void* env);                         /* LMDBCursor::SeekToFirst(); returns valid() as 1 / 0, -1 on error */

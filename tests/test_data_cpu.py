@@ -380,6 +380,99 @@ def test_library_exports_every_symbol_b2h_data_h_declares():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "b2h_data.h")).read(), flags=re.S)
     syms = sorted(set(re.findall(r"\b(b2h_[a-z0-9_]+)\s*\(", txt)))
-    assert len(syms) == 19
+    assert len(syms) == 22
     L = host_api.lib()
     assert not [s for s in syms if not hasattr(L, s)]
+
+
+# ------------------------------------------------------------------------------------------------------------ db::LMDB NEW / WRITE
+def test_writer_appends_like_convert_imageset(tmp_path):
+    """tools/convert_imageset.cpp: Open(NEW), Put under "%08d_name" keys, Commit every 1 000 records (here: every 37) and once at
+    the end.  Every commit is a readable database; the C++ cursor and the independent Python reader agree with what was put."""
+    path = str(tmp_path / "new_db")
+    items = _items(400, [0, 5, 300, 2014, 2017, 2030, 9000, 70000], seed=21)      # inline, around nodemax, overflow runs
+    env = data_api.LMDB(path, "NEW")
+    assert env.stat()["entries"] == 0 and not env.valid()
+    done = 0
+    for i, (k, v) in enumerate(items):
+        env.put(k, v)
+        if (i + 1) % 37 == 0 or i + 1 == len(items):
+            env.commit()
+            done = i + 1
+            st = env.stat()
+            assert st["entries"] == done and st["txnid"] == (i // 37) + 1
+            if (i + 1) % 111 == 0:
+                assert lmdb_io.read_lmdb(path) == items[:done]                     # the Python reader on a mid-way state
+                assert data_api.LMDB(path).items() == items[:done]
+    assert env.items() == items and lmdb_io.read_lmdb(path) == items
+    assert env.stat()["depth"] >= 2
+    env.close()
+    with pytest.raises(data_api.DataError, match="mkdir .* failed"):
+        data_api.LMDB(path, "NEW")                                                 # db_lmdb.cpp:12-14: the directory must not exist
+    rd = data_api.LMDB(path)
+    with pytest.raises(data_api.DataError, match="READ"):
+        rd.put(b"k", b"v")
+
+
+def test_writer_merges_unordered_and_overwriting_commits(tmp_path):
+    """test_db.cpp TestWrite: Open(WRITE) on an existing database and Put keys it already holds; plus keys that sort before the last
+    one, empty commits, a database written by someone else (the Python writer) and reopening."""
+    path = str(tmp_path / "db")
+    base = {lmdb_io.caffe_key(i): bytes([i]) * (i * 40) for i in range(30)}
+    lmdb_io.write_lmdb(path, base.items(), txnid=5)
+    env = data_api.LMDB(path, "WRITE")
+    assert env.stat()["entries"] == 30
+    env.put(lmdb_io.caffe_key(3), b"replaced")                  # overwrite
+    env.put(b"0000000", b"sorts first")                         # before every existing key
+    env.put(b"zz", b"sorts last")
+    env.put(b"zz", b"put twice: the last value stays")
+    env.commit()
+    want = dict(base)
+    want[lmdb_io.caffe_key(3)] = b"replaced"
+    want[b"0000000"] = b"sorts first"
+    want[b"zz"] = b"put twice: the last value stays"
+    assert env.stat()["entries"] == 32 and env.stat()["txnid"] == 6
+    assert env.items() == sorted(want.items()) == lmdb_io.read_lmdb(path)
+    env.commit()                                                 # an empty transaction is still a transaction
+    assert env.stat()["txnid"] == 7 and env.items() == sorted(want.items())
+    env.put(b"zzz", b"x" * 5000)                                 # after the rebuild, ascending keys append again
+    env.commit()
+    want[b"zzz"] = b"x" * 5000
+    assert env.items() == sorted(want.items()) == lmdb_io.read_lmdb(path)
+    env.close()
+    env = data_api.LMDB(path, "WRITE")                           # reopen: this object does not know the leaf index -> merge path
+    env.put(b"zzzz", b"tail")
+    env.commit()
+    want[b"zzzz"] = b"tail"
+    assert env.items() == sorted(want.items()) == lmdb_io.read_lmdb(path)
+    assert not os.path.exists(os.path.join(path, "data.mdb.tmp"))
+    with pytest.raises(data_api.DataError, match="BAD_VALSIZE"):
+        env.put(b"", b"empty key")
+        env.commit()
+    # WRITE in an existing, empty directory creates the environment
+    empty = tmp_path / "fresh"
+    empty.mkdir()
+    e2 = data_api.LMDB(str(empty), "WRITE")
+    e2.put(b"a", b"1")
+    e2.commit()
+    assert data_api.LMDB(str(empty)).items() == [(b"a", b"1")]
+
+
+def test_reader_trains_from_a_database_the_cpp_writer_made(tmp_path):
+    """Datums serialised and written by the C++ side, read back by DataReader: the whole storage path without Python's writer."""
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (12, 3, 5, 4), dtype=np.uint8)
+    labels = rng.integers(0, 9, 12)
+    path = str(tmp_path / "cpp_db")
+    env = data_api.LMDB(path, "NEW")
+    for i in range(12):
+        env.put(lmdb_io.caffe_key(i, "img%d" % i), data_api.datum_serialize(3, 5, 4, imgs[i].tobytes(), int(labels[i])))
+        if i % 5 == 4:
+            env.commit()
+    env.commit()
+    env.close()
+    rd = data_api.DataReader(path, 4)
+    for k in range(3):
+        data, label, ids, _ = rd.next()
+        assert np.array_equal(data, imgs[4 * k:4 * k + 4]) and np.array_equal(label, labels[4 * k:4 * k + 4].astype(np.float32))
+    rd.close()

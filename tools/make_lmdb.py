@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Write an LMDB of Caffe Datums without liblmdb (caffe_mpi_b200/lmdb_io.py) -- the stand-in for the reference's
+"""Write an LMDB of Caffe Datums without liblmdb (the C++ db::LMDB writer of host/lmdb_reader.cpp) -- the stand-in for the reference's
 `convert_imageset` (tools/convert_imageset.cpp) on a machine with neither LMDB nor OpenCV.
 
   python tools/make_lmdb.py OUT_DIR --random N --shape 3x256x256 [--classes 1000] [--seed 0]     synthetic uint8 images
@@ -40,10 +40,21 @@ def main():
         labels = rng.integers(0, a.classes, a.random)
     else:
         sys.exit("make_lmdb: give --random N or --npz FILE")
-    pages = lmdb_io.write_datum_lmdb(a.out, imgs, labels)
-    print("wrote %d datums of %s to %s (%d pages, %.1f MB)" % (len(labels), "x".join(map(str, imgs.shape[1:])), a.out, pages, pages * 4096 / 1e6))
+    # the C++ writer (host/lmdb_reader.cpp, db::LMDB Mode NEW + Transaction), filled the way convert_imageset fills a database:
+    # ascending "%08d_name" keys, one Commit per 1 000 records -- each commit appends, nothing but the leaf index stays in memory
+    from caffe_mpi_b200 import data_api
+    env = data_api.LMDB(a.out, "NEW")
+    for i in range(len(labels)):
+        env.put(lmdb_io.caffe_key(i, "img%d.jpg" % i), lmdb_io.datum_bytes(imgs[i], int(labels[i])))
+        if (i + 1) % 1000 == 0:
+            env.commit()
+    env.commit()
+    st = env.stat()
+    env.close()
+    size = os.path.getsize(os.path.join(a.out, "data.mdb"))
+    print("wrote %d datums of %s to %s (%.1f MB, tree depth %d, %d transactions)" % (st["entries"], "x".join(map(str, imgs.shape[1:])), a.out,
+                                                                                    size / 1e6, st["depth"], st["txnid"]))
     if a.mean:
-        from caffe_mpi_b200 import data_api
         data_api.blobproto_save(a.mean, imgs.mean(axis=0, dtype=np.float64).astype(np.float32)[None])
         print("wrote the mean image to %s" % a.mean)
 
