@@ -94,3 +94,17 @@ def test_rank_batch_divides_the_prototxt_batch_like_p2psync(tmp_path):
     assert cli.rank_batch(net, True, 96, 1) == 96
     inp = 'layer { name: "in" type: "Input" top: "data" input_param { shape { dim: 6 dim: 3 dim: 8 dim: 8 } } }\n'
     assert cli.rank_batch(inp, True, 0, 4) == 0                 # no data_param: left alone
+
+
+def test_time_table_has_the_reference_layout():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("caffe_cli3", os.path.join(ROOT, "tools", "caffe.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    layers = [("data", "Data"), ("conv1", "Convolution"), ("loss", "SoftmaxWithLoss")]
+    prof = [(0, "fwd", 0.01), (1, "fwd", 0.5), (1, "bwd", 1.25), (1, "wgrad", 0.75), (1, "dgrad", 0.5), (2, "fwd", 0.02), (2, "bwd", 0.03)]
+    lines, f, b = cli.layer_time_lines(layers, prof)
+    assert lines[0] == "Average time per layer: " and len(lines) == 1 + 2 * len(layers)
+    assert lines[3] == "     conv1\tforward: 0.5 ms." and lines[4] == "     conv1\tbackward: 1.25 ms. (dgrad 0.5) (wgrad 0.75)"
+    assert lines[2] == "      data\tbackward: 0 ms."
+    assert abs(f - 0.53) < 1e-12 and abs(b - 1.28) < 1e-12

@@ -118,9 +118,24 @@ def cmd_train(args):
         batch = 0
     end = t.iter() + args.iterations if args.iterations else max(d["max_iter"], t.iter())   # a resumed run goes on to max_iter
     last_snapshot = -1
+    # SignalHandler (src/caffe/util/signal_handler.cpp, tools/caffe.cpp:43-48,209-214): SIGINT = stop (with a snapshot when
+    # snapshot_after_train), SIGHUP = snapshot and carry on; both take effect at the next point where the host looks at the device
+    import signal
+    got = {"stop": False, "snapshot": False}
+    signal.signal(signal.SIGINT, lambda *_: got.__setitem__("stop", True))
+    if hasattr(signal, "SIGHUP"):
+        signal.signal(signal.SIGHUP, lambda *_: got.__setitem__("snapshot", True))
     for n, it, show, snap in schedule(t.iter(), end, display, snap_every):
         ms = t.timed_steps(n, copy_input=True)
         assert t.iter() == it
+        if got["snapshot"] and rank == 0 and snap_prefix:
+            log("Snapshotting solver state to binary proto file %s" % t.snapshot(snap_prefix))
+            last_snapshot = it
+        got["snapshot"] = False
+        if got["stop"]:
+            if rank == 0:
+                log("Optimization stopped early.")
+            break
         if rank == 0 and show:
             log("Iteration %d (%.2f iter/s%s), loss = %.6g" % (it, n / (ms / 1e3), ", %.1f img/s" % (batch * world * n / (ms / 1e3)) if batch else "", t.loss()))
         if rank == 0 and snap and snap_prefix:
@@ -132,6 +147,26 @@ def cmd_train(args):
         log("Optimization Done.")
 
 
+def layer_time_lines(layers, prof):
+    """The per-layer table of `caffe time` (tools/caffe.cpp:424-438) from TrainNet's CUDA-event profile: `layers` = [(name, type)],
+    `prof` = [(layer index, "fwd" | "bwd" | "wgrad" | "dgrad", ms per iteration)].  Returns (lines, forward ms, backward ms); the
+    conv layers' weight- / data-gradient split is nested inside their backward time and listed after it."""
+    fwd, bwd, extra = {}, {}, {}
+    for li, op, ms in prof:
+        if op == "fwd":
+            fwd[li] = fwd.get(li, 0.0) + ms
+        elif op == "bwd":
+            bwd[li] = bwd.get(li, 0.0) + ms
+        else:
+            extra.setdefault(li, {})[op] = extra.get(li, {}).get(op, 0.0) + ms
+    lines = ["Average time per layer: "]
+    for i, (name, _) in enumerate(layers):
+        lines.append("%10s\tforward: %g ms." % (name, fwd.get(i, 0.0)))
+        tail = "".join(" (%s %g)" % (k, v) for k, v in sorted(extra.get(i, {}).items()))
+        lines.append("%10s\tbackward: %g ms.%s" % (name, bwd.get(i, 0.0), tail))
+    return lines, sum(fwd.values()), sum(bwd.values())
+
+
 def cmd_time(args):
     from caffe_mpi_b200 import models
     if not args.model:
@@ -139,11 +174,24 @@ def cmd_time(args):
     if args.seed < 0:
         args.seed = 1701
     t, rank, world = build_trainer(args, args.model, False, models.RESNET50_SOLVER, True)
+    iters = args.iterations or 50
     t.step(3)
     t.sync()
-    ms = t.timed_steps(args.iterations or 50)
     if rank == 0:
-        log("Average Forward-Backward-Update: %.4f ms over %d iterations." % (ms / (args.iterations or 50), args.iterations or 50))
+        log("*** Benchmark begins ***")
+        log("Testing for %d iterations." % iters)
+    prof = t.profile(min(iters, 5))                  # CUDA events around every layer call (serialises nothing, but is not free)
+    ms = t.timed_steps(iters)                        # the un-instrumented step: forward + backward + exchange + update
+    if rank == 0:
+        lines, f, b = layer_time_lines(t.layers(), prof)
+        for ln in lines:
+            log(ln)
+        log("Average Forward pass: %g ms." % f)
+        log("Average Backward pass: %g ms." % b)
+        log("Average Forward-Backward-Update: %.4f ms over %d iterations (%s)." % (ms / iters, iters,
+            "per-layer times are device times of single calls; the step overlaps the exchange and update with backward"))
+        log("Total Time: %g ms." % ms)
+        log("*** Benchmark ends ***")
 
 
 def main():
