@@ -27,6 +27,13 @@ inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v;
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
+// NUMKEYS(page) with the sanity a corrupted file needs: `lower` must lie inside the page and after the header
+unsigned num_keys(const uint8_t* pg, unsigned psize) {
+  const unsigned lower = rd16(pg + 12);
+  B2_CHECK(lower >= kPageHdr && lower <= psize && rd16(pg + 14) <= psize, "lmdb: MDB_CORRUPTED: page bounds outside the page");
+  return (lower - kPageHdr) >> 1;
+}
+
 std::string data_file(const std::string& source) {
   struct stat st;
   if (stat(source.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) return source + "/data.mdb";
@@ -286,7 +293,7 @@ void LMDB::Map(const std::string& f) {
   root_ = m.root;
   last_pg_ = m.last_pg;
   txnid_ = m.txnid;
-  if (root_ != kInvalid && (root_ + 1) * (uint64_t)psize_ > map_bytes_) { Unmap(); Fatal(__FILE__, __LINE__, "lmdb " + f + ": root page past the end of the file (truncated copy?)"); }
+  if (root_ != kInvalid && root_ >= map_bytes_ / psize_) { Unmap(); Fatal(__FILE__, __LINE__, "lmdb " + f + ": root page past the end of the file (truncated copy?)"); }
   madvise(const_cast<uint8_t*>(map_), map_bytes_, MADV_SEQUENTIAL);   // Caffe reads in key order, front to back
   stale_ = false;
 }
@@ -339,7 +346,7 @@ void LMDBTransaction::Commit() {
 
 const uint8_t* LMDB::page(uint64_t pgno) const {
   B2_CHECK(map_ != nullptr, "lmdb: environment is closed");
-  B2_CHECK(pgno != kInvalid && (pgno + 1) * (uint64_t)psize_ <= map_bytes_, "lmdb: MDB_PAGE_NOTFOUND: page " + std::to_string(pgno) + " is outside the file");
+  B2_CHECK(psize_ && pgno < map_bytes_ / psize_, "lmdb: MDB_PAGE_NOTFOUND: page " + std::to_string(pgno) + " is outside the file");   // no pgno * psize overflow
   return map_ + pgno * (uint64_t)psize_;
 }
 
@@ -350,7 +357,7 @@ void LMDBCursor::descend_leftmost(uint64_t pgno) {
   for (;;) {
     const uint8_t* pg = env_->page(pgno);
     const uint16_t flags = rd16(pg + 10);
-    const unsigned nkeys = (rd16(pg + 12) - kPageHdr) >> 1;
+    const unsigned nkeys = num_keys(pg, env_->page_size());
     B2_CHECK(!(flags & P_LEAF2), "lmdb: LEAF2 (fixed-size key) pages are not built");
     B2_CHECK(nkeys > 0 && stack_.size() < 64, "lmdb: MDB_CORRUPTED: empty page or runaway depth");
     stack_.push_back(Level{pgno, 0});
@@ -367,6 +374,7 @@ void LMDBCursor::load() {
   const Level& lv = stack_.back();
   const uint8_t* pg = env_->page(lv.pgno);
   const unsigned psize = env_->page_size();
+  B2_CHECK(lv.idx >= 0 && (unsigned)lv.idx < num_keys(pg, psize), "lmdb: MDB_CORRUPTED: node index past the page's keys");
   const unsigned off = rd16(pg + kPageHdr + 2 * lv.idx);
   B2_CHECK(off >= kPageHdr && off + kNodeHdr <= psize, "lmdb: MDB_CORRUPTED: node offset past the page");
   const uint8_t* nd = pg + off;
@@ -383,6 +391,7 @@ void LMDBCursor::load() {
     B2_CHECK(rd16(ov + 10) & P_OVERFLOW, "lmdb: MDB_CORRUPTED: page " + std::to_string(opg) + " is not an overflow page");
     const uint32_t npages = rd32(ov + 12);
     B2_CHECK((uint64_t)kPageHdr + dsz <= (uint64_t)npages * psize, "lmdb: MDB_CORRUPTED: value larger than its overflow run");
+    B2_CHECK(npages >= 1 && opg + (uint64_t)npages > opg, "lmdb: MDB_CORRUPTED: overflow run length");
     env_->page(opg + npages - 1);                     // the whole run lies inside the file
     data_ = ov + kPageHdr;
   } else {
@@ -407,7 +416,7 @@ void LMDBCursor::Next() {
   while (!stack_.empty()) {
     Level& lv = stack_.back();
     const uint8_t* pg = env_->page(lv.pgno);
-    const int nkeys = (int)((rd16(pg + 12) - kPageHdr) >> 1);
+    const int nkeys = (int)num_keys(pg, env_->page_size());
     if (lv.idx + 1 < nkeys) {
       ++lv.idx;
       if (rd16(pg + 10) & P_LEAF) { load(); return; }

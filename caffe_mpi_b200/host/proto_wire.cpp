@@ -88,14 +88,14 @@ BlobData parse_blob(Cursor c) {
       Cursor d = c.sub();
       const size_t n = (size_t)(d.end - d.p) / 4, at = b.data.size();
       b.data.resize(at + n);
-      memcpy(b.data.data() + at, d.p, n * 4);
+      if (n) memcpy(b.data.data() + at, d.p, n * 4);
     } else if (f == 5 && wt == 5) {
       B2_CHECK(c.end - c.p >= 4, "protobuf: truncated float"); float v; memcpy(&v, c.p, 4); c.p += 4; b.data.push_back(v);
     } else if (f == 8 && wt == 2) {
       Cursor d = c.sub();
       const size_t n = (size_t)(d.end - d.p) / 8, at = dd.size();
       dd.resize(at + n);
-      memcpy(dd.data() + at, d.p, n * 8);
+      if (n) memcpy(dd.data() + at, d.p, n * 8);
     } else if (f == 8 && wt == 1) {
       B2_CHECK(c.end - c.p >= 8, "protobuf: truncated double"); double v; memcpy(&v, c.p, 8); c.p += 8; dd.push_back(v);
     } else if (f == 10 && wt == 0) raw_type = (int)c.varint();
@@ -207,7 +207,7 @@ bool ParseDatum(const void* bytes, size_t n, Datum* d) {
         if ((b.end - b.p) % 4) return false;
         const size_t k = (size_t)(b.end - b.p) / 4, at = d->float_data.size();
         d->float_data.resize(at + k);
-        memcpy(d->float_data.data() + at, b.p, k * 4);
+        if (k) memcpy(d->float_data.data() + at, b.p, k * 4);
       } else if (f == 6 && wt == 5) {
         if (c.end - c.p < 4) return false;
         float v; memcpy(&v, c.p, 4); c.p += 4; d->float_data.push_back(v);
