@@ -106,7 +106,7 @@ BlobData parse_blob(Cursor c) {
   if (!dd.empty()) { b.data.assign(dd.begin(), dd.end()); }
   else if (b.data.empty() && !raw.empty()) {
     B2_CHECK(raw_type >= 0, "Missing raw data type");
-    if (raw_type == 1) { b.data.resize(raw.size() / 4); memcpy(b.data.data(), raw.data(), b.data.size() * 4); }
+    if (raw_type == 1) { b.data.resize(raw.size() / 4); if (!b.data.empty()) memcpy(b.data.data(), raw.data(), b.data.size() * 4); }
     else if (raw_type == 0) { b.data.resize(raw.size() / 8); for (size_t i = 0; i < b.data.size(); ++i) { double v; memcpy(&v, raw.data() + 8 * i, 8); b.data[i] = (float)v; } }
     else if (raw_type == 2) { b.data.resize(raw.size() / 2); for (size_t i = 0; i < b.data.size(); ++i) { uint16_t h; memcpy(&h, raw.data() + 2 * i, 2); b.data[i] = half_to_float(h); } }
     else B2_CHECK(false, "Unsupported raw type " + std::to_string(raw_type));

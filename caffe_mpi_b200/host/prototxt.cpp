@@ -264,7 +264,9 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       const auto shp = ip->all("shape");
       for (size_t i = 0; i < L.param.top.size(); ++i) {
         B2_CHECK(!shp.empty(), "Input layer needs shape");
-        std::vector<int> s = to_int(shp[std::min(i, shp.size() - 1)]->msg->ints("dim"));
+        const PField* sf = shp[std::min(i, shp.size() - 1)];
+        B2_CHECK(sf->is_msg(), type + " layer: `shape` must be a message { dim: ... }");
+        std::vector<int> s = to_int(sf->msg->ints("dim"));
         if (batch_override > 0 && !s.empty()) s[0] = batch_override;
         tops.push_back(s);
       }
@@ -300,6 +302,9 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       p.dh = ax(c.dilation, -1, -1, 1, 0); p.dw = ax(c.dilation, -1, -1, 1, 1);
       p.has_bias = c.bias_term;
       B2_CHECK(p.kh > 0 && p.kw > 0, "Filter dimensions must be nonzero.");
+      B2_CHECK(p.sh > 0 && p.sw > 0, "Stride dimensions must be nonzero.");                 // base_conv_layer.cpp:66-69
+      B2_CHECK(p.dh > 0 && p.dw > 0 && p.ph >= 0 && p.pw >= 0, "dilation must be positive and pad non-negative");
+      B2_CHECK(p.G > 0 && p.O > 0, "num_output and group must be positive");
       B2_CHECK(p.C % p.G == 0 && p.O % p.G == 0, "channels / num_output must be multiples of group");
       const int Ho = (p.H + 2 * p.ph - (p.dh * (p.kh - 1) + 1)) / p.sh + 1;     // conv_layer.cpp:7-22
       const int Wo = (p.W + 2 * p.pw - (p.dw * (p.kw - 1) + 1)) / p.sw + 1;
@@ -311,6 +316,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
     } else if (type == "Pooling") {
       const PMessage* pp = lp.sub("pooling_param");
       const std::vector<int>& bs = bottom_shape(0);
+      B2_CHECK(bs.size() == 4, "Pooling expects a 4-D bottom (num, channels, height, width)");   // pooling_layer.cpp:84-86
       PoolingParameter& q = L.pooling;
       if (pp) {
         const std::string pool = pp->str("pool", "MAX");
@@ -323,6 +329,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       }
       if (q.global_pooling) { q.kernel_h = bs[2]; q.kernel_w = bs[3]; q.stride_h = q.stride_w = 1; q.pad_h = q.pad_w = 0; }
       B2_CHECK(q.kernel_h > 0 && q.kernel_w > 0, "Filter dimensions cannot be zero.");
+      B2_CHECK(q.stride_h > 0 && q.stride_w > 0 && q.pad_h >= 0 && q.pad_w >= 0, "Pooling stride must be positive and pad non-negative");
       tops.push_back({bs[0], bs[1], pooled_extent(bs[2], q.kernel_h, q.stride_h, q.pad_h), pooled_extent(bs[3], q.kernel_w, q.stride_w, q.pad_w)});
     } else if (type == "InnerProduct") {
       const PMessage* ip = lp.sub("inner_product_param");
@@ -332,6 +339,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       L.ip_weight_filler = filler_of(ip->sub("weight_filler"));
       L.ip_bias_filler = filler_of(ip->sub("bias_filler"));
       const std::vector<int>& bs = bottom_shape(0);
+      B2_CHECK(bs.size() >= 2 && L.ip_num_output > 0, "InnerProduct needs a bottom with at least 2 axes and a positive num_output");
       const int K = (int)prod(bs, 1);
       tops.push_back({bs[0], L.ip_num_output});
       blobs.push_back({{L.ip_num_output, K}, 0});
@@ -343,6 +351,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       if (bp && bp->has("scale_filler")) { L.bn_scale_filler = filler_of(bp->sub("scale_filler")); L.bn_has_scale_filler = true; }
       if (bp && bp->has("bias_filler")) { L.bn_bias_filler = filler_of(bp->sub("bias_filler")); L.bn_has_bias_filler = true; }
       const std::vector<int>& bs = bottom_shape(0);
+      B2_CHECK(bs.size() >= 2, "BatchNorm needs a bottom with a channel axis");
       tops.push_back(bs);
       // blobs_[0..2] = running mean / variance / correction (statistics, not exchanged with the cuDNN engine:
       // include/caffe/layers/cudnn_batch_norm_layer.hpp:30-32); [3], [4] = scale, bias when scale_bias
@@ -350,6 +359,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
     } else if (type == "Scale") {
       const PMessage* sp = lp.sub("scale_param");
       const std::vector<int>& bs = bottom_shape(0);
+      B2_CHECK(bs.size() >= 2, "Scale needs a bottom with a channel axis");
       tops.push_back(bs);
       if (L.param.bottom.size() == 1) {
         blobs.push_back({{bs[1]}, 0});
@@ -359,6 +369,7 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
       const PMessage* cp = lp.sub("concat_param");
       L.concat_axis = cp ? (int)cp->integer("axis", 1) : 1;
       std::vector<int> s = bottom_shape(0);
+      B2_CHECK(L.concat_axis >= 0 && L.concat_axis < (int)s.size(), "Concat: axis outside the bottom's axes");
       for (size_t i = 1; i < L.param.bottom.size(); ++i) {
         const std::vector<int>& b = bottom_shape((int)i);
         B2_CHECK(b.size() == s.size(), "Concat: all inputs must have the same #axes.");

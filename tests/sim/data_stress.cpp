@@ -4,7 +4,9 @@
 //   2. the reader on DAMAGED files: random byte flips and truncations of a valid database must end in caffe::FatalError or in a
 //      clean walk -- never in a crash or an out-of-bounds access;
 //   3. ParseDatum on random bytes and on truncated valid datums;
-//   4. DataReader: parser threads started, drained and destroyed at random points.
+//   4. DataReader: parser threads started, drained and destroyed at random points;
+//   5. the two parsers of files that come from outside -- prototxt text (models, solvers) and the .caffemodel / .solverstate wire
+//      format (model-zoo weights) -- on mutated inputs: FatalError or a parse, never a crash.
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -16,6 +18,7 @@
 
 #include "../../caffe_mpi_b200/host/b2caffe.hpp"
 #include "../../caffe_mpi_b200/host/data_reader.hpp"
+#include "../../caffe_mpi_b200/host/prototxt.hpp"
 
 using namespace caffe;
 
@@ -128,6 +131,60 @@ int main(int argc, char** argv) {
       const int pops = (int)rnd(12);
       for (int i = 0; i < pops; ++i) { BatchBuf* b = rd.full_pop(); REQUIRE(b->batch_id == (size_t)i); rd.free_push(b); }
     }                                                      // ~DataReader with batches in flight
+  }
+  // ---- 5. text and wire parsers on mutated input
+  {
+    const std::string net =
+        "name: \"fuzz\"\n"
+        "layer { name: \"in\" type: \"Input\" top: \"data\" top: \"label\" input_param { shape { dim: 4 dim: 3 dim: 12 dim: 12 } shape { dim: 4 } } }\n"
+        "layer { name: \"c1\" type: \"Convolution\" bottom: \"data\" top: \"c1\" param { lr_mult: 1 decay_mult: 1 } param { lr_mult: 2 decay_mult: 0 }\n"
+        "  convolution_param { num_output: 8 kernel_size: 3 pad: 1 stride: 2 group: 1 weight_filler { type: \"msra\" } bias_filler { type: \"constant\" value: 0.1 } } }\n"
+        "layer { name: \"bn\" type: \"BatchNorm\" bottom: \"c1\" top: \"bn\" batch_norm_param { scale_bias: true eps: 1e-4 } }\n"
+        "layer { name: \"r\" type: \"ReLU\" bottom: \"bn\" top: \"bn\" }  # in place\n"
+        "layer { name: \"p\" type: \"Pooling\" bottom: \"bn\" top: \"p\" pooling_param { pool: MAX kernel_size: 3 stride: 2 } }\n"
+        "layer { name: \"ip\" type: \"InnerProduct\" bottom: \"p\" top: \"ip\" inner_product_param { num_output: 10 } }\n"
+        "layer { name: \"acc\" type: \"Accuracy\" bottom: \"ip\" bottom: \"label\" top: \"acc\" include { phase: TEST } }\n"
+        "layer { name: \"loss\" type: \"SoftmaxWithLoss\" bottom: \"ip\" bottom: \"label\" top: \"loss\" loss_weight: 1 }\n";
+    { Net ok(ParseTextProto(net), TRAIN); REQUIRE(ok.layers().size() == 7 && ok.learnable_params().size() == 6); }   // TEST-only Accuracy filtered out; BatchNorm lists its scale and bias here
+    const char alphabet[] = "{}:\"#\n 0123456789-.eE_abclmnoprstuyINPUTX";
+    int parsed = 0, rejected = 0;
+    for (int trial = 0; trial < 1500; ++trial) {
+      std::string t = net;
+      const int edits = 1 + (int)rnd(4);
+      for (int e = 0; e < edits; ++e) {
+        const size_t at = rnd((unsigned)t.size());
+        switch (rnd(4)) {
+          case 0: t[at] = alphabet[rnd(sizeof(alphabet) - 1)]; break;
+          case 1: t.erase(at, 1 + rnd(12)); break;
+          case 2: t.insert(at, 1, alphabet[rnd(sizeof(alphabet) - 1)]); break;
+          default: t.insert(at, t.substr(rnd((unsigned)t.size()), rnd(40))); break;
+        }
+      }
+      try { Net n(ParseTextProto(t), rnd(2) ? TRAIN : TEST, (int)rnd(3)); ReadSolverParameter(ParseTextProto(t)); ++parsed; }
+      catch (const FatalError&) { ++rejected; }
+      catch (const std::exception&) { ++rejected; }          // std::stoi and friends on damaged numbers
+    }
+    REQUIRE(parsed > 0 && rejected > 0);
+    NetWeights w;
+    w.name = "fuzz";
+    for (int l = 0; l < 3; ++l) {
+      LayerWeights lw; lw.name = "layer" + std::to_string(l); lw.type = "Convolution"; lw.bottom = {"a"}; lw.top = {"b"};
+      BlobData b; b.shape = {2, 3, 1 + l, 2}; b.data.resize((size_t)2 * 3 * (1 + l) * 2, 0.5f * l);
+      lw.blobs.push_back(b);
+      w.layers.push_back(lw);
+    }
+    SolverStateData st; st.iter = 7; st.learned_net = "x.caffemodel"; st.history.push_back(w.layers[0].blobs[0]);
+    for (int raw = 0; raw < 2; ++raw) {
+      const std::string model = SerializeNetWeights(w, raw != 0), state = SerializeSolverState(st, raw != 0);
+      REQUIRE(ParseNetWeights(model).layers.size() == 3 && ParseSolverState(state).iter == 7);
+      for (int trial = 0; trial < 1500; ++trial) {
+        std::string m = trial % 2 ? model : state;
+        if (rnd(5) == 0) m.resize(rnd((unsigned)m.size() + 1));
+        const int flips = 1 + (int)rnd(5);
+        for (int f = 0; f < flips && !m.empty(); ++f) m[rnd((unsigned)m.size())] = (char)rnd(256);
+        try { if (trial % 2) ParseNetWeights(m); else ParseSolverState(m); ParseBlobProto(m); } catch (const FatalError&) {}
+      }
+    }
   }
   printf("data_stress ok: %zu records, damaged files: %d refused, %d walked\n", model.size(), refused, walked);
   return 0;

@@ -1,7 +1,10 @@
 """AddressSanitizer + UBSan run of the input pipeline's host code (tests/sim/data_stress.cpp): the db::LMDB writer against a
 std::map model over random commits, the reader on hundreds of damaged copies of a valid database (byte flips in page headers, node
 tables and meta pages; truncations) -- each must end in caffe::FatalError or a clean walk, never in a crash -- ParseDatum on random
-and truncated bytes, and DataReader objects destroyed with batches in flight."""
+and truncated bytes, DataReader objects destroyed with batches in flight, and the two parsers of files that come from outside:
+prototxt text through the Net graph builder and the solver reader (1 500 mutated nets per run: it found a Pooling layer fed a 1-D
+blob indexing past its shape, zero strides dividing by zero and a scalar `shape:` dereferenced as a message -- all now fatal
+checks), and the .caffemodel / .solverstate / BlobProto wire format on flipped and truncated bytes."""
 import os
 import subprocess
 
