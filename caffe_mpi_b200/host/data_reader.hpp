@@ -64,7 +64,8 @@ class DataReader {
   size_t datum_bytes() const { return (size_t)c_ * h_ * w_; }
   size_t entries() const { return db_->entries(); }
   size_t full_cycle() const { return full_cycle_; }
-  // Hand an empty buffer to the reader: the n-th buffer pushed receives batch n (filled by parser thread n % P).
+  // Hand an empty buffer to the reader: the n-th buffer pushed receives batch n (filled by parser thread n % P).  The buffer must
+  // stay valid until it comes back from full_pop() or the reader is destroyed: destroy the reader first, then free the buffers.
   void free_push(BatchBuf* b);
   // Next assembled batch, in batch order 0, 1, 2, ...  Blocks; rethrows a parser thread's failure as caffe::FatalError.
   BatchBuf* full_pop();

@@ -35,13 +35,17 @@ static void spit(const std::string& f, const std::string& b) {
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: data_stress <scratch dir> [seed]\n"); return 2; }
   const std::string dir = argv[1];
+  mkdir(dir.c_str(), 0755);
   std::mt19937 rng(argc > 2 ? (unsigned)atoi(argv[2]) : 7u);
   auto rnd = [&](unsigned n) { return (unsigned)(rng() % n); };
   auto blob = [&](size_t n) { std::string s(n, '\0'); for (auto& c : s) c = (char)rnd(256); return s; };
+  const bool threads_only = argc > 3 && std::string(argv[3]) == "threads";      // the ThreadSanitizer build runs section 4 alone
+  std::map<std::string, std::string> model;
+  int refused = 0, walked = 0;
+  if (!threads_only) {
 
   // ---- 1. writer vs model
   const std::string db = dir + "/w";
-  std::map<std::string, std::string> model;
   {
     db::LMDB env;
     env.Open(db, db::NEW);
@@ -73,7 +77,6 @@ int main(int argc, char** argv) {
   const std::string good = slurp(db + "/data.mdb");
   REQUIRE(good.size() > 8192);
   mkdir((dir + "/bad").c_str(), 0755);
-  int refused = 0, walked = 0;
   for (int trial = 0; trial < 400; ++trial) {
     std::string bad = good;
     if (trial % 4 == 0) bad.resize(4096 * (2 + rnd((unsigned)(good.size() / 4096 - 2))) + rnd(4096));
@@ -105,6 +108,7 @@ int main(int argc, char** argv) {
   const std::string datum = SerializeDatum(2, 3, 4, px, sizeof(px), 5);
   for (size_t cut = 0; cut <= datum.size(); ++cut) { Datum d; ParseDatum(datum.data(), cut, &d); }
   for (int trial = 0; trial < 2000; ++trial) { const std::string junk = blob(rnd(64)); Datum d; ParseDatum(junk.data(), junk.size(), &d); }
+  }  // !threads_only
   // ---- 4. DataReader life cycle
   {
     const std::string ddb = dir + "/d";
@@ -122,18 +126,28 @@ int main(int argc, char** argv) {
       DataReaderParam p;
       p.source = ddb; p.batch_size = 1 + (int)rnd(5); p.parser_threads = 1 + rnd(3);
       p.solver_count = 1 + rnd(3); p.solver_rank = rnd((unsigned)p.solver_count);
-      DataReader rd(p);
+      // the buffers are declared BEFORE the reader: they must outlive it, its threads write into them until it is destroyed
+      // (the data layer and the C binding release theirs after reader.reset() for the same reason)
       const int nbuf = 1 + (int)rnd(4);
-      std::vector<std::vector<uint8_t>> data(nbuf, std::vector<uint8_t>(rd.datum_bytes() * p.batch_size));
+      std::vector<std::vector<uint8_t>> data(nbuf, std::vector<uint8_t>((size_t)3 * 6 * 5 * p.batch_size));
       std::vector<std::vector<float>> lab(nbuf, std::vector<float>(p.batch_size));
       std::vector<BatchBuf> bufs(nbuf);
+      DataReader rd(p);
+      REQUIRE(rd.datum_bytes() == 3 * 6 * 5);
       for (int i = 0; i < nbuf; ++i) { bufs[i].data = data[i].data(); bufs[i].label = lab[i].data(); rd.free_push(&bufs[i]); }
       const int pops = (int)rnd(12);
-      for (int i = 0; i < pops; ++i) { BatchBuf* b = rd.full_pop(); REQUIRE(b->batch_id == (size_t)i); rd.free_push(b); }
+      for (int i = 0; i < pops; ++i) {
+        BatchBuf* b = rd.full_pop();
+        REQUIRE(b->batch_id == (size_t)i);
+        unsigned sum = 0;
+        for (size_t k = 0; k < rd.datum_bytes() * p.batch_size; ++k) sum += b->data[k];      // read what the parser thread wrote
+        REQUIRE(sum > 0 && b->label[0] >= 0.f);
+        rd.free_push(b);
+      }
     }                                                      // ~DataReader with batches in flight
   }
   // ---- 5. text and wire parsers on mutated input
-  {
+  if (!threads_only) {
     const std::string net =
         "name: \"fuzz\"\n"
         "layer { name: \"in\" type: \"Input\" top: \"data\" top: \"label\" input_param { shape { dim: 4 dim: 3 dim: 12 dim: 12 } shape { dim: 4 } } }\n"

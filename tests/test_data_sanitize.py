@@ -27,3 +27,24 @@ def test_data_pipeline_host_code_is_clean_under_sanitizers(tmp_path, seed):
     r = subprocess.run([os.path.join(HERE, "sim", "data_stress"), str(tmp_path), str(seed)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "data_stress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-4000:]
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-4000:]
+
+
+def test_reader_threads_are_clean_under_thread_sanitizer(tmp_path):
+    """DataReader's parser threads against ThreadSanitizer: hand-over of batches through the per-thread queues, the first-error
+    channel, destruction with batches in flight (tests/sim/data_stress.cpp, section 4 alone)."""
+    from caffe_mpi_b200 import capi
+    capi.lib()
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "sim"), "data_stress_tsan"], capture_output=True, text=True)
+    if r.returncode != 0:
+        if "sanitize" in r.stderr or "tsan" in r.stderr.lower():
+            pytest.skip("toolchain has no ThreadSanitizer runtime: " + r.stderr[-300:])
+        pytest.fail("tests/sim/data_stress_tsan does not build:\n" + r.stdout[-1000:] + r.stderr[-3000:])
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0:second_deadlock_stack=1")
+    env.pop("LD_PRELOAD", None)
+    for seed in ("3", "8"):
+        r = subprocess.run([os.path.join(HERE, "sim", "data_stress_tsan"), str(tmp_path / seed), seed, "threads"], capture_output=True, text=True, env=env,
+                           timeout=600)
+        if "FATAL: ThreadSanitizer" in r.stderr and "unexpected memory mapping" in r.stderr:
+            pytest.skip("ThreadSanitizer cannot map its shadow in this container: " + r.stderr[-200:])
+        assert r.returncode == 0 and "data_stress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-4000:]
+        assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
