@@ -111,8 +111,13 @@ void fakecuda_launch(cudaStream_t st, std::function<void()> fn) { push_exec(st, 
 extern "C" {
 
 const char* cudaGetErrorString(cudaError_t) { return "fake_cuda error"; }
-cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static cudaError_t aligned_zeroed(void** p, size_t n) {        // cudaMalloc / cudaMallocHost return at least 256-byte aligned memory
+  if (posix_memalign(p, 256, n ? n : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  std::memset(*p, 0, n ? n : 1);
+  return cudaSuccess;
+}
+cudaError_t cudaMalloc(void** p, size_t n) { return aligned_zeroed(p, n); }
+cudaError_t cudaMallocHost(void** p, size_t n) { return aligned_zeroed(p, n); }
 cudaError_t cudaFree(void* p) { force_all(); std::free(p); return cudaSuccess; }            // cudaFree synchronises the device
 cudaError_t cudaFreeHost(void* p) { force_all(); std::free(p); return cudaSuccess; }
 
@@ -158,6 +163,13 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.
 
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t s) {
   push_exec(s, [=] { std::memmove(dst, src, n); });  // the source is read when the copy RUNS
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind,
+                              cudaStream_t s) {
+  push_exec(s, [=] {
+    for (size_t r = 0; r < height; ++r) std::memmove(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+  });
   return cudaSuccess;
 }
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t s) {

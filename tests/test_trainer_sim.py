@@ -1,0 +1,122 @@
+"""TrainNet's HOST logic without a GPU: the whole C++ host layer (prototxt -> layers -> parameter arena -> solver -> snapshot code
+-> C handle API) linked against tests/sim/fake_cuda.cpp instead of the CUDA runtime.  No kernel can run there (libb2c.so refuses to
+launch without a device), so nothing here computes; what runs is everything the host does around the kernels: building the five
+BASELINE nets, sizing the arena the gradient allreduce covers, the learnable-parameter list, and Solver::Snapshot / Restore /
+CopyTrainedLayersFrom moving parameters between "device" memory and the .caffemodel / .solverstate files.  The same round trip
+with real updates in between is tests/test_trainer_gpu.py::test_snapshot_restore_roundtrip_on_device."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from caffe_mpi_b200 import capi, host_api, models
+import netoracle as no
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOLVER = 'base_lr: 0.05 lr_policy: "fixed" momentum: 0.9 weight_decay: 0.0005 max_iter: 100 solver_mode: GPU'
+
+
+@pytest.fixture(scope="module")
+def sim_host():
+    """host_api pointed at libtrainsim.so for the duration of the module."""
+    capi.lib()
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "sim"), "libtrainsim.so"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.fail("tests/sim/libtrainsim.so does not build:\n" + r.stdout[-1000:] + r.stderr[-3000:])
+    saved = (host_api._lib, host_api._SO, os.environ.get("B2C_NCCL_ARENA"))
+    host_api._lib, host_api._SO = None, os.path.join(HERE, "sim", "libtrainsim.so")
+    os.environ["B2C_NCCL_ARENA"] = "0"                       # plain cudaMalloc for the diff arena (ncclMemAlloc needs a device)
+    try:
+        yield host_api
+    finally:
+        host_api._lib, host_api._SO = saved[0], saved[1]
+        if saved[2] is None:
+            os.environ.pop("B2C_NCCL_ARENA", None)
+        else:
+            os.environ["B2C_NCCL_ARENA"] = saved[2]
+
+
+# Sigma even(count_i) * 4 bytes of the weights the layers differentiate -- SURVEY.md 8(a) row a17 -- and the number of BatchNorm
+# layers, whose three statistic blobs (mean, variance, correction; lr_mult 0) ride in the arena as in Net::learnable_params()
+SURVEY_ARENA_MB = {"resnet50": 102.2, "alexnet": 243.9, "googlenet": 53.5, "lenet": 1.7}
+
+
+@pytest.mark.parametrize("name", ["lenet", "resnet50", "googlenet", "alexnet"])
+def test_baseline_nets_build_and_size_their_arena_like_the_survey_says(sim_host, name):
+    kw = dict(default_channels=1, default_size=28, num_classes=10) if name == "lenet" else {}
+    t = sim_host.Trainer(models.PROTOTXT[name](2), models.SOLVERS[name], batch=2, **kw)
+    layers = t.layers()
+    n_bn = sum(1 for _, ty in layers if ty == "BatchNorm")
+    n_conv = sum(1 for _, ty in layers if ty == "Convolution")
+    assert n_conv == {"lenet": 2, "resnet50": 53, "googlenet": 59, "alexnet": 5}[name]          # GoogLeNet: 57 + the two auxiliary heads
+    # trainable blobs = what the reference counts per iteration (ResNet-50: 53 conv weights + 53 x (scale, bias) + fc weight, bias = 161)
+    assert t.num_params() == {"lenet": 8, "resnet50": 161, "googlenet": 128, "alexnet": 16}[name]
+    assert t.num_learnable() == t.num_params() + 3 * n_bn                           # 5 blobs per BatchNorm layer in the history list
+    trainable = sum(len(t.get_param(i)) + (len(t.get_param(i)) & 1) for i in range(t.num_params()))
+    assert abs(trainable * 4 / 1e6 - SURVEY_ARENA_MB[name]) < 0.06
+    assert t.arena_floats() >= trainable and (t.arena_floats() - trainable) * 4 < 1.5e6   # + the BatchNorm statistics, even-padded
+    assert t.iter() == 0
+
+
+def _fill(t, rng):
+    vals = []
+    for i in range(t.num_params()):
+        for what in (0, 2):                                   # data, momentum history
+            v = rng.standard_normal(len(t.get_param(i))).astype(np.float32)
+            t.set_param(i, v, what)
+            vals.append(v)
+    return vals
+
+
+def test_snapshot_restore_and_finetune_round_trip_on_the_host_side(sim_host, tmp_path):
+    """Solver::Snapshot -> Restore (solver.cpp:447-604, sgd_solver.cpp:261-353) and Net::CopyTrainedLayersFrom (net.cpp) through
+    "device" memory: every parameter and history value written into the arena comes back bit for bit in a fresh trainer, the file
+    names and the iteration follow the reference, a second snapshot after the arena changed holds the NEW values (the ADVICE
+    round-1 bug: the host mirror of a blob going stale), and shape mismatches are refused."""
+    spec = no.mini_resnet()
+    proto = no.to_prototxt(spec)
+    t = sim_host.Trainer(proto, SOLVER, num_classes=10)
+    rng = np.random.default_rng(5)
+    vals = _fill(t, rng)
+    state = t.snapshot(str(tmp_path / "snap"))
+    assert os.path.basename(state) == "snap_iter_0.solverstate" and os.path.exists(str(tmp_path / "snap_iter_0.caffemodel"))
+    t2 = sim_host.Trainer(proto, SOLVER, num_classes=10, seed=99)
+    assert not np.array_equal(t2.get_param(0), vals[0])
+    t2.restore(state)
+    k = 0
+    for i in range(t.num_params()):
+        for what in (0, 2):
+            assert np.array_equal(t2.get_param(i, what).view(np.uint32), vals[k].view(np.uint32)), (i, what)
+            k += 1
+    # the arena changes behind the blobs' host mirrors (what the fused SGD kernel does on the device): the next snapshot must see it
+    vals2 = _fill(t, np.random.default_rng(6))
+    state_b = t.snapshot(str(tmp_path / "again"))
+    t3 = sim_host.Trainer(proto, SOLVER, num_classes=10, seed=7)
+    t3.restore(state_b)
+    k = 0
+    for i in range(t.num_params()):
+        for what in (0, 2):
+            assert np.array_equal(t3.get_param(i, what).view(np.uint32), vals2[k].view(np.uint32)), ("stale snapshot", i, what)
+            k += 1
+    # fine-tuning: weights by layer name, history untouched
+    t4 = sim_host.Trainer(proto, SOLVER, num_classes=10, seed=11)
+    before_h = t4.get_param(0, 2).copy()
+    copied = t4.copy_trained_layers_from(str(tmp_path / "again_iter_0.caffemodel"))
+    assert copied > 0
+    assert np.array_equal(t4.get_param(0).view(np.uint32), vals2[0].view(np.uint32)) and np.array_equal(t4.get_param(0, 2), before_h)
+    # the history list is Net::learnable_params()-long (5 blobs per BatchNorm layer), like the reference's SolverState
+    L = sim_host.lib()
+    L.b2h_wire_load.restype = C.c_void_p
+    L.b2h_wire_load.argtypes = [C.c_char_p, C.c_int]
+    L.b2h_wire_num_history.argtypes = [C.c_void_p]
+    L.b2h_wire_destroy.argtypes = [C.c_void_p]
+    h = L.b2h_wire_load(state.encode(), 1)
+    assert h and L.b2h_wire_num_history(h) == t.num_learnable() > t.num_params()
+    L.b2h_wire_destroy(h)
+    # a net of another shape refuses the state ("Incorrect length of history blobs" / shape mismatch), as the reference does
+    other = sim_host.Trainer(no.to_prototxt(no.mini_lenet()) if hasattr(no, "mini_lenet") else models.PROTOTXT["lenet"](2), SOLVER,
+                             num_classes=10, default_channels=1, default_size=28)
+    with pytest.raises(sim_host.HostError):
+        other.restore(state)
