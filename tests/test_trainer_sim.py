@@ -120,3 +120,24 @@ def test_snapshot_restore_and_finetune_round_trip_on_the_host_side(sim_host, tmp
                              num_classes=10, default_channels=1, default_size=28)
     with pytest.raises(sim_host.HostError):
         other.restore(state)
+
+
+def test_trainer_setup_and_snapshot_code_is_clean_under_sanitizers(tmp_path):
+    """tests/sim/trainer_stress.cpp: ResNet-50, GoogLeNet and AlexNet built through the C handle API under AddressSanitizer + UBSan,
+    every parameter and history blob written, snapshotted, restored into a second trainer and compared, then fine-tuned from."""
+    capi.lib()
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "sim"), "trainer_stress"], capture_output=True, text=True)
+    if r.returncode != 0:
+        if "sanitize" in r.stderr or "asan" in r.stderr.lower():
+            pytest.skip("toolchain has no sanitizer runtime: " + r.stderr[-300:])
+        pytest.fail("tests/sim/trainer_stress does not build:\n" + r.stdout[-1000:] + r.stderr[-3000:])
+    paths = []
+    for name in ("resnet50", "googlenet", "alexnet"):
+        p = tmp_path / (name + ".prototxt")
+        p.write_text(models.PROTOTXT[name](2))
+        paths.append(str(p))
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([os.path.join(HERE, "sim", "trainer_stress"), str(tmp_path), "3", "224"] + paths, capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and "trainer_stress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-4000:]
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr and "LeakSanitizer" not in r.stderr, r.stderr[-4000:]
