@@ -294,7 +294,8 @@ void LMDB::Map(const std::string& f) {
   last_pg_ = m.last_pg;
   txnid_ = m.txnid;
   if (root_ != kInvalid && root_ >= map_bytes_ / psize_) { Unmap(); Fatal(__FILE__, __LINE__, "lmdb " + f + ": root page past the end of the file (truncated copy?)"); }
-  madvise(const_cast<uint8_t*>(map_), map_bytes_, MADV_SEQUENTIAL);   // Caffe reads in key order, front to back
+  // no madvise: like liblmdb, default read-ahead.  (MADV_SEQUENTIAL would also drop pages behind the cursor, which costs the
+  // second epoch of a database that fits the page cache.)
   stale_ = false;
 }
 
@@ -370,7 +371,7 @@ void LMDBCursor::descend_leftmost(uint64_t pgno) {
   }
 }
 
-void LMDBCursor::load() {
+void LMDBCursor::load() const {
   const Level& lv = stack_.back();
   const uint8_t* pg = env_->page(lv.pgno);
   const unsigned psize = env_->page_size();
@@ -399,6 +400,7 @@ void LMDBCursor::load() {
     data_ = key_ + ksize_;
   }
   dsize_ = dsz;
+  loaded_ = true;
 }
 
 void LMDBCursor::SeekToFirst() {
@@ -406,7 +408,7 @@ void LMDBCursor::SeekToFirst() {
   valid_ = false;
   if (env_->root_ == kInvalid || env_->entries_ == 0) return;   // MDB_NOTFOUND on an empty database
   descend_leftmost(env_->root_);
-  load();
+  loaded_ = false;
   valid_ = true;
 }
 
@@ -419,13 +421,13 @@ void LMDBCursor::Next() {
     const int nkeys = (int)num_keys(pg, env_->page_size());
     if (lv.idx + 1 < nkeys) {
       ++lv.idx;
-      if (rd16(pg + 10) & P_LEAF) { load(); return; }
+      if (rd16(pg + 10) & P_LEAF) { loaded_ = false; return; }
       const unsigned off = rd16(pg + kPageHdr + 2 * lv.idx);
       B2_CHECK(off + kNodeHdr <= env_->page_size(), "lmdb: MDB_CORRUPTED: node offset past the page");
       const uint8_t* nd = pg + off;
       const uint64_t child = (uint64_t)rd16(nd) | ((uint64_t)rd16(nd + 2) << 16) | ((uint64_t)rd16(nd + 4) << 32);
       descend_leftmost(child);
-      load();
+      loaded_ = false;
       return;
     }
     stack_.pop_back();

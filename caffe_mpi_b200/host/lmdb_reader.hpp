@@ -49,21 +49,26 @@ class LMDBCursor {
   void SeekToFirst();
   void Next();
   bool valid() const { return valid_; }
-  std::string key() const { return std::string(reinterpret_cast<const char*>(key_), ksize_); }
-  std::string value() const { return std::string(reinterpret_cast<const char*>(data_), dsize_); }
-  const void* data() const { return data_; }   // into the mapping; stable while the LMDB object lives
-  size_t size() const { return dsize_; }
-  const void* key_data() const { return key_; }
-  size_t key_size() const { return ksize_; }
+  std::string key() const { ensure(); return std::string(reinterpret_cast<const char*>(key_), ksize_); }
+  std::string value() const { ensure(); return std::string(reinterpret_cast<const char*>(data_), dsize_); }
+  const void* data() const { ensure(); return data_; }   // into the mapping; stable while the LMDB object lives
+  size_t size() const { ensure(); return dsize_; }
+  const void* key_data() const { ensure(); return key_; }
+  size_t key_size() const { ensure(); return ksize_; }
  private:
   struct Level { uint64_t pgno; int idx; };
   void descend_leftmost(uint64_t pgno);        // push pages down to the leftmost leaf under pgno
-  void load();                                 // key_ / data_ from the top of the stack
+  void load() const;                           // key_ / data_ from the top of the stack
+  // The node is decoded on first access, not on Next(): a DataReader that strides over the other solvers' records
+  // (CursorManager::next steps full_cycle - batch_size records between batches) then touches only leaf pages, never the
+  // overflow pages holding the datums it skips.
+  void ensure() const { if (valid_ && !loaded_) load(); }
+  mutable bool loaded_ = false;
   const LMDB* env_;
   std::vector<Level> stack_;                   // root .. leaf
-  const uint8_t* key_ = nullptr;
-  const uint8_t* data_ = nullptr;
-  size_t ksize_ = 0, dsize_ = 0;
+  mutable const uint8_t* key_ = nullptr;
+  mutable const uint8_t* data_ = nullptr;
+  mutable size_t ksize_ = 0, dsize_ = 0;
   bool valid_ = false;
 };
 
