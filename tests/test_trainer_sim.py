@@ -141,3 +141,76 @@ def test_trainer_setup_and_snapshot_code_is_clean_under_sanitizers(tmp_path):
     r = subprocess.run([os.path.join(HERE, "sim", "trainer_stress"), str(tmp_path), "3", "224"] + paths, capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0 and "trainer_stress ok" in r.stdout, r.stdout[-1000:] + r.stderr[-4000:]
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr and "LeakSanitizer" not in r.stderr, r.stderr[-4000:]
+
+
+# ---- TrainNet::Step end to end on the stream-order model (fully-connected nets: tests/sim/fake_kernels.cpp) ----------------------------
+DB_NET = ('name: "db_net"\n'
+          'layer {{ name: "data" type: "Data" top: "data" top: "label" include {{ phase: TRAIN }}\n'
+          '  data_param {{ source: "{src}" backend: LMDB batch_size: {B} {dp} }}\n'
+          '  transform_param {{ {tp} }} }}\n'
+          'layer {{ name: "ip" type: "InnerProduct" bottom: "data" top: "ip" inner_product_param {{ num_output: 10 weight_filler {{ type: "gaussian" std: 0.01 }} }} }}\n'
+          'layer {{ name: "loss" type: "SoftmaxWithLoss" bottom: "ip" bottom: "label" top: "loss" }}\n')
+STEP_MODES = {"all-lazy": (0, 0), "all-eager": (1, 1), "compute-lazy_side-eager": (0, 1), "compute-eager_side-lazy": (1, 0)}
+
+
+@pytest.mark.parametrize("mode", sorted(STEP_MODES))
+def test_training_from_a_database_end_to_end_under_extreme_stream_orders(sim_host, tmp_path, monkeypatch, mode):
+    """The scenario of tests/test_zz_data_layer_gpu.py, plus the arithmetic of the steps: a Data layer on an LMDB (two parser threads)
+    -> InnerProduct -> SoftmaxWithLoss trained for 12 iterations through TrainNet::Step with the compute stream and the side streams
+    (the data layer's copy stream, the solver's update stream) each running as late or as early as their event dependencies allow.
+    Every batch the net sees, every loss and the final weights and momentum must equal a numpy replay of the same iterations."""
+    from caffe_mpi_b200 import data_api, lmdb_io
+    from oracle import layers_oracle as lo
+    from test_data_cpu import oracle_batches
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    rng = np.random.default_rng(77)
+    n, Cc, H, W, B, crop, seed, steps, P = 50, 3, 12, 10, 4, 7, 77, 12, 2
+    imgs = rng.integers(0, 256, (n, Cc, H, W), dtype=np.uint8)
+    labels = rng.integers(0, 10, n)
+    path = str(tmp_path / "train_lmdb")
+    lmdb_io.write_datum_lmdb(path, imgs, labels)
+    mean, scale = [104.0, 117.0, 123.0], 0.0078125
+    net = DB_NET.format(src=path, B=B, dp="parser_threads: %d" % P,
+                        tp="crop_size: %d mirror: true scale: %g random_seed: %d %s" % (crop, scale, seed, " ".join("mean_value: %g" % m for m in mean)))
+    L = sim_host.lib()
+    L.fakecuda_set_eager.argtypes = [C.c_void_p, C.c_int]
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_set_all_eager(0)
+    t = sim_host.Trainer(net, SOLVER, num_classes=10)
+    assert t.database_batches() == 0 and t.num_params() == 2
+    compute_eager, side_eager = STEP_MODES[mode]
+    L.fakecuda_set_all_eager(side_eager)
+    L.fakecuda_set_eager(None, compute_eager)
+    w, b = t.get_param(0).reshape(10, -1).astype(np.float64), t.get_param(1).astype(np.float64)
+    hw, hb = np.zeros_like(w), np.zeros_like(b)
+    want_batches = oracle_batches(n, steps, B, 1, 0, P)
+    ho, wo, mir = data_api.transform_draws(seed, True, crop, True, B * steps, H, W)
+    lr, mom, wd = 0.05, 0.9, 0.0005
+    for i in range(steps):
+        t.step(1, copy_input=True)
+        pos = [p for p, _ in want_batches[i]]
+        x = lo.transform_u8(imgs[pos], (crop, crop), ho[B * i:B * i + B], wo[B * i:B * i + B], mir[B * i:B * i + B], mean, None, scale)
+        y = labels[pos].astype(np.float32)
+        if i % 3 != 1:                                            # not after every step: several steps run with work still queued
+            assert np.array_equal(t.get_blob("data").reshape(x.shape), x), f"{mode}: batch {i}"
+            assert np.array_equal(t.get_blob("label"), y), f"{mode}: labels {i}"
+        # numpy replay of the iteration (float64): forward, loss, backward, SGD with momentum and L2 decay
+        z = x.reshape(B, -1).astype(np.float64) @ w.T + b
+        z -= z.max(axis=1, keepdims=True)
+        p = np.exp(z)
+        p /= p.sum(axis=1, keepdims=True)
+        loss = -np.log(p[np.arange(B), y.astype(int)]).mean()
+        if i % 3 != 1:
+            assert abs(t.loss() - loss) <= 1e-5 * max(1.0, abs(loss)), f"{mode}: loss of iteration {i}"
+        d = p.copy()
+        d[np.arange(B), y.astype(int)] -= 1.0
+        d /= B
+        gw, gb = d.T @ x.reshape(B, -1).astype(np.float64), d.sum(axis=0)
+        hw = mom * hw + lr * (gw + wd * w)
+        hb = mom * hb + lr * (gb + wd * b)
+        w, b = w - hw, b - hb
+    assert t.database_batches() == steps and t.iter() == steps
+    for got, ref in ((t.get_param(0), w), (t.get_param(1), b), (t.get_param(0, 2), hw), (t.get_param(1, 2), hb)):
+        assert np.abs(got.astype(np.float64) - ref.reshape(-1)).max() <= 2e-5 * max(np.abs(ref).max(), 1e-3), mode
+    assert np.abs(t.get_param(0, 1)).max() == 0.0                # the update cleared the parameter diffs (sgd_solver.cu:18)
+    L.fakecuda_set_all_eager(0)
