@@ -505,7 +505,11 @@ float SGDSolver::GetLearningRate() {
   }
   const string& pol = p.lr_policy;
   if (pol == "fixed") return p.base_lr;
-  if (pol == "step") { current_step_ = iter_ / p.stepsize; return p.base_lr * std::pow(p.gamma, (float)current_step_); }
+  if (pol == "step") {
+    B2_CHECK(p.stepsize > 0, "lr_policy \"step\" needs a positive stepsize");      // the reference divides by it unchecked (sgd_solver.cpp:40)
+    current_step_ = iter_ / p.stepsize;
+    return p.base_lr * std::pow(p.gamma, (float)current_step_);
+  }
   if (pol == "exp") return p.base_lr * std::pow(p.gamma, (float)iter_);
   if (pol == "inv") return p.base_lr * std::pow(1.f + p.gamma * float(iter_), -p.power);
   if (pol == "multistep") {
