@@ -37,8 +37,9 @@ def lib():
         L.b2h_datum_serialize.argtypes = [i, i, i, C.c_char_p, C.c_size_t, i, i, C.POINTER(C.c_float), i, C.c_char_p, C.c_size_t]
         L.b2h_blobproto_load.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(ll), vp]
         L.b2h_blobproto_save.argtypes = [C.c_char_p, i, C.POINTER(i), C.POINTER(C.c_float), i]
+        L.b2h_jpeg_decode.argtypes = [C.c_char_p, C.c_size_t, i, C.POINTER(i), vp, C.c_size_t]
         L.b2h_data_reader_create.restype = vp
-        L.b2h_data_reader_create.argtypes = [C.c_char_p, i, i, i, i, i, i, i]
+        L.b2h_data_reader_create.argtypes = [C.c_char_p, i, i, i, i, i, i, i, i]
         L.b2h_data_reader_destroy.argtypes = [vp]
         L.b2h_data_reader_info.argtypes = [vp, C.POINTER(i), C.POINTER(ll), C.POINTER(ll)]
         L.b2h_data_reader_first_record.restype = ll
@@ -144,6 +145,17 @@ def datum_serialize(channels, height, width, data, label, encoded=False, float_d
     return out.raw[:n]
 
 
+def jpeg_decode(buf, force_color=False):
+    """uint8 [C][H][W] (channels B, G, R like cv2) of a baseline JPEG file's bytes; DataError for what the decoder does not take."""
+    chw = (C.c_int * 3)()
+    if lib().b2h_jpeg_decode(buf, len(buf), int(force_color), chw, None, 0) != 0:
+        raise _err()
+    out = np.empty((chw[0], chw[1], chw[2]), np.uint8)
+    if lib().b2h_jpeg_decode(buf, len(buf), int(force_color), chw, out.ctypes.data_as(C.c_void_p), out.size) != 0:
+        raise _err()
+    return out
+
+
 def blobproto_load(path):
     nd, shp, cnt = C.c_int(), (C.c_int * 8)(), C.c_longlong()
     if lib().b2h_blobproto_load(path.encode(), C.byref(nd), shp, C.byref(cnt), None) != 0:
@@ -163,8 +175,10 @@ def blobproto_save(path, arr, raw=False):
 class DataReader:
     """caffe::DataReader: parser threads over an LMDB with the reference's (node, solver, thread) record partition."""
 
-    def __init__(self, source, batch_size, solver_count=1, solver_rank=0, node_count=1, node_rank=0, parser_threads=1, depth=2):
-        self._h = lib().b2h_data_reader_create(source.encode(), batch_size, solver_count, solver_rank, node_count, node_rank, parser_threads, depth)
+    def __init__(self, source, batch_size, solver_count=1, solver_rank=0, node_count=1, node_rank=0, parser_threads=1, depth=2,
+                 force_encoded_color=False):
+        self._h = lib().b2h_data_reader_create(source.encode(), batch_size, solver_count, solver_rank, node_count, node_rank, parser_threads, depth,
+                                               int(force_encoded_color))
         if not self._h:
             raise _err()
         chw, n, fc = (C.c_int * 3)(), C.c_longlong(), C.c_longlong()

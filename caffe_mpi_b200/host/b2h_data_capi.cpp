@@ -8,6 +8,7 @@
 #include "../../include/b2h_data.h"
 #include "b2caffe.hpp"
 #include "data_reader.hpp"
+#include "jpeg_decode.hpp"
 #include "lmdb_reader.hpp"
 #include "proto_wire.hpp"
 
@@ -138,15 +139,32 @@ int b2h_blobproto_save(const char* path, int ndim, const int* shape, const float
   });
 }
 
+// ---- encoded datums ------------------------------------------------------------------------------------------------------------------
+// DecodeDatumToCVMatNative / DecodeDatumToCVMat(force_color) + CVMatToDatum's [channel][row][column] layout, channels B, G, R
+// (src/caffe/util/io.cpp:167-230).  chw[0..2] = channels, height, width; `out` may be null (query the shape); returns -1 on
+// unsupported or damaged files.
+int b2h_jpeg_decode(const void* bytes, size_t n, int force_color, int* chw, unsigned char* out, size_t cap) {
+  B2D_TRY({
+    DecodedImage img;
+    DecodeJpeg(bytes, n, force_color != 0, &img);
+    chw[0] = img.channels; chw[1] = img.height; chw[2] = img.width;
+    if (out) {
+      B2_CHECK(img.chw.size() <= cap, "b2h_jpeg_decode: buffer too small");
+      memcpy(out, img.chw.data(), img.chw.size());
+    }
+  });
+}
+
 // ---- DataReader ----------------------------------------------------------------------------------------------------------------
 void* b2h_data_reader_create(const char* source, int batch_size, int solver_count, int solver_rank, int node_count, int node_rank,
-                             int parser_threads, int depth) {
+                             int parser_threads, int depth, int force_encoded_color) {
   try {
     DataReaderParam p;
     p.source = source; p.batch_size = batch_size;
     p.solver_count = (size_t)solver_count; p.solver_rank = (size_t)solver_rank;
     p.node_count = (size_t)node_count; p.node_rank = (size_t)node_rank;
     p.parser_threads = (size_t)parser_threads;
+    p.force_encoded_color = force_encoded_color != 0;
     std::unique_ptr<ReaderHandle> h(new ReaderHandle);
     h->reader.reset(new DataReader(p));
     const size_t bytes = h->reader->datum_bytes() * (size_t)batch_size;

@@ -33,7 +33,7 @@ void DataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& top) {
   B2_CHECK(top.size() == 1 || top.size() == 2, "Data layer produces data, or data and label");
   B2_CHECK(L_.batch_size > 0, "Data layer needs a positive batch_size");
   N_ = L_.batch_size;
-  PeekDatumShape(L_.data_source, &C_, &Hd_, &Wd_);                       // data_layer.cpp:176-183: shape from one datum
+  PeekDatumShape(L_.data_source, &C_, &Hd_, &Wd_, L_.force_encoded_color);                       // data_layer.cpp:176-183: shape from one datum
   crop_h_ = L_.crop_size > 0 ? L_.crop_size : Hd_;
   crop_w_ = L_.crop_size > 0 ? L_.crop_size : Wd_;
   B2_CHECK(Hd_ >= crop_h_ && Wd_ >= crop_w_, "crop_size larger than the datum");   // data_transformer.cpp:192-193
@@ -93,6 +93,7 @@ void DataLayer::EnsureStarted() {
   p.solver_count = (size_t)solver_count_;
   p.solver_rank = (size_t)solver_rank_;
   p.parser_threads = (size_t)std::max(1, L_.parser_threads);
+  p.force_encoded_color = L_.force_encoded_color;
   reader_.reset(new DataReader(p));
   B2_CHECK(reader_->channels() == C_ && reader_->height() == Hd_ && reader_->width() == Wd_, "database changed shape between set-up and start");
   // random_seed >= 0: "Use random_seed setting for deterministic transformations" (data_transformer.cpp:733-736); otherwise every

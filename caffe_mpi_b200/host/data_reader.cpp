@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "b2caffe.hpp"
+#include "jpeg_decode.hpp"
 
 namespace caffe {
 
@@ -17,6 +18,23 @@ void step(db::LMDBCursor* cur) {
 }
 void advance(db::LMDBCursor* cur, size_t n, size_t entries) {
   for (size_t i = n % entries; i > 0; --i) step(cur);
+}
+}  // namespace
+
+namespace {
+// What a datum contributes to a batch: its own bytes, or the decoded image of an encoded one (DecodeDatumToCVMat[Native] +
+// CVMatToDatum, io.cpp:167-230).  `img` is scratch that keeps the decoded pixels alive.
+void datum_pixels(const Datum& d, bool force_color, DecodedImage* img, const uint8_t** px, int* c, int* h, int* w) {
+  if (d.encoded) {
+    B2_CHECK(LooksLikeJpeg(d.data, d.data_size), "encoded datum is not a JPEG file (PNG and other encodings are not built)");
+    DecodeJpeg(d.data, d.data_size, force_color, img);
+    *px = img->chw.data(); *c = img->channels; *h = img->height; *w = img->width;
+    return;
+  }
+  B2_CHECK(d.data_size > 0 || d.float_data.empty(), "DataReader: float_data datums are not built (uint8 `data` only)");
+  B2_CHECK(d.channels > 0 && d.height > 0 && d.width > 0, "DataReader: datum has no shape");
+  B2_CHECK(d.data_size == (size_t)d.channels * d.height * d.width, "DataReader: datum data size disagrees with channels*height*width");
+  *px = d.data; *c = d.channels; *h = d.height; *w = d.width;
 }
 }  // namespace
 
@@ -33,10 +51,9 @@ DataReader::DataReader(const DataReaderParam& p) : p_(p) {
     B2_CHECK(cur->valid(), "DataReader: database " + p_.source + " has no first record");
     Datum d;
     B2_CHECK(ParseDatum(cur->data(), cur->size(), &d), "Database cursor failed to parse Datum record");
-    B2_CHECK(!d.encoded, "DataReader: encoded (JPEG / PNG) datums need an image decoder, which this build does not have; "
-                         "convert the database with `convert_imageset` without --encoded");
-    B2_CHECK(d.channels > 0 && d.height > 0 && d.width > 0, "DataReader: first datum has no shape");
-    c_ = d.channels; h_ = d.height; w_ = d.width;
+    DecodedImage img;
+    const uint8_t* px = nullptr;
+    datum_pixels(d, p_.force_encoded_color, &img, &px, &c_, &h_, &w_);
   }
   full_cycle_ = p_.parser_threads * (size_t)p_.batch_size * p_.solver_count * p_.node_count;
   for (size_t t = 0; t < p_.parser_threads; ++t) {
@@ -85,17 +102,17 @@ BatchBuf* DataReader::full_pop() {
 void DataReader::fill(db::LMDBCursor* cur, size_t rec_id, BatchBuf* b) {
   const size_t B = (size_t)p_.batch_size, bytes = datum_bytes();
   Datum d;
+  DecodedImage img;
   for (size_t j = 0; j < B; ++j) {
     B2_CHECK(ParseDatum(cur->data(), cur->size(), &d), "Database cursor failed to parse Datum record");
-    B2_CHECK(!d.encoded, "DataReader: encoded datum in " + p_.source + " (no image decoder in this build)");
-    B2_CHECK(d.channels == c_, "Number of channels can't vary in the same batch");
-    B2_CHECK(d.height == h_, "Image height can't vary in the same batch (crop might help here)");   // data_layer.cpp:262-271; all
-    B2_CHECK(d.width == w_, "Image width can't vary in the same batch (crop might help here)");     // datums share the sample's shape
-    B2_CHECK(d.data_size == bytes, d.data_size == 0 && !d.float_data.empty()
-                                       ? "DataReader: float_data datums are not built (uint8 `data` only)"
-                                       : "DataReader: datum data size disagrees with channels*height*width");
+    const uint8_t* px = nullptr;
+    int c = 0, h = 0, w = 0;
+    datum_pixels(d, p_.force_encoded_color, &img, &px, &c, &h, &w);
+    B2_CHECK(c == c_, "Number of channels can't vary in the same batch");
+    B2_CHECK(h == h_, "Image height can't vary in the same batch (crop might help here)");   // data_layer.cpp:262-271; all
+    B2_CHECK(w == w_, "Image width can't vary in the same batch (crop might help here)");     // datums share the sample's shape
     const size_t item = (rec_id + j) % B;                              // data_layer.cpp:256
-    memcpy(b->data + item * bytes, d.data, bytes);
+    memcpy(b->data + item * bytes, px, bytes);
     b->label[item] = (float)d.label;
     if (b->record_id) b->record_id[item] = (uint32_t)(rec_id + j);
     step(cur);
@@ -146,15 +163,16 @@ bool UseDatabase(const std::string& source, int backend) {
   return true;
 }
 
-void PeekDatumShape(const std::string& source, int* c, int* h, int* w) {
+void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool force_encoded_color) {
   db::LMDB env;
   env.Open(source, db::READ);
   std::unique_ptr<db::LMDBCursor> cur(env.NewCursor());
   B2_CHECK(cur->valid(), "database " + source + " is empty");
   Datum d;
   B2_CHECK(ParseDatum(cur->data(), cur->size(), &d), "Database cursor failed to parse Datum record");
-  B2_CHECK(d.channels > 0 && d.height > 0 && d.width > 0, "first datum of " + source + " has no shape (encoded datums are not built)");
-  *c = d.channels; *h = d.height; *w = d.width;
+  DecodedImage img;
+  const uint8_t* px = nullptr;
+  datum_pixels(d, force_encoded_color, &img, &px, c, h, w);
 }
 
 // ------------------------------------------------------------------------------------------------ TransformDraws

@@ -16,7 +16,10 @@
 // batch anyway -- and it is assembled in place in a buffer the consumer provides (the data layer passes pinned host memory), the
 // datum's pixel bytes being copied once, from the file mapping.  The reference moves every datum three times (LMDB value ->
 // Datum string -> batch blob -> device).  DataParameter.cache / shuffle are accepted and ignored with a note: the mapping is the
-// cache; shuffling is not built.  Encoded (JPEG / PNG) datums are fatal: there is no image decoder in the toolchain.
+// cache; shuffling is not built.  ENCODED datums (convert_imageset --encoded) are decoded by the parser threads with the baseline
+// JPEG decoder of jpeg_decode.hpp -- bit-identical to the reference's cv::imdecode on the files it takes; PNG-encoded datums and
+// the JPEG variants that decoder lists are fatal.  Raw datums are the fast path: a decode costs a few milliseconds per image and
+// thread, so an encoded database wants `parser_threads` raised accordingly.
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -40,6 +43,7 @@ struct DataReaderParam {
   size_t solver_count = 1, solver_rank = 0;     // Caffe::solver_count(), solver_rank_
   size_t node_count = 1, node_rank = 0;         // Clusters::node_count() / node_rank()
   size_t parser_threads = 1;                    // DataParameter.parser_threads (0 = auto in the reference; 1 here)
+  bool force_encoded_color = false;             // DataParameter.force_encoded_color: decode one-channel files to three channels
 };
 
 // One batch under assembly / assembled.  `data` is [batch][C][H][W] uint8 in datum layout, `label` one float per item (the
@@ -96,8 +100,8 @@ class DataReader {
 // reference's behaviour, db_lmdb.cpp:19); unset / "auto": the database when <source>/data.mdb exists, else the synthetic source
 // (bench.py and the tests run the reference's prototxts on machines that do not hold ImageNet).
 bool UseDatabase(const std::string& source, int backend);
-// channels / height / width of the first datum (DataReader::sample())
-void PeekDatumShape(const std::string& source, int* c, int* h, int* w);
+// channels / height / width of the first datum (DataReader::sample()); an encoded first datum is decoded to learn them
+void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool force_encoded_color = false);
 
 // DataTransformer's random draws (src/caffe/data_transformer.cpp:127-137 Fill3Randoms, :187,219-226 their use, :729-749
 // InitRand / Rand): per datum  rand0 = Rand() + 1 if mirror;  rand1 = Rand() + 1, rand2 = Rand() + 1 if TRAIN and crop_size;

@@ -246,10 +246,11 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
         const std::string be = dp->str("backend", "LEVELDB");
         L.data_backend = (be == "LMDB" || be == "1") ? 1 : 0;
         L.parser_threads = (int)dp->integer("parser_threads", 0);
+        L.force_encoded_color = dp->boolean("force_encoded_color", false);
         if (tp) { L.mean_file = tp->str("mean_file"); L.transform_random_seed = tp->integer("random_seed", -1); }
         // DataLayerSetUp reads one datum to size the top blob (data_layer.cpp:176-183); so does this, when the database is there
         L.use_database = UseDatabase(L.data_source, L.data_backend);
-        if (L.use_database) PeekDatumShape(L.data_source, &dc, &dh, &dw);
+        if (L.use_database) PeekDatumShape(L.data_source, &dc, &dh, &dw, L.force_encoded_color);
       }
       if (L.crop_size > 0) {
         if (L.use_database) B2_CHECK(dh >= L.crop_size && dw >= L.crop_size, "crop_size larger than the datums of " + L.data_source);

@@ -44,6 +44,10 @@ int b2h_datum_parse(const void* bytes, size_t n, long long* out, const void** da
  * written to `out`, -1 if it does not fit */
 long long b2h_datum_serialize(int channels, int height, int width, const void* data, size_t data_size, int label, int encoded,
                               const float* float_data, int n_float, void* out, size_t cap);
+/* An ENCODED datum's image: DecodeDatumToCVMatNative / DecodeDatumToCVMat(force_color) (src/caffe/util/io.cpp:167-190, cv::imdecode)
+ * followed by CVMatToDatum's [channel][row][column] layout with OpenCV's channel order B, G, R (io.cpp:205-230).  Baseline JPEG only
+ * (host/jpeg_decode.hpp).  chw[0..2] = channels, height, width; `out` may be NULL to learn the shape. */
+int b2h_jpeg_decode(const void* bytes, size_t n, int force_color, int* chw, unsigned char* out, size_t cap);
 /* ReadProtoFromBinaryFileOrDie(mean_file) + Blob::FromProto (src/caffe/data_transformer.cpp:21-30, src/caffe/blob.cpp:352-414):
  * shape gets up to 8 axes; call with data == NULL to learn the count first */
 int b2h_blobproto_load(const char* path, int* ndim, int* shape, long long* count, float* data);
@@ -52,10 +56,10 @@ int b2h_blobproto_save(const char* path, int ndim, const int* shape, const float
 /* ---- DataReader (src/caffe/data_reader.cpp:16-124 threads and queues, :206-310 CursorManager) ---------------------------------------
  * Same arguments as the reference's constructor: which solver of how many (Caffe::solver_count(), solver_rank_), which node of how
  * many (Clusters::node_count() / node_rank()), parser threads per solver, batch size.  `depth` = batches in flight per parser
- * thread (queue_depth).  Batches come back in the order the data layer consumes them: batch n of this solver = records
+ * thread (queue_depth); force_encoded_color = DataParameter.force_encoded_color (encoded datums are decoded by the parser threads).  Batches come back in the order the data layer consumes them: batch n of this solver = records
  * [first_record(n), first_record(n) + batch_size) of the (node, solver, thread) partition, positions taken modulo the entries. */
 void* b2h_data_reader_create(const char* source, int batch_size, int solver_count, int solver_rank, int node_count, int node_rank,
-                             int parser_threads, int depth);
+                             int parser_threads, int depth, int force_encoded_color);
 void b2h_data_reader_destroy(void* reader);
 int b2h_data_reader_info(void* reader, int* chw, long long* entries, long long* full_cycle);   /* DataReader::sample() shape */
 long long b2h_data_reader_first_record(void* reader, long long batch);                           /* CursorManager::rewind / next */

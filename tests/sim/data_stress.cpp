@@ -6,7 +6,9 @@
 //   3. ParseDatum on random bytes and on truncated valid datums;
 //   4. DataReader: parser threads started, drained and destroyed at random points;
 //   5. the two parsers of files that come from outside -- prototxt text (models, solvers) and the .caffemodel / .solverstate wire
-//      format (model-zoo weights) -- on mutated inputs: FatalError or a parse, never a crash.
+//      format (model-zoo weights) -- on mutated inputs: FatalError or a parse, never a crash;
+//   6. the JPEG decoder on mutated copies of the files <scratch dir>/seed*.jpg (written by the test): flips in headers, tables and
+//      entropy-coded data, truncations.
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -18,6 +20,7 @@
 
 #include "../../caffe_mpi_b200/host/b2caffe.hpp"
 #include "../../caffe_mpi_b200/host/data_reader.hpp"
+#include "../../caffe_mpi_b200/host/jpeg_decode.hpp"
 #include "../../caffe_mpi_b200/host/prototxt.hpp"
 
 using namespace caffe;
@@ -199,6 +202,27 @@ int main(int argc, char** argv) {
         try { if (trial % 2) ParseNetWeights(m); else ParseSolverState(m); ParseBlobProto(m); } catch (const FatalError&) {}
       }
     }
+  }
+  // ---- 6. JPEG decoder on damaged files
+  if (!threads_only) {
+    int decoded = 0, rejected = 0, files = 0;
+    for (int f = 0; f < 8; ++f) {
+      const std::string jpg = slurp(dir + "/seed" + std::to_string(f) + ".jpg");
+      if (jpg.empty()) continue;
+      ++files;
+      { DecodedImage img; DecodeJpeg(jpg.data(), jpg.size(), false, &img); REQUIRE(img.channels >= 1 && img.height > 0 && img.width > 0); }
+      for (int trial = 0; trial < 1200; ++trial) {
+        std::string m = jpg;
+        if (rnd(6) == 0) m.resize(rnd((unsigned)m.size() + 1));
+        const int flips = 1 + (int)rnd(4);
+        for (int k = 0; k < flips && !m.empty(); ++k) {
+          const size_t at = rnd(3) ? rnd((unsigned)std::min<size_t>(m.size(), 700)) : rnd((unsigned)m.size());   // headers and tables first
+          m[at] = (char)rnd(256);
+        }
+        try { DecodedImage img; DecodeJpeg(m.data(), m.size(), rnd(2) != 0, &img); ++decoded; } catch (const FatalError&) { ++rejected; }
+      }
+    }
+    if (files) REQUIRE(decoded > 0 && rejected > 0);
   }
   printf("data_stress ok: %zu records, damaged files: %d refused, %d walked\n", model.size(), refused, walked);
   return 0;

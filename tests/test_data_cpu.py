@@ -287,8 +287,8 @@ def test_reader_refuses_what_it_cannot_feed(tmp_path):
     img = np.zeros((3, 4, 4), np.uint8)
     enc = str(tmp_path / "enc")
     lmdb_io.write_lmdb(enc, [(lmdb_io.caffe_key(0), lmdb_io.datum_bytes(img, 1, encoded=True))])
-    with pytest.raises(data_api.DataError, match="encoded"):
-        data_api.DataReader(enc, 2)
+    with pytest.raises(data_api.DataError, match="encoded datum is not a JPEG file"):
+        data_api.DataReader(enc, 2)                               # `encoded` set, but the bytes are no image file
     mixed = str(tmp_path / "mixed")
     lmdb_io.write_lmdb(mixed, [(lmdb_io.caffe_key(0), lmdb_io.datum_bytes(img, 1)), (lmdb_io.caffe_key(1), lmdb_io.datum_bytes(np.zeros((3, 5, 4), np.uint8), 1))])
     rd = data_api.DataReader(mixed, 2)
@@ -380,7 +380,7 @@ def test_library_exports_every_symbol_b2h_data_h_declares():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "b2h_data.h")).read(), flags=re.S)
     syms = sorted(set(re.findall(r"\b(b2h_[a-z0-9_]+)\s*\(", txt)))
-    assert len(syms) == 22
+    assert len(syms) == 23
     L = host_api.lib()
     assert not [s for s in syms if not hasattr(L, s)]
 

@@ -22,6 +22,18 @@ def test_data_pipeline_host_code_is_clean_under_sanitizers(tmp_path, seed):
         if "sanitize" in r.stderr or "asan" in r.stderr.lower():
             pytest.skip("toolchain has no sanitizer runtime: " + r.stderr[-300:])
         pytest.fail("tests/sim/data_stress does not build:\n" + r.stdout[-1000:] + r.stderr[-3000:])
+    try:                                                     # seed files for the JPEG-decoder section (skipped there when cv2 is absent)
+        import cv2
+        import numpy as np
+        rng = np.random.default_rng(seed)
+        for k, (h, w, extra) in enumerate([(40, 56, []), (33, 17, [cv2.IMWRITE_JPEG_RST_INTERVAL, 2]), (24, 24, [cv2.IMWRITE_JPEG_OPTIMIZE, 1])]):
+            img = cv2.resize(rng.integers(0, 256, (6, 6, 3), dtype=np.uint8), (w, h), interpolation=cv2.INTER_CUBIC)
+            ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 70] + extra)
+            (tmp_path / ("seed%d.jpg" % k)).write_bytes(enc.tobytes())
+        ok, enc = cv2.imencode(".jpg", img[:, :, 0])
+        (tmp_path / "seed3.jpg").write_bytes(enc.tobytes())
+    except ImportError:
+        pass
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
     env.pop("LD_PRELOAD", None)
     r = subprocess.run([os.path.join(HERE, "sim", "data_stress"), str(tmp_path), str(seed)], capture_output=True, text=True, env=env, timeout=600)
