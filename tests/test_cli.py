@@ -108,3 +108,22 @@ def test_time_table_has_the_reference_layout():
     assert lines[3] == "     conv1\tforward: 0.5 ms." and lines[4] == "     conv1\tbackward: 1.25 ms. (dgrad 0.5) (wgrad 0.75)"
     assert lines[2] == "      data\tbackward: 0 ms."
     assert abs(f - 0.53) < 1e-12 and abs(b - 1.28) < 1e-12
+
+
+def test_compute_image_mean_writes_what_the_data_layer_reads(tmp_path):
+    import numpy as np
+    from caffe_mpi_b200 import data_api, lmdb_io
+    rng = np.random.default_rng(2)
+    imgs = rng.integers(0, 256, (37, 3, 6, 5), dtype=np.uint8)
+    db = str(tmp_path / "db")
+    lmdb_io.write_datum_lmdb(db, imgs, rng.integers(0, 9, 37))
+    out = str(tmp_path / "mean.binaryproto")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "compute_image_mean.py"), db, out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Number of channels: 3" in r.stdout and "Processed 37 files." in r.stdout, r.stdout + r.stderr
+    got = data_api.blobproto_load(out)                               # the parser the Data layer's mean_file goes through
+    want = np.zeros((3, 6, 5), np.float32)
+    for im in imgs:                                                   # compute_image_mean.cpp:75-99: float running sum, then / count
+        want += im.astype(np.float32)
+    want /= np.float32(37)
+    assert got.shape == (1, 3, 6, 5) and np.array_equal(got[0], want)
+    assert ("mean_value channel [0]: %g" % float(want[0].sum(dtype=np.float32) / 30)) in r.stdout
