@@ -127,3 +127,49 @@ def test_compute_image_mean_writes_what_the_data_layer_reads(tmp_path):
     want /= np.float32(37)
     assert got.shape == (1, 3, 6, 5) and np.array_equal(got[0], want)
     assert ("mean_value channel [0]: %g" % float(want[0].sum(dtype=np.float32) / 30)) in r.stdout
+
+
+def test_convert_imageset_raw_and_encoded(tmp_path):
+    """tools/convert_imageset.py -> db::LMDB writer -> DataReader: raw datums hold cv2's B,G,R planes (resized), --encoded datums the
+    re-encoded or original files, which the parser threads decode back to the same pixels cv2.imdecode gives."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from caffe_mpi_b200 import data_api
+    rng = np.random.default_rng(6)
+    root = tmp_path / "imgs"
+    (root / "a").mkdir(parents=True)
+    names = []
+    for i in range(7):
+        img = cv2.resize(rng.integers(0, 256, (5, 6, 3), dtype=np.uint8), (40 + i, 30 + i), interpolation=cv2.INTER_CUBIC)
+        name = "a/im%d.jpg" % i
+        assert cv2.imwrite(str(root / name), img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+        names.append(name)
+    lst = tmp_path / "list.txt"
+    lst.write_text("".join("%s %d\n" % (n, i % 3) for i, n in enumerate(names)) + "a/missing.jpg 1\n")
+    tool = [sys.executable, os.path.join(ROOT, "tools", "convert_imageset.py")]
+    raw_db = str(tmp_path / "raw_db")
+    r = subprocess.run(tool + ["--resize_width=24", "--resize_height=20", "--check_size", str(root) + "/", str(lst), raw_db], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Processed 7 files." in r.stdout and "Could not open or find file" in r.stderr, r.stdout + r.stderr
+    items = data_api.LMDB(raw_db).items()
+    assert [k for k, _ in items] == [("%08d_%s" % (i, n)).encode() for i, n in enumerate(names)]
+    rd = data_api.DataReader(raw_db, 7)
+    data, label, _, _ = rd.next()
+    rd.close()
+    want = np.stack([cv2.resize(cv2.imread(str(root / n)), (24, 20)).transpose(2, 0, 1) for n in names])
+    assert np.array_equal(data, want) and label.tolist() == [i % 3 for i in range(7)]
+    enc_db = str(tmp_path / "enc_db")
+    r = subprocess.run(tool + ["--encoded", "--resize_width=24", "--resize_height=20", str(root) + "/", str(lst), enc_db], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rd = data_api.DataReader(enc_db, 7, parser_threads=2)
+    data, label, _, _ = rd.next()
+    rd.close()
+    for i, n in enumerate(names):                                 # what the reference would train on: imdecode of the stored bytes
+        d = data_api.datum_parse(data_api.LMDB(enc_db).items()[i][1])
+        assert d["encoded"] and d["channels"] == 0
+        assert np.array_equal(data[i], cv2.imdecode(np.frombuffer(d["data"], np.uint8), cv2.IMREAD_UNCHANGED).transpose(2, 0, 1))
+    # no resize + matching extension: the original file is stored untouched (ReadFileToDatum)
+    keep_db = str(tmp_path / "keep_db")
+    lst.write_text("%s 2\n" % names[0])
+    r = subprocess.run(tool + ["--encoded", str(root) + "/", str(lst), keep_db], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert data_api.datum_parse(data_api.LMDB(keep_db).items()[0][1])["data"] == (root / names[0]).read_bytes()
