@@ -214,3 +214,113 @@ def test_training_from_a_database_end_to_end_under_extreme_stream_orders(sim_hos
         assert np.abs(got.astype(np.float64) - ref.reshape(-1)).max() <= 2e-5 * max(np.abs(ref).max(), 1e-3), mode
     assert np.abs(t.get_param(0, 1)).max() == 0.0                # the update cleared the parameter diffs (sgd_solver.cu:18)
     L.fakecuda_set_all_eager(0)
+
+
+# ---- the ResNet-style net: TrainNet's graph logic on the CPU (tests/sim/fake_kernels_conv.cpp) ------------------------------------------------
+def _set_modes(L, mode):
+    L.fakecuda_set_eager.argtypes = [C.c_void_p, C.c_int]
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    compute_eager, side_eager = STEP_MODES[mode]
+    L.fakecuda_set_all_eager(side_eager)
+    L.fakecuda_set_eager(None, compute_eager)
+
+
+@pytest.mark.parametrize("fuse", [False, True], ids=["unfused", "fused"])
+@pytest.mark.parametrize("conv_bias", [False, True])
+def test_bottleneck_resnet_forward_backward_matches_the_net_oracle_on_the_cpu(sim_host, rng, conv_bias, fuse):
+    """tests/test_trainer_gpu.py::test_forward_backward_matches_oracle with host stand-ins for the kernels: what is under test is
+    TrainNet -- shape plumbing, the fusion pass (BatchNorm+ReLU, the residual tail), fan-out shadow diffs and their deferred adds,
+    need-backward -- against tests/netoracle.py: loss, activations, blob diffs and every parameter gradient."""
+    from test_trainer_gpu import make_trainer, rel
+    sim_host.lib().fakecuda_set_all_eager.argtypes = [C.c_int]
+    sim_host.lib().fakecuda_set_all_eager(0)
+    spec = no.mini_resnet(conv_bias=conv_bias)
+    t, params, data, label = make_trainer(spec, rng, fuse=fuse)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss)
+    for name in ("conv1", "pool1", "resA.1.sum", "resA.2.sum", "pool2", "fc"):
+        assert rel(t.get_blob(name), v[name]) <= 1e-4, name
+    for name in ("fc", "pool2", "resA.1.conv1", "pool1", "conv1") + (() if fuse else ("resA.2.sum",)):
+        assert rel(t.get_blob(name, diff=True), d[name]) <= 1e-4, name
+    # (a conv bias in front of BatchNorm has a mathematically zero gradient -- rounding noise on both sides -- hence the floor and
+    # the GPU test's 1e-3 here)
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g, floor) <= 1e-3, no.param_shapes(spec)[i]
+
+
+@pytest.mark.parametrize("mode", sorted(STEP_MODES))
+def test_bottleneck_resnet_sgd_steps_under_extreme_stream_orders(sim_host, rng, mode):
+    """Three Solver::Step iterations (forward, backward, per-bucket update on the side stream, the event hand-overs) of the fused
+    graph under each extreme stream order, against the net oracle's SGD replay: losses, parameters, momentum, cleared diffs."""
+    from test_trainer_gpu import make_trainer, rel
+    L = sim_host.lib()
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_set_all_eager(0)
+    spec = no.mini_resnet()
+    t, params, data, label = make_trainer(spec, rng)
+    _set_modes(L, mode)
+    ref_losses, ref_params, ref_hist = no.sgd_steps(spec, params, data, label, 3, 0.05, 0.9, 0.0005)
+    losses = []
+    for k in range(3):
+        t.step(1)
+        if k != 1:                                        # the second step starts with the first one's loss never read
+            losses.append(t.loss())
+    np.testing.assert_allclose(losses, [ref_losses[0], ref_losses[2]], rtol=2e-4)
+    hfloor = 1e-3 * max(float(np.max(np.abs(h))) for h in ref_hist)
+    for i, (p, h) in enumerate(zip(ref_params, ref_hist)):
+        assert rel(t.get_param(i, 0), p) <= 2e-4, (mode, i)
+        assert rel(t.get_param(i, 2), h, hfloor) <= 5e-4, (mode, i)
+        assert not t.get_param(i, 1).any()
+    L.fakecuda_set_all_eager(0)
+
+
+def test_lenet_matches_the_net_oracle_on_the_cpu(sim_host, rng):
+    from test_trainer_gpu import make_trainer, rel
+    sim_host.lib().fakecuda_set_all_eager.argtypes = [C.c_int]
+    sim_host.lib().fakecuda_set_all_eager(0)
+    spec = no.lenet(batch=8)
+    t, params, data, label = make_trainer(spec, rng)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss)
+    for name in ("conv1", "pool1", "conv2", "pool2", "ip1", "ip2"):
+        assert rel(t.get_blob(name), v[name]) <= 1e-4, name
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g, floor) <= 1e-4, no.param_shapes(spec)[i]
+
+
+def test_iter_size_accumulation_equals_one_pass_on_the_cpu(sim_host, rng):
+    """Solver::Step with iter_size = 2 (solver.cpp:277-288): two forward / backward passes accumulate into the parameter diffs, only
+    the second releases parameters to the update, which folds 1/iter_size in (sgd_solver.cpp Normalize).  On a resident batch --
+    the same samples twice -- three such iterations must equal three iterations with iter_size = 1, here under a lazy side stream.
+    (LeNet: a BatchNorm layer OVERWRITES its scale / bias diffs, in the reference too -- batch_norm_layer.cpp:234-283 -- so nets
+    with BatchNorm do not have this equivalence.)"""
+    from test_trainer_gpu import rel
+    L = sim_host.lib()
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_set_all_eager(0)
+    spec = no.lenet(batch=8)
+    shapes = no.param_shapes(spec)
+    vals = []
+    for _, kind, shp in shapes:
+        vals.append((rng.standard_normal(shp) * np.sqrt(2.0 / np.prod(shp[1:]))).astype(np.float32) if kind == "w" else
+                    rng.uniform(0.5, 1.5, shp).astype(np.float32) if kind == "scale" else rng.uniform(-0.2, 0.2, shp).astype(np.float32))
+    data = rng.standard_normal(spec[0]["shape"]).astype(np.float32)
+    label = rng.integers(0, 10, spec[0]["shape"][0]).astype(np.float32)
+    out = []
+    for iter_size in (1, 2):
+        t = sim_host.Trainer(no.to_prototxt(spec), SOLVER + (" iter_size: %d" % iter_size), num_classes=10)
+        for i, v in enumerate(vals):
+            t.set_param(i, v)
+        t.set_blob("data", data)
+        t.set_blob("label", label)
+        t.step(3)
+        assert t.iter() == 3
+        out.append(([t.get_param(i, 0) for i in range(len(vals))], [t.get_param(i, 2) for i in range(len(vals))], t.loss()))
+    (p1, h1, l1), (p2, h2, l2) = out
+    assert abs(l1 - l2) <= 1e-5 * abs(l1)
+    for i in range(len(vals)):
+        assert rel(p2[i], p1[i]) <= 1e-5 and rel(h2[i], h1[i], 1e-6) <= 1e-4, shapes[i]
