@@ -1,7 +1,8 @@
 // trainer_stress.cpp -- AddressSanitizer + UBSan run of the host layer's graph executor set-up and snapshot code
 // (tests/test_trainer_sim.py builds and runs it).  TEST INFRASTRUCTURE ONLY.  For every net prototxt given on the command line:
 // build the TrainNet through the C handle API (layers, parameter arena, fusion pass, bucket plan), write every parameter and its
-// momentum history, Snapshot, build a second trainer, Restore, compare; then CopyTrainedLayersFrom.  No kernel runs (fake CUDA).
+// momentum history, Snapshot, build a second trainer, Restore, compare; then CopyTrainedLayersFrom.  Nets named *_step.prototxt also
+// run forward / backward and three Solver::Step iterations on the host stand-ins for the kernels.
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -20,6 +21,10 @@ int b2h_trainer_snapshot(void*, const char* prefix, char* state_path, int len);
 int b2h_trainer_restore(void*, const char* state_path);
 int b2h_trainer_copy_from(void*, const char* model_path, int* copied);
 long long b2h_trainer_arena_floats(void*);
+int b2h_trainer_step(void*, int nsteps, int copy_input);
+int b2h_trainer_forward_backward(void*, float* loss);
+int b2h_trainer_clear_param_diffs(void*);
+int b2h_trainer_loss(void*, float* loss);
 }
 #define REQUIRE(c) do { if (!(c)) { fprintf(stderr, "trainer_stress: %s:%d: %s  [%s]\n", __FILE__, __LINE__, #c, b2h_last_error()); return 1; } } while (0)
 
@@ -42,6 +47,18 @@ int main(int argc, char** argv) {
         REQUIRE(b2h_trainer_param(t, i, what, 1, v.data()) == 0);
         vals.push_back(v);
       }
+    if (std::string(argv[a]).find("_step.prototxt") != std::string::npos) {
+      // a small net: whole iterations on the host stand-ins for the kernels (fake_kernels*.cpp), so that the executor's own
+      // allocations -- shadow diffs, fused-layer scratch, the update's segment tables -- are exercised under the sanitizers
+      float loss = 0.f;
+      REQUIRE(b2h_trainer_forward_backward(t, &loss) == 0 && loss == loss);
+      REQUIRE(b2h_trainer_clear_param_diffs(t) == 0);
+      REQUIRE(b2h_trainer_step(t, 3, 1) == 0);
+      REQUIRE(b2h_trainer_loss(t, &loss) == 0 && loss == loss);
+      size_t k = 0;                                        // the snapshot below must hold the TRAINED state
+      for (int i = 0; i < n; ++i)
+        for (int what : {0, 2}) { REQUIRE(b2h_trainer_param(t, i, what, 0, vals[k].data()) == 0); ++k; }
+    }
     char state[1024];
     const std::string prefix = dir + "/net" + std::to_string(a);
     REQUIRE(b2h_trainer_snapshot(t, prefix.c_str(), state, sizeof(state)) == 0);
@@ -58,7 +75,9 @@ int main(int argc, char** argv) {
       }
     int copied = 0;
     void* w = b2h_trainer_create(argv[a], 0, solver, 1, 2, 1000, 9, 0, ch, sz);
-    REQUIRE(w != nullptr && b2h_trainer_copy_from(w, (prefix + "_iter_0.caffemodel").c_str(), &copied) == 0 && copied > 0);
+    std::string model = state;                              // <prefix>_iter_<N>.solverstate -> .caffemodel
+    model.replace(model.rfind(".solverstate"), std::string::npos, ".caffemodel");
+    REQUIRE(w != nullptr && b2h_trainer_copy_from(w, model.c_str(), &copied) == 0 && copied > 0);
     b2h_trainer_destroy(w);
     b2h_trainer_destroy(u);
     b2h_trainer_destroy(t);

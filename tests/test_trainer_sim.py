@@ -136,6 +136,10 @@ def test_trainer_setup_and_snapshot_code_is_clean_under_sanitizers(tmp_path):
         p = tmp_path / (name + ".prototxt")
         p.write_text(models.PROTOTXT[name](2))
         paths.append(str(p))
+    for name, spec in (("mini_resnet", no.mini_resnet()), ("mini_resnet_bias", no.mini_resnet(conv_bias=True))):
+        p = tmp_path / (name + "_step.prototxt")              # small enough to run whole iterations on the host stand-ins
+        p.write_text(no.to_prototxt(spec))
+        paths.append(str(p))
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
     env.pop("LD_PRELOAD", None)
     r = subprocess.run([os.path.join(HERE, "sim", "trainer_stress"), str(tmp_path), "3", "224"] + paths, capture_output=True, text=True, env=env, timeout=900)
