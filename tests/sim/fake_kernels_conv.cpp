@@ -340,3 +340,76 @@ int b2c_pool_backward(int method, int NC, int H, int W, int kh, int kw, int sh, 
 }
 
 }  // extern "C"
+
+// ---- the layers AlexNet / GoogLeNet / VGG-16 add: LRN across channels, Dropout, Accuracy ------------------------------------------------------------
+extern "C" {
+
+int b2c_lrn_forward(int N, int C, int Sp, int size, float alpha, float beta, float k, const float* x, float* scale, float* y, void* stream) {
+  fakecuda_launch(S(stream), [=] {
+    const int pre = (size - 1) / 2;
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < C; ++c)
+        for (int i = 0; i < Sp; ++i) {
+          double acc = 0;
+          for (int cc = std::max(c - pre, 0); cc < std::min(c - pre + size, C); ++cc) { const double v = x[((size_t)n * C + cc) * Sp + i]; acc += v * v; }
+          const size_t at = ((size_t)n * C + c) * Sp + i;
+          const double sc = k + acc * alpha / size;
+          scale[at] = (float)sc;
+          y[at] = (float)(x[at] * std::pow(sc, -(double)beta));
+        }
+  });
+  return B2C_OK;
+}
+int b2c_lrn_backward(int N, int C, int Sp, int size, float alpha, float beta, const float* x, const float* y, const float* scale, const float* dy,
+                     float* dx, void* stream) {
+  fakecuda_launch(S(stream), [=] {
+    const int ipp = size - (size + 1) / 2;                    // inverse_pre_pad, lrn_layer.cpp CrossChannelBackward_cpu
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < C; ++c)
+        for (int i = 0; i < Sp; ++i) {
+          const size_t at = ((size_t)n * C + c) * Sp + i;
+          double acc = 0;
+          for (int cc = std::max(c - ipp, 0); cc < std::min(c - ipp + size, C); ++cc) {
+            const size_t o = ((size_t)n * C + cc) * Sp + i;
+            acc += (double)dy[o] * y[o] / scale[o];
+          }
+          dx[at] = (float)(dy[at] * std::pow((double)scale[at], -(double)beta) - 2.0 * alpha * beta / size * x[at] * acc);
+        }
+  });
+  return B2C_OK;
+}
+int b2c_dropout_mask(size_t n, float ratio, unsigned long long seed, unsigned long long offset, float* mask, void* stream) {
+  fakecuda_launch(S(stream), [=] {
+    const unsigned thr = (unsigned)(int)((double)ratio * 16777216.0);
+    const float keep = 1.f / (1.f - ratio);
+    for (size_t i = 0; i < n; ++i) {
+      unsigned long long z = seed + offset + i + 0x9E3779B97F4A7C15ull;          // splitmix64
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      mask[i] = (unsigned)(z >> 40) >= thr ? keep : 0.f;
+    }
+  });
+  return B2C_OK;
+}
+int b2c_mul(size_t n, const float* a, const float* b, float* y, void* stream) {
+  fakecuda_launch(S(stream), [=] { for (size_t i = 0; i < n; ++i) y[i] = a[i] * b[i]; });
+  return B2C_OK;
+}
+// the label must be among the top_k of (score, class) pairs ordered by std::greater (accuracy_layer.cpp:44-100)
+int b2c_accuracy(int N, int C, int top_k, const float* scores, const float* labels, float* accuracy, void*, void* stream) {
+  fakecuda_launch(S(stream), [=] {
+    int hits = 0;
+    for (int n = 0; n < N; ++n) {
+      const int lab = (int)labels[n];
+      const float s = scores[(size_t)n * C + lab];
+      int better = 0;
+      for (int c = 0; c < C; ++c) { const float v = scores[(size_t)n * C + c]; if (v > s || (v == s && c > lab)) ++better; }
+      hits += better < top_k;
+    }
+    *accuracy = (float)hits / N;
+  });
+  return B2C_OK;
+}
+
+}  // extern "C"

@@ -328,3 +328,38 @@ def test_iter_size_accumulation_equals_one_pass_on_the_cpu(sim_host, rng):
     assert abs(l1 - l2) <= 1e-5 * abs(l1)
     for i in range(len(vals)):
         assert rel(p2[i], p1[i]) <= 1e-5 and rel(h2[i], h1[i], 1e-6) <= 1e-4, shapes[i]
+
+
+def test_inception_style_net_matches_the_net_oracle_on_the_cpu(sim_host, rng):
+    """tests/test_trainer_gpu.py::test_inception_style_net_matches_oracle on the host stand-ins: grouped convolution, LRN, an inception
+    module joined by Concat (strided 2-D copies), an auxiliary classifier with Dropout and loss_weight 0.3, the main classifier
+    behind Dropout -- both losses, blobs on every branch, every parameter gradient, then two Solver::Step iterations with the dropout
+    streams advancing, under a lazy side stream."""
+    import oracle
+    from test_trainer_gpu import make_trainer, rel
+    L = sim_host.lib()
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_set_all_eager(0)
+    spec = no.mini_inception()
+    t, params, data, label = make_trainer(spec, rng)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss)
+    assert abs(float(t.get_blob("aux/loss1")[0]) - float(v["aux/loss1"])) <= 1e-4 * abs(float(v["aux/loss1"]))
+    for name in ("conv1", "norm1", "pool1", "inc/3x3", "inc/5x5", "inc/pool_proj", "inc/output", "aux/fc", "pool5", "cls"):
+        assert rel(t.get_blob(name), v[name]) <= 1e-4, name
+    for name in ("cls", "aux/cls", "inc/output", "pool1", "norm1"):
+        assert rel(t.get_blob(name, diff=True), d[name]) <= 1e-4, name
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g, floor) <= 1e-4, no.param_shapes(spec)[i]
+    t.clear_param_diffs()
+    p, h = [q.copy() for q in params], [np.zeros_like(q) for q in params]
+    for it in range(2):
+        _, g, _, _ = no.forward_backward(spec, p, data, label, iteration=it + 1)
+        for i in range(len(p)):
+            _, w, hh = oracle.sgd_update(g[i], p[i], h[i], 0.9, 0.05, 0.0005)
+            p[i], h[i] = w.reshape(p[i].shape), hh.reshape(p[i].shape)
+        t.step(1)
+    for i in range(len(p)):
+        assert rel(t.get_param(i, 0), p[i]) <= 2e-4, i
