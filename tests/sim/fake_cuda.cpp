@@ -18,6 +18,7 @@
 #include <deque>
 #include <functional>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <vector>
 
@@ -29,11 +30,21 @@ struct Event {
   unsigned long long done = 0;                                  // latest generation that has executed
   std::map<unsigned long long, std::pair<Stream*, size_t>> at;  // generation -> (stream, absolute op index of its record op)
 };
+// A collective over several streams (tests/sim/fake_comm.cpp: the allreduce of N in-process "ranks"): one COLLECTIVE op per rank,
+// on that rank's stream.  It can run only when every rank's op has reached the FRONT of its stream -- everything each rank enqueued
+// before it has executed -- and then runs once, for all ranks; the other ranks' ops complete as no-ops.
+struct Collective {
+  std::vector<char> enqueued;
+  std::vector<std::pair<Stream*, size_t>> where;                // per rank: stream and absolute index of its op
+  std::function<void()> run;
+  bool done = false;
+};
 struct Op {
-  enum Kind { EXEC, RECORD, WAIT } kind = EXEC;
+  enum Kind { EXEC, RECORD, WAIT, COLLECTIVE } kind = EXEC;
   std::function<void()> fn;
   Event* ev = nullptr;
   unsigned long long gen = 0;
+  std::shared_ptr<Collective> coll;
 };
 struct Stream {
   std::deque<Op> q;
@@ -50,7 +61,12 @@ Event* E(cudaEvent_t e) { return reinterpret_cast<Event*>(e); }
 
 void force(Stream* s, size_t upto_abs);     // run everything on s with absolute index < upto_abs
 
-bool runnable(const Op& op) { return op.kind != Op::WAIT || op.ev->done >= op.gen; }
+bool collective_ready(const Collective& c);
+bool runnable(const Op& op) {
+  if (op.kind == Op::WAIT) return op.ev->done >= op.gen;
+  if (op.kind == Op::COLLECTIVE) return op.coll->done || collective_ready(*op.coll);
+  return true;
+}
 
 void run_front(Stream* s) {
   Op op = std::move(s->q.front());
@@ -59,6 +75,12 @@ void run_front(Stream* s) {
   ++g_executed;
   if (op.kind == Op::EXEC) op.fn();
   else if (op.kind == Op::RECORD) { if (op.ev->done < op.gen) op.ev->done = op.gen; }
+  else if (op.kind == Op::COLLECTIVE && !op.coll->done) { op.coll->done = true; op.coll->run(); }
+}
+bool collective_ready(const Collective& c) {
+  for (size_t r = 0; r < c.where.size(); ++r)
+    if (!c.enqueued[r] || c.where[r].first->base != c.where[r].second) return false;
+  return true;
 }
 
 void progress() {                            // eager streams run as far as their dependencies allow
@@ -80,6 +102,16 @@ void force(Stream* s, size_t upto_abs) {
   while (s->base < upto_abs && !s->q.empty()) {
     Op& op = s->q.front();
     if (op.kind == Op::WAIT && op.ev->done < op.gen) { force_event(op.ev, op.gen); continue; }   // re-read the queue: it may have moved
+    if (op.kind == Op::COLLECTIVE && !op.coll->done && !collective_ready(*op.coll)) {
+      // bring every other rank up to its own op of this collective; a rank that has not even enqueued it means the host program
+      // synchronised on one rank before launching the others -- a deadlock on real hardware too
+      std::shared_ptr<Collective> c = op.coll;
+      for (size_t r = 0; r < c->where.size(); ++r) {
+        if (!c->enqueued[r]) throw std::runtime_error("fake_cuda: collective waits for a rank that has not enqueued it (host-side deadlock)");
+        if (c->where[r].first != s) force(c->where[r].first, c->where[r].second);
+      }
+      continue;
+    }
     run_front(s);
     progress();
   }
@@ -106,6 +138,17 @@ extern "C" unsigned long long fakecuda_executed() { return g_executed; }
 extern "C" unsigned long long fakecuda_pending() { unsigned long long n = 0; for (Stream* s : g_streams) n += s->q.size(); return n; }
 // enqueue an arbitrary "kernel" (used by the fake b2c_transform_u8)
 void fakecuda_launch(cudaStream_t st, std::function<void()> fn) { push_exec(st, std::move(fn)); }
+// one rank's part of a collective over `nranks` streams; `run` (taken from the first caller) executes it once for all ranks
+std::shared_ptr<void> fakecuda_collective(cudaStream_t st, std::shared_ptr<void> handle, int nranks, int rank, std::function<void()> run) {
+  std::shared_ptr<Collective> c = handle ? std::static_pointer_cast<Collective>(handle) : std::make_shared<Collective>();
+  if (c->where.empty()) { c->enqueued.assign(nranks, 0); c->where.assign(nranks, {nullptr, 0}); c->run = std::move(run); }
+  Stream* s = S(st);
+  c->enqueued[rank] = 1;
+  c->where[rank] = {s, s->base + s->q.size()};
+  Op op; op.kind = Op::COLLECTIVE; op.coll = c;
+  push(s, std::move(op));
+  return c;
+}
 
 // ---- the runtime entry points the host layer uses -----------------------------------------------------------------------------------
 extern "C" {

@@ -94,6 +94,23 @@ int sim_transform_log(unsigned long long* out, int cap, int clear) {
   if (clear) g_transform_log.clear();
   return n;
 }
+// Several "ranks" in one process: each gets its own compute stream (Caffe::thread_stream() is what every layer launches on); call
+// before creating / stepping that rank's trainer.  rank < 0 goes back to the legacy stream.
+static std::vector<cudaStream_t>& rank_streams() { static std::vector<cudaStream_t> v; return v; }
+int sim_use_rank_stream(int rank) {
+  std::vector<cudaStream_t>& streams = rank_streams();
+  if (rank < 0) { Caffe::set_thread_stream(nullptr); return 0; }
+  while ((int)streams.size() <= rank) { cudaStream_t s = nullptr; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); streams.push_back(s); }
+  Caffe::set_thread_stream(streams[rank]);
+  return 0;
+}
+extern "C" void fakecuda_set_eager(cudaStream_t st, int eager);
+void sim_set_rank_stream_eager(int rank, int eager) {
+  if (rank >= 0 && rank < (int)rank_streams().size()) fakecuda_set_eager(rank_streams()[rank], eager);
+}
+// P2PSync's constructor sets the process-wide solver count (one process is one rank in the product); a test that afterwards runs a
+// single solver in the same process puts it back.
+void sim_set_solver_count(int n) { Caffe::set_solver_count(n); Caffe::set_root_solver(true); }
 long long sim_batches(void* hv) { return (long long)static_cast<SimHandle*>(hv)->layer->batches_loaded(); }
 
 }  // extern "C"

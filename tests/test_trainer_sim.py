@@ -363,3 +363,73 @@ def test_inception_style_net_matches_the_net_oracle_on_the_cpu(sim_host, rng):
         t.step(1)
     for i in range(len(p)):
         assert rel(t.get_param(i, 0), p[i]) <= 2e-4, i
+
+
+# ---- N data-parallel solvers in one process: the product's P2PSync + ReduceScheduler over tests/sim/fake_comm.cpp ------------------------------
+@pytest.mark.parametrize("mode", sorted(STEP_MODES))
+@pytest.mark.parametrize("world", [2, 3])
+def test_n_solvers_equal_one_solver_on_the_full_batch_on_the_cpu(sim_host, world, mode):
+    """The reference's multi-device check (test_gradient_based_solver.cpp:471-509; tests/test_multi_gpu.py on hardware): `world`
+    TrainNets, each with its own compute stream, comm stream and P2PSync, train LeNet on their slices of a fixed global batch
+    through the bucketed allreduce + fused update of the C++ ReduceScheduler; the allreduce is a collective of the stream-order
+    model that completes only when every rank's comm stream has reached it.  (a) every rank ends with the same bits; (b) they equal
+    one solver on the whole batch within 1e-5; (c) the mean of the per-rank losses is the one solver's loss.  Each combination of
+    lazy / eager compute and side streams must give this, and rank 0's weights must have replaced the others' at on_start."""
+    import multi_rank_worker as mw
+    L = sim_host.lib()
+    L.sim_use_rank_stream.argtypes = [C.c_int]
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_set_eager.argtypes = [C.c_void_p, C.c_int]
+    L.fakecuda_set_all_eager(0)
+    global_batch, steps = 6 * world, 3
+    params, data, label = mw.build_case(global_batch)
+    per = global_batch // world
+    L.sim_use_rank_stream(-1)
+    L.sim_set_solver_count.argtypes = [C.c_int]
+    L.sim_set_solver_count(1)                                                  # (an earlier case's P2PSync left the process at `world`)
+    one = mw.run(global_batch, params, data, label, steps)                    # one solver, the whole batch
+    try:
+        ranks = []
+        uid = None
+        for r in range(world):
+            L.sim_use_rank_stream(r)
+            t = sim_host.Trainer(no.to_prototxt(no.lenet(batch=per)), mw.SOLVER, num_classes=10)
+            for i, p in enumerate(params):
+                t.set_param(i, p if r == 0 else p + np.float32(0.5 + r))       # only rank 0 holds the right weights: on_start broadcasts them
+            if r == 0:
+                uid = t.new_unique_id()
+            t.attach_sync(world, r, uid)
+            t.set_blob("data", data[r * per:(r + 1) * per])
+            t.set_blob("label", label[r * per:(r + 1) * per])
+            ranks.append(t)
+        compute_eager, side_eager = STEP_MODES[mode]
+        L.fakecuda_set_all_eager(side_eager)
+        L.sim_set_rank_stream_eager.argtypes = [C.c_int, C.c_int]
+        for r in range(world):                                                  # the ranks' compute streams: lazy or eager as the mode says
+            L.sim_set_rank_stream_eager(r, compute_eager)
+        losses = [[] for _ in range(world)]
+        for k in range(steps):
+            for r, t in enumerate(ranks):                                       # every rank enqueues its iteration ...
+                L.sim_use_rank_stream(r)
+                t.step(1)
+            for r, t in enumerate(ranks):                                       # ... before anybody looks at a result
+                L.sim_use_rank_stream(r)
+                losses[r].append(t.loss())
+        out = []
+        for r, t in enumerate(ranks):
+            L.sim_use_rank_stream(r)
+            out.append(([t.get_param(i, 0) for i in range(len(params))], [t.get_param(i, 2) for i in range(len(params))]))
+    finally:
+        L.sim_use_rank_stream(-1)
+        L.fakecuda_set_all_eager(0)
+        L.sim_set_solver_count(1)
+    n = len(params)
+    hfloor = 1e-3 * max(float(np.abs(one[f"h{j}"]).max()) for j in range(n))
+    for i in range(n):
+        for r in range(1, world):
+            assert np.array_equal(out[0][0][i].view(np.uint32), out[r][0][i].view(np.uint32)), f"param {i} differs on rank {r}"
+            assert np.array_equal(out[0][1][i].view(np.uint32), out[r][1][i].view(np.uint32)), f"history {i} differs on rank {r}"
+        ref = one[f"p{i}"]
+        assert float(np.abs(out[0][0][i].astype(np.float64) - ref).max()) / max(float(np.abs(ref).max()), 1e-20) < 1e-5, i
+        assert float(np.abs(out[0][1][i] - one[f"h{i}"]).max()) / max(float(np.abs(one[f"h{i}"]).max()), hfloor) < 1e-4, i
+    np.testing.assert_allclose(np.mean(losses, axis=0), one["losses"], rtol=1e-5)
