@@ -433,3 +433,55 @@ def test_n_solvers_equal_one_solver_on_the_full_batch_on_the_cpu(sim_host, world
         assert float(np.abs(out[0][0][i].astype(np.float64) - ref).max()) / max(float(np.abs(ref).max()), 1e-20) < 1e-5, i
         assert float(np.abs(out[0][1][i] - one[f"h{i}"]).max()) / max(float(np.abs(one[f"h{i}"]).max()), hfloor) < 1e-4, i
     np.testing.assert_allclose(np.mean(losses, axis=0), one["losses"], rtol=1e-5)
+
+
+def test_two_solvers_on_their_stripes_of_a_database_equal_one_solver_on_the_cpu(sim_host, tmp_path, monkeypatch):
+    """The whole data-parallel path in one test: two ranks, each reading ITS stripe of the same LMDB (DataLayer <- P2PSync's rank,
+    CursorManager's partition), forward / backward, bucketed allreduce, fused update -- against one solver with twice the batch
+    reading the database front to back.  Rank r's batch k is records [2Bk + rB, 2Bk + (r + 1)B): the two batches side by side ARE the
+    one solver's batch k, so four iterations must leave the same weights (1e-5) -- and the same bits on both ranks."""
+    from caffe_mpi_b200 import lmdb_io
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim_host.lib()
+    for fn, at in (("sim_use_rank_stream", [C.c_int]), ("fakecuda_set_all_eager", [C.c_int]), ("sim_set_solver_count", [C.c_int])):
+        getattr(L, fn).argtypes = at
+    L.fakecuda_set_all_eager(0)
+    L.sim_use_rank_stream(-1)
+    L.sim_set_solver_count(1)
+    rng = np.random.default_rng(3)
+    n, B, steps = 44, 3, 4                                             # 44 records, global batch 6: iteration 8 would wrap; 4 do not
+    imgs = rng.integers(0, 256, (n, 3, 5, 5), dtype=np.uint8)
+    path = str(tmp_path / "db")
+    lmdb_io.write_datum_lmdb(path, imgs, rng.integers(0, 10, n))
+    net = lambda batch: DB_NET.format(src=path, B=batch, dp="", tp="scale: 0.0078125")
+    one = sim_host.Trainer(net(2 * B), SOLVER, num_classes=10)
+    w0, b0 = one.get_param(0).copy(), one.get_param(1).copy()
+    one.step(steps, copy_input=True)
+    want = [one.get_param(0), one.get_param(1), one.get_param(0, 2), one.get_param(1, 2)]
+    assert one.database_batches() == steps
+    try:
+        ranks, uid = [], None
+        for r in range(2):
+            L.sim_use_rank_stream(r)
+            t = sim_host.Trainer(net(B), SOLVER, num_classes=10, seed=50 + r)
+            t.set_param(0, w0)
+            t.set_param(1, b0)
+            if r == 0:
+                uid = t.new_unique_id()
+            t.attach_sync(2, r, uid)
+            ranks.append(t)
+        for _ in range(steps):
+            for r, t in enumerate(ranks):
+                L.sim_use_rank_stream(r)
+                t.step(1, copy_input=True)
+        got = []
+        for r, t in enumerate(ranks):
+            L.sim_use_rank_stream(r)
+            got.append([t.get_param(0), t.get_param(1), t.get_param(0, 2), t.get_param(1, 2)])
+            assert t.database_batches() == steps
+    finally:
+        L.sim_use_rank_stream(-1)
+        L.sim_set_solver_count(1)
+    for a, b, ref in zip(got[0], got[1], want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.abs(a.astype(np.float64) - ref).max() <= 1e-5 * max(float(np.abs(ref).max()), 1e-3)
