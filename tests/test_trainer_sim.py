@@ -123,7 +123,7 @@ def test_snapshot_restore_and_finetune_round_trip_on_the_host_side(sim_host, tmp
 
 
 def test_trainer_setup_and_snapshot_code_is_clean_under_sanitizers(tmp_path):
-    """tests/sim/trainer_stress.cpp: ResNet-50 and GoogLeNet built through the C handle API under AddressSanitizer + UBSan,
+    """tests/sim/trainer_stress.cpp: ResNet-50 built through the C handle API under AddressSanitizer + UBSan,
     every parameter and history blob written, snapshotted, restored into a second trainer and compared, then fine-tuned from."""
     capi.lib()
     r = subprocess.run(["make", "-C", os.path.join(HERE, "sim"), "trainer_stress"], capture_output=True, text=True)
@@ -132,7 +132,7 @@ def test_trainer_setup_and_snapshot_code_is_clean_under_sanitizers(tmp_path):
             pytest.skip("toolchain has no sanitizer runtime: " + r.stderr[-300:])
         pytest.fail("tests/sim/trainer_stress does not build:\n" + r.stdout[-1000:] + r.stderr[-3000:])
     paths = []
-    for name in ("resnet50", "googlenet"):                    # (AlexNet's 37 M-float fc6 triples the run time and adds no code path)
+    for name in ("resnet50",):                                # (GoogLeNet / AlexNet add run time, not code paths: they are built un-sanitised above)
         p = tmp_path / (name + ".prototxt")
         p.write_text(models.PROTOTXT[name](2))
         paths.append(str(p))
