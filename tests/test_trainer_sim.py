@@ -485,3 +485,64 @@ def test_two_solvers_on_their_stripes_of_a_database_equal_one_solver_on_the_cpu(
     for a, b, ref in zip(got[0], got[1], want):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
         assert np.abs(a.astype(np.float64) - ref).max() <= 1e-5 * max(float(np.abs(ref).max()), 1e-3)
+
+
+# ---- the synthetic data layer's prefetch: what bench.py's end-to-end steps feed the net ------------------------------------------------------------
+def _splitmix64(z):
+    z = (z + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+@pytest.mark.parametrize("mode", sorted(STEP_MODES))
+def test_synthetic_datum_source_prefetch_delivers_its_own_batches(sim_host, mode):
+    """bench.py's e2e path: SyntheticDataLayer in datum mode (a pinned batch of uint8 datums, crop + 32 on a side; every step the next
+    batch's bytes and crop / mirror draws cross on the copy stream into the other of two device slots while the current step computes).
+    Nothing on hardware checks WHAT those steps train on; here every batch the net sees is recomputed from the layer's documented
+    generator (host/train_net.cpp: splitmix64 bytes, draws rand % extent) under each extreme stream order."""
+    from oracle import layers_oracle as lo
+    L = sim_host.lib()
+    for fn, at in (("sim_use_rank_stream", [C.c_int]), ("fakecuda_set_all_eager", [C.c_int]), ("fakecuda_set_eager", [C.c_void_p, C.c_int]),
+                   ("sim_set_solver_count", [C.c_int])):
+        getattr(L, fn).argtypes = at
+    L.sim_use_rank_stream(-1)
+    L.sim_set_solver_count(1)
+    L.fakecuda_set_all_eager(0)
+    N, Cc, crop, seed, scale = 3, 3, 5, 1701, 0.5
+    mean = [104.0, 117.0, 123.0]
+    net = ('name: "syn" layer { name: "data" type: "Data" top: "data" top: "label" data_param { source: "synthetic" batch_size: %d backend: LMDB }\n'
+           '  transform_param { crop_size: %d mirror: true scale: %g mean_value: 104 mean_value: 117 mean_value: 123 } }\n'
+           'layer { name: "ip" type: "InnerProduct" bottom: "data" top: "ip" inner_product_param { num_output: 10 weight_filler { type: "gaussian" std: 0.01 } } }\n'
+           'layer { name: "loss" type: "SoftmaxWithLoss" bottom: "ip" bottom: "label" top: "loss" }\n') % (N, crop, scale)
+    t = sim_host.Trainer(net, SOLVER, num_classes=10, seed=seed)
+    compute_eager, side_eager = STEP_MODES[mode]
+    L.fakecuda_set_all_eager(side_eager)
+    L.fakecuda_set_eager(None, compute_eager)
+    Hd = crop + 32
+    nbytes = N * Cc * Hd * Hd
+    raw = bytearray(nbytes)
+    for i in range(0, nbytes, 8):                             # "uniform bytes, 8 per draw"
+        r = _splitmix64((seed * 0x100000001B3 + i) & 0xFFFFFFFFFFFFFFFF)
+        for k in range(min(8, nbytes - i)):
+            raw[i + k] = (r >> (8 * k)) & 0xFF
+    datums = np.frombuffer(bytes(raw), np.uint8).reshape(N, Cc, Hd, Hd)
+
+    def batch(draw):                                           # the draw-th batch since construction (set-up loaded batch 0)
+        ho, wo, mir = np.zeros(N, np.int32), np.zeros(N, np.int32), np.zeros(N, np.uint8)
+        for i in range(N):
+            base = (draw * N + i) * 3
+            r0, r1, r2 = ((_splitmix64((seed + base + k) & 0xFFFFFFFFFFFFFFFF) >> 33) + 1 for k in range(3))
+            mir[i], ho[i], wo[i] = r0 % 2, r1 % (Hd - crop + 1), r2 % (Hd - crop + 1)
+        return lo.transform_u8(datums, (crop, crop), ho, wo, mir, mean, None, scale)
+
+    assert np.array_equal(t.get_blob("data").reshape(N, Cc, crop, crop), batch(0))          # the resident batch of the non-e2e steps
+    draw = 1                                                   # set-up also issued the prefetch of batch 1
+    for step in range(9):
+        t.step(1, copy_input=True)
+        if step % 4 != 2:
+            assert np.array_equal(t.get_blob("data").reshape(N, Cc, crop, crop), batch(draw)), (mode, step)
+        draw += 1
+    t.step(2, copy_input=False)                                # device-only steps keep the last batch
+    assert np.array_equal(t.get_blob("data").reshape(N, Cc, crop, crop), batch(draw - 1))
+    L.fakecuda_set_all_eager(0)
