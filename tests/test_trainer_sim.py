@@ -546,3 +546,31 @@ def test_synthetic_datum_source_prefetch_delivers_its_own_batches(sim_host, mode
     t.step(2, copy_input=False)                                # device-only steps keep the last batch
     assert np.array_equal(t.get_blob("data").reshape(N, Cc, crop, crop), batch(draw - 1))
     L.fakecuda_set_all_eager(0)
+
+
+@pytest.mark.parametrize("switches", [dict(B2C_FUSE_RES="0"), dict(B2C_FUSE_SPLIT="0"), dict(B2C_FUSE_FANOUT="1"), dict(B2C_FUSE_FANOUT="1", B2C_FUSE_RES="0"),
+                                      dict(B2C_FUSE="0", B2C_FUSE_FANOUT="1")], ids=lambda d: ",".join("%s=%s" % kv for kv in sorted(d.items())))
+def test_graph_switches_leave_the_arithmetic_alone_on_the_cpu(sim_host, rng, monkeypatch, switches):
+    """DESIGN.md 7a's TrainNet switches (residual-tail fusion, the shadow-diff add inside the residual backward, conv data gradients
+    adding straight into a fan-out blob's diff): whichever way the graph is rewritten, loss, gradients and three SGD steps of the
+    bottleneck ResNet are the net oracle's."""
+    from test_trainer_gpu import make_trainer, rel
+    L = sim_host.lib()
+    L.fakecuda_set_all_eager.argtypes = [C.c_int]
+    L.fakecuda_set_all_eager(0)
+    for k, v in switches.items():
+        monkeypatch.setenv(k, v)
+    spec = no.mini_resnet()
+    t, params, data, label = make_trainer(spec, rng)
+    loss = t.forward_backward()
+    ref_loss, grads, v, d = no.forward_backward(spec, params, data, label)
+    assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss)
+    floor = 1e-3 * max(float(np.max(np.abs(g))) for g in grads)
+    for i, g in enumerate(grads):
+        assert rel(t.get_param(i, 1), g, floor) <= 1e-3, (switches, no.param_shapes(spec)[i])
+    t.clear_param_diffs()
+    ref_losses, ref_params, _ = no.sgd_steps(spec, params, data, label, 3, 0.05, 0.9, 0.0005)
+    t.step(3)
+    assert abs(t.loss() - ref_losses[2]) <= 2e-4 * abs(ref_losses[2])
+    for i, p in enumerate(ref_params):
+        assert rel(t.get_param(i, 0), p) <= 2e-4, (switches, i)
