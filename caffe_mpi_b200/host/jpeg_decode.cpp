@@ -171,13 +171,15 @@ struct Component {
   int bw = 0, bh = 0;                 // blocks allocated (MCU-padded)
   int pred = 0;
   std::vector<uint8_t> plane;         // (bw * 8) x (bh * 8)
+  std::vector<int16_t> coef;          // progressive files: every block's 64 coefficients (natural order), built up scan by scan
 };
 
 struct Decoder {
   const uint8_t* p;
   const uint8_t* end;
   int W = 0, H = 0, ncomp = 0, maxh = 1, maxv = 1, mcux = 0, mcuy = 0, restart_interval = 0;
-  bool have_sof = false, adobe = false;
+  bool have_sof = false, adobe = false, progressive = false;
+  int eobrun = 0;
   int adobe_transform = -1;
   uint16_t quant[4][64];
   bool have_quant[4] = {false, false, false, false};
@@ -213,8 +215,9 @@ struct Decoder {
       h.build();
     }
   }
-  void read_sof(int len) {
+  void read_sof(int len, bool prog) {
     if (have_sof) bad("more than one frame header");
+    progressive = prog;
     if (u8() != 8) bad("only 8-bit samples are built");
     H = u16(); W = u16(); ncomp = u8();
     if (H <= 0 || W <= 0) bad("empty image");
@@ -237,6 +240,7 @@ struct Decoder {
       c.hh = (H * c.v + maxv - 1) / maxv;
       c.bw = mcux * c.h; c.bh = mcuy * c.v;
       c.plane.assign((size_t)c.bw * 8 * c.bh * 8, 0);
+      if (progressive) c.coef.assign((size_t)c.bw * c.bh * 64, 0);
     }
     have_sof = true;
   }
@@ -276,6 +280,123 @@ struct Decoder {
     br.p += 2;
     *next_rst = (*next_rst + 1) & 7;
     for (int i = 0; i < ncomp; ++i) comp[i].pred = 0;
+    eobrun = 0;
+  }
+
+  // ---- progressive scans (T.81 Annex G; libjpeg jdphuff.c) ----------------------------------------------------------------------------
+  void prog_dc(BitReader& br, Component& c, int16_t* blk, int ah, int al) {
+    if (ah == 0) {                                    // first pass: the DC difference, scaled by the point transform
+      const int t = br.decode(dc[c.td]);
+      if (t > 15) bad("corrupt DC coefficient");
+      c.pred += t ? extend(br.get(t), t) : 0;
+      if (c.pred < -32768 || c.pred > 32767) bad("corrupt DC coefficient");
+      blk[0] = (int16_t)(c.pred * (1 << al));
+    } else if (br.get(1)) {                           // refinement: one more bit of every DC value
+      blk[0] = (int16_t)(blk[0] | (1 << al));
+    }
+  }
+  void prog_ac_first(BitReader& br, const Huff& h, int16_t* blk, int ss, int se, int al) {
+    if (eobrun > 0) { --eobrun; return; }
+    for (int k = ss; k <= se; ++k) {
+      const int rs = br.decode(h), r = rs >> 4, s = rs & 15;
+      if (s) {
+        k += r;
+        if (k > 63) bad("corrupt AC coefficient run");
+        blk[kZigzag[k]] = (int16_t)(extend(br.get(s), s) * (1 << al));
+      } else if (r == 15) {
+        k += 15;                                      // ZRL: sixteen zeros
+      } else {                                        // EOBr: this band ends here in the next 2^r + extra - 1 blocks too
+        eobrun = 1 << r;
+        if (r) eobrun += br.get(r);
+        --eobrun;
+        break;
+      }
+    }
+  }
+  void prog_ac_refine(BitReader& br, const Huff& h, int16_t* blk, int ss, int se, int al) {
+    const int p1 = 1 << al, m1 = -(1 << al);
+    int k = ss;
+    if (eobrun == 0) {
+      for (; k <= se; ++k) {
+        const int rs = br.decode(h);
+        int r = rs >> 4;
+        const int s = rs & 15;
+        int value = 0;
+        if (s) {
+          if (s != 1) bad("corrupt AC refinement");
+          value = br.get(1) ? p1 : m1;                // a coefficient that becomes non-zero in this pass
+        } else if (r != 15) {
+          eobrun = 1 << r;
+          if (r) eobrun += br.get(r);
+          break;                                      // the rest of the block only gets correction bits (below)
+        }
+        // skip r still-zero coefficients, handing a correction bit to every already non-zero one on the way
+        while (k <= se) {
+          int16_t& cf = blk[kZigzag[k]];
+          if (cf != 0) {
+            if (br.get(1) && (cf & p1) == 0) cf = (int16_t)(cf + (cf >= 0 ? p1 : m1));
+          } else {
+            if (--r < 0) break;
+          }
+          ++k;
+        }
+        if (s) {
+          if (k > 63) bad("corrupt AC refinement");
+          blk[kZigzag[k]] = (int16_t)value;
+        }
+      }
+    }
+    if (eobrun > 0) {
+      for (; k <= se; ++k) {
+        int16_t& cf = blk[kZigzag[k]];
+        if (cf != 0 && br.get(1) && (cf & p1) == 0) cf = (int16_t)(cf + (cf >= 0 ? p1 : m1));
+      }
+      --eobrun;
+    }
+  }
+  void read_sos_progressive(Component** sc, int ns, int ss, int se, int ah, int al) {
+    if (ss > se || se > 63 || ah > 13 || al > 13 || (ss == 0 && se != 0) || (ss > 0 && ns != 1)) bad("bad progressive scan parameters");
+    for (int i = 0; i < ncomp; ++i) comp[i].pred = 0;
+    eobrun = 0;
+    BitReader br{p, end};
+    int next_rst = 0;
+    long done = 0;
+    auto one = [&](Component& c, int bx, int by) {
+      int16_t* blk = c.coef.data() + ((size_t)by * c.bw + bx) * 64;
+      if (ss == 0) prog_dc(br, c, blk, ah, al);
+      else if (ah == 0) prog_ac_first(br, ac[c.ta], blk, ss, se, al);
+      else prog_ac_refine(br, ac[c.ta], blk, ss, se, al);
+    };
+    if (ns == 1) {
+      Component& c = *sc[0];
+      const int nbx = (c.w + 7) / 8, nby = (c.hh + 7) / 8;
+      for (int by = 0; by < nby; ++by)
+        for (int bx = 0; bx < nbx; ++bx) {
+          if (restart_interval && done && done % restart_interval == 0) restart(br, &next_rst);
+          one(c, bx, by);
+          ++done;
+        }
+    } else {
+      for (int my = 0; my < mcuy; ++my)
+        for (int mx = 0; mx < mcux; ++mx) {
+          if (restart_interval && done && done % restart_interval == 0) restart(br, &next_rst);
+          for (int i = 0; i < ns; ++i)
+            for (int by = 0; by < sc[i]->v; ++by)
+              for (int bx = 0; bx < sc[i]->h; ++bx) one(*sc[i], mx * sc[i]->h + bx, my * sc[i]->v + by);
+          ++done;
+        }
+    }
+    p = br.p;
+    while (p < end && *p != 0xFF) ++p;
+  }
+  void finish_progressive() {                          // all scans are in: dequantise + inverse DCT of every block
+    for (int i = 0; i < ncomp; ++i) {
+      Component& c = comp[i];
+      if (!have_quant[c.tq]) bad("component uses a quantisation table that was not defined");
+      for (int by = 0; by < c.bh; ++by)
+        for (int bx = 0; bx < c.bw; ++bx)
+          idct_islow(c.coef.data() + ((size_t)by * c.bw + bx) * 64, quant[c.tq], c.plane.data() + ((size_t)by * 8 * c.bw + bx) * 8, c.bw * 8);
+    }
   }
 
   void read_sos(int len) {
@@ -289,10 +410,15 @@ struct Decoder {
       for (int k = 0; k < ncomp; ++k) if (comp[k].id == id) sc[i] = &comp[k];
       if (!sc[i]) bad("scan names an unknown component");
       sc[i]->td = tt >> 4; sc[i]->ta = tt & 15;
-      if (sc[i]->td > 3 || sc[i]->ta > 3 || !dc[sc[i]->td].present || !ac[sc[i]->ta].present) bad("scan uses a Huffman table that was not defined");
-      if (!have_quant[sc[i]->tq]) bad("component uses a quantisation table that was not defined");
+      if (sc[i]->td > 3 || sc[i]->ta > 3) bad("scan uses a Huffman table that was not defined");
     }
     const int ss = u8(), se = u8(), ahal = u8();
+    for (int i = 0; i < ns; ++i) {
+      const bool need_dc = !progressive || (ss == 0 && (ahal >> 4) == 0), need_ac = !progressive || ss > 0;
+      if ((need_dc && !dc[sc[i]->td].present) || (need_ac && !ac[sc[i]->ta].present)) bad("scan uses a Huffman table that was not defined");
+      if (!progressive && !have_quant[sc[i]->tq]) bad("component uses a quantisation table that was not defined");
+    }
+    if (progressive) { read_sos_progressive(sc, ns, ss, se, ahal >> 4, ahal & 15); return; }
     if (ss != 0 || se != 63 || ahal != 0) bad("progressive scan parameters in a sequential file");
     for (int i = 0; i < ncomp; ++i) comp[i].pred = 0;
     BitReader br{p, end};
@@ -341,8 +467,8 @@ struct Decoder {
       switch (m) {
         case 0xDB: read_dqt(len - 2); break;
         case 0xC4: read_dht(len - 2); break;
-        case 0xC0: case 0xC1: read_sof(len - 2); break;
-        case 0xC2: bad("progressive JPEG files are not built (re-encode the database as baseline, or store raw datums)");
+        case 0xC0: case 0xC1: read_sof(len - 2, false); break;
+        case 0xC2: read_sof(len - 2, true); break;
         case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
           bad("lossless / hierarchical / arithmetic-coded JPEG files are not built");
         case 0xDD: restart_interval = u16(); break;
@@ -355,6 +481,7 @@ struct Decoder {
       p = next;
     }
     if (!have_sof || !scans) bad("no image data");
+    if (progressive) finish_progressive();
   }
 };
 

@@ -32,6 +32,8 @@ def test_data_pipeline_host_code_is_clean_under_sanitizers(tmp_path, seed):
             (tmp_path / ("seed%d.jpg" % k)).write_bytes(enc.tobytes())
         ok, enc = cv2.imencode(".jpg", img[:, :, 0])
         (tmp_path / "seed3.jpg").write_bytes(enc.tobytes())
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 60])
+        (tmp_path / "seed4.jpg").write_bytes(enc.tobytes())              # progressive: refinement scans on damaged input
     except ImportError:
         pass
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")

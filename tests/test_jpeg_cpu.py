@@ -1,7 +1,7 @@
 """Encoded datums (convert_imageset --encoded): host/jpeg_decode.cpp against this image's cv2.imdecode -- OpenCV on libjpeg-turbo,
 i.e. what the reference's DecodeDatumToCVMat[Native] (src/caffe/util/io.cpp:167-190) calls.  Bit-exact, over sampling modes
 4:4:4 / 4:2:2 / 4:2:0, qualities 10..100, restart intervals, optimised Huffman tables, grayscale files, force_color, odd sizes
-down to 1x1, and files written by a second encoder (PIL); then a database of encoded datums through DataReader."""
+down to 1x1, progressive files, and files written by a second encoder (PIL); then a database of encoded datums through DataReader."""
 import io
 
 import numpy as np
@@ -64,10 +64,6 @@ def test_files_from_another_encoder():
             PIL.fromarray(_img(rng, h, w)[:, :, ::-1]).save(b, "JPEG", quality=int(rng.integers(20, 98)), subsampling=ss, optimize=bool(k % 2))
             assert _same(b.getvalue()), (h, w, ss)
     b = io.BytesIO()
-    PIL.fromarray(_img(rng, 32, 32)).save(b, "JPEG", progressive=True)
-    with pytest.raises(data_api.DataError, match="progressive"):
-        data_api.jpeg_decode(b.getvalue())
-    b = io.BytesIO()
     PIL.fromarray(_img(rng, 32, 32, 4), "CMYK").save(b, "JPEG")
     with pytest.raises(data_api.DataError, match="CMYK"):
         data_api.jpeg_decode(b.getvalue())
@@ -76,6 +72,28 @@ def test_files_from_another_encoder():
     ok, enc = cv2.imencode(".jpg", _img(rng, 48, 48))
     cut = enc.tobytes()[:len(enc) // 2]                                        # libjpeg pads a truncated scan with zeros and warns; so does this
     assert data_api.jpeg_decode(cut).shape == (3, 48, 48)
+
+
+def test_progressive_files_are_bit_identical_too():
+    """SOF2: spectral selection + successive approximation (DC / AC first and refinement scans, end-of-band runs), as written by
+    libjpeg's default progression script (PIL, cv2 IMWRITE_JPEG_PROGRESSIVE): ImageNet's original files, stored as they are by
+    `convert_imageset --encoded` without a resize, include them."""
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(21)
+    for k in range(40):
+        h, w = int(rng.integers(1, 100)), int(rng.integers(1, 100))
+        for ss in (0, 1, 2):
+            b = io.BytesIO()
+            PIL.fromarray(_img(rng, h, w)).save(b, "JPEG", quality=int(rng.integers(15, 98)), subsampling=ss, progressive=True, optimize=bool(k % 2))
+            assert _same(b.getvalue()), ("PIL progressive", h, w, ss)
+        b = io.BytesIO()
+        PIL.fromarray(_img(rng, h, w, 1)[:, :, 0]).save(b, "JPEG", progressive=True)
+        assert _same(b.getvalue()), ("progressive gray", h, w)
+        params = [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(10, 100))]
+        if k % 3 == 0:
+            params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 5))]
+        ok, enc = cv2.imencode(".jpg", _img(rng, h, w), params)
+        assert ok and _same(enc.tobytes()), ("cv2 progressive", h, w, params)
 
 
 def test_database_of_encoded_datums_feeds_the_reader(tmp_path):
