@@ -146,7 +146,7 @@ int b2h_blobproto_save(const char* path, int ndim, const int* shape, const float
 int b2h_jpeg_decode(const void* bytes, size_t n, int force_color, int* chw, unsigned char* out, size_t cap) {
   B2D_TRY({
     DecodedImage img;
-    DecodeJpeg(bytes, n, force_color != 0, &img);
+    DecodeImage(bytes, n, force_color != 0, &img);             // JPEG or PNG by signature (the name is historical)
     chw[0] = img.channels; chw[1] = img.height; chw[2] = img.width;
     if (out) {
       B2_CHECK(img.chw.size() <= cap, "b2h_jpeg_decode: buffer too small");

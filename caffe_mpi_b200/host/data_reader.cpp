@@ -26,8 +26,7 @@ namespace {
 // CVMatToDatum, io.cpp:167-230).  `img` is scratch that keeps the decoded pixels alive.
 void datum_pixels(const Datum& d, bool force_color, DecodedImage* img, const uint8_t** px, int* c, int* h, int* w) {
   if (d.encoded) {
-    B2_CHECK(LooksLikeJpeg(d.data, d.data_size), "encoded datum is not a JPEG file (PNG and other encodings are not built)");
-    DecodeJpeg(d.data, d.data_size, force_color, img);
+    DecodeImage(d.data, d.data_size, force_color, img);        // JPEG or PNG, by the file's own signature (cv::imdecode does the same)
     *px = img->chw.data(); *c = img->channels; *h = img->height; *w = img->width;
     return;
   }

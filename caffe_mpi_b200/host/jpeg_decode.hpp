@@ -34,4 +34,11 @@ bool LooksLikeJpeg(const void* bytes, size_t n);
 // reference goes on with "Could not decode datum"; a training run on holes is not something to continue).
 void DecodeJpeg(const void* bytes, size_t n, bool force_color, DecodedImage* out);
 
+// PNG (png_decode.cpp): 8-bit gray / RGB / RGBA / gray+alpha and palette images, non-interlaced; OpenCV's channel layouts
+// (gray -> 1, RGB -> B,G,R, with alpha -> B,G,R,A; force_color -> always B,G,R).
+bool LooksLikePng(const void* bytes, size_t n);
+void DecodePng(const void* bytes, size_t n, bool force_color, DecodedImage* out);
+// whichever of the two the bytes are; anything else is fatal
+void DecodeImage(const void* bytes, size_t n, bool force_color, DecodedImage* out);
+
 }  // namespace caffe

@@ -46,7 +46,7 @@ long long b2h_datum_serialize(int channels, int height, int width, const void* d
                               const float* float_data, int n_float, void* out, size_t cap);
 /* An ENCODED datum's image: DecodeDatumToCVMatNative / DecodeDatumToCVMat(force_color) (src/caffe/util/io.cpp:167-190, cv::imdecode)
  * followed by CVMatToDatum's [channel][row][column] layout with OpenCV's channel order B, G, R (io.cpp:205-230).  Baseline and progressive
- * Huffman JPEG (host/jpeg_decode.hpp).  chw[0..2] = channels, height, width; `out` may be NULL to learn the shape. */
+ * Huffman JPEG and non-interlaced 8-bit PNG, picked by the file's signature (host/jpeg_decode.hpp, png_decode.cpp).  chw[0..2] = channels, height, width; `out` may be NULL to learn the shape. */
 int b2h_jpeg_decode(const void* bytes, size_t n, int force_color, int* chw, unsigned char* out, size_t cap);
 /* ReadProtoFromBinaryFileOrDie(mean_file) + Blob::FromProto (src/caffe/data_transformer.cpp:21-30, src/caffe/blob.cpp:352-414):
  * shape gets up to 8 axes; call with data == NULL to learn the count first */

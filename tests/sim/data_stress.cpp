@@ -7,8 +7,8 @@
 //   4. DataReader: parser threads started, drained and destroyed at random points;
 //   5. the two parsers of files that come from outside -- prototxt text (models, solvers) and the .caffemodel / .solverstate wire
 //      format (model-zoo weights) -- on mutated inputs: FatalError or a parse, never a crash;
-//   6. the JPEG decoder on mutated copies of the files <scratch dir>/seed*.jpg (written by the test): flips in headers, tables and
-//      entropy-coded data, truncations.
+//   6. the JPEG and PNG decoders on mutated copies of the files <scratch dir>/seed*.jpg|png (written by the test): flips in headers,
+//      tables and entropy-coded / compressed data, truncations.
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -207,10 +207,11 @@ int main(int argc, char** argv) {
   if (!threads_only) {
     int decoded = 0, rejected = 0, files = 0;
     for (int f = 0; f < 8; ++f) {
-      const std::string jpg = slurp(dir + "/seed" + std::to_string(f) + ".jpg");
+      std::string jpg = slurp(dir + "/seed" + std::to_string(f) + ".jpg");
+      if (jpg.empty()) jpg = slurp(dir + "/seed" + std::to_string(f) + ".png");
       if (jpg.empty()) continue;
       ++files;
-      { DecodedImage img; DecodeJpeg(jpg.data(), jpg.size(), false, &img); REQUIRE(img.channels >= 1 && img.height > 0 && img.width > 0); }
+      { DecodedImage img; DecodeImage(jpg.data(), jpg.size(), false, &img); REQUIRE(img.channels >= 1 && img.height > 0 && img.width > 0); }
       for (int trial = 0; trial < 1200; ++trial) {
         std::string m = jpg;
         if (rnd(6) == 0) m.resize(rnd((unsigned)m.size() + 1));
@@ -219,7 +220,7 @@ int main(int argc, char** argv) {
           const size_t at = rnd(3) ? rnd((unsigned)std::min<size_t>(m.size(), 700)) : rnd((unsigned)m.size());   // headers and tables first
           m[at] = (char)rnd(256);
         }
-        try { DecodedImage img; DecodeJpeg(m.data(), m.size(), rnd(2) != 0, &img); ++decoded; } catch (const FatalError&) { ++rejected; }
+        try { DecodedImage img; DecodeImage(m.data(), m.size(), rnd(2) != 0, &img); ++decoded; } catch (const FatalError&) { ++rejected; }
       }
     }
     if (files) REQUIRE(decoded > 0 && rejected > 0);

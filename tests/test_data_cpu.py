@@ -287,7 +287,7 @@ def test_reader_refuses_what_it_cannot_feed(tmp_path):
     img = np.zeros((3, 4, 4), np.uint8)
     enc = str(tmp_path / "enc")
     lmdb_io.write_lmdb(enc, [(lmdb_io.caffe_key(0), lmdb_io.datum_bytes(img, 1, encoded=True))])
-    with pytest.raises(data_api.DataError, match="encoded datum is not a JPEG file"):
+    with pytest.raises(data_api.DataError, match="neither a JPEG nor a PNG"):
         data_api.DataReader(enc, 2)                               # `encoded` set, but the bytes are no image file
     mixed = str(tmp_path / "mixed")
     lmdb_io.write_lmdb(mixed, [(lmdb_io.caffe_key(0), lmdb_io.datum_bytes(img, 1)), (lmdb_io.caffe_key(1), lmdb_io.datum_bytes(np.zeros((3, 5, 4), np.uint8), 1))])

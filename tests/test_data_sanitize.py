@@ -34,6 +34,9 @@ def test_data_pipeline_host_code_is_clean_under_sanitizers(tmp_path, seed):
         (tmp_path / "seed3.jpg").write_bytes(enc.tobytes())
         ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 60])
         (tmp_path / "seed4.jpg").write_bytes(enc.tobytes())              # progressive: refinement scans on damaged input
+        for k, im in ((5, img), (6, img[:, :, 0])):                       # PNG: inflate + unfilter on damaged input (CRC / Adler mostly refuse)
+            ok, enc = cv2.imencode(".png", im, [cv2.IMWRITE_PNG_COMPRESSION, 3 * (k - 5)])
+            (tmp_path / ("seed%d.png" % k)).write_bytes(enc.tobytes())
     except ImportError:
         pass
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")

@@ -1,4 +1,4 @@
-"""Encoded datums (convert_imageset --encoded): host/jpeg_decode.cpp against this image's cv2.imdecode -- OpenCV on libjpeg-turbo,
+"""Encoded datums (convert_imageset --encoded): host/jpeg_decode.cpp and host/png_decode.cpp against this image's cv2.imdecode -- OpenCV on libjpeg-turbo,
 i.e. what the reference's DecodeDatumToCVMat[Native] (src/caffe/util/io.cpp:167-190) calls.  Bit-exact, over sampling modes
 4:4:4 / 4:2:2 / 4:2:0, qualities 10..100, restart intervals, optimised Huffman tables, grayscale files, force_color, odd sizes
 down to 1x1, progressive files, and files written by a second encoder (PIL); then a database of encoded datums through DataReader."""
@@ -94,6 +94,36 @@ def test_progressive_files_are_bit_identical_too():
             params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 5))]
         ok, enc = cv2.imencode(".jpg", _img(rng, h, w), params)
         assert ok and _same(enc.tobytes()), ("cv2 progressive", h, w, params)
+
+
+def test_png_files_decode_to_what_imdecode_returns():
+    """--encode_type png: lossless, so the only question is OpenCV's layouts -- gray -> 1 channel, RGB -> B,G,R, RGBA and gray+alpha
+    -> B,G,R,A, palette -> B,G,R (IMREAD_UNCHANGED); always B,G,R with force_color (IMREAD_COLOR) -- over every zlib compression
+    level (stored, fixed and dynamic Huffman blocks), all five scanline filters, sub-byte palettes, sizes down to 1x1."""
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(31)
+    for t in range(40):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        for c in (1, 3, 4):
+            ok, enc = cv2.imencode(".png", _img(rng, h, w, c), [cv2.IMWRITE_PNG_COMPRESSION, int(rng.integers(0, 10))])
+            assert ok and _same(enc.tobytes()) and _same(enc.tobytes(), cv2.IMREAD_COLOR, force=True), ("cv2 png", h, w, c)
+        pil = PIL.fromarray(_img(rng, h, w))
+        b = io.BytesIO()
+        pil.convert("P", palette=PIL.ADAPTIVE, colors=int(rng.choice([2, 4, 16, 200]))).save(b, "PNG", optimize=bool(t % 2))
+        assert _same(b.getvalue()) and _same(b.getvalue(), cv2.IMREAD_COLOR, force=True), ("palette", h, w)
+        b = io.BytesIO()
+        PIL.fromarray(_img(rng, h, w, 2), "LA").save(b, "PNG")
+        assert _same(b.getvalue()) and _same(b.getvalue(), cv2.IMREAD_COLOR, force=True), ("gray+alpha", h, w)
+        b = io.BytesIO()
+        pil.save(b, "PNG", compress_level=0)
+        assert _same(b.getvalue()), ("stored blocks", h, w)
+    ok, enc = cv2.imencode(".png", _img(rng, 20, 20))
+    enc = bytearray(enc.tobytes())
+    enc[60] ^= 0x10                                                            # one flipped bit in IDAT: the chunk CRC catches it
+    with pytest.raises(data_api.DataError, match="CRC|PNG"):
+        data_api.jpeg_decode(bytes(enc))
+    with pytest.raises(data_api.DataError, match="neither a JPEG nor a PNG"):
+        data_api.jpeg_decode(b"GIF89a" + bytes(40))
 
 
 def test_database_of_encoded_datums_feeds_the_reader(tmp_path):
