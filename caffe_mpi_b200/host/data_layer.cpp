@@ -33,10 +33,13 @@ void DataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& top) {
   B2_CHECK(top.size() == 1 || top.size() == 2, "Data layer produces data, or data and label");
   B2_CHECK(L_.batch_size > 0, "Data layer needs a positive batch_size");
   N_ = L_.batch_size;
-  PeekDatumShape(L_.data_source, &C_, &Hd_, &Wd_, L_.force_encoded_color);                       // data_layer.cpp:176-183: shape from one datum
+  bool encoded = false;
+  PeekDatumShape(L_.data_source, &C_, &Hd_, &Wd_, L_.force_encoded_color, &encoded);             // data_layer.cpp:176-183: shape from one datum
   crop_h_ = L_.crop_size > 0 ? L_.crop_size : Hd_;
   crop_w_ = L_.crop_size > 0 ? L_.crop_size : Wd_;
   B2_CHECK(Hd_ >= crop_h_ && Wd_ >= crop_w_, "crop_size larger than the datum");   // data_transformer.cpp:192-193
+  host_crop_ = encoded && L_.crop_size > 0 && L_.mean_file.empty();
+  if (host_crop_) Hd_ = Wd_ = L_.crop_size;                                        // the slots hold crop windows
   top[0]->Reshape({N_, C_, crop_h_, crop_w_});
   if (top.size() > 1) top[1]->Reshape({N_});
   u8_bytes_ = (size_t)N_ * C_ * Hd_ * Wd_;
@@ -94,13 +97,24 @@ void DataLayer::EnsureStarted() {
   p.solver_rank = (size_t)solver_rank_;
   p.parser_threads = (size_t)std::max(1, L_.parser_threads);
   p.force_encoded_color = L_.force_encoded_color;
+  p.host_crop = host_crop_ ? L_.crop_size : 0;
   reader_.reset(new DataReader(p));
   B2_CHECK(reader_->channels() == C_ && reader_->height() == Hd_ && reader_->width() == Wd_, "database changed shape between set-up and start");
   // random_seed >= 0: "Use random_seed setting for deterministic transformations" (data_transformer.cpp:733-736); otherwise every
   // solver gets its own stream (the reference: Caffe::next_seed() of a solver seeded with seed + rank, parallel.cpp:179-187)
   const uint64_t s = L_.transform_random_seed >= 0 ? (uint64_t)L_.transform_random_seed : seed_ + 0x9E3779B9ull * (uint64_t)(solver_rank_ + 1);
   draws_.reset(new TransformDraws(s, L_.mirror, L_.crop_size, /*train=*/true));
-  for (Slot& sl : slot_) reader_->free_push(&sl.buf);   // slot k assembles batch k, k + K, k + 2K, ...
+  for (int s = 0; s < (int)slot_.size(); ++s) HandToReader(s);   // slot k assembles batch k, k + K, k + 2K, ...
+}
+
+void DataLayer::HandToReader(int s) {
+  Slot& sl = slot_[s];
+  if (host_crop_) {                                      // Fill3Randoms per item, in batch order: the stream one transformer thread draws
+    sl.rand.resize((size_t)3 * N_);
+    for (int i = 0; i < N_; ++i) draws_->Fill3Randoms(sl.rand.data() + 3 * i);
+    sl.buf.rand = sl.rand.data();
+  }
+  reader_->free_push(&sl.buf);
 }
 
 void DataLayer::IssueCopy(int s) {
@@ -111,7 +125,11 @@ void DataLayer::IssueCopy(int s) {
   // crop / mirror draws in item order (one parser thread pops datums in record order, so pop order == item order;
   // data_layer.cpp:283-296).  host_off is free: LoadBatch waited for this slot's previous copy before handing the slot back.
   unsigned char* mir = reinterpret_cast<unsigned char*>(sl.host_off + 2 * N_);
-  for (int i = 0; i < N_; ++i) draws_->Draw(Hd_, Wd_, sl.host_off + i, sl.host_off + N_ + i, mir + i);
+  if (host_crop_) {                                      // the windows are cut already; what is left for the device is the flip
+    for (int i = 0; i < N_; ++i) { sl.host_off[i] = sl.host_off[N_ + i] = 0; mir[i] = (L_.mirror && (sl.rand[3 * i] % 2)) ? 1 : 0; }
+  } else {
+    for (int i = 0; i < N_; ++i) draws_->Draw(Hd_, Wd_, sl.host_off + i, sl.host_off + N_ + i, mir + i);
+  }
   CUDA_CHECK(cudaMemcpyAsync(sl.dev_u8, sl.buf.data, u8_bytes_, cudaMemcpyHostToDevice, copy_stream_));
   CUDA_CHECK(cudaMemcpyAsync(sl.dev_off, sl.host_off, sizeof(int) * 3 * N_, cudaMemcpyHostToDevice, copy_stream_));
   CUDA_CHECK(cudaMemcpyAsync(sl.dev_label, sl.buf.label, sizeof(float) * N_, cudaMemcpyHostToDevice, copy_stream_));
@@ -135,7 +153,7 @@ void DataLayer::LoadBatch(const vector<Blob*>& top, cudaStream_t st) {
   CUDA_CHECK(cudaEventSynchronize(sl.copied));
   sl.in_flight = false;
   sl.used = true;
-  reader_->free_push(&sl.buf);
+  HandToReader(cur_);
   ++batches_;
   cur_ = (cur_ + 1) % (int)slot_.size();
   IssueCopy(cur_);                                       // the next batch crosses PCIe while this one is computed on

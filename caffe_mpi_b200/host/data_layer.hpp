@@ -45,6 +45,7 @@ class DataLayer : public LayerBase {
   struct Slot {
     BatchBuf buf;                 // pinned: data, label (and record ids)
     int* host_off = nullptr;      // pinned: h_off[N], w_off[N], mirror[N] (bytes)
+    vector<unsigned> rand;        // host-crop mode: Fill3Randoms' draws of the batch this slot is assembling (3 per item)
     unsigned char* dev_u8 = nullptr;
     int* dev_off = nullptr;
     float* dev_label = nullptr;
@@ -53,6 +54,11 @@ class DataLayer : public LayerBase {
   };
   void EnsureStarted();
   void IssueCopy(int s);
+  void HandToReader(int s);         // host-crop mode: draw the batch's randoms, then free_push the slot
+  // Encoded datums with a crop_size and no mean_file: the parser threads -- which decode anyway -- also cut the crop window, so the
+  // database may hold images of different sizes (original files) and only crop^2 bytes per image cross PCIe.  Raw datums keep the
+  // whole-datum path (one memcpy per datum, crop on the device); a mean_file is indexed in datum coordinates and needs it too.
+  bool host_crop_ = false;
   NetLayer L_;
   uint64_t seed_;
   int solver_count_ = 1, solver_rank_ = 0;

@@ -53,6 +53,10 @@ DataReader::DataReader(const DataReaderParam& p) : p_(p) {
     DecodedImage img;
     const uint8_t* px = nullptr;
     datum_pixels(d, p_.force_encoded_color, &img, &px, &c_, &h_, &w_);
+    if (p_.host_crop > 0) {
+      B2_CHECK(h_ >= p_.host_crop && w_ >= p_.host_crop, "crop_size larger than the datum");
+      h_ = w_ = p_.host_crop;                            // the batch holds windows
+    }
   }
   full_cycle_ = p_.parser_threads * (size_t)p_.batch_size * p_.solver_count * p_.node_count;
   for (size_t t = 0; t < p_.parser_threads; ++t) {
@@ -108,10 +112,22 @@ void DataReader::fill(db::LMDBCursor* cur, size_t rec_id, BatchBuf* b) {
     int c = 0, h = 0, w = 0;
     datum_pixels(d, p_.force_encoded_color, &img, &px, &c, &h, &w);
     B2_CHECK(c == c_, "Number of channels can't vary in the same batch");
-    B2_CHECK(h == h_, "Image height can't vary in the same batch (crop might help here)");   // data_layer.cpp:262-271; all
-    B2_CHECK(w == w_, "Image width can't vary in the same batch (crop might help here)");     // datums share the sample's shape
     const size_t item = (rec_id + j) % B;                              // data_layer.cpp:256
-    memcpy(b->data + item * bytes, px, bytes);
+    if (p_.host_crop > 0) {
+      // the window of DataTransformer::Transform (data_transformer.cpp:216-229), cut here so that datums of any size fit the batch
+      const int crop = p_.host_crop;
+      B2_CHECK(h >= crop && w >= crop, "crop_size larger than a datum of " + p_.source);        // data_transformer.cpp:192-193
+      B2_CHECK(b->rand != nullptr || !p_.train, "DataReader: host_crop needs the consumer's draws (BatchBuf::rand)");
+      const int h_off = p_.train ? (int)(b->rand[3 * item + 1] % (unsigned)(h - crop + 1)) : (h - crop) / 2;
+      const int w_off = p_.train ? (int)(b->rand[3 * item + 2] % (unsigned)(w - crop + 1)) : (w - crop) / 2;
+      uint8_t* dst = b->data + item * bytes;
+      for (int cc = 0; cc < c; ++cc)
+        for (int y = 0; y < crop; ++y) memcpy(dst + ((size_t)cc * crop + y) * crop, px + ((size_t)cc * h + h_off + y) * w + w_off, (size_t)crop);
+    } else {
+      B2_CHECK(h == h_, "Image height can't vary in the same batch (crop might help here)");   // data_layer.cpp:262-271; all
+      B2_CHECK(w == w_, "Image width can't vary in the same batch (crop might help here)");     // datums share the sample's shape
+      memcpy(b->data + item * bytes, px, bytes);
+    }
     b->label[item] = (float)d.label;
     if (b->record_id) b->record_id[item] = (uint32_t)(rec_id + j);
     step(cur);
@@ -162,7 +178,7 @@ bool UseDatabase(const std::string& source, int backend) {
   return true;
 }
 
-void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool force_encoded_color) {
+void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool force_encoded_color, bool* encoded) {
   db::LMDB env;
   env.Open(source, db::READ);
   std::unique_ptr<db::LMDBCursor> cur(env.NewCursor());
@@ -172,6 +188,7 @@ void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool forc
   DecodedImage img;
   const uint8_t* px = nullptr;
   datum_pixels(d, force_encoded_color, &img, &px, c, h, w);
+  if (encoded) *encoded = d.encoded;
 }
 
 // ------------------------------------------------------------------------------------------------ TransformDraws

@@ -44,6 +44,12 @@ struct DataReaderParam {
   size_t node_count = 1, node_rank = 0;         // Clusters::node_count() / node_rank()
   size_t parser_threads = 1;                    // DataParameter.parser_threads (0 = auto in the reference; 1 here)
   bool force_encoded_color = false;             // DataParameter.force_encoded_color: decode one-channel files to three channels
+  // > 0: the parser threads cut the crop_size x crop_size window out of every datum themselves, from the draws the consumer hands
+  // over with the buffer (BatchBuf::rand), and the batch holds only the windows.  This is what lets datums of DIFFERENT sizes share a
+  // batch -- the reference's "crop might help here" (data_layer.cpp:262-271), i.e. databases of original, un-resized image files --
+  // and it moves crop^2 instead of H x W bytes per image over PCIe.  0: whole datums, one size, cropped on the device.
+  int host_crop = 0;
+  bool train = true;                            // TRAIN: random window; TEST: the centre window (data_transformer.cpp:219-229)
 };
 
 // One batch under assembly / assembled.  `data` is [batch][C][H][W] uint8 in datum layout, `label` one float per item (the
@@ -52,6 +58,10 @@ struct BatchBuf {
   uint8_t* data = nullptr;
   float* label = nullptr;
   uint32_t* record_id = nullptr;    // may be null
+  // host_crop only: DataTransformer::Fill3Randoms' three draws per item (rand[3i + 1], rand[3i + 2] place the window), filled by the
+  // consumer in batch order before free_push -- the draws do not depend on the datum, so the stream is the one a single transformer
+  // thread would produce however many parser threads cut the windows
+  const unsigned* rand = nullptr;
   size_t batch_id = 0;              // k*P + t, set by the reader
 };
 
@@ -101,7 +111,7 @@ class DataReader {
 // (bench.py and the tests run the reference's prototxts on machines that do not hold ImageNet).
 bool UseDatabase(const std::string& source, int backend);
 // channels / height / width of the first datum (DataReader::sample()); an encoded first datum is decoded to learn them
-void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool force_encoded_color = false);
+void PeekDatumShape(const std::string& source, int* c, int* h, int* w, bool force_encoded_color = false, bool* encoded = nullptr);
 
 // DataTransformer's random draws (src/caffe/data_transformer.cpp:127-137 Fill3Randoms, :187,219-226 their use, :729-749
 // InitRand / Rand): per datum  rand0 = Rand() + 1 if mirror;  rand1 = Rand() + 1, rand2 = Rand() + 1 if TRAIN and crop_size;

@@ -292,3 +292,54 @@ def test_reference_TestReadCropTrainSequenceSeeded_and_Unseeded(sim, tmp_path, m
     a = _crop_sequence(L, path, 1, tp="crop_size: 1 mirror: true random_seed: 9")
     b = _crop_sequence(L, path, 2, tp="crop_size: 1 mirror: true random_seed: 9")
     assert np.array_equal(a, b)
+
+
+# ---- encoded datums of DIFFERENT sizes: the parser threads decode and cut the crop window ---------------------------------------------------------
+@pytest.mark.parametrize("P", [1, 3])
+def test_encoded_datums_of_varying_size_are_cropped_by_the_parser_threads(sim, tmp_path, monkeypatch, P):
+    """A database of original image files (convert_imageset --encoded without a resize): every datum has its own height and width,
+    which the reference allows as long as crop_size is set (data_layer.cpp:262-271, "crop might help here").  The parser threads decode
+    each file and cut the window DataTransformer::Transform would (h_off = rand1 % (H - crop + 1), data_transformer.cpp:219-226) from
+    the Fill3Randoms draws the layer makes in batch order; the device only flips.  Expected values: cv2.imdecode + those rules."""
+    cv2 = pytest.importorskip("cv2")
+    from test_data_cpu import _mt19937
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    L = sim
+    rng = np.random.default_rng(8)
+    n, B, crop, seed, steps = 11, 3, 12, 99, 6
+    files, labels = [], rng.integers(0, 10, n)
+    for i in range(n):
+        h, w = int(rng.integers(crop, 40)), int(rng.integers(crop, 40))
+        img = cv2.resize(rng.integers(0, 256, (5, 5, 3), dtype=np.uint8), (w, h), interpolation=cv2.INTER_CUBIC)
+        ok, enc = cv2.imencode(".jpg" if i % 3 else ".png", img, [cv2.IMWRITE_JPEG_QUALITY, 85] if i % 3 else [])
+        files.append(enc.tobytes())
+    path = str(tmp_path / "orig_db")
+    env = data_api.LMDB(path, "NEW")
+    for i, f in enumerate(files):
+        env.put(lmdb_io.caffe_key(i, "im%d" % i), data_api.datum_serialize(0, 0, 0, f, int(labels[i]), encoded=True))
+    env.commit()
+    env.close()
+    decoded = [cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_UNCHANGED).transpose(2, 0, 1) for f in files]
+    L.fakecuda_set_all_eager(0)
+    h = L.sim_create(NET.format(src=path, B=B, dp="parser_threads: %d" % P, tp="crop_size: %d mirror: true scale: 0.5 mean_value: 100 random_seed: %d" % (crop, seed)).encode(),
+                     7, 1, 0)
+    assert h, L.sim_last_error().decode()
+    shp = (C.c_int * 4)()
+    L.sim_shape(h, shp)
+    assert tuple(shp) == (B, 3, crop, crop)
+    raw = _mt19937(seed, 3 * B * (steps + P + 2)).tolist()                     # three draws per item, batch after batch
+    want_batches = oracle_batches(n, steps, B, 1, 0, P)
+    got, lab = np.empty((B, 3, crop, crop), np.float32), np.empty(B, np.float32)
+    for i in range(steps):
+        assert L.sim_load_batch(h) == 0, L.sim_last_error().decode()
+        assert L.sim_read(h, got.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p)) == 0
+        for j, (pos, _) in enumerate(want_batches[i]):
+            r0, r1, r2 = ((raw[3 * (B * i + j) + k] + 1) & 0xFFFFFFFF for k in range(3))
+            img = decoded[pos]
+            ho, wo = r1 % (img.shape[1] - crop + 1), r2 % (img.shape[2] - crop + 1)
+            win = (img[:, ho:ho + crop, wo:wo + crop].astype(np.float32) - np.float32(100.0)) * np.float32(0.5)
+            if r0 % 2:
+                win = win[:, :, ::-1]
+            assert np.array_equal(got[j], win), (i, j, pos)
+            assert lab[j] == labels[pos]
+    L.sim_destroy(h)
