@@ -574,3 +574,56 @@ def test_graph_switches_leave_the_arithmetic_alone_on_the_cpu(sim_host, rng, mon
     assert abs(t.loss() - ref_losses[2]) <= 2e-4 * abs(ref_losses[2])
     for i, p in enumerate(ref_params):
         assert rel(t.get_param(i, 0), p) <= 2e-4, (switches, i)
+
+
+# ---- the command-line shell, end to end --------------------------------------------------------------------------------------------------------------
+def test_caffe_train_cli_runs_a_solver_file_end_to_end_on_the_cpu(sim_host, tmp_path, monkeypatch, capsys):
+    """tools/caffe.py train --solver=... on the simulator: the reference's workflow -- solver.prototxt naming a train_val.prototxt whose Data
+    layer reads an LMDB -- with the solver file's display / snapshot / snapshot_prefix honoured, then `--snapshot` resuming to max_iter and
+    `--weights` fine-tuning (tools/caffe.cpp:154-241, solver.cpp:277-345)."""
+    import argparse
+    import importlib.util
+    from caffe_mpi_b200 import lmdb_io
+    monkeypatch.delenv("B2C_DATA", raising=False)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    L = sim_host.lib()
+    for fn, at in (("sim_use_rank_stream", [C.c_int]), ("fakecuda_set_all_eager", [C.c_int]), ("sim_set_solver_count", [C.c_int])):
+        getattr(L, fn).argtypes = at
+    L.sim_use_rank_stream(-1)
+    L.sim_set_solver_count(1)
+    L.fakecuda_set_all_eager(0)
+    rng = np.random.default_rng(1)
+    db = str(tmp_path / "train_lmdb")
+    lmdb_io.write_datum_lmdb(db, rng.integers(0, 256, (20, 3, 7, 7), dtype=np.uint8), rng.integers(0, 10, 20))
+    net = tmp_path / "train_val.prototxt"
+    net.write_text(DB_NET.format(src=db, B=4, dp="", tp="scale: 0.0078125 mirror: true"))
+    solver = tmp_path / "solver.prototxt"
+    solver.write_text('net: "%s"\nbase_lr: 0.05 lr_policy: "step" stepsize: 4 gamma: 0.5 momentum: 0.9 weight_decay: 0.0005\n'
+                      'display: 3 max_iter: 10 snapshot: 4 snapshot_prefix: "%s" snapshot_after_train: true random_seed: 5 solver_mode: GPU\n'
+                      % (net, tmp_path / "snap"))
+    spec = importlib.util.spec_from_file_location("caffe_cli_sim", os.path.join(os.path.dirname(HERE), "tools", "caffe.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    base = dict(command="train", solver=str(solver), model="", iterations=0, batch=0, classes=10, display=0, seed=-1, snapshot="", weights="",
+                snapshot_prefix="")
+    cli.cmd_train(argparse.Namespace(**base))
+    out = capsys.readouterr().out
+    assert "reading the LMDB named by data_param.source" in out and "Optimization Done." in out
+    for it in (3, 6, 9, 10):
+        assert "Iteration %d (" % it in out
+    for it in (4, 8, 10):                                     # iter % snapshot == 0, and the one after training
+        assert os.path.exists(str(tmp_path / ("snap_iter_%d.solverstate" % it))) and os.path.exists(str(tmp_path / ("snap_iter_%d.caffemodel" % it)))
+    assert not os.path.exists(str(tmp_path / "snap_iter_6.solverstate"))
+    # resume from iteration 4: runs on to max_iter
+    for f in ("snap_iter_8", "snap_iter_10"):
+        for ext in (".solverstate", ".caffemodel"):
+            os.remove(str(tmp_path / (f + ext)))
+    cli.cmd_train(argparse.Namespace(**dict(base, snapshot=str(tmp_path / "snap_iter_4.solverstate"))))
+    out = capsys.readouterr().out
+    assert "Resuming from" in out and "at iteration 4" in out and "Iteration 10 (" in out and "Iteration 3 (" not in out
+    assert os.path.exists(str(tmp_path / "snap_iter_8.solverstate")) and os.path.exists(str(tmp_path / "snap_iter_10.caffemodel"))
+    # fine-tune from the trained weights for two iterations
+    cli.cmd_train(argparse.Namespace(**dict(base, weights=str(tmp_path / "snap_iter_10.caffemodel"), iterations=2, snapshot_prefix=str(tmp_path / "ft"))))
+    out = capsys.readouterr().out
+    assert "Finetuning from" in out and "layers copied" in out and os.path.exists(str(tmp_path / "ft_iter_2.caffemodel"))

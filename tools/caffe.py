@@ -126,7 +126,7 @@ def cmd_train(args):
     if hasattr(signal, "SIGHUP"):
         signal.signal(signal.SIGHUP, lambda *_: got.__setitem__("snapshot", True))
     for n, it, show, snap in schedule(t.iter(), end, display, snap_every):
-        ms = t.timed_steps(n, copy_input=True)
+        ms = max(t.timed_steps(n, copy_input=True), 1e-6)
         assert t.iter() == it
         if got["snapshot"] and rank == 0 and snap_prefix:
             log("Snapshotting solver state to binary proto file %s" % t.snapshot(snap_prefix))
