@@ -627,3 +627,8 @@ def test_caffe_train_cli_runs_a_solver_file_end_to_end_on_the_cpu(sim_host, tmp_
     cli.cmd_train(argparse.Namespace(**dict(base, weights=str(tmp_path / "snap_iter_10.caffemodel"), iterations=2, snapshot_prefix=str(tmp_path / "ft"))))
     out = capsys.readouterr().out
     assert "Finetuning from" in out and "layers copied" in out and os.path.exists(str(tmp_path / "ft_iter_2.caffemodel"))
+    # `caffe time`: the per-layer table from the CUDA-event profile, then the un-instrumented step
+    cli.cmd_time(argparse.Namespace(**dict(base, command="time", solver="", model=str(net), iterations=4)))
+    out = capsys.readouterr().out
+    assert "*** Benchmark begins ***" in out and "Average time per layer: " in out and "*** Benchmark ends ***" in out
+    assert "        ip\tforward: " in out and "      loss\tbackward: " in out and "Average Forward-Backward-Update: " in out
