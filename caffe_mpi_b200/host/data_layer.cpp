@@ -2,6 +2,7 @@
 #include "data_layer.hpp"
 
 #include <algorithm>
+#include <cstdio>
 
 #include "proto_wire.hpp"
 
@@ -62,6 +63,10 @@ void DataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& top) {
     CUDA_CHECK(cudaMemcpy(dev_mean_values_, mv.data(), sizeof(float) * C_, cudaMemcpyHostToDevice));
   }
 
+  if (L_.data_cache || L_.data_shuffle)
+    fprintf(stderr, "DataLayer '%s': data_param { cache: %s shuffle: %s } -- the database is a read-only mapping of the page cache, "
+                    "so `cache` has nothing to add; `shuffle` is not built: records are read in key order (shuffle when converting)\n",
+            L_.param.name.c_str(), L_.data_cache ? "true" : "false", L_.data_shuffle ? "true" : "false");
   const int K = std::max(2, std::max(1, L_.parser_threads) + 1);
   slot_.resize(K);
   CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));

@@ -247,6 +247,8 @@ Net::Net(const PMessage& np, Phase phase, int batch_override, int default_channe
         L.data_backend = (be == "LMDB" || be == "1") ? 1 : 0;
         L.parser_threads = (int)dp->integer("parser_threads", 0);
         L.force_encoded_color = dp->boolean("force_encoded_color", false);
+        L.data_cache = dp->boolean("cache", false);
+        L.data_shuffle = dp->boolean("shuffle", false);
         if (tp) { L.mean_file = tp->str("mean_file"); L.transform_random_seed = tp->integer("random_seed", -1); }
         // DataLayerSetUp reads one datum to size the top blob (data_layer.cpp:176-183); so does this, when the database is there
         L.use_database = UseDatabase(L.data_source, L.data_backend);

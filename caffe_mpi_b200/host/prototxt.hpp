@@ -71,6 +71,7 @@ struct NetLayer {                       // one LayerParameter after phase filter
   int data_backend = 0;                 // DataParameter.DB: LEVELDB = 0 (the proto's default), LMDB = 1
   int parser_threads = 0;               // 0 = automatic in the reference; one parser thread here
   bool force_encoded_color = false;     // DataParameter.force_encoded_color
+  bool data_cache = false, data_shuffle = false;   // DataParameter.cache / shuffle (accepted; see DataLayer::LayerSetUp)
   long long transform_random_seed = -1; // TransformationParameter.random_seed
   bool use_database = false;            // the source opened: this layer reads it (else the synthetic in-memory source stands in)
   std::vector<int> input_shape;         // Input / DummyData layers
