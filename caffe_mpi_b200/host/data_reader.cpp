@@ -1,6 +1,8 @@
 // data_reader.cpp -- see data_reader.hpp.
 #include "data_reader.hpp"
 
+#include <sys/stat.h>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -173,7 +175,15 @@ bool UseDatabase(const std::string& source, int backend) {
   if (mode == "synthetic" || source.empty() || source == "synthetic") return false;   // "synthetic": the name caffe_mpi_b200/models.py gives its stand-in source
   const bool there = db::LMDB::Exists(source);
   if (mode == "db") B2_CHECK(there, "Failed to open lmdb " + source + ": no data.mdb (B2C_DATA=db)");
-  if (!there) return false;
+  if (!there) {
+    // a directory that is there but holds no data.mdb is a LevelDB or a wrong path: training on the synthetic stand-in instead would be
+    // a silent surprise.  (A source that does not exist at all is the benchmark / test case: the reference's prototxts on a machine
+    // without ImageNet.)
+    struct stat st;
+    B2_CHECK(!(stat(source.c_str(), &st) == 0 && S_ISDIR(st.st_mode)),
+             "Data layer source " + source + " exists but holds no data.mdb (LevelDB databases are not built; B2C_DATA=synthetic ignores the source)");
+    return false;
+  }
   B2_CHECK(backend == 1, "Data layer source " + source + " exists but its backend is LEVELDB: only `backend: LMDB` is built");
   return true;
 }

@@ -370,6 +370,9 @@ def test_net_sizes_the_data_top_from_the_first_datum(tmp_path, monkeypatch):
     with pytest.raises(host_api.HostError, match="Failed to open lmdb"):
         host_api.Net(proto % (str(tmp_path / "absent"), ""), is_text=True)
     monkeypatch.delenv("B2C_DATA")
+    (tmp_path / "a_leveldb").mkdir()                             # there, but no data.mdb inside: not silently replaced by synthetic data
+    with pytest.raises(host_api.HostError, match="holds no data.mdb"):
+        host_api.Net(proto % (str(tmp_path / "a_leveldb"), ""), is_text=True)
     with pytest.raises(host_api.HostError, match="LEVELDB"):
         host_api.Net(proto.replace("backend: LMDB ", "") % (path, ""), is_text=True)
 
