@@ -613,7 +613,9 @@ P2PSync::~P2PSync() {
   if (comm_stream_) cudaStreamDestroy(comm_stream_);
 }
 void P2PSync::on_start(ParamArena& arena) {
-  // the reference broadcasts blob by blob; the arena makes it one call
+  // the reference broadcasts blob by blob; the arena makes it one call.  The comm stream knows nothing of the compute stream yet (the
+  // per-iteration events come later): whatever filled or uploaded the parameters there must have landed before they travel.
+  CUDA_CHECK(cudaStreamSynchronize(Caffe::thread_stream()));
   B2C_CHECK(b2c_comm_bcast(comm_, arena.data(), arena.total(), 0, comm_stream_));
   CUDA_CHECK(cudaStreamSynchronize(comm_stream_));
   if (arena.diff_is_nccl_memory()) {
