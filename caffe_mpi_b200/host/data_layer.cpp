@@ -67,7 +67,8 @@ void DataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& top) {
     fprintf(stderr, "DataLayer '%s': data_param { cache: %s shuffle: %s } -- the database is a read-only mapping of the page cache, "
                     "so `cache` has nothing to add; `shuffle` is not built: records are read in key order (shuffle when converting)\n",
             L_.param.name.c_str(), L_.data_cache ? "true" : "false", L_.data_shuffle ? "true" : "false");
-  const int K = std::max(2, std::max(1, L_.parser_threads) + 1);
+  parsers_ = L_.parser_threads > 0 ? L_.parser_threads : (encoded ? 4 : 1);
+  const int K = std::max(2, parsers_ + 1);
   slot_.resize(K);
   CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
   for (Slot& sl : slot_) {
@@ -100,7 +101,7 @@ void DataLayer::EnsureStarted() {
   p.batch_size = N_;
   p.solver_count = (size_t)solver_count_;
   p.solver_rank = (size_t)solver_rank_;
-  p.parser_threads = (size_t)std::max(1, L_.parser_threads);
+  p.parser_threads = (size_t)parsers_;
   p.force_encoded_color = L_.force_encoded_color;
   p.host_crop = host_crop_ ? L_.crop_size : 0;
   reader_.reset(new DataReader(p));

@@ -59,6 +59,9 @@ class DataLayer : public LayerBase {
   // database may hold images of different sizes (original files) and only crop^2 bytes per image cross PCIe.  Raw datums keep the
   // whole-datum path (one memcpy per datum, crop on the device); a mean_file is indexed in datum coordinates and needs it too.
   bool host_crop_ = false;
+  // DataParameter.parser_threads; 0 ("Caffe optimizes it automatically", caffe.proto:841-844; the reference's auto mode ends between 1
+  // and 4, data_layer.cpp:85-95) becomes 1 for raw datums -- one thread's memcpy outruns the GPU -- and 4 for encoded ones
+  int parsers_ = 1;
   NetLayer L_;
   uint64_t seed_;
   int solver_count_ = 1, solver_rank_ = 0;
