@@ -67,7 +67,7 @@ void DataLayer::LayerSetUp(const vector<Blob*>&, const vector<Blob*>& top) {
     fprintf(stderr, "DataLayer '%s': data_param { cache: %s shuffle: %s } -- the database is a read-only mapping of the page cache, "
                     "so `cache` has nothing to add; `shuffle` is not built: records are read in key order (shuffle when converting)\n",
             L_.param.name.c_str(), L_.data_cache ? "true" : "false", L_.data_shuffle ? "true" : "false");
-  parsers_ = L_.parser_threads > 0 ? L_.parser_threads : (encoded ? 4 : 1);
+  parsers_ = L_.parser_threads > 0 ? L_.parser_threads : (encoded ? 6 : 1);
   const int K = std::max(2, parsers_ + 1);
   slot_.resize(K);
   CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
