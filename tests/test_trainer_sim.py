@@ -653,3 +653,26 @@ def test_the_gpu_data_layer_tests_hold_on_the_simulator(sim_host, tmp_path, monk
             d.mkdir()
             test(d, monkeypatch)
     L.fakecuda_set_all_eager(0)
+
+
+def test_the_gpu_trainer_tests_hold_on_the_simulator(sim_host, rng, tmp_path):
+    """tests/test_trainer_gpu.py's whole-net tests, verbatim, against the host layer on the stream-order model: forward / backward vs the
+    net oracle (fused and unfused, with and without conv bias), LeNet, SGD steps, the snapshot / restore round trip with real updates
+    in between (bitwise), the fusion pass being bitwise neutral, the inception-style net.  (Not the TF32 and full ResNet-50 cases:
+    those are about the device.)"""
+    import test_trainer_gpu as g
+    L = sim_host.lib()
+    for fn, at in (("sim_use_rank_stream", [C.c_int]), ("fakecuda_set_all_eager", [C.c_int]), ("sim_set_solver_count", [C.c_int])):
+        getattr(L, fn).argtypes = at
+    L.sim_use_rank_stream(-1)
+    L.sim_set_solver_count(1)
+    L.fakecuda_set_all_eager(0)
+    fresh = lambda: np.random.default_rng(1701)
+    for conv_bias in (False, True):
+        for fuse in (False, True):
+            g.test_forward_backward_matches_oracle(fresh(), conv_bias, fuse)
+    g.test_lenet_matches_oracle(fresh())
+    g.test_sgd_steps_match_oracle(fresh())
+    g.test_snapshot_restore_roundtrip_on_device(fresh(), tmp_path)
+    g.test_fusion_pass_is_bitwise_neutral(fresh())
+    g.test_inception_style_net_matches_oracle(fresh())
