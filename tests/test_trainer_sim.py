@@ -676,3 +676,24 @@ def test_the_gpu_trainer_tests_hold_on_the_simulator(sim_host, rng, tmp_path):
     g.test_snapshot_restore_roundtrip_on_device(fresh(), tmp_path)
     g.test_fusion_pass_is_bitwise_neutral(fresh())
     g.test_inception_style_net_matches_oracle(fresh())
+
+
+def test_the_gpu_host_layer_tests_hold_on_the_simulator(sim_host):
+    """tests/test_host_gpu.py, verbatim where the host stand-ins reach: caffe::ConvolutionLayer through LayerRegistry (DEFAULT engine)
+    over the reference's test shapes, the edge cases and five model layers -- SetUp's output shape, blob creation, the accumulate /
+    overwrite conventions across repeated Backward calls -- and SGDSolver + ReduceScheduler over four iterations for three learning-
+    rate policies on an arena with odd-sized, even-padded slots.  (The CAFFE engine and the N-D path need the real im2col kernels.)"""
+    import test_host_gpu as g
+    L = sim_host.lib()
+    for fn, at in (("sim_use_rank_stream", [C.c_int]), ("fakecuda_set_all_eager", [C.c_int]), ("sim_set_solver_count", [C.c_int])):
+        getattr(L, fn).argtypes = at
+    L.sim_use_rank_stream(-1)
+    L.sim_set_solver_count(1)
+    L.fakecuda_set_all_eager(0)
+    for name, case in g.SOME:
+        g.test_convolution_layer_forward_backward(np.random.default_rng(1701), name, case, capi.ENGINE_DEFAULT)
+    for policy in (dict(lr_policy="fixed"), dict(lr_policy="poly", power=2.0, max_iter=100), dict(lr_policy="step", gamma=0.5, stepsize=2)):
+        for eager in (0, 1):
+            L.fakecuda_set_all_eager(eager)
+            g.test_sgd_solver_iterations_match_oracle(np.random.default_rng(1701), policy)
+    L.fakecuda_set_all_eager(0)
