@@ -99,3 +99,16 @@ int b2c_sgd_update_arena(int nseg, const size_t* offset, const size_t* count, co
 }
 
 }  // extern "C"
+
+// y = alpha * op(A) * x + beta * y, A row-major M x N (caffe_gpu_gemv, math_functions.cu:73-82)
+extern "C" int b2c_sgemv(int tA, int M, int N, float alpha, const float* A, const float* x, float beta, float* y, void* stream) {
+  fakecuda_launch(S(stream), [=] {
+    const int rows = tA ? N : M, cols = tA ? M : N;
+    for (int i = 0; i < rows; ++i) {
+      double acc = 0;
+      for (int j = 0; j < cols; ++j) acc += (double)(tA ? A[(size_t)j * N + i] : A[(size_t)i * N + j]) * x[j];
+      y[i] = (float)(alpha * acc + (beta == 0.f ? 0.0 : (double)beta * y[i]));
+    }
+  });
+  return B2C_OK;
+}

@@ -7,6 +7,7 @@
 // tests/netoracle.py (tests/test_trainer_sim.py).  TEST INFRASTRUCTURE ONLY; the real kernels are checked on hardware.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -412,4 +413,53 @@ int b2c_accuracy(int N, int C, int top_k, const float* scores, const float* labe
   return B2C_OK;
 }
 
+}  // extern "C"
+
+// ---- N-D im2col / col2im (im2col_nd_cpu / col2im_nd_cpu, src/caffe/util/im2col.cpp:76-174): the host layer's N-D convolution path calls
+// these directly (b2caffe.cpp), per image, around b2c_sgemm.  Shape arrays are HOST arrays: im_shape [C, d0..], col_shape [C*prod(k), o0..].
+namespace {
+void nd_core(bool to_col, const float* src, int num_axes, std::vector<int> ims, std::vector<int> cols, std::vector<int> k, std::vector<int> pad,
+             std::vector<int> stride, std::vector<int> dil, float* dst) {
+  size_t im_size = ims[0], kernel_size = 1, out_spatial = 1;
+  for (int i = 0; i < num_axes; ++i) { im_size *= (size_t)ims[1 + i]; kernel_size *= (size_t)k[i]; out_spatial *= (size_t)cols[1 + i]; }
+  const int channels_col = cols[0];
+  if (!to_col) for (size_t i = 0; i < im_size; ++i) dst[i] = 0.f;
+  std::vector<int> d_off(num_axes), d_iter(num_axes);
+  for (int c_col = 0; c_col < channels_col; ++c_col) {
+    int offset = c_col;                                           // which kernel tap this column row is
+    for (int d = num_axes - 1; d >= 0; --d) { if (d < num_axes - 1) offset /= k[d + 1]; d_off[d] = offset % k[d]; }
+    const int c_im = c_col / (int)kernel_size;
+    std::fill(d_iter.begin(), d_iter.end(), 0);
+    for (size_t o = 0; o < out_spatial; ++o) {
+      size_t idx_im = (size_t)c_im;
+      bool padded = false;
+      for (int d = 0; d < num_axes; ++d) {
+        const int pos = d_iter[d] * stride[d] - pad[d] + d_off[d] * dil[d];
+        padded |= pos < 0 || pos >= ims[1 + d];
+        idx_im = idx_im * (size_t)ims[1 + d] + (size_t)(pos < 0 ? 0 : pos);
+      }
+      const size_t idx_col = (size_t)c_col * out_spatial + o;
+      if (to_col) dst[idx_col] = padded ? 0.f : src[idx_im];
+      else if (!padded) dst[idx_im] += src[idx_col];
+      for (int d = num_axes - 1; d >= 0; --d) { if (++d_iter[d] < cols[1 + d]) break; d_iter[d] = 0; }
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+int b2c_im2col_nd(const float* im, int num_axes, const int* im_shape, const int* col_shape, const int* kernel, const int* pad, const int* stride,
+                  const int* dilation, float* col, void* stream) {
+  std::vector<int> a(im_shape, im_shape + num_axes + 1), b(col_shape, col_shape + num_axes + 1), k(kernel, kernel + num_axes), p(pad, pad + num_axes),
+      s(stride, stride + num_axes), d(dilation, dilation + num_axes);
+  fakecuda_launch(S(stream), [=] { nd_core(true, im, num_axes, a, b, k, p, s, d, col); });
+  return B2C_OK;
+}
+int b2c_col2im_nd(const float* col, int num_axes, const int* im_shape, const int* col_shape, const int* kernel, const int* pad, const int* stride,
+                  const int* dilation, float* im, void* stream) {
+  std::vector<int> a(im_shape, im_shape + num_axes + 1), b(col_shape, col_shape + num_axes + 1), k(kernel, kernel + num_axes), p(pad, pad + num_axes),
+      s(stride, stride + num_axes), d(dilation, dilation + num_axes);
+  fakecuda_launch(S(stream), [=] { nd_core(false, col, num_axes, a, b, k, p, s, d, im); });
+  return B2C_OK;
+}
 }  // extern "C"

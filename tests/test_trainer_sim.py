@@ -682,7 +682,7 @@ def test_the_gpu_host_layer_tests_hold_on_the_simulator(sim_host):
     """tests/test_host_gpu.py, verbatim where the host stand-ins reach: caffe::ConvolutionLayer through LayerRegistry (DEFAULT engine)
     over the reference's test shapes, the edge cases and five model layers -- SetUp's output shape, blob creation, the accumulate /
     overwrite conventions across repeated Backward calls -- and SGDSolver + ReduceScheduler over four iterations for three learning-
-    rate policies on an arena with odd-sized, even-padded slots.  (The CAFFE engine and the N-D path need the real im2col kernels.)"""
+    rate policies on an arena with odd-sized, even-padded slots.  The 3-D convolution of TestSimple3DConvolution runs through the host layer's N-D loop (im2col_nd + GEMM per image)."""
     import test_host_gpu as g
     L = sim_host.lib()
     for fn, at in (("sim_use_rank_stream", [C.c_int]), ("fakecuda_set_all_eager", [C.c_int]), ("sim_set_solver_count", [C.c_int])):
@@ -692,6 +692,7 @@ def test_the_gpu_host_layer_tests_hold_on_the_simulator(sim_host):
     L.fakecuda_set_all_eager(0)
     for name, case in g.SOME:
         g.test_convolution_layer_forward_backward(np.random.default_rng(1701), name, case, capi.ENGINE_DEFAULT)
+    g.test_3d_convolution_nd_path(np.random.default_rng(1701))       # three spatial axes: the host layer's own im2col_nd + GEMM + col2im_nd loop
     for policy in (dict(lr_policy="fixed"), dict(lr_policy="poly", power=2.0, max_iter=100), dict(lr_policy="step", gamma=0.5, stepsize=2)):
         for eager in (0, 1):
             L.fakecuda_set_all_eager(eager)
